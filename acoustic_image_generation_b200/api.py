@@ -1,0 +1,389 @@
+"""Host-side mirror of the reference's interface for the acoustic-image path.
+
+The reference exposes this path as Python callables on NumPy arrays.  The functions
+here keep those names, argument meanings and return conventions and run the
+arithmetic on a B200 through libaig.so (include/aig.h):
+
+    createfilters, get_feats                 dataloader/outdoor_data_mfcc.py:826-876
+    _normalize_acoustic_images_rescaled,
+    _map_func_acoustic_images                dataloader/outdoor_data_mfcc.py:657-679
+    find_logen                               iouenergythreshold.py:294-323
+    iou_sweep / ciou_sweep / auc             iouenergythreshold.py:213-236,
+                                             showimages_bb.py:287-328, areaundercurve.py:26-40
+
+Arrays may be NumPy arrays (host; results come back as NumPy) or CUDA tensors / anything
+exposing ``__cuda_array_interface__`` (device; results are torch CUDA tensors, nothing is
+copied to the host).  There is no CPU fallback: without libaig.so and a B200 every compute
+call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+
+import numpy as np
+
+from . import _lib, tables
+from ._lib import AigError
+
+FRAME_H, FRAME_W, FRAME_PIXELS, MFCC_NUM, FFT_LEN = 36, 48, 1728, 12, 512
+HEAT_H, HEAT_W = 224, 298                      # cv2.resize(map, (298, 224)), showimages.py:147
+REFERENCE_THRESHOLDS = (0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0)   # areaundercurve.py:27
+
+_TORCH_DTYPES = {}
+
+
+def _torch():
+    import torch
+    if not _TORCH_DTYPES:
+        _TORCH_DTYPES.update({np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+                              np.dtype(np.uint8): torch.uint8, np.dtype(np.int32): torch.int32,
+                              np.dtype(np.int64): torch.int64})
+    return torch
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith('torch') and hasattr(x, 'data_ptr')
+
+
+def _is_cuda_tensor(x):
+    return _is_torch(x) and x.is_cuda
+
+
+class _Arg:
+    """A caller buffer resolved to (pointer, keep-alive object)."""
+
+    __slots__ = ('ptr', 'keep', 'shape', 'on_device', 'torch_device')
+
+    def __init__(self, x, dtype, writable=False):
+        dtype = np.dtype(dtype)
+        self.torch_device = None
+        if _is_torch(x):
+            torch = _torch()
+            want = _TORCH_DTYPES[dtype]
+            if x.dtype != want or not x.is_contiguous():
+                if writable:
+                    raise ValueError('output tensor must be contiguous %s' % want)
+                x = x.to(want).contiguous()
+            self.ptr, self.keep, self.shape = x.data_ptr(), x, tuple(x.shape)
+            self.on_device = x.is_cuda
+            if x.is_cuda:
+                self.torch_device = x.device
+        elif hasattr(x, '__cuda_array_interface__'):
+            cai = x.__cuda_array_interface__
+            if np.dtype(cai['typestr']) != dtype or cai.get('strides'):
+                raise ValueError('device array must be contiguous %s' % dtype)
+            self.ptr, self.keep, self.shape, self.on_device = cai['data'][0], x, tuple(cai['shape']), True
+        else:
+            arr = np.asarray(x)
+            if writable:
+                if arr.dtype != dtype or not arr.flags.c_contiguous or not arr.flags.writeable:
+                    raise ValueError('output array must be a writable C-contiguous %s array' % dtype)
+            else:
+                arr = np.ascontiguousarray(arr, dtype=dtype)
+            self.ptr, self.keep, self.shape, self.on_device = arr.ctypes.data, arr, arr.shape, False
+
+
+class AcousticPath:
+    """One libaig handle: a CUDA device plus a stream.
+
+    ``stream=None`` uses the legacy default stream (ordered with torch's default stream);
+    pass ``torch.cuda.current_stream().cuda_stream`` to enqueue on a torch stream.  A handle is
+    not thread-safe; the module-level drop-ins below keep one per thread, like giving each of
+    the reference's four tf.data workers (outdoor_data_mfcc.py:82) its own.
+    """
+
+    def __init__(self, device=0, stream=None, tables_=None):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        self.device = int(device)
+        code = self._lib.aig_create(self.device, int(stream or 0), ctypes.byref(self._h))
+        if code != 0:
+            raise AigError(code, (self._lib.aig_last_error(None) or b'').decode())
+        self._tables_key = None
+        self.set_tables(*(tables_ if tables_ is not None else tables.reference_tables()))
+
+    # -- plumbing -----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self._lib.aig_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, code):
+        if code != 0:
+            raise AigError(code, (self._lib.aig_last_error(self._h) or b'').decode())
+
+    def synchronize(self):
+        self._check(self._lib.aig_synchronize(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.aig_launch_count(self._h))
+
+    def set_mfcc_variant(self, variant):
+        self._check(self._lib.aig_set_mfcc_variant(self._h, int(variant)))
+
+    def _empty(self, shape, dtype, like):
+        """Output buffer on the side the input lives on."""
+        if like.torch_device is not None or like.on_device:
+            torch = _torch()
+            dev = like.torch_device if like.torch_device is not None else torch.device('cuda', self.device)
+            return torch.empty(shape, dtype=_TORCH_DTYPES[np.dtype(dtype)], device=dev)
+        return np.empty(shape, dtype=dtype)
+
+    # -- tables -------------------------------------------------------------------------------
+    def set_tables(self, filter_mat, dct_base, lifter, mfnorm):
+        bank = np.ascontiguousarray(filter_mat, dtype=np.float64)
+        dct = np.ascontiguousarray(dct_base, dtype=np.float64)
+        lift = np.ascontiguousarray(lifter, dtype=np.float64)
+        if bank.ndim != 2 or dct.ndim != 2 or dct.shape[0] != bank.shape[1] or lift.shape != (dct.shape[1],):
+            raise ValueError('inconsistent table shapes %s %s %s' % (bank.shape, dct.shape, lift.shape))
+        key = (bank.shape, dct.shape, float(mfnorm), hash(bank.tobytes()), hash(dct.tobytes()), hash(lift.tobytes()))
+        if key == self._tables_key:
+            return
+        self._check(self._lib.aig_set_tables(self._h, bank.ctypes.data, bank.shape[0], bank.shape[1],
+                                             dct.ctypes.data, dct.shape[1], lift.ctypes.data, float(mfnorm)))
+        self._tables_key = key
+        self.fft_len, self.filter_num, self.mfcc_num = bank.shape[0], bank.shape[1], dct.shape[1]
+
+    @property
+    def tables_are_reference(self):
+        return self._lib.aig_tables_are_reference(self._h) == 1
+
+    # -- stage 1 ------------------------------------------------------------------------------
+    def mfcc_rows(self, beam, flip180=False, frame_pixels=FRAME_PIXELS, out=None):
+        """[n, fft_len] float32 power rows -> [n, mfcc_num] float32 (get_feats + np.float32)."""
+        a = _Arg(beam, np.float32)
+        n = int(np.prod(a.shape)) // self.fft_len
+        if n * self.fft_len != int(np.prod(a.shape)):
+            raise ValueError('beam has %s elements, not a multiple of fft_len=%d' % (a.shape, self.fft_len))
+        res = out if out is not None else self._empty((n, self.mfcc_num), np.float32, a)
+        o = _Arg(res, np.float32, writable=True)
+        if int(np.prod(o.shape)) != n * self.mfcc_num:
+            raise ValueError('out has shape %s, expected %d x %d values' % (o.shape, n, self.mfcc_num))
+        self._check(self._lib.aig_mfcc(self._h, a.ptr, n, o.ptr, int(bool(flip180)), int(frame_pixels)))
+        return res
+
+    def mfcc_image(self, power, flip=False):
+        """[N, 36, 48, 512] float32 -> [N, 36, 48, 12] float32 MFCC acoustic images; ``flip`` applies the
+        flip_left_right + flip_up_down of _parse_sequence (outdoor_data_mfcc.py:314-315)."""
+        a = _Arg(power, np.float32)
+        if len(a.shape) != 4 or a.shape[1:] != (FRAME_H, FRAME_W, FFT_LEN):
+            raise ValueError('expected [N, 36, 48, 512], got %s' % (a.shape,))
+        rows = self.mfcc_rows(a.keep, flip180=flip, frame_pixels=FRAME_PIXELS)
+        return rows.reshape(a.shape[0], FRAME_H, FRAME_W, MFCC_NUM)
+
+    # -- stage 2 ------------------------------------------------------------------------------
+    def normalize_images(self, images):
+        """Per-frame (x - min) / max(x - min) in float32 over [N, 36, 48, 12] (outdoor_data_mfcc.py:672-679)."""
+        a = _Arg(images, np.float32)
+        n = self._frames(a.shape, FRAME_PIXELS * MFCC_NUM)
+        res = self._empty(a.shape, np.float32, a)
+        self._check(self._lib.aig_normalize_images(self._h, a.ptr, n, _Arg(res, np.float32, True).ptr))
+        return res
+
+    @staticmethod
+    def _frames(shape, per_frame):
+        total = int(np.prod(shape))
+        if total % per_frame:
+            raise ValueError('shape %s is not a whole number of frames of %d values' % (shape, per_frame))
+        return total // per_frame
+
+    def energy(self, images, normalize_first=False, want_scaled=False, want_mean=False):
+        """find_logen + mean mask over a batch.  Returns (energy f64 [N,36,48], mask u8 [N,36,48][, scaled][, mean])."""
+        a = _Arg(images, np.float32)
+        n = self._frames(a.shape, FRAME_PIXELS * MFCC_NUM)
+        energy = self._empty((n, FRAME_H, FRAME_W), np.float64, a)
+        mask = self._empty((n, FRAME_H, FRAME_W), np.uint8, a)
+        scaled = self._empty((n, FRAME_H, FRAME_W, MFCC_NUM), np.float32, a) if want_scaled else None
+        mean = self._empty((n,), np.float64, a) if want_mean else None
+        self._check(self._lib.aig_energy(
+            self._h, a.ptr, n, int(bool(normalize_first)),
+            _Arg(scaled, np.float32, True).ptr if want_scaled else None,
+            _Arg(energy, np.float64, True).ptr, _Arg(mask, np.uint8, True).ptr,
+            _Arg(mean, np.float64, True).ptr if want_mean else None))
+        out = (energy, mask)
+        if want_scaled:
+            out += (scaled,)
+        if want_mean:
+            out += (mean,)
+        return out
+
+    def find_logen(self, mfcc, inplace=True):
+        """Drop-in for find_logen(mfcc) -> float64 [36, 48] (iouenergythreshold.py:294-323).
+
+        Like the reference, the caller's contiguous float32 array is left scaled by
+        1/lifter * mfnorm (``mfcc /= lifter; mfcc *= mfnorm`` act on a reshape view);
+        ``inplace=False`` suppresses that side effect."""
+        if isinstance(mfcc, np.ndarray) and mfcc.dtype == np.float32 and mfcc.flags.c_contiguous and inplace:
+            if mfcc.size != FRAME_PIXELS * MFCC_NUM:
+                raise ValueError('find_logen expects 36*48*12 values, got %d' % mfcc.size)
+            energy = np.empty((FRAME_H, FRAME_W), np.float64)
+            self._check(self._lib.aig_energy(self._h, mfcc.ctypes.data, 1, 0, mfcc.ctypes.data,
+                                             energy.ctypes.data, None, None))
+            return energy
+        if _is_cuda_tensor(mfcc) and inplace and mfcc.is_contiguous() and mfcc.dtype == _torch().float32:
+            energy = _torch().empty((FRAME_H, FRAME_W), dtype=_torch().float64, device=mfcc.device)
+            self._check(self._lib.aig_energy(self._h, mfcc.data_ptr(), 1, 0, mfcc.data_ptr(),
+                                             energy.data_ptr(), None, None))
+            return energy
+        energy, _ = self.energy(mfcc, normalize_first=False)
+        return energy.reshape(FRAME_H, FRAME_W)
+
+    def heatmap(self, energy, out_h=HEAT_H, out_w=HEAT_W):
+        """cv2.resize(map, (out_w, out_h)) + imshow's implicit min/max normalisation, float32 [N, out_h, out_w]."""
+        a = _Arg(energy, np.float64)
+        n = self._frames(a.shape, FRAME_PIXELS)
+        res = self._empty((n, out_h, out_w), np.float32, a)
+        self._check(self._lib.aig_heatmap(self._h, a.ptr, n, int(out_h), int(out_w), _Arg(res, np.float32, True).ptr))
+        return res
+
+    def resize_mask(self, mask, out_h=HEAT_H, out_w=HEAT_W):
+        """1.0 * (cv2.resize(mask * 1.0, (out_w, out_h)) > 0.5) as uint8 [N, out_h, out_w] (showimages_bb.py:303-304)."""
+        a = _Arg(mask, np.uint8)
+        n = self._frames(a.shape, FRAME_PIXELS)
+        res = self._empty((n, out_h, out_w), np.uint8, a)
+        self._check(self._lib.aig_resize_mask(self._h, a.ptr, n, int(out_h), int(out_w), _Arg(res, np.uint8, True).ptr))
+        return res
+
+    def mfcc_energy(self, power, flip=False, normalize_first=True, want_mean=False):
+        """Stages 1 + 2 chained on the device: [N,36,48,512] f32 -> (mfcc f32 [N,36,48,12], energy f64, mask u8)."""
+        a = _Arg(power, np.float32)
+        n = self._frames(a.shape, FRAME_PIXELS * FFT_LEN)
+        mfcc = self._empty((n, FRAME_H, FRAME_W, MFCC_NUM), np.float32, a)
+        energy = self._empty((n, FRAME_H, FRAME_W), np.float64, a)
+        mask = self._empty((n, FRAME_H, FRAME_W), np.uint8, a)
+        mean = self._empty((n,), np.float64, a) if want_mean else None
+        self._check(self._lib.aig_mfcc_energy(
+            self._h, a.ptr, n, int(bool(flip)), int(bool(normalize_first)), _Arg(mfcc, np.float32, True).ptr,
+            _Arg(energy, np.float64, True).ptr, _Arg(mask, np.uint8, True).ptr,
+            _Arg(mean, np.float64, True).ptr if want_mean else None))
+        return (mfcc, energy, mask) + ((mean,) if want_mean else ())
+
+    # -- stage 3 ------------------------------------------------------------------------------
+    def iou_sweep(self, mask_a, mask_b, thresholds=REFERENCE_THRESHOLDS, pos=None, num=None):
+        """Mask IoU and success counts (iouenergythreshold.py:224-229) for all thresholds at once.
+
+        Returns (inter int64 [n], union int64 [n], pos int64 [K], num int).  ``pos`` / ``num`` from a
+        previous call can be passed back in to accumulate across batches."""
+        a, b = _Arg(mask_a, np.uint8), _Arg(mask_b, np.uint8)
+        n = self._frames(a.shape, FRAME_PIXELS)
+        if self._frames(b.shape, FRAME_PIXELS) != n:
+            raise ValueError('mask batches differ: %s vs %s' % (a.shape, b.shape))
+        thr = np.ascontiguousarray(thresholds, dtype=np.float64)
+        pos = np.zeros(len(thr), np.int64) if pos is None else np.ascontiguousarray(pos, dtype=np.int64)
+        cnt = np.array([0 if num is None else int(num)], np.int64)
+        inter = self._empty((n,), np.int64, a)
+        union = self._empty((n,), np.int64, a)
+        self._check(self._lib.aig_iou_sweep(self._h, a.ptr, b.ptr, n, thr.ctypes.data, len(thr),
+                                            _Arg(inter, np.int64, True).ptr, _Arg(union, np.int64, True).ptr,
+                                            pos.ctypes.data, cnt.ctypes.data))
+        return inter, union, pos, int(cnt[0])
+
+    def ciou_sweep(self, mask, xmin, xmax, ymin, ymax, thresholds=REFERENCE_THRESHOLDS,
+                   out_hw=(HEAT_H, HEAT_W), pos=None, num=None):
+        """FlickrSoundNet consensus IoU and success counts (showimages_bb.py:288-321).
+
+        mask u8 [n, 36, 48]; boxes int32 [n, 3] each.  Returns (2*I int64 [n], 2*U int64 [n], pos, num)."""
+        a = _Arg(mask, np.uint8)
+        n = self._frames(a.shape, FRAME_PIXELS)
+        boxes = [_Arg(v, np.int32) for v in (xmin, xmax, ymin, ymax)]
+        for bx in boxes:
+            if int(np.prod(bx.shape)) != 3 * n:
+                raise ValueError('boxes must be [n, 3] int32, got %s for n=%d' % (bx.shape, n))
+        thr = np.ascontiguousarray(thresholds, dtype=np.float64)
+        pos = np.zeros(len(thr), np.int64) if pos is None else np.ascontiguousarray(pos, dtype=np.int64)
+        cnt = np.array([0 if num is None else int(num)], np.int64)
+        inter2 = self._empty((n,), np.int64, a)
+        union2 = self._empty((n,), np.int64, a)
+        self._check(self._lib.aig_ciou_sweep(self._h, a.ptr, boxes[0].ptr, boxes[1].ptr, boxes[2].ptr, boxes[3].ptr,
+                                             n, int(out_hw[0]), int(out_hw[1]), thr.ctypes.data, len(thr),
+                                             _Arg(inter2, np.int64, True).ptr, _Arg(union2, np.int64, True).ptr,
+                                             pos.ctypes.data, cnt.ctypes.data))
+        return inter2, union2, pos, int(cnt[0])
+
+
+def auc(thresholds, values):
+    """areaundercurve.py:32-37: sklearn.metrics.auc(threshold[::-1], value[::-1]) (trapezoid), float64."""
+    thr = np.ascontiguousarray(thresholds, dtype=np.float64)
+    val = np.ascontiguousarray(values, dtype=np.float64)
+    if thr.shape != val.shape or thr.ndim != 1:
+        raise ValueError('thresholds and values must be equal-length vectors')
+    out = ctypes.c_double()
+    code = _lib.load().aig_auc(thr.ctypes.data, val.ctypes.data, len(thr), ctypes.byref(out))
+    if code != 0:
+        raise AigError(code, 'aig_auc: thresholds must be monotonic with at least two entries')
+    return out.value
+
+
+def success_rates(pos, num):
+    """``1.0 * pos / num`` (iouenergythreshold.py:236)."""
+    return np.asarray(pos, dtype=np.float64) / np.float64(num)
+
+
+# ---------------------------------------------------------------------------------------------
+# module-level drop-ins with the reference's names and signatures
+# ---------------------------------------------------------------------------------------------
+_local = threading.local()
+
+
+def default_path(device=None):
+    """The calling thread's handle (created on first use on the current CUDA device)."""
+    path = getattr(_local, 'path', None)
+    if device is None:
+        if path is not None:
+            return path
+        try:
+            device = _torch().cuda.current_device() if _torch().cuda.is_available() else 0
+        except Exception:
+            device = 0
+    if path is None or path.device != device:
+        path = AcousticPath(device)
+        _local.path = path
+    return path
+
+
+createfilters = tables.createfilters
+
+
+def get_feats(fft_len, beam, mfcc_num, dct_base, mfnorm, lifter, filter_mat):
+    """Drop-in for get_feats (dataloader/outdoor_data_mfcc.py:851-876).
+
+    NumPy in -> float64 [n, mfcc_num] out, like the reference (the values are the GPU's float32
+    results; the reference's callers cast to float32 at :823 anyway).  CUDA tensor in -> float32
+    CUDA tensor out."""
+    path = default_path()
+    bank = np.asarray(filter_mat)
+    if bank.shape[0] != fft_len or np.shape(dct_base) != (bank.shape[1], mfcc_num):
+        raise ValueError('table shapes do not match fft_len=%d mfcc_num=%d' % (fft_len, mfcc_num))
+    path.set_tables(bank, dct_base, lifter, mfnorm)
+    try:
+        rows = path.mfcc_rows(beam)
+    finally:
+        path.set_tables(*tables.reference_tables())
+    return rows.astype(np.float64) if isinstance(rows, np.ndarray) else rows
+
+
+def find_logen(mfcc):
+    """Drop-in for find_logen (iouenergythreshold.py:294-323), including its in-place scaling of ``mfcc``."""
+    return default_path().find_logen(mfcc, inplace=True)
+
+
+def _normalize_acoustic_images_rescaled(image):
+    """Drop-in for ActionsDataLoader._normalize_acoustic_images_rescaled (outdoor_data_mfcc.py:672-679): one
+    [36, 48, 12] frame -> float32 (x - min) / max(x - min)."""
+    out = default_path().normalize_images(image)
+    return out.reshape(FRAME_H, FRAME_W, MFCC_NUM)
+
+
+def _map_func_acoustic_images(audio_images, audio_samples, video_images, action, location, filtered_audio_samples):
+    """Drop-in for ActionsDataLoader._map_func_acoustic_images (outdoor_data_mfcc.py:657-670): element 0 of the
+    6-tuple ([T, 36, 48, 12] acoustic images) is normalised frame by frame, the rest pass through."""
+    processed = default_path().normalize_images(audio_images)
+    return processed, audio_samples, video_images, action, location, filtered_audio_samples

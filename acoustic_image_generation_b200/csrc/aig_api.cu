@@ -1,0 +1,769 @@
+// libaig.so - C ABI (include/aig.h) over the sm_100a kernels of this directory.
+//
+// Host-side responsibilities: argument validation, pointer classification (device / pinned /
+// pageable host), staging of host buffers through handle-owned device scratch (double-buffered
+// on a copy stream for the large spectrum input), TMA descriptor encoding, launch geometry
+// (persistent grids sized from the SM count), error reporting.  No compute happens on the host
+// except aig_auc's 10-term trapezoid.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/aig.h"
+#include "aig_common.cuh"
+#include "energy_kernel.cuh"
+#include "mfcc_kernel.cuh"
+#include "score_kernel.cuh"
+
+namespace {
+
+using namespace aig;
+
+// ---- reference tables as host data (generated) --------------------------------------------------
+const unsigned short kRefNzBin[AIG_REF_NNZ] = AIG_REF_NZ_BIN;
+const unsigned char kRefNzCol[AIG_REF_NNZ] = AIG_REF_NZ_COL;
+const double kRefNzVal[AIG_REF_NNZ] = AIG_REF_NZ_VAL;
+const double kRefDct[AIG_REF_FILTER_NUM * AIG_REF_MFCC_NUM] = AIG_REF_DCT;
+const double kRefLifter[AIG_REF_MFCC_NUM] = AIG_REF_LIFTER;
+const double kRefMfnorm = AIG_REF_MFNORM;
+
+thread_local std::string g_create_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+enum MemKind { kDevice, kHostPinned, kHostPageable };
+
+MemKind classify(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return kHostPageable;
+    }
+    switch (attr.type) {
+        case cudaMemoryTypeDevice:
+        case cudaMemoryTypeManaged:
+            return kDevice;
+        case cudaMemoryTypeHost:
+            return kHostPinned;
+        default:
+            return kHostPageable;
+    }
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct aig_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+    cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
+    int sm_count = 0;
+    std::string err;
+    // tables
+    bool tables_set = false, tables_ref = false;
+    int fft_len = 0, filter_num = 0, mfcc_num = 0;
+    double mfnorm = 0.0;
+    double* d_tables = nullptr;   // bank | dct | lifter (generic kernel)
+    // scratch: one grow-only arena plus per-call overflow blocks folded in at the next reset
+    char* arena = nullptr;
+    size_t arena_cap = 0, arena_off = 0;
+    std::vector<std::pair<void*, size_t>> overflow;
+    // misc
+    int variant = -1;
+    int64_t launches = 0;
+    EncodeTiledFn encode = nullptr;
+    bool smem_attr_set[16] = {false};
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+    int fail_cuda(cudaError_t e, const char* what) {
+        cudaGetLastError();
+        return fail(AIG_ERR_CUDA_BASE - static_cast<int>(e), "%s: %s (%s)", what, cudaGetErrorName(e),
+                    cudaGetErrorString(e));
+    }
+};
+
+#define AIG_CK(call)                                                   \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) return h->fail_cuda(e_, #call);         \
+    } while (0)
+
+namespace {
+
+// ---- scratch ------------------------------------------------------------------------------------
+int scratch_reset(aig_handle* h) {
+    if (!h->overflow.empty()) {
+        size_t total = h->arena_cap;
+        for (auto& b : h->overflow) total += align_up(b.second, 256);
+        AIG_CK(cudaStreamSynchronize(h->stream));
+        AIG_CK(cudaStreamSynchronize(h->copy_stream));
+        for (auto& b : h->overflow) cudaFree(b.first);
+        h->overflow.clear();
+        if (h->arena) cudaFree(h->arena);
+        h->arena = nullptr;
+        h->arena_cap = 0;
+        total = align_up(total + total / 4, 1 << 20);
+        if (cudaMalloc(&h->arena, total) != cudaSuccess) {
+            cudaGetLastError();
+            return h->fail(AIG_ERR_ALLOC, "cudaMalloc of %zu scratch bytes failed", total);
+        }
+        h->arena_cap = total;
+    }
+    h->arena_off = 0;
+    return AIG_OK;
+}
+
+void* scratch(aig_handle* h, size_t bytes) {
+    bytes = align_up(std::max<size_t>(bytes, 1), 256);
+    if (h->arena_off + bytes <= h->arena_cap) {
+        void* p = h->arena + h->arena_off;
+        h->arena_off += bytes;
+        return p;
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        h->fail(AIG_ERR_ALLOC, "cudaMalloc of %zu scratch bytes failed", bytes);
+        return nullptr;
+    }
+    h->overflow.emplace_back(p, bytes);
+    return p;
+}
+
+// ---- host/device staging of small and medium buffers ----------------------------------------------
+struct Io {
+    aig_handle* h;
+    bool any_host = false;
+    bool failed = false;
+    struct Pending { void* host; void* dev; size_t bytes; };
+    std::vector<Pending> outs;
+    explicit Io(aig_handle* handle) : h(handle) {}
+
+    template <typename T>
+    const T* in(const T* p, size_t count) {
+        if (p == nullptr) return nullptr;
+        if (classify(p) == kDevice) return p;
+        any_host = true;
+        void* d = scratch(h, count * sizeof(T));
+        if (!d) { failed = true; return nullptr; }
+        if (cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
+            h->fail_cuda(cudaGetLastError(), "cudaMemcpyAsync(H2D)");
+            failed = true;
+            return nullptr;
+        }
+        return static_cast<const T*>(d);
+    }
+    // in/out buffer (accumulators): copied in now, copied back at finish()
+    template <typename T>
+    T* inout(T* p, size_t count) {
+        if (p == nullptr) return nullptr;
+        if (classify(p) == kDevice) return p;
+        T* d = const_cast<T*>(in(const_cast<const T*>(p), count));
+        if (d) outs.push_back({p, d, count * sizeof(T)});
+        return d;
+    }
+    template <typename T>
+    T* out(T* p, size_t count) {
+        if (p == nullptr) return nullptr;
+        if (classify(p) == kDevice) return p;
+        any_host = true;
+        void* d = scratch(h, count * sizeof(T));
+        if (!d) { failed = true; return nullptr; }
+        outs.push_back({p, d, count * sizeof(T)});
+        return static_cast<T*>(d);
+    }
+    int finish() {
+        if (failed) return h->err.empty() ? h->fail(AIG_ERR_ALLOC, "staging failed") : AIG_ERR_ALLOC;
+        for (auto& o : outs)
+            AIG_CK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, h->stream));
+        if (any_host) AIG_CK(cudaStreamSynchronize(h->stream));
+        return AIG_OK;
+    }
+};
+
+int check_launch(aig_handle* h, const char* name) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return h->fail_cuda(e, name);
+    h->launches += 1;
+    return AIG_OK;
+}
+
+int frames_grid(const aig_handle* h, int64_t n_frames, int per_sm) {
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_frames, static_cast<int64_t>(h->sm_count) * per_sm)));
+}
+
+// ---- fused MFCC kernel variants -------------------------------------------------------------------
+struct Variant { int rows, slabs, stages, ctas; };
+constexpr int kNumVariants = 10;
+// Ring geometry {spectra per tile, 32-bin slabs per stage, stages, CTAs per SM}.  A stage count that
+// divides the 16/slabs stages of a tile lets the compiler resolve every ring address statically.
+constexpr Variant kVariants[kNumVariants] = {
+    {128, 1, 4, 3},    // 0: 16 KiB stages, 64 KiB ring, 3 CTAs/SM (192 KiB of loads in flight per SM)
+    {128, 2, 2, 3},    // 1: 32 KiB stages (256 B contiguous per spectrum)
+    {128, 1, 8, 1},    // 2: one CTA/SM, 128 KiB ring
+    {64, 2, 4, 3},     // 3
+    {64, 4, 2, 3},     // 4: 512 B contiguous per spectrum
+    {128, 4, 2, 1},    // 5: 64 KiB stages
+    {64, 1, 4, 6},     // 6: many small CTAs
+    {32, 16, 1, 3},    // 7: whole spectra per stage, pipelining across CTAs only
+    {256, 1, 4, 1},    // 8: 256-spectrum tiles
+    {128, 1, 6, 2},    // 9: run-time ring index (6 does not divide 16)
+};
+constexpr int kDefaultVariant = 0;
+
+template <int V>
+int launch_banded_variant(aig_handle* h, const CUtensorMap& map, float* out, unsigned n_rows, int flip180,
+                          unsigned frame_pixels) {
+    constexpr Variant v = kVariants[V];
+    using P = MfccPipe<v.rows, v.slabs, v.stages>;
+    auto kernel = mfcc_banded_kernel<v.rows, v.slabs, v.stages, v.ctas>;
+    if (!h->smem_attr_set[V]) {
+        AIG_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kSmemBytes));
+        h->smem_attr_set[V] = true;
+    }
+    const unsigned n_tiles = (n_rows + v.rows - 1) / v.rows;
+    const unsigned grid = std::min<unsigned>(n_tiles, static_cast<unsigned>(h->sm_count * v.ctas));
+    kernel<<<grid, P::kThreads, P::kSmemBytes, h->stream>>>(map, out, n_rows, n_tiles, flip180, frame_pixels);
+    return check_launch(h, "mfcc_banded_kernel");
+}
+
+int encode_spectrum_map(aig_handle* h, const float* d_power, uint64_t n_rows, int box_rows, CUtensorMap* map) {
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kFftLen), static_cast<cuuint64_t>(n_rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kFftLen) * sizeof(float)};
+    const cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(box_rows)};
+    const cuuint32_t elem[2] = {1u, 1u};
+    CUresult r = h->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d_power), dims, strides, box,
+                           elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return h->fail(AIG_ERR_CUDA_BASE, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return AIG_OK;
+}
+
+// d_power / d_out are device pointers; rows are processed in launches of < 2^31 rows.
+int launch_mfcc(aig_handle* h, const float* d_power, int64_t n_rows, float* d_out, int flip180, int frame_pixels) {
+    if (n_rows == 0) return AIG_OK;
+    if (!h->tables_ref) {
+        const double* bank = h->d_tables;
+        const double* dct = bank + static_cast<size_t>(h->fft_len) * h->filter_num;
+        const double* lifter = dct + static_cast<size_t>(h->filter_num) * h->mfcc_num;
+        const int64_t blocks = std::min<int64_t>((n_rows + kGenericWarps - 1) / kGenericWarps,
+                                                 static_cast<int64_t>(h->sm_count) * 8);
+        mfcc_generic_kernel<<<static_cast<unsigned>(blocks), kGenericWarps * 32, 0, h->stream>>>(
+            d_power, n_rows, h->fft_len, h->filter_num, h->mfcc_num, bank, dct, lifter, h->mfnorm, d_out, flip180,
+            frame_pixels);
+        return check_launch(h, "mfcc_generic_kernel");
+    }
+    if ((reinterpret_cast<uintptr_t>(d_power) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u))
+        return h->fail(AIG_ERR_ARGUMENT, "aig_mfcc: device buffers must be 16-byte aligned");
+    const int variant = h->variant < 0 ? kDefaultVariant : h->variant;
+    const int64_t unit = flip180 ? frame_pixels : 256;
+    const int64_t max_rows = ((int64_t(1) << 31) - 1024) / unit * unit;
+    for (int64_t done = 0; done < n_rows; done += max_rows) {
+        const int64_t rows = std::min(max_rows, n_rows - done);
+        CUtensorMap map;
+        int rc = encode_spectrum_map(h, d_power + done * kFftLen, static_cast<uint64_t>(rows),
+                                     kVariants[variant].rows, &map);
+        if (rc != AIG_OK) return rc;
+        float* out = d_out + done * kMfccNum;
+        const unsigned r = static_cast<unsigned>(rows), fp = static_cast<unsigned>(frame_pixels);
+        switch (variant) {
+            case 0: rc = launch_banded_variant<0>(h, map, out, r, flip180, fp); break;
+            case 1: rc = launch_banded_variant<1>(h, map, out, r, flip180, fp); break;
+            case 2: rc = launch_banded_variant<2>(h, map, out, r, flip180, fp); break;
+            case 3: rc = launch_banded_variant<3>(h, map, out, r, flip180, fp); break;
+            case 4: rc = launch_banded_variant<4>(h, map, out, r, flip180, fp); break;
+            case 5: rc = launch_banded_variant<5>(h, map, out, r, flip180, fp); break;
+            case 6: rc = launch_banded_variant<6>(h, map, out, r, flip180, fp); break;
+            case 7: rc = launch_banded_variant<7>(h, map, out, r, flip180, fp); break;
+            case 8: rc = launch_banded_variant<8>(h, map, out, r, flip180, fp); break;
+            case 9: rc = launch_banded_variant<9>(h, map, out, r, flip180, fp); break;
+            default: rc = h->fail(AIG_ERR_ARGUMENT, "unknown MFCC kernel variant %d", variant);
+        }
+        if (rc != AIG_OK) return rc;
+    }
+    return AIG_OK;
+}
+
+int launch_energy(aig_handle* h, const float* d_images, int64_t n_frames, int normalize_first, float* d_scaled,
+                  double* d_energy, uint8_t* d_mask, double* d_mean) {
+    if (n_frames == 0) return AIG_OK;
+    energy_kernel<<<frames_grid(h, n_frames, 8), kEnergyThreads, 0, h->stream>>>(
+        d_images, n_frames, normalize_first, d_scaled, d_energy, d_mask, d_mean);
+    return check_launch(h, "energy_kernel");
+}
+
+int require(aig_handle* h) {
+    if (h == nullptr) return AIG_ERR_ARGUMENT;
+    h->err.clear();
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return h->fail_cuda(e, "cudaSetDevice");
+    return scratch_reset(h);
+}
+
+// Host spectra -> device in frame-aligned chunks, double-buffered on the copy stream so the H2D
+// copy of chunk i+1 overlaps the kernels of chunk i.  `consume(chunk device ptr, first row, rows)`
+// enqueues the work of one chunk on h->stream.
+template <typename Consume>
+int stream_host_rows(aig_handle* h, const float* host, int64_t n_rows, int row_floats, int64_t rows_per_chunk,
+                     Consume consume) {
+    const size_t chunk_bytes = static_cast<size_t>(rows_per_chunk) * row_floats * sizeof(float);
+    float* buf[2] = {static_cast<float*>(scratch(h, chunk_bytes)), static_cast<float*>(scratch(h, chunk_bytes))};
+    if (!buf[0] || !buf[1]) return AIG_ERR_ALLOC;
+    // the scratch may still be in use by earlier work on h->stream
+    AIG_CK(cudaEventRecord(h->ev_consumed[0], h->stream));
+    AIG_CK(cudaEventRecord(h->ev_consumed[1], h->stream));
+    int slot = 0;
+    for (int64_t row = 0; row < n_rows; row += rows_per_chunk, slot ^= 1) {
+        const int64_t rows = std::min(rows_per_chunk, n_rows - row);
+        AIG_CK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0));
+        AIG_CK(cudaMemcpyAsync(buf[slot], host + row * row_floats, static_cast<size_t>(rows) * row_floats * sizeof(float),
+                               cudaMemcpyHostToDevice, h->copy_stream));
+        AIG_CK(cudaEventRecord(h->ev_copied[slot], h->copy_stream));
+        AIG_CK(cudaStreamWaitEvent(h->stream, h->ev_copied[slot], 0));
+        int rc = consume(buf[slot], row, rows);
+        if (rc != AIG_OK) return rc;
+        AIG_CK(cudaEventRecord(h->ev_consumed[slot], h->stream));
+    }
+    return AIG_OK;
+}
+
+int64_t host_chunk_rows(int64_t unit_rows, int row_floats) {
+    const int64_t target = int64_t(64) << 20;   // ~64 MiB per H2D copy
+    const int64_t unit_bytes = unit_rows * row_floats * 4;
+    return std::max<int64_t>(1, target / unit_bytes) * unit_rows;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int aig_abi_version(void) { return AIG_ABI_VERSION; }
+
+const char* aig_last_error(const aig_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int aig_create(int device, uint64_t stream, aig_handle** out) {
+    if (out == nullptr) { g_create_error = "aig_create: out is null"; return AIG_ERR_ARGUMENT; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        g_create_error = "aig_create: no CUDA device available (this library has no CPU fallback)";
+        return AIG_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) {
+        g_create_error = "aig_create: device index out of range";
+        return AIG_ERR_ARGUMENT;
+    }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        cudaGetLastError();
+        g_create_error = "aig_create: cannot select the device";
+        return AIG_ERR_NO_DEVICE;
+    }
+    if (prop.major != 10) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "aig_create: device %d is sm_%d%d; libaig is built for sm_100a (B200) only", device,
+                 prop.major, prop.minor);
+        g_create_error = buf;
+        return AIG_ERR_NO_DEVICE;
+    }
+    aig_handle* h = new aig_handle();
+    h->device = device;
+    h->stream = reinterpret_cast<cudaStream_t>(stream);
+    h->sm_count = prop.multiProcessorCount;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || fn == nullptr) {
+        cudaGetLastError();
+        g_create_error = "aig_create: the driver does not export cuTensorMapEncodeTiled";
+        delete h;
+        return AIG_ERR_NO_DEVICE;
+    }
+    h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    bool ok = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) {
+        ok = cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) {
+        cudaGetLastError();
+        g_create_error = "aig_create: stream / event creation failed";
+        aig_destroy(h);
+        return AIG_ERR_ALLOC;
+    }
+    *out = h;
+    return AIG_OK;
+}
+
+int aig_destroy(aig_handle* h) {
+    if (h == nullptr) return AIG_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+        if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
+    }
+    for (auto& b : h->overflow) cudaFree(b.first);
+    if (h->arena) cudaFree(h->arena);
+    if (h->d_tables) cudaFree(h->d_tables);
+    cudaGetLastError();
+    delete h;
+    return AIG_OK;
+}
+
+int aig_synchronize(aig_handle* h) {
+    if (h == nullptr) return AIG_ERR_ARGUMENT;
+    AIG_CK(cudaSetDevice(h->device));
+    AIG_CK(cudaStreamSynchronize(h->copy_stream));
+    AIG_CK(cudaStreamSynchronize(h->stream));
+    return AIG_OK;
+}
+
+int64_t aig_launch_count(const aig_handle* h) { return h ? h->launches : -1; }
+
+int aig_set_mfcc_variant(aig_handle* h, int variant) {
+    if (h == nullptr) return AIG_ERR_ARGUMENT;
+    if (variant < -1 || variant >= kNumVariants) return h->fail(AIG_ERR_ARGUMENT, "unknown MFCC kernel variant %d", variant);
+    h->variant = variant;
+    return AIG_OK;
+}
+
+int aig_set_tables(aig_handle* h, const double* filter_mat, int fft_len, int filter_num, const double* dct_base,
+                   int mfcc_num, const double* lifter, double mfnorm) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (!filter_mat || !dct_base || !lifter) return h->fail(AIG_ERR_ARGUMENT, "aig_set_tables: null table");
+    if (fft_len < 1 || fft_len > 4096 || filter_num < 1 || filter_num > kGenericMaxFilters || mfcc_num < 1 ||
+        mfcc_num > 32)
+        return h->fail(AIG_ERR_TABLES, "aig_set_tables: unsupported geometry fft_len=%d filter_num=%d mfcc_num=%d",
+                       fft_len, filter_num, mfcc_num);
+    // Is this exactly the reference configuration the banded mel program was generated from?
+    bool ref = fft_len == AIG_REF_FFT_LEN && filter_num == AIG_REF_FILTER_NUM && mfcc_num == AIG_REF_MFCC_NUM &&
+               mfnorm == kRefMfnorm;
+    if (ref) {
+        ref = std::memcmp(dct_base, kRefDct, sizeof kRefDct) == 0 && std::memcmp(lifter, kRefLifter, sizeof kRefLifter) == 0;
+    }
+    if (ref) {
+        std::vector<double> dense(static_cast<size_t>(AIG_REF_FFT_LEN) * AIG_REF_FILTER_NUM, 0.0);
+        for (int i = 0; i < AIG_REF_NNZ; ++i) dense[kRefNzBin[i] * AIG_REF_FILTER_NUM + kRefNzCol[i]] = kRefNzVal[i];
+        for (size_t i = 0; i < dense.size() && ref; ++i) ref = dense[i] == filter_mat[i];
+    }
+    const size_t n_bank = static_cast<size_t>(fft_len) * filter_num, n_dct = static_cast<size_t>(filter_num) * mfcc_num;
+    AIG_CK(cudaStreamSynchronize(h->stream));
+    if (h->d_tables) { cudaFree(h->d_tables); h->d_tables = nullptr; }
+    if (cudaMalloc(&h->d_tables, (n_bank + n_dct + mfcc_num) * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        return h->fail(AIG_ERR_ALLOC, "aig_set_tables: cudaMalloc failed");
+    }
+    AIG_CK(cudaMemcpy(h->d_tables, filter_mat, n_bank * sizeof(double), cudaMemcpyHostToDevice));
+    AIG_CK(cudaMemcpy(h->d_tables + n_bank, dct_base, n_dct * sizeof(double), cudaMemcpyHostToDevice));
+    AIG_CK(cudaMemcpy(h->d_tables + n_bank + n_dct, lifter, mfcc_num * sizeof(double), cudaMemcpyHostToDevice));
+    h->fft_len = fft_len; h->filter_num = filter_num; h->mfcc_num = mfcc_num; h->mfnorm = mfnorm;
+    h->tables_set = true;
+    h->tables_ref = ref;
+    return AIG_OK;
+}
+
+int aig_tables_are_reference(const aig_handle* h) {
+    if (h == nullptr) return AIG_ERR_ARGUMENT;
+    if (!h->tables_set) return AIG_ERR_TABLES;
+    return h->tables_ref ? 1 : 0;
+}
+
+int aig_mfcc(aig_handle* h, const float* power, int64_t n_rows, float* mfcc_out, int flip180, int frame_pixels) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (!h->tables_set) return h->fail(AIG_ERR_TABLES, "aig_mfcc: call aig_set_tables first");
+    if (n_rows < 0 || (n_rows > 0 && (!power || !mfcc_out))) return h->fail(AIG_ERR_ARGUMENT, "aig_mfcc: bad buffers");
+    if (flip180 && (frame_pixels < 1 || n_rows % frame_pixels != 0))
+        return h->fail(AIG_ERR_ARGUMENT, "aig_mfcc: flip180 needs n_rows (%lld) to be a multiple of frame_pixels (%d)",
+                       (long long)n_rows, frame_pixels);
+    if (!flip180 && frame_pixels < 1) frame_pixels = 1;
+    if (n_rows == 0) return AIG_OK;
+    const int in_floats = h->fft_len, out_floats = h->mfcc_num;
+    const bool in_dev = classify(power) == kDevice, out_dev = classify(mfcc_out) == kDevice;
+    float* d_out = out_dev ? mfcc_out : static_cast<float*>(scratch(h, static_cast<size_t>(n_rows) * out_floats * 4));
+    if (!d_out) return AIG_ERR_ALLOC;
+    if (in_dev) {
+        rc = launch_mfcc(h, power, n_rows, d_out, flip180, frame_pixels);
+        if (rc != AIG_OK) return rc;
+    } else {
+        const int64_t chunk = host_chunk_rows(flip180 ? frame_pixels : 128, in_floats);
+        rc = stream_host_rows(h, power, n_rows, in_floats, chunk, [&](const float* d_chunk, int64_t row, int64_t rows) {
+            return launch_mfcc(h, d_chunk, rows, d_out + row * out_floats, flip180, frame_pixels);
+        });
+        if (rc != AIG_OK) return rc;
+    }
+    if (!out_dev)
+        AIG_CK(cudaMemcpyAsync(mfcc_out, d_out, static_cast<size_t>(n_rows) * out_floats * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (!out_dev || !in_dev) AIG_CK(cudaStreamSynchronize(h->stream));
+    return AIG_OK;
+}
+
+int aig_normalize_images(aig_handle* h, const float* images, int64_t n_frames, float* out) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (n_frames < 0 || (n_frames > 0 && (!images || !out))) return h->fail(AIG_ERR_ARGUMENT, "aig_normalize_images: bad buffers");
+    if (n_frames == 0) return AIG_OK;
+    Io io(h);
+    const size_t count = static_cast<size_t>(n_frames) * kFrameValues;
+    const float* d_in = io.in(images, count);
+    float* d_out = io.out(out, count);
+    if (io.failed) return io.finish();
+    normalize_kernel<<<frames_grid(h, n_frames, 8), 256, 0, h->stream>>>(d_in, n_frames, d_out);
+    rc = check_launch(h, "normalize_kernel");
+    if (rc != AIG_OK) return rc;
+    return io.finish();
+}
+
+int aig_energy(aig_handle* h, const float* images, int64_t n_frames, int normalize_first, float* scaled_out,
+               double* energy_out, uint8_t* mask_out, double* mean_out) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (n_frames < 0 || (n_frames > 0 && !images)) return h->fail(AIG_ERR_ARGUMENT, "aig_energy: bad buffers");
+    if (n_frames == 0) return AIG_OK;
+    Io io(h);
+    const size_t n = static_cast<size_t>(n_frames);
+    const float* d_in = io.in(images, n * kFrameValues);
+    float* d_scaled = io.out(scaled_out, n * kFrameValues);
+    double* d_energy = io.out(energy_out, n * kFramePixels);
+    uint8_t* d_mask = io.out(mask_out, n * kFramePixels);
+    double* d_mean = io.out(mean_out, n);
+    if (io.failed) return io.finish();
+    rc = launch_energy(h, d_in, n_frames, normalize_first, d_scaled, d_energy, d_mask, d_mean);
+    if (rc != AIG_OK) return rc;
+    return io.finish();
+}
+
+int aig_heatmap(aig_handle* h, const double* energy, int64_t n_frames, int out_h, int out_w, float* heat_out) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (n_frames < 0 || (n_frames > 0 && (!energy || !heat_out))) return h->fail(AIG_ERR_ARGUMENT, "aig_heatmap: bad buffers");
+    if (out_h < 1 || out_w < 1 || out_h > kMaxOut || out_w > kMaxOut)
+        return h->fail(AIG_ERR_ARGUMENT, "aig_heatmap: output size %dx%d outside 1..%d", out_h, out_w, kMaxOut);
+    if (n_frames == 0) return AIG_OK;
+    Io io(h);
+    const size_t n = static_cast<size_t>(n_frames);
+    const double* d_energy = io.in(energy, n * kFramePixels);
+    float* d_heat = io.out(heat_out, n * out_h * out_w);
+    if (io.failed) return io.finish();
+    const size_t smem = static_cast<size_t>(out_w + out_h) * (sizeof(double) + sizeof(int));
+    heatmap_kernel<<<frames_grid(h, n_frames, 4), kHeatThreads, smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);
+    rc = check_launch(h, "heatmap_kernel");
+    if (rc != AIG_OK) return rc;
+    return io.finish();
+}
+
+int aig_resize_mask(aig_handle* h, const uint8_t* mask, int64_t n_frames, int out_h, int out_w, uint8_t* mask_up) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (n_frames < 0 || (n_frames > 0 && (!mask || !mask_up))) return h->fail(AIG_ERR_ARGUMENT, "aig_resize_mask: bad buffers");
+    if (out_h < 1 || out_w < 1 || out_h > kMaxOut || out_w > kMaxOut)
+        return h->fail(AIG_ERR_ARGUMENT, "aig_resize_mask: output size %dx%d outside 1..%d", out_h, out_w, kMaxOut);
+    if (n_frames == 0) return AIG_OK;
+    Io io(h);
+    const size_t n = static_cast<size_t>(n_frames);
+    const uint8_t* d_mask = io.in(mask, n * kFramePixels);
+    uint8_t* d_up = io.out(mask_up, n * out_h * out_w);
+    if (io.failed) return io.finish();
+    const size_t smem = static_cast<size_t>(out_w + out_h) * 2 * sizeof(int);
+    resize_mask_kernel<<<frames_grid(h, n_frames, 4), kHeatThreads, smem, h->stream>>>(d_mask, n_frames, out_h, out_w, d_up);
+    rc = check_launch(h, "resize_mask_kernel");
+    if (rc != AIG_OK) return rc;
+    return io.finish();
+}
+
+int aig_mfcc_energy(aig_handle* h, const float* power, int64_t n_frames, int flip180, int normalize_first,
+                    float* mfcc_out, double* energy_out, uint8_t* mask_out, double* mean_out) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (!h->tables_set || !h->tables_ref)
+        return h->fail(AIG_ERR_TABLES, "aig_mfcc_energy: needs the reference tables (aig_set_tables)");
+    if (n_frames < 0 || (n_frames > 0 && (!power || !mfcc_out))) return h->fail(AIG_ERR_ARGUMENT, "aig_mfcc_energy: bad buffers");
+    if (n_frames == 0) return AIG_OK;
+    const size_t n = static_cast<size_t>(n_frames);
+    const bool in_dev = classify(power) == kDevice;
+    Io io(h);
+    float* d_mfcc = io.out(mfcc_out, n * kFrameValues);
+    double* d_energy = io.out(energy_out, n * kFramePixels);
+    uint8_t* d_mask = io.out(mask_out, n * kFramePixels);
+    double* d_mean = io.out(mean_out, n);
+    if (io.failed) return io.finish();
+    auto run = [&](const float* d_power, int64_t frame0, int64_t frames) -> int {
+        float* mf = d_mfcc + frame0 * kFrameValues;
+        int r = launch_mfcc(h, d_power, frames * kFramePixels, mf, flip180, kFramePixels);
+        if (r != AIG_OK) return r;
+        return launch_energy(h, mf, frames, normalize_first, nullptr, d_energy ? d_energy + frame0 * kFramePixels : nullptr,
+                             d_mask ? d_mask + frame0 * kFramePixels : nullptr, d_mean ? d_mean + frame0 : nullptr);
+    };
+    if (in_dev) {
+        rc = run(power, 0, n_frames);
+    } else {
+        io.any_host = true;
+        const int64_t chunk_rows = host_chunk_rows(kFramePixels, kFftLen);
+        rc = stream_host_rows(h, power, n_frames * kFramePixels, kFftLen, chunk_rows,
+                              [&](const float* d_chunk, int64_t row, int64_t rows) {
+                                  return run(d_chunk, row / kFramePixels, rows / kFramePixels);
+                              });
+    }
+    if (rc != AIG_OK) return rc;
+    return io.finish();
+}
+
+static int check_sweep_args(aig_handle* h, const char* who, int64_t n, const double* thr, int k, int64_t* pos, int64_t* num) {
+    if (n < 0 || k < 0 || k > kMaxThresholds) return h->fail(AIG_ERR_ARGUMENT, "%s: n=%lld k=%d out of range (k <= %d)", who, (long long)n, k, kMaxThresholds);
+    if ((k > 0 && (!thr || !pos)) || !num) return h->fail(AIG_ERR_ARGUMENT, "%s: null threshold / count buffers", who);
+    return AIG_OK;
+}
+
+// num += n on whichever side the counter lives
+static int add_num(aig_handle* h, Io& io, int64_t* num, int64_t n) {
+    if (classify(num) == kDevice) {
+        int64_t cur = 0;
+        AIG_CK(cudaMemcpyAsync(&cur, num, sizeof cur, cudaMemcpyDeviceToHost, h->stream));
+        AIG_CK(cudaStreamSynchronize(h->stream));
+        cur += n;
+        AIG_CK(cudaMemcpyAsync(num, &cur, sizeof cur, cudaMemcpyHostToDevice, h->stream));
+        AIG_CK(cudaStreamSynchronize(h->stream));
+    } else {
+        *num += n;
+    }
+    (void)io;
+    return AIG_OK;
+}
+
+int aig_iou_sweep(aig_handle* h, const uint8_t* mask_a, const uint8_t* mask_b, int64_t n, const double* thr, int k,
+                  int64_t* inter_out, int64_t* union_out, int64_t* pos_inout, int64_t* num_inout) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    rc = check_sweep_args(h, "aig_iou_sweep", n, thr, k, pos_inout, num_inout);
+    if (rc != AIG_OK) return rc;
+    if (n > 0 && (!mask_a || !mask_b)) return h->fail(AIG_ERR_ARGUMENT, "aig_iou_sweep: null masks");
+    if (n == 0) return AIG_OK;
+    Io io(h);
+    const size_t cnt = static_cast<size_t>(n);
+    const uint8_t* d_a = io.in(mask_a, cnt * kFramePixels);
+    const uint8_t* d_b = io.in(mask_b, cnt * kFramePixels);
+    const double* d_thr = io.in(thr, static_cast<size_t>(k));
+    int64_t* d_inter = io.out(inter_out, cnt);
+    int64_t* d_union = io.out(union_out, cnt);
+    int64_t* d_pos = io.inout(pos_inout, static_cast<size_t>(k));
+    if (io.failed) return io.finish();
+    if ((reinterpret_cast<uintptr_t>(d_a) & 3u) || (reinterpret_cast<uintptr_t>(d_b) & 3u))
+        return h->fail(AIG_ERR_ARGUMENT, "aig_iou_sweep: mask buffers must be 4-byte aligned");
+    const int blocks = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 4));
+    iou_sweep_kernel<<<blocks, kIouThreads, 0, h->stream>>>(d_a, d_b, n, d_thr, k, reinterpret_cast<long long*>(d_inter),
+                                                            reinterpret_cast<long long*>(d_union),
+                                                            reinterpret_cast<unsigned long long*>(d_pos));
+    rc = check_launch(h, "iou_sweep_kernel");
+    if (rc != AIG_OK) return rc;
+    rc = io.finish();
+    if (rc != AIG_OK) return rc;
+    return add_num(h, io, num_inout, n);
+}
+
+int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, const int32_t* xmax, const int32_t* ymin,
+                   const int32_t* ymax, int64_t n, int out_h, int out_w, const double* thr, int k, int64_t* inter2_out,
+                   int64_t* union2_out, int64_t* pos_inout, int64_t* num_inout) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    rc = check_sweep_args(h, "aig_ciou_sweep", n, thr, k, pos_inout, num_inout);
+    if (rc != AIG_OK) return rc;
+    if (n > 0 && (!mask || !xmin || !xmax || !ymin || !ymax)) return h->fail(AIG_ERR_ARGUMENT, "aig_ciou_sweep: null inputs");
+    if (out_h < 1 || out_w < 1 || out_h > kMaxOut || out_w > kMaxOut)
+        return h->fail(AIG_ERR_ARGUMENT, "aig_ciou_sweep: output size %dx%d outside 1..%d", out_h, out_w, kMaxOut);
+    if (n == 0) return AIG_OK;
+    Io io(h);
+    const size_t cnt = static_cast<size_t>(n);
+    const uint8_t* d_mask = io.in(mask, cnt * kFramePixels);
+    const int32_t* d_xmin = io.in(xmin, cnt * 3);
+    const int32_t* d_xmax = io.in(xmax, cnt * 3);
+    const int32_t* d_ymin = io.in(ymin, cnt * 3);
+    const int32_t* d_ymax = io.in(ymax, cnt * 3);
+    const double* d_thr = io.in(thr, static_cast<size_t>(k));
+    int64_t* d_inter = io.out(inter2_out, cnt);
+    int64_t* d_union = io.out(union2_out, cnt);
+    int64_t* d_pos = io.inout(pos_inout, static_cast<size_t>(k));
+    if (io.failed) return io.finish();
+    const size_t smem = static_cast<size_t>(out_w + out_h) * 2 * sizeof(int);
+    ciou_sweep_kernel<<<frames_grid(h, n, 4), kIouThreads, smem, h->stream>>>(
+        d_mask, d_xmin, d_xmax, d_ymin, d_ymax, n, out_h, out_w, d_thr, k, reinterpret_cast<long long*>(d_inter),
+        reinterpret_cast<long long*>(d_union), reinterpret_cast<unsigned long long*>(d_pos));
+    rc = check_launch(h, "ciou_sweep_kernel");
+    if (rc != AIG_OK) return rc;
+    rc = io.finish();
+    if (rc != AIG_OK) return rc;
+    return add_num(h, io, num_inout, n);
+}
+
+int aig_auc(const double* thr, const double* value, int k, double* auc_out) {
+    if (!thr || !value || !auc_out || k < 2) return AIG_ERR_ARGUMENT;
+    // areaundercurve.py:32-37: both arrays reversed, then sklearn.metrics.auc: direction * sum(diff(x) * (y[1:] + y[:-1]) / 2)
+    bool inc = true, dec = true;
+    for (int i = 1; i < k; ++i) {
+        const double d = thr[k - 1 - i] - thr[k - i];   // diff of the reversed x
+        if (d > 0) dec = false;
+        if (d < 0) inc = false;
+    }
+    if (!inc && !dec) return AIG_ERR_ARGUMENT;
+    // NumPy's sum over k-1 terms: plain left-to-right for < 8 terms, else 8 strided partial sums
+    std::vector<double> term(k - 1);
+    for (int i = 0; i < k - 1; ++i) {
+        const double dx = thr[k - 2 - i] - thr[k - 1 - i];
+        term[i] = dx * (value[k - 2 - i] + value[k - 1 - i]) / 2.0;
+    }
+    const int n = k - 1;
+    double sum;
+    if (n < 8) {
+        sum = 0.0;
+        for (int i = 0; i < n; ++i) sum += term[i];
+    } else {
+        // pairwise_sum of numpy for n <= 128 (the sweep has at most kMaxThresholds terms: recurse above 128)
+        struct Pw {
+            static double run(const double* a, int n) {
+                if (n < 8) { double r = 0.0; for (int i = 0; i < n; ++i) r += a[i]; return r; }
+                if (n <= 128) {
+                    double r[8];
+                    for (int j = 0; j < 8; ++j) r[j] = a[j];
+                    int i = 8;
+                    for (; i < n - (n % 8); i += 8) for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+                    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+                    for (; i < n; ++i) res += a[i];
+                    return res;
+                }
+                int n2 = n / 2;
+                n2 -= n2 % 8;
+                return run(a, n2) + run(a + n2, n - n2);
+            }
+        };
+        sum = Pw::run(term.data(), n);
+    }
+    *auc_out = ((dec && !inc) ? -1.0 : 1.0) * sum;
+    return AIG_OK;
+}
+
+}  // extern "C"

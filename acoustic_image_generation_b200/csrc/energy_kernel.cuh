@@ -1,0 +1,317 @@
+// Stage 2 kernels: 12-channel acoustic image -> energy map, mean mask, up-sampled heat map.
+//
+// energy_kernel      F4 + F5 + F7  per-frame min-max (outdoor_data_mfcc.py:672-679), find_logen
+//                    (iouenergythreshold.py:294-323) and the mean-threshold mask (:217-219).
+// heatmap_kernel     F6            cv2.resize bilinear + implicit Normalize (showimages.py:147-148).
+// resize_mask_kernel F9 (part)     cv2.resize(mask) > 0.5 in exact integers (showimages_bb.py:303-304).
+//
+// One CTA per frame: the per-frame reductions (min, max, mean) are CTA-local.  The energy is
+// computed in float64 like the reference (float32-stored in-place scaling, then a float64
+// 12x24 projection, exp, band sum in NumPy's pairwise order, reciprocal) so that the
+// `map > mean(map)` decision is reproduced bit for bit up to the last-ulp differences of exp()
+// and of the BLAS summation order; the float64 mean follows NumPy's pairwise summation tree
+// for 1728 elements exactly.  FP64 work per frame is ~2 MFLOP, far below the HBM time of the
+// stage-1 stream it follows, and runs on the otherwise idle FP64 pipe.
+#pragma once
+
+#include "aig_common.cuh"
+#include "mel_tables_ref.inc"
+
+namespace aig {
+
+// find_logen's constants (iouenergythreshold.py:304-308), identical to the MFCC constants.
+__constant__ double c_dct[kFilterNum * kMfccNum] = AIG_REF_DCT;      // [24][12]
+__constant__ double c_lifter[kMfccNum] = AIG_REF_LIFTER;
+__constant__ double c_mfnorm = AIG_REF_MFNORM;
+
+constexpr int kEnergyThreads = 192;                                  // 9 pixels per thread
+constexpr int kPixelsPerThread = kFramePixels / kEnergyThreads;
+static_assert(kFramePixels % kEnergyThreads == 0, "pixels must divide evenly over the CTA");
+
+// NumPy pairwise-sum leaves for n = 1728: 1728 -> 864 -> 432 -> 216 -> (104, 112); every leaf is
+// summed with 8 strided accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)).
+__device__ __forceinline__ int leaf_start(int leaf) { return 216 * (leaf >> 1) + ((leaf & 1) ? 104 : 0); }
+__device__ __forceinline__ int leaf_len(int leaf) { return (leaf & 1) ? 112 : 104; }
+
+__global__ void __launch_bounds__(kEnergyThreads)
+energy_kernel(const float* __restrict__ images, long long n_frames, int normalize_first,
+              float* __restrict__ scaled_out, double* __restrict__ energy_out,
+              uint8_t* __restrict__ mask_out, double* __restrict__ mean_out) {
+    __shared__ double s_map[kFramePixels];
+    __shared__ double s_part[16][8];
+    __shared__ double s_leaf[16];
+    __shared__ float s_red[2][kEnergyThreads / 32];
+    __shared__ double s_mean;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
+        const float* img = images + frame * kFrameValues;
+        float lo = 0.f, range = 1.f;
+        if (normalize_first) {
+            // min and max of the frame; max(x - min) == fl(max - min) because rounding is monotonic
+            float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+            const float4* img4 = reinterpret_cast<const float4*>(img);
+            for (int i = tid; i < kFrameValues / 4; i += kEnergyThreads) {
+                const float4 v = __ldg(img4 + i);
+                mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
+                mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+            }
+            mn = warp_min(mn);
+            mx = warp_max(mx);
+            if (lane == 0) { s_red[0][warp] = mn; s_red[1][warp] = mx; }
+            __syncthreads();
+            mn = s_red[0][0]; mx = s_red[1][0];
+#pragma unroll
+            for (int w = 1; w < kEnergyThreads / 32; ++w) {
+                mn = fminf(mn, s_red[0][w]);
+                mx = fmaxf(mx, s_red[1][w]);
+            }
+            lo = mn;
+            range = __fsub_rn(mx, mn);
+        }
+
+#pragma unroll 1
+        for (int i = 0; i < kPixelsPerThread; ++i) {
+            const int p = tid + i * kEnergyThreads;
+            const float4* src = reinterpret_cast<const float4*>(img + p * kMfccNum);
+            const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+            float x[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+            double z[kMfccNum];
+#pragma unroll
+            for (int m = 0; m < kMfccNum; ++m) {
+                float v = x[m];
+                if (normalize_first) v = __fdiv_rn(__fsub_rn(v, lo), range);      // float32, as TF
+                // mfcc /= lifter; mfcc *= mfnorm : float64 compute, float32 store (:310-311)
+                v = __double2float_rn(__ddiv_rn(static_cast<double>(v), c_lifter[m]));
+                v = __double2float_rn(__dmul_rn(static_cast<double>(v), c_mfnorm));
+                x[m] = v;
+                z[m] = static_cast<double>(v);
+            }
+            if (scaled_out != nullptr) {
+                float4* dst = reinterpret_cast<float4*>(scaled_out + frame * kFrameValues + p * kMfccNum);
+                dst[0] = make_float4(x[0], x[1], x[2], x[3]);
+                dst[1] = make_float4(x[4], x[5], x[6], x[7]);
+                dst[2] = make_float4(x[8], x[9], x[10], x[11]);
+            }
+            // melspec = exp(mfcc . dct_base^T); band sum in NumPy's order for n = 24:
+            // r[k] = e[k] + e[k+8] + e[k+16], then the balanced tree over r[0..7] (:313-320)
+            double r[8];
+#pragma unroll
+            for (int j = 0; j < kFilterNum; ++j) {
+                double mel = 0.0;
+#pragma unroll
+                for (int m = 0; m < kMfccNum; ++m) mel = fma(z[m], c_dct[j * kMfccNum + m], mel);
+                const double e = exp(mel);
+                r[j & 7] = (j < 8) ? e : __dadd_rn(r[j & 7], e);
+            }
+            const double total = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+            const double en = __ddiv_rn(1.0, total);                                  // :321
+            s_map[p] = en;
+            if (energy_out != nullptr) energy_out[frame * kFramePixels + p] = en;
+        }
+        __syncthreads();
+
+        if (mask_out != nullptr || mean_out != nullptr) {
+            // np.mean(map): pairwise tree, bit-compatible with NumPy for 1728 contiguous doubles
+            if (tid < 128) {
+                const int leaf = tid >> 3, k = tid & 7;
+                const double* a = s_map + leaf_start(leaf);
+                const int len = leaf_len(leaf);
+                double r = a[k];
+                for (int i = 8; i < len; i += 8) r = __dadd_rn(r, a[i + k]);
+                s_part[leaf][k] = r;
+            }
+            __syncthreads();
+            if (tid < 16) {
+                const double* r = s_part[tid];
+                s_leaf[tid] = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                                        __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double s8[8], s4[4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s8[i] = __dadd_rn(s_leaf[2 * i], s_leaf[2 * i + 1]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s4[i] = __dadd_rn(s8[2 * i], s8[2 * i + 1]);
+                const double sum = __dadd_rn(__dadd_rn(s4[0], s4[1]), __dadd_rn(s4[2], s4[3]));
+                const double mean = __ddiv_rn(sum, static_cast<double>(kFramePixels));
+                s_mean = mean;
+                if (mean_out != nullptr) mean_out[frame] = mean;
+            }
+            __syncthreads();
+            if (mask_out != nullptr) {
+                const double mean = s_mean;
+                for (int p = tid; p < kFramePixels; p += kEnergyThreads)
+                    mask_out[frame * kFramePixels + p] = s_map[p] > mean ? 1 : 0;
+            }
+        }
+        __syncthreads();   // s_map / s_red are reused by the next frame
+    }
+}
+
+// F4 alone: _normalize_acoustic_images_rescaled over frames (float32).
+__global__ void __launch_bounds__(256)
+normalize_kernel(const float* __restrict__ images, long long n_frames, float* __restrict__ out) {
+    __shared__ float s_red[2][8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
+        const float4* img4 = reinterpret_cast<const float4*>(images + frame * kFrameValues);
+        float4* out4 = reinterpret_cast<float4*>(out + frame * kFrameValues);
+        float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+        for (int i = tid; i < kFrameValues / 4; i += 256) {
+            const float4 v = img4[i];
+            mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
+            mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+        }
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        if (lane == 0) { s_red[0][warp] = mn; s_red[1][warp] = mx; }
+        __syncthreads();
+        mn = s_red[0][0]; mx = s_red[1][0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { mn = fminf(mn, s_red[0][w]); mx = fmaxf(mx, s_red[1][w]); }
+        const float range = __fsub_rn(mx, mn);
+        for (int i = tid; i < kFrameValues / 4; i += 256) {
+            float4 v = img4[i];
+            v.x = __fdiv_rn(__fsub_rn(v.x, mn), range);
+            v.y = __fdiv_rn(__fsub_rn(v.y, mn), range);
+            v.z = __fdiv_rn(__fsub_rn(v.z, mn), range);
+            v.w = __fdiv_rn(__fsub_rn(v.w, mn), range);
+            out4[i] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- bilinear taps (cv2.resize INTER_LINEAR: half-pixel centres, border clamp) -------------------
+// float64 taps exactly as the oracle forms them: pos = (d + 0.5) * (n_src / n_dst) - 0.5.
+__device__ __forceinline__ void linear_tap(int d, int n_src, int n_dst, int* i0, int* i1, double* w1) {
+    const double scale = __ddiv_rn(static_cast<double>(n_src), static_cast<double>(n_dst));
+    const double pos = __dadd_rn(__dmul_rn(static_cast<double>(d) + 0.5, scale), -0.5);
+    int lo = static_cast<int>(floor(pos));
+    double w = __dadd_rn(pos, -static_cast<double>(lo));
+    if (lo < 0) { lo = 0; w = 0.0; }
+    if (lo >= n_src - 1) { lo = n_src - 1; w = 0.0; }
+    *i0 = lo;
+    *i1 = min(lo + 1, n_src - 1);
+    *w1 = w;
+}
+// Integer taps: pos = ((2d+1) * n_src - n_dst) / (2 * n_dst); weight numerator over den = 2 * n_dst.
+__device__ __forceinline__ void linear_tap_exact(int d, int n_src, int n_dst, int* i0, int* i1, int* num) {
+    const int den = 2 * n_dst;
+    const int t = (2 * d + 1) * n_src - n_dst;
+    int lo = (t >= 0) ? t / den : -((-t + den - 1) / den);
+    int r = t - lo * den;
+    if (lo < 0) { lo = 0; r = 0; }
+    if (lo >= n_src - 1) { lo = n_src - 1; r = 0; }
+    *i0 = lo;
+    *i1 = min(lo + 1, n_src - 1);
+    *num = r;
+}
+
+constexpr int kHeatThreads = 256;
+constexpr int kMaxOut = 2048;   // out_h, out_w <= 2048
+
+// energy [n, 36, 48] f64 -> heat [n, out_h, out_w] f32 = (up - min(up)) / (max(up) - min(up)).
+// Dynamic shared memory: out_w * (2 int + 1 double) + out_h * (2 int + 1 double).
+__global__ void __launch_bounds__(kHeatThreads)
+heatmap_kernel(const double* __restrict__ energy, long long n_frames, int out_h, int out_w,
+               float* __restrict__ heat) {
+    extern __shared__ double s_dyn[];
+    __shared__ double s_map[kFramePixels];
+    __shared__ double s_red[2][kHeatThreads / 32];
+    double* s_wx = s_dyn;                      // [out_w]
+    double* s_wy = s_wx + out_w;               // [out_h]
+    int* s_x0 = reinterpret_cast<int*>(s_wy + out_h);   // [out_w] x0 | x1 << 16
+    int* s_y0 = s_x0 + out_w;                  // [out_h]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int d = tid; d < out_w; d += kHeatThreads) {
+        int i0, i1; double w;
+        linear_tap(d, kFrameW, out_w, &i0, &i1, &w);
+        s_x0[d] = i0 | (i1 << 16); s_wx[d] = w;
+    }
+    for (int d = tid; d < out_h; d += kHeatThreads) {
+        int i0, i1; double w;
+        linear_tap(d, kFrameH, out_h, &i0, &i1, &w);
+        s_y0[d] = i0 | (i1 << 16); s_wy[d] = w;
+    }
+    const int n_out = out_h * out_w;
+    for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
+        __syncthreads();
+        for (int p = tid; p < kFramePixels; p += kHeatThreads) s_map[p] = energy[frame * kFramePixels + p];
+        __syncthreads();
+        auto sample = [&](int idx) -> double {
+            const int y = idx / out_w, x = idx - y * out_w;
+            const int xi = s_x0[x], yi = s_y0[y];
+            const int x0 = xi & 0xffff, x1 = xi >> 16, y0 = yi & 0xffff, y1 = yi >> 16;
+            const double wx = s_wx[x], wy = s_wy[y];
+            const double ux = __dadd_rn(1.0, -wx), uy = __dadd_rn(1.0, -wy);
+            // horizontal pass on the two source rows, then the vertical pass (no FMA contraction)
+            const double top = __dadd_rn(__dmul_rn(s_map[y0 * kFrameW + x0], ux), __dmul_rn(s_map[y0 * kFrameW + x1], wx));
+            const double bot = __dadd_rn(__dmul_rn(s_map[y1 * kFrameW + x0], ux), __dmul_rn(s_map[y1 * kFrameW + x1], wx));
+            return __dadd_rn(__dmul_rn(top, uy), __dmul_rn(bot, wy));
+        };
+        double mn = CUDART_INF, mx = -CUDART_INF;
+        for (int idx = tid; idx < n_out; idx += kHeatThreads) {
+            const double v = sample(idx);
+            mn = fmin(mn, v); mx = fmax(mx, v);
+        }
+        mn = warp_min(mn); mx = warp_max(mx);
+        if (lane == 0) { s_red[0][warp] = mn; s_red[1][warp] = mx; }
+        __syncthreads();
+        mn = s_red[0][0]; mx = s_red[1][0];
+#pragma unroll
+        for (int w = 1; w < kHeatThreads / 32; ++w) { mn = fmin(mn, s_red[0][w]); mx = fmax(mx, s_red[1][w]); }
+        const double range = __dadd_rn(mx, -mn);
+        float* dst = heat + frame * n_out;
+        for (int idx = tid; idx < n_out; idx += kHeatThreads)
+            dst[idx] = __double2float_rn(__ddiv_rn(__dadd_rn(sample(idx), -mn), range));
+    }
+}
+
+// mask [n, 36, 48] u8 -> mask_up [n, out_h, out_w] u8, value 1 iff bilinear(mask != 0) > 1/2 exactly.
+// Dynamic shared memory: (out_w + out_h) * 2 ints.
+__device__ __forceinline__ int upsampled_bit(const uint8_t* s_mask, int xi, int xn, int yi, int yn,
+                                             int xd, int yd) {
+    const int x0 = xi & 0xffff, x1 = xi >> 16, y0 = yi & 0xffff, y1 = yi >> 16;
+    const int top = s_mask[y0 * kFrameW + x0] * (xd - xn) + s_mask[y0 * kFrameW + x1] * xn;
+    const int bot = s_mask[y1 * kFrameW + x0] * (xd - xn) + s_mask[y1 * kFrameW + x1] * xn;
+    const long long val = static_cast<long long>(top) * (yd - yn) + static_cast<long long>(bot) * yn;
+    return 2 * val > static_cast<long long>(xd) * yd;
+}
+
+__global__ void __launch_bounds__(kHeatThreads)
+resize_mask_kernel(const uint8_t* __restrict__ mask, long long n_frames, int out_h, int out_w,
+                   uint8_t* __restrict__ mask_up) {
+    extern __shared__ int s_taps[];
+    __shared__ uint8_t s_mask[kFramePixels];
+    int* s_x0 = s_taps;            // [out_w] x0 | x1 << 16
+    int* s_xn = s_x0 + out_w;      // [out_w]
+    int* s_y0 = s_xn + out_w;      // [out_h]
+    int* s_yn = s_y0 + out_h;      // [out_h]
+    const int tid = threadIdx.x;
+    for (int d = tid; d < out_w; d += kHeatThreads) {
+        int i0, i1, r; linear_tap_exact(d, kFrameW, out_w, &i0, &i1, &r);
+        s_x0[d] = i0 | (i1 << 16); s_xn[d] = r;
+    }
+    for (int d = tid; d < out_h; d += kHeatThreads) {
+        int i0, i1, r; linear_tap_exact(d, kFrameH, out_h, &i0, &i1, &r);
+        s_y0[d] = i0 | (i1 << 16); s_yn[d] = r;
+    }
+    const int xd = 2 * out_w, yd = 2 * out_h, n_out = out_h * out_w;
+    for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
+        __syncthreads();
+        for (int p = tid; p < kFramePixels; p += kHeatThreads) s_mask[p] = mask[frame * kFramePixels + p] != 0;
+        __syncthreads();
+        uint8_t* dst = mask_up + frame * n_out;
+        for (int idx = tid; idx < n_out; idx += kHeatThreads) {
+            const int y = idx / out_w, x = idx - y * out_w;
+            dst[idx] = static_cast<uint8_t>(upsampled_bit(s_mask, s_x0[x], s_xn[x], s_y0[y], s_yn[y], xd, yd));
+        }
+    }
+}
+
+}  // namespace aig

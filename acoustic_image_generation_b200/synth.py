@@ -1,0 +1,95 @@
+"""Deterministic synthetic inputs shaped like the reference's datasets.
+
+Host-side NumPy only; shared by the tests, ``bench.py`` and ``oracle/make_golden.py``
+so that every party sees the same seeded arrays.  Nothing here touches the GPU or
+the oracle.
+
+* ``power_frames``   - [n, 36, 48, 512] float32 per-pixel frequency power, the
+  input of ``get_feats`` (dataloader/outdoor_data_mfcc.py:803-804 squares an rFFT
+  magnitude, hence non-negative).
+* ``sigmoid_images`` - [n, 36, 48, 12] float32 in (0, 1), the range of the UNet's
+  sigmoid output (models/unet_acresnet.py:89-94) that ``find_logen`` is fed with.
+* ``flickr_boxes``   - FlickrSoundNet-style annotator boxes in 298x224 pixel
+  coordinates (dataloader/frames.py:290-299, convert_data2.py:225-260).
+"""
+from __future__ import annotations
+
+import hashlib
+
+import numpy as np
+
+FRAME_H, FRAME_W, FFT_LEN, MFCC_NUM = 36, 48, 512, 12
+POWER_KINDS = ('chi2', 'lognormal', 'floor')
+
+
+def power_frames(n, seed=0, kind='chi2'):
+    """n synthetic multispectral acoustic frames, float32 [n, 36, 48, 512].
+
+    ``chi2``      squared standard normal (a squared rFFT magnitude of noise);
+    ``lognormal`` exp(3 * N(0,1)), nine decades of dynamic range;
+    ``floor``     1e-6 * U(0,1): every mel band falls under the 0.001 floor.
+    """
+    rng = np.random.default_rng(seed)
+    shape = (n, FRAME_H, FRAME_W, FFT_LEN)
+    if kind == 'chi2':
+        x = rng.standard_normal(shape, dtype=np.float32)
+        return x * x
+    if kind == 'lognormal':
+        return np.exp(np.float32(3.0) * rng.standard_normal(shape, dtype=np.float32))
+    if kind == 'floor':
+        return np.float32(1e-6) * rng.random(shape, dtype=np.float32)
+    raise ValueError('unknown kind %r (expected one of %s)' % (kind, POWER_KINDS))
+
+
+def sigmoid_images(n, seed=0):
+    """n synthetic 12-channel acoustic images with values in [0, 1), float32 [n, 36, 48, 12]."""
+    rng = np.random.default_rng(seed)
+    return rng.random((n, FRAME_H, FRAME_W, MFCC_NUM), dtype=np.float32)
+
+
+def smooth_images(n, seed=0):
+    """Blob-like 12-channel images (a few Gaussian sources per frame) so that the energy
+    masks are connected regions rather than salt-and-pepper; float32 [n, 36, 48, 12] in (0, 1)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:FRAME_H, 0:FRAME_W].astype(np.float32)
+    out = np.empty((n, FRAME_H, FRAME_W, MFCC_NUM), dtype=np.float32)
+    for i in range(n):
+        field = np.zeros((FRAME_H, FRAME_W), dtype=np.float32)
+        for _ in range(int(rng.integers(1, 4))):
+            cy, cx = rng.uniform(0, FRAME_H), rng.uniform(0, FRAME_W)
+            s = rng.uniform(2.0, 8.0)
+            field += np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / np.float32(2 * s * s)).astype(np.float32)
+        chan = rng.uniform(0.2, 1.0, MFCC_NUM).astype(np.float32)
+        img = field[:, :, None] * chan[None, None, :] + np.float32(0.05) * rng.random(
+            (FRAME_H, FRAME_W, MFCC_NUM), dtype=np.float32)
+        out[i] = img / (img.max() + np.float32(1e-3))
+    return out
+
+
+def flickr_boxes(n, seed=0, height=224, width=298):
+    """(xmin, xmax, ymin, ymax), each int32 [n, 3]; 1-3 annotators per frame, absent ones all-zero.
+
+    Coordinates are inclusive pixel indices with xmax allowed to equal ``width``
+    (convert_data2.py:257-258 rounds 256-px annotations up to 298), which the
+    consumer clips."""
+    rng = np.random.default_rng(seed)
+    xmin = np.zeros((n, 3), np.int32); xmax = np.zeros((n, 3), np.int32)
+    ymin = np.zeros((n, 3), np.int32); ymax = np.zeros((n, 3), np.int32)
+    count = rng.integers(1, 4, n)
+    for i in range(n):
+        for c in range(int(count[i])):
+            xa, xb = np.sort(rng.integers(0, width + 1, 2))
+            ya, yb = np.sort(rng.integers(0, height + 1, 2))
+            if xb == xa:
+                xb = min(xa + 1, width)
+            if xb == 0:
+                xb = 1
+            if yb == ya:
+                yb = min(ya + 1, height)
+            xmin[i, c], xmax[i, c], ymin[i, c], ymax[i, c] = xa, xb, ya, yb
+    return xmin, xmax, ymin, ymax
+
+
+def digest(array):
+    """Short SHA-256 of an array's bytes; golden files store it to detect generator drift."""
+    return hashlib.sha256(np.ascontiguousarray(array).tobytes()).hexdigest()[:16]

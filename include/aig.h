@@ -1,0 +1,198 @@
+/*
+ * aig.h - C ABI of libaig.so: the B200 (sm_100a) acoustic-image front end and
+ * localisation scoring path of IIT-PAVIS/Acoustic-Image-Generation.
+ *
+ * The reference exposes this path as plain Python callables on NumPy arrays (the
+ * only "plugin API" is tf.py_func(fn, [tensor], tf.float32),
+ * dataloader/outdoor_data_mfcc.py:788).  Each entry point below replaces one of
+ * those callables / inline blocks; the reference location is cited per function.
+ * The Python drop-ins in acoustic_image_generation_b200/ bind these with ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - Plain C: pointers and sizes only, no C++/torch types.
+ *   - Every data pointer may be a DEVICE pointer (DLPack / __cuda_array_interface__ /
+ *     torch.Tensor.data_ptr()) or a HOST pointer (NumPy; pinned memory makes the copies
+ *     asynchronous).  The library classifies each pointer with
+ *     cudaPointerGetAttributes and stages host buffers through its own device
+ *     scratch; the caller owns every buffer, nothing allocated here crosses the ABI.
+ *   - Every function returns 0 on success, a negative code on failure
+ *     (AIG_ERR_* below, or -(1000 + cudaError_t) for CUDA runtime failures) and
+ *     records a message retrievable with aig_last_error().  No C++ exception
+ *     crosses the boundary.  There is no CPU fallback: without a CUDA device
+ *     aig_create() fails.
+ *   - A handle is one device + one stream.  Calls on one handle are serialised by
+ *     the caller (the reference's tf.data map runs 4 worker threads,
+ *     outdoor_data_mfcc.py:82: give each its own handle).  Calls return after
+ *     the work has been enqueued when all buffers are device memory, and after
+ *     completion when any buffer is host memory (NumPy semantics).
+ */
+#ifndef AIG_H_
+#define AIG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AIG_ABI_VERSION 1
+
+#define AIG_OK 0
+#define AIG_ERR_ARGUMENT (-1)    /* null / out-of-range / inconsistent argument        */
+#define AIG_ERR_NO_DEVICE (-2)   /* no CUDA device, or device is not sm_100            */
+#define AIG_ERR_TABLES (-3)      /* aig_set_tables not called, or unsupported geometry */
+#define AIG_ERR_ALLOC (-4)       /* device / pinned allocation failed                  */
+#define AIG_ERR_CUDA_BASE (-1000) /* -(1000 + cudaError_t)                             */
+
+/* Frame geometry fixed by the reference (outdoor_data_mfcc.py:445 reshape [-1, 36, 48, 12];
+ * iouenergythreshold.py:322 reshape (36, 48)). */
+#define AIG_FRAME_H 36
+#define AIG_FRAME_W 48
+#define AIG_FRAME_PIXELS (AIG_FRAME_H * AIG_FRAME_W)
+#define AIG_MFCC_NUM 12
+#define AIG_FILTER_NUM 24
+
+typedef struct aig_handle aig_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+
+/* Create a handle on CUDA device `device`.  `stream` is a cudaStream_t passed as an
+ * integer (0 = the legacy default stream, which orders with torch's default stream;
+ * pass torch.cuda.current_stream().cuda_stream to run on a torch stream).
+ * Replaces: `with tf.device('/gpu:0')` / CUDA_VISIBLE_DEVICES selection
+ * (iouenergythreshold.py:75, scripts/iou.bash:49). */
+int aig_create(int device, uint64_t stream, aig_handle** out);
+int aig_destroy(aig_handle* h);
+
+/* Message of the last failure on this handle (or of the last failed aig_create when
+ * h is NULL).  The pointer stays valid until the next call on the same handle. */
+const char* aig_last_error(const aig_handle* h);
+
+/* ABI version of the loaded library (== AIG_ABI_VERSION of the header it was built from). */
+int aig_abi_version(void);
+
+/* Block until everything enqueued on the handle's stream(s) has finished. */
+int aig_synchronize(aig_handle* h);
+
+/* ---- tables --------------------------------------------------------------------------- */
+
+/* Install the MFCC tables, all float64 host arrays, row-major:
+ *   filter_mat [fft_len, filter_num]  from createfilters (outdoor_data_mfcc.py:826-849)
+ *   dct_base   [filter_num, mfcc_num] (outdoor_data_mfcc.py:813-815)
+ *   lifter     [mfcc_num]             (:816)
+ *   mfnorm                            (:818)
+ * The tables come from the caller so that parity never depends on re-deriving them
+ * in C.  When they equal the reference configuration (512 bins, 24 filters, 12
+ * coefficients, createfilters(512, 24, 0, 6400, 12800)) value for value, aig_mfcc
+ * runs the fused banded kernel; any other tables run the generic float64 kernel
+ * (fft_len <= 4096, filter_num <= 64, mfcc_num <= 32).
+ * aig_tables_are_reference() reports which one is active (1 / 0, negative on error). */
+int aig_set_tables(aig_handle* h, const double* filter_mat, int fft_len, int filter_num,
+                   const double* dct_base, int mfcc_num, const double* lifter, double mfnorm);
+int aig_tables_are_reference(const aig_handle* h);
+
+/* ---- stage 1: spectra -> MFCC image ---------------------------------------------------- */
+
+/* get_feats (outdoor_data_mfcc.py:851-876; copies at iouenergythreshold.py:325-350, ...)
+ * followed by the np.float32 cast of its caller (:823):
+ *   power    [n_rows, fft_len] float32  power spectra, one row per pixel (row-major)
+ *   mfcc_out [n_rows, mfcc_num] float32
+ * mel = power . filter_mat; floor at 0.001; ln; . dct_base; * mfnorm; * lifter; NaN/Inf -> 0.
+ * flip180 != 0 additionally applies tf.image.flip_left_right + flip_up_down of
+ * _parse_sequence (outdoor_data_mfcc.py:314-315) on store: rows are grouped in
+ * frames of `frame_pixels` rows and row p of a frame is written to row
+ * frame_pixels-1-p (n_rows must then be a multiple of frame_pixels). */
+int aig_mfcc(aig_handle* h, const float* power, int64_t n_rows, float* mfcc_out,
+             int flip180, int frame_pixels);
+
+/* ---- stage 2: MFCC image -> energy map, mask, heat map --------------------------------- */
+
+/* _normalize_acoustic_images_rescaled mapped over frames by _map_func_acoustic_images
+ * (outdoor_data_mfcc.py:657-679): per frame, float32, x -= min(x); x /= max(x) over all
+ * 36*48*12 values.  images / out: [n_frames, 36, 48, 12] float32 (may alias). */
+int aig_normalize_images(aig_handle* h, const float* images, int64_t n_frames, float* out);
+
+/* find_logen (iouenergythreshold.py:294-323) + the mean threshold mask
+ * (iouenergythreshold.py:217-219), batched over frames.
+ *   images          [n_frames, 36, 48, 12] float32 (12-channel acoustic image)
+ *   normalize_first != 0: apply aig_normalize_images' arithmetic first (the dataloader
+ *                   feeds find_logen with the normalised image)
+ *   scaled_out      nullable [n_frames, 36, 48, 12] float32: the in-place side effect of
+ *                   find_logen on its argument (x / lifter, then * mfnorm, each computed
+ *                   in float64 and rounded to float32); may alias `images`
+ *   energy_out      nullable [n_frames, 36, 48] float64: 1 / sum_j exp(sum_m x_m dct[j][m])
+ *   mask_out        nullable [n_frames, 36, 48] uint8: energy > mean(energy), mean in
+ *                   float64 with NumPy's pairwise summation order
+ *   mean_out        nullable [n_frames] float64 */
+int aig_energy(aig_handle* h, const float* images, int64_t n_frames, int normalize_first,
+               float* scaled_out, double* energy_out, uint8_t* mask_out, double* mean_out);
+
+/* Heat-map rendering arithmetic: cv2.resize(map, (out_w, out_h)) (bilinear, half-pixel
+ * centres, border clamp; showimages.py:147, showvideo.py:227) followed by the implicit
+ * matplotlib Normalize of imshow (showimages.py:148): (x - min) / (max - min) with min/max
+ * over the up-sampled image.
+ *   energy   [n_frames, 36, 48] float64
+ *   heat_out [n_frames, out_h, out_w] float32 */
+int aig_heatmap(aig_handle* h, const double* energy, int64_t n_frames, int out_h, int out_w,
+                float* heat_out);
+
+/* 1.0 * (cv2.resize(mask * 1.0, (out_w, out_h)) > 0.5) (showimages_bb.py:303-304), decided in
+ * exact integer arithmetic.  mask [n_frames, 36, 48] uint8 -> mask_up [n_frames, out_h, out_w] uint8. */
+int aig_resize_mask(aig_handle* h, const uint8_t* mask, int64_t n_frames, int out_h, int out_w,
+                    uint8_t* mask_up);
+
+/* Stages 1 + 2 chained on the device (the north-star "MFCC + energy" pass):
+ * power [n_frames, 36, 48, 512] float32 -> mfcc_out [n_frames, 36, 48, 12] float32 (flip180 as in
+ * aig_mfcc), then aig_energy(normalize_first) on it.  mfcc_out must be non-null (device scratch is
+ * NOT substituted: the MFCC image is a product of the pass); energy_out / mask_out / mean_out as in
+ * aig_energy.  Requires the reference tables. */
+int aig_mfcc_energy(aig_handle* h, const float* power, int64_t n_frames, int flip180,
+                    int normalize_first, float* mfcc_out, double* energy_out, uint8_t* mask_out,
+                    double* mean_out);
+
+/* ---- stage 3: scoring ------------------------------------------------------------------ */
+
+/* ACIVW / AVIA IoU and success counts (iouenergythreshold.py:224-229), all thresholds in one pass
+ * (the reference re-runs the evaluation once per threshold, scripts/iou.bash:47-53).
+ *   mask_a, mask_b [n, 36*48] uint8 (non-zero = set)
+ *   thr            [k] float64 host or device
+ *   inter_out, union_out nullable [n] int64: sum(a & b), sum(a | b)
+ *   pos_inout      [k] int64: pos[j] += #frames with (double)I/(double)U > thr[j] (strict; U == 0
+ *                  gives NaN and never counts).  ACCUMULATES, so shards/batches can be chained;
+ *                  zero it before the first call.
+ *   num_inout      [1] int64: += n */
+int aig_iou_sweep(aig_handle* h, const uint8_t* mask_a, const uint8_t* mask_b, int64_t n,
+                  const double* thr, int k, int64_t* inter_out, int64_t* union_out,
+                  int64_t* pos_inout, int64_t* num_inout);
+
+/* FlickrSoundNet consensus IoU and success counts (showimages_bb.py:288-321).
+ *   mask  [n, 36*48] uint8 predicted mask at acoustic resolution (up-sampled here exactly as
+ *         aig_resize_mask does)
+ *   xmin, xmax, ymin, ymax [n, 3] int32 annotator boxes in out_w x out_h pixel coordinates,
+ *         inclusive corners, clipped; a box is present iff xmax != 0 (dataloader/frames.py:290-299)
+ *   inter2_out, union2_out nullable [n] int64: TWICE the reference's weighted intersection / union
+ *         (the weights are multiples of 0.5, so the doubled sums are exact integers)
+ *   pos_inout, num_inout as in aig_iou_sweep, with iou = (double)I2/(double)U2. */
+int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, const int32_t* xmax,
+                   const int32_t* ymin, const int32_t* ymax, int64_t n, int out_h, int out_w,
+                   const double* thr, int k, int64_t* inter2_out, int64_t* union2_out,
+                   int64_t* pos_inout, int64_t* num_inout);
+
+/* areaundercurve.py:32-37: sklearn.metrics.auc on the reversed (descending) threshold / success-rate
+ * arrays == direction * trapezoid.  Host-side, float64.  thr / value are host arrays of length k. */
+int aig_auc(const double* thr, const double* value, int k, double* auc_out);
+
+/* ---- instrumentation ------------------------------------------------------------------- */
+
+/* Number of kernels this handle has launched since creation (for bench.py's gpu_launches). */
+int64_t aig_launch_count(const aig_handle* h);
+
+/* Tuning knob for the fused MFCC kernel: `variant` selects the pipeline geometry
+ * (see mfcc_kernel.cuh); -1 restores the default.  Returns AIG_ERR_ARGUMENT for unknown variants. */
+int aig_set_mfcc_variant(aig_handle* h, int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIG_H_ */

@@ -1,0 +1,121 @@
+"""CPU-side checks of the drop-in boundary: the library builds for sm_100a, loads, exports every
+symbol include/aig.h declares, and fails loudly (no fallback) without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import acoustic_image_generation_b200 as aig
+from acoustic_image_generation_b200 import _lib, metrics_io, tables
+from oracle import acoustic_oracle as oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    _lib.build()
+    return _lib.load()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'aig.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(aig_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_header_symbols_are_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 17
+    for name in names:
+        assert hasattr(lib, name), 'libaig.so does not export %s' % name
+    assert sorted(_lib.SIGNATURES) == names, 'ctypes binding and header disagree'
+
+
+def test_abi_version(lib):
+    assert lib.aig_abi_version() == 1
+
+
+def test_shared_object_is_in_tree_and_sm100a():
+    assert os.path.dirname(_lib.LIB_PATH).endswith(os.path.join('acoustic_image_generation_b200', 'csrc'))
+    assert os.path.exists(_lib.LIB_PATH)
+    assert 'arch=compute_100a,code=sm_100a' in _lib.NVCC_FLAGS
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    h = ctypes.c_void_p()
+    assert lib.aig_create(0, 0, ctypes.byref(h)) == -2
+    assert b'no CUDA device' in lib.aig_last_error(None)
+    with pytest.raises(aig.AigError):
+        aig.AcousticPath(0)
+    with pytest.raises(aig.AigError):
+        aig.find_logen(np.zeros((36, 48, 12), np.float32))
+
+
+def test_auc_host_entry_matches_oracle(lib, golden):
+    g = golden('auc')
+    a = golden('acivw_iou'); f = golden('flickr_ciou')
+    thr = list(oracle.REFERENCE_THRESHOLDS)
+    assert aig.auc(thr, aig.success_rates(a['pos11'], a['num'])) == float(g['acivw11'])
+    assert aig.auc(thr, aig.success_rates(f['pos11'], f['num'])) == float(g['flickr11'])
+    t101 = np.linspace(0, 1, 101)
+    v101 = aig.success_rates(f['pos101'], f['num'])
+    assert aig.auc(t101, v101) == oracle.auc(t101, v101)
+    rng = np.random.default_rng(0)
+    for k in (2, 3, 8, 9, 11, 101, 130, 300, 1000):
+        t = np.linspace(0, 1, k)
+        v = np.sort(rng.random(k))[::-1]
+        assert aig.auc(t, v) == oracle.auc(t, v), k
+    with pytest.raises(aig.AigError):
+        aig.auc([0.0, 0.5, 0.2], [1, 1, 1])
+
+
+def test_product_tables_equal_oracle_tables():
+    bank, dct, lifter, mfnorm = tables.reference_tables()
+    ob, od, ol, om = oracle.reference_tables()
+    assert np.array_equal(bank, ob) and np.array_equal(dct, od) and np.array_equal(lifter, ol) and mfnorm == om
+    assert np.array_equal(aig.createfilters(256, 20, 300, 4000, 8000), oracle.createfilters(256, 20, 300, 4000, 8000))
+
+
+def test_generated_mel_program_matches_tables():
+    """The straight-line program compiled into the kernel is the float32 image of the oracle's bank."""
+    bank, dct, lifter, mfnorm = oracle.reference_tables()
+    text = open(os.path.join(ROOT, 'acoustic_image_generation_b200', 'csrc', 'mel_program_ref.inc')).read()
+    comp = {'x': 0, 'y': 1, 'z': 2, 'w': 3}
+    got = np.zeros((512, 24), np.float32)
+    folded = np.zeros((24, 12), np.float32)
+    slab = None
+    for line in text.splitlines():
+        m = re.match(r'MEL_SLAB_BEGIN\((\d+)\)', line)
+        if m:
+            slab = int(m.group(1)); continue
+        m = re.match(r'MEL_BIN1\((\d+), (\w), (\d+), \d, ([^)]+)\)', line)
+        if m:
+            k = 32 * slab + 4 * int(m.group(1)) + comp[m.group(2)]
+            got[k, int(m.group(3))] = float.fromhex(m.group(4).rstrip('f')); continue
+        m = re.match(r'MEL_BIN2\((\d+), (\w), (\d+), \d, ([^,]+), (\d+), \d, ([^)]+)\)', line)
+        if m:
+            k = 32 * slab + 4 * int(m.group(1)) + comp[m.group(2)]
+            got[k, int(m.group(3))] = float.fromhex(m.group(4).rstrip('f'))
+            got[k, int(m.group(5))] = float.fromhex(m.group(6).rstrip('f')); continue
+        m = re.match(r'MEL_DONE\((\d+), (.+)\)', line)
+        if m:
+            folded[int(m.group(1))] = [float.fromhex(v.strip().rstrip('f')) if 'x' in v else float(v.strip().rstrip('f'))
+                                       for v in m.group(2).split(',')]
+    assert np.array_equal(got, bank.astype(np.float32))
+    assert np.array_equal(folded, (dct * mfnorm * lifter[None, :]).astype(np.float32))
+
+
+def test_metric_files_round_trip(tmp_path):
+    for thr, pos in zip(oracle.REFERENCE_THRESHOLDS, range(11)):
+        p = metrics_io.write_accuracy_file(str(tmp_path), thr, pos, 10)
+        assert os.path.basename(p) == 'intersection_{}_accuracy.txt'.format(thr * 1.0)
+        assert open(p).read() == 'iou {:6f}'.format(pos / 10)
+        assert metrics_io.read_accuracy_file(str(tmp_path), thr) == round(pos / 10, 6)
+    p = metrics_io.write_area_file(str(tmp_path), 0.4321987)
+    assert open(p).read() == 'area 0.432199'
