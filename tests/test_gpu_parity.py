@@ -1,0 +1,382 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden vectors.  Needs a B200.
+
+Tolerances (BASELINE.json north_star): MFCC images and heat maps max abs error <= 1e-4 against the
+reference's float32 output; integer counts (I, U, pos, num) bit-exact whenever the masks agree, with
+every disagreeing boundary pixel reported; AUC <= 1e-12.
+"""
+import numpy as np
+import pytest
+
+import acoustic_image_generation_b200 as aig
+from acoustic_image_generation_b200 import synth, tables
+from oracle import acoustic_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+MFCC_TOL = 1e-4          # stated tolerance of the north star
+HEAT_TOL = 1e-4
+ENERGY_RTOL = 1e-13      # float64 energy: exp() and BLAS-order last-ulp differences only
+REF_THR = list(oracle.REFERENCE_THRESHOLDS)
+NUM_VARIANTS = 10
+
+
+@pytest.fixture(scope='module')
+def path():
+    p = aig.AcousticPath(0)
+    assert p.tables_are_reference
+    yield p
+    p.close()
+
+
+@pytest.fixture(scope='module')
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+# ----------------------------------------------------------------------------------------------
+# stage 1: MFCC
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('kind,n', [('chi2', 2), ('lognormal', 1), ('floor', 1)])
+def test_mfcc_matches_golden_and_oracle(path, golden, kind, n):
+    g = golden('mfcc')
+    power = synth.power_frames(n, int(g['seed_' + kind]), kind)
+    got = path.mfcc_image(power)
+    assert isinstance(got, np.ndarray) and got.dtype == np.float32 and got.shape == (n, 36, 48, 12)
+    err = np.abs(got.astype(np.float64) - g['mfcc_' + kind].astype(np.float64)).max()
+    print('mfcc %s: max abs err vs reference float32 output = %.3e (max |mfcc| %.1f)' % (kind, err, np.abs(g['mfcc_' + kind]).max()))
+    assert err <= MFCC_TOL
+    assert np.array_equal(oracle.mfcc_image(power), g['mfcc_' + kind])
+
+
+@pytest.mark.parametrize('variant', range(NUM_VARIANTS))
+def test_mfcc_every_pipeline_variant(path, variant):
+    power = synth.power_frames(3, 7, 'chi2')
+    want = oracle.mfcc_image(power)
+    path.set_mfcc_variant(variant)
+    try:
+        got = path.mfcc_image(power)
+    finally:
+        path.set_mfcc_variant(-1)
+    assert np.abs(got - want).max() <= MFCC_TOL
+
+
+def test_mfcc_variants_agree_bitwise(path):
+    """Every ring geometry runs the same per-spectrum program: results are identical bit for bit."""
+    power = synth.power_frames(2, 8, 'lognormal')
+    outs = []
+    for variant in range(NUM_VARIANTS):
+        path.set_mfcc_variant(variant)
+        outs.append(path.mfcc_image(power))
+    path.set_mfcc_variant(-1)
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])
+
+
+def test_mfcc_device_tensor_in_device_tensor_out(path, torch):
+    power = synth.power_frames(2, 0, 'chi2')
+    d = torch.from_numpy(power).cuda()
+    got = path.mfcc_image(d)
+    assert got.is_cuda and got.dtype == torch.float32 and tuple(got.shape) == (2, 36, 48, 12)
+    assert np.array_equal(got.cpu().numpy(), path.mfcc_image(power))
+
+
+def test_mfcc_flip180(path):
+    power = synth.power_frames(3, 5, 'chi2')
+    plain = path.mfcc_image(power)
+    flipped = path.mfcc_image(power, flip=True)
+    assert np.array_equal(flipped, oracle.flip180(plain))
+    assert np.abs(flipped - oracle.mfcc_image(power, flip=True)).max() <= MFCC_TOL
+
+
+@pytest.mark.parametrize('n_rows', [0, 1, 31, 127, 128, 129, 1727, 1729, 5000])
+def test_mfcc_ragged_row_counts(path, n_rows):
+    rng = np.random.default_rng(n_rows)
+    beam = rng.standard_normal((n_rows, 512), dtype=np.float32) ** 2
+    got = path.mfcc_rows(beam)
+    assert got.shape == (n_rows, 12)
+    if n_rows:
+        bank, dct, lifter, mfnorm = oracle.reference_tables()
+        want = np.float32(oracle.get_feats(512, beam, 12, dct, mfnorm, lifter, bank))
+        assert np.abs(got - want).max() <= MFCC_TOL
+
+
+def test_mfcc_nan_inf_rows_are_zeroed_like_the_reference(path):
+    bank, dct, lifter, mfnorm = oracle.reference_tables()
+    beam = np.ones((8, 512), np.float32)
+    beam[0, 100] = np.nan
+    beam[1, 200] = np.inf
+    beam[2, 0] = np.inf        # bin 0 has an all-zero filter row: inf * 0 = NaN in the dense product
+    beam[3, 511] = np.nan      # same for the last bin
+    beam[4, 300] = -np.inf
+    beam[5, 5] = np.inf        # a triangle peak
+    with np.errstate(invalid='ignore'):
+        want = np.float32(oracle.get_feats(512, beam, 12, dct, mfnorm, lifter, bank))
+    got = path.mfcc_rows(beam)
+    assert np.isfinite(got).all()
+    for r in range(6):
+        assert np.array_equal(got[r], np.zeros(12, np.float32)), r
+        assert np.array_equal(want[r], np.zeros(12, np.float32)), r
+    assert np.abs(got[6:] - want[6:]).max() <= MFCC_TOL and np.abs(got[6]).max() > 0
+
+
+def test_mfcc_negative_and_tiny_inputs_hit_the_floor(path):
+    bank, dct, lifter, mfnorm = oracle.reference_tables()
+    rng = np.random.default_rng(3)
+    beam = rng.standard_normal((256, 512), dtype=np.float32) * np.float32(1e-3)     # signed: many mel sums < 0.001
+    want = np.float32(oracle.get_feats(512, beam, 12, dct, mfnorm, lifter, bank))
+    assert np.abs(path.mfcc_rows(beam) - want).max() <= MFCC_TOL
+
+
+def test_get_feats_dropin_reference_and_generic_tables(path):
+    bank, dct, lifter, mfnorm = tables.reference_tables()
+    beam = synth.power_frames(1, 9, 'chi2').reshape(-1, 512)[:300]
+    got = aig.get_feats(512, beam, 12, dct, mfnorm, lifter, bank)
+    assert got.dtype == np.float64 and got.shape == (300, 12)
+    assert np.abs(got - oracle.get_feats(512, beam, 12, dct, mfnorm, lifter, bank)).max() <= MFCC_TOL
+    # a geometry the fused kernel does not cover: 256 bins, 20 filters, 10 coefficients (generic float64 kernel)
+    bank2 = aig.createfilters(256, 20, 300, 4000, 8000)
+    dct2, lifter2, mfnorm2 = tables.mfcc_constants(20, 10, 22)
+    rng = np.random.default_rng(4)
+    beam2 = rng.standard_normal((777, 256), dtype=np.float32) ** 2
+    p2 = aig.AcousticPath(0, tables_=(bank2, dct2, lifter2, mfnorm2))
+    assert not p2.tables_are_reference
+    got2 = p2.mfcc_rows(beam2)
+    want2 = oracle.get_feats(256, beam2, 10, dct2, mfnorm2, lifter2, bank2)
+    assert np.abs(got2 - np.float32(want2)).max() <= 1e-5
+    got3 = aig.get_feats(256, beam2, 10, dct2, mfnorm2, lifter2, bank2)
+    assert np.array_equal(got3, got2.astype(np.float64))
+    p2.close()
+
+
+def test_mfcc_host_staging_across_chunks(path):
+    """A host batch larger than one 64 MiB staging chunk goes through the double-buffered H2D pipeline."""
+    power = synth.power_frames(45, 11, 'chi2')          # 159 MB
+    got = path.mfcc_image(power, flip=True)
+    want = oracle.mfcc_image(power, flip=True)
+    assert np.abs(got - want).max() <= MFCC_TOL
+
+
+def test_mfcc_large_batch_is_the_small_case_tiled(path, torch):
+    """Size-independent property at bench scale: frames are independent, so 2048 frames made of 8 distinct
+    frames repeated give exactly the 8-frame answer repeated (7.2 GB of spectra, larger than L2)."""
+    base = torch.from_numpy(synth.power_frames(8, 12, 'chi2')).cuda()
+    small = path.mfcc_image(base)
+    assert np.abs(small.cpu().numpy() - oracle.mfcc_image(base.cpu().numpy())).max() <= MFCC_TOL
+    big = base.repeat(256, 1, 1, 1)
+    out = path.mfcc_image(big)
+    assert torch.equal(out.view(256, 8, 36, 48, 12), small.unsqueeze(0).expand(256, -1, -1, -1, -1))
+
+
+# ----------------------------------------------------------------------------------------------
+# stage 2: normalise, energy, mask, heat map
+# ----------------------------------------------------------------------------------------------
+def test_normalize_bit_exact(path, golden):
+    mf = golden('mfcc')['mfcc_chi2']
+    got = path.normalize_images(mf)
+    assert np.array_equal(got, golden('energy')['normed_input'])
+    assert np.array_equal(got, oracle.normalize_acoustic_images(mf))
+    one = aig._normalize_acoustic_images_rescaled(mf[0])
+    assert one.shape == (36, 48, 12) and np.array_equal(one, got[0])
+    tup = aig._map_func_acoustic_images(mf, 'a', 'v', 1, 2, 'f')
+    assert np.array_equal(tup[0], got) and tup[1:] == ('a', 'v', 1, 2, 'f')
+    const = path.normalize_images(np.full((1, 36, 48, 12), 3.0, np.float32))
+    assert np.isnan(const).all()                          # 0/0, as in the reference
+
+
+def _mask_report(name, energy, mean, got_mask, want_mask):
+    diff = np.argwhere(got_mask != want_mask)
+    for idx in diff[:20]:
+        f = idx[0]
+        print('boundary pixel %s %s: energy %.17g mean %.17g' % (name, tuple(idx), energy[tuple(idx)], mean[f]))
+    return len(diff)
+
+
+@pytest.mark.parametrize('name', ['normed', 'sigmoid', 'smooth'])
+def test_energy_and_mask_match_reference(path, golden, name):
+    g = golden('energy')
+    imgs = {'normed': g['normed_input'], 'sigmoid': synth.sigmoid_images(2, 3), 'smooth': synth.smooth_images(2, 4)}[name]
+    energy, mask, scaled, mean = path.energy(imgs, normalize_first=False, want_scaled=True, want_mean=True)
+    want = g['energy_' + name]
+    assert energy.dtype == np.float64 and mask.dtype == np.uint8
+    rel = np.abs(energy - want).max() / np.abs(want).max()
+    print('energy %s: max rel err %.3e; bit-identical %.1f%%' % (name, rel, 100 * (energy == want).mean()))
+    assert rel <= ENERGY_RTOL
+    assert np.abs(mean - g['mean_' + name]).max() <= ENERGY_RTOL * np.abs(g['mean_' + name]).max()
+    assert _mask_report(name, energy, mean, mask, g['mask_' + name]) == 0
+    if name == 'sigmoid':
+        assert np.array_equal(scaled[0], g['sigmoid0_after_call'])    # the in-place side effect, bit-exact
+
+
+def test_energy_mean_is_numpy_pairwise(path):
+    """Fed back its own energies, the device mean equals np.mean bit for bit (same summation tree)."""
+    imgs = synth.sigmoid_images(6, 30)
+    energy, mask, mean = path.energy(imgs, want_mean=True)
+    assert np.array_equal(mean, np.array([np.mean(e) for e in energy]))
+    assert np.array_equal(mask, np.stack([oracle.mean_mask(e) for e in energy], 0))
+
+
+def test_energy_with_normalisation_first(path, golden):
+    mf = golden('mfcc')['mfcc_chi2']
+    energy, mask = path.energy(mf, normalize_first=True)
+    want_e, want_m = oracle.energy_stage(mf, normalize_first=True)
+    assert np.abs(energy - want_e).max() <= ENERGY_RTOL * np.abs(want_e).max()
+    assert (mask != want_m).sum() == 0
+
+
+def test_find_logen_dropin_scales_argument_in_place(path, golden, torch):
+    g = golden('energy')
+    frame = synth.sigmoid_images(2, 3)[0].copy()
+    en = aig.find_logen(frame)
+    assert en.shape == (36, 48) and en.dtype == np.float64
+    assert np.array_equal(frame, g['sigmoid0_after_call'])
+    assert np.abs(en - g['energy_sigmoid'][0]).max() <= ENERGY_RTOL * np.abs(en).max()
+    keep = synth.sigmoid_images(2, 3)[0].copy()
+    path.find_logen(keep, inplace=False)
+    assert np.array_equal(keep, synth.sigmoid_images(2, 3)[0])
+    dev = torch.from_numpy(synth.sigmoid_images(2, 3)[0].copy()).cuda()
+    en_dev = path.find_logen(dev)
+    assert en_dev.is_cuda and np.array_equal(dev.cpu().numpy(), g['sigmoid0_after_call'])
+    assert np.array_equal(en_dev.cpu().numpy(), en)
+
+
+@pytest.mark.parametrize('shape', [(224, 298), (224, 224), (36, 48), (100, 77)])
+def test_heatmap_matches_oracle_and_cv2_golden(path, golden, shape):
+    e = golden('energy')['energy_smooth']
+    got = path.heatmap(e, *shape)
+    want = np.stack([oracle.heatmap(x, *shape) for x in e], 0)
+    assert got.dtype == np.float32 and got.shape == (2,) + shape
+    err = np.abs(got.astype(np.float64) - want).max()
+    print('heatmap %s: max abs err %.3e' % (shape, err))
+    assert err <= HEAT_TOL
+    assert got.min() == 0.0 and got.max() == 1.0
+    key = 'up_%d_%d' % shape
+    if key in golden('heatmap'):
+        up = golden('heatmap')[key]                       # cv2.resize output of frame 0
+        ref = np.float32((up - up.min()) / (up.max() - up.min()))
+        assert np.abs(got[0] - ref).max() <= HEAT_TOL
+
+
+@pytest.mark.parametrize('shape', [(224, 298), (224, 224), (36, 48), (73, 95)])
+def test_resize_mask_bit_exact(path, golden, shape):
+    e = golden('energy')
+    masks = np.concatenate([e['mask_smooth'], e['mask_sigmoid']], 0)
+    got = path.resize_mask(masks, *shape)
+    want = np.stack([oracle.resize_mask(m, *shape) for m in masks], 0)
+    assert np.array_equal(got, want)
+    if shape == (224, 298):
+        cvg = np.unpackbits(golden('heatmap')['mask_up_224_298'], axis=-1)[..., :298]
+        assert np.array_equal(got[:2], cvg)
+
+
+# ----------------------------------------------------------------------------------------------
+# stage 3: IoU sweeps and AUC
+# ----------------------------------------------------------------------------------------------
+def test_acivw_iou_sweep_bit_exact(path, golden):
+    g = golden('acivw_iou')
+    n = int(g['num'])
+    a = synth.smooth_images(n, 10)
+    b = synth.smooth_images(n, 11)
+    b[: n // 2] = a[: n // 2] * np.float32(0.9) + b[: n // 2] * np.float32(0.1)
+    _, mask_a = path.energy(a)
+    _, mask_b = path.energy(b)
+    for thr, key in ((REF_THR, 'pos11'), (np.linspace(0, 1, 101), 'pos101')):
+        inter, union, pos, num = path.iou_sweep(mask_a, mask_b, thr)
+        assert np.array_equal(inter, g['inter']) and np.array_equal(union, g['union'])
+        assert np.array_equal(pos, g[key]) and num == n
+    # accumulate over two shards == one pass (what the multi-GPU all-reduce relies on)
+    _, _, pos1, num1 = path.iou_sweep(mask_a[:20], mask_b[:20], REF_THR)
+    _, _, pos2, num2 = path.iou_sweep(mask_a[20:], mask_b[20:], REF_THR, pos=pos1, num=num1)
+    assert np.array_equal(pos2, g['pos11']) and num2 == n
+    rates = aig.success_rates(pos2, num2)
+    assert abs(aig.auc(REF_THR, rates) - float(golden('auc')['acivw11'])) <= 1e-12
+
+
+def test_iou_sweep_edge_cases(path):
+    empty = np.zeros((3, 36, 48), np.uint8)
+    full = np.ones((3, 36, 48), np.uint8)
+    inter, union, pos, num = path.iou_sweep(empty, empty, [0.0, 0.5])
+    assert inter.tolist() == [0, 0, 0] and union.tolist() == [0, 0, 0]
+    assert pos.tolist() == [0, 0] and num == 3                     # 0/0 = NaN never counts, but num does
+    inter, union, pos, num = path.iou_sweep(full * 7, full, [0.0, 0.5, 1.0])   # any non-zero byte is "set"
+    assert inter.tolist() == [1728] * 3 and pos.tolist() == [3, 3, 0]
+    rng = np.random.default_rng(5)
+    a = (rng.random((257, 36, 48)) > 0.5).astype(np.uint8)
+    b = (rng.random((257, 36, 48)) > 0.7).astype(np.uint8)
+    thr = np.linspace(0, 1, 1024)
+    inter, union, pos, num = path.iou_sweep(a, b, thr)
+    want = [oracle.iou_pair(x, y) for x, y in zip(a, b)]
+    assert inter.tolist() == [w[0] for w in want] and union.tolist() == [w[1] for w in want]
+    wpos, wnum = oracle.success_counts([w[2] for w in want], thr)
+    assert np.array_equal(pos, wpos) and num == wnum
+
+
+@pytest.mark.parametrize('shape', [(224, 298), (224, 224)])
+def test_flickr_ciou_sweep_bit_exact(path, golden, shape):
+    g = golden('flickr_ciou')
+    n = int(g['num'])
+    pred = synth.smooth_images(n, 20)
+    if shape == (224, 298):
+        xmin, xmax, ymin, ymax = synth.flickr_boxes(n, 21)
+    else:
+        xmin, xmax, ymin, ymax = synth.flickr_boxes(n, 22, 224, 224)
+    _, masks = path.energy(pred)
+    for thr in (REF_THR, np.linspace(0, 1, 101)):
+        i2, u2, pos, num = path.ciou_sweep(masks, xmin, xmax, ymin, ymax, thr, out_hw=shape)
+        wi, wu, wpos, wnum = oracle.flickr_sweep(masks, xmin, xmax, ymin, ymax, thr, *shape)
+        assert np.array_equal(i2, wi) and np.array_equal(u2, wu)
+        assert np.array_equal(pos, wpos) and num == wnum
+    if shape == (224, 298):
+        i2, u2, pos, num = path.ciou_sweep(masks, xmin, xmax, ymin, ymax, REF_THR)
+        assert np.array_equal(i2 / 2.0, g['inter']) and np.array_equal(u2 / 2.0, g['union'])
+        assert np.array_equal(pos, g['pos11'])
+        assert abs(aig.auc(REF_THR, aig.success_rates(pos, num)) - float(golden('auc')['flickr11'])) <= 1e-12
+
+
+def test_ciou_box_edge_cases(path):
+    mask = np.zeros((4, 36, 48), np.uint8)
+    mask[1] = 1
+    mask[2, 10:20, 10:30] = 1
+    mask[3, :, :24] = 1
+    xmin = np.array([[0, 0, 0], [0, 290, 0], [50, 50, 50], [-5, 100, 0]], np.int32)
+    xmax = np.array([[0, 0, 0], [10, 298, 0], [200, 200, 200], [400, 20, 0]], np.int32)   # absent / clipped / x3 / swapped
+    ymin = np.array([[0, 0, 0], [0, 200, 0], [40, 40, 40], [-3, 10, 0]], np.int32)
+    ymax = np.array([[0, 0, 0], [5, 224, 0], [180, 180, 180], [300, 5, 0]], np.int32)
+    i2, u2, pos, num = path.ciou_sweep(mask, xmin, xmax, ymin, ymax, REF_THR)
+    wi, wu, wpos, wnum = oracle.flickr_sweep(mask, xmin, xmax, ymin, ymax, REF_THR)
+    assert np.array_equal(i2, wi) and np.array_equal(u2, wu) and np.array_equal(pos, wpos) and num == wnum
+    assert u2[0] == 0 and pos.sum() >= 0
+
+
+# ----------------------------------------------------------------------------------------------
+# chained path
+# ----------------------------------------------------------------------------------------------
+def test_mfcc_energy_chain_against_oracle_chain(path, torch):
+    """End to end from spectra: stage-1 rounding (<= 2e-5) may flip pixels whose energy sits at the mean; every
+    such boundary pixel is listed, and counts are exact wherever the masks agree."""
+    power = synth.power_frames(6, 40, 'chi2')
+    mfcc, energy, mask, mean = path.mfcc_energy(power, flip=True, normalize_first=True, want_mean=True)
+    want_mfcc = oracle.mfcc_image(power, flip=True)
+    assert np.abs(mfcc - want_mfcc).max() <= MFCC_TOL
+    # (i) stage 2 alone, fed the oracle's MFCC image: exact masks
+    e2, m2 = path.energy(want_mfcc, normalize_first=True)
+    want_e, want_m = oracle.energy_stage(want_mfcc, normalize_first=True)
+    assert (m2 != want_m).sum() == 0
+    # (ii) end to end
+    flips = _mask_report('chain', energy, mean, mask, want_m)
+    print('end-to-end mask disagreements: %d of %d pixels' % (flips, mask.size))
+    assert flips <= 0.002 * mask.size
+    rel = np.abs(energy - want_e).max() / np.abs(want_e).max()
+    print('end-to-end energy max rel err %.3e' % rel)
+    assert rel <= 1e-3
+    # device in / device out gives the same bits as host in / host out
+    d = path.mfcc_energy(torch.from_numpy(power).cuda(), flip=True, normalize_first=True)
+    assert np.array_equal(d[0].cpu().numpy(), mfcc) and np.array_equal(d[1].cpu().numpy(), energy)
+    assert np.array_equal(d[2].cpu().numpy(), mask)
+
+
+def test_launch_counter_counts_kernels(path):
+    before = path.launch_count
+    path.energy(synth.sigmoid_images(1, 0))
+    assert path.launch_count == before + 1
