@@ -93,7 +93,8 @@ SIGNATURES = {
     'aig_ciou_sweep': (_int, [_p, _p, _p, _p, _p, _p, _i64, _int, _int, _p, _int, _p, _p, _p, _p]),
     'aig_auc': (_int, [_p, _p, _int, _p]),
     'aig_launch_count': (_i64, [_p]),
-    'aig_set_mfcc_variant': (_int, [_p, _int]),
+    'aig_set_option': (_int, [_p, ctypes.c_char_p, _i64]),
+    'aig_profile_read': (_int, [_p, _p, _p]),
 }
 
 _lib = None

@@ -126,8 +126,19 @@ class AcousticPath:
     def launch_count(self):
         return int(self._lib.aig_launch_count(self._h))
 
+    def set_option(self, name, value):
+        """Tuning / instrumentation knobs of include/aig.h: mfcc_variant, chain_chunk_frames, chain_overlap, profile."""
+        self._check(self._lib.aig_set_option(self._h, name.encode(), int(value)))
+
     def set_mfcc_variant(self, variant):
-        self._check(self._lib.aig_set_mfcc_variant(self._h, int(variant)))
+        self.set_option('mfcc_variant', variant)
+
+    def profile_read(self):
+        """{'mfcc': (ms, launches), 'energy': (...), 'other': (...)} gathered since the last read (needs profile=1)."""
+        ms = (ctypes.c_double * 3)()
+        cnt = (ctypes.c_int64 * 3)()
+        self._check(self._lib.aig_profile_read(self._h, ms, cnt))
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(('mfcc', 'energy', 'other'))}
 
     def _empty(self, shape, dtype, like):
         """Output buffer on the side the input lives on."""
@@ -252,21 +263,60 @@ class AcousticPath:
         self._check(self._lib.aig_resize_mask(self._h, a.ptr, n, int(out_h), int(out_w), _Arg(res, np.uint8, True).ptr))
         return res
 
-    def mfcc_energy(self, power, flip=False, normalize_first=True, want_mean=False):
-        """Stages 1 + 2 chained on the device: [N,36,48,512] f32 -> (mfcc f32 [N,36,48,12], energy f64, mask u8)."""
+    def mfcc_energy(self, power, flip=False, normalize_first=True, want_mean=False, out=None):
+        """Stages 1 + 2 chained on the device: [N,36,48,512] f32 -> (mfcc f32 [N,36,48,12], energy f64, mask u8).
+
+        ``out=(mfcc, energy, mask)`` supplies the result buffers (e.g. pinned host arrays, or device tensors
+        reused across calls) instead of allocating them."""
         a = _Arg(power, np.float32)
         n = self._frames(a.shape, FRAME_PIXELS * FFT_LEN)
-        mfcc = self._empty((n, FRAME_H, FRAME_W, MFCC_NUM), np.float32, a)
-        energy = self._empty((n, FRAME_H, FRAME_W), np.float64, a)
-        mask = self._empty((n, FRAME_H, FRAME_W), np.uint8, a)
+        if out is not None:
+            mfcc, energy, mask = out
+        else:
+            mfcc = self._empty((n, FRAME_H, FRAME_W, MFCC_NUM), np.float32, a)
+            energy = self._empty((n, FRAME_H, FRAME_W), np.float64, a)
+            mask = self._empty((n, FRAME_H, FRAME_W), np.uint8, a)
+        o_mfcc, o_energy, o_mask = _Arg(mfcc, np.float32, True), _Arg(energy, np.float64, True), _Arg(mask, np.uint8, True)
+        if (int(np.prod(o_mfcc.shape)), int(np.prod(o_energy.shape)), int(np.prod(o_mask.shape))) != (
+                n * FRAME_PIXELS * MFCC_NUM, n * FRAME_PIXELS, n * FRAME_PIXELS):
+            raise ValueError('out buffers do not match %d frames' % n)
         mean = self._empty((n,), np.float64, a) if want_mean else None
         self._check(self._lib.aig_mfcc_energy(
-            self._h, a.ptr, n, int(bool(flip)), int(bool(normalize_first)), _Arg(mfcc, np.float32, True).ptr,
-            _Arg(energy, np.float64, True).ptr, _Arg(mask, np.uint8, True).ptr,
+            self._h, a.ptr, n, int(bool(flip)), int(bool(normalize_first)), o_mfcc.ptr, o_energy.ptr, o_mask.ptr,
             _Arg(mean, np.float64, True).ptr if want_mean else None))
         return (mfcc, energy, mask) + ((mean,) if want_mean else ())
 
     # -- stage 3 ------------------------------------------------------------------------------
+    @staticmethod
+    def _thresholds(thresholds):
+        """Threshold vector as a float64 buffer: NumPy (host) or a CUDA tensor kept on the device."""
+        if _is_torch(thresholds):
+            arg = _Arg(thresholds, np.float64)
+        else:
+            arg = _Arg(np.ascontiguousarray(thresholds, dtype=np.float64), np.float64)
+        if len(arg.shape) != 1:
+            raise ValueError('thresholds must be a vector')
+        return arg
+
+    @staticmethod
+    def _counters(thr, pos, num):
+        """(pos, num) accumulators: NumPy by default, or caller-supplied int64 arrays / CUDA tensors
+        (device-resident counters let a whole evaluation run without touching the host)."""
+        if pos is None:
+            pos = np.zeros(thr.shape[0], np.int64)
+        elif not _is_torch(pos):
+            pos = np.ascontiguousarray(pos, dtype=np.int64)
+        if num is None or isinstance(num, (int, np.integer)):
+            num = np.array([0 if num is None else int(num)], np.int64)
+        p, c = _Arg(pos, np.int64, True), _Arg(num, np.int64, True)
+        if int(np.prod(p.shape)) != thr.shape[0] or int(np.prod(c.shape)) != 1:
+            raise ValueError('pos must hold one int64 per threshold and num exactly one int64')
+        return pos, num, p, c
+
+    @staticmethod
+    def _num_result(num):
+        return int(num[0]) if isinstance(num, np.ndarray) else num
+
     def iou_sweep(self, mask_a, mask_b, thresholds=REFERENCE_THRESHOLDS, pos=None, num=None):
         """Mask IoU and success counts (iouenergythreshold.py:224-229) for all thresholds at once.
 
@@ -276,15 +326,14 @@ class AcousticPath:
         n = self._frames(a.shape, FRAME_PIXELS)
         if self._frames(b.shape, FRAME_PIXELS) != n:
             raise ValueError('mask batches differ: %s vs %s' % (a.shape, b.shape))
-        thr = np.ascontiguousarray(thresholds, dtype=np.float64)
-        pos = np.zeros(len(thr), np.int64) if pos is None else np.ascontiguousarray(pos, dtype=np.int64)
-        cnt = np.array([0 if num is None else int(num)], np.int64)
+        thr = self._thresholds(thresholds)
+        pos, cnt, p_arg, c_arg = self._counters(thr, pos, num)
         inter = self._empty((n,), np.int64, a)
         union = self._empty((n,), np.int64, a)
-        self._check(self._lib.aig_iou_sweep(self._h, a.ptr, b.ptr, n, thr.ctypes.data, len(thr),
+        self._check(self._lib.aig_iou_sweep(self._h, a.ptr, b.ptr, n, thr.ptr, thr.shape[0],
                                             _Arg(inter, np.int64, True).ptr, _Arg(union, np.int64, True).ptr,
-                                            pos.ctypes.data, cnt.ctypes.data))
-        return inter, union, pos, int(cnt[0])
+                                            p_arg.ptr, c_arg.ptr))
+        return inter, union, pos, self._num_result(cnt)
 
     def ciou_sweep(self, mask, xmin, xmax, ymin, ymax, thresholds=REFERENCE_THRESHOLDS,
                    out_hw=(HEAT_H, HEAT_W), pos=None, num=None):
@@ -297,16 +346,15 @@ class AcousticPath:
         for bx in boxes:
             if int(np.prod(bx.shape)) != 3 * n:
                 raise ValueError('boxes must be [n, 3] int32, got %s for n=%d' % (bx.shape, n))
-        thr = np.ascontiguousarray(thresholds, dtype=np.float64)
-        pos = np.zeros(len(thr), np.int64) if pos is None else np.ascontiguousarray(pos, dtype=np.int64)
-        cnt = np.array([0 if num is None else int(num)], np.int64)
+        thr = self._thresholds(thresholds)
+        pos, cnt, p_arg, c_arg = self._counters(thr, pos, num)
         inter2 = self._empty((n,), np.int64, a)
         union2 = self._empty((n,), np.int64, a)
         self._check(self._lib.aig_ciou_sweep(self._h, a.ptr, boxes[0].ptr, boxes[1].ptr, boxes[2].ptr, boxes[3].ptr,
-                                             n, int(out_hw[0]), int(out_hw[1]), thr.ctypes.data, len(thr),
+                                             n, int(out_hw[0]), int(out_hw[1]), thr.ptr, thr.shape[0],
                                              _Arg(inter2, np.int64, True).ptr, _Arg(union2, np.int64, True).ptr,
-                                             pos.ctypes.data, cnt.ctypes.data))
-        return inter2, union2, pos, int(cnt[0])
+                                             p_arg.ptr, c_arg.ptr))
+        return inter2, union2, pos, self._num_result(cnt)
 
 
 def auc(thresholds, values):

@@ -81,6 +81,17 @@ struct aig_handle {
     char* arena = nullptr;
     size_t arena_cap = 0, arena_off = 0;
     std::vector<std::pair<void*, size_t>> overflow;
+    // chained MFCC -> energy pipeline
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_chain[4] = {nullptr, nullptr, nullptr, nullptr};   // start, mfcc[2], energy-done
+    int chain_chunk_frames = 512;
+    bool chain_overlap = true;
+    int chain_energy_ctas_per_sm = 3;   // footprint of the overlapped energy kernel (measured: profiles/r01_tune_chain.txt)
+    // profiling: (start, stop) event pairs per launch, by kernel kind
+    bool profile = false;
+    struct Span { cudaEvent_t start, stop; int kind; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
     // misc
     int variant = -1;
     int64_t launches = 0;
@@ -202,12 +213,43 @@ struct Io {
     }
 };
 
-int check_launch(aig_handle* h, const char* name) {
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return h->fail_cuda(e, name);
-    h->launches += 1;
-    return AIG_OK;
+enum KernelKind { kKindMfcc = 0, kKindEnergy = 1, kKindOther = 2 };
+
+cudaEvent_t pooled_event(aig_handle* h) {
+    if (!h->event_pool.empty()) {
+        cudaEvent_t e = h->event_pool.back();
+        h->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
 }
+
+// Brackets one launch with events on the launching stream when profiling is on.
+struct LaunchScope {
+    aig_handle* h;
+    cudaStream_t stream;
+    cudaEvent_t start = nullptr;
+    int kind;
+    LaunchScope(aig_handle* handle, cudaStream_t s, int k) : h(handle), stream(s), kind(k) {
+        if (h->profile) {
+            start = pooled_event(h);
+            cudaEventRecord(start, stream);
+        }
+    }
+    int done(const char* name) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return h->fail_cuda(e, name);
+        h->launches += 1;
+        if (start) {
+            cudaEvent_t stop = pooled_event(h);
+            cudaEventRecord(stop, stream);
+            h->spans.push_back({start, stop, kind});
+        }
+        return AIG_OK;
+    }
+};
 
 int frames_grid(const aig_handle* h, int64_t n_frames, int per_sm) {
     return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_frames, static_cast<int64_t>(h->sm_count) * per_sm)));
@@ -230,7 +272,7 @@ constexpr Variant kVariants[kNumVariants] = {
     {256, 1, 4, 1},    // 8: 256-spectrum tiles
     {128, 1, 6, 2},    // 9: run-time ring index (6 does not divide 16)
 };
-constexpr int kDefaultVariant = 0;
+constexpr int kDefaultVariant = 0;   // best for the chained pass on B200 (profiles/r01_tune_chain.txt); 5 is best for MFCC alone
 
 template <int V>
 int launch_banded_variant(aig_handle* h, const CUtensorMap& map, float* out, unsigned n_rows, int flip180,
@@ -244,8 +286,9 @@ int launch_banded_variant(aig_handle* h, const CUtensorMap& map, float* out, uns
     }
     const unsigned n_tiles = (n_rows + v.rows - 1) / v.rows;
     const unsigned grid = std::min<unsigned>(n_tiles, static_cast<unsigned>(h->sm_count * v.ctas));
+    LaunchScope scope(h, h->stream, kKindMfcc);
     kernel<<<grid, P::kThreads, P::kSmemBytes, h->stream>>>(map, out, n_rows, n_tiles, flip180, frame_pixels);
-    return check_launch(h, "mfcc_banded_kernel");
+    return scope.done("mfcc_banded_kernel");
 }
 
 int encode_spectrum_map(aig_handle* h, const float* d_power, uint64_t n_rows, int box_rows, CUtensorMap* map) {
@@ -269,10 +312,11 @@ int launch_mfcc(aig_handle* h, const float* d_power, int64_t n_rows, float* d_ou
         const double* lifter = dct + static_cast<size_t>(h->filter_num) * h->mfcc_num;
         const int64_t blocks = std::min<int64_t>((n_rows + kGenericWarps - 1) / kGenericWarps,
                                                  static_cast<int64_t>(h->sm_count) * 8);
+        LaunchScope scope(h, h->stream, kKindMfcc);
         mfcc_generic_kernel<<<static_cast<unsigned>(blocks), kGenericWarps * 32, 0, h->stream>>>(
             d_power, n_rows, h->fft_len, h->filter_num, h->mfcc_num, bank, dct, lifter, h->mfnorm, d_out, flip180,
             frame_pixels);
-        return check_launch(h, "mfcc_generic_kernel");
+        return scope.done("mfcc_generic_kernel");
     }
     if ((reinterpret_cast<uintptr_t>(d_power) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u))
         return h->fail(AIG_ERR_ARGUMENT, "aig_mfcc: device buffers must be 16-byte aligned");
@@ -305,12 +349,13 @@ int launch_mfcc(aig_handle* h, const float* d_power, int64_t n_rows, float* d_ou
     return AIG_OK;
 }
 
-int launch_energy(aig_handle* h, const float* d_images, int64_t n_frames, int normalize_first, float* d_scaled,
-                  double* d_energy, uint8_t* d_mask, double* d_mean) {
+int launch_energy(aig_handle* h, cudaStream_t stream, const float* d_images, int64_t n_frames, int normalize_first,
+                  float* d_scaled, double* d_energy, uint8_t* d_mask, double* d_mean, int ctas_per_sm = 8) {
     if (n_frames == 0) return AIG_OK;
-    energy_kernel<<<frames_grid(h, n_frames, 8), kEnergyThreads, 0, h->stream>>>(
+    LaunchScope scope(h, stream, kKindEnergy);
+    energy_kernel<<<frames_grid(h, n_frames, ctas_per_sm), kEnergyThreads, 0, stream>>>(
         d_images, n_frames, normalize_first, d_scaled, d_energy, d_mask, d_mean);
-    return check_launch(h, "energy_kernel");
+    return scope.done("energy_kernel");
 }
 
 int require(aig_handle* h) {
@@ -403,7 +448,9 @@ int aig_create(int device, uint64_t stream, aig_handle** out) {
         return AIG_ERR_NO_DEVICE;
     }
     h->encode = reinterpret_cast<EncodeTiledFn>(fn);
-    bool ok = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    bool ok = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&h->ev_chain[i], cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) {
         ok = cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
@@ -423,6 +470,10 @@ int aig_destroy(aig_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
+    for (int i = 0; i < 4; ++i) if (h->ev_chain[i]) cudaEventDestroy(h->ev_chain[i]);
+    for (auto& sp : h->spans) { cudaEventDestroy(sp.start); cudaEventDestroy(sp.stop); }
+    for (auto& e : h->event_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
         if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
@@ -440,15 +491,51 @@ int aig_synchronize(aig_handle* h) {
     AIG_CK(cudaSetDevice(h->device));
     AIG_CK(cudaStreamSynchronize(h->copy_stream));
     AIG_CK(cudaStreamSynchronize(h->stream));
+    AIG_CK(cudaStreamSynchronize(h->aux_stream));
     return AIG_OK;
 }
 
 int64_t aig_launch_count(const aig_handle* h) { return h ? h->launches : -1; }
 
-int aig_set_mfcc_variant(aig_handle* h, int variant) {
-    if (h == nullptr) return AIG_ERR_ARGUMENT;
-    if (variant < -1 || variant >= kNumVariants) return h->fail(AIG_ERR_ARGUMENT, "unknown MFCC kernel variant %d", variant);
-    h->variant = variant;
+int aig_set_option(aig_handle* h, const char* name, int64_t value) {
+    if (h == nullptr || name == nullptr) return AIG_ERR_ARGUMENT;
+    const std::string key(name);
+    if (key == "mfcc_variant") {
+        if (value < -1 || value >= kNumVariants) return h->fail(AIG_ERR_ARGUMENT, "unknown MFCC kernel variant %lld", (long long)value);
+        h->variant = static_cast<int>(value);
+    } else if (key == "chain_chunk_frames") {
+        if (value < 1 || value > (1 << 20)) return h->fail(AIG_ERR_ARGUMENT, "chain_chunk_frames out of range");
+        h->chain_chunk_frames = static_cast<int>(value);
+    } else if (key == "chain_overlap") {
+        h->chain_overlap = value != 0;
+    } else if (key == "chain_energy_ctas_per_sm") {
+        if (value < 1 || value > 16) return h->fail(AIG_ERR_ARGUMENT, "chain_energy_ctas_per_sm out of range");
+        h->chain_energy_ctas_per_sm = static_cast<int>(value);
+    } else if (key == "profile") {
+        h->profile = value != 0;
+    } else {
+        return h->fail(AIG_ERR_ARGUMENT, "unknown option '%s'", name);
+    }
+    return AIG_OK;
+}
+
+int aig_profile_read(aig_handle* h, double* ms_out, int64_t* launches_out) {
+    if (h == nullptr || ms_out == nullptr || launches_out == nullptr) return AIG_ERR_ARGUMENT;
+    int rc = aig_synchronize(h);
+    if (rc != AIG_OK) return rc;
+    for (int k = 0; k < 3; ++k) { ms_out[k] = 0.0; launches_out[k] = 0; }
+    for (auto& sp : h->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.start, sp.stop) == cudaSuccess) {
+            ms_out[sp.kind] += ms;
+            launches_out[sp.kind] += 1;
+        } else {
+            cudaGetLastError();
+        }
+        h->event_pool.push_back(sp.start);
+        h->event_pool.push_back(sp.stop);
+    }
+    h->spans.clear();
     return AIG_OK;
 }
 
@@ -534,8 +621,9 @@ int aig_normalize_images(aig_handle* h, const float* images, int64_t n_frames, f
     const float* d_in = io.in(images, count);
     float* d_out = io.out(out, count);
     if (io.failed) return io.finish();
+    LaunchScope scope(h, h->stream, kKindOther);
     normalize_kernel<<<frames_grid(h, n_frames, 8), 256, 0, h->stream>>>(d_in, n_frames, d_out);
-    rc = check_launch(h, "normalize_kernel");
+    rc = scope.done("normalize_kernel");
     if (rc != AIG_OK) return rc;
     return io.finish();
 }
@@ -554,7 +642,7 @@ int aig_energy(aig_handle* h, const float* images, int64_t n_frames, int normali
     uint8_t* d_mask = io.out(mask_out, n * kFramePixels);
     double* d_mean = io.out(mean_out, n);
     if (io.failed) return io.finish();
-    rc = launch_energy(h, d_in, n_frames, normalize_first, d_scaled, d_energy, d_mask, d_mean);
+    rc = launch_energy(h, h->stream, d_in, n_frames, normalize_first, d_scaled, d_energy, d_mask, d_mean);
     if (rc != AIG_OK) return rc;
     return io.finish();
 }
@@ -572,8 +660,9 @@ int aig_heatmap(aig_handle* h, const double* energy, int64_t n_frames, int out_h
     float* d_heat = io.out(heat_out, n * out_h * out_w);
     if (io.failed) return io.finish();
     const size_t smem = static_cast<size_t>(out_w + out_h) * (sizeof(double) + sizeof(int));
+    LaunchScope scope(h, h->stream, kKindOther);
     heatmap_kernel<<<frames_grid(h, n_frames, 4), kHeatThreads, smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);
-    rc = check_launch(h, "heatmap_kernel");
+    rc = scope.done("heatmap_kernel");
     if (rc != AIG_OK) return rc;
     return io.finish();
 }
@@ -591,8 +680,9 @@ int aig_resize_mask(aig_handle* h, const uint8_t* mask, int64_t n_frames, int ou
     uint8_t* d_up = io.out(mask_up, n * out_h * out_w);
     if (io.failed) return io.finish();
     const size_t smem = static_cast<size_t>(out_w + out_h) * 2 * sizeof(int);
+    LaunchScope scope(h, h->stream, kKindOther);
     resize_mask_kernel<<<frames_grid(h, n_frames, 4), kHeatThreads, smem, h->stream>>>(d_mask, n_frames, out_h, out_w, d_up);
-    rc = check_launch(h, "resize_mask_kernel");
+    rc = scope.done("resize_mask_kernel");
     if (rc != AIG_OK) return rc;
     return io.finish();
 }
@@ -613,12 +703,35 @@ int aig_mfcc_energy(aig_handle* h, const float* power, int64_t n_frames, int fli
     uint8_t* d_mask = io.out(mask_out, n * kFramePixels);
     double* d_mean = io.out(mean_out, n);
     if (io.failed) return io.finish();
+    // The energy kernel is FP64-compute-bound and touches 2 % of the bytes; the MFCC kernel is HBM-bound
+    // and leaves the FP64 pipe idle.  Run them chunk-wise on two streams so that the energy kernel of
+    // chunk i executes underneath the MFCC kernel of chunk i+1 (its input is still in L2).
+    const bool overlap = h->chain_overlap;
+    cudaStream_t energy_stream = overlap ? h->aux_stream : h->stream;
+    if (overlap) {
+        AIG_CK(cudaEventRecord(h->ev_chain[0], h->stream));              // order after earlier work
+        AIG_CK(cudaStreamWaitEvent(h->aux_stream, h->ev_chain[0], 0));
+    }
+    int64_t chunk_index = 0;
     auto run = [&](const float* d_power, int64_t frame0, int64_t frames) -> int {
-        float* mf = d_mfcc + frame0 * kFrameValues;
-        int r = launch_mfcc(h, d_power, frames * kFramePixels, mf, flip180, kFramePixels);
-        if (r != AIG_OK) return r;
-        return launch_energy(h, mf, frames, normalize_first, nullptr, d_energy ? d_energy + frame0 * kFramePixels : nullptr,
-                             d_mask ? d_mask + frame0 * kFramePixels : nullptr, d_mean ? d_mean + frame0 : nullptr);
+        for (int64_t f = 0; f < frames; f += h->chain_chunk_frames, ++chunk_index) {
+            const int64_t cf = std::min<int64_t>(h->chain_chunk_frames, frames - f);
+            const int64_t g = frame0 + f;
+            float* mf = d_mfcc + g * kFrameValues;
+            int r = launch_mfcc(h, d_power + f * kFramePixels * kFftLen, cf * kFramePixels, mf, flip180, kFramePixels);
+            if (r != AIG_OK) return r;
+            if (overlap) {
+                cudaEvent_t ev = h->ev_chain[1 + (chunk_index & 1)];
+                AIG_CK(cudaEventRecord(ev, h->stream));
+                AIG_CK(cudaStreamWaitEvent(energy_stream, ev, 0));
+            }
+            r = launch_energy(h, energy_stream, mf, cf, normalize_first, nullptr,
+                              d_energy ? d_energy + g * kFramePixels : nullptr,
+                              d_mask ? d_mask + g * kFramePixels : nullptr, d_mean ? d_mean + g : nullptr,
+                              overlap ? h->chain_energy_ctas_per_sm : 8);
+            if (r != AIG_OK) return r;
+        }
+        return AIG_OK;
     };
     if (in_dev) {
         rc = run(power, 0, n_frames);
@@ -631,28 +744,16 @@ int aig_mfcc_energy(aig_handle* h, const float* power, int64_t n_frames, int fli
                               });
     }
     if (rc != AIG_OK) return rc;
+    if (overlap) {
+        AIG_CK(cudaEventRecord(h->ev_chain[3], h->aux_stream));          // results visible to the handle's stream
+        AIG_CK(cudaStreamWaitEvent(h->stream, h->ev_chain[3], 0));
+    }
     return io.finish();
 }
 
 static int check_sweep_args(aig_handle* h, const char* who, int64_t n, const double* thr, int k, int64_t* pos, int64_t* num) {
     if (n < 0 || k < 0 || k > kMaxThresholds) return h->fail(AIG_ERR_ARGUMENT, "%s: n=%lld k=%d out of range (k <= %d)", who, (long long)n, k, kMaxThresholds);
     if ((k > 0 && (!thr || !pos)) || !num) return h->fail(AIG_ERR_ARGUMENT, "%s: null threshold / count buffers", who);
-    return AIG_OK;
-}
-
-// num += n on whichever side the counter lives
-static int add_num(aig_handle* h, Io& io, int64_t* num, int64_t n) {
-    if (classify(num) == kDevice) {
-        int64_t cur = 0;
-        AIG_CK(cudaMemcpyAsync(&cur, num, sizeof cur, cudaMemcpyDeviceToHost, h->stream));
-        AIG_CK(cudaStreamSynchronize(h->stream));
-        cur += n;
-        AIG_CK(cudaMemcpyAsync(num, &cur, sizeof cur, cudaMemcpyHostToDevice, h->stream));
-        AIG_CK(cudaStreamSynchronize(h->stream));
-    } else {
-        *num += n;
-    }
-    (void)io;
     return AIG_OK;
 }
 
@@ -672,18 +773,19 @@ int aig_iou_sweep(aig_handle* h, const uint8_t* mask_a, const uint8_t* mask_b, i
     int64_t* d_inter = io.out(inter_out, cnt);
     int64_t* d_union = io.out(union_out, cnt);
     int64_t* d_pos = io.inout(pos_inout, static_cast<size_t>(k));
+    int64_t* d_num = io.inout(num_inout, 1);
     if (io.failed) return io.finish();
     if ((reinterpret_cast<uintptr_t>(d_a) & 3u) || (reinterpret_cast<uintptr_t>(d_b) & 3u))
         return h->fail(AIG_ERR_ARGUMENT, "aig_iou_sweep: mask buffers must be 4-byte aligned");
     const int blocks = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 4));
+    LaunchScope scope(h, h->stream, kKindOther);
     iou_sweep_kernel<<<blocks, kIouThreads, 0, h->stream>>>(d_a, d_b, n, d_thr, k, reinterpret_cast<long long*>(d_inter),
                                                             reinterpret_cast<long long*>(d_union),
-                                                            reinterpret_cast<unsigned long long*>(d_pos));
-    rc = check_launch(h, "iou_sweep_kernel");
+                                                            reinterpret_cast<unsigned long long*>(d_pos),
+                                                            reinterpret_cast<unsigned long long*>(d_num));
+    rc = scope.done("iou_sweep_kernel");
     if (rc != AIG_OK) return rc;
-    rc = io.finish();
-    if (rc != AIG_OK) return rc;
-    return add_num(h, io, num_inout, n);
+    return io.finish();
 }
 
 int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, const int32_t* xmax, const int32_t* ymin,
@@ -708,16 +810,17 @@ int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, cons
     int64_t* d_inter = io.out(inter2_out, cnt);
     int64_t* d_union = io.out(union2_out, cnt);
     int64_t* d_pos = io.inout(pos_inout, static_cast<size_t>(k));
+    int64_t* d_num = io.inout(num_inout, 1);
     if (io.failed) return io.finish();
     const size_t smem = static_cast<size_t>(out_w + out_h) * 2 * sizeof(int);
+    LaunchScope scope(h, h->stream, kKindOther);
     ciou_sweep_kernel<<<frames_grid(h, n, 4), kIouThreads, smem, h->stream>>>(
         d_mask, d_xmin, d_xmax, d_ymin, d_ymax, n, out_h, out_w, d_thr, k, reinterpret_cast<long long*>(d_inter),
-        reinterpret_cast<long long*>(d_union), reinterpret_cast<unsigned long long*>(d_pos));
-    rc = check_launch(h, "ciou_sweep_kernel");
+        reinterpret_cast<long long*>(d_union), reinterpret_cast<unsigned long long*>(d_pos),
+        reinterpret_cast<unsigned long long*>(d_num));
+    rc = scope.done("ciou_sweep_kernel");
     if (rc != AIG_OK) return rc;
-    rc = io.finish();
-    if (rc != AIG_OK) return rc;
-    return add_num(h, io, num_inout, n);
+    return io.finish();
 }
 
 int aig_auc(const double* thr, const double* value, int k, double* auc_out) {

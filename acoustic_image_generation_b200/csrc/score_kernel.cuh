@@ -22,10 +22,12 @@ constexpr int kMaskWords = kFramePixels / 4;     // 432 x 4 bytes
 __global__ void __launch_bounds__(kIouThreads)
 iou_sweep_kernel(const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__ mask_b, long long n,
                  const double* __restrict__ thr, int k_thr, long long* __restrict__ inter_out,
-                 long long* __restrict__ union_out, unsigned long long* __restrict__ pos) {
+                 long long* __restrict__ union_out, unsigned long long* __restrict__ pos,
+                 unsigned long long* __restrict__ num) {
     __shared__ unsigned int s_pos[kMaxThresholds];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int k = tid; k < k_thr; k += kIouThreads) s_pos[k] = 0;
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(num, static_cast<unsigned long long>(n));   // num += 1 per frame (:229)
     __syncthreads();
     const long long warps_total = static_cast<long long>(gridDim.x) * (kIouThreads / 32);
     for (long long f = static_cast<long long>(blockIdx.x) * (kIouThreads / 32) + warp; f < n; f += warps_total) {
@@ -58,7 +60,8 @@ __global__ void __launch_bounds__(kIouThreads)
 ciou_sweep_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ xmin, const int* __restrict__ xmax,
                   const int* __restrict__ ymin, const int* __restrict__ ymax, long long n, int out_h, int out_w,
                   const double* __restrict__ thr, int k_thr, long long* __restrict__ inter2_out,
-                  long long* __restrict__ union2_out, unsigned long long* __restrict__ pos) {
+                  long long* __restrict__ union2_out, unsigned long long* __restrict__ pos,
+                  unsigned long long* __restrict__ num) {
     extern __shared__ int s_taps[];
     __shared__ unsigned int s_pos[kMaxThresholds];
     __shared__ uint8_t s_mask[kFramePixels];
@@ -71,6 +74,7 @@ ciou_sweep_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ xmin
     int* s_yn = s_y0 + out_h;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int k = tid; k < k_thr; k += kIouThreads) s_pos[k] = 0;
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(num, static_cast<unsigned long long>(n));   // num += 1 per frame (:321)
     for (int d = tid; d < out_w; d += kIouThreads) {
         int i0, i1, r; linear_tap_exact(d, kFrameW, out_w, &i0, &i1, &r);
         s_x0[d] = i0 | (i1 << 16); s_xn[d] = r;

@@ -1,0 +1,345 @@
+"""Headline benchmark: acoustic frames/s through MFCC compression + energy heat map (+ mask and IoU
+success counts) on synthetic ACIVW-shaped data - BASELINE.json's metric on configs[1].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames B] [--impl reference]
+
+One "step" is one pass of the hot path over one batch of B resident frames (default 8192 frames =
+29 GB of float32 spectra per GPU, far larger than the 126 MB L2, so every step streams from HBM):
+stage 1+2 chained (aig_mfcc_energy: fused MFCC kernel + energy/mask kernel) and the stage-3 IoU sweep of
+the first half of the batch against the second half (11 thresholds, device-resident counters).  At N > 1
+every rank runs the same per-GPU workload on its own GPU (weak scaling; frames shard trivially) and the
+only exchange is one NCCL all-reduce of the int64[K+1] count vector inside the timed region.
+
+Prints ONE JSON line (rank 0).  `value` is the whole-job frames/s with inputs resident in HBM; `e2e` is
+the same metric through the public host API (pinned NumPy in, pinned NumPy out, H2D/D2H inside the timed
+region); `roofline` reports the fused MFCC kernel's algorithmic GB/s (event-timed per launch inside the
+timed region) against the measured HBM peak; `cpu_baseline` times the oracle port of the reference's
+NumPy path on this box's host cores (rank 0, N = 1).  `--impl reference` runs only that CPU arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'acoustic frames/sec (36x48x512->MFCC+energy)'
+UNIT = 'frames/s'
+FRAME_PIXELS, FFT_LEN, MFCC_NUM = 1728, 512, 12
+IN_BYTES = FRAME_PIXELS * FFT_LEN * 4                    # 3 538 944 B of spectra per frame
+MFCC_BYTES = FRAME_PIXELS * MFCC_NUM * 4                 # 82 944 B MFCC image per frame
+ALGO_BYTES_MFCC_KERNEL = IN_BYTES + MFCC_BYTES           # what the fused MFCC kernel must move per frame
+ALGO_BYTES_PATH = IN_BYTES + MFCC_BYTES + FRAME_PIXELS * 4   # 3 628 800 B per frame, MFCC + energy
+THRESHOLDS = (0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0)
+CPU_SAMPLE_FRAMES = 16                                   # BASELINE.json configs[0]
+
+
+def workload_config(frames, n_gpus):
+    return {
+        'workload': 'configs[1]: MFCC compression + energy heatmap, synthetic ACIVW frames 36x48x512 f32, '
+                    '%d resident frames per step per GPU (%.1f GB > L2), + mean mask + IoU sweep (11 thresholds)'
+                    % (frames, frames * IN_BYTES / 1e9),
+        'frames_per_step_per_gpu': frames,
+        'flip180': True,
+        'normalize_first': True,
+        'l2': 'inputs larger than L2 (no flush needed)',
+        'parallelism': 'frames sharded by rank, dp%d, one NCCL all-reduce of int64[12] per run' % n_gpus,
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's NumPy path (test infrastructure used as the baseline)
+# --------------------------------------------------------------------------------------------------
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        counts = [p.get('num_threads', 1) for p in threadpool_info() if p.get('user_api') == 'blas']
+        if counts:
+            return int(max(counts))
+    except Exception:
+        pass
+    return int(os.cpu_count() or 1)
+
+
+def cpu_chain(oracle, power):
+    """The reference path on the host for one sample: get_feats -> flip -> min-max -> find_logen -> mask -> IoU -> counts."""
+    mfcc = oracle.mfcc_image(power, flip=True)
+    energy, mask = oracle.energy_stage(mfcc, normalize_first=True)
+    half = len(mask) // 2
+    scores = [oracle.iou_pair(a, b)[2] for a, b in zip(mask[:half], mask[half:])]
+    return oracle.success_counts(scores, THRESHOLDS)
+
+
+def time_cpu(steps, warmup, budget_s=None):
+    from acoustic_image_generation_b200 import synth
+    from oracle import acoustic_oracle as oracle
+    power = synth.power_frames(CPU_SAMPLE_FRAMES, 0, 'chi2')
+    for _ in range(warmup):
+        cpu_chain(oracle, power)
+    times = []
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_chain(oracle, power)
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_all > budget_s and len(times) >= 3:
+            break
+    total = sum(times)
+    return {
+        'value': CPU_SAMPLE_FRAMES * len(times) / total,
+        'unit': UNIT,
+        'cores': blas_threads(),
+        'kind': 'port',
+        'sample': '%d x %d-frame batches (BASELINE configs[0]) through the NumPy oracle port of get_feats/'
+                  'find_logen/IoU, %.1f s, median %.1f ms per batch, host cpu_count=%s'
+                  % (len(times), CPU_SAMPLE_FRAMES, total, 1e3 * statistics.median(times), os.cpu_count()),
+    }, len(times), total
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    base, steps_done, total = time_cpu(args.steps, max(args.warmup, 1))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': steps_done, 'warmup': max(args.warmup, 1), 'ms_per_step': 1e3 * total / steps_done,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': dict(workload_config(args.frames, args.gpus),
+                       note='CPU arm: each step is a bounded %d-frame sample of the same workload' % CPU_SAMPLE_FRAMES),
+        'cpu_baseline': base,
+        'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (NVML) for the timed region
+# --------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown',
+               0x10: 'sync_boost', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+               0x80: 'hw_power_brake_slowdown', 0x100: 'display_clock_setting'}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.mask, self.max_mhz, self.stop_flag, self.ok = index, [], 0, None, False, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:                                    # CUDA ordinal -> NVML device through the UUID
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith('GPU-') else 'GPU-' + uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.handle, self.nv.NVML_CLOCK_SM)))
+                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                break
+            time.sleep(0.01)
+
+    def result(self):
+        self.stop_flag = True
+        if self.ok:
+            self.join(timeout=1.0)
+        reasons = [name for bit, name in self.REASONS.items() if self.mask & bit and name != 'gpu_idle']
+        return {'sm_mhz': statistics.median(self.samples) if self.samples else None, 'sm_max_mhz': self.max_mhz,
+                'reasons': reasons, 'samples': len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import acoustic_image_generation_b200 as aig
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    path = aig.AcousticPath(local, stream=stream.cuda_stream)
+    frames = args.frames
+    # synthetic spectra generated on the device, chi-square like synth.power_frames (squared normal), seeded per rank
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    power = torch.empty((frames, 36, 48, FFT_LEN), device=dev, dtype=torch.float32)
+    for f0 in range(0, frames, 256):
+        blk = power[f0:f0 + 256]
+        blk.normal_(generator=gen)
+        blk.square_()
+    mfcc = torch.empty((frames, 36, 48, MFCC_NUM), device=dev, dtype=torch.float32)
+    energy = torch.empty((frames, 36, 48), device=dev, dtype=torch.float64)
+    mask = torch.empty((frames, 36, 48), device=dev, dtype=torch.uint8)
+    thr = torch.tensor(THRESHOLDS, device=dev, dtype=torch.float64)
+    counts = torch.zeros(len(THRESHOLDS) + 1, device=dev, dtype=torch.int64)   # pos[0..K-1], num
+    half = frames // 2
+
+    def step():
+        path.mfcc_energy(power, flip=True, normalize_first=True, out=(mfcc, energy, mask))
+        path.iou_sweep(mask[:half], mask[half:2 * half], thr, pos=counts[:-1], num=counts[-1:])
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    counts.zero_()
+    path.set_option('profile', 1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = path.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    if world > 1:
+        dist.all_reduce(counts)                     # the path's only exchange: int64[K+1] success counts
+    e1.record(stream)
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    clocks = sampler.result()
+    launches = path.launch_count - launches0
+    prof = path.profile_read()
+    path.set_option('profile', 0)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    total_frames = world * frames * args.steps
+    value = total_frames / (elapsed_ms / 1e3)
+    host_counts = counts.cpu().numpy()
+    rates = aig.success_rates(host_counts[:-1], max(int(host_counts[-1]), 1))
+    auc = aig.auc(THRESHOLDS, rates)
+
+    # ---- end to end through the host API: pinned NumPy in / out, copies inside the timed region ----
+    e2e_frames = min(args.e2e_frames, frames)
+    pin = lambda shape, dtype: torch.empty(shape, dtype=dtype, pin_memory=True)
+    h_power = pin((e2e_frames, 36, 48, FFT_LEN), torch.float32)
+    h_power.copy_(power[:e2e_frames])
+    h_out = (pin((e2e_frames, 36, 48, MFCC_NUM), torch.float32), pin((e2e_frames, 36, 48), torch.float64),
+             pin((e2e_frames, 36, 48), torch.uint8))
+    np_power, np_out = h_power.numpy(), tuple(t.numpy() for t in h_out)
+    for _ in range(2):
+        path.mfcc_energy(np_power, flip=True, normalize_first=True, out=np_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        path.mfcc_energy(np_power, flip=True, normalize_first=True, out=np_out)   # returns after the D2H copies
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * e2e_frames * args.e2e_steps / e2e_s
+    # the end-to-end result must be the resident result (same frames)
+    assert np.array_equal(np_out[2], mask[:e2e_frames].cpu().numpy()), 'e2e mask differs from the resident run'
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused MFCC), event-timed per launch in the timed region ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    mfcc_ms, mfcc_launches = prof['mfcc']
+    energy_ms, energy_launches = prof['energy']
+    frames_per_launch = frames * args.steps / max(mfcc_launches, 1)
+    achieved = (ALGO_BYTES_MFCC_KERNEL * frames_per_launch) / (mfcc_ms / max(mfcc_launches, 1) / 1e3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))['mfcc_banded_kernel_bytes_per_frame'] * frames_per_launch
+    except Exception:
+        pass
+    roofline = {
+        'bound': 'hbm', 'kernel': 'mfcc_banded_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+        'frac': achieved / peak, 'traffic': traffic,
+        'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured copy)' if peaks else 'fallback 6650 GB/s',
+        'frac_of_nominal_8TBs': achieved / 8000.0,
+        'algorithmic_bytes_per_frame': ALGO_BYTES_MFCC_KERNEL,
+        'frames_per_launch': frames_per_launch, 'launches': mfcc_launches,
+        'avg_launch_ms': mfcc_ms / max(mfcc_launches, 1),
+        'kernel_share_of_step': mfcc_ms / elapsed_ms,
+        'energy_kernel_ms_per_launch': energy_ms / max(energy_launches, 1),
+        'path_gbs_whole_step': ALGO_BYTES_PATH * frames * args.steps / (elapsed_ms / 1e3) / 1e9 ,
+    }
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(frames, world),
+        'roofline': roofline,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': e2e_frames * IN_BYTES,
+                'd2h_bytes_per_step': e2e_frames * (MFCC_BYTES + FRAME_PIXELS * 8 + FRAME_PIXELS),
+                'frames_per_step': e2e_frames, 'steps': args.e2e_steps,
+                'api': 'AcousticPath.mfcc_energy(pinned numpy) -> aig_mfcc_energy, synchronous'},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'result': {'auc': auc, 'num': int(host_counts[-1]), 'pos': [int(v) for v in host_counts[:-1]]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = time_cpu(10 ** 6, 1, budget_s=args.cpu_seconds)[0]
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=40)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--frames', type=int, default=8192, help='resident frames per step per GPU')
+    ap.add_argument('--e2e-frames', type=int, default=256, help='frames per end-to-end step (pinned host batch)')
+    ap.add_argument('--e2e-steps', type=int, default=5)
+    ap.add_argument('--cpu-seconds', type=float, default=12.0, help='CPU baseline time budget')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3                                 # timing rule: at least three warm-up steps
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

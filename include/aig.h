@@ -183,14 +183,26 @@ int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, cons
  * arrays == direction * trapezoid.  Host-side, float64.  thr / value are host arrays of length k. */
 int aig_auc(const double* thr, const double* value, int k, double* auc_out);
 
-/* ---- instrumentation ------------------------------------------------------------------- */
+/* ---- instrumentation and tuning --------------------------------------------------------- */
 
 /* Number of kernels this handle has launched since creation (for bench.py's gpu_launches). */
 int64_t aig_launch_count(const aig_handle* h);
 
-/* Tuning knob for the fused MFCC kernel: `variant` selects the pipeline geometry
- * (see mfcc_kernel.cuh); -1 restores the default.  Returns AIG_ERR_ARGUMENT for unknown variants. */
-int aig_set_mfcc_variant(aig_handle* h, int variant);
+/* Integer options, by name:
+ *   "mfcc_variant"       ring geometry of the fused MFCC kernel (see aig_api.cu kVariants); -1 = default
+ *   "chain_chunk_frames" frames per launch pair in aig_mfcc_energy (default 512: the chunk's MFCC
+ *                        images, 42 MB, stay in the 126 MB L2 between the two kernels)
+ *   "chain_overlap"      1 (default): the energy kernel of chunk i runs on a second stream while the
+ *                        MFCC kernel of chunk i+1 streams from HBM; 0: both on the handle's stream
+ *   "profile"            1: bracket every MFCC / energy kernel launch with CUDA events on the stream it
+ *                        is launched on (read back with aig_profile_read); 0 (default): off
+ * Unknown names or out-of-range values return AIG_ERR_ARGUMENT. */
+int aig_set_option(aig_handle* h, const char* name, int64_t value);
+
+/* Synchronise, then report and reset the event timings gathered while "profile" was on:
+ * ms_out[3] / launches_out[3] = summed device time and launch count of
+ * {0: MFCC kernels, 1: energy kernels, 2: every other kernel}. */
+int aig_profile_read(aig_handle* h, double* ms_out, int64_t* launches_out);
 
 #ifdef __cplusplus
 }

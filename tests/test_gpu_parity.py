@@ -380,3 +380,38 @@ def test_launch_counter_counts_kernels(path):
     before = path.launch_count
     path.energy(synth.sigmoid_images(1, 0))
     assert path.launch_count == before + 1
+
+
+# ----------------------------------------------------------------------------------------------
+# evaluation drivers (the callers of the scoring path) and their metric files
+# ----------------------------------------------------------------------------------------------
+def test_acivw_evaluation_driver_writes_reference_files(path, golden, tmp_path):
+    from acoustic_image_generation_b200 import evaluate, metrics_io
+    g = golden('acivw_iou')
+    n = int(g['num'])
+    a = synth.smooth_images(n, 10)
+    b = synth.smooth_images(n, 11)
+    b[: n // 2] = a[: n // 2] * np.float32(0.9) + b[: n // 2] * np.float32(0.1)
+    ev = evaluate.AcivwEvaluation(path)
+    for lo in range(0, n, 16):                         # batches, like the session.run loop
+        ev.add_batch(a[lo:lo + 16], b[lo:lo + 16])
+    res = ev.finish(str(tmp_path))
+    assert np.array_equal(res['pos'], g['pos11']) and res['num'] == n
+    assert abs(res['auc'] - float(golden('auc')['acivw11'])) <= 1e-12
+    for t, p in zip(REF_THR, g['pos11']):
+        assert metrics_io.read_accuracy_file(str(tmp_path), t) == float('{:6f}'.format(p / n))
+    assert open(str(tmp_path / 'area.txt')).read() == 'area {:6f}'.format(res['auc'])
+
+
+def test_flickr_evaluation_driver(path, golden, torch):
+    from acoustic_image_generation_b200 import evaluate
+    g = golden('flickr_ciou')
+    n = int(g['num'])
+    pred = torch.from_numpy(synth.smooth_images(n, 20)).cuda()      # device-resident inputs
+    boxes = [torch.from_numpy(v).cuda() for v in synth.flickr_boxes(n, 21)]
+    ev = evaluate.FlickrEvaluation(path)
+    ev.add_batch(pred[:20], *[v[:20] for v in boxes])
+    ev.add_batch(pred[20:], *[v[20:] for v in boxes])
+    res = ev.finish()
+    assert np.array_equal(res['pos'], g['pos11']) and res['num'] == n
+    assert abs(res['auc'] - float(golden('auc')['flickr11'])) <= 1e-12
