@@ -19,7 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 NVCC_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-Xcompiler', '-fPIC', '-shared']
 SOURCES = ['aig_api.cu']
-DEPENDS = ['aig_api.cu', 'aig_common.cuh', 'mfcc_kernel.cuh', 'energy_kernel.cuh', 'score_kernel.cuh',
+DEPENDS = ['aig_api.cu', 'aig_common.cuh', 'mfcc_kernel.cuh', 'energy_kernel.cuh', 'score_kernel.cuh', 'fused_kernel.cuh',
            'mel_program_ref.inc', 'mel_tables_ref.inc', os.path.join(INCLUDE, 'aig.h')]
 
 AIG_OK = 0

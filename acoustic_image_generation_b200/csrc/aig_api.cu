@@ -20,6 +20,7 @@
 #include "../../include/aig.h"
 #include "aig_common.cuh"
 #include "energy_kernel.cuh"
+#include "fused_kernel.cuh"
 #include "mfcc_kernel.cuh"
 #include "score_kernel.cuh"
 
@@ -86,6 +87,11 @@ struct aig_handle {
     cudaEvent_t ev_chain[4] = {nullptr, nullptr, nullptr, nullptr};   // start, mfcc[2], energy-done
     int chain_chunk_frames = 512;
     bool chain_overlap = true;
+    int chain_mode = 2;                 // 2: one fused persistent kernel; 1/0: two kernels (see chain_overlap)
+    int fused_variant = 2;              // 96 KiB stages x 2 measured best (profiles/r01_tune_chain.txt)
+    int l2_evict_first = 0;             // L2 evict-first hint on the spectrum loads (measured slower: off)
+    int keep_mfcc_in_l2 = 1;            // fused kernel: evict-last hint on the MFCC stores the energy warps re-read
+    bool fused_attr_set[4] = {false, false, false, false};
     int chain_energy_ctas_per_sm = 3;   // footprint of the overlapped energy kernel (measured: profiles/r01_tune_chain.txt)
     // profiling: (start, stop) event pairs per launch, by kernel kind
     bool profile = false;
@@ -287,7 +293,8 @@ int launch_banded_variant(aig_handle* h, const CUtensorMap& map, float* out, uns
     const unsigned n_tiles = (n_rows + v.rows - 1) / v.rows;
     const unsigned grid = std::min<unsigned>(n_tiles, static_cast<unsigned>(h->sm_count * v.ctas));
     LaunchScope scope(h, h->stream, kKindMfcc);
-    kernel<<<grid, P::kThreads, P::kSmemBytes, h->stream>>>(map, out, n_rows, n_tiles, flip180, frame_pixels);
+    kernel<<<grid, P::kThreads, P::kSmemBytes, h->stream>>>(map, out, n_rows, n_tiles, flip180, frame_pixels,
+                                                            h->l2_evict_first);
     return scope.done("mfcc_banded_kernel");
 }
 
@@ -356,6 +363,59 @@ int launch_energy(aig_handle* h, cudaStream_t stream, const float* d_images, int
     energy_kernel<<<frames_grid(h, n_frames, ctas_per_sm), kEnergyThreads, 0, stream>>>(
         d_images, n_frames, normalize_first, d_scaled, d_energy, d_mask, d_mean);
     return scope.done("energy_kernel");
+}
+
+// ---- fused MFCC + energy kernel ---------------------------------------------------------------------
+struct FusedVariant { int slabs, stages; };
+constexpr int kNumFusedVariants = 3;
+constexpr FusedVariant kFusedVariants[kNumFusedVariants] = {
+    {1, 8},    // 0: 24 KiB stages x 8  = 192 KiB ring
+    {2, 4},    // 1: 48 KiB stages x 4
+    {4, 2},    // 2: 96 KiB stages x 2
+};
+
+template <int V>
+int launch_fused_variant(aig_handle* h, const CUtensorMap& map, float* d_mfcc, unsigned n_frames, int flip180,
+                         int normalize_first, double* d_energy, uint8_t* d_mask, double* d_mean) {
+    constexpr FusedVariant v = kFusedVariants[V];
+    using F = FusedPipe<v.slabs, v.stages>;
+    auto kernel = mfcc_energy_fused_kernel<v.slabs, v.stages>;
+    if (!h->fused_attr_set[V]) {
+        AIG_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F::kSmemBytes));
+        h->fused_attr_set[V] = true;
+    }
+    const unsigned grid = std::min<unsigned>(n_frames, static_cast<unsigned>(h->sm_count));
+    LaunchScope scope(h, h->stream, kKindMfcc);
+    kernel<<<grid, kFusedThreads, F::kSmemBytes, h->stream>>>(map, d_mfcc, n_frames, flip180, normalize_first, d_energy,
+                                                             d_mask, d_mean, h->l2_evict_first, h->keep_mfcc_in_l2);
+    return scope.done("mfcc_energy_fused_kernel");
+}
+
+int launch_fused(aig_handle* h, const float* d_power, int64_t n_frames, float* d_mfcc, int flip180, int normalize_first,
+                 double* d_energy, uint8_t* d_mask, double* d_mean) {
+    if ((reinterpret_cast<uintptr_t>(d_power) & 15u) || (reinterpret_cast<uintptr_t>(d_mfcc) & 15u))
+        return h->fail(AIG_ERR_ARGUMENT, "aig_mfcc_energy: device buffers must be 16-byte aligned");
+    const int64_t max_frames = ((int64_t(1) << 31) - 1024) / kFramePixels;
+    for (int64_t done = 0; done < n_frames; done += max_frames) {
+        const int64_t frames = std::min(max_frames, n_frames - done);
+        CUtensorMap map;
+        int rc = encode_spectrum_map(h, d_power + done * kFramePixels * kFftLen, static_cast<uint64_t>(frames) * kFramePixels,
+                                     kFusedRows, &map);
+        if (rc != AIG_OK) return rc;
+        float* mf = d_mfcc + done * kFrameValues;
+        double* en = d_energy ? d_energy + done * kFramePixels : nullptr;
+        uint8_t* mk = d_mask ? d_mask + done * kFramePixels : nullptr;
+        double* mn = d_mean ? d_mean + done : nullptr;
+        const unsigned f = static_cast<unsigned>(frames);
+        switch (h->fused_variant) {
+            case 0: rc = launch_fused_variant<0>(h, map, mf, f, flip180, normalize_first, en, mk, mn); break;
+            case 1: rc = launch_fused_variant<1>(h, map, mf, f, flip180, normalize_first, en, mk, mn); break;
+            case 2: rc = launch_fused_variant<2>(h, map, mf, f, flip180, normalize_first, en, mk, mn); break;
+            default: rc = h->fail(AIG_ERR_ARGUMENT, "unknown fused kernel variant %d", h->fused_variant);
+        }
+        if (rc != AIG_OK) return rc;
+    }
+    return AIG_OK;
 }
 
 int require(aig_handle* h) {
@@ -508,9 +568,20 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
         h->chain_chunk_frames = static_cast<int>(value);
     } else if (key == "chain_overlap") {
         h->chain_overlap = value != 0;
+    } else if (key == "chain_mode") {
+        if (value < 0 || value > 2) return h->fail(AIG_ERR_ARGUMENT, "chain_mode must be 0, 1 or 2");
+        h->chain_mode = static_cast<int>(value);
+        if (value < 2) h->chain_overlap = value == 1;
+    } else if (key == "fused_variant") {
+        if (value < 0 || value >= kNumFusedVariants) return h->fail(AIG_ERR_ARGUMENT, "unknown fused kernel variant %lld", (long long)value);
+        h->fused_variant = static_cast<int>(value);
     } else if (key == "chain_energy_ctas_per_sm") {
         if (value < 1 || value > 16) return h->fail(AIG_ERR_ARGUMENT, "chain_energy_ctas_per_sm out of range");
         h->chain_energy_ctas_per_sm = static_cast<int>(value);
+    } else if (key == "keep_mfcc_in_l2") {
+        h->keep_mfcc_in_l2 = value != 0;
+    } else if (key == "l2_evict_first") {
+        h->l2_evict_first = value != 0;
     } else if (key == "profile") {
         h->profile = value != 0;
     } else {
@@ -706,7 +777,8 @@ int aig_mfcc_energy(aig_handle* h, const float* power, int64_t n_frames, int fli
     // The energy kernel is FP64-compute-bound and touches 2 % of the bytes; the MFCC kernel is HBM-bound
     // and leaves the FP64 pipe idle.  Run them chunk-wise on two streams so that the energy kernel of
     // chunk i executes underneath the MFCC kernel of chunk i+1 (its input is still in L2).
-    const bool overlap = h->chain_overlap;
+    const bool fused = h->chain_mode == 2;
+    const bool overlap = h->chain_overlap && !fused;
     cudaStream_t energy_stream = overlap ? h->aux_stream : h->stream;
     if (overlap) {
         AIG_CK(cudaEventRecord(h->ev_chain[0], h->stream));              // order after earlier work
@@ -714,6 +786,10 @@ int aig_mfcc_energy(aig_handle* h, const float* power, int64_t n_frames, int fli
     }
     int64_t chunk_index = 0;
     auto run = [&](const float* d_power, int64_t frame0, int64_t frames) -> int {
+        if (fused)
+            return launch_fused(h, d_power, frames, d_mfcc + frame0 * kFrameValues, flip180, normalize_first,
+                                d_energy ? d_energy + frame0 * kFramePixels : nullptr,
+                                d_mask ? d_mask + frame0 * kFramePixels : nullptr, d_mean ? d_mean + frame0 : nullptr);
         for (int64_t f = 0; f < frames; f += h->chain_chunk_frames, ++chunk_index) {
             const int64_t cf = std::min<int64_t>(h->chain_chunk_frames, frames - f);
             const int64_t g = frame0 + f;

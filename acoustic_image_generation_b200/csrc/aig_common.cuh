@@ -60,12 +60,33 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     return policy;
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
+}
+// 16-byte global store with an L2 cache-hint policy.
+__device__ __forceinline__ void stg128_hint(float4* p, const float4& v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_descriptor(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 // 2-D tiled bulk tensor load global -> shared, completion signalled on an mbarrier.
+// policy == 0: default L2 policy (measured faster for this read-mostly stream, profiles/r01_read_peak_probe.txt);
+// otherwise an L2 cache-hint policy from createpolicy.
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                             int32_t x, int32_t y, uint64_t policy) {
+    if (policy == 0) {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
+            : "memory");
+        return;
+    }
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
         " [%0], [%1, {%3, %4}], [%2], %5;"

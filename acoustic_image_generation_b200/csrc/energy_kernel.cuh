@@ -33,6 +33,69 @@ static_assert(kFramePixels % kEnergyThreads == 0, "pixels must divide evenly ove
 __device__ __forceinline__ int leaf_start(int leaf) { return 216 * (leaf >> 1) + ((leaf & 1) ? 104 : 0); }
 __device__ __forceinline__ int leaf_len(int leaf) { return (leaf & 1) ? 112 : 104; }
 
+// One pixel of find_logen: optional float32 min-max normalisation (:672-679), the float64-compute /
+// float32-store scaling `mfcc /= lifter; mfcc *= mfnorm` (:310-311), the float64 projection on dct_base^T,
+// exp, the band sum in NumPy's order for n = 24 (r[k] = e[k] + e[k+8] + e[k+16], then the balanced tree
+// over r[0..7]) and the reciprocal (:313-321).  x[] is left holding the scaled float32 values.
+__device__ __forceinline__ double pixel_energy(float (&x)[kMfccNum], bool normalize, float lo, float range) {
+    double z[kMfccNum];
+#pragma unroll
+    for (int m = 0; m < kMfccNum; ++m) {
+        float v = x[m];
+        if (normalize) v = __fdiv_rn(__fsub_rn(v, lo), range);                // float32, as TF
+        v = __double2float_rn(__ddiv_rn(static_cast<double>(v), c_lifter[m]));
+        v = __double2float_rn(__dmul_rn(static_cast<double>(v), c_mfnorm));
+        x[m] = v;
+        z[m] = static_cast<double>(v);
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < kFilterNum; ++j) {
+        double mel = 0.0;
+#pragma unroll
+        for (int m = 0; m < kMfccNum; ++m) mel = fma(z[m], c_dct[j * kMfccNum + m], mel);
+        const double e = exp(mel);
+        r[j & 7] = (j < 8) ? e : __dadd_rn(r[j & 7], e);
+    }
+    const double total = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                                   __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    return __ddiv_rn(1.0, total);
+}
+
+// np.mean over the 1728 doubles of s_map, bit-compatible with NumPy's pairwise summation.  Called by a
+// thread group of at least 128 threads (index t within the group); `sync` is the group's barrier.
+// Returns the mean in every thread of the group.
+template <typename Sync>
+__device__ __forceinline__ double frame_mean(const double* s_map, double (*s_part)[8], double* s_leaf,
+                                             double* s_mean, int t, Sync sync) {
+    if (t < 128) {
+        const int leaf = t >> 3, k = t & 7;
+        const double* a = s_map + leaf_start(leaf);
+        const int len = leaf_len(leaf);
+        double r = a[k];
+        for (int i = 8; i < len; i += 8) r = __dadd_rn(r, a[i + k]);
+        s_part[leaf][k] = r;
+    }
+    sync();
+    if (t < 16) {
+        const double* r = s_part[t];
+        s_leaf[t] = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                              __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    }
+    sync();
+    if (t == 0) {
+        double s8[8], s4[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s8[i] = __dadd_rn(s_leaf[2 * i], s_leaf[2 * i + 1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s4[i] = __dadd_rn(s8[2 * i], s8[2 * i + 1]);
+        const double sum = __dadd_rn(__dadd_rn(s4[0], s4[1]), __dadd_rn(s4[2], s4[3]));
+        *s_mean = __ddiv_rn(sum, static_cast<double>(kFramePixels));
+    }
+    sync();
+    return *s_mean;
+}
+
 __global__ void __launch_bounds__(kEnergyThreads)
 energy_kernel(const float* __restrict__ images, long long n_frames, int normalize_first,
               float* __restrict__ scaled_out, double* __restrict__ energy_out,
@@ -77,73 +140,22 @@ energy_kernel(const float* __restrict__ images, long long n_frames, int normaliz
             const float4* src = reinterpret_cast<const float4*>(img + p * kMfccNum);
             const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
             float x[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-            double z[kMfccNum];
-#pragma unroll
-            for (int m = 0; m < kMfccNum; ++m) {
-                float v = x[m];
-                if (normalize_first) v = __fdiv_rn(__fsub_rn(v, lo), range);      // float32, as TF
-                // mfcc /= lifter; mfcc *= mfnorm : float64 compute, float32 store (:310-311)
-                v = __double2float_rn(__ddiv_rn(static_cast<double>(v), c_lifter[m]));
-                v = __double2float_rn(__dmul_rn(static_cast<double>(v), c_mfnorm));
-                x[m] = v;
-                z[m] = static_cast<double>(v);
-            }
+            const double en = pixel_energy(x, normalize_first != 0, lo, range);
             if (scaled_out != nullptr) {
                 float4* dst = reinterpret_cast<float4*>(scaled_out + frame * kFrameValues + p * kMfccNum);
                 dst[0] = make_float4(x[0], x[1], x[2], x[3]);
                 dst[1] = make_float4(x[4], x[5], x[6], x[7]);
                 dst[2] = make_float4(x[8], x[9], x[10], x[11]);
             }
-            // melspec = exp(mfcc . dct_base^T); band sum in NumPy's order for n = 24:
-            // r[k] = e[k] + e[k+8] + e[k+16], then the balanced tree over r[0..7] (:313-320)
-            double r[8];
-#pragma unroll
-            for (int j = 0; j < kFilterNum; ++j) {
-                double mel = 0.0;
-#pragma unroll
-                for (int m = 0; m < kMfccNum; ++m) mel = fma(z[m], c_dct[j * kMfccNum + m], mel);
-                const double e = exp(mel);
-                r[j & 7] = (j < 8) ? e : __dadd_rn(r[j & 7], e);
-            }
-            const double total = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-            const double en = __ddiv_rn(1.0, total);                                  // :321
             s_map[p] = en;
             if (energy_out != nullptr) energy_out[frame * kFramePixels + p] = en;
         }
         __syncthreads();
 
         if (mask_out != nullptr || mean_out != nullptr) {
-            // np.mean(map): pairwise tree, bit-compatible with NumPy for 1728 contiguous doubles
-            if (tid < 128) {
-                const int leaf = tid >> 3, k = tid & 7;
-                const double* a = s_map + leaf_start(leaf);
-                const int len = leaf_len(leaf);
-                double r = a[k];
-                for (int i = 8; i < len; i += 8) r = __dadd_rn(r, a[i + k]);
-                s_part[leaf][k] = r;
-            }
-            __syncthreads();
-            if (tid < 16) {
-                const double* r = s_part[tid];
-                s_leaf[tid] = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                                        __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-            }
-            __syncthreads();
-            if (tid == 0) {
-                double s8[8], s4[4];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) s8[i] = __dadd_rn(s_leaf[2 * i], s_leaf[2 * i + 1]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) s4[i] = __dadd_rn(s8[2 * i], s8[2 * i + 1]);
-                const double sum = __dadd_rn(__dadd_rn(s4[0], s4[1]), __dadd_rn(s4[2], s4[3]));
-                const double mean = __ddiv_rn(sum, static_cast<double>(kFramePixels));
-                s_mean = mean;
-                if (mean_out != nullptr) mean_out[frame] = mean;
-            }
-            __syncthreads();
+            const double mean = frame_mean(s_map, s_part, s_leaf, &s_mean, tid, [] { __syncthreads(); });
+            if (tid == 0 && mean_out != nullptr) mean_out[frame] = mean;
             if (mask_out != nullptr) {
-                const double mean = s_mean;
                 for (int p = tid; p < kFramePixels; p += kEnergyThreads)
                     mask_out[frame * kFramePixels + p] = s_map[p] > mean ? 1 : 0;
             }

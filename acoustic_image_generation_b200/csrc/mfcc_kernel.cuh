@@ -44,10 +44,96 @@ struct MfccPipe {
 
 #define AIG_MEL_DECL(f) float m##f##_0 = 0.f, m##f##_1 = 0.f;
 
+// One consumer thread's work on one tile: wait for the tile's ring stages, run the straight-line mel
+// program on the thread's spectrum, release the stages, and return the 12 cepstra with the reference's
+// NaN/Inf -> 0 fix-up applied.  `stage` / `phase` are the thread's view of the ring position.
+template <int ROWS, int SLABS_PER_STAGE, int STAGES>
+__device__ __forceinline__ void mel_tile(uint32_t ring, uint32_t bar_full, uint32_t bar_empty, uint32_t row_off,
+                                         uint32_t sw, int lane, int& stage, uint32_t& phase, float (&c)[12]) {
+    using P = MfccPipe<ROWS, SLABS_PER_STAGE, STAGES>;
+    AIG_MEL_DECL(0) AIG_MEL_DECL(1) AIG_MEL_DECL(2) AIG_MEL_DECL(3) AIG_MEL_DECL(4) AIG_MEL_DECL(5)
+    AIG_MEL_DECL(6) AIG_MEL_DECL(7) AIG_MEL_DECL(8) AIG_MEL_DECL(9) AIG_MEL_DECL(10) AIG_MEL_DECL(11)
+    AIG_MEL_DECL(12) AIG_MEL_DECL(13) AIG_MEL_DECL(14) AIG_MEL_DECL(15) AIG_MEL_DECL(16) AIG_MEL_DECL(17)
+    AIG_MEL_DECL(18) AIG_MEL_DECL(19) AIG_MEL_DECL(20) AIG_MEL_DECL(21) AIG_MEL_DECL(22) AIG_MEL_DECL(23)
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f, c5 = 0.f;
+    float c6 = 0.f, c7 = 0.f, c8 = 0.f, c9 = 0.f, c10 = 0.f, c11 = 0.f;
+    float poison = 0.f;   // 0, or NaN once any bin of the row is NaN/Inf (reference: x * 0 = NaN)
+
+#define MEL_SLAB_BEGIN(s)                                                                        \
+    {                                                                                            \
+        if ((s) % SLABS_PER_STAGE == 0) mbar_wait(bar_full + 8 * stage, phase);                  \
+        const uint32_t slab = ring + stage * P::kStageBytes +                                    \
+                              ((s) % SLABS_PER_STAGE) * P::kSlabBytes + row_off;
+#define MEL_LOAD(s, j) const float4 v##j = lds128(slab + ((static_cast<uint32_t>(j) << 4) ^ sw));
+#define MEL_BIN0(j, c) poison = fmaf(v##j.c, 0.f, poison);
+#define MEL_BIN1(j, c, f, p, w) m##f##_##p = fmaf(v##j.c, w, m##f##_##p);
+#define MEL_BIN2(j, c, f, p, w, g, q, u) MEL_BIN1(j, c, f, p, w) MEL_BIN1(j, c, g, q, u)
+#define MEL_DONE(f, d0, d1, d2, d3, d4, d5, d6, d7, d8, d9, d10, d11)                            \
+        {                                                                                        \
+            float e = m##f##_0 + m##f##_1;                                                       \
+            /* floor at 0.001 (:858); -Inf would be floored away here but is NaN in the        */\
+            /* reference's other columns, so turn it into NaN                                   */\
+            e = (e < 0.001f) ? ((e == -CUDART_INF_F) ? CUDART_NAN_F : 0.001f) : e;               \
+            const float lg = logf(e);                                                            \
+            c0 = fmaf(lg, d0, c0); c1 = fmaf(lg, d1, c1); c2 = fmaf(lg, d2, c2);                \
+            c3 = fmaf(lg, d3, c3); c4 = fmaf(lg, d4, c4); c5 = fmaf(lg, d5, c5);                \
+            c6 = fmaf(lg, d6, c6); c7 = fmaf(lg, d7, c7); c8 = fmaf(lg, d8, c8);                \
+            c9 = fmaf(lg, d9, c9); c10 = fmaf(lg, d10, c10); c11 = fmaf(lg, d11, c11);          \
+        }
+#define MEL_SLAB_END(s)                                                                          \
+        if ((s) % SLABS_PER_STAGE == SLABS_PER_STAGE - 1) {                                      \
+            __syncwarp();                                                                        \
+            if (lane == 0) mbar_arrive(bar_empty + 8 * stage);                                   \
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }                                   \
+        }                                                                                        \
+    }
+#include "mel_program_ref.inc"
+#undef MEL_SLAB_BEGIN
+#undef MEL_LOAD
+#undef MEL_BIN0
+#undef MEL_BIN1
+#undef MEL_BIN2
+#undef MEL_DONE
+#undef MEL_SLAB_END
+
+    const float raw[12] = {c0, c1, c2, c3, c4, c5, c6, c7, c8, c9, c10, c11};
+#pragma unroll
+    for (int m = 0; m < 12; ++m) {
+        const float v = raw[m] + poison;
+        c[m] = (fabsf(v) <= 3.402823466e38f) ? v : 0.f;     // NaN / Inf -> 0 (:871-872)
+    }
+}
+
+// The producer lane's work on one tile: stream its 16 slabs through the ring.
+template <int ROWS, int SLABS_PER_STAGE, int STAGES>
+__device__ __forceinline__ void load_tile(const CUtensorMap* tmap, uint32_t ring, uint32_t bar_full,
+                                          uint32_t bar_empty, int32_t row0, uint64_t policy, int& stage,
+                                          uint32_t& phase) {
+    using P = MfccPipe<ROWS, SLABS_PER_STAGE, STAGES>;
+#pragma unroll 1
+    for (int kb = 0; kb < P::kStagesPerTile; ++kb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+        mbar_arrive_expect_tx(bar_full + 8 * stage, P::kStageBytes);
+#pragma unroll
+        for (int s = 0; s < SLABS_PER_STAGE; ++s)
+            tma_load_2d(ring + stage * P::kStageBytes + s * P::kSlabBytes, tmap, bar_full + 8 * stage,
+                        (kb * SLABS_PER_STAGE + s) * 32, row0, policy);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+}
+
+__device__ __forceinline__ void store_cepstra(float* __restrict__ out, size_t dst_row, const float (&c)[12]) {
+    float4* o = reinterpret_cast<float4*>(out + dst_row * 12u);
+    o[0] = make_float4(c[0], c[1], c[2], c[3]);
+    o[1] = make_float4(c[4], c[5], c[6], c[7]);
+    o[2] = make_float4(c[8], c[9], c[10], c[11]);
+}
+
 template <int ROWS, int SLABS_PER_STAGE, int STAGES, int MIN_CTAS>
 __global__ void __launch_bounds__(ROWS + 32, MIN_CTAS)
 mfcc_banded_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ out,
-                   unsigned int n_rows, unsigned int n_tiles, int flip180, unsigned int frame_pixels) {
+                   unsigned int n_rows, unsigned int n_tiles, int flip180, unsigned int frame_pixels,
+                   int l2_evict_first) {
     using P = MfccPipe<ROWS, SLABS_PER_STAGE, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle atoms are 1024 B
@@ -65,26 +151,16 @@ mfcc_banded_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
     }
     __syncthreads();
 
+    int stage = 0;
+    uint32_t phase = 0;
     if (warp == P::kConsumerWarps) {
         // ---------------- producer: one lane streams tiles through the ring ----------------
         if (lane == 0) {
             tma_prefetch_descriptor(&tmap);
-            const uint64_t policy = l2_policy_evict_first();
-            int stage = 0;
-            uint32_t phase = 0;
-            for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int32_t row0 = static_cast<int32_t>(tile * ROWS);
-#pragma unroll 1
-                for (int kb = 0; kb < P::kStagesPerTile; ++kb) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-                    mbar_arrive_expect_tx(bar_full + 8 * stage, P::kStageBytes);
-#pragma unroll
-                    for (int s = 0; s < SLABS_PER_STAGE; ++s)
-                        tma_load_2d(ring + stage * P::kStageBytes + s * P::kSlabBytes, &tmap,
-                                    bar_full + 8 * stage, (kb * SLABS_PER_STAGE + s) * 32, row0, policy);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                }
-            }
+            const uint64_t policy = l2_evict_first ? l2_policy_evict_first() : 0ull;
+            for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                load_tile<ROWS, SLABS_PER_STAGE, STAGES>(&tmap, ring, bar_full, bar_empty,
+                                                         static_cast<int32_t>(tile * ROWS), policy, stage, phase);
         }
         return;
     }
@@ -92,72 +168,17 @@ mfcc_banded_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
     // -------------------- consumers: one thread per spectrum of the tile --------------------
     const uint32_t row_off = threadIdx.x * 128u;
     const uint32_t sw = (threadIdx.x & 7u) << 4;    // 128B swizzle: 16-byte chunk index ^= row % 8
-    int stage = 0;
-    uint32_t phase = 0;
-
     for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        AIG_MEL_DECL(0) AIG_MEL_DECL(1) AIG_MEL_DECL(2) AIG_MEL_DECL(3) AIG_MEL_DECL(4) AIG_MEL_DECL(5)
-        AIG_MEL_DECL(6) AIG_MEL_DECL(7) AIG_MEL_DECL(8) AIG_MEL_DECL(9) AIG_MEL_DECL(10) AIG_MEL_DECL(11)
-        AIG_MEL_DECL(12) AIG_MEL_DECL(13) AIG_MEL_DECL(14) AIG_MEL_DECL(15) AIG_MEL_DECL(16) AIG_MEL_DECL(17)
-        AIG_MEL_DECL(18) AIG_MEL_DECL(19) AIG_MEL_DECL(20) AIG_MEL_DECL(21) AIG_MEL_DECL(22) AIG_MEL_DECL(23)
-        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f, c5 = 0.f;
-        float c6 = 0.f, c7 = 0.f, c8 = 0.f, c9 = 0.f, c10 = 0.f, c11 = 0.f;
-        float poison = 0.f;   // 0, or NaN once any bin of the row is NaN/Inf (reference: x * 0 = NaN)
-
-#define MEL_SLAB_BEGIN(s)                                                                        \
-        {                                                                                        \
-            if ((s) % SLABS_PER_STAGE == 0) mbar_wait(bar_full + 8 * stage, phase);              \
-            const uint32_t slab = ring + stage * P::kStageBytes +                                \
-                                  ((s) % SLABS_PER_STAGE) * P::kSlabBytes + row_off;
-#define MEL_LOAD(s, j) const float4 v##j = lds128(slab + ((static_cast<uint32_t>(j) << 4) ^ sw));
-#define MEL_BIN0(j, c) poison = fmaf(v##j.c, 0.f, poison);
-#define MEL_BIN1(j, c, f, p, w) m##f##_##p = fmaf(v##j.c, w, m##f##_##p);
-#define MEL_BIN2(j, c, f, p, w, g, q, u) MEL_BIN1(j, c, f, p, w) MEL_BIN1(j, c, g, q, u)
-#define MEL_DONE(f, d0, d1, d2, d3, d4, d5, d6, d7, d8, d9, d10, d11)                            \
-            {                                                                                    \
-                float e = m##f##_0 + m##f##_1;                                                   \
-                /* floor at 0.001 (:858); -Inf would be floored away here but is NaN in the    */\
-                /* reference's other columns, so turn it into NaN                               */\
-                e = (e < 0.001f) ? ((e == -CUDART_INF_F) ? CUDART_NAN_F : 0.001f) : e;           \
-                const float lg = logf(e);                                                        \
-                c0 = fmaf(lg, d0, c0); c1 = fmaf(lg, d1, c1); c2 = fmaf(lg, d2, c2);            \
-                c3 = fmaf(lg, d3, c3); c4 = fmaf(lg, d4, c4); c5 = fmaf(lg, d5, c5);            \
-                c6 = fmaf(lg, d6, c6); c7 = fmaf(lg, d7, c7); c8 = fmaf(lg, d8, c8);            \
-                c9 = fmaf(lg, d9, c9); c10 = fmaf(lg, d10, c10); c11 = fmaf(lg, d11, c11);      \
-            }
-#define MEL_SLAB_END(s)                                                                          \
-            if ((s) % SLABS_PER_STAGE == SLABS_PER_STAGE - 1) {                                  \
-                __syncwarp();                                                                    \
-                if (lane == 0) mbar_arrive(bar_empty + 8 * stage);                               \
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }                               \
-            }                                                                                    \
-        }
-#include "mel_program_ref.inc"
-#undef MEL_SLAB_BEGIN
-#undef MEL_LOAD
-#undef MEL_BIN0
-#undef MEL_BIN1
-#undef MEL_BIN2
-#undef MEL_DONE
-#undef MEL_SLAB_END
-
+        float c[12];
+        mel_tile<ROWS, SLABS_PER_STAGE, STAGES>(ring, bar_full, bar_empty, row_off, sw, lane, stage, phase, c);
         const unsigned int row = tile * ROWS + threadIdx.x;
         if (row < n_rows) {
-            float c[12] = {c0, c1, c2, c3, c4, c5, c6, c7, c8, c9, c10, c11};
-#pragma unroll
-            for (int m = 0; m < 12; ++m) {
-                const float v = c[m] + poison;
-                c[m] = (fabsf(v) <= 3.402823466e38f) ? v : 0.f;     // NaN / Inf -> 0 (:871-872)
-            }
             unsigned int dst = row;
             if (flip180) {
                 const unsigned int frame = row / frame_pixels;
                 dst = frame * frame_pixels + (frame_pixels - 1u - (row - frame * frame_pixels));
             }
-            float4* o = reinterpret_cast<float4*>(out + static_cast<size_t>(dst) * 12u);
-            o[0] = make_float4(c[0], c[1], c[2], c[3]);
-            o[1] = make_float4(c[4], c[5], c[6], c[7]);
-            o[2] = make_float4(c[8], c[9], c[10], c[11]);
+            store_cepstra(out, dst, c);
         }
     }
 }

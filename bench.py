@@ -37,7 +37,7 @@ UNIT = 'frames/s'
 FRAME_PIXELS, FFT_LEN, MFCC_NUM = 1728, 512, 12
 IN_BYTES = FRAME_PIXELS * FFT_LEN * 4                    # 3 538 944 B of spectra per frame
 MFCC_BYTES = FRAME_PIXELS * MFCC_NUM * 4                 # 82 944 B MFCC image per frame
-ALGO_BYTES_MFCC_KERNEL = IN_BYTES + MFCC_BYTES           # what the fused MFCC kernel must move per frame
+ALGO_BYTES_MFCC_KERNEL = IN_BYTES + MFCC_BYTES + FRAME_PIXELS * 4   # 3 628 800 B per frame through the fused MFCC + energy kernel
 ALGO_BYTES_PATH = IN_BYTES + MFCC_BYTES + FRAME_PIXELS * 4   # 3 628 800 B per frame, MFCC + energy
 THRESHOLDS = (0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0)
 CPU_SAMPLE_FRAMES = 16                                   # BASELINE.json configs[0]
@@ -286,11 +286,11 @@ def run_gpu(args):
     achieved = (ALGO_BYTES_MFCC_KERNEL * frames_per_launch) / (mfcc_ms / max(mfcc_launches, 1) / 1e3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))['mfcc_banded_kernel_bytes_per_frame'] * frames_per_launch
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))['fused_kernel_bytes_per_frame'] * frames_per_launch
     except Exception:
         pass
     roofline = {
-        'bound': 'hbm', 'kernel': 'mfcc_banded_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+        'bound': 'hbm', 'kernel': 'mfcc_energy_fused_kernel (fused MFCC + energy persistent kernel)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
         'frac': achieved / peak, 'traffic': traffic,
         'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured copy)' if peaks else 'fallback 6650 GB/s',
         'frac_of_nominal_8TBs': achieved / 8000.0,

@@ -190,10 +190,17 @@ int64_t aig_launch_count(const aig_handle* h);
 
 /* Integer options, by name:
  *   "mfcc_variant"       ring geometry of the fused MFCC kernel (see aig_api.cu kVariants); -1 = default
- *   "chain_chunk_frames" frames per launch pair in aig_mfcc_energy (default 512: the chunk's MFCC
+ *   "chain_mode"         how aig_mfcc_energy runs its two stages: 2 (default) one fused persistent kernel
+ *                        (fused_kernel.cuh); 1 two kernels overlapped on two streams; 0 two kernels in sequence
+ *   "fused_variant"      ring geometry of the fused kernel (0..2)
+ *   "chain_energy_ctas_per_sm" footprint of the overlapped energy kernel in mode 1 (default 3)
+ *   "chain_chunk_frames" frames per launch pair in modes 0/1 (default 512: the chunk's MFCC
  *                        images, 42 MB, stay in the 126 MB L2 between the two kernels)
  *   "chain_overlap"      1 (default): the energy kernel of chunk i runs on a second stream while the
  *                        MFCC kernel of chunk i+1 streams from HBM; 0: both on the handle's stream
+ *   "keep_mfcc_in_l2"    fused kernel: 1 (default) L2 evict-last hint on the MFCC stores, so the energy warps'
+ *                        read-back one frame later still hits L2; 0: plain stores
+ *   "l2_evict_first"     1: L2 evict-first cache hint on the TMA spectrum loads; 0 (default): normal policy
  *   "profile"            1: bracket every MFCC / energy kernel launch with CUDA events on the stream it
  *                        is launched on (read back with aig_profile_read); 0 (default): off
  * Unknown names or out-of-range values return AIG_ERR_ARGUMENT. */

@@ -376,6 +376,51 @@ def test_mfcc_energy_chain_against_oracle_chain(path, torch):
     assert np.array_equal(d[2].cpu().numpy(), mask)
 
 
+@pytest.mark.parametrize('flip,normalize', [(True, True), (False, False)])
+def test_chain_modes_agree_bitwise(path, torch, flip, normalize):
+    """The fused persistent kernel (mode 2, every ring geometry), the two-stream overlap (mode 1) and the plain
+    sequence (mode 0) run the same arithmetic: identical bits, over enough frames (700 > 4 per CTA) to cycle
+    the frame hand-off slots and barrier phases several times."""
+    n = 700
+    base = torch.from_numpy(synth.power_frames(7, 41, 'chi2')).cuda()
+    power = base.repeat(100, 1, 1, 1)
+    results = []
+    try:
+        for mode, variant in ((0, 0), (1, 0), (2, 0), (2, 1), (2, 2)):
+            path.set_option('chain_mode', mode)
+            path.set_option('fused_variant', variant)
+            mfcc, energy, mask, mean = path.mfcc_energy(power, flip=flip, normalize_first=normalize, want_mean=True)
+            results.append((mfcc.clone(), energy.clone(), mask.clone(), mean.clone()))
+    finally:
+        path.set_option('chain_mode', 2)
+        path.set_option('fused_variant', 0)
+    ref = results[0]
+    for got in results[1:]:
+        for a, b in zip(ref, got):
+            assert torch.equal(a, b)
+    # and they are the 7-frame answer tiled (frames are independent)
+    small = path.mfcc_energy(base, flip=flip, normalize_first=normalize)
+    assert torch.equal(ref[0].view(100, 7, 36, 48, 12), small[0].unsqueeze(0).expand(100, -1, -1, -1, -1))
+    assert torch.equal(ref[2].view(100, 7, 36, 48), small[2].unsqueeze(0).expand(100, -1, -1, -1))
+    want_mfcc = oracle.mfcc_image(base.cpu().numpy(), flip=flip)
+    assert np.abs(small[0].cpu().numpy() - want_mfcc).max() <= MFCC_TOL
+
+
+@pytest.mark.parametrize('n', [1, 2, 147, 149, 300])
+def test_fused_kernel_ragged_frame_counts(path, torch, n):
+    base = torch.from_numpy(synth.power_frames(3, 42, 'lognormal')).cuda()
+    power = base.repeat((n + 2) // 3, 1, 1, 1)[:n].contiguous()
+    path.set_option('chain_mode', 2)
+    fused = path.mfcc_energy(power, flip=True, normalize_first=True)
+    path.set_option('chain_mode', 0)
+    try:
+        seq = path.mfcc_energy(power, flip=True, normalize_first=True)
+    finally:
+        path.set_option('chain_mode', 2)
+    for a, b in zip(fused, seq):
+        assert torch.equal(a, b)
+
+
 def test_launch_counter_counts_kernels(path):
     before = path.launch_count
     path.energy(synth.sigmoid_images(1, 0))

@@ -18,9 +18,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--frames', type=int, default=4096)
     ap.add_argument('--iters', type=int, default=5)
-    ap.add_argument('--variants', default='5,8')
-    ap.add_argument('--chunks', default='256,512,1024')
-    ap.add_argument('--energy-ctas', default='1,2,3')
+    ap.add_argument('--variants', default='0')
+    ap.add_argument('--chunks', default='512')
+    ap.add_argument('--energy-ctas', default='3')
     args = ap.parse_args()
     dev = torch.device('cuda', 0)
     stream = torch.cuda.current_stream()
@@ -30,13 +30,15 @@ def main():
     out = (torch.empty((n, 36, 48, 12), device=dev, dtype=torch.float32),
            torch.empty((n, 36, 48), device=dev, dtype=torch.float64),
            torch.empty((n, 36, 48), device=dev, dtype=torch.uint8))
-    for variant, overlap, chunk, ectas in itertools.product([int(v) for v in args.variants.split(',')], (1,),
-                                                            [int(c) for c in args.chunks.split(',')],
-                                                            [int(c) for c in args.energy_ctas.split(',')]):
-        path.set_option('chain_energy_ctas_per_sm', ectas)
-        path.set_option('mfcc_variant', variant)
-        path.set_option('chain_overlap', overlap)
-        path.set_option('chain_chunk_frames', chunk)
+    configs = [('fused v%d keep %d' % (v, k), {'chain_mode': 2, 'fused_variant': v, 'keep_mfcc_in_l2': k}) for k in (1, 0, 1, 0) for v in (2, 1)]
+    configs += [('overlap v%d chunk %d ectas %d' % (v, c, e),
+                 {'chain_mode': 1, 'mfcc_variant': v, 'chain_chunk_frames': c, 'chain_energy_ctas_per_sm': e})
+                for v in [int(x) for x in args.variants.split(',')] for c in [int(x) for x in args.chunks.split(',')]
+                for e in [int(x) for x in args.energy_ctas.split(',')]]
+    configs += [('sequential v5 chunk 4096', {'chain_mode': 0, 'mfcc_variant': 5, 'chain_chunk_frames': 4096})]
+    for name, opts in configs:
+        for k, v in opts.items():
+            path.set_option(k, v)
         for _ in range(2):
             path.mfcc_energy(power, flip=True, normalize_first=True, out=out)
         torch.cuda.synchronize()
@@ -52,8 +54,9 @@ def main():
         prof = path.profile_read()
         path.set_option('profile', 0)
         ms = sorted(times)[len(times) // 2]
-        print('variant %d overlap %d chunk %5d ectas %d: %.3f ms/pass  %.0f frames/s  | mfcc kernels %.3f ms, energy kernels %.3f ms per pass'
-              % (variant, overlap, chunk, ectas, ms, n / ms * 1e3, prof['mfcc'][0] / args.iters, prof['energy'][0] / args.iters), flush=True)
+        print('%-36s %.3f ms/pass (best %.3f)  %.0f frames/s  %.0f GB/s | mfcc/fused kernels %.3f ms, energy kernels %.3f ms per pass'
+              % (name, ms, min(times), n / ms * 1e3, n * 3628800 / ms / 1e6, prof['mfcc'][0] / args.iters,
+                 prof['energy'][0] / args.iters), flush=True)
 
 
 if __name__ == '__main__':

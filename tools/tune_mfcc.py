@@ -34,8 +34,9 @@ def main():
     power = torch.randn((n, 36, 48, 512), device=dev, dtype=torch.float32).square_()
     out = torch.empty((n * 1728, 12), device=dev, dtype=torch.float32)
     bytes_per_pass = n * 1728 * (2048 + 48)
-    for v in [int(x) for x in args.variants.split(',')]:
+    for v, hint in [(int(x), hh) for hh in (0, 1) for x in args.variants.split(',')]:
         path.set_mfcc_variant(v)
+        path.set_option('l2_evict_first', hint)
         for _ in range(2):
             path.mfcc_rows(power, out=out)
         torch.cuda.synchronize()
@@ -49,8 +50,8 @@ def main():
             times.append(e0.elapsed_time(e1))
         ms = sorted(times)[len(times) // 2]
         gbs = bytes_per_pass / ms / 1e6
-        print('variant %d: %.3f ms/pass (best %.3f)  %.0f frames/s  %.0f GB/s  %.3f of measured peak %.0f'
-              % (v, ms, min(times), n / ms * 1e3, gbs, gbs / peak, peak), flush=True)
+        print('variant %d hint %d: %.3f ms/pass (best %.3f)  %.0f frames/s  %.0f GB/s  %.3f of measured peak %.0f'
+              % (v, hint, ms, min(times), n / ms * 1e3, gbs, gbs / peak, peak), flush=True)
     # energy stage on the MFCC images just produced
     img = out.view(n, 36, 48, 12)
     for _ in range(2):
