@@ -79,9 +79,19 @@ def cpu_chain(oracle, power):
     return oracle.success_counts(scores, THRESHOLDS)
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core NumPy's BLAS can."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=int(os.cpu_count() or 1), user_api='blas')
+    except Exception:
+        pass
+
+
 def time_cpu(steps, warmup, budget_s=None):
     from acoustic_image_generation_b200 import synth
     from oracle import acoustic_oracle as oracle
+    use_all_host_threads()
     power = synth.power_frames(CPU_SAMPLE_FRAMES, 0, 'chi2')
     for _ in range(warmup):
         cpu_chain(oracle, power)

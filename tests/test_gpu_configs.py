@@ -1,0 +1,109 @@
+"""BASELINE.json configs[2] and configs[3] at their stated sizes, through the C ABI on a B200.
+
+The oracle runs on a random subset (it needs ~1 ms per frame); the full-size results are held to
+size-independent properties: the sweep counts equal the counts recomputed from the per-frame integer (I, U),
+the success curve is non-increasing, shards merge to the global result, AUC of merged counts == global AUC.
+"""
+import numpy as np
+import pytest
+
+import acoustic_image_generation_b200 as aig
+from acoustic_image_generation_b200 import sharding, synth
+from oracle import acoustic_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+REF_THR = list(oracle.REFERENCE_THRESHOLDS)
+
+
+@pytest.fixture(scope='module')
+def path():
+    p = aig.AcousticPath(0)
+    yield p
+    p.close()
+
+
+def counts_from_ratios(num, den, thr):
+    with np.errstate(invalid='ignore', divide='ignore'):
+        score = num.astype(np.float64) / den.astype(np.float64)
+    return oracle.success_counts(score, thr)[0]
+
+
+@pytest.mark.parametrize('shape', [(224, 224), (224, 298)])
+def test_config2_flickr_5k_frames_heatmap_and_ciou_sweep(path, shape):
+    """configs[2]: energy heat map up-sampled to 224x224 (BASELINE) / 224x298 (reference) + consensus-IoU sweep over
+    101 thresholds (and the reference's 11) on FlickrSoundNet-shaped boxes, 5000 frames."""
+    n = 5000
+    pred = synth.smooth_images(n, 60)
+    boxes = synth.flickr_boxes(n, 61, shape[0], shape[1])
+    energy, masks = path.energy(pred)
+    heat = path.heatmap(energy, *shape)
+    assert heat.shape == (n,) + shape and heat.dtype == np.float32
+    assert np.all(heat.reshape(n, -1).min(1) == 0.0) and np.all(heat.reshape(n, -1).max(1) == 1.0)
+    thr101 = np.linspace(0, 1, 101)
+    i2, u2, pos101, num = path.ciou_sweep(masks, *boxes, thr101, out_hw=shape)
+    _, _, pos11, num11 = path.ciou_sweep(masks, *boxes, REF_THR, out_hw=shape)
+    assert num == n and num11 == n
+    assert np.array_equal(pos101, counts_from_ratios(i2, u2, thr101))
+    assert np.array_equal(pos11, counts_from_ratios(i2, u2, REF_THR))
+    assert np.all(np.diff(pos101) <= 0) and pos101[-1] == 0
+    assert np.all(i2 <= u2) and np.all(u2 <= 2 * shape[0] * shape[1])
+    # oracle on a random subset
+    rng = np.random.default_rng(0)
+    for h in rng.choice(n, 48, replace=False):
+        want_e = oracle.find_logen(pred[h].copy())
+        assert np.abs(energy[h] - want_e).max() <= 1e-13 * np.abs(want_e).max()
+        want_m = oracle.mean_mask(want_e)
+        assert np.array_equal(masks[h], want_m)
+        assert np.abs(heat[h] - oracle.heatmap(want_e, *shape)).max() <= 1e-4
+        gt = oracle.boxes_to_consensus(boxes[0][h], boxes[1][h], boxes[2][h], boxes[3][h], *shape)
+        wi, wu, _ = oracle.consensus_iou(gt, oracle.resize_mask(want_m, *shape))
+        assert (int(i2[h]), int(u2[h])) == (wi, wu)
+    auc101 = aig.auc(thr101, aig.success_rates(pos101, num))
+    assert abs(auc101 - oracle.auc(thr101, oracle.success_rates(pos101, num))) <= 1e-12
+    assert 0.0 <= auc101 <= 1.0
+
+
+@pytest.mark.parametrize('frames_per_clip,n_clips', [(120, 16), (300, 8)])
+def test_config3_clip_stream_sharded_by_clip(path, frames_per_clip, n_clips):
+    """configs[3]: VGGSound-shaped stream of 10 s clips (120 frames at the reference's 12 fps, 300 at BASELINE's
+    30 fps): MFCC + energy + per-clip and global AUC; clips sharded over 2 / 4 / 8 ranks merge to the global counts."""
+    import torch
+    n = frames_per_clip * n_clips
+    base = torch.from_numpy(synth.power_frames(24, 70, 'chi2')).cuda()
+    idx = torch.from_numpy(np.random.default_rng(1).integers(0, 24, n)).cuda()
+    power_a = base[idx]                                   # "real" stream
+    power_b = base[torch.roll(idx, 1)]                    # "generated" stream: neighbouring frame
+    _, _, mask_a = path.mfcc_energy(power_a, flip=True, normalize_first=True)
+    _, _, mask_b = path.mfcc_energy(power_b, flip=True, normalize_first=True)
+    inter, union, pos, num = path.iou_sweep(mask_a, mask_b, REF_THR)
+    inter, union = inter.cpu().numpy(), union.cpu().numpy()
+    assert num == n and np.array_equal(pos, counts_from_ratios(inter, union, REF_THR))
+    global_auc = aig.auc(REF_THR, aig.success_rates(pos, num))
+    # per-clip AUC from per-clip sweeps == AUC recomputed from the per-frame (I, U)
+    for c in range(0, n_clips, max(1, n_clips // 4)):
+        lo, hi = c * frames_per_clip, (c + 1) * frames_per_clip
+        _, _, cpos, cnum = path.iou_sweep(mask_a[lo:hi], mask_b[lo:hi], REF_THR)
+        assert cnum == frames_per_clip
+        assert np.array_equal(cpos, counts_from_ratios(inter[lo:hi], union[lo:hi], REF_THR))
+    # clip-major shards merge to the global result
+    for world in (2, 4, 8):
+        shards = []
+        for rank in range(world):
+            c0, c1, f0, f1 = sharding.shard_clips(n_clips, frames_per_clip, rank, world)
+            if f1 > f0:
+                _, _, spos, snum = path.iou_sweep(mask_a[f0:f1], mask_b[f0:f1], REF_THR)
+            else:
+                spos, snum = np.zeros(len(REF_THR), np.int64), 0
+            shards.append(np.concatenate([spos, [snum]]))
+        merged = sharding.merge_counts(shards)
+        assert np.array_equal(merged[:-1], pos) and merged[-1] == n
+        assert aig.auc(REF_THR, aig.success_rates(merged[:-1], merged[-1])) == global_auc
+    # oracle on a few frames of the stream
+    want = oracle.mfcc_image(base.cpu().numpy(), flip=True)
+    _, want_masks = oracle.energy_stage(want, normalize_first=True)
+    host_idx = idx.cpu().numpy()
+    flips = 0
+    for h in range(0, n, max(1, n // 40)):
+        flips += int((mask_a[h].cpu().numpy() != want_masks[host_idx[h]]).sum())
+    print('clip stream: boundary-pixel disagreements on sampled frames: %d' % flips)
+    assert flips <= 8
