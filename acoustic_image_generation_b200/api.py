@@ -148,6 +148,30 @@ class AcousticPath:
             return torch.empty(shape, dtype=_TORCH_DTYPES[np.dtype(dtype)], device=dev)
         return np.empty(shape, dtype=dtype)
 
+    # -- multi-GPU ----------------------------------------------------------------------------
+    def init_comm(self, rank=None, world=None, group=None):
+        """Join the NCCL communicator of libaig (aig_comm_init).  The 128-byte unique id is created on rank 0
+        and shipped through the already-initialised torch.distributed group, which is used only for that."""
+        import torch.distributed as dist
+        rank = dist.get_rank(group) if rank is None else rank
+        world = dist.get_world_size(group) if world is None else world
+        ident = (ctypes.c_uint8 * 128)()
+        if rank == 0:
+            code = self._lib.aig_comm_unique_id(ident)
+            if code != 0:
+                raise AigError(code, (self._lib.aig_last_error(None) or b'').decode())
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        ident = (ctypes.c_uint8 * 128).from_buffer_copy(box[0])
+        self._check(self._lib.aig_comm_init(self._h, ident, int(rank), int(world)))
+
+    def allreduce_counts(self, counts):
+        """In-place sum of an int64 count vector over the ranks of init_comm (identity without a communicator);
+        a CUDA tensor stays on the device and the reduction is enqueued on the handle's stream."""
+        arg = _Arg(counts, np.int64, writable=True)
+        self._check(self._lib.aig_allreduce_counts(self._h, arg.ptr, int(np.prod(arg.shape))))
+        return counts
+
     # -- tables -------------------------------------------------------------------------------
     def set_tables(self, filter_mat, dct_base, lifter, mfnorm):
         bank = np.ascontiguousarray(filter_mat, dtype=np.float64)

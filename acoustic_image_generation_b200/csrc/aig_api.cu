@@ -63,6 +63,34 @@ MemKind classify(const void* p) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ---- NCCL through dlopen --------------------------------------------------------------------------
+struct NcclId { char internal[AIG_COMM_ID_BYTES]; };
+struct NcclApi {
+    bool tried = false, ok = false;
+    int (*get_unique_id)(NcclId*) = nullptr;
+    int (*comm_init_rank)(void**, int, NcclId, int) = nullptr;
+    int (*all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*comm_destroy)(void*) = nullptr;
+    const char* (*get_error_string)(int) = nullptr;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    if (api.tried) return api;
+    api.tried = true;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return api;
+    api.get_unique_id = reinterpret_cast<decltype(api.get_unique_id)>(dlsym(lib, "ncclGetUniqueId"));
+    api.comm_init_rank = reinterpret_cast<decltype(api.comm_init_rank)>(dlsym(lib, "ncclCommInitRank"));
+    api.all_reduce = reinterpret_cast<decltype(api.all_reduce)>(dlsym(lib, "ncclAllReduce"));
+    api.comm_destroy = reinterpret_cast<decltype(api.comm_destroy)>(dlsym(lib, "ncclCommDestroy"));
+    api.get_error_string = reinterpret_cast<decltype(api.get_error_string)>(dlsym(lib, "ncclGetErrorString"));
+    api.ok = api.get_unique_id && api.comm_init_rank && api.all_reduce && api.comm_destroy;
+    return api;
+}
+constexpr int kNcclInt64 = 4;   // ncclInt64
+constexpr int kNcclSum = 0;     // ncclSum
+
 }  // namespace
 
 struct aig_handle {
@@ -98,6 +126,9 @@ struct aig_handle {
     struct Span { cudaEvent_t start, stop; int kind; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
+    // NCCL communicator (resolved with dlopen; see aig_comm_init)
+    void* comm = nullptr;
+    int comm_world = 1;
     // misc
     int variant = -1;
     int64_t launches = 0;
@@ -538,6 +569,7 @@ int aig_destroy(aig_handle* h) {
         if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
         if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
     }
+    if (h->comm != nullptr) { nccl().comm_destroy(h->comm); h->comm = nullptr; }
     for (auto& b : h->overflow) cudaFree(b.first);
     if (h->arena) cudaFree(h->arena);
     if (h->d_tables) cudaFree(h->d_tables);
@@ -896,6 +928,60 @@ int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, cons
         reinterpret_cast<unsigned long long*>(d_num));
     rc = scope.done("ciou_sweep_kernel");
     if (rc != AIG_OK) return rc;
+    return io.finish();
+}
+
+int aig_comm_unique_id(uint8_t* id_out) {
+    if (id_out == nullptr) return AIG_ERR_ARGUMENT;
+    NcclApi& api = nccl();
+    if (!api.ok) { g_create_error = "aig_comm_unique_id: libnccl.so.2 could not be loaded"; return AIG_ERR_NO_DEVICE; }
+    NcclId id;
+    const int r = api.get_unique_id(&id);
+    if (r != 0) { g_create_error = "aig_comm_unique_id: ncclGetUniqueId failed"; return AIG_ERR_CUDA_BASE; }
+    std::memcpy(id_out, id.internal, AIG_COMM_ID_BYTES);
+    return AIG_OK;
+}
+
+int aig_comm_destroy(aig_handle* h) {
+    if (h == nullptr) return AIG_ERR_ARGUMENT;
+    if (h->comm != nullptr) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+        nccl().comm_destroy(h->comm);
+        h->comm = nullptr;
+        h->comm_world = 1;
+    }
+    return AIG_OK;
+}
+
+int aig_comm_init(aig_handle* h, const uint8_t* id, int rank, int world) {
+    if (h == nullptr) return AIG_ERR_ARGUMENT;
+    if (id == nullptr || world < 1 || rank < 0 || rank >= world) return h->fail(AIG_ERR_ARGUMENT, "aig_comm_init: bad rank/world %d/%d", rank, world);
+    NcclApi& api = nccl();
+    if (!api.ok) return h->fail(AIG_ERR_NO_DEVICE, "aig_comm_init: libnccl.so.2 could not be loaded");
+    aig_comm_destroy(h);
+    AIG_CK(cudaSetDevice(h->device));
+    NcclId nid;
+    std::memcpy(nid.internal, id, AIG_COMM_ID_BYTES);
+    const int r = api.comm_init_rank(&h->comm, world, nid, rank);
+    if (r != 0) {
+        h->comm = nullptr;
+        return h->fail(AIG_ERR_CUDA_BASE, "ncclCommInitRank failed: %s", api.get_error_string ? api.get_error_string(r) : "?");
+    }
+    h->comm_world = world;
+    return AIG_OK;
+}
+
+int aig_allreduce_counts(aig_handle* h, int64_t* counts, int n) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (counts == nullptr || n < 0) return h->fail(AIG_ERR_ARGUMENT, "aig_allreduce_counts: bad buffer");
+    if (h->comm == nullptr || h->comm_world == 1 || n == 0) return AIG_OK;    // single rank: identity
+    Io io(h);
+    int64_t* d = io.inout(counts, static_cast<size_t>(n));
+    if (io.failed) return io.finish();
+    const int r = nccl().all_reduce(d, d, static_cast<size_t>(n), kNcclInt64, kNcclSum, h->comm, h->stream);
+    if (r != 0) return h->fail(AIG_ERR_CUDA_BASE, "ncclAllReduce failed: %s", nccl().get_error_string ? nccl().get_error_string(r) : "?");
     return io.finish();
 }
 

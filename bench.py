@@ -188,6 +188,8 @@ def run_gpu(args):
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'           # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
     torch.cuda.set_device(local)
@@ -202,6 +204,8 @@ def run_gpu(args):
 
     stream = torch.cuda.current_stream()
     path = aig.AcousticPath(local, stream=stream.cuda_stream)
+    if world > 1:
+        path.init_comm()                            # libaig's own NCCL communicator (aig_comm_init)
     frames = args.frames
     # synthetic spectra generated on the device, chi-square like synth.power_frames (squared normal), seeded per rank
     gen = torch.Generator(device=dev)
@@ -224,6 +228,8 @@ def run_gpu(args):
 
     for _ in range(args.warmup):
         step()
+    if world > 1:
+        path.allreduce_counts(counts)               # warm-up: NCCL sets up its channels on the first collective
     barrier()
     counts.zero_()
     path.set_option('profile', 1)
@@ -236,7 +242,8 @@ def run_gpu(args):
     for _ in range(args.steps):
         step()
     if world > 1:
-        dist.all_reduce(counts)                     # the path's only exchange: int64[K+1] success counts
+        path.allreduce_counts(counts)               # the path's only exchange: int64[K+1] success counts, NCCL via libaig,
+                                                    # enqueued on the same stream as the sweeps that filled the vector
     e1.record(stream)
     barrier()
     elapsed_ms = e0.elapsed_time(e1)

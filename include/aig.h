@@ -179,6 +179,25 @@ int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, cons
                    const double* thr, int k, int64_t* inter2_out, int64_t* union2_out,
                    int64_t* pos_inout, int64_t* num_inout);
 
+/* ---- multi-GPU: the path's only exchange ------------------------------------------------------
+ * Frames shard across GPUs with no data-path collective; at the end of an evaluation the int64[K+1]
+ * count vector (pos[0..K-1], num) is summed over ranks.  The reference has no counterpart (single GPU,
+ * one whole run per threshold, scripts/iou.bash:47-53).  NCCL is resolved at run time with
+ * dlopen("libnccl.so.2") - in a torch process that is torch's bundled NCCL - so libaig has no link-time
+ * dependency on it; without NCCL these calls return AIG_ERR_NO_DEVICE.
+ *   aig_comm_unique_id   rank 0 creates the 128-byte NCCL unique id; the host program ships it to the other
+ *                        ranks (torch.distributed broadcast, a file, MPI ...)
+ *   aig_comm_init        every rank: join the communicator on the handle's device
+ *   aig_allreduce_counts in-place sum of n int64 values over all ranks, enqueued on the handle's stream
+ *                        (device buffer: asynchronous, ordered after the sweeps that filled it; host buffer:
+ *                        staged and synchronous).  With no communicator (single rank) it is the identity.
+ *   aig_comm_destroy     leave the communicator (also done by aig_destroy) */
+#define AIG_COMM_ID_BYTES 128
+int aig_comm_unique_id(uint8_t* id_out);
+int aig_comm_init(aig_handle* h, const uint8_t* id, int rank, int world);
+int aig_allreduce_counts(aig_handle* h, int64_t* counts, int n);
+int aig_comm_destroy(aig_handle* h);
+
 /* areaundercurve.py:32-37: sklearn.metrics.auc on the reversed (descending) threshold / success-rate
  * arrays == direction * trapezoid.  Host-side, float64.  thr / value are host arrays of length k. */
 int aig_auc(const double* thr, const double* value, int k, double* auc_out);
