@@ -19,7 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 NVCC_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-Xcompiler', '-fPIC', '-shared', '-ldl']
 SOURCES = ['aig_api.cu']
-DEPENDS = ['aig_api.cu', 'aig_common.cuh', 'mfcc_kernel.cuh', 'energy_kernel.cuh', 'score_kernel.cuh', 'fused_kernel.cuh',
+DEPENDS = ['aig_api.cu', 'aig_common.cuh', 'mfcc_kernel.cuh', 'energy_kernel.cuh', 'score_kernel.cuh', 'fused_kernel.cuh', 'frontend_kernel.cuh',
            'mel_program_ref.inc', 'mel_tables_ref.inc', os.path.join(INCLUDE, 'aig.h')]
 
 AIG_OK = 0
@@ -91,6 +91,10 @@ SIGNATURES = {
     'aig_mfcc_energy': (_int, [_p, _p, _i64, _int, _int, _p, _p, _p, _p]),
     'aig_iou_sweep': (_int, [_p, _p, _p, _i64, _p, _int, _p, _p, _p, _p]),
     'aig_ciou_sweep': (_int, [_p, _p, _p, _p, _p, _p, _i64, _int, _int, _p, _int, _p, _p, _p, _p]),
+    'aig_power_spectrum': (_int, [_p, _p, _int, _i64, _p, _p]),
+    'aig_filtfilt': (_int, [_p, _p, _int, _i64, _int, _p, _p, _p, _int, _p]),
+    'aig_normalize_mfcc': (_int, [_p, _p, _i64, _p]),
+    'aig_tile_mfcc': (_int, [_p, _p, _i64, _int, _p]),
     'aig_comm_unique_id': (_int, [_p]),
     'aig_comm_init': (_int, [_p, _p, _int, _int]),
     'aig_allreduce_counts': (_int, [_p, _p, _int]),

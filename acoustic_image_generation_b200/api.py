@@ -214,6 +214,65 @@ class AcousticPath:
         rows = self.mfcc_rows(a.keep, flip180=flip, frame_pixels=FRAME_PIXELS)
         return rows.reshape(a.shape[0], FRAME_H, FRAME_W, MFCC_NUM)
 
+    # -- callers either side of the path ----------------------------------
+    @staticmethod
+    def _audio_arg(audio):
+        """Audio rows as a 4-byte buffer: int32 (tfrecord samples) stays int32, everything else becomes float32."""
+        if _is_torch(audio):
+            is_int = audio.dtype == _torch().int32
+        else:
+            is_int = np.asarray(audio).dtype == np.int32
+        return _Arg(audio, np.int32 if is_int else np.float32), int(is_int)
+
+    def power_spectrum(self, audio, window='tukey'):
+        """[n, 1024] audio -> float32 [n, 512] power: window, 1024-point rFFT, drop Nyquist, |.|^2
+        (outdoor_data_mfcc.py:799-804).  ``window``: 'tukey' (reference), None (frames.py variant) or a float64[1024]."""
+        a, is_int = self._audio_arg(audio)
+        n = self._frames(a.shape, 1024)
+        win = tables.tukey_window() if isinstance(window, str) else window
+        win = None if win is None else np.ascontiguousarray(win, dtype=np.float64)
+        if win is not None and win.shape != (1024,):
+            raise ValueError('window must have 1024 entries')
+        res = self._empty((n, 512), np.float32, a)
+        self._check(self._lib.aig_power_spectrum(self._h, a.ptr, is_int, n, None if win is None else win.ctypes.data,
+                                                 _Arg(res, np.float32, True).ptr))
+        return res
+
+    def build_spectrograms(self, audio):
+        """_build_spectrograms_function (outdoor_data_mfcc.py:796-824): [n, 1024] audio -> float32 [n, 12] MFCC,
+        spectrum and MFCC kernels chained on the device."""
+        return self.mfcc_rows(self.power_spectrum(audio))
+
+    def butter_lowpass_filter(self, data, cutoff=125, order=10, sample_rate=12288):
+        """butter_lowpass_filter (outdoor_data_mfcc.py:571-575): zero-phase order-10 Butterworth low-pass along rows,
+        float32 out."""
+        a, is_int = self._audio_arg(data)
+        if len(a.shape) < 1:
+            raise ValueError('data must have at least one axis')
+        length = a.shape[-1]
+        n = int(np.prod(a.shape)) // length
+        b, acoef, zi = tables.butter_lowpass(sample_rate, cutoff, order)
+        res = self._empty(a.shape, np.float32, a)
+        self._check(self._lib.aig_filtfilt(self._h, a.ptr, is_int, n, int(length), b.ctypes.data, acoef.ctypes.data,
+                                           zi.ctypes.data, len(b), _Arg(res, np.float32, True).ptr))
+        return res
+
+    def normalize_mfcc(self, mfcc):
+        """Per-vector float32 min-max of [n, 12] MFCCs (_normalize_mfcc, outdoor_data_mfcc.py:696-703)."""
+        a = _Arg(mfcc, np.float32)
+        n = self._frames(a.shape, MFCC_NUM)
+        res = self._empty(a.shape, np.float32, a)
+        self._check(self._lib.aig_normalize_mfcc(self._h, a.ptr, n, _Arg(res, np.float32, True).ptr))
+        return res
+
+    def tile_mfcc(self, mfcc, normalize=False):
+        """mfccmap: [B, 12] -> [B, 36, 48, 12] (trainer/mfcctrainer.py:38-40), optionally normalising each vector first."""
+        a = _Arg(mfcc, np.float32)
+        n = self._frames(a.shape, MFCC_NUM)
+        res = self._empty((n, FRAME_H, FRAME_W, MFCC_NUM), np.float32, a)
+        self._check(self._lib.aig_tile_mfcc(self._h, a.ptr, n, int(bool(normalize)), _Arg(res, np.float32, True).ptr))
+        return res
+
     # -- stage 2 ------------------------------------------------------------------------------
     def normalize_images(self, images):
         """Per-frame (x - min) / max(x - min) in float32 over [N, 36, 48, 12] (outdoor_data_mfcc.py:672-679)."""
@@ -440,6 +499,29 @@ def get_feats(fft_len, beam, mfcc_num, dct_base, mfnorm, lifter, filter_mat):
     finally:
         path.set_tables(*tables.reference_tables())
     return rows.astype(np.float64) if isinstance(rows, np.ndarray) else rows
+
+
+def _build_spectrograms_function(audio_data):
+    """Drop-in for _build_spectrograms_function (outdoor_data_mfcc.py:796-824, iouenergythreshold.py:238-266)."""
+    return default_path().build_spectrograms(audio_data)
+
+
+def butter_lowpass_filter(data, cutoff=125, order=10, sample_rate=12288):
+    """Drop-in for ActionsDataLoader.butter_lowpass_filter (outdoor_data_mfcc.py:571-575)."""
+    return default_path().butter_lowpass_filter(data, cutoff, order, sample_rate)
+
+
+def _normalize_mfcc(mfcc):
+    """Drop-in for ActionsDataLoader._normalize_mfcc (outdoor_data_mfcc.py:696-703) on one 12-vector."""
+    return default_path().normalize_mfcc(mfcc).reshape(MFCC_NUM)
+
+
+def _map_func_mfcc(audio_images, audio_samples, video_images, action, location, filtered_audio_samples):
+    """Drop-in for ActionsDataLoader._map_func_mfcc (outdoor_data_mfcc.py:681-694): elements 1 and 5 ([T, 12] MFCCs of
+    the raw and the low-passed audio) are normalised vector by vector."""
+    path = default_path()
+    return (audio_images, path.normalize_mfcc(audio_samples), video_images, action, location,
+            path.normalize_mfcc(filtered_audio_samples))
 
 
 def find_logen(mfcc):

@@ -20,6 +20,7 @@
 #include "../../include/aig.h"
 #include "aig_common.cuh"
 #include "energy_kernel.cuh"
+#include "frontend_kernel.cuh"
 #include "fused_kernel.cuh"
 #include "mfcc_kernel.cuh"
 #include "score_kernel.cuh"
@@ -126,6 +127,7 @@ struct aig_handle {
     struct Span { cudaEvent_t start, stop; int kind; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
+    double2* d_twiddle = nullptr;       // exp(-2*pi*i*k/1024), k < 512 (aig_power_spectrum)
     // NCCL communicator (resolved with dlopen; see aig_comm_init)
     void* comm = nullptr;
     int comm_world = 1;
@@ -573,6 +575,7 @@ int aig_destroy(aig_handle* h) {
     for (auto& b : h->overflow) cudaFree(b.first);
     if (h->arena) cudaFree(h->arena);
     if (h->d_tables) cudaFree(h->d_tables);
+    if (h->d_twiddle) cudaFree(h->d_twiddle);
     cudaGetLastError();
     delete h;
     return AIG_OK;
@@ -927,6 +930,105 @@ int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, cons
         reinterpret_cast<long long*>(d_union), reinterpret_cast<unsigned long long*>(d_pos),
         reinterpret_cast<unsigned long long*>(d_num));
     rc = scope.done("ciou_sweep_kernel");
+    if (rc != AIG_OK) return rc;
+    return io.finish();
+}
+
+int aig_power_spectrum(aig_handle* h, const void* audio, int audio_is_int32, int64_t n_rows, const double* window,
+                       float* power_out) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (n_rows < 0 || (n_rows > 0 && (!audio || !power_out))) return h->fail(AIG_ERR_ARGUMENT, "aig_power_spectrum: bad buffers");
+    if (n_rows == 0) return AIG_OK;
+    if (h->d_twiddle == nullptr) {
+        std::vector<double2> tw(kAudioSamples / 2);
+        for (int k = 0; k < kAudioSamples / 2; ++k) {
+            const double ang = -2.0 * 3.14159265358979323846 * k / kAudioSamples;
+            tw[k] = make_double2(std::cos(ang), std::sin(ang));
+        }
+        if (cudaMalloc(&h->d_twiddle, tw.size() * sizeof(double2)) != cudaSuccess) {
+            cudaGetLastError();
+            return h->fail(AIG_ERR_ALLOC, "aig_power_spectrum: cudaMalloc failed");
+        }
+        AIG_CK(cudaMemcpy(h->d_twiddle, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    }
+    Io io(h);
+    const size_t n = static_cast<size_t>(n_rows);
+    const float* d_in = io.in(static_cast<const float*>(audio), n * kAudioSamples);      // 4-byte samples either way
+    const double* d_win = io.in(window, kAudioSamples);
+    float* d_out = io.out(power_out, n * (kAudioSamples / 2));
+    if (io.failed) return io.finish();
+    const int grid = frames_grid(h, n_rows, 8);
+    LaunchScope scope(h, h->stream, kKindOther);
+    if (audio_is_int32)
+        spectrum_kernel<int><<<grid, kSpectrumThreads, 0, h->stream>>>(reinterpret_cast<const int*>(d_in), n_rows, d_win, h->d_twiddle, d_out);
+    else
+        spectrum_kernel<float><<<grid, kSpectrumThreads, 0, h->stream>>>(d_in, n_rows, d_win, h->d_twiddle, d_out);
+    rc = scope.done("spectrum_kernel");
+    if (rc != AIG_OK) return rc;
+    return io.finish();
+}
+
+int aig_filtfilt(aig_handle* h, const void* x, int x_is_int32, int64_t n_rows, int length, const double* b, const double* a,
+                 const double* zi, int ntaps, float* y_out) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (n_rows < 0 || !b || !a || !zi || (n_rows > 0 && (!x || !y_out))) return h->fail(AIG_ERR_ARGUMENT, "aig_filtfilt: bad buffers");
+    if (ntaps < 2 || ntaps > kMaxTaps) return h->fail(AIG_ERR_ARGUMENT, "aig_filtfilt: ntaps %d outside 2..%d", ntaps, kMaxTaps);
+    const int pad = 3 * ntaps;
+    if (length <= pad) return h->fail(AIG_ERR_ARGUMENT, "aig_filtfilt: rows of %d samples are not longer than padlen %d", length, pad);
+    if (a[0] == 0.0) return h->fail(AIG_ERR_ARGUMENT, "aig_filtfilt: a[0] is zero");
+    if (n_rows == 0) return AIG_OK;
+    Io io(h);
+    const size_t n = static_cast<size_t>(n_rows);
+    std::vector<double> coef(3 * ntaps - 1);
+    for (int i = 0; i < ntaps; ++i) { coef[i] = b[i]; coef[ntaps + i] = a[i]; }
+    for (int i = 0; i < ntaps - 1; ++i) coef[2 * ntaps + i] = zi[i];
+    const float* d_x = io.in(static_cast<const float*>(x), n * length);
+    const double* d_coef = io.in(coef.data(), coef.size());
+    float* d_y = io.out(y_out, n * length);
+    double* d_scratch = static_cast<double*>(scratch(h, n * (length + 2 * pad) * sizeof(double)));
+    if (io.failed || !d_scratch) return io.finish();
+    io.any_host = true;                          // `coef` is a stack-lifetime host buffer: complete before returning
+    const int threads = 32, blocks = static_cast<int>((n_rows + threads - 1) / threads);
+    LaunchScope scope(h, h->stream, kKindOther);
+    if (x_is_int32)
+        filtfilt_kernel<int><<<blocks, threads, 0, h->stream>>>(reinterpret_cast<const int*>(d_x), n_rows, length, ntaps, pad, d_coef, d_scratch, d_y);
+    else
+        filtfilt_kernel<float><<<blocks, threads, 0, h->stream>>>(d_x, n_rows, length, ntaps, pad, d_coef, d_scratch, d_y);
+    rc = scope.done("filtfilt_kernel");
+    if (rc != AIG_OK) return rc;
+    return io.finish();
+}
+
+int aig_normalize_mfcc(aig_handle* h, const float* mfcc, int64_t n, float* out) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (n < 0 || (n > 0 && (!mfcc || !out))) return h->fail(AIG_ERR_ARGUMENT, "aig_normalize_mfcc: bad buffers");
+    if (n == 0) return AIG_OK;
+    Io io(h);
+    const float* d_in = io.in(mfcc, static_cast<size_t>(n) * kMfccNum);
+    float* d_out = io.out(out, static_cast<size_t>(n) * kMfccNum);
+    if (io.failed) return io.finish();
+    LaunchScope scope(h, h->stream, kKindOther);
+    normalize_mfcc_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, h->stream>>>(d_in, n, d_out);
+    rc = scope.done("normalize_mfcc_kernel");
+    if (rc != AIG_OK) return rc;
+    return io.finish();
+}
+
+int aig_tile_mfcc(aig_handle* h, const float* mfcc, int64_t n, int normalize, float* map_out) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (n < 0 || (n > 0 && (!mfcc || !map_out))) return h->fail(AIG_ERR_ARGUMENT, "aig_tile_mfcc: bad buffers");
+    if (n == 0) return AIG_OK;
+    Io io(h);
+    const float* d_in = io.in(mfcc, static_cast<size_t>(n) * kMfccNum);
+    float* d_out = io.out(map_out, static_cast<size_t>(n) * kFrameValues);
+    if (io.failed) return io.finish();
+    LaunchScope scope(h, h->stream, kKindOther);
+    tile_mfcc_kernel<<<frames_grid(h, n, 8), kTileThreads, 0, h->stream>>>(d_in, n, normalize, d_out);
+    rc = scope.done("tile_mfcc_kernel");
     if (rc != AIG_OK) return rc;
     return io.finish();
 }

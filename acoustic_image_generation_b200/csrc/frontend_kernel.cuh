@@ -1,0 +1,159 @@
+// "Next" rows N1 and N2: the callers' arithmetic on either side of the hot path.
+//
+// N1  spectrum_kernel   front half of _build_spectrograms_function (dataloader/outdoor_data_mfcc.py:796-805):
+//                       Tukey window * audio -> 1024-point real FFT -> drop Nyquist -> squared magnitude,
+//                       float64 like NumPy, producing the [n, 512] power rows the MFCC kernel consumes.
+//     filtfilt_kernel   butter_lowpass_filter (:565-575): scipy.signal.filtfilt of an order-10 Butterworth -
+//                       odd extension, forward/backward direct-form-II-transposed IIR with lfilter_zi initial
+//                       state, float64, in scipy's operation order (no FMA contraction: the order-10 transfer
+//                       function is ill-conditioned and amplifies any reordering).
+// N2  normalize_mfcc_kernel   _normalize_mfcc (:696-703): per-vector float32 min-max of the 12 MFCCs.
+//     tile_mfcc_kernel        mfccmap = tile(reshape(mfcc, (-1,1,12)), (1, 36*48, 1)) (trainer/mfcctrainer.py:38-40,
+//                             iouenergythreshold.py:99-101): the [B,36,48,12] conditioning image of the UNet.
+#pragma once
+
+#include <type_traits>
+
+#include "aig_common.cuh"
+
+namespace aig {
+
+constexpr int kAudioSamples = 1024;     // _NUMBER_OF_SAMPLES (outdoor_data_mfcc.py:9)
+constexpr int kSpectrumThreads = 256;
+
+// ---- N1: windowed power spectrum --------------------------------------------------------------------
+// twiddle[k] = exp(-2*pi*i*k/1024), k < 512, float64, built on the host.
+template <typename In>
+__global__ void __launch_bounds__(kSpectrumThreads)
+spectrum_kernel(const In* __restrict__ audio, long long n_rows, const double* __restrict__ window,
+                const double2* __restrict__ twiddle, float* __restrict__ power) {
+    __shared__ double s_re[kAudioSamples];
+    __shared__ double s_im[kAudioSamples];
+    const int tid = threadIdx.x;
+    for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        __syncthreads();
+        // load in bit-reversed order (decimation in time), real input
+        for (int i = tid; i < kAudioSamples; i += kSpectrumThreads) {
+            double v = static_cast<double>(audio[row * kAudioSamples + i]);
+            if (window != nullptr) v = __dmul_rn(v, window[i]);
+            const int r = __brev(static_cast<unsigned>(i)) >> 22;     // 10-bit reversal
+            s_re[r] = v;
+            s_im[r] = 0.0;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int half = 1; half < kAudioSamples; half <<= 1) {        // 10 radix-2 stages
+            const int step = (kAudioSamples / 2) / half;              // twiddle stride
+            for (int b = tid; b < kAudioSamples / 2; b += kSpectrumThreads) {
+                const int j = b & (half - 1);
+                const int lo = ((b - j) << 1) + j, hi = lo + half;
+                const double2 w = twiddle[j * step];
+                const double xr = s_re[hi], xi = s_im[hi];
+                const double tr = xr * w.x - xi * w.y, ti = xr * w.y + xi * w.x;
+                const double ur = s_re[lo], ui = s_im[lo];
+                s_re[lo] = ur + tr; s_im[lo] = ui + ti;
+                s_re[hi] = ur - tr; s_im[hi] = ui - ti;
+            }
+            __syncthreads();
+        }
+        // np.abs(rfft)[:, :-1] ** 2 (:802-803): bins 0..511
+        for (int k = tid; k < kAudioSamples / 2; k += kSpectrumThreads) {
+            const double mag = hypot(s_re[k], s_im[k]);
+            power[row * (kAudioSamples / 2) + k] = static_cast<float>(__dmul_rn(mag, mag));
+        }
+    }
+}
+
+// ---- N1: zero-phase IIR (scipy.signal.filtfilt, padtype='odd', method='pad') -------------------------
+constexpr int kMaxTaps = 16;
+
+// One thread per signal row.  scratch [n_rows, length + 2 * pad] float64 holds the forward pass.
+template <typename In>
+__global__ void filtfilt_kernel(const In* __restrict__ x, long long n_rows, int length, int ntaps, int pad,
+                                const double* __restrict__ coef /* b[ntaps] | a[ntaps] | zi[ntaps-1] */,
+                                double* __restrict__ scratch, float* __restrict__ y_out) {
+    const long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    double b[kMaxTaps], a[kMaxTaps], z[kMaxTaps];
+    for (int i = 0; i < kMaxTaps; ++i) { b[i] = 0.0; a[i] = 0.0; z[i] = 0.0; }
+    const double a0 = coef[ntaps];
+    for (int i = 0; i < ntaps; ++i) { b[i] = __ddiv_rn(coef[i], a0); a[i] = __ddiv_rn(coef[ntaps + i], a0); }
+    const In* xr = x + row * length;
+    double* fwd = scratch + row * (length + 2 * pad);
+    const int total = length + 2 * pad;
+    const double first = static_cast<double>(xr[0]), last = static_cast<double>(xr[length - 1]);
+    // odd extension: 2*x[0] - x[pad..1], x, 2*x[-1] - x[-2..-(pad+1)].  scipy builds it in the INPUT dtype before the
+    // filter promotes to float64: float32 arithmetic for float32 audio, exact integers for the int32 samples of the
+    // tfrecords (|x| < 2^30 assumed).
+    auto reflect = [&](double end, In v) -> double {
+        if (std::is_same<In, float>::value)
+            return static_cast<double>(__fsub_rn(__fmul_rn(2.f, static_cast<float>(end)), static_cast<float>(v)));
+        return __dadd_rn(__dmul_rn(2.0, end), -static_cast<double>(v));
+    };
+    auto ext = [&](int i) -> double {
+        if (i < pad) return reflect(first, xr[pad - i]);
+        if (i < pad + length) return static_cast<double>(xr[i - pad]);
+        return reflect(last, xr[length - 2 - (i - pad - length)]);
+    };
+    // scipy's direct form II transposed step: y = z0 + b0*x; z[i] = z[i+1] + x*b[i+1] - y*a[i+1]; z[last] = x*b[n-1] - y*a[n-1]
+    auto step = [&](double xn) -> double {
+        const double yn = __dadd_rn(z[0], __dmul_rn(b[0], xn));
+#pragma unroll
+        for (int i = 0; i < kMaxTaps - 2; ++i)
+            if (i < ntaps - 2)
+                z[i] = __dadd_rn(__dadd_rn(z[i + 1], __dmul_rn(xn, b[i + 1])), -__dmul_rn(yn, a[i + 1]));
+        z[ntaps - 2] = __dadd_rn(__dmul_rn(xn, b[ntaps - 1]), -__dmul_rn(yn, a[ntaps - 1]));
+        return yn;
+    };
+    const double x0 = ext(0);
+    for (int i = 0; i < ntaps - 1; ++i) z[i] = __dmul_rn(coef[2 * ntaps + i], x0);      // zi * ext[0]
+    for (int i = 0; i < total; ++i) fwd[i] = step(ext(i));
+    const double y0 = fwd[total - 1];
+    for (int i = 0; i < ntaps - 1; ++i) z[i] = __dmul_rn(coef[2 * ntaps + i], y0);      // zi * y[-1]
+    for (int i = total - 1; i >= 0; --i) {
+        const double v = step(fwd[i]);
+        if (i >= pad && i < pad + length) y_out[row * length + (i - pad)] = static_cast<float>(v);   // np.float32(y) (:574)
+    }
+}
+
+// ---- N2: per-vector min-max and the tiled conditioning image ------------------------------------------
+__device__ __forceinline__ void minmax_normalize12(float (&v)[12]) {
+    float mn = v[0], mx = v[0];
+#pragma unroll
+    for (int m = 1; m < 12; ++m) { mn = fminf(mn, v[m]); mx = fmaxf(mx, v[m]); }
+    const float range = __fsub_rn(mx, mn);          // max(x - min) == fl(max - min)
+#pragma unroll
+    for (int m = 0; m < 12; ++m) v[m] = __fdiv_rn(__fsub_rn(v[m], mn), range);
+}
+
+__global__ void normalize_mfcc_kernel(const float* __restrict__ mfcc, long long n, float* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4* src = reinterpret_cast<const float4*>(mfcc + i * 12);
+    const float4 a = src[0], b = src[1], c = src[2];
+    float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    minmax_normalize12(v);
+    float4* dst = reinterpret_cast<float4*>(out + i * 12);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+}
+
+constexpr int kTileThreads = 192;       // a multiple of 3: every thread always writes the same third of the vector
+__global__ void __launch_bounds__(kTileThreads)
+tile_mfcc_kernel(const float* __restrict__ mfcc, long long n, int normalize, float* __restrict__ map_out) {
+    for (long long f = blockIdx.x; f < n; f += gridDim.x) {
+        const float4* src = reinterpret_cast<const float4*>(mfcc + f * 12);
+        const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        if (normalize) minmax_normalize12(v);
+        const int third = threadIdx.x % 3;
+        const float4 mine = third == 0 ? make_float4(v[0], v[1], v[2], v[3])
+                          : third == 1 ? make_float4(v[4], v[5], v[6], v[7]) : make_float4(v[8], v[9], v[10], v[11]);
+        float4* dst = reinterpret_cast<float4*>(map_out + f * kFrameValues);
+#pragma unroll 3
+        for (int i = threadIdx.x; i < kFrameValues / 4; i += kTileThreads) __stcs(dst + i, mine);
+    }
+}
+
+}  // namespace aig

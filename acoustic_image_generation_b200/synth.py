@@ -90,6 +90,21 @@ def flickr_boxes(n, seed=0, height=224, width=298):
     return xmin, xmax, ymin, ymax
 
 
+def audio_rows(n, seed=0, dtype=np.int32, amplitude=20000.0):
+    """n rows of 1024 audio samples (one acoustic frame's worth at 12 288 Hz): a few decaying tones plus noise,
+    int32 like the tfrecords' `audio/data` (outdoor_data_mfcc.py:326) or float32."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(1024) / 12288.0
+    out = np.zeros((n, 1024))
+    for i in range(n):
+        for _ in range(int(rng.integers(1, 5))):
+            f = rng.uniform(40.0, 5000.0)
+            out[i] += rng.uniform(0.1, 1.0) * np.sin(2 * np.pi * f * t + rng.uniform(0, 6.28)) * np.exp(-t * rng.uniform(0, 30))
+        out[i] += 0.05 * rng.standard_normal(1024)
+    out *= amplitude / np.abs(out).max()
+    return np.rint(out).astype(np.int32) if np.dtype(dtype) == np.int32 else out.astype(np.float32)
+
+
 def digest(array):
     """Short SHA-256 of an array's bytes; golden files store it to detect generator drift."""
     return hashlib.sha256(np.ascontiguousarray(array).tobytes()).hexdigest()[:16]

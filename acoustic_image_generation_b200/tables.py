@@ -46,6 +46,28 @@ def mfcc_constants(filter_num=FILTER_NUM, mfcc_num=MFCC_NUM, lifter_num=LIFTER_N
     return dct_base, lifter, mfnorm
 
 
+@functools.lru_cache(maxsize=4)
+def tukey_window(m=1024, alpha=0.75):
+    """The window of _build_spectrograms_function: scipy.signal.tukey(1024, alpha=0.75)
+    (outdoor_data_mfcc.py:799), float64: raised-cosine tapers over alpha/2 of each end, flat in between."""
+    n = np.arange(0, m)
+    width = int(np.floor(alpha * (m - 1) / 2.0))
+    rise = 0.5 * (1 + np.cos(np.pi * (-1 + 2.0 * n[:width + 1] / alpha / (m - 1))))
+    fall = 0.5 * (1 + np.cos(np.pi * (-2.0 / alpha + 1 + 2.0 * n[m - width - 1:] / alpha / (m - 1))))
+    win = np.concatenate((rise, np.ones(m - 2 * (width + 1)), fall))
+    win.setflags(write=False)
+    return win
+
+
+@functools.lru_cache(maxsize=8)
+def butter_lowpass(sample_rate=12288, cutoff=125, order=10):
+    """(b, a, zi) of butter_lowpass (outdoor_data_mfcc.py:565-569) plus the lfilter_zi state filtfilt starts from.
+    Filter design is table building (a dozen coefficients, via scipy like the reference); the filtering runs on the GPU."""
+    from scipy import signal
+    b, a = signal.butter(order, cutoff / (0.5 * sample_rate), btype='low', analog=False)
+    return np.ascontiguousarray(b), np.ascontiguousarray(a), np.ascontiguousarray(signal.lfilter_zi(b, a))
+
+
 @functools.lru_cache(maxsize=1)
 def reference_tables():
     """(filter_mat, dct_base, lifter, mfnorm) of the reference configuration:

@@ -179,6 +179,31 @@ int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, cons
                    const double* thr, int k, int64_t* inter2_out, int64_t* union2_out,
                    int64_t* pos_inout, int64_t* num_inout);
 
+/* ---- callers either side of the path ("next" rows N1, N2 of SURVEY.md section 8(f)) ----------------
+ *
+ * aig_power_spectrum: front half of _build_spectrograms_function (outdoor_data_mfcc.py:796-805; the variant
+ * without a window is dataloader/frames.py:659-667): rows of 1024 audio samples (int32 when audio_is_int32,
+ * else float32) are multiplied by `window` (float64[1024], host or device; NULL = no window), transformed with
+ * a 1024-point real FFT in float64, the Nyquist bin is dropped and the squared magnitude is written as
+ * float32 power[n_rows, 512] - the input of aig_mfcc.
+ *
+ * aig_filtfilt: butter_lowpass_filter (outdoor_data_mfcc.py:565-575) = scipy.signal.filtfilt(b, a, x) along rows
+ * (padtype 'odd', padlen 3*ntaps, lfilter_zi initial state), float64 arithmetic in scipy's operation order,
+ * result cast to float32.  b, a: float64[ntaps] (ntaps <= 16), zi = scipy.signal.lfilter_zi(b, a): float64[ntaps-1],
+ * all host arrays; x: [n_rows, length] int32 or float32 with length > 3*ntaps.
+ *
+ * aig_normalize_mfcc: _normalize_mfcc mapped by _map_func_mfcc (outdoor_data_mfcc.py:681-703): per 12-vector
+ * float32 (x - min) / max(x - min).
+ *
+ * aig_tile_mfcc: mfccmap = tile(reshape(mfcc, (-1,1,12)), (1, 36*48, 1)) -> [n, 36, 48, 12]
+ * (trainer/mfcctrainer.py:38-40, iouenergythreshold.py:99-101), optionally normalising each vector first. */
+int aig_power_spectrum(aig_handle* h, const void* audio, int audio_is_int32, int64_t n_rows,
+                       const double* window, float* power_out);
+int aig_filtfilt(aig_handle* h, const void* x, int x_is_int32, int64_t n_rows, int length, const double* b,
+                 const double* a, const double* zi, int ntaps, float* y_out);
+int aig_normalize_mfcc(aig_handle* h, const float* mfcc, int64_t n, float* out);
+int aig_tile_mfcc(aig_handle* h, const float* mfcc, int64_t n, int normalize, float* map_out);
+
 /* ---- multi-GPU: the path's only exchange ------------------------------------------------------
  * Frames shard across GPUs with no data-path collective; at the end of an evaluation the int64[K+1]
  * count vector (pos[0..K-1], num) is summed over ranks.  The reference has no counterpart (single GPU,

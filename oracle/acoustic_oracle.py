@@ -361,6 +361,72 @@ def auc(thresholds, values):
 
 
 # ---------------------------------------------------------------------------
+# N1  audio front half                    dataloader/outdoor_data_mfcc.py:565-575, 796-805
+# ---------------------------------------------------------------------------
+AUDIO_SAMPLES = 1024      # _NUMBER_OF_SAMPLES, outdoor_data_mfcc.py:9
+SAMPLE_RATE = 12288       # ActionsDataLoader.__init__ default, outdoor_data_mfcc.py:17
+
+
+def tukey_window(m=AUDIO_SAMPLES, alpha=0.75):
+    """scipy.signal.tukey(1024, alpha=0.75) (outdoor_data_mfcc.py:799; moved to scipy.signal.windows.tukey):
+    cosine tapers over the first and last alpha/2 of the window, ones in between (symmetric form)."""
+    n = np.arange(0, m)
+    width = int(np.floor(alpha * (m - 1) / 2.0))
+    n1, n3 = n[0:width + 1], n[m - width - 1:]
+    w1 = 0.5 * (1 + np.cos(np.pi * (-1 + 2.0 * n1 / alpha / (m - 1))))
+    w2 = np.ones(m - 2 * (width + 1))
+    w3 = 0.5 * (1 + np.cos(np.pi * (-2.0 / alpha + 1 + 2.0 * n3 / alpha / (m - 1))))
+    return np.concatenate((w1, w2, w3))
+
+
+def power_spectrum(audio, window=None):
+    """[n, 1024] audio rows -> float64 [n, 512] power (outdoor_data_mfcc.py:800-804): window, rfft(1024), drop the
+    Nyquist bin, |.|**2.  ``window=None`` is the variant of dataloader/frames.py:659-667 (no window)."""
+    x = np.asarray(audio)
+    if window is not None:
+        x = x * np.reshape(np.tile(window, (x.shape[0], 1)), (x.shape[0], AUDIO_SAMPLES))
+    else:
+        # without the float64 window the dtype of the input decides the FFT precision: NumPy < 2 (the reference's
+        # era) always transformed in float64, NumPy >= 2 keeps float32.  The oracle pins the float64 behaviour.
+        x = x.astype(np.float64)
+    spec = np.abs(np.fft.rfft(x, AUDIO_SAMPLES, axis=1))[:, :-1]
+    return spec ** 2
+
+
+def build_spectrograms(audio):
+    """_build_spectrograms_function (outdoor_data_mfcc.py:796-824): [n, 1024] audio -> float32 [n, 12] MFCC."""
+    bank, dct_base, lifter, mfnorm = reference_tables()
+    power = power_spectrum(audio, tukey_window())
+    return np.float32(get_feats(FFT_LEN, power, MFCC_NUM, dct_base, mfnorm, lifter, bank))
+
+
+def butter_lowpass_filter(data, sample_rate=SAMPLE_RATE, cutoff=125, order=10):
+    """butter_lowpass + butter_lowpass_filter (outdoor_data_mfcc.py:565-575): order-10 Butterworth low-pass at
+    cutoff / (sample_rate / 2), zero-phase with scipy.signal.filtfilt, cast to float32.  scipy is the third-party
+    arithmetic the reference itself calls here (unpinned there; 1.18.1 in this image)."""
+    from scipy import signal
+    b, a = signal.butter(order, cutoff / (0.5 * sample_rate), btype='low', analog=False)
+    return np.float32(signal.filtfilt(b, a, data))
+
+
+# ---------------------------------------------------------------------------
+# N2  batch assembly for the models       outdoor_data_mfcc.py:681-703, trainer/mfcctrainer.py:38-40
+# ---------------------------------------------------------------------------
+def normalize_mfcc(mfcc):
+    """_normalize_mfcc over rows: float32 (x - min) / max(x - min) per 12-vector (outdoor_data_mfcc.py:696-703)."""
+    x = np.asarray(mfcc, dtype=np.float32).reshape(-1, MFCC_NUM)
+    shifted = x - x.min(axis=1, keepdims=True)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        return shifted / shifted.max(axis=1, keepdims=True)
+
+
+def tile_mfcc(mfcc):
+    """mfccmap (trainer/mfcctrainer.py:38-40): [B, 12] -> [B, 36, 48, 12], every pixel holds the clip's MFCC vector."""
+    x = np.asarray(mfcc, dtype=np.float32).reshape(-1, 1, MFCC_NUM)
+    return np.reshape(np.tile(x, (1, FRAME_PIXELS, 1)), (-1, FRAME_H, FRAME_W, MFCC_NUM))
+
+
+# ---------------------------------------------------------------------------
 # whole-path composites used by the tests and the CPU baseline
 # ---------------------------------------------------------------------------
 def energy_stage(mfcc_images, normalize_first=True):

@@ -215,6 +215,41 @@ def main(reference_root='/root/reference'):
         aucs[name] = np.float64(metrics.auc(list(thr)[::-1], value[::-1]))
     np.savez_compressed(os.path.join(GOLDEN_DIR, 'auc.npz'), **aucs)
 
+    # ---- G8: audio front half (N1): the reference's module-level _build_spectrograms_function and the loader's
+    # butter_lowpass_filter, unmodified; `signal.tukey` moved to scipy.signal.windows in current scipy, so the
+    # namespace they run in maps the old name to the new function -------------------------------------------------------
+    import types
+    from scipy import signal as sp_signal
+    shim = types.SimpleNamespace(tukey=sp_signal.windows.tukey, butter=sp_signal.butter, filtfilt=sp_signal.filtfilt)
+    with open(os.path.join(reference_root, 'iouenergythreshold.py')) as fh:
+        tree = ast.parse(fh.read())
+    scope = {'np': np, 'signal': shim, 'createfilters': ref['createfilters'], 'get_feats': ref['get_feats']}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == '_build_spectrograms_function':
+            exec(compile(ast.Module([node], []), 'iouenergythreshold.py', 'exec'), scope)
+    with open(os.path.join(reference_root, 'dataloader', 'outdoor_data_mfcc.py')) as fh:
+        tree = ast.parse(fh.read())
+    methods = {}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == 'ActionsDataLoader':
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name in ('butter_lowpass', 'butter_lowpass_filter'):
+                    exec(compile(ast.Module([item], []), 'outdoor_data_mfcc.py', 'exec'), {'np': np, 'signal': shim}, methods)
+    loader = types.SimpleNamespace(sample_rate=12288)
+    loader.butter_lowpass = types.MethodType(methods['butter_lowpass'], loader)
+    audio_i = synth.audio_rows(24, 90, np.int32)
+    audio_f = synth.audio_rows(8, 91, np.float32, amplitude=1.0)
+    front = dict(
+        digest_int=np.array(synth.digest(audio_i)), digest_float=np.array(synth.digest(audio_f)),
+        tukey=sp_signal.windows.tukey(1024, alpha=0.75),
+        mfcc_int=scope['_build_spectrograms_function'](audio_i),
+        mfcc_float=scope['_build_spectrograms_function'](audio_f),
+        lowpass_int=methods['butter_lowpass_filter'](loader, audio_i),
+        lowpass_float=methods['butter_lowpass_filter'](loader, audio_f),
+        power_int_f64=(np.abs(np.fft.rfft(audio_i * sp_signal.windows.tukey(1024, alpha=0.75), 1024, axis=1))[:, :-1] ** 2)[:4])
+    front['mfcc_lowpassed_int'] = scope['_build_spectrograms_function'](front['lowpass_int'])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, 'audio_front.npz'), **front)
+
     total = sum(os.path.getsize(os.path.join(GOLDEN_DIR, f)) for f in os.listdir(GOLDEN_DIR))
     print('golden vectors written to %s (%.1f KiB)' % (GOLDEN_DIR, total / 1024.0))
 

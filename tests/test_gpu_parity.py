@@ -460,3 +460,68 @@ def test_flickr_evaluation_driver(path, golden, torch):
     res = ev.finish()
     assert np.array_equal(res['pos'], g['pos11']) and res['num'] == n
     assert abs(res['auc'] - float(golden('auc')['flickr11'])) <= 1e-12
+
+
+# ----------------------------------------------------------------------------------------------
+# "next" rows N1 (audio front half) and N2 (batch assembly)
+# ----------------------------------------------------------------------------------------------
+def test_power_spectrum_matches_numpy_rfft(path, golden):
+    g = golden('audio_front')
+    for audio in (synth.audio_rows(24, 90, np.int32), synth.audio_rows(8, 91, np.float32, amplitude=1.0)):
+        got = path.power_spectrum(audio)
+        want = oracle.power_spectrum(audio, oracle.tukey_window())
+        assert got.dtype == np.float32 and got.shape == want.shape
+        # float64 FFT rounded to float32: relative to the row's peak power the error is at float32 rounding level
+        rel = np.abs(got - want).max(axis=1) / want.max(axis=1)
+        assert rel.max() <= 1e-7
+        bare = path.power_spectrum(audio, window=None)
+        want_bare = oracle.power_spectrum(audio, None)
+        assert (np.abs(bare - want_bare).max(axis=1) / want_bare.max(axis=1)).max() <= 1e-7
+    assert np.abs(path.power_spectrum(synth.audio_rows(24, 90, np.int32))[:4] - g['power_int_f64']).max() \
+        <= 1e-7 * g['power_int_f64'].max()
+
+
+def test_build_spectrograms_dropin_matches_reference(path, golden):
+    g = golden('audio_front')
+    for key, audio in (('mfcc_int', synth.audio_rows(24, 90, np.int32)),
+                       ('mfcc_float', synth.audio_rows(8, 91, np.float32, amplitude=1.0))):
+        got = aig._build_spectrograms_function(audio)
+        assert got.dtype == np.float32 and got.shape == g[key].shape
+        err = np.abs(got - g[key]).max()
+        print('%s: max abs err %.3e (max |mfcc| %.1f)' % (key, err, np.abs(g[key]).max()))
+        assert err <= MFCC_TOL
+
+
+def test_butter_lowpass_filter_matches_scipy(path, golden, torch):
+    g = golden('audio_front')
+    audio_i = synth.audio_rows(24, 90, np.int32)
+    audio_f = synth.audio_rows(8, 91, np.float32, amplitude=1.0)
+    got_i = aig.butter_lowpass_filter(audio_i)
+    got_f = path.butter_lowpass_filter(audio_f)
+    assert got_i.dtype == np.float32 and got_i.shape == audio_i.shape
+    # same float64 recurrence in the same order: agreement far below the float32 output resolution
+    for got, key in ((got_i, 'lowpass_int'), (got_f, 'lowpass_float')):
+        scale = np.abs(g[key]).max()
+        err = np.abs(got.astype(np.float64) - g[key].astype(np.float64)).max() / scale
+        print('%s: max err / max |y| = %.3e, bit-identical %.1f%%' % (key, err, 100 * (got == g[key]).mean()))
+        assert err <= 1e-6
+    dev = path.butter_lowpass_filter(torch.from_numpy(audio_i).cuda())
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), got_i)
+    # low-passed audio through the spectrogram function, as the dataloader chains them (:78-82)
+    mf = aig._build_spectrograms_function(got_i)
+    assert np.abs(mf - g['mfcc_lowpassed_int']).max() <= 5e-4     # |MFCC| up to ~100 on a 1e9-range spectrum
+
+
+def test_normalize_and_tile_mfcc_bit_exact(path, torch):
+    rng = np.random.default_rng(1)
+    m = (rng.standard_normal((301, 12)) * 7).astype(np.float32)
+    assert np.array_equal(path.normalize_mfcc(m), oracle.normalize_mfcc(m))
+    assert np.array_equal(aig._normalize_mfcc(m[5]), oracle.normalize_mfcc(m[5:6])[0])
+    tup = aig._map_func_mfcc('img', m, 'vid', 1, 2, m[::-1].copy())
+    assert np.array_equal(tup[1], oracle.normalize_mfcc(m)) and np.array_equal(tup[5], oracle.normalize_mfcc(m[::-1]))
+    assert tup[0] == 'img' and tup[2:5] == ('vid', 1, 2)
+    assert np.array_equal(path.tile_mfcc(m), oracle.tile_mfcc(m))
+    assert np.array_equal(path.tile_mfcc(m, normalize=True), oracle.tile_mfcc(oracle.normalize_mfcc(m)))
+    dev = path.tile_mfcc(torch.from_numpy(m).cuda())
+    assert dev.is_cuda and tuple(dev.shape) == (301, 36, 48, 12)
+    assert np.isnan(path.normalize_mfcc(np.full((1, 12), 2.0, np.float32))).all()

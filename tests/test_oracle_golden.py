@@ -205,3 +205,34 @@ def test_auc_matches_sklearn(golden):
 def test_success_counts_nan_and_strictness():
     pos, num = oracle.success_counts([np.nan, 0.5, 1.0, 0.0], [0.0, 0.5, 1.0])
     assert pos.tolist() == [2, 1, 0] and num == 4
+
+
+# ---- "next" rows N1 / N2 ---------------------------------------------------------------------------
+def test_tukey_window_matches_scipy(golden):
+    from acoustic_image_generation_b200 import tables
+    g = golden('audio_front')
+    assert np.array_equal(oracle.tukey_window(), g['tukey'])
+    assert np.array_equal(tables.tukey_window(), g['tukey'])
+
+
+def test_audio_front_half_matches_reference(golden):
+    g = golden('audio_front')
+    audio_i = synth.audio_rows(24, 90, np.int32)
+    audio_f = synth.audio_rows(8, 91, np.float32, amplitude=1.0)
+    assert synth.digest(audio_i) == str(g['digest_int']) and synth.digest(audio_f) == str(g['digest_float'])
+    assert np.array_equal(oracle.build_spectrograms(audio_i), g['mfcc_int'])
+    assert np.array_equal(oracle.build_spectrograms(audio_f), g['mfcc_float'])
+    assert np.array_equal(oracle.power_spectrum(audio_i, oracle.tukey_window())[:4], g['power_int_f64'])
+    assert np.array_equal(oracle.butter_lowpass_filter(audio_i), g['lowpass_int'])
+    assert np.array_equal(oracle.butter_lowpass_filter(audio_f), g['lowpass_float'])
+    assert np.array_equal(oracle.build_spectrograms(g['lowpass_int']), g['mfcc_lowpassed_int'])
+
+
+def test_normalize_and_tile_mfcc():
+    rng = np.random.default_rng(0)
+    m = rng.standard_normal((5, 12)).astype(np.float32) * 10
+    n = oracle.normalize_mfcc(m)
+    assert n.dtype == np.float32 and np.all(n.min(1) == 0) and np.all(n.max(1) == 1)
+    t = oracle.tile_mfcc(m)
+    assert t.shape == (5, 36, 48, 12) and np.array_equal(t[3, 17, 29], m[3]) and np.array_equal(t[:, 0, 0], m)
+    assert np.isnan(oracle.normalize_mfcc(np.full((1, 12), 2.0, np.float32))).all()
