@@ -17,9 +17,9 @@ LIB_PATH = os.path.join(CSRC, 'libaig.so')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
 NVCC_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
-              '-Xcompiler', '-fPIC', '-shared', '-ldl']
-SOURCES = ['aig_api.cu']
-DEPENDS = ['aig_api.cu', 'aig_common.cuh', 'mfcc_kernel.cuh', 'energy_kernel.cuh', 'score_kernel.cuh', 'fused_kernel.cuh', 'frontend_kernel.cuh',
+              '-Xcompiler', '-fPIC', '-shared', '-ldl', '-lz']
+SOURCES = ['aig_api.cu', 'record_reader.cpp']
+DEPENDS = ['aig_api.cu', 'record_reader.cpp', 'aig_common.cuh', 'mfcc_kernel.cuh', 'energy_kernel.cuh', 'score_kernel.cuh', 'fused_kernel.cuh', 'frontend_kernel.cuh',
            'mel_program_ref.inc', 'mel_tables_ref.inc', os.path.join(INCLUDE, 'aig.h')]
 
 AIG_OK = 0
@@ -95,6 +95,13 @@ SIGNATURES = {
     'aig_filtfilt': (_int, [_p, _p, _int, _i64, _int, _p, _p, _p, _int, _p]),
     'aig_normalize_mfcc': (_int, [_p, _p, _i64, _p]),
     'aig_tile_mfcc': (_int, [_p, _p, _i64, _int, _p]),
+    'aig_records_open': (_int, [ctypes.c_char_p, ctypes.POINTER(_p)]),
+    'aig_records_close': (_int, [_p]),
+    'aig_records_count': (_i64, [_p]),
+    'aig_record_context_int64': (_int, [_p, _int, ctypes.c_char_p, _p, _int, ctypes.POINTER(_int)]),
+    'aig_record_sequence_size': (_int, [_p, _int, ctypes.c_char_p, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    'aig_record_sequence_read': (_int, [_p, _int, ctypes.c_char_p, _p, _i64]),
+    'aig_records_last_error': (ctypes.c_char_p, []),
     'aig_comm_unique_id': (_int, [_p]),
     'aig_comm_init': (_int, [_p, _p, _int, _int]),
     'aig_allreduce_counts': (_int, [_p, _p, _int]),

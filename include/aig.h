@@ -204,6 +204,30 @@ int aig_filtfilt(aig_handle* h, const void* x, int x_is_int32, int64_t n_rows, i
 int aig_normalize_mfcc(aig_handle* h, const float* mfcc, int64_t n, float* out);
 int aig_tile_mfcc(aig_handle* h, const float* mfcc, int64_t n, int normalize, float* map_out);
 
+/* ---- on-disk format ("next" row N3) --------------------------------------------------------------
+ * Reader for the reference's data files: GZIP (or plain) TFRecord files of tf.train.SequenceExample records
+ * (writer convert_data.py:247-279; parsers dataloader/outdoor_data_mfcc.py:260-344, dataloader/frames.py:246-341).
+ * Host-side C++ (zlib + CRC-32C + a minimal protobuf wire walk), no TensorFlow.  Replaces
+ * tf.data.TFRecordDataset(compression_type='GZIP') + tf.parse_single_sequence_example + tf.decode_raw.
+ *   aig_records_open           inflate the file, verify every record's masked CRC-32C, index the records
+ *   aig_records_count          number of records (-1 for a null reader)
+ *   aig_record_context_int64   int64 context feature (e.g. "classes", "audio_image/height", "xmin"): up to
+ *                              `capacity` values are written, *count_out receives how many the feature holds
+ *   aig_record_sequence_size   feature list of byte strings (e.g. "audio/image"): steps and total payload bytes
+ *   aig_record_sequence_read   the steps' byte strings concatenated into dst (host memory) - what
+ *                              tf.decode_raw + reshape([-1, H, W, D]) sees
+ *   aig_records_last_error     message of the calling thread's last reader failure */
+typedef struct aig_record_reader aig_record_reader;
+int aig_records_open(const char* path, aig_record_reader** out);
+int aig_records_close(aig_record_reader* r);
+int64_t aig_records_count(const aig_record_reader* r);
+int aig_record_context_int64(const aig_record_reader* r, int record, const char* key, int64_t* values_out,
+                             int capacity, int* count_out);
+int aig_record_sequence_size(const aig_record_reader* r, int record, const char* key, int64_t* steps_out,
+                             int64_t* bytes_out);
+int aig_record_sequence_read(const aig_record_reader* r, int record, const char* key, void* dst, int64_t dst_bytes);
+const char* aig_records_last_error(void);
+
 /* ---- multi-GPU: the path's only exchange ------------------------------------------------------
  * Frames shard across GPUs with no data-path collective; at the end of an evaluation the int64[K+1]
  * count vector (pos[0..K-1], num) is summed over ranks.  The reference has no counterpart (single GPU,

@@ -1,0 +1,131 @@
+"""N3: the GZIP TFRecord / SequenceExample reader of libaig against records serialised by the official protobuf
+runtime (message types built from descriptors that restate tensorflow/core/example/{example,feature}.proto), plus the
+package's own writer.  CPU only - the reader is host code."""
+import gzip
+import struct
+
+import numpy as np
+import pytest
+
+from acoustic_image_generation_b200 import AigError, synth, tfrecord
+
+
+def _tf_example_messages():
+    """tf.train.SequenceExample and friends, declared at run time (no TensorFlow needed)."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    fd = descriptor_pb2.FileDescriptorProto(name='aig_test_example.proto', package='aigtest', syntax='proto3')
+    L = descriptor_pb2.FieldDescriptorProto
+
+    def msg(name, fields, nested=()):
+        m = fd.message_type.add(name=name)
+        for fname, number, ftype, label, type_name in fields:
+            f = m.field.add(name=fname, number=number, type=ftype, label=label)
+            if type_name:
+                f.type_name = type_name
+        return m
+
+    msg('BytesList', [('value', 1, L.TYPE_BYTES, L.LABEL_REPEATED, None)])
+    msg('FloatList', [('value', 1, L.TYPE_FLOAT, L.LABEL_REPEATED, None)])
+    msg('Int64List', [('value', 1, L.TYPE_INT64, L.LABEL_REPEATED, None)])
+    msg('Feature', [('bytes_list', 1, L.TYPE_MESSAGE, L.LABEL_OPTIONAL, '.aigtest.BytesList'),
+                    ('float_list', 2, L.TYPE_MESSAGE, L.LABEL_OPTIONAL, '.aigtest.FloatList'),
+                    ('int64_list', 3, L.TYPE_MESSAGE, L.LABEL_OPTIONAL, '.aigtest.Int64List')])
+    msg('FeatureList', [('feature', 1, L.TYPE_MESSAGE, L.LABEL_REPEATED, '.aigtest.Feature')])
+    for holder, value in (('Features', 'Feature'), ('FeatureLists', 'FeatureList')):
+        m = msg(holder, [('entry', 1, L.TYPE_MESSAGE, L.LABEL_REPEATED, '.aigtest.%s.Entry' % holder)])
+        e = m.nested_type.add(name='Entry')              # map<string, V> is wire-identical to repeated {key=1, value=2}
+        e.field.add(name='key', number=1, type=L.TYPE_STRING, label=L.LABEL_OPTIONAL)
+        e.field.add(name='value', number=2, type=L.TYPE_MESSAGE, label=L.LABEL_OPTIONAL, type_name='.aigtest.' + value)
+    msg('SequenceExample', [('context', 1, L.TYPE_MESSAGE, L.LABEL_OPTIONAL, '.aigtest.Features'),
+                            ('feature_lists', 2, L.TYPE_MESSAGE, L.LABEL_OPTIONAL, '.aigtest.FeatureLists')])
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    get = getattr(message_factory, 'GetMessageClass', None)
+    return {n: get(pool.FindMessageTypeByName('aigtest.' + n)) for n in ('SequenceExample', 'Feature')}
+
+
+def _official_example(context, feature_lists):
+    cls = _tf_example_messages()['SequenceExample']
+    ex = cls()
+    for k, v in context.items():
+        e = ex.context.entry.add(key=k)
+        e.value.int64_list.value.extend(int(x) for x in np.atleast_1d(v))
+    for k, steps in feature_lists.items():
+        e = ex.feature_lists.entry.add(key=k)
+        for s in steps:
+            e.value.feature.add().bytes_list.value.append(bytes(s))
+    return ex.SerializeToString()
+
+
+def _frame(blob):
+    header = struct.pack('<Q', len(blob))
+    return header + struct.pack('<I', tfrecord._masked_crc32c(header)) + blob + struct.pack('<I', tfrecord._masked_crc32c(blob))
+
+
+def test_crc32c_known_answer():
+    # CRC-32C("123456789") = 0xE3069283; the TFRecord mask is rot-right 15 plus 0xA282EAD8
+    c = 0xE3069283
+    assert tfrecord._masked_crc32c(b'123456789') == (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+@pytest.mark.parametrize('compress', [True, False])
+def test_reader_on_officially_serialised_records(tmp_path, compress):
+    images = synth.sigmoid_images(12, 5)                                  # one second of 12 fps acoustic images
+    audio = synth.audio_rows(12, 6, np.int32)
+    video = np.random.default_rng(0).integers(0, 255, (3, 8, 10, 3), dtype=np.uint8)
+    ctx = {'classes': 7, 'location': 2, 'audio_image/height': 36, 'audio_image/width': 48, 'audio_image/depth': 12,
+           'audio_data/mics': 1, 'audio_data/samples': 1024, 'video/height': 8, 'video/width': 10, 'video/depth': 3,
+           'xmin': [10, 0, 30], 'xmax': [100, 0, 298], 'ymin': [5, 0, 0], 'ymax': [50, 0, 224], 'neg': -5}
+    lists = {'audio/image': [f.tobytes() for f in images], 'audio/data': [a.tobytes() for a in audio],
+             'video/image': [v.tobytes() for v in video]}
+    blobs = [_official_example(ctx, lists), _official_example({'classes': 1, 'location': 0}, {})]
+    path = str(tmp_path / ('data.tfrecord'))
+    payload = b''.join(_frame(b) for b in blobs)
+    with (gzip.open(path, 'wb') if compress else open(path, 'wb')) as fh:
+        fh.write(payload)
+    with tfrecord.RecordFile(path) as rec:
+        assert len(rec) == 2
+        ex = tfrecord.parse_flickr_example(rec, 0)
+        assert ex['classes'] == 7 and ex['location'] == 2
+        assert np.array_equal(ex['audio_images'], images)
+        assert np.array_equal(ex['audio_samples'], audio)
+        assert np.array_equal(ex['video_images'], video)
+        assert ex['xmax'].tolist() == [100, 0, 298] and ex['ymin'].dtype == np.int32
+        assert rec.context(0, 'neg').tolist() == [-5]
+        flipped = tfrecord.parse_acoustic_example(rec, 0)['audio_images']      # outdoor_data_mfcc.py:314-315
+        assert np.array_equal(flipped, images[:, ::-1, ::-1, :])
+        assert tfrecord.parse_acoustic_example(rec, 1) == {'classes': 1, 'location': 0}
+        with pytest.raises(AigError):
+            rec.context(0, 'missing')
+        with pytest.raises(AigError):
+            rec.sequence(1, 'audio/image', np.float32)
+
+
+def test_own_writer_is_byte_identical_to_protobuf_and_round_trips(tmp_path):
+    images = synth.sigmoid_images(3, 9)
+    ctx = {'classes': 3, 'location': 1, 'audio_image/height': 36, 'audio_image/width': 48, 'audio_image/depth': 12}
+    lists = {'audio/image': [f.tobytes() for f in images]}
+    mine = tfrecord.encode_sequence_example(ctx, lists)
+    assert mine == _official_example(ctx, lists)
+    path = tfrecord.write_sequence_examples(str(tmp_path / 'Data_001.tfrecord'), [mine] * 5)
+    with tfrecord.RecordFile(path) as rec:
+        assert len(rec) == 5
+        assert np.array_equal(tfrecord.parse_acoustic_example(rec, 4, flip=False)['audio_images'], images)
+
+
+def test_corruption_is_detected(tmp_path):
+    blob = tfrecord.encode_sequence_example({'classes': 1, 'location': 1}, {})
+    good = _frame(blob)
+    bad = bytearray(good)
+    bad[14] ^= 0xFF
+    for name, payload in (('flip.tfrecord', bytes(bad)), ('short.tfrecord', good[:-3])):
+        p = str(tmp_path / name)
+        open(p, 'wb').write(payload)
+        with pytest.raises(AigError):
+            tfrecord.RecordFile(p)
+    with pytest.raises(AigError):
+        tfrecord.RecordFile(str(tmp_path / 'does_not_exist.tfrecord'))
+    empty = str(tmp_path / 'empty.tfrecord')
+    open(empty, 'wb').close()
+    with tfrecord.RecordFile(empty) as rec:
+        assert len(rec) == 0
