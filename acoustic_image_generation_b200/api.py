@@ -338,6 +338,24 @@ class AcousticPath:
         self._check(self._lib.aig_heatmap(self._h, a.ptr, n, int(out_h), int(out_w), _Arg(res, np.float32, True).ptr))
         return res
 
+    def overlay(self, heat, frames_bgr=None, alpha=0.7):
+        """Jet-coloured heat map blended over the gray video frame (showvideo.py:224-229), RGB uint8 [N, H, W, 3].
+        heat: float32 [N, H, W] in [0, 1] (from ``heatmap``); frames_bgr: uint8 [N, H, W, 3] (OpenCV order) or None."""
+        a = _Arg(heat, np.float32)
+        if len(a.shape) != 3:
+            raise ValueError('heat must be [N, H, W], got %s' % (a.shape,))
+        n, hh, ww = a.shape
+        b = None
+        if frames_bgr is not None:
+            b = _Arg(frames_bgr, np.uint8)
+            if tuple(b.shape) != (n, hh, ww, 3):
+                raise ValueError('frames must be [N, H, W, 3] uint8 matching the heat maps')
+        lut = tables.jet_lut()
+        res = self._empty((n, hh, ww, 3), np.uint8, a)
+        self._check(self._lib.aig_overlay(self._h, a.ptr, b.ptr if b is not None else None, n, hh, ww, float(alpha),
+                                          lut.ctypes.data, _Arg(res, np.uint8, True).ptr))
+        return res
+
     def resize_mask(self, mask, out_h=HEAT_H, out_w=HEAT_W):
         """1.0 * (cv2.resize(mask * 1.0, (out_w, out_h)) > 0.5) as uint8 [N, out_h, out_w] (showimages_bb.py:303-304)."""
         a = _Arg(mask, np.uint8)

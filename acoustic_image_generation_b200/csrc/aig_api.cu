@@ -1033,6 +1033,28 @@ int aig_tile_mfcc(aig_handle* h, const float* mfcc, int64_t n, int normalize, fl
     return io.finish();
 }
 
+int aig_overlay(aig_handle* h, const float* heat, const uint8_t* bgr, int64_t n_frames, int out_h, int out_w, float alpha,
+                const uint8_t* jet_lut, uint8_t* rgb_out) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (n_frames < 0 || !jet_lut || (n_frames > 0 && (!heat || !rgb_out))) return h->fail(AIG_ERR_ARGUMENT, "aig_overlay: bad buffers");
+    if (out_h < 1 || out_w < 1 || out_h > kMaxOut || out_w > kMaxOut || !(alpha >= 0.f && alpha <= 1.f))
+        return h->fail(AIG_ERR_ARGUMENT, "aig_overlay: bad geometry %dx%d or alpha %g", out_h, out_w, alpha);
+    if (n_frames == 0) return AIG_OK;
+    Io io(h);
+    const size_t n = static_cast<size_t>(n_frames), px = static_cast<size_t>(out_h) * out_w;
+    const float* d_heat = io.in(heat, n * px);
+    const uint8_t* d_bgr = io.in(bgr, n * px * 3);
+    const uint8_t* d_lut = io.in(jet_lut, 768);
+    uint8_t* d_out = io.out(rgb_out, n * px * 3);
+    if (io.failed) return io.finish();
+    LaunchScope scope(h, h->stream, kKindOther);
+    overlay_kernel<<<frames_grid(h, n_frames, 8), 256, 0, h->stream>>>(d_heat, d_bgr, n_frames, static_cast<int>(px), alpha, d_lut, d_out);
+    rc = scope.done("overlay_kernel");
+    if (rc != AIG_OK) return rc;
+    return io.finish();
+}
+
 int aig_comm_unique_id(uint8_t* id_out) {
     if (id_out == nullptr) return AIG_ERR_ARGUMENT;
     NcclApi& api = nccl();

@@ -156,4 +156,59 @@ tile_mfcc_kernel(const float* __restrict__ mfcc, long long n, int normalize, flo
     }
 }
 
+// ---- N4: heat-map overlay (showvideo.py:217-233, showimages.py:144-150) ----------------------------------
+// gray = cv2.cvtColor(frame, COLOR_BGR2GRAY) (OpenCV 4.x: 15-bit fixed point, (3735 B + 19235 G + 9798 R + 2^14) >> 15), shown with imshow(cmap=gray) - i.e. min/max
+// normalised and quantised to 256 levels - then imshow(map, cmap=jet, alpha=0.7): the normalised heat map goes through
+// matplotlib's 256-entry jet table and is alpha-blended over the gray image.  One CTA per frame; out is RGB8.
+// jet_lut: 256 x 3 uint8.  Without a frame (bgr == nullptr) the colour-mapped heat map alone is written.
+__global__ void __launch_bounds__(256)
+overlay_kernel(const float* __restrict__ heat, const uint8_t* __restrict__ bgr, long long n_frames, int n_pixels,
+               float alpha, const uint8_t* __restrict__ jet_lut, uint8_t* __restrict__ rgb_out) {
+    __shared__ uint8_t s_lut[768];
+    __shared__ int s_red[2][8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 768; i += 256) s_lut[i] = jet_lut[i];
+    for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        __syncthreads();
+        const uint8_t* img = bgr ? bgr + f * n_pixels * 3 : nullptr;
+        int lo = 255, hi = 0;
+        if (img != nullptr) {
+            for (int p = tid; p < n_pixels; p += 256) {
+                const int y = (img[3 * p] * 3735 + img[3 * p + 1] * 19235 + img[3 * p + 2] * 9798 + 16384) >> 15;
+                lo = min(lo, y); hi = max(hi, y);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            if (lane == 0) { s_red[0][warp] = lo; s_red[1][warp] = hi; }
+            __syncthreads();
+            lo = s_red[0][0]; hi = s_red[1][0];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) { lo = min(lo, s_red[0][w]); hi = max(hi, s_red[1][w]); }
+        }
+        const float range = static_cast<float>(hi - lo);
+        for (int p = tid; p < n_pixels; p += 256) {
+            const float hv = heat[f * n_pixels + p];
+            int ji = static_cast<int>(__fmul_rn(hv, 256.f));            // Colormap.__call__: int(x * N), x == 1 -> N - 1
+            ji = min(max(ji, 0), 255);
+            float r = s_lut[3 * ji], g = s_lut[3 * ji + 1], b = s_lut[3 * ji + 2];
+            if (img != nullptr) {
+                const int y = (img[3 * p] * 3735 + img[3 * p + 1] * 19235 + img[3 * p + 2] * 9798 + 16384) >> 15;
+                int gi = range > 0.f ? static_cast<int>(__fmul_rn(__fdiv_rn(static_cast<float>(y - lo), range), 256.f)) : 0;
+                gi = min(gi, 255);
+                const float gray = static_cast<float>(gi), keep = __fsub_rn(1.f, alpha);
+                r = __fadd_rn(__fmul_rn(r, alpha), __fmul_rn(gray, keep));
+                g = __fadd_rn(__fmul_rn(g, alpha), __fmul_rn(gray, keep));
+                b = __fadd_rn(__fmul_rn(b, alpha), __fmul_rn(gray, keep));
+            }
+            uint8_t* o = rgb_out + (f * n_pixels + p) * 3;
+            o[0] = static_cast<uint8_t>(__float2int_rn(r));
+            o[1] = static_cast<uint8_t>(__float2int_rn(g));
+            o[2] = static_cast<uint8_t>(__float2int_rn(b));
+        }
+    }
+}
+
 }  // namespace aig

@@ -68,6 +68,30 @@ def butter_lowpass(sample_rate=12288, cutoff=125, order=10):
     return np.ascontiguousarray(b), np.ascontiguousarray(a), np.ascontiguousarray(signal.lfilter_zi(b, a))
 
 
+_JET_SEGMENTS = {   # matplotlib's `jet` LinearSegmentedColormap (x, y0, y1) anchors
+    'red': ((0.00, 0, 0), (0.35, 0, 0), (0.66, 1, 1), (0.89, 1, 1), (1.00, 0.5, 0.5)),
+    'green': ((0.000, 0, 0), (0.125, 0, 0), (0.375, 1, 1), (0.640, 1, 1), (0.910, 0, 0), (1.000, 0, 0)),
+    'blue': ((0.00, 0.5, 0.5), (0.11, 1, 1), (0.34, 1, 1), (0.65, 0, 0), (1.00, 0, 0)),
+}
+
+
+@functools.lru_cache(maxsize=1)
+def jet_lut(n=256):
+    """plt.cm.jet as a [n, 3] uint8 table (showvideo.py:228 `imshow(map, cmap=plt.cm.jet, alpha=0.7)`): matplotlib's
+    piecewise-linear segment data sampled at n points, then `(rgb * 255).astype(uint8)` as Colormap(bytes=True) does."""
+    lut = np.zeros((n, 3))
+    xind = (n - 1) * np.linspace(0, 1, n)
+    for c, name in enumerate(('red', 'green', 'blue')):
+        data = np.array(_JET_SEGMENTS[name], dtype=float)
+        x, y0, y1 = data[:, 0] * (n - 1), data[:, 1], data[:, 2]
+        ind = np.searchsorted(x, xind)[1:-1]
+        dist = (xind[1:-1] - x[ind - 1]) / (x[ind] - x[ind - 1])
+        lut[:, c] = np.concatenate([[y1[0]], dist * (y0[ind] - y1[ind - 1]) + y1[ind - 1], [y0[-1]]])
+    out = (np.clip(lut, 0.0, 1.0) * 255).astype(np.uint8)
+    out.setflags(write=False)
+    return out
+
+
 @functools.lru_cache(maxsize=1)
 def reference_tables():
     """(filter_mat, dct_base, lifter, mfnorm) of the reference configuration:

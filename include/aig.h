@@ -204,6 +204,18 @@ int aig_filtfilt(aig_handle* h, const void* x, int x_is_int32, int64_t n_rows, i
 int aig_normalize_mfcc(aig_handle* h, const float* mfcc, int64_t n, float* out);
 int aig_tile_mfcc(aig_handle* h, const float* mfcc, int64_t n, int normalize, float* map_out);
 
+/* Heat-map overlay rendering ("next" row N4; showvideo.py:217-233, showimages.py:144-150):
+ *   heat     [n, out_h, out_w] float32 in [0, 1] (aig_heatmap's output)
+ *   bgr      nullable [n, out_h, out_w, 3] uint8 video frames in OpenCV's BGR order
+ *   jet_lut  [256, 3] uint8 host array: matplotlib's jet table (tables.jet_lut())
+ *   rgb_out  [n, out_h, out_w, 3] uint8
+ * gray = cv2.cvtColor(frame, COLOR_BGR2GRAY), min/max normalised and quantised to 256 levels (imshow(cmap=gray));
+ * colour = jet_lut[min(int(heat * 256), 255)]; out = round(alpha * colour + (1 - alpha) * gray) (imshow(cmap=jet,
+ * alpha=0.7)).  matplotlib's figure-resolution resampling and Agg's 8-bit compositing are not reproduced: the
+ * overlay is produced at the heat map's own resolution. */
+int aig_overlay(aig_handle* h, const float* heat, const uint8_t* bgr, int64_t n_frames, int out_h, int out_w,
+                float alpha, const uint8_t* jet_lut, uint8_t* rgb_out);
+
 /* ---- on-disk format ("next" row N3) --------------------------------------------------------------
  * Reader for the reference's data files: GZIP (or plain) TFRecord files of tf.train.SequenceExample records
  * (writer convert_data.py:247-279; parsers dataloader/outdoor_data_mfcc.py:260-344, dataloader/frames.py:246-341).

@@ -427,6 +427,30 @@ def tile_mfcc(mfcc):
 
 
 # ---------------------------------------------------------------------------
+# N4  heat-map overlay                    showvideo.py:217-233, showimages.py:144-150
+# ---------------------------------------------------------------------------
+def overlay(heat, frame_bgr, lut, alpha=0.7):
+    """One frame: gray = cv2.cvtColor(frame, COLOR_BGR2GRAY) (restated: OpenCV 4.x's 15-bit fixed point, checked against cv2
+    in the tests); imshow(gray, cmap=gray) = min/max normalise + 256 levels; imshow(map, cmap=jet, alpha) = jet table
+    lookup of the normalised heat map, blended alpha * jet + (1 - alpha) * gray in float32, rounded to uint8.
+    PARITY UNPINNED against matplotlib (absent here; its figure resampling and Agg compositing are not reproduced)."""
+    heat = np.asarray(heat, dtype=np.float32)
+    ji = np.clip((heat * np.float32(256.0)).astype(np.int64), 0, 255)
+    rgb = lut[ji].astype(np.float32)
+    if frame_bgr is not None:
+        f = np.asarray(frame_bgr).astype(np.int64)
+        gray = (f[..., 0] * 3735 + f[..., 1] * 19235 + f[..., 2] * 9798 + 16384) >> 15
+        lo, hi = gray.min(), gray.max()
+        if hi > lo:
+            gi = np.minimum(((gray - lo).astype(np.float32) / np.float32(hi - lo) * np.float32(256.0)).astype(np.int64), 255)
+        else:
+            gi = np.zeros_like(gray)
+        a = np.float32(alpha)
+        rgb = rgb * a + gi.astype(np.float32)[..., None] * (np.float32(1.0) - a)
+    return np.rint(rgb).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------
 # whole-path composites used by the tests and the CPU baseline
 # ---------------------------------------------------------------------------
 def energy_stage(mfcc_images, normalize_first=True):

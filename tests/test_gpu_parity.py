@@ -525,3 +525,20 @@ def test_normalize_and_tile_mfcc_bit_exact(path, torch):
     dev = path.tile_mfcc(torch.from_numpy(m).cuda())
     assert dev.is_cuda and tuple(dev.shape) == (301, 36, 48, 12)
     assert np.isnan(path.normalize_mfcc(np.full((1, 12), 2.0, np.float32))).all()
+
+
+def test_overlay_bit_exact_vs_oracle(path, golden, torch):
+    lut = tables.jet_lut()
+    e = golden('energy')['energy_smooth']
+    heat = path.heatmap(e)                                   # [2, 224, 298] float32
+    rng = np.random.default_rng(2)
+    frames = rng.integers(0, 256, (2, 224, 298, 3), dtype=np.uint8)
+    frames[1, :, :, :] = 77                                  # constant frame: zero gray range
+    got = path.overlay(heat, frames)
+    assert got.dtype == np.uint8 and got.shape == (2, 224, 298, 3)
+    for i in range(2):
+        assert np.array_equal(got[i], oracle.overlay(heat[i], frames[i], lut))
+    bare = path.overlay(heat)
+    assert np.array_equal(bare[0], oracle.overlay(heat[0], None, lut))
+    dev = path.overlay(torch.from_numpy(heat).cuda(), torch.from_numpy(frames).cuda(), alpha=0.5)
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy()[0], oracle.overlay(heat[0], frames[0], lut, 0.5))

@@ -236,3 +236,19 @@ def test_normalize_and_tile_mfcc():
     t = oracle.tile_mfcc(m)
     assert t.shape == (5, 36, 48, 12) and np.array_equal(t[3, 17, 29], m[3]) and np.array_equal(t[:, 0, 0], m)
     assert np.isnan(oracle.normalize_mfcc(np.full((1, 12), 2.0, np.float32))).all()
+
+
+def test_overlay_gray_matches_cv2_and_jet_table_shape():
+    import cv2
+    from acoustic_image_generation_b200 import tables
+    rng = np.random.default_rng(0)
+    frame = rng.integers(0, 256, (224, 298, 3), dtype=np.uint8)
+    f = frame.astype(np.int64)
+    gray = (f[..., 0] * 3735 + f[..., 1] * 19235 + f[..., 2] * 9798 + 16384) >> 15
+    assert np.array_equal(gray, cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY))
+    lut = tables.jet_lut()
+    assert lut.shape == (256, 3) and lut.dtype == np.uint8
+    assert lut[0].tolist() == [0, 0, 127] and lut[255].tolist() == [127, 0, 0]      # dark blue -> dark red
+    assert lut[128].tolist() == [124, 255, 121]                                   # green plateau in the middle
+    out = oracle.overlay(np.zeros((4, 4), np.float32), None, lut)
+    assert out.shape == (4, 4, 3) and np.array_equal(out[0, 0], lut[0])
