@@ -118,6 +118,8 @@ struct aig_handle {
     bool chain_overlap = true;
     int chain_mode = 2;                 // 2: one fused persistent kernel; 1/0: two kernels (see chain_overlap)
     int fused_variant = 2;              // 96 KiB stages x 2 measured best (profiles/r01_tune_chain.txt)
+    int heatmap_exact = 0;              // 1: float64 replica of the oracle's bilinear; 0: float32 fast path
+    bool heat_attr_set = false;
     int l2_evict_first = 0;             // L2 evict-first hint on the spectrum loads (measured slower: off)
     int keep_mfcc_in_l2 = 1;            // fused kernel: evict-last hint on the MFCC stores the energy warps re-read
     bool fused_attr_set[4] = {false, false, false, false};
@@ -613,6 +615,8 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
     } else if (key == "chain_energy_ctas_per_sm") {
         if (value < 1 || value > 16) return h->fail(AIG_ERR_ARGUMENT, "chain_energy_ctas_per_sm out of range");
         h->chain_energy_ctas_per_sm = static_cast<int>(value);
+    } else if (key == "heatmap_exact") {
+        h->heatmap_exact = value != 0;
     } else if (key == "keep_mfcc_in_l2") {
         h->keep_mfcc_in_l2 = value != 0;
     } else if (key == "l2_evict_first") {
@@ -765,9 +769,19 @@ int aig_heatmap(aig_handle* h, const double* energy, int64_t n_frames, int out_h
     const double* d_energy = io.in(energy, n * kFramePixels);
     float* d_heat = io.out(heat_out, n * out_h * out_w);
     if (io.failed) return io.finish();
-    const size_t smem = static_cast<size_t>(out_w + out_h) * (sizeof(double) + sizeof(int));
+    const size_t fast_smem = (static_cast<size_t>(kFrameH) * out_w + 2 * static_cast<size_t>(out_w + out_h)) * sizeof(float);
     LaunchScope scope(h, h->stream, kKindOther);
-    heatmap_kernel<<<frames_grid(h, n_frames, 4), kHeatThreads, smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);
+    if (!h->heatmap_exact && fast_smem <= 200 * 1024) {
+        if (!h->heat_attr_set) {
+            AIG_CK(cudaFuncSetAttribute(heatmap_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            h->heat_attr_set = true;
+        }
+        const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (fast_smem + 12 * 1024))));
+        heatmap_fast_kernel<<<frames_grid(h, n_frames, per_sm), kHeatThreads, fast_smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);
+    } else {
+        const size_t smem = static_cast<size_t>(out_w + out_h) * (sizeof(double) + sizeof(int));
+        heatmap_kernel<<<frames_grid(h, n_frames, 4), kHeatThreads, smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);
+    }
     rc = scope.done("heatmap_kernel");
     if (rc != AIG_OK) return rc;
     return io.finish();

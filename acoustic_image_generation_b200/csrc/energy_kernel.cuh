@@ -284,6 +284,105 @@ heatmap_kernel(const double* __restrict__ energy, long long n_frames, int out_h,
     }
 }
 
+// Fast path (default): the same map in float32.  Bilinear interpolation commutes with the affine map
+// t = (e - min e) / (max e - min e), so the frame is first normalised to [0, 1] in float64 (1728 values) and everything
+// per output pixel - separable bilinear, min/max of the up-sampled image, final normalisation - runs in float32 on
+// values of order one: error ~1e-7 of the output range however flat the raw energies are.  The horizontal pass is done
+// once into shared memory (36 x out_w), so an output pixel costs two shared loads and three FMAs per pass and the
+// kernel approaches the HBM write rate (out_h * out_w * 4 B per frame).
+// Dynamic shared memory: 36 * out_w floats (rows) + out_w * (int + float) + out_h * (int + float).
+__global__ void __launch_bounds__(kHeatThreads)
+heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int out_h, int out_w,
+                    float* __restrict__ heat) {
+    extern __shared__ float s_fast[];
+    __shared__ float s_t[kFramePixels];
+    __shared__ double s_red64[2][kHeatThreads / 32];
+    __shared__ float s_red32[2][kHeatThreads / 32];
+    float* s_rows = s_fast;                                         // [36][out_w]
+    float* s_wx = s_rows + kFrameH * out_w;                         // [out_w]
+    float* s_wy = s_wx + out_w;                                     // [out_h]
+    int* s_x0 = reinterpret_cast<int*>(s_wy + out_h);               // [out_w] x0 | x1 << 16
+    int* s_y0 = s_x0 + out_w;                                       // [out_h]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int d = tid; d < out_w; d += kHeatThreads) {
+        int i0, i1; double w;
+        linear_tap(d, kFrameW, out_w, &i0, &i1, &w);
+        s_x0[d] = i0 | (i1 << 16); s_wx[d] = static_cast<float>(w);
+    }
+    for (int d = tid; d < out_h; d += kHeatThreads) {
+        int i0, i1; double w;
+        linear_tap(d, kFrameH, out_h, &i0, &i1, &w);
+        s_y0[d] = i0 | (i1 << 16); s_wy[d] = static_cast<float>(w);
+    }
+    for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
+        __syncthreads();
+        // frame min / max in float64, then t = (e - min) / (max - min) as float32
+        double e[(kFramePixels + kHeatThreads - 1) / kHeatThreads];
+        double lo = CUDART_INF, hi = -CUDART_INF;
+#pragma unroll
+        for (int i = 0; i < (kFramePixels + kHeatThreads - 1) / kHeatThreads; ++i) {
+            const int p = tid + i * kHeatThreads;
+            e[i] = p < kFramePixels ? energy[frame * kFramePixels + p] : CUDART_NAN;
+            lo = fmin(lo, e[i]); hi = fmax(hi, e[i]);
+        }
+        lo = warp_min(lo); hi = warp_max(hi);
+        if (lane == 0) { s_red64[0][warp] = lo; s_red64[1][warp] = hi; }
+        __syncthreads();
+        lo = s_red64[0][0]; hi = s_red64[1][0];
+#pragma unroll
+        for (int w = 1; w < kHeatThreads / 32; ++w) { lo = fmin(lo, s_red64[0][w]); hi = fmax(hi, s_red64[1][w]); }
+        const double span = hi - lo;
+#pragma unroll
+        for (int i = 0; i < (kFramePixels + kHeatThreads - 1) / kHeatThreads; ++i) {
+            const int p = tid + i * kHeatThreads;
+            if (p < kFramePixels) s_t[p] = span > 0.0 ? static_cast<float>((e[i] - lo) / span) : 0.f;
+        }
+        __syncthreads();
+        // horizontal pass, once
+        for (int i = tid; i < kFrameH * out_w; i += kHeatThreads) {
+            const int r = i / out_w, x = i - r * out_w;
+            const int xi = s_x0[x];
+            const float wx = s_wx[x];
+            const float a = s_t[r * kFrameW + (xi & 0xffff)], b = s_t[r * kFrameW + (xi >> 16)];
+            s_rows[i] = fmaf(b - a, wx, a);
+        }
+        __syncthreads();
+        // pass 1: min / max of the up-sampled image
+        float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+        for (int y = warp; y < out_h; y += kHeatThreads / 32) {
+            const int yi = s_y0[y];
+            const float wy = s_wy[y];
+            const float* r0 = s_rows + (yi & 0xffff) * out_w;
+            const float* r1 = s_rows + (yi >> 16) * out_w;
+            for (int x = lane; x < out_w; x += 32) {
+                const float v = fmaf(r1[x] - r0[x], wy, r0[x]);
+                mn = fminf(mn, v); mx = fmaxf(mx, v);
+            }
+        }
+        mn = warp_min(mn); mx = warp_max(mx);
+        if (lane == 0) { s_red32[0][warp] = mn; s_red32[1][warp] = mx; }
+        __syncthreads();
+        mn = s_red32[0][0]; mx = s_red32[1][0];
+#pragma unroll
+        for (int w = 1; w < kHeatThreads / 32; ++w) { mn = fminf(mn, s_red32[0][w]); mx = fmaxf(mx, s_red32[1][w]); }
+        // a constant frame gives 0/0 = NaN, like the reference's (x - min) / (max - min)
+        const float inv = (span > 0.0 && mx > mn) ? 1.f / (mx - mn) : CUDART_NAN_F;
+        float* dst = heat + frame * static_cast<long long>(out_h) * out_w;
+        // pass 2: normalise and stream out (coalesced 128 B per warp store)
+        for (int y = warp; y < out_h; y += kHeatThreads / 32) {
+            const int yi = s_y0[y];
+            const float wy = s_wy[y];
+            const float* r0 = s_rows + (yi & 0xffff) * out_w;
+            const float* r1 = s_rows + (yi >> 16) * out_w;
+            float* o = dst + static_cast<long long>(y) * out_w;
+            for (int x = lane; x < out_w; x += 32) {
+                const float v = fmaf(r1[x] - r0[x], wy, r0[x]);
+                __stcs(o + x, (v - mn) * inv);
+            }
+        }
+    }
+}
+
 // mask [n, 36, 48] u8 -> mask_up [n, out_h, out_w] u8, value 1 iff bilinear(mask != 0) > 1/2 exactly.
 // Dynamic shared memory: (out_w + out_h) * 2 ints.
 __device__ __forceinline__ int upsampled_bit(const uint8_t* s_mask, int xi, int xn, int yi, int yn,

@@ -133,7 +133,8 @@ int aig_energy(aig_handle* h, const float* images, int64_t n_frames, int normali
  * matplotlib Normalize of imshow (showimages.py:148): (x - min) / (max - min) with min/max
  * over the up-sampled image.
  *   energy   [n_frames, 36, 48] float64
- *   heat_out [n_frames, out_h, out_w] float32 */
+ *   heat_out [n_frames, out_h, out_w] float32
+ * A constant map gives NaN (0/0) like the reference.  See the "heatmap_exact" option for the two arithmetic modes. */
 int aig_heatmap(aig_handle* h, const double* energy, int64_t n_frames, int out_h, int out_w,
                 float* heat_out);
 
@@ -278,6 +279,8 @@ int64_t aig_launch_count(const aig_handle* h);
  *                        images, 42 MB, stay in the 126 MB L2 between the two kernels)
  *   "chain_overlap"      1 (default): the energy kernel of chunk i runs on a second stream while the
  *                        MFCC kernel of chunk i+1 streams from HBM; 0: both on the handle's stream
+ *   "heatmap_exact"      aig_heatmap: 0 (default) float32 bilinear on the frame-normalised map (error ~1e-7, HBM-write
+ *                        bound); 1 the float64 replica of cv2.resize + Normalize (bit-equal to the NumPy oracle)
  *   "keep_mfcc_in_l2"    fused kernel: 1 (default) L2 evict-last hint on the MFCC stores, so the energy warps'
  *                        read-back one frame later still hits L2; 0: plain stores
  *   "l2_evict_first"     1: L2 evict-first cache hint on the TMA spectrum loads; 0 (default): normal policy

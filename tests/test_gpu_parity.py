@@ -241,16 +241,34 @@ def test_find_logen_dropin_scales_argument_in_place(path, golden, torch):
     assert np.array_equal(en_dev.cpu().numpy(), en)
 
 
-@pytest.mark.parametrize('shape', [(224, 298), (224, 224), (36, 48), (100, 77)])
-def test_heatmap_matches_oracle_and_cv2_golden(path, golden, shape):
+@pytest.mark.parametrize('exact', [0, 1])
+@pytest.mark.parametrize('shape', [(224, 298), (224, 224), (36, 48), (100, 77), (448, 596)])
+def test_heatmap_matches_oracle_and_cv2_golden(path, golden, shape, exact):
+    """Default: float32 bilinear on the frame-normalised map (HBM-write-bound, error ~1e-7); heatmap_exact = 1: the
+    float64 replica of the oracle's arithmetic (error exactly 0)."""
     e = golden('energy')['energy_smooth']
-    got = path.heatmap(e, *shape)
+    path.set_option('heatmap_exact', exact)
+    try:
+        got = path.heatmap(e, *shape)
+        flat = path.heatmap(np.full((1, 36, 48), 0.25), *shape)
+    finally:
+        path.set_option('heatmap_exact', 0)
     want = np.stack([oracle.heatmap(x, *shape) for x in e], 0)
     assert got.dtype == np.float32 and got.shape == (2,) + shape
     err = np.abs(got.astype(np.float64) - want).max()
-    print('heatmap %s: max abs err %.3e' % (shape, err))
-    assert err <= HEAT_TOL
-    assert got.min() == 0.0 and got.max() == 1.0
+    print('heatmap %s exact=%d: max abs err %.3e' % (shape, exact, err))
+    assert err <= (0.0 if exact else 2e-6) and err <= HEAT_TOL
+    assert got.min() == 0.0 and abs(float(got.max()) - 1.0) <= 1e-6
+    assert np.isnan(flat).all()                              # constant map: (x - min) / (max - min) = 0/0, as matplotlib
+    # nearly flat map (range 1e-9 of the level): float32 on raw energies would lose it, the normalised form does not
+    base = np.full((1, 36, 48), 0.04)
+    base[0, 10:20, 5:30] += 4e-11
+    path.set_option('heatmap_exact', exact)
+    try:
+        tiny = path.heatmap(base, *shape)
+    finally:
+        path.set_option('heatmap_exact', 0)
+    assert np.abs(tiny[0] - oracle.heatmap(base[0], *shape)).max() <= 2e-6
     key = 'up_%d_%d' % shape
     if key in golden('heatmap'):
         up = golden('heatmap')[key]                       # cv2.resize output of frame 0
@@ -542,3 +560,51 @@ def test_overlay_bit_exact_vs_oracle(path, golden, torch):
     assert np.array_equal(bare[0], oracle.overlay(heat[0], None, lut))
     dev = path.overlay(torch.from_numpy(heat).cuda(), torch.from_numpy(frames).cuda(), alpha=0.5)
     assert dev.is_cuda and np.array_equal(dev.cpu().numpy()[0], oracle.overlay(heat[0], frames[0], lut, 0.5))
+
+
+# ----------------------------------------------------------------------------------------------
+# error behaviour of the C ABI (negative status + message, never a crash, never a CPU fallback)
+# ----------------------------------------------------------------------------------------------
+def test_argument_errors_are_reported(path):
+    import ctypes
+    from acoustic_image_generation_b200 import _lib
+    lib = _lib.load()
+    h = path._h
+    buf = np.zeros((1728, 512), np.float32)
+    out = np.zeros((1728, 12), np.float32)
+    # flip180 needs whole frames
+    assert lib.aig_mfcc(h, buf.ctypes.data, 1000, out.ctypes.data, 1, 1728) == -1
+    assert b'multiple of frame_pixels' in lib.aig_last_error(h)
+    # null buffers
+    assert lib.aig_mfcc(h, None, 10, out.ctypes.data, 0, 1) == -1
+    assert lib.aig_energy(h, None, 1, 0, None, None, None, None) == -1
+    # negative counts, oversize outputs, too many thresholds
+    assert lib.aig_normalize_images(h, buf.ctypes.data, -1, buf.ctypes.data) == -1
+    e = np.zeros((1, 36, 48)); big = np.zeros(4, np.float32)
+    assert lib.aig_heatmap(h, e.ctypes.data, 1, 4096, 10, big.ctypes.data) == -1
+    thr = np.linspace(0, 1, 2000); pos = np.zeros(2000, np.int64); num = np.zeros(1, np.int64)
+    m = np.zeros((1, 1728), np.uint8)
+    assert lib.aig_iou_sweep(h, m.ctypes.data, m.ctypes.data, 1, thr.ctypes.data, 2000, None, None, pos.ctypes.data, num.ctypes.data) == -1
+    assert lib.aig_set_option(h, b'no_such_option', 1) == -1
+    assert lib.aig_set_option(h, b'mfcc_variant', 99) == -1
+    with pytest.raises(aig.AigError):
+        path.set_option('chain_mode', 7)
+    with pytest.raises(ValueError):
+        path.mfcc_image(np.zeros((1, 36, 48, 100), np.float32))
+    with pytest.raises(aig.AigError):
+        aig.auc([0.0], [1.0])
+    # filtfilt: rows must be longer than the padding
+    b, a, zi = tables.butter_lowpass()
+    with pytest.raises(aig.AigError):
+        path.butter_lowpass_filter(np.zeros((2, 20), np.float32))
+    # the chained pass refuses non-reference tables instead of silently using the wrong filter bank
+    bank2 = aig.createfilters(256, 20, 300, 4000, 8000)
+    dct2, lifter2, mfnorm2 = tables.mfcc_constants(20, 10, 22)
+    p2 = aig.AcousticPath(0, tables_=(bank2, dct2, lifter2, mfnorm2))
+    with pytest.raises(aig.AigError) as info:
+        p2.mfcc_energy(np.zeros((1, 36, 48, 512), np.float32))
+    assert info.value.code == -3
+    p2.close()
+    # zero-sized work is a no-op
+    assert path.mfcc_rows(np.zeros((0, 512), np.float32)).shape == (0, 12)
+    assert lib.aig_energy(h, buf.ctypes.data, 0, 0, None, None, None, None) == 0
