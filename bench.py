@@ -188,8 +188,7 @@ def run_gpu(args):
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
-    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-        os.environ['NCCL_DEBUG'] = 'WARN'           # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # NCCL's banner / warnings go to stderr: stdout is ONE JSON line
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
     torch.cuda.set_device(local)
