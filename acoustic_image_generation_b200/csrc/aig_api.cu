@@ -313,7 +313,7 @@ constexpr Variant kVariants[kNumVariants] = {
     {256, 1, 4, 1},    // 8: 256-spectrum tiles
     {128, 1, 6, 2},    // 9: run-time ring index (6 does not divide 16)
 };
-constexpr int kDefaultVariant = 0;   // best for the chained pass on B200 (profiles/r01_tune_chain.txt); 5 is best for MFCC alone
+constexpr int kDefaultVariant = 8;   // 256-spectrum tiles, one CTA/SM: best for aig_mfcc alone (profiles/r01_tune_fused_and_hint.txt)
 
 template <int V>
 int launch_banded_variant(aig_handle* h, const CUtensorMap& map, float* out, unsigned n_rows, int flip180,

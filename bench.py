@@ -177,6 +177,28 @@ class ClockSampler(threading.Thread):
                 'reasons': reasons, 'samples': len(self.samples)}
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank's host threads (and, by first touch, its pinned staging buffers) to the NUMA node its GPU hangs
+    off, so that eight ranks streaming 53 GB/s each over PCIe do not all pull from one socket's memory."""
+    try:
+        prop = torch.cuda.get_device_properties(local)
+        bdf = '%04x:%02x:%02x.0' % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
@@ -193,6 +215,7 @@ def run_gpu(args):
         raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa_node = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -325,7 +348,8 @@ def run_gpu(args):
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': e2e_frames * IN_BYTES,
                 'd2h_bytes_per_step': e2e_frames * (MFCC_BYTES + FRAME_PIXELS * 8 + FRAME_PIXELS),
                 'frames_per_step': e2e_frames, 'steps': args.e2e_steps,
-                'api': 'AcousticPath.mfcc_energy(pinned numpy) -> aig_mfcc_energy, synchronous'},
+                'api': 'AcousticPath.mfcc_energy(pinned numpy) -> aig_mfcc_energy, synchronous',
+                'host_numa_node_rank0': numa_node},
         'gpu_launches': int(launches),
         'clocks': clocks,
         'result': {'auc': auc, 'num': int(host_counts[-1]), 'pos': [int(v) for v in host_counts[:-1]]},

@@ -608,3 +608,50 @@ def test_argument_errors_are_reported(path):
     # zero-sized work is a no-op
     assert path.mfcc_rows(np.zeros((0, 512), np.float32)).shape == (0, 12)
     assert lib.aig_energy(h, buf.ctypes.data, 0, 0, None, None, None, None) == 0
+
+
+def test_four_worker_threads_each_with_their_own_handle(golden):
+    """The reference's tf.data map runs num_parallel_calls=4 Python workers (outdoor_data_mfcc.py:82) that call
+    get_feats / find_logen concurrently; the drop-ins keep one handle per thread and ctypes releases the GIL."""
+    import threading
+    bank, dct, lifter, mfnorm = tables.reference_tables()
+    power = synth.power_frames(4, 33, 'chi2').reshape(4, -1, 512)
+    want = [oracle.get_feats(512, p, 12, dct, mfnorm, lifter, bank) for p in power]
+    imgs = synth.sigmoid_images(4, 34)
+    want_e = [oracle.find_logen(f.copy()) for f in imgs]
+    results, errors, handles = [None] * 4, [], [None] * 4
+
+    def worker(i):
+        try:
+            for _ in range(5):
+                feats = aig.get_feats(512, power[i], 12, dct, mfnorm, lifter, bank)
+                en = aig.find_logen(imgs[i].copy())
+            results[i] = (feats, en)
+            handles[i] = id(aig.default_path())
+        except Exception as exc:            # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert len(set(handles)) == 4                       # one libaig handle per worker thread
+    for i in range(4):
+        assert np.abs(results[i][0] - want[i]).max() <= MFCC_TOL
+        assert np.abs(results[i][1] - want_e[i]).max() <= ENERGY_RTOL * np.abs(want_e[i]).max()
+
+
+def test_plain_c_program_against_the_abi(tmp_path):
+    """examples/c_abi_smoke.c: the ABI is usable from C with nothing but the header and the shared object."""
+    import os
+    import subprocess
+    from acoustic_image_generation_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / 'c_abi_smoke')
+    subprocess.run(['gcc', '-O2', '-I', os.path.join(root, 'include'), os.path.join(root, 'examples', 'c_abi_smoke.c'), '-o', exe,
+                    '-L', _lib.CSRC, '-laig', '-lm', '-Wl,-rpath,' + _lib.CSRC], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    print(out)
+    assert 'tables match' in out and 'energy[0]' in out and 'auc =' in out
