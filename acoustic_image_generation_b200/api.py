@@ -140,6 +140,13 @@ class AcousticPath:
         self._check(self._lib.aig_profile_read(self._h, ms, cnt))
         return {k: (ms[i], int(cnt[i])) for i, k in enumerate(('mfcc', 'energy', 'other'))}
 
+    def _a(self, x, dtype, writable=False):
+        """Resolve a caller buffer and refuse CUDA tensors that live on another device than this handle's."""
+        arg = _Arg(x, dtype, writable)
+        if arg.torch_device is not None and arg.torch_device.index not in (None, self.device):
+            raise ValueError('tensor is on %s but this AcousticPath runs on cuda:%d' % (arg.torch_device, self.device))
+        return arg
+
     def _empty(self, shape, dtype, like):
         """Output buffer on the side the input lives on."""
         if like.torch_device is not None or like.on_device:
@@ -194,12 +201,12 @@ class AcousticPath:
     # -- stage 1 ------------------------------------------------------------------------------
     def mfcc_rows(self, beam, flip180=False, frame_pixels=FRAME_PIXELS, out=None):
         """[n, fft_len] float32 power rows -> [n, mfcc_num] float32 (get_feats + np.float32)."""
-        a = _Arg(beam, np.float32)
+        a = self._a(beam, np.float32)
         n = int(np.prod(a.shape)) // self.fft_len
         if n * self.fft_len != int(np.prod(a.shape)):
             raise ValueError('beam has %s elements, not a multiple of fft_len=%d' % (a.shape, self.fft_len))
         res = out if out is not None else self._empty((n, self.mfcc_num), np.float32, a)
-        o = _Arg(res, np.float32, writable=True)
+        o = self._a(res, np.float32, writable=True)
         if int(np.prod(o.shape)) != n * self.mfcc_num:
             raise ValueError('out has shape %s, expected %d x %d values' % (o.shape, n, self.mfcc_num))
         self._check(self._lib.aig_mfcc(self._h, a.ptr, n, o.ptr, int(bool(flip180)), int(frame_pixels)))
@@ -208,7 +215,7 @@ class AcousticPath:
     def mfcc_image(self, power, flip=False):
         """[N, 36, 48, 512] float32 -> [N, 36, 48, 12] float32 MFCC acoustic images; ``flip`` applies the
         flip_left_right + flip_up_down of _parse_sequence (outdoor_data_mfcc.py:314-315)."""
-        a = _Arg(power, np.float32)
+        a = self._a(power, np.float32)
         if len(a.shape) != 4 or a.shape[1:] != (FRAME_H, FRAME_W, FFT_LEN):
             raise ValueError('expected [N, 36, 48, 512], got %s' % (a.shape,))
         rows = self.mfcc_rows(a.keep, flip180=flip, frame_pixels=FRAME_PIXELS)
@@ -235,7 +242,7 @@ class AcousticPath:
             raise ValueError('window must have 1024 entries')
         res = self._empty((n, 512), np.float32, a)
         self._check(self._lib.aig_power_spectrum(self._h, a.ptr, is_int, n, None if win is None else win.ctypes.data,
-                                                 _Arg(res, np.float32, True).ptr))
+                                                 self._a(res, np.float32, True).ptr))
         return res
 
     def build_spectrograms(self, audio):
@@ -254,32 +261,32 @@ class AcousticPath:
         b, acoef, zi = tables.butter_lowpass(sample_rate, cutoff, order)
         res = self._empty(a.shape, np.float32, a)
         self._check(self._lib.aig_filtfilt(self._h, a.ptr, is_int, n, int(length), b.ctypes.data, acoef.ctypes.data,
-                                           zi.ctypes.data, len(b), _Arg(res, np.float32, True).ptr))
+                                           zi.ctypes.data, len(b), self._a(res, np.float32, True).ptr))
         return res
 
     def normalize_mfcc(self, mfcc):
         """Per-vector float32 min-max of [n, 12] MFCCs (_normalize_mfcc, outdoor_data_mfcc.py:696-703)."""
-        a = _Arg(mfcc, np.float32)
+        a = self._a(mfcc, np.float32)
         n = self._frames(a.shape, MFCC_NUM)
         res = self._empty(a.shape, np.float32, a)
-        self._check(self._lib.aig_normalize_mfcc(self._h, a.ptr, n, _Arg(res, np.float32, True).ptr))
+        self._check(self._lib.aig_normalize_mfcc(self._h, a.ptr, n, self._a(res, np.float32, True).ptr))
         return res
 
     def tile_mfcc(self, mfcc, normalize=False):
         """mfccmap: [B, 12] -> [B, 36, 48, 12] (trainer/mfcctrainer.py:38-40), optionally normalising each vector first."""
-        a = _Arg(mfcc, np.float32)
+        a = self._a(mfcc, np.float32)
         n = self._frames(a.shape, MFCC_NUM)
         res = self._empty((n, FRAME_H, FRAME_W, MFCC_NUM), np.float32, a)
-        self._check(self._lib.aig_tile_mfcc(self._h, a.ptr, n, int(bool(normalize)), _Arg(res, np.float32, True).ptr))
+        self._check(self._lib.aig_tile_mfcc(self._h, a.ptr, n, int(bool(normalize)), self._a(res, np.float32, True).ptr))
         return res
 
     # -- stage 2 ------------------------------------------------------------------------------
     def normalize_images(self, images):
         """Per-frame (x - min) / max(x - min) in float32 over [N, 36, 48, 12] (outdoor_data_mfcc.py:672-679)."""
-        a = _Arg(images, np.float32)
+        a = self._a(images, np.float32)
         n = self._frames(a.shape, FRAME_PIXELS * MFCC_NUM)
         res = self._empty(a.shape, np.float32, a)
-        self._check(self._lib.aig_normalize_images(self._h, a.ptr, n, _Arg(res, np.float32, True).ptr))
+        self._check(self._lib.aig_normalize_images(self._h, a.ptr, n, self._a(res, np.float32, True).ptr))
         return res
 
     @staticmethod
@@ -291,7 +298,7 @@ class AcousticPath:
 
     def energy(self, images, normalize_first=False, want_scaled=False, want_mean=False):
         """find_logen + mean mask over a batch.  Returns (energy f64 [N,36,48], mask u8 [N,36,48][, scaled][, mean])."""
-        a = _Arg(images, np.float32)
+        a = self._a(images, np.float32)
         n = self._frames(a.shape, FRAME_PIXELS * MFCC_NUM)
         energy = self._empty((n, FRAME_H, FRAME_W), np.float64, a)
         mask = self._empty((n, FRAME_H, FRAME_W), np.uint8, a)
@@ -299,9 +306,9 @@ class AcousticPath:
         mean = self._empty((n,), np.float64, a) if want_mean else None
         self._check(self._lib.aig_energy(
             self._h, a.ptr, n, int(bool(normalize_first)),
-            _Arg(scaled, np.float32, True).ptr if want_scaled else None,
-            _Arg(energy, np.float64, True).ptr, _Arg(mask, np.uint8, True).ptr,
-            _Arg(mean, np.float64, True).ptr if want_mean else None))
+            self._a(scaled, np.float32, True).ptr if want_scaled else None,
+            self._a(energy, np.float64, True).ptr, self._a(mask, np.uint8, True).ptr,
+            self._a(mean, np.float64, True).ptr if want_mean else None))
         out = (energy, mask)
         if want_scaled:
             out += (scaled,)
@@ -332,36 +339,36 @@ class AcousticPath:
 
     def heatmap(self, energy, out_h=HEAT_H, out_w=HEAT_W):
         """cv2.resize(map, (out_w, out_h)) + imshow's implicit min/max normalisation, float32 [N, out_h, out_w]."""
-        a = _Arg(energy, np.float64)
+        a = self._a(energy, np.float64)
         n = self._frames(a.shape, FRAME_PIXELS)
         res = self._empty((n, out_h, out_w), np.float32, a)
-        self._check(self._lib.aig_heatmap(self._h, a.ptr, n, int(out_h), int(out_w), _Arg(res, np.float32, True).ptr))
+        self._check(self._lib.aig_heatmap(self._h, a.ptr, n, int(out_h), int(out_w), self._a(res, np.float32, True).ptr))
         return res
 
     def overlay(self, heat, frames_bgr=None, alpha=0.7):
         """Jet-coloured heat map blended over the gray video frame (showvideo.py:224-229), RGB uint8 [N, H, W, 3].
         heat: float32 [N, H, W] in [0, 1] (from ``heatmap``); frames_bgr: uint8 [N, H, W, 3] (OpenCV order) or None."""
-        a = _Arg(heat, np.float32)
+        a = self._a(heat, np.float32)
         if len(a.shape) != 3:
             raise ValueError('heat must be [N, H, W], got %s' % (a.shape,))
         n, hh, ww = a.shape
         b = None
         if frames_bgr is not None:
-            b = _Arg(frames_bgr, np.uint8)
+            b = self._a(frames_bgr, np.uint8)
             if tuple(b.shape) != (n, hh, ww, 3):
                 raise ValueError('frames must be [N, H, W, 3] uint8 matching the heat maps')
         lut = tables.jet_lut()
         res = self._empty((n, hh, ww, 3), np.uint8, a)
         self._check(self._lib.aig_overlay(self._h, a.ptr, b.ptr if b is not None else None, n, hh, ww, float(alpha),
-                                          lut.ctypes.data, _Arg(res, np.uint8, True).ptr))
+                                          lut.ctypes.data, self._a(res, np.uint8, True).ptr))
         return res
 
     def resize_mask(self, mask, out_h=HEAT_H, out_w=HEAT_W):
         """1.0 * (cv2.resize(mask * 1.0, (out_w, out_h)) > 0.5) as uint8 [N, out_h, out_w] (showimages_bb.py:303-304)."""
-        a = _Arg(mask, np.uint8)
+        a = self._a(mask, np.uint8)
         n = self._frames(a.shape, FRAME_PIXELS)
         res = self._empty((n, out_h, out_w), np.uint8, a)
-        self._check(self._lib.aig_resize_mask(self._h, a.ptr, n, int(out_h), int(out_w), _Arg(res, np.uint8, True).ptr))
+        self._check(self._lib.aig_resize_mask(self._h, a.ptr, n, int(out_h), int(out_w), self._a(res, np.uint8, True).ptr))
         return res
 
     def mfcc_energy(self, power, flip=False, normalize_first=True, want_mean=False, out=None):
@@ -369,7 +376,7 @@ class AcousticPath:
 
         ``out=(mfcc, energy, mask)`` supplies the result buffers (e.g. pinned host arrays, or device tensors
         reused across calls) instead of allocating them."""
-        a = _Arg(power, np.float32)
+        a = self._a(power, np.float32)
         n = self._frames(a.shape, FRAME_PIXELS * FFT_LEN)
         if out is not None:
             mfcc, energy, mask = out
@@ -377,14 +384,14 @@ class AcousticPath:
             mfcc = self._empty((n, FRAME_H, FRAME_W, MFCC_NUM), np.float32, a)
             energy = self._empty((n, FRAME_H, FRAME_W), np.float64, a)
             mask = self._empty((n, FRAME_H, FRAME_W), np.uint8, a)
-        o_mfcc, o_energy, o_mask = _Arg(mfcc, np.float32, True), _Arg(energy, np.float64, True), _Arg(mask, np.uint8, True)
+        o_mfcc, o_energy, o_mask = self._a(mfcc, np.float32, True), self._a(energy, np.float64, True), self._a(mask, np.uint8, True)
         if (int(np.prod(o_mfcc.shape)), int(np.prod(o_energy.shape)), int(np.prod(o_mask.shape))) != (
                 n * FRAME_PIXELS * MFCC_NUM, n * FRAME_PIXELS, n * FRAME_PIXELS):
             raise ValueError('out buffers do not match %d frames' % n)
         mean = self._empty((n,), np.float64, a) if want_mean else None
         self._check(self._lib.aig_mfcc_energy(
             self._h, a.ptr, n, int(bool(flip)), int(bool(normalize_first)), o_mfcc.ptr, o_energy.ptr, o_mask.ptr,
-            _Arg(mean, np.float64, True).ptr if want_mean else None))
+            self._a(mean, np.float64, True).ptr if want_mean else None))
         return (mfcc, energy, mask) + ((mean,) if want_mean else ())
 
     # -- stage 3 ------------------------------------------------------------------------------
@@ -423,7 +430,7 @@ class AcousticPath:
 
         Returns (inter int64 [n], union int64 [n], pos int64 [K], num int).  ``pos`` / ``num`` from a
         previous call can be passed back in to accumulate across batches."""
-        a, b = _Arg(mask_a, np.uint8), _Arg(mask_b, np.uint8)
+        a, b = self._a(mask_a, np.uint8), self._a(mask_b, np.uint8)
         n = self._frames(a.shape, FRAME_PIXELS)
         if self._frames(b.shape, FRAME_PIXELS) != n:
             raise ValueError('mask batches differ: %s vs %s' % (a.shape, b.shape))
@@ -432,7 +439,7 @@ class AcousticPath:
         inter = self._empty((n,), np.int64, a)
         union = self._empty((n,), np.int64, a)
         self._check(self._lib.aig_iou_sweep(self._h, a.ptr, b.ptr, n, thr.ptr, thr.shape[0],
-                                            _Arg(inter, np.int64, True).ptr, _Arg(union, np.int64, True).ptr,
+                                            self._a(inter, np.int64, True).ptr, self._a(union, np.int64, True).ptr,
                                             p_arg.ptr, c_arg.ptr))
         return inter, union, pos, self._num_result(cnt)
 
@@ -441,9 +448,9 @@ class AcousticPath:
         """FlickrSoundNet consensus IoU and success counts (showimages_bb.py:288-321).
 
         mask u8 [n, 36, 48]; boxes int32 [n, 3] each.  Returns (2*I int64 [n], 2*U int64 [n], pos, num)."""
-        a = _Arg(mask, np.uint8)
+        a = self._a(mask, np.uint8)
         n = self._frames(a.shape, FRAME_PIXELS)
-        boxes = [_Arg(v, np.int32) for v in (xmin, xmax, ymin, ymax)]
+        boxes = [self._a(v, np.int32) for v in (xmin, xmax, ymin, ymax)]
         for bx in boxes:
             if int(np.prod(bx.shape)) != 3 * n:
                 raise ValueError('boxes must be [n, 3] int32, got %s for n=%d' % (bx.shape, n))
@@ -453,7 +460,7 @@ class AcousticPath:
         union2 = self._empty((n,), np.int64, a)
         self._check(self._lib.aig_ciou_sweep(self._h, a.ptr, boxes[0].ptr, boxes[1].ptr, boxes[2].ptr, boxes[3].ptr,
                                              n, int(out_hw[0]), int(out_hw[1]), thr.ptr, thr.shape[0],
-                                             _Arg(inter2, np.int64, True).ptr, _Arg(union2, np.int64, True).ptr,
+                                             self._a(inter2, np.int64, True).ptr, self._a(union2, np.int64, True).ptr,
                                              p_arg.ptr, c_arg.ptr))
         return inter2, union2, pos, self._num_result(cnt)
 

@@ -118,6 +118,7 @@ struct aig_handle {
     bool chain_overlap = true;
     int chain_mode = 2;                 // 2: one fused persistent kernel; 1/0: two kernels (see chain_overlap)
     int fused_variant = 2;              // 96 KiB stages x 2 measured best (profiles/r01_tune_chain.txt)
+    int64_t launch_row_limit = (int64_t(1) << 31) - 1024;   // TMA coordinates are int32: rows per launch (testable via option)
     int heatmap_exact = 0;              // 1: float64 replica of the oracle's bilinear; 0: float32 fast path
     bool heat_attr_set = false;
     int l2_evict_first = 0;             // L2 evict-first hint on the spectrum loads (measured slower: off)
@@ -364,7 +365,7 @@ int launch_mfcc(aig_handle* h, const float* d_power, int64_t n_rows, float* d_ou
         return h->fail(AIG_ERR_ARGUMENT, "aig_mfcc: device buffers must be 16-byte aligned");
     const int variant = h->variant < 0 ? kDefaultVariant : h->variant;
     const int64_t unit = flip180 ? frame_pixels : 256;
-    const int64_t max_rows = ((int64_t(1) << 31) - 1024) / unit * unit;
+    const int64_t max_rows = std::max<int64_t>(unit, h->launch_row_limit / unit * unit);
     for (int64_t done = 0; done < n_rows; done += max_rows) {
         const int64_t rows = std::min(max_rows, n_rows - done);
         CUtensorMap map;
@@ -430,7 +431,7 @@ int launch_fused(aig_handle* h, const float* d_power, int64_t n_frames, float* d
                  double* d_energy, uint8_t* d_mask, double* d_mean) {
     if ((reinterpret_cast<uintptr_t>(d_power) & 15u) || (reinterpret_cast<uintptr_t>(d_mfcc) & 15u))
         return h->fail(AIG_ERR_ARGUMENT, "aig_mfcc_energy: device buffers must be 16-byte aligned");
-    const int64_t max_frames = ((int64_t(1) << 31) - 1024) / kFramePixels;
+    const int64_t max_frames = std::max<int64_t>(1, h->launch_row_limit / kFramePixels);
     for (int64_t done = 0; done < n_frames; done += max_frames) {
         const int64_t frames = std::min(max_frames, n_frames - done);
         CUtensorMap map;
@@ -615,6 +616,9 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
     } else if (key == "chain_energy_ctas_per_sm") {
         if (value < 1 || value > 16) return h->fail(AIG_ERR_ARGUMENT, "chain_energy_ctas_per_sm out of range");
         h->chain_energy_ctas_per_sm = static_cast<int>(value);
+    } else if (key == "launch_row_limit") {
+        if (value < 1 || value > (int64_t(1) << 31) - 1024) return h->fail(AIG_ERR_ARGUMENT, "launch_row_limit out of range");
+        h->launch_row_limit = value;
     } else if (key == "heatmap_exact") {
         h->heatmap_exact = value != 0;
     } else if (key == "keep_mfcc_in_l2") {

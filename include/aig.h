@@ -279,6 +279,8 @@ int64_t aig_launch_count(const aig_handle* h);
  *                        images, 42 MB, stay in the 126 MB L2 between the two kernels)
  *   "chain_overlap"      1 (default): the energy kernel of chunk i runs on a second stream while the
  *                        MFCC kernel of chunk i+1 streams from HBM; 0: both on the handle's stream
+ *   "launch_row_limit"   spectra per kernel launch (default 2^31 - 1024: TMA tile coordinates are int32, larger batches
+ *                        are split into several launches); lowering it exercises that split on small inputs
  *   "heatmap_exact"      aig_heatmap: 0 (default) float32 bilinear on the frame-normalised map (error ~1e-7, HBM-write
  *                        bound); 1 the float64 replica of cv2.resize + Normalize (bit-equal to the NumPy oracle)
  *   "keep_mfcc_in_l2"    fused kernel: 1 (default) L2 evict-last hint on the MFCC stores, so the energy warps'

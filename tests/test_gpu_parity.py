@@ -655,3 +655,25 @@ def test_plain_c_program_against_the_abi(tmp_path):
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     print(out)
     assert 'tables match' in out and 'energy[0]' in out and 'auc =' in out
+
+
+def test_batches_beyond_the_per_launch_limit_are_split(path):
+    """TMA tile coordinates are int32, so more than 2^31 spectra (1.2 M frames) go out as several launches; the same
+    split forced at 3000 spectra / 2 frames must not change a bit (with and without the 180-degree flip)."""
+    power = synth.power_frames(7, 44, 'chi2')
+    ref_rows = path.mfcc_rows(power.reshape(-1, 512)[:7000])
+    ref_img = path.mfcc_image(power, flip=True)
+    ref_chain = path.mfcc_energy(power, flip=True, normalize_first=True)
+    before = path.launch_count
+    path.set_option('launch_row_limit', 3000)
+    try:
+        rows = path.mfcc_rows(power.reshape(-1, 512)[:7000])
+        assert path.launch_count - before == 3                      # 7000 rows in launches of 2816 (11 x 256)
+        img = path.mfcc_image(power, flip=True)
+        path.set_option('launch_row_limit', 2 * 1728)
+        chain = path.mfcc_energy(power, flip=True, normalize_first=True)
+    finally:
+        path.set_option('launch_row_limit', (1 << 31) - 1024)
+    assert np.array_equal(rows, ref_rows) and np.array_equal(img, ref_img)
+    for a, b in zip(chain, ref_chain):
+        assert np.array_equal(a, b)
