@@ -862,16 +862,42 @@ int aig_mfcc_energy(aig_handle* h, const float* power, int64_t n_frames, int fli
         }
         return AIG_OK;
     };
+    bool d2h_overlapped = false;
     if (in_dev) {
         rc = run(power, 0, n_frames);
     } else {
         io.any_host = true;
+        // Host outputs of a host-input call: instead of one device-to-host copy at the very end, ship each chunk's
+        // results on the (otherwise idle, in fused mode) second stream while the next chunk's spectra are still coming in -
+        // PCIe is full duplex, so the result copies disappear behind the 40x larger input copies.
+        struct HostOut { char* host; char* dev; size_t bytes_per_frame; };
+        std::vector<HostOut> host_outs;
+        if (fused) {
+            const size_t per_frame[4] = {kFrameValues * sizeof(float), kFramePixels * sizeof(double), kFramePixels, sizeof(double)};
+            void* const user[4] = {mfcc_out, energy_out, mask_out, mean_out};
+            void* const devp[4] = {d_mfcc, d_energy, d_mask, d_mean};
+            for (int i = 0; i < 4; ++i)
+                if (user[i] != nullptr && devp[i] != user[i])
+                    host_outs.push_back({static_cast<char*>(user[i]), static_cast<char*>(devp[i]), per_frame[i]});
+            io.outs.clear();                       // handled chunk by chunk below
+            d2h_overlapped = !host_outs.empty();
+        }
         const int64_t chunk_rows = host_chunk_rows(kFramePixels, kFftLen);
         rc = stream_host_rows(h, power, n_frames * kFramePixels, kFftLen, chunk_rows,
                               [&](const float* d_chunk, int64_t row, int64_t rows) {
-                                  return run(d_chunk, row / kFramePixels, rows / kFramePixels);
+                                  const int64_t f0 = row / kFramePixels, nf = rows / kFramePixels;
+                                  int r = run(d_chunk, f0, nf);
+                                  if (r != AIG_OK || host_outs.empty()) return r;
+                                  AIG_CK(cudaEventRecord(h->ev_chain[1], h->stream));
+                                  AIG_CK(cudaStreamWaitEvent(h->aux_stream, h->ev_chain[1], 0));
+                                  for (auto& o : host_outs)
+                                      AIG_CK(cudaMemcpyAsync(o.host + f0 * o.bytes_per_frame, o.dev + f0 * o.bytes_per_frame,
+                                                             static_cast<size_t>(nf) * o.bytes_per_frame, cudaMemcpyDeviceToHost,
+                                                             h->aux_stream));
+                                  return AIG_OK;
                               });
     }
+    if (d2h_overlapped) AIG_CK(cudaStreamSynchronize(h->aux_stream));
     if (rc != AIG_OK) return rc;
     if (overlap) {
         AIG_CK(cudaEventRecord(h->ev_chain[3], h->aux_stream));          // results visible to the handle's stream
