@@ -87,6 +87,7 @@ SIGNATURES = {
     'aig_normalize_images': (_int, [_p, _p, _i64, _p]),
     'aig_energy': (_int, [_p, _p, _i64, _int, _p, _p, _p, _p]),
     'aig_heatmap': (_int, [_p, _p, _i64, _int, _int, _p]),
+    'aig_energy_heatmap': (_int, [_p, _p, _i64, _int, _p, _p, _p, _int, _int]),
     'aig_resize_mask': (_int, [_p, _p, _i64, _int, _int, _p]),
     'aig_mfcc_energy': (_int, [_p, _p, _i64, _int, _int, _p, _p, _p, _p]),
     'aig_iou_sweep': (_int, [_p, _p, _p, _i64, _p, _int, _p, _p, _p, _p]),

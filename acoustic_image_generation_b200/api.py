@@ -345,6 +345,19 @@ class AcousticPath:
         self._check(self._lib.aig_heatmap(self._h, a.ptr, n, int(out_h), int(out_w), self._a(res, np.float32, True).ptr))
         return res
 
+    def energy_heatmap(self, images, normalize_first=False, out_h=HEAT_H, out_w=HEAT_W):
+        """find_logen -> cv2.resize -> imshow normalisation for a batch in one call (showvideo.py:226-228):
+        returns (energy f64 [N,36,48], mask u8 [N,36,48], heat f32 [N,out_h,out_w])."""
+        a = self._a(images, np.float32)
+        n = self._frames(a.shape, FRAME_PIXELS * MFCC_NUM)
+        energy = self._empty((n, FRAME_H, FRAME_W), np.float64, a)
+        mask = self._empty((n, FRAME_H, FRAME_W), np.uint8, a)
+        heat = self._empty((n, out_h, out_w), np.float32, a)
+        self._check(self._lib.aig_energy_heatmap(self._h, a.ptr, n, int(bool(normalize_first)),
+                                                 self._a(energy, np.float64, True).ptr, self._a(mask, np.uint8, True).ptr,
+                                                 self._a(heat, np.float32, True).ptr, int(out_h), int(out_w)))
+        return energy, mask, heat
+
     def overlay(self, heat, frames_bgr=None, alpha=0.7):
         """Jet-coloured heat map blended over the gray video frame (showvideo.py:224-229), RGB uint8 [N, H, W, 3].
         heat: float32 [N, H, W] in [0, 1] (from ``heatmap``); frames_bgr: uint8 [N, H, W, 3] (OpenCV order) or None."""

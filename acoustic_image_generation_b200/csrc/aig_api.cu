@@ -401,6 +401,23 @@ int launch_energy(aig_handle* h, cudaStream_t stream, const float* d_images, int
     return scope.done("energy_kernel");
 }
 
+int launch_heatmap(aig_handle* h, const double* d_energy, int64_t n_frames, int out_h, int out_w, float* d_heat) {
+    const size_t fast_smem = (static_cast<size_t>(kFrameH) * out_w + 2 * static_cast<size_t>(out_w + out_h)) * sizeof(float);
+    LaunchScope scope(h, h->stream, kKindOther);
+    if (!h->heatmap_exact && fast_smem <= 200 * 1024) {
+        if (!h->heat_attr_set) {
+            AIG_CK(cudaFuncSetAttribute(heatmap_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            h->heat_attr_set = true;
+        }
+        const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (fast_smem + 12 * 1024))));
+        heatmap_fast_kernel<<<frames_grid(h, n_frames, per_sm), kHeatThreads, fast_smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);
+    } else {
+        const size_t smem = static_cast<size_t>(out_w + out_h) * (sizeof(double) + sizeof(int));
+        heatmap_kernel<<<frames_grid(h, n_frames, 4), kHeatThreads, smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);
+    }
+    return scope.done("heatmap_kernel");
+}
+
 // ---- fused MFCC + energy kernel ---------------------------------------------------------------------
 struct FusedVariant { int slabs, stages; };
 constexpr int kNumFusedVariants = 3;
@@ -773,20 +790,29 @@ int aig_heatmap(aig_handle* h, const double* energy, int64_t n_frames, int out_h
     const double* d_energy = io.in(energy, n * kFramePixels);
     float* d_heat = io.out(heat_out, n * out_h * out_w);
     if (io.failed) return io.finish();
-    const size_t fast_smem = (static_cast<size_t>(kFrameH) * out_w + 2 * static_cast<size_t>(out_w + out_h)) * sizeof(float);
-    LaunchScope scope(h, h->stream, kKindOther);
-    if (!h->heatmap_exact && fast_smem <= 200 * 1024) {
-        if (!h->heat_attr_set) {
-            AIG_CK(cudaFuncSetAttribute(heatmap_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            h->heat_attr_set = true;
-        }
-        const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (fast_smem + 12 * 1024))));
-        heatmap_fast_kernel<<<frames_grid(h, n_frames, per_sm), kHeatThreads, fast_smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);
-    } else {
-        const size_t smem = static_cast<size_t>(out_w + out_h) * (sizeof(double) + sizeof(int));
-        heatmap_kernel<<<frames_grid(h, n_frames, 4), kHeatThreads, smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);
-    }
-    rc = scope.done("heatmap_kernel");
+    rc = launch_heatmap(h, d_energy, n_frames, out_h, out_w, d_heat);
+    if (rc != AIG_OK) return rc;
+    return io.finish();
+}
+
+int aig_energy_heatmap(aig_handle* h, const float* images, int64_t n_frames, int normalize_first, double* energy_out,
+                       uint8_t* mask_out, float* heat_out, int out_h, int out_w) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (n_frames < 0 || (n_frames > 0 && (!images || !heat_out))) return h->fail(AIG_ERR_ARGUMENT, "aig_energy_heatmap: bad buffers");
+    if (out_h < 1 || out_w < 1 || out_h > kMaxOut || out_w > kMaxOut)
+        return h->fail(AIG_ERR_ARGUMENT, "aig_energy_heatmap: output size %dx%d outside 1..%d", out_h, out_w, kMaxOut);
+    if (n_frames == 0) return AIG_OK;
+    Io io(h);
+    const size_t n = static_cast<size_t>(n_frames);
+    const float* d_in = io.in(images, n * kFrameValues);
+    double* d_energy = energy_out ? io.out(energy_out, n * kFramePixels) : static_cast<double*>(scratch(h, n * kFramePixels * sizeof(double)));
+    uint8_t* d_mask = io.out(mask_out, n * kFramePixels);
+    float* d_heat = io.out(heat_out, n * out_h * out_w);
+    if (io.failed || !d_energy) return io.finish();
+    rc = launch_energy(h, h->stream, d_in, n_frames, normalize_first, nullptr, d_energy, d_mask, nullptr);
+    if (rc != AIG_OK) return rc;
+    rc = launch_heatmap(h, d_energy, n_frames, out_h, out_w, d_heat);
     if (rc != AIG_OK) return rc;
     return io.finish();
 }

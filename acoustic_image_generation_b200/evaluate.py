@@ -64,3 +64,11 @@ class FlickrEvaluation(_Evaluation):
         i2, u2, _, _ = self.path.ciou_sweep(mask, xmin, xmax, ymin, ymax, self._thr, out_hw=self.out_hw,
                                             pos=self.counts[:-1], num=self.counts[-1:])
         return i2, u2
+
+
+def render_heatmaps(path, reconstructed, frames_bgr=None, out_hw=(224, 298), alpha=0.7, normalize_first=False):
+    """The per-frame body of showvideo.py:217-233 / showimages.py:144-150 for a batch, on the GPU: find_logen ->
+    bilinear up-sampling -> min/max normalisation -> jet colour map blended over the gray video frame.
+    Returns RGB uint8 [N, H, W, 3] (PNG encoding and ffmpeg muxing stay with the caller)."""
+    _, _, heat = path.energy_heatmap(reconstructed, normalize_first, *out_hw)
+    return path.overlay(heat, frames_bgr, alpha)

@@ -138,6 +138,12 @@ int aig_energy(aig_handle* h, const float* images, int64_t n_frames, int normali
 int aig_heatmap(aig_handle* h, const double* energy, int64_t n_frames, int out_h, int out_w,
                 float* heat_out);
 
+/* aig_energy followed by aig_heatmap on the device, without a host round trip for the energy map: the per-frame body of
+ * showvideo.py:226-228 / showimages.py:146-148 (find_logen -> cv2.resize -> imshow normalisation) for a batch.
+ * energy_out / mask_out are nullable; heat_out [n_frames, out_h, out_w] float32 is required. */
+int aig_energy_heatmap(aig_handle* h, const float* images, int64_t n_frames, int normalize_first, double* energy_out,
+                       uint8_t* mask_out, float* heat_out, int out_h, int out_w);
+
 /* 1.0 * (cv2.resize(mask * 1.0, (out_w, out_h)) > 0.5) (showimages_bb.py:303-304), decided in
  * exact integer arithmetic.  mask [n_frames, 36, 48] uint8 -> mask_up [n_frames, out_h, out_w] uint8. */
 int aig_resize_mask(aig_handle* h, const uint8_t* mask, int64_t n_frames, int out_h, int out_w,

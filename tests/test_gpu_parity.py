@@ -677,3 +677,22 @@ def test_batches_beyond_the_per_launch_limit_are_split(path):
     assert np.array_equal(rows, ref_rows) and np.array_equal(img, ref_img)
     for a, b in zip(chain, ref_chain):
         assert np.array_equal(a, b)
+
+
+def test_energy_heatmap_combined_call(path, golden):
+    imgs = synth.smooth_images(3, 4)
+    energy, mask, heat = path.energy_heatmap(imgs)
+    e2, m2 = path.energy(imgs)
+    assert np.array_equal(energy, e2) and np.array_equal(mask, m2)
+    assert np.array_equal(heat, path.heatmap(e2))
+    assert np.abs(heat[0] - oracle.heatmap(oracle.find_logen(imgs[0].copy()))).max() <= 2e-6
+
+
+def test_render_heatmaps_driver(path):
+    from acoustic_image_generation_b200 import evaluate
+    imgs = synth.smooth_images(2, 6)
+    frames = np.random.default_rng(3).integers(0, 256, (2, 224, 298, 3), dtype=np.uint8)
+    rgb = evaluate.render_heatmaps(path, imgs, frames)
+    assert rgb.shape == (2, 224, 298, 3) and rgb.dtype == np.uint8
+    heat = path.heatmap(path.energy(imgs)[0])
+    assert np.array_equal(rgb[1], oracle.overlay(heat[1], frames[1], tables.jet_lut()))
