@@ -107,3 +107,50 @@ def test_config3_clip_stream_sharded_by_clip(path, frames_per_clip, n_clips):
         flips += int((mask_a[h].cpu().numpy() != want_masks[host_idx[h]]).sum())
     print('clip stream: boundary-pixel disagreements on sampled frames: %d' % flips)
     assert flips <= 8
+
+
+def test_soak_2048_distinct_frames_invariants_and_oracle_sample(path):
+    """2048 distinct random frames (7.2 GB) through the fused pass: global invariants recomputed on the host from the
+    GPU's own float64 energies for every frame, the oracle on a 48-frame sample, and the degenerate frames the reference
+    turns into NaN."""
+    import torch
+    n = 2048
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(99)
+    power = torch.empty((n, 36, 48, 512), device='cuda', dtype=torch.float32)
+    power.normal_(generator=gen).square_()
+    power[5] = float('nan')                     # every spectrum non-finite -> MFCC all 0 -> constant frame -> 0/0
+    power[6] = 0.0                              # all-floor frame: MFCC ~ 1e-6 rounding noise, still normalisable
+    mfcc, energy, mask, mean = path.mfcc_energy(power, flip=True, normalize_first=True, want_mean=True)
+    mfcc_h, energy_h, mask_h, mean_h = (t.cpu().numpy() for t in (mfcc, energy, mask, mean))
+    assert np.all(mfcc_h[5] == 0.0) and np.isnan(energy_h[5]).all() and np.isnan(mean_h[5]) and mask_h[5].sum() == 0
+    ok = np.ones(n, bool); ok[5] = False
+    assert np.isfinite(mfcc_h).all() and np.isfinite(energy_h[ok]).all()
+    # mean and mask are functions of the energies alone: recompute them with NumPy for all frames
+    assert np.array_equal(mean_h[ok], energy_h[ok].reshape(-1, 1728).mean(axis=1))
+    assert np.array_equal(mask_h[ok], (energy_h[ok] > mean_h[ok][:, None, None]).astype(np.uint8))
+    assert 0.2 < mask_h[ok].mean() < 0.8
+    # energies are functions of the MFCC image alone: replay stage 2 of the oracle on the GPU's MFCC for a sample
+    rng = np.random.default_rng(7)
+    sample = [5, 6] + rng.choice(n, 46, replace=False).tolist()
+    host_power = power[sample].cpu().numpy()
+    with np.errstate(invalid='ignore'):
+        want_mfcc = oracle.mfcc_image(host_power, flip=True)
+        err = np.abs(mfcc_h[sample] - want_mfcc).max()
+        assert err <= 1e-4
+        e_replay, m_replay = oracle.energy_stage(mfcc_h[sample], normalize_first=True)
+    fin = np.isfinite(e_replay).all(axis=(1, 2))
+    assert not fin[0] and fin[1:].all()
+    assert np.abs(energy_h[sample][fin] - e_replay[fin]).max() <= 1e-13 * np.abs(e_replay[fin]).max()
+    assert np.array_equal(mask_h[sample][fin], m_replay[fin])
+    # and end to end against the oracle's own MFCC: count boundary flips
+    with np.errstate(invalid='ignore'):
+        _, m_oracle = oracle.energy_stage(want_mfcc, normalize_first=True)
+    per_frame = (mask_h[sample] != m_oracle).reshape(len(sample), -1).sum(axis=1)
+    # sample[1] is the all-floor frame: its MFCC is mathematically 0, i.e. pure rounding noise (1e-15 in the reference's
+    # float64, 1e-6 here, both far inside the 1e-4 tolerance) that the min-max normalisation then stretches to [0, 1] -
+    # the reference's own mask for such a frame is noise, so it is excluded from the boundary-pixel count
+    flips = int(per_frame[2:].sum())
+    print('soak: mfcc max abs err %.2e; boundary flips vs the all-oracle chain on %d frames: %d (all-floor frame: %d)'
+          % (err, len(sample) - 2, flips, int(per_frame[1])))
+    assert flips <= 10
