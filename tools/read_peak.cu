@@ -196,6 +196,15 @@ __global__ void __launch_bounds__(ROWS + 32) tma2d_consume(const __grid_constant
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { if (WORK == 5) o[k * 32 + lane] = so[k * 32 + lane]; else __stcs(o + k * 32 + lane, so[k * 32 + lane]); }
                 __syncwarp();
+            } else if (WORK == 10 || WORK == 11 || WORK == 12) {   // per-thread stores with an L2 policy: evict_last / evict_first / no_allocate-ish
+                uint64_t pol;
+                if (WORK == 10) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+                else if (WORK == 11) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+                else asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol));
+                float* o = out + (size_t(t) * ROWS + threadIdx.x) * 12;
+                asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(o), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "l"(pol) : "memory");
+                asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(o + 4), "f"(a1), "f"(a2), "f"(a3), "f"(a0), "l"(pol) : "memory");
+                asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(o + 8), "f"(a2), "f"(a3), "f"(a0), "f"(a1), "l"(pol) : "memory");
             } else if (WORK == 8) {     // same stores as 3, but every tile overwrites the CTA's own 6 KiB: stays in L2, ~no DRAM writes
                 float4* o = reinterpret_cast<float4*>(out + (size_t(blockIdx.x) * ROWS + threadIdx.x) * 12);
                 o[0] = make_float4(a0, a1, a2, a3); o[1] = make_float4(a1, a2, a3, a0); o[2] = make_float4(a2, a3, a0, a1);
@@ -330,6 +339,11 @@ int main() {
     run_consume<128, 4, 2, 5, false>(enc, buf, bytes, out, 1, e0, e1);
     run_consume<128, 4, 2, 6, false>(enc, buf, bytes, out, 1, e0, e1);
     run_consume<128, 4, 2, 7, false>(enc, buf, bytes, out, 1, e0, e1);
+    run_consume<128, 4, 2, 10, false>(enc, buf, bytes, out, 1, e0, e1);
+    run_consume<128, 4, 2, 11, false>(enc, buf, bytes, out, 1, e0, e1);
+    run_consume<128, 4, 2, 12, false>(enc, buf, bytes, out, 1, e0, e1);
+    run_consume<256, 1, 4, 10, false>(enc, buf, bytes, out, 1, e0, e1);
+    run_consume<256, 1, 4, 3, false>(enc, buf, bytes, out, 1, e0, e1);
     run_consume<128, 4, 2, 8, false>(enc, buf, bytes, out, 1, e0, e1);
     run_consume<128, 4, 2, 9, false>(enc, buf, bytes, out, 1, e0, e1);
     run_consume<128, 4, 2, 3, false>(enc, buf, bytes, out, 1, e0, e1);
