@@ -333,6 +333,9 @@ def run_gpu(args):
         'frac': achieved / peak, 'traffic': traffic,
         'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured copy)' if peaks else 'fallback 6650 GB/s',
         'frac_of_nominal_8TBs': achieved / 8000.0,
+        # context: a pure-read stream tops out at 7.40 TB/s on this pool and any stream that also writes 2.3 % of its bytes
+        # (this kernel's MFCC output) at 6.9 TB/s - tools/read_peak.cu, profiles/r01_read_peak_probe*.txt
+        'frac_of_read_plus_2pct_write_probe_6900': achieved / 6900.0,
         'algorithmic_bytes_per_frame': ALGO_BYTES_MFCC_KERNEL,
         'frames_per_launch': frames_per_launch, 'launches': mfcc_launches,
         'avg_launch_ms': mfcc_ms / max(mfcc_launches, 1),
