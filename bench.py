@@ -3,8 +3,8 @@ success counts) on synthetic ACIVW-shaped data - BASELINE.json's metric on confi
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--frames B] [--impl reference]
 
-One "step" is one pass of the hot path over one batch of B resident frames (default 8288 frames = 56 per SM =
-29.3 GB of float32 spectra per GPU, far larger than the 126 MB L2, so every step streams from HBM):
+One "step" is one pass of the hot path over one batch of B resident frames (default 8192 frames =
+29 GB of float32 spectra per GPU, far larger than the 126 MB L2, so every step streams from HBM):
 stage 1+2 chained (aig_mfcc_energy: fused MFCC kernel + energy/mask kernel) and the stage-3 IoU sweep of
 the first half of the batch against the second half (11 thresholds, device-resident counters).  At N > 1
 every rank runs the same per-GPU workload on its own GPU (weak scaling; frames shard trivially) and the
@@ -369,9 +369,8 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--frames', type=int, default=8288,
-                    help='resident frames per step per GPU (default 56 frames for each of the 148 SMs: the fused kernel '
-                         'assigns whole frames to its persistent CTAs, so a multiple of the SM count leaves no tail)')
+    ap.add_argument('--frames', type=int, default=8192,
+                    help='resident frames per step per GPU')
     ap.add_argument('--e2e-frames', type=int, default=256, help='frames per end-to-end step (pinned host batch)')
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='CPU baseline time budget')

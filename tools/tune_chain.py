@@ -30,7 +30,7 @@ def main():
     out = (torch.empty((n, 36, 48, 12), device=dev, dtype=torch.float32),
            torch.empty((n, 36, 48), device=dev, dtype=torch.float64),
            torch.empty((n, 36, 48), device=dev, dtype=torch.uint8))
-    configs = [('fused v%d keep %d' % (v, k), {'chain_mode': 2, 'fused_variant': v, 'keep_mfcc_in_l2': k}) for k in (1, 0, 1, 0) for v in (2, 1)]
+    configs = [('fused v%d' % v, {'chain_mode': 2, 'fused_variant': v}) for v in (2, 1, 0)]
     configs += [('overlap v%d chunk %d ectas %d' % (v, c, e),
                  {'chain_mode': 1, 'mfcc_variant': v, 'chain_chunk_frames': c, 'chain_energy_ctas_per_sm': e})
                 for v in [int(x) for x in args.variants.split(',')] for c in [int(x) for x in args.chunks.split(',')]
