@@ -696,3 +696,21 @@ def test_render_heatmaps_driver(path):
     assert rgb.shape == (2, 224, 298, 3) and rgb.dtype == np.uint8
     heat = path.heatmap(path.energy(imgs)[0])
     assert np.array_equal(rgb[1], oracle.overlay(heat[1], frames[1], tables.jet_lut()))
+
+
+def test_generic_tables_with_flip_and_zero_thresholds(path):
+    bank2 = aig.createfilters(128, 10, 0, 3000, 8000)
+    dct2, lifter2, mfnorm2 = tables.mfcc_constants(10, 6, 22)
+    p2 = aig.AcousticPath(0, tables_=(bank2, dct2, lifter2, mfnorm2))
+    rng = np.random.default_rng(9)
+    beam = rng.standard_normal((35, 128), dtype=np.float32) ** 2          # 5 "frames" of 7 rows
+    plain = p2.mfcc_rows(beam)
+    flipped = p2.mfcc_rows(beam, flip180=True, frame_pixels=7)
+    assert np.array_equal(flipped.reshape(5, 7, 6), plain.reshape(5, 7, 6)[:, ::-1, :])
+    want = oracle.get_feats(128, beam, 6, dct2, mfnorm2, lifter2, bank2)
+    assert np.abs(plain - np.float32(want)).max() <= 1e-5
+    p2.close()
+    # a sweep with no thresholds still returns the per-frame counts
+    m = (rng.random((3, 36, 48)) > 0.5).astype(np.uint8)
+    inter, union, pos, num = path.iou_sweep(m, m[::-1].copy(), [])
+    assert pos.shape == (0,) and num == 3 and inter.tolist() == [oracle.iou_pair(a, b)[0] for a, b in zip(m, m[::-1])]
