@@ -456,6 +456,27 @@ class AcousticPath:
                                             p_arg.ptr, c_arg.ptr))
         return inter, union, pos, self._num_result(cnt)
 
+    def iou_sweep_clips(self, mask_a, mask_b, frames_per_clip, thresholds=REFERENCE_THRESHOLDS, pos=None):
+        """Per-clip success counts for a stream of fixed-length clips in one launch: returns (inter [n], union [n],
+        pos int64 [n_clips, K]); pos accumulates into a caller-supplied array / CUDA tensor when given."""
+        a, b = self._a(mask_a, np.uint8), self._a(mask_b, np.uint8)
+        n = self._frames(a.shape, FRAME_PIXELS)
+        if self._frames(b.shape, FRAME_PIXELS) != n:
+            raise ValueError('mask batches differ: %s vs %s' % (a.shape, b.shape))
+        thr = self._thresholds(thresholds)
+        n_clips = -(-n // int(frames_per_clip))
+        if pos is None:
+            pos = np.zeros((n_clips, thr.shape[0]), np.int64)
+        p_arg = _Arg(pos, np.int64, True)
+        if int(np.prod(p_arg.shape)) != n_clips * thr.shape[0]:
+            raise ValueError('pos must be int64 [%d, %d]' % (n_clips, thr.shape[0]))
+        inter = self._empty((n,), np.int64, a)
+        union = self._empty((n,), np.int64, a)
+        self._check(self._lib.aig_iou_sweep_clips(self._h, a.ptr, b.ptr, n, int(frames_per_clip), thr.ptr, thr.shape[0],
+                                                  self._a(inter, np.int64, True).ptr, self._a(union, np.int64, True).ptr,
+                                                  p_arg.ptr))
+        return inter, union, pos
+
     def ciou_sweep(self, mask, xmin, xmax, ymin, ymax, thresholds=REFERENCE_THRESHOLDS,
                    out_hw=(HEAT_H, HEAT_W), pos=None, num=None):
         """FlickrSoundNet consensus IoU and success counts (showimages_bb.py:288-321).

@@ -969,6 +969,38 @@ int aig_iou_sweep(aig_handle* h, const uint8_t* mask_a, const uint8_t* mask_b, i
     return io.finish();
 }
 
+int aig_iou_sweep_clips(aig_handle* h, const uint8_t* mask_a, const uint8_t* mask_b, int64_t n, int64_t frames_per_clip,
+                        const double* thr, int k, int64_t* inter_out, int64_t* union_out, int64_t* pos_inout) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (n < 0 || k < 1 || k > kMaxThresholds || frames_per_clip < 1 || !thr || !pos_inout)
+        return h->fail(AIG_ERR_ARGUMENT, "aig_iou_sweep_clips: bad arguments (n=%lld k=%d frames_per_clip=%lld)", (long long)n, k,
+                       (long long)frames_per_clip);
+    if (n > 0 && (!mask_a || !mask_b)) return h->fail(AIG_ERR_ARGUMENT, "aig_iou_sweep_clips: null masks");
+    if (n == 0) return AIG_OK;
+    Io io(h);
+    const size_t cnt = static_cast<size_t>(n);
+    const size_t n_clips = static_cast<size_t>((n + frames_per_clip - 1) / frames_per_clip);
+    const uint8_t* d_a = io.in(mask_a, cnt * kFramePixels);
+    const uint8_t* d_b = io.in(mask_b, cnt * kFramePixels);
+    const double* d_thr = io.in(thr, static_cast<size_t>(k));
+    int64_t* d_inter = io.out(inter_out, cnt);
+    int64_t* d_union = io.out(union_out, cnt);
+    int64_t* d_pos = io.inout(pos_inout, n_clips * k);
+    if (io.failed) return io.finish();
+    if ((reinterpret_cast<uintptr_t>(d_a) & 3u) || (reinterpret_cast<uintptr_t>(d_b) & 3u))
+        return h->fail(AIG_ERR_ARGUMENT, "aig_iou_sweep_clips: mask buffers must be 4-byte aligned");
+    const int blocks = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 8));
+    LaunchScope scope(h, h->stream, kKindOther);
+    iou_sweep_clips_kernel<<<blocks, kIouThreads, 0, h->stream>>>(d_a, d_b, n, frames_per_clip, d_thr, k,
+                                                                  reinterpret_cast<long long*>(d_inter),
+                                                                  reinterpret_cast<long long*>(d_union),
+                                                                  reinterpret_cast<unsigned long long*>(d_pos));
+    rc = scope.done("iou_sweep_clips_kernel");
+    if (rc != AIG_OK) return rc;
+    return io.finish();
+}
+
 int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, const int32_t* xmax, const int32_t* ymin,
                    const int32_t* ymax, int64_t n, int out_h, int out_w, const double* thr, int k, int64_t* inter2_out,
                    int64_t* union2_out, int64_t* pos_inout, int64_t* num_inout) {

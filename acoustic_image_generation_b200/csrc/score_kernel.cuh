@@ -55,6 +55,40 @@ iou_sweep_kernel(const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__
         if (s_pos[k] != 0) atomicAdd(pos + k, static_cast<unsigned long long>(s_pos[k]));
 }
 
+// Per-clip variant for video streams (BASELINE configs[3]: 10 s clips of 120 or 300 frames): frame f belongs to clip
+// f / frames_per_clip and the success counts are kept per clip, pos[clip][k], so that every clip's success curve and AUC
+// come out of ONE launch instead of one sweep per clip.  One warp per frame pair; the (clip, k) counters are global
+// 64-bit atomics (at most n * K increments spread over n_clips * K addresses).
+__global__ void __launch_bounds__(kIouThreads)
+iou_sweep_clips_kernel(const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__ mask_b, long long n,
+                       long long frames_per_clip, const double* __restrict__ thr, int k_thr,
+                       long long* __restrict__ inter_out, long long* __restrict__ union_out,
+                       unsigned long long* __restrict__ pos /* [n_clips, k_thr] */) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long warps_total = static_cast<long long>(gridDim.x) * (kIouThreads / 32);
+    for (long long f = static_cast<long long>(blockIdx.x) * (kIouThreads / 32) + warp; f < n; f += warps_total) {
+        const uint32_t* a = reinterpret_cast<const uint32_t*>(mask_a + f * kFramePixels);
+        const uint32_t* b = reinterpret_cast<const uint32_t*>(mask_b + f * kFramePixels);
+        int inter = 0, uni = 0;
+        for (int w = lane; w < kMaskWords; w += 32) {
+            const uint32_t ma = __vcmpne4(__ldg(a + w), 0u);
+            const uint32_t mb = __vcmpne4(__ldg(b + w), 0u);
+            inter += __popc(ma & mb);
+            uni += __popc(ma | mb);
+        }
+        inter = warp_sum(inter) >> 3;
+        uni = warp_sum(uni) >> 3;
+        if (lane == 0) {
+            if (inter_out != nullptr) inter_out[f] = inter;
+            if (union_out != nullptr) union_out[f] = uni;
+        }
+        const double iou = __ddiv_rn(static_cast<double>(inter), static_cast<double>(uni));
+        unsigned long long* clip_pos = pos + (f / frames_per_clip) * k_thr;
+        for (int k = lane; k < k_thr; k += 32)
+            if (iou > __ldg(thr + k)) atomicAdd(clip_pos + k, 1ull);
+    }
+}
+
 // Dynamic shared memory: (out_w + out_h) * 2 ints of bilinear taps.
 __global__ void __launch_bounds__(kIouThreads)
 ciou_sweep_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ xmin, const int* __restrict__ xmax,

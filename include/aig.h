@@ -173,6 +173,13 @@ int aig_iou_sweep(aig_handle* h, const uint8_t* mask_a, const uint8_t* mask_b, i
                   const double* thr, int k, int64_t* inter_out, int64_t* union_out,
                   int64_t* pos_inout, int64_t* num_inout);
 
+/* The same for a stream of fixed-length clips (BASELINE configs[3]: 10 s clips, 120 frames at the reference's 12 fps,
+ * showvideo.py:139, or 300 at 30 fps): frame f belongs to clip f / frames_per_clip; pos_inout is [n_clips, k] row-major
+ * (n_clips = ceil(n / frames_per_clip)) and accumulates per clip, so every clip's success curve and AUC come out of one
+ * launch.  The per-clip frame count is frames_per_clip (the last clip may be shorter). */
+int aig_iou_sweep_clips(aig_handle* h, const uint8_t* mask_a, const uint8_t* mask_b, int64_t n, int64_t frames_per_clip,
+                        const double* thr, int k, int64_t* inter_out, int64_t* union_out, int64_t* pos_inout);
+
 /* FlickrSoundNet consensus IoU and success counts (showimages_bb.py:288-321).
  *   mask  [n, 36*48] uint8 predicted mask at acoustic resolution (up-sampled here exactly as
  *         aig_resize_mask does)

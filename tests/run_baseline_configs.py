@@ -128,12 +128,10 @@ def main():
         def clip_stream():
             _, _, ma = path.mfcc_energy(a, flip=True, normalize_first=True)
             _, _, mb = path.mfcc_energy(b, flip=True, normalize_first=True)
-            per_clip = []
-            for c in range(clips):
-                _, _, pos, num = path.iou_sweep(ma[c * fpc:(c + 1) * fpc], mb[c * fpc:(c + 1) * fpc], THR11)
-                per_clip.append(aig.auc(THR11, aig.success_rates(pos, num)))
-            _, _, pos, num = path.iou_sweep(ma, mb, THR11)
-            return per_clip, aig.auc(THR11, aig.success_rates(pos, num))
+            _, _, clip_pos = path.iou_sweep_clips(ma, mb, fpc, THR11)              # every clip's counts in one launch
+            clip_pos = clip_pos if isinstance(clip_pos, np.ndarray) else clip_pos.cpu().numpy()
+            per_clip = [aig.auc(THR11, aig.success_rates(p, fpc)) for p in clip_pos]
+            return per_clip, aig.auc(THR11, aig.success_rates(clip_pos.sum(axis=0), nf))
         ms, (per_clip, glob) = timed(stream, clip_stream)
         print(json.dumps({'config': 'C4: %d clips x %d frames (two streams), MFCC + energy + per-clip and global AUC' % (clips, fpc),
                           'frames_per_s': 2 * nf / ms * 1e3, 'ms': ms, 'global_auc': glob,

@@ -85,6 +85,18 @@ def test_config3_clip_stream_sharded_by_clip(path, frames_per_clip, n_clips):
         _, _, cpos, cnum = path.iou_sweep(mask_a[lo:hi], mask_b[lo:hi], REF_THR)
         assert cnum == frames_per_clip
         assert np.array_equal(cpos, counts_from_ratios(inter[lo:hi], union[lo:hi], REF_THR))
+    # ... and all clips at once from the per-clip kernel (one launch)
+    _, _, clip_pos = path.iou_sweep_clips(mask_a, mask_b, frames_per_clip, REF_THR)
+    assert clip_pos.shape == (n_clips, len(REF_THR)) and np.array_equal(clip_pos.sum(axis=0), pos)
+    for c in range(n_clips):
+        lo, hi = c * frames_per_clip, (c + 1) * frames_per_clip
+        assert np.array_equal(clip_pos[c], counts_from_ratios(inter[lo:hi], union[lo:hi], REF_THR))
+    clip_auc = [aig.auc(REF_THR, aig.success_rates(p, frames_per_clip)) for p in clip_pos]
+    assert min(clip_auc) <= global_auc <= max(clip_auc)
+    # a ragged last clip
+    _, _, ragged = path.iou_sweep_clips(mask_a[:frames_per_clip + 7], mask_b[:frames_per_clip + 7], frames_per_clip, REF_THR)
+    assert ragged.shape == (2, len(REF_THR)) and np.array_equal(ragged[0], clip_pos[0])
+    assert np.array_equal(ragged[1], counts_from_ratios(inter[frames_per_clip:frames_per_clip + 7], union[frames_per_clip:frames_per_clip + 7], REF_THR))
     # clip-major shards merge to the global result
     for world in (2, 4, 8):
         shards = []
