@@ -96,7 +96,7 @@ __device__ __forceinline__ double frame_mean(const double* s_map, double (*s_par
     return *s_mean;
 }
 
-__global__ void __launch_bounds__(kEnergyThreads)
+__global__ void __launch_bounds__(kEnergyThreads, 3)
 energy_kernel(const float* __restrict__ images, long long n_frames, int normalize_first,
               float* __restrict__ scaled_out, double* __restrict__ energy_out,
               uint8_t* __restrict__ mask_out, double* __restrict__ mean_out) {
