@@ -406,11 +406,20 @@ int launch_heatmap(aig_handle* h, const double* d_energy, int64_t n_frames, int 
     LaunchScope scope(h, h->stream, kKindOther);
     if (!h->heatmap_exact && fast_smem <= 200 * 1024) {
         if (!h->heat_attr_set) {
-            AIG_CK(cudaFuncSetAttribute(heatmap_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            AIG_CK(cudaFuncSetAttribute(heatmap_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            AIG_CK(cudaFuncSetAttribute(heatmap_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            AIG_CK(cudaFuncSetAttribute(heatmap_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             h->heat_attr_set = true;
         }
         const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (fast_smem + 12 * 1024))));
-        heatmap_fast_kernel<<<frames_grid(h, n_frames, per_sm), kHeatThreads, fast_smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);
+        const int grid = frames_grid(h, n_frames, per_sm);
+        const bool aligned = (reinterpret_cast<uintptr_t>(d_heat) & 15u) == 0;
+        if (aligned && out_w % 4 == 0)
+            heatmap_fast_kernel<4><<<grid, kHeatThreads, fast_smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);
+        else if (aligned && out_w % 2 == 0)
+            heatmap_fast_kernel<2><<<grid, kHeatThreads, fast_smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);
+        else
+            heatmap_fast_kernel<1><<<grid, kHeatThreads, fast_smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);
     } else {
         const size_t smem = static_cast<size_t>(out_w + out_h) * (sizeof(double) + sizeof(int));
         heatmap_kernel<<<frames_grid(h, n_frames, 4), kHeatThreads, smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);

@@ -291,10 +291,54 @@ heatmap_kernel(const double* __restrict__ energy, long long n_frames, int out_h,
 // once into shared memory (36 x out_w), so an output pixel costs two shared loads and three FMAs per pass and the
 // kernel approaches the HBM write rate (out_h * out_w * 4 B per frame).
 // Dynamic shared memory: 36 * out_w floats (rows) + out_w * (int + float) + out_h * (int + float).
+// VEC = pixels per thread per step (4 when out_w % 4 == 0, 2 when even, else 1): the kernel is issue-bound, so the
+// vertical passes use 8/16-byte shared loads and global stores.
+template <int VEC>
+struct HeatVec;
+template <>
+struct HeatVec<1> {
+    using T = float;
+    static __device__ __forceinline__ void lerp_minmax(const float* r0, const float* r1, int x, float wy, float& mn, float& mx) {
+        const float v = fmaf(r1[x] - r0[x], wy, r0[x]);
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    static __device__ __forceinline__ void lerp_store(const float* r0, const float* r1, int x, float wy, float mn, float inv, float* o) {
+        __stcs(o + x, (fmaf(r1[x] - r0[x], wy, r0[x]) - mn) * inv);
+    }
+};
+template <>
+struct HeatVec<2> {
+    static __device__ __forceinline__ void lerp_minmax(const float* r0, const float* r1, int x, float wy, float& mn, float& mx) {
+        const float2 a = *reinterpret_cast<const float2*>(r0 + x), b = *reinterpret_cast<const float2*>(r1 + x);
+        const float v0 = fmaf(b.x - a.x, wy, a.x), v1 = fmaf(b.y - a.y, wy, a.y);
+        mn = fminf(mn, fminf(v0, v1)); mx = fmaxf(mx, fmaxf(v0, v1));
+    }
+    static __device__ __forceinline__ void lerp_store(const float* r0, const float* r1, int x, float wy, float mn, float inv, float* o) {
+        const float2 a = *reinterpret_cast<const float2*>(r0 + x), b = *reinterpret_cast<const float2*>(r1 + x);
+        __stcs(reinterpret_cast<float2*>(o + x), make_float2((fmaf(b.x - a.x, wy, a.x) - mn) * inv, (fmaf(b.y - a.y, wy, a.y) - mn) * inv));
+    }
+};
+template <>
+struct HeatVec<4> {
+    static __device__ __forceinline__ void lerp_minmax(const float* r0, const float* r1, int x, float wy, float& mn, float& mx) {
+        const float4 a = *reinterpret_cast<const float4*>(r0 + x), b = *reinterpret_cast<const float4*>(r1 + x);
+        const float v0 = fmaf(b.x - a.x, wy, a.x), v1 = fmaf(b.y - a.y, wy, a.y);
+        const float v2 = fmaf(b.z - a.z, wy, a.z), v3 = fmaf(b.w - a.w, wy, a.w);
+        mn = fminf(fminf(mn, fminf(v0, v1)), fminf(v2, v3)); mx = fmaxf(fmaxf(mx, fmaxf(v0, v1)), fmaxf(v2, v3));
+    }
+    static __device__ __forceinline__ void lerp_store(const float* r0, const float* r1, int x, float wy, float mn, float inv, float* o) {
+        const float4 a = *reinterpret_cast<const float4*>(r0 + x), b = *reinterpret_cast<const float4*>(r1 + x);
+        __stcs(reinterpret_cast<float4*>(o + x),
+               make_float4((fmaf(b.x - a.x, wy, a.x) - mn) * inv, (fmaf(b.y - a.y, wy, a.y) - mn) * inv,
+                           (fmaf(b.z - a.z, wy, a.z) - mn) * inv, (fmaf(b.w - a.w, wy, a.w) - mn) * inv));
+    }
+};
+
+template <int VEC>
 __global__ void __launch_bounds__(kHeatThreads)
 heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int out_h, int out_w,
                     float* __restrict__ heat) {
-    extern __shared__ float s_fast[];
+    extern __shared__ __align__(16) float s_fast[];
     __shared__ float s_t[kFramePixels];
     __shared__ double s_red64[2][kHeatThreads / 32];
     __shared__ float s_red32[2][kHeatThreads / 32];
@@ -338,13 +382,15 @@ heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int o
             if (p < kFramePixels) s_t[p] = span > 0.0 ? static_cast<float>((e[i] - lo) / span) : 0.f;
         }
         __syncthreads();
-        // horizontal pass, once
-        for (int i = tid; i < kFrameH * out_w; i += kHeatThreads) {
-            const int r = i / out_w, x = i - r * out_w;
-            const int xi = s_x0[x];
-            const float wx = s_wx[x];
-            const float a = s_t[r * kFrameW + (xi & 0xffff)], b = s_t[r * kFrameW + (xi >> 16)];
-            s_rows[i] = fmaf(b - a, wx, a);
+        // horizontal pass, once: warps own source rows, lanes walk the output columns
+        for (int r = warp; r < kFrameH; r += kHeatThreads / 32) {
+            const float* t = s_t + r * kFrameW;
+            float* row = s_rows + r * out_w;
+            for (int x = lane; x < out_w; x += 32) {
+                const int xi = s_x0[x];
+                const float a = t[xi & 0xffff], b = t[xi >> 16];
+                row[x] = fmaf(b - a, s_wx[x], a);
+            }
         }
         __syncthreads();
         // pass 1: min / max of the up-sampled image
@@ -354,10 +400,7 @@ heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int o
             const float wy = s_wy[y];
             const float* r0 = s_rows + (yi & 0xffff) * out_w;
             const float* r1 = s_rows + (yi >> 16) * out_w;
-            for (int x = lane; x < out_w; x += 32) {
-                const float v = fmaf(r1[x] - r0[x], wy, r0[x]);
-                mn = fminf(mn, v); mx = fmaxf(mx, v);
-            }
+            for (int x = lane * VEC; x < out_w; x += 32 * VEC) HeatVec<VEC>::lerp_minmax(r0, r1, x, wy, mn, mx);
         }
         mn = warp_min(mn); mx = warp_max(mx);
         if (lane == 0) { s_red32[0][warp] = mn; s_red32[1][warp] = mx; }
@@ -368,17 +411,14 @@ heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int o
         // a constant frame gives 0/0 = NaN, like the reference's (x - min) / (max - min)
         const float inv = (span > 0.0 && mx > mn) ? 1.f / (mx - mn) : CUDART_NAN_F;
         float* dst = heat + frame * static_cast<long long>(out_h) * out_w;
-        // pass 2: normalise and stream out (coalesced 128 B per warp store)
+        // pass 2: normalise and stream out
         for (int y = warp; y < out_h; y += kHeatThreads / 32) {
             const int yi = s_y0[y];
             const float wy = s_wy[y];
             const float* r0 = s_rows + (yi & 0xffff) * out_w;
             const float* r1 = s_rows + (yi >> 16) * out_w;
             float* o = dst + static_cast<long long>(y) * out_w;
-            for (int x = lane; x < out_w; x += 32) {
-                const float v = fmaf(r1[x] - r0[x], wy, r0[x]);
-                __stcs(o + x, (v - mn) * inv);
-            }
+            for (int x = lane * VEC; x < out_w; x += 32 * VEC) HeatVec<VEC>::lerp_store(r0, r1, x, wy, mn, inv, o);
         }
     }
 }

@@ -70,7 +70,7 @@ def main():
     m = min(n, 2048)
     for shape in ((224, 298), (224, 224)):
         ms = timed(lambda: path.heatmap(energy[:m], *shape))
-        report('heat map %dx%d (aig_heatmap)' % shape, m, 'frames', ms, m * (13824 + shape[0] * shape[1] * 4), 'FP64 bilinear x2 passes')
+        report('heat map %dx%d (aig_heatmap)' % shape, m, 'frames', ms, m * (13824 + shape[0] * shape[1] * 4), 'float32 fast path, write-bound')
         ms = timed(lambda: path.resize_mask(mask[:m], *shape))
         report('mask resize %dx%d' % shape, m, 'frames', ms, m * (1728 + shape[0] * shape[1]))
     heat = path.heatmap(energy[:m])
