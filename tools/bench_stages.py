@@ -85,6 +85,15 @@ def main():
     boxes = [torch.from_numpy(v).to(dev) for v in synth.flickr_boxes(m, 3)]
     ms = timed(lambda: path.ciou_sweep(mask[:m], *boxes, thr, pos=counts[:-1], num=counts[-1:]))
     report('consensus IoU sweep 224x298, 101 thr', m, 'frames', ms, m * (1728 + 48), 'integer compute: 66 752 px/frame')
+    from acoustic_image_generation_b200 import tables
+    bank2 = aig.createfilters(256, 20, 300, 4000, 8000)
+    dct2, lifter2, mfnorm2 = tables.mfcc_constants(20, 10, 22)
+    p2 = aig.AcousticPath(0, stream=stream.cuda_stream, tables_=(bank2, dct2, lifter2, mfnorm2))
+    rows2 = torch.randn((1 << 20, 256), device=dev, dtype=torch.float32).square_()
+    ms = timed(lambda: p2.mfcc_rows(rows2))
+    report('generic-table MFCC (256 bins, float64)', rows2.shape[0], 'rows', ms, rows2.shape[0] * (1024 + 40), 'fallback kernel, not tuned')
+    p2.close()
+    del rows2
     vec = torch.randn((n, 12), device=dev, dtype=torch.float32)
     ms = timed(lambda: path.tile_mfcc(vec, normalize=True))
     report('tile MFCC -> [36,48,12] (aig_tile_mfcc)', n, 'frames', ms, n * 82944, 'write-only')
