@@ -12,8 +12,8 @@ arithmetic on a B200 through libaig.so (include/aig.h):
                                              showimages_bb.py:287-328, areaundercurve.py:26-40
 
 Arrays may be NumPy arrays (host; results come back as NumPy) or CUDA tensors / anything
-exposing ``__cuda_array_interface__`` (device; results are torch CUDA tensors, nothing is
-copied to the host).  There is no CPU fallback: without libaig.so and a B200 every compute
+exposing ``__cuda_array_interface__`` or ``__dlpack__`` (device; results are torch CUDA tensors,
+nothing is copied to the host).  There is no CPU fallback: without libaig.so and a B200 every compute
 call raises.
 """
 from __future__ import annotations
@@ -58,6 +58,9 @@ class _Arg:
     def __init__(self, x, dtype, writable=False):
         dtype = np.dtype(dtype)
         self.torch_device = None
+        if not _is_torch(x) and not hasattr(x, '__cuda_array_interface__') and not isinstance(x, np.ndarray) \
+                and hasattr(x, '__dlpack__'):
+            x = _torch().from_dlpack(x)          # DLPack producers (CuPy, JAX, TF ...): zero-copy view as a torch tensor
         if _is_torch(x):
             torch = _torch()
             want = _TORCH_DTYPES[dtype]

@@ -714,3 +714,26 @@ def test_generic_tables_with_flip_and_zero_thresholds(path):
     m = (rng.random((3, 36, 48)) > 0.5).astype(np.uint8)
     inter, union, pos, num = path.iou_sweep(m, m[::-1].copy(), [])
     assert pos.shape == (0,) and num == 3 and inter.tolist() == [oracle.iou_pair(a, b)[0] for a, b in zip(m, m[::-1])]
+
+
+def test_dlpack_and_cuda_array_interface_inputs(path, torch):
+    class DlpackOnly:                      # what a CuPy / JAX / TF array looks like to us
+        def __init__(self, t):
+            self._t = t
+
+        def __dlpack__(self, *args, **kwargs):
+            return self._t.__dlpack__(*args, **kwargs)
+
+        def __dlpack_device__(self):
+            return self._t.__dlpack_device__()
+
+    class CaiOnly:
+        def __init__(self, t):
+            self._t = t
+            self.__cuda_array_interface__ = t.__cuda_array_interface__
+
+    imgs = torch.from_numpy(synth.sigmoid_images(2, 12)).cuda()
+    ref_e, ref_m = path.energy(imgs)
+    for wrapper in (DlpackOnly, CaiOnly):
+        e, m = path.energy(wrapper(imgs))
+        assert e.is_cuda and torch.equal(e, ref_e) and torch.equal(m, ref_m)
