@@ -737,3 +737,31 @@ def test_dlpack_and_cuda_array_interface_inputs(path, torch):
     for wrapper in (DlpackOnly, CaiOnly):
         e, m = path.energy(wrapper(imgs))
         assert e.is_cuda and torch.equal(e, ref_e) and torch.equal(m, ref_m)
+
+
+def test_tfrecord_to_metric_files_example(tmp_path):
+    """examples/evaluate_tfrecords.py: TFRecords -> reader -> normalise -> energy masks -> IoU sweep -> metric files,
+    checked against the oracle chain on the same records."""
+    import importlib.util
+    import os
+    from acoustic_image_generation_b200 import metrics_io, tfrecord
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('evaluate_tfrecords', os.path.join(root, 'examples', 'evaluate_tfrecords.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    res, out_dir = mod.main(str(tmp_path))
+    assert res['num'] == 72
+    rng = np.random.default_rng(0)
+    scores = []
+    for r in range(6):
+        with tfrecord.RecordFile(os.path.join(out_dir, 'Data_%03d.tfrecord' % (r + 1))) as rec:
+            imgs = tfrecord.parse_acoustic_example(rec, 0)['audio_images']
+        assert np.array_equal(imgs, oracle.flip180(synth.smooth_images(12, 100 + r)))
+        data = oracle.normalize_acoustic_images(imgs)
+        recon = np.clip(data * np.float32(0.8) + np.float32(0.2) * rng.random(data.shape, dtype=np.float32), 0, 1)
+        ea, _ = oracle.energy_stage(data, normalize_first=False)
+        eb, _ = oracle.energy_stage(recon, normalize_first=False)
+        scores += [oracle.iou_pair(oracle.mean_mask(x), oracle.mean_mask(y))[2] for x, y in zip(ea, eb)]
+    pos, num = oracle.success_counts(scores, REF_THR)
+    assert np.array_equal(res['pos'], pos) and num == 72
+    assert metrics_io.read_accuracy_file(out_dir, 0.5) == float('{:6f}'.format(pos[5] / 72))
