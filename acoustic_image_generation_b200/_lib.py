@@ -113,6 +113,7 @@ SIGNATURES = {
     'aig_launch_count': (_i64, [_p]),
     'aig_set_option': (_int, [_p, ctypes.c_char_p, _i64]),
     'aig_profile_read': (_int, [_p, _p, _p]),
+    'aig_selftest': (_int, [_p, _int, _p]),
 }
 
 _lib = None

@@ -136,6 +136,12 @@ class AcousticPath:
     def set_mfcc_variant(self, variant):
         self.set_option('mfcc_variant', variant)
 
+    def selftest(self, which):
+        """Device self-tests of the energy stage's exact-division and table-exp shortcuts (see aig_selftest)."""
+        out = (ctypes.c_uint64 * 4)()
+        self._check(self._lib.aig_selftest(self._h, int(which), out))
+        return [int(v) for v in out]
+
     def profile_read(self):
         """{'mfcc': (ms, launches), 'energy': (...), 'other': (...)} gathered since the last read (needs profile=1)."""
         ms = (ctypes.c_double * 3)()

@@ -659,6 +659,25 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
     return AIG_OK;
 }
 
+int aig_selftest(aig_handle* h, int which, uint64_t* out) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (out == nullptr || which < 0 || which > 1) return h->fail(AIG_ERR_ARGUMENT, "aig_selftest: bad arguments");
+    unsigned long long* d_out = static_cast<unsigned long long*>(scratch(h, 4 * sizeof(unsigned long long)));
+    if (!d_out) return AIG_ERR_ALLOC;
+    AIG_CK(cudaMemsetAsync(d_out, 0, 4 * sizeof(unsigned long long), h->stream));
+    LaunchScope scope(h, h->stream, kKindOther);
+    if (which == 0)
+        selftest_division_kernel<<<h->sm_count * 16, 256, 0, h->stream>>>(d_out);
+    else
+        selftest_exp_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(1ull << 26, d_out);
+    rc = scope.done("selftest kernel");
+    if (rc != AIG_OK) return rc;
+    AIG_CK(cudaMemcpyAsync(out, d_out, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    AIG_CK(cudaStreamSynchronize(h->stream));
+    return AIG_OK;
+}
+
 int aig_profile_read(aig_handle* h, double* ms_out, int64_t* launches_out) {
     if (h == nullptr || ms_out == nullptr || launches_out == nullptr) return AIG_ERR_ARGUMENT;
     int rc = aig_synchronize(h);

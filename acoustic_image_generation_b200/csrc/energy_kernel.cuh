@@ -33,33 +33,134 @@ static_assert(kFramePixels % kEnergyThreads == 0, "pixels must divide evenly ove
 __device__ __forceinline__ int leaf_start(int leaf) { return 216 * (leaf >> 1) + ((leaf & 1) ? 104 : 0); }
 __device__ __forceinline__ int leaf_len(int leaf) { return (leaf & 1) ? 112 : 104; }
 
+__constant__ double c_inv_lifter[kMfccNum] = AIG_REF_INV_LIFTER;     // RN(1 / lifter[m])
+__constant__ double c_exp2_table[64] = AIG_EXP2_TABLE;               // RN(2^(j/64)); kernels copy it to shared memory
+
+// v / L for a constant L with r = RN(1 / L): q0 = RN(v * r), e = v - q0 * L (exact in one FMA), q = RN(q0 + e * r).
+// By Markstein's theorem q is the correctly rounded quotient; tests/test_gpu_parity.py checks it against __ddiv_rn
+// for every float32 v and all twelve lifter constants.  Non-finite v takes the ordinary division.
+__device__ __forceinline__ double div_by_lifter(double v, int m) {
+    if (!(fabs(v) <= 3.402823466e38)) return __ddiv_rn(v, c_lifter[m]);
+    const double r = c_inv_lifter[m];
+    const double q0 = __dmul_rn(v, r);
+    const double e = __fma_rn(-q0, c_lifter[m], v);
+    return __fma_rn(e, r, q0);
+}
+
+// exp(x) for |x| <= 700 by table: k = rint(x * 64 / ln2), r = x - k * ln2 / 64 (two-part constant), exp(x) =
+// 2^(k >> 6) * T[k & 63] * (1 + p(r)) with a degree-6 polynomial on |r| <= ln2 / 128 (truncation 3e-20).  Worst-case
+// error just under 1 ulp (table entry + final rounding), the same class as CUDA's and NumPy's exp; 11 FP64 operations
+// instead of ~17 plus the special-case branches.  Anything else (huge, NaN, Inf) goes to exp().
+__device__ __forceinline__ double exp_table64(double x, const double* __restrict__ table) {
+    if (!(fabs(x) <= 700.0)) return exp(x);
+    const double magic = 6755399441055744.0;                          // 1.5 * 2^52: rint by addition
+    const double t = __fma_rn(x, AIG_EXP_64_OVER_LN2, magic);
+    const int k = __double2loint(t);
+    const double kd = __dadd_rn(t, -magic);
+    double r = __fma_rn(kd, -AIG_EXP_LN2_64_HEAD, x);
+    r = __fma_rn(kd, -AIG_EXP_LN2_64_TAIL, r);
+    double p = __fma_rn(r, 1.0 / 720.0, 1.0 / 120.0);
+    p = __fma_rn(p, r, 1.0 / 24.0);
+    p = __fma_rn(p, r, 1.0 / 6.0);
+    p = __fma_rn(p, r, 0.5);
+    p = __fma_rn(__dmul_rn(r, r), p, r);                              // e^r - 1
+    const double tj = table[k & 63];
+    const double y = __fma_rn(tj, p, tj);
+    return __hiloint2double(__double2hiint(y) + ((k >> 6) << 20), __double2loint(y));   // * 2^(k >> 6)
+}
+
 // One pixel of find_logen: optional float32 min-max normalisation (:672-679), the float64-compute /
 // float32-store scaling `mfcc /= lifter; mfcc *= mfnorm` (:310-311), the float64 projection on dct_base^T,
 // exp, the band sum in NumPy's order for n = 24 (r[k] = e[k] + e[k+8] + e[k+16], then the balanced tree
 // over r[0..7]) and the reciprocal (:313-321).  x[] is left holding the scaled float32 values.
-__device__ __forceinline__ double pixel_energy(float (&x)[kMfccNum], bool normalize, float lo, float range) {
+//
+// FP64 work is what this stage costs (and, on a board that sits at its power cap, what it costs the HBM stream next to
+// it), so the projection uses the symmetry of the basis: cos((m+1) pi (23-j+0.5) / 24) = (-1)^(m+1) cos((m+1) pi (j+0.5) / 24),
+// i.e. mel[j] = A_j + B_j and mel[23-j] = A_j - B_j with A over odd m and B over even m - 144 FMAs instead of 288.
+// The result differs from a straight 12-term dot product only in the last ulp, like one BLAS differs from another.
+__device__ __forceinline__ double pixel_energy(float (&x)[kMfccNum], bool normalize, float lo, float range,
+                                               const double* __restrict__ exp_table) {
     double z[kMfccNum];
 #pragma unroll
     for (int m = 0; m < kMfccNum; ++m) {
         float v = x[m];
         if (normalize) v = __fdiv_rn(__fsub_rn(v, lo), range);                // float32, as TF
-        v = __double2float_rn(__ddiv_rn(static_cast<double>(v), c_lifter[m]));
+        v = __double2float_rn(div_by_lifter(static_cast<double>(v), m));
         v = __double2float_rn(__dmul_rn(static_cast<double>(v), c_mfnorm));
         x[m] = v;
         z[m] = static_cast<double>(v);
     }
-    double r[8];
+    double r[8], third[8];
 #pragma unroll
-    for (int j = 0; j < kFilterNum; ++j) {
-        double mel = 0.0;
+    for (int j = 0; j < 12; ++j) {
+        double a = 0.0, b = 0.0;
 #pragma unroll
-        for (int m = 0; m < kMfccNum; ++m) mel = fma(z[m], c_dct[j * kMfccNum + m], mel);
-        const double e = exp(mel);
-        r[j & 7] = (j < 8) ? e : __dadd_rn(r[j & 7], e);
+        for (int m = 0; m < kMfccNum; m += 2) {
+            b = fma(z[m], c_dct[j * kMfccNum + m], b);                        // m + 1 odd: antisymmetric in j <-> 23 - j
+            a = fma(z[m + 1], c_dct[j * kMfccNum + m + 1], a);                // m + 1 even: symmetric
+        }
+        const double e_lo = exp_table64(__dadd_rn(a, b), exp_table);         // band j
+        const double e_hi = exp_table64(__dadd_rn(a, -b), exp_table);        // band 23 - j
+        if (j < 8) {
+            r[j] = e_lo;                      // first term of r[j]
+            third[7 - j] = e_hi;              // band 23 - j = 16 + (7 - j): third term of r[7 - j]
+        } else {
+            r[j - 8] = __dadd_rn(r[j - 8], e_lo);          // band j = 8 + (j - 8): second term of r[j - 8]
+            r[15 - j] = __dadd_rn(r[15 - j], e_hi);        // band 23 - j = 8 + (15 - j): second term of r[15 - j]
+        }
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], third[k]);
     const double total = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
                                    __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
     return __ddiv_rn(1.0, total);
+}
+
+// ---- self-tests of the two arithmetic shortcuts above (aig_selftest) -----------------------------------------------
+// out[0]: float32 bit patterns v (all 2^32) x 12 lifters where div_by_lifter(v) != __ddiv_rn(v, lifter) as values
+//         (NaN == NaN, -0 == +0); out[1]: of those, how many differ after the float32 store the reference applies.
+__global__ void selftest_division_kernel(unsigned long long* out) {
+    unsigned long long bad = 0, bad_after_store = 0;
+    const unsigned long long total = 1ull << 32;
+    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+        const double v = static_cast<double>(__uint_as_float(static_cast<unsigned int>(i)));
+#pragma unroll
+        for (int m = 0; m < kMfccNum; ++m) {
+            const double fast = div_by_lifter(v, m), exact = __ddiv_rn(v, c_lifter[m]);
+            const bool same = (fast == exact) || (fast != fast && exact != exact);
+            if (!same) {
+                ++bad;
+                const float a = __double2float_rn(fast), b = __double2float_rn(exact);
+                if (!((a == b) || (a != a && b != b))) ++bad_after_store;
+            }
+        }
+    }
+    if (bad) atomicAdd(out, bad);
+    if (bad_after_store) atomicAdd(out + 1, bad_after_store);
+}
+
+// exp_table64 against CUDA's exp() (itself <= 1 ulp) on n points spread over [-700, 700] plus a dense sweep of
+// [-12, 12], the range find_logen's inputs produce: out[0] = points differing, out[1] = max difference in ulps,
+// out[2] = points compared.
+__global__ void selftest_exp_kernel(unsigned long long n, unsigned long long* out) {
+    __shared__ double s_exp[64];
+    if (threadIdx.x < 64) s_exp[threadIdx.x] = c_exp2_table[threadIdx.x];
+    __syncthreads();
+    unsigned long long differ = 0, max_ulps = 0, count = 0;
+    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < 2 * n;
+         i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+        const double u = static_cast<double>(i % n) / static_cast<double>(n);           // [0, 1)
+        const double x = (i < n) ? (u * 1400.0 - 700.0) : (u * 24.0 - 12.0);
+        const long long a = __double_as_longlong(exp_table64(x, s_exp)), b = __double_as_longlong(exp(x));
+        const unsigned long long d = static_cast<unsigned long long>(a > b ? a - b : b - a);
+        differ += d != 0;
+        max_ulps = d > max_ulps ? d : max_ulps;
+        ++count;
+    }
+    atomicAdd(out, differ);
+    atomicMax(out + 1, max_ulps);
+    atomicAdd(out + 2, count);
 }
 
 // np.mean over the 1728 doubles of s_map, bit-compatible with NumPy's pairwise summation.  Called by a
@@ -105,8 +206,11 @@ energy_kernel(const float* __restrict__ images, long long n_frames, int normaliz
     __shared__ double s_leaf[16];
     __shared__ float s_red[2][kEnergyThreads / 32];
     __shared__ double s_mean;
+    __shared__ double s_exp[64];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    if (tid < 64) s_exp[tid] = c_exp2_table[tid];
+    __syncthreads();
 
     for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
         const float* img = images + frame * kFrameValues;
@@ -140,7 +244,7 @@ energy_kernel(const float* __restrict__ images, long long n_frames, int normaliz
             const float4* src = reinterpret_cast<const float4*>(img + p * kMfccNum);
             const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
             float x[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-            const double en = pixel_energy(x, normalize_first != 0, lo, range);
+            const double en = pixel_energy(x, normalize_first != 0, lo, range, s_exp);
             if (scaled_out != nullptr) {
                 float4* dst = reinterpret_cast<float4*>(scaled_out + frame * kFrameValues + p * kMfccNum);
                 dst[0] = make_float4(x[0], x[1], x[2], x[3]);

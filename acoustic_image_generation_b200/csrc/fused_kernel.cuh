@@ -35,6 +35,7 @@ struct FusedShared {           // lives after the ring in dynamic shared memory
     double part[16][8];
     double leaf[16];
     double mean;
+    double exp_table[64];
     float minmax[2][kFusedConsumerWarps][2];
     unsigned long long bar[4];         // frame_full[2], frame_empty[2]
 };
@@ -80,6 +81,7 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* __rest
         }
         mbar_fence_init();
     }
+    if (threadIdx.x < 64) sh.exp_table[threadIdx.x] = c_exp2_table[threadIdx.x];
     __syncthreads();
 
     int stage = 0;
@@ -159,7 +161,7 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* __rest
             const float4* src = reinterpret_cast<const float4*>(img + p * kMfccNum);
             const float4 a = __ldcg(src), b = __ldcg(src + 1), c = __ldcg(src + 2);   // L2: written by this SM just now
             float x[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-            const double en = pixel_energy(x, normalize_first != 0, lo, range);
+            const double en = pixel_energy(x, normalize_first != 0, lo, range, sh.exp_table);
             sh.map[p] = en;
             if (energy_out != nullptr) energy_out[static_cast<size_t>(frame) * kFramePixels + p] = en;
         }

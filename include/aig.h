@@ -304,6 +304,14 @@ int64_t aig_launch_count(const aig_handle* h);
  * Unknown names or out-of-range values return AIG_ERR_ARGUMENT. */
 int aig_set_option(aig_handle* h, const char* name, int64_t value);
 
+/* Device self-tests of the energy stage's two arithmetic shortcuts (energy_kernel.cuh):
+ *   which = 0  the Markstein division by the lifter constants against IEEE division for ALL 2^32 float32 inputs:
+ *              out[0] = mismatching (input, lifter) pairs, out[1] = mismatches surviving the float32 store
+ *   which = 1  the table-driven exp against CUDA's exp() on 2 * 2^26 points of [-700, 700] and [-12, 12]:
+ *              out[0] = points differing, out[1] = largest difference in ulps, out[2] = points compared
+ * `out` is a host array of 4 uint64. */
+int aig_selftest(aig_handle* h, int which, uint64_t* out);
+
 /* Synchronise, then report and reset the event timings gathered while "profile" was on:
  * ms_out[3] / launches_out[3] = summed device time and launch count of
  * {0: MFCC kernels, 1: energy kernels, 2: every other kernel}. */

@@ -765,3 +765,15 @@ def test_tfrecord_to_metric_files_example(tmp_path):
     pos, num = oracle.success_counts(scores, REF_THR)
     assert np.array_equal(res['pos'], pos) and num == 72
     assert metrics_io.read_accuracy_file(out_dir, 0.5) == float('{:6f}'.format(pos[5] / 72))
+
+
+def test_energy_stage_arithmetic_shortcuts_selftest(path):
+    """The energy stage divides by the lifter with a reciprocal + one exact FMA correction (Markstein) and evaluates exp
+    with a 64-entry table; both are checked on the device: the division against IEEE division for every float32 input
+    and all twelve lifters, the exp against CUDA's exp() on 1.3e8 points."""
+    bad, bad_after_store, _, _ = path.selftest(0)
+    print('division: %d of %d (input, lifter) pairs differ from IEEE division; %d after the float32 store' % (bad, 12 << 32, bad_after_store))
+    assert bad == 0 and bad_after_store == 0
+    differ, max_ulps, count, _ = path.selftest(1)
+    print('exp: %d of %d points differ from CUDA exp(), max %d ulp' % (differ, count, max_ulps))
+    assert count == 2 << 26 and max_ulps <= 1
