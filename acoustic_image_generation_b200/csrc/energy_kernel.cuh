@@ -39,8 +39,10 @@ __constant__ double c_exp2_table[64] = AIG_EXP2_TABLE;               // RN(2^(j/
 // v / L for a constant L with r = RN(1 / L): q0 = RN(v * r), e = v - q0 * L (exact in one FMA), q = RN(q0 + e * r).
 // By Markstein's theorem q is the correctly rounded quotient; tests/test_gpu_parity.py checks it against __ddiv_rn
 // for every float32 v and all twelve lifter constants.  Non-finite v takes the ordinary division.
+__device__ __noinline__ double div_rare(double v, double l) { return __ddiv_rn(v, l); }   // NaN / Inf inputs only
+
 __device__ __forceinline__ double div_by_lifter(double v, int m) {
-    if (!(fabs(v) <= 3.402823466e38)) return __ddiv_rn(v, c_lifter[m]);
+    if (!(fabs(v) <= 3.402823466e38)) return div_rare(v, c_lifter[m]);
     const double r = c_inv_lifter[m];
     const double q0 = __dmul_rn(v, r);
     const double e = __fma_rn(-q0, c_lifter[m], v);
@@ -51,18 +53,25 @@ __device__ __forceinline__ double div_by_lifter(double v, int m) {
 // 2^(k >> 6) * T[k & 63] * (1 + p(r)) with a degree-6 polynomial on |r| <= ln2 / 128 (truncation 3e-20).  Worst-case
 // error just under 1 ulp (table entry + final rounding), the same class as CUDA's and NumPy's exp; 11 FP64 operations
 // instead of ~17 plus the special-case branches.  Anything else (huge, NaN, Inf) goes to exp().
+// The constants live in __constant__ memory so that each FMA takes its coefficient as a constant-bank operand (as
+// immediates every 64-bit coefficient costs two extra UMOVs per use).
+__constant__ double c_exp_k[9] = {AIG_EXP_64_OVER_LN2, 6755399441055744.0 /* 1.5 * 2^52: rint by addition */,
+                                  -(AIG_EXP_LN2_64_HEAD), -(AIG_EXP_LN2_64_TAIL),
+                                  1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+
+__device__ __noinline__ double exp_rare(double x) { return exp(x); }   // |x| > 700, NaN, Inf: one shared copy of exp()
+
 __device__ __forceinline__ double exp_table64(double x, const double* __restrict__ table) {
-    if (!(fabs(x) <= 700.0)) return exp(x);
-    const double magic = 6755399441055744.0;                          // 1.5 * 2^52: rint by addition
-    const double t = __fma_rn(x, AIG_EXP_64_OVER_LN2, magic);
+    if (!(fabs(x) <= 700.0)) return exp_rare(x);
+    const double t = __fma_rn(x, c_exp_k[0], c_exp_k[1]);
     const int k = __double2loint(t);
-    const double kd = __dadd_rn(t, -magic);
-    double r = __fma_rn(kd, -AIG_EXP_LN2_64_HEAD, x);
-    r = __fma_rn(kd, -AIG_EXP_LN2_64_TAIL, r);
-    double p = __fma_rn(r, 1.0 / 720.0, 1.0 / 120.0);
-    p = __fma_rn(p, r, 1.0 / 24.0);
-    p = __fma_rn(p, r, 1.0 / 6.0);
-    p = __fma_rn(p, r, 0.5);
+    const double kd = __dadd_rn(t, -c_exp_k[1]);
+    double r = __fma_rn(kd, c_exp_k[2], x);
+    r = __fma_rn(kd, c_exp_k[3], r);
+    double p = __fma_rn(r, c_exp_k[4], c_exp_k[5]);
+    p = __fma_rn(p, r, c_exp_k[6]);
+    p = __fma_rn(p, r, c_exp_k[7]);
+    p = __fma_rn(p, r, c_exp_k[8]);
     p = __fma_rn(__dmul_rn(r, r), p, r);                              // e^r - 1
     const double tj = table[k & 63];
     const double y = __fma_rn(tj, p, tj);
