@@ -37,34 +37,31 @@ __constant__ double c_inv_lifter[kMfccNum] = AIG_REF_INV_LIFTER;     // RN(1 / l
 __constant__ double c_exp2_table[64] = AIG_EXP2_TABLE;               // RN(2^(j/64)); kernels copy it to shared memory
 
 // v / L for a constant L with r = RN(1 / L): q0 = RN(v * r), e = v - q0 * L (exact in one FMA), q = RN(q0 + e * r).
-// By Markstein's theorem q is the correctly rounded quotient; tests/test_gpu_parity.py checks it against __ddiv_rn
-// for every float32 v and all twelve lifter constants.  Non-finite v takes the ordinary division.
-__device__ __noinline__ double div_rare(double v, double l) { return __ddiv_rn(v, l); }   // NaN / Inf inputs only
-
+// By Markstein's theorem q is the correctly rounded quotient for finite v; tests/test_gpu_parity.py checks it against
+// __ddiv_rn for every finite float32 v and all twelve lifter constants.  Non-finite inputs never reach it: pixel_energy
+// sends such pixels down the plain path.
 __device__ __forceinline__ double div_by_lifter(double v, int m) {
-    if (!(fabs(v) <= 3.402823466e38)) return div_rare(v, c_lifter[m]);
     const double r = c_inv_lifter[m];
     const double q0 = __dmul_rn(v, r);
     const double e = __fma_rn(-q0, c_lifter[m], v);
     return __fma_rn(e, r, q0);
 }
 
-// exp(x) for |x| <= 700 by table: k = rint(x * 64 / ln2), r = x - k * ln2 / 64 (two-part constant), exp(x) =
+// exp(x) by table: k = rint(x * 64 / ln2), r = x - k * ln2 / 64 (two-part constant), exp(x) =
 // 2^(k >> 6) * T[k & 63] * (1 + p(r)) with a degree-6 polynomial on |r| <= ln2 / 128 (truncation 3e-20).  Worst-case
 // error just under 1 ulp (table entry + final rounding), the same class as CUDA's and NumPy's exp; 11 FP64 operations
-// instead of ~17 plus the special-case branches.  Anything else (huge, NaN, Inf) goes to exp().
+// instead of ~17 plus the special-case branches.  Valid for |x| <= 700 (|k| < 2^16); `out_of_range` collects the
+// violation so that the caller can redo the pixel with exp() - NaN propagates by itself.
 // The constants live in __constant__ memory so that each FMA takes its coefficient as a constant-bank operand (as
 // immediates every 64-bit coefficient costs two extra UMOVs per use).
 __constant__ double c_exp_k[9] = {AIG_EXP_64_OVER_LN2, 6755399441055744.0 /* 1.5 * 2^52: rint by addition */,
                                   -(AIG_EXP_LN2_64_HEAD), -(AIG_EXP_LN2_64_TAIL),
                                   1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
 
-__device__ __noinline__ double exp_rare(double x) { return exp(x); }   // |x| > 700, NaN, Inf: one shared copy of exp()
-
-__device__ __forceinline__ double exp_table64(double x, const double* __restrict__ table) {
-    if (!(fabs(x) <= 700.0)) return exp_rare(x);
+__device__ __forceinline__ double exp_table64(double x, const double* __restrict__ table, unsigned int& out_of_range) {
     const double t = __fma_rn(x, c_exp_k[0], c_exp_k[1]);
     const int k = __double2loint(t);
+    out_of_range |= static_cast<unsigned int>(k + 65536) >> 17;       // non-zero iff |k| >= 2^16 (|x| > ~709)
     const double kd = __dadd_rn(t, -c_exp_k[1]);
     double r = __fma_rn(kd, c_exp_k[2], x);
     r = __fma_rn(kd, c_exp_k[3], r);
@@ -78,6 +75,32 @@ __device__ __forceinline__ double exp_table64(double x, const double* __restrict
     return __hiloint2double(__double2hiint(y) + ((k >> 6) << 20), __double2loint(y));   // * 2^(k >> 6)
 }
 
+// The plain form of one pixel (IEEE divisions, exp(), straight 12-term dot products), kept out of line: it serves the
+// pixels the fast path cannot (non-finite inputs, |mel| > 700) and is what the fast path is checked against.
+// `src` / `scaled_dst` are global-memory pointers (scaled_dst may be null).
+__device__ __noinline__ double pixel_energy_plain(const float* __restrict__ src, float* __restrict__ scaled_dst, bool normalize,
+                                                  float lo, float range) {
+    double z[kMfccNum];
+    for (int m = 0; m < kMfccNum; ++m) {
+        float v = src[m];
+        if (normalize) v = __fdiv_rn(__fsub_rn(v, lo), range);
+        v = __double2float_rn(__ddiv_rn(static_cast<double>(v), c_lifter[m]));
+        v = __double2float_rn(__dmul_rn(static_cast<double>(v), c_mfnorm));
+        if (scaled_dst != nullptr) scaled_dst[m] = v;
+        z[m] = static_cast<double>(v);
+    }
+    double r[8];
+    for (int j = 0; j < kFilterNum; ++j) {
+        double mel = 0.0;
+        for (int m = 0; m < kMfccNum; ++m) mel = fma(z[m], c_dct[j * kMfccNum + m], mel);
+        const double e = exp(mel);
+        r[j & 7] = (j < 8) ? e : __dadd_rn(r[j & 7], e);
+    }
+    const double total = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                                   __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    return __ddiv_rn(1.0, total);
+}
+
 // One pixel of find_logen: optional float32 min-max normalisation (:672-679), the float64-compute /
 // float32-store scaling `mfcc /= lifter; mfcc *= mfnorm` (:310-311), the float64 projection on dct_base^T,
 // exp, the band sum in NumPy's order for n = 24 (r[k] = e[k] + e[k+8] + e[k+16], then the balanced tree
@@ -87,13 +110,16 @@ __device__ __forceinline__ double exp_table64(double x, const double* __restrict
 // it), so the projection uses the symmetry of the basis: cos((m+1) pi (23-j+0.5) / 24) = (-1)^(m+1) cos((m+1) pi (j+0.5) / 24),
 // i.e. mel[j] = A_j + B_j and mel[23-j] = A_j - B_j with A over odd m and B over even m - 144 FMAs instead of 288.
 // The result differs from a straight 12-term dot product only in the last ulp, like one BLAS differs from another.
+// `rare` comes back non-zero when the pixel needs the plain path instead (the caller redoes it with pixel_energy_plain).
 __device__ __forceinline__ double pixel_energy(float (&x)[kMfccNum], bool normalize, float lo, float range,
-                                               const double* __restrict__ exp_table) {
+                                               const double* __restrict__ exp_table, unsigned int& rare) {
     double z[kMfccNum];
+    rare = 0;
 #pragma unroll
     for (int m = 0; m < kMfccNum; ++m) {
         float v = x[m];
         if (normalize) v = __fdiv_rn(__fsub_rn(v, lo), range);                // float32, as TF
+        rare |= (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u;            // NaN / Inf: plain path
         v = __double2float_rn(div_by_lifter(static_cast<double>(v), m));
         v = __double2float_rn(__dmul_rn(static_cast<double>(v), c_mfnorm));
         x[m] = v;
@@ -108,8 +134,8 @@ __device__ __forceinline__ double pixel_energy(float (&x)[kMfccNum], bool normal
             b = fma(z[m], c_dct[j * kMfccNum + m], b);                        // m + 1 odd: antisymmetric in j <-> 23 - j
             a = fma(z[m + 1], c_dct[j * kMfccNum + m + 1], a);                // m + 1 even: symmetric
         }
-        const double e_lo = exp_table64(__dadd_rn(a, b), exp_table);         // band j
-        const double e_hi = exp_table64(__dadd_rn(a, -b), exp_table);        // band 23 - j
+        const double e_lo = exp_table64(__dadd_rn(a, b), exp_table, rare);   // band j
+        const double e_hi = exp_table64(__dadd_rn(a, -b), exp_table, rare);  // band 23 - j
         if (j < 8) {
             r[j] = e_lo;                      // first term of r[j]
             third[7 - j] = e_hi;              // band 23 - j = 16 + (7 - j): third term of r[7 - j]
@@ -136,6 +162,7 @@ __global__ void selftest_division_kernel(unsigned long long* out) {
         const double v = static_cast<double>(__uint_as_float(static_cast<unsigned int>(i)));
 #pragma unroll
         for (int m = 0; m < kMfccNum; ++m) {
+            if (!(fabs(v) <= 3.402823466e38)) continue;          // non-finite inputs take the plain path
             const double fast = div_by_lifter(v, m), exact = __ddiv_rn(v, c_lifter[m]);
             const bool same = (fast == exact) || (fast != fast && exact != exact);
             if (!same) {
@@ -161,7 +188,9 @@ __global__ void selftest_exp_kernel(unsigned long long n, unsigned long long* ou
          i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
         const double u = static_cast<double>(i % n) / static_cast<double>(n);           // [0, 1)
         const double x = (i < n) ? (u * 1400.0 - 700.0) : (u * 24.0 - 12.0);
-        const long long a = __double_as_longlong(exp_table64(x, s_exp)), b = __double_as_longlong(exp(x));
+        unsigned int oob = 0;
+        const long long a = __double_as_longlong(exp_table64(x, s_exp, oob)), b = __double_as_longlong(exp(x));
+        if (oob) { differ += 1ull << 40; }                      // must never trigger on [-700, 700]
         const unsigned long long d = static_cast<unsigned long long>(a > b ? a - b : b - a);
         differ += d != 0;
         max_ulps = d > max_ulps ? d : max_ulps;
@@ -253,9 +282,13 @@ energy_kernel(const float* __restrict__ images, long long n_frames, int normaliz
             const float4* src = reinterpret_cast<const float4*>(img + p * kMfccNum);
             const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
             float x[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-            const double en = pixel_energy(x, normalize_first != 0, lo, range, s_exp);
-            if (scaled_out != nullptr) {
-                float4* dst = reinterpret_cast<float4*>(scaled_out + frame * kFrameValues + p * kMfccNum);
+            unsigned int rare;
+            double en = pixel_energy(x, normalize_first != 0, lo, range, s_exp, rare);
+            float* scaled_dst = scaled_out != nullptr ? scaled_out + frame * kFrameValues + p * kMfccNum : nullptr;
+            if (rare) {
+                en = pixel_energy_plain(img + p * kMfccNum, scaled_dst, normalize_first != 0, lo, range);
+            } else if (scaled_dst != nullptr) {
+                float4* dst = reinterpret_cast<float4*>(scaled_dst);
                 dst[0] = make_float4(x[0], x[1], x[2], x[3]);
                 dst[1] = make_float4(x[4], x[5], x[6], x[7]);
                 dst[2] = make_float4(x[8], x[9], x[10], x[11]);

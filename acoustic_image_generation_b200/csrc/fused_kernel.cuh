@@ -161,7 +161,9 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* __rest
             const float4* src = reinterpret_cast<const float4*>(img + p * kMfccNum);
             const float4 a = __ldcg(src), b = __ldcg(src + 1), c = __ldcg(src + 2);   // L2: written by this SM just now
             float x[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-            const double en = pixel_energy(x, normalize_first != 0, lo, range, sh.exp_table);
+            unsigned int rare;
+            double en = pixel_energy(x, normalize_first != 0, lo, range, sh.exp_table, rare);
+            if (rare) en = pixel_energy_plain(img + p * kMfccNum, nullptr, normalize_first != 0, lo, range);
             sh.map[p] = en;
             if (energy_out != nullptr) energy_out[static_cast<size_t>(frame) * kFramePixels + p] = en;
         }
