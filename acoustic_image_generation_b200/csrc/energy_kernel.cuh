@@ -47,6 +47,16 @@ __device__ __forceinline__ double div_by_lifter(double v, int m) {
     return __fma_rn(e, r, q0);
 }
 
+// The per-frame min-max normalisation (x - lo) / range in float32 (:672-679): one IEEE division per value, like the
+// reference.  (A shared-reciprocal form with one or two residual corrections was tried and rejected: against __fdiv_rn on
+// 2^34 pseudo-random triples it left 7e-5 of the quotients one ulp off - a 24-bit reciprocal is not enough - so unlike
+// the float64 division by the lifter constants it cannot replace the division exactly.)
+struct FrameNorm {
+    float lo, range;
+    __device__ __forceinline__ FrameNorm(float lo_, float range_) : lo(lo_), range(range_) {}
+    __device__ __forceinline__ float apply(float x) const { return __fdiv_rn(__fsub_rn(x, lo), range); }
+};
+
 // exp(x) by table: k = rint(x * 64 / ln2), r = x - k * ln2 / 64 (two-part constant), exp(x) =
 // 2^(k >> 6) * T[k & 63] * (1 + p(r)) with a degree-6 polynomial on |r| <= ln2 / 128 (truncation 3e-20).  Worst-case
 // error just under 1 ulp (table entry + final rounding), the same class as CUDA's and NumPy's exp; 11 FP64 operations
@@ -111,14 +121,14 @@ __device__ __noinline__ double pixel_energy_plain(const float* __restrict__ src,
 // i.e. mel[j] = A_j + B_j and mel[23-j] = A_j - B_j with A over odd m and B over even m - 144 FMAs instead of 288.
 // The result differs from a straight 12-term dot product only in the last ulp, like one BLAS differs from another.
 // `rare` comes back non-zero when the pixel needs the plain path instead (the caller redoes it with pixel_energy_plain).
-__device__ __forceinline__ double pixel_energy(float (&x)[kMfccNum], bool normalize, float lo, float range,
+__device__ __forceinline__ double pixel_energy(float (&x)[kMfccNum], bool normalize, const FrameNorm& norm,
                                                const double* __restrict__ exp_table, unsigned int& rare) {
     double z[kMfccNum];
     rare = 0;
 #pragma unroll
     for (int m = 0; m < kMfccNum; ++m) {
         float v = x[m];
-        if (normalize) v = __fdiv_rn(__fsub_rn(v, lo), range);                // float32, as TF
+        if (normalize) v = norm.apply(v);                                     // float32, as TF
         rare |= (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u;            // NaN / Inf: plain path
         v = __double2float_rn(div_by_lifter(static_cast<double>(v), m));
         v = __double2float_rn(__dmul_rn(static_cast<double>(v), c_mfnorm));
@@ -276,6 +286,7 @@ energy_kernel(const float* __restrict__ images, long long n_frames, int normaliz
             range = __fsub_rn(mx, mn);
         }
 
+        const FrameNorm norm(lo, range);
 #pragma unroll 1
         for (int i = 0; i < kPixelsPerThread; ++i) {
             const int p = tid + i * kEnergyThreads;
@@ -283,7 +294,7 @@ energy_kernel(const float* __restrict__ images, long long n_frames, int normaliz
             const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
             float x[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
             unsigned int rare;
-            double en = pixel_energy(x, normalize_first != 0, lo, range, s_exp, rare);
+            double en = pixel_energy(x, normalize_first != 0, norm, s_exp, rare);
             float* scaled_dst = scaled_out != nullptr ? scaled_out + frame * kFrameValues + p * kMfccNum : nullptr;
             if (rare) {
                 en = pixel_energy_plain(img + p * kMfccNum, scaled_dst, normalize_first != 0, lo, range);

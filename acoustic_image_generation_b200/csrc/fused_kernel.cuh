@@ -154,7 +154,7 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* __rest
             hi = fmaxf(hi, sh.minmax[slot][w][1]);
         }
         mbar_arrive(frame_empty + 8 * slot);
-        const float range = __fsub_rn(hi, lo);
+        const FrameNorm norm(lo, __fsub_rn(hi, lo));
         const float* img = mfcc_out + static_cast<size_t>(frame) * kFrameValues;
 #pragma unroll 1
         for (int p = et; p < kFramePixels; p += kFusedEnergyThreads) {
@@ -162,8 +162,8 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* __rest
             const float4 a = __ldcg(src), b = __ldcg(src + 1), c = __ldcg(src + 2);   // L2: written by this SM just now
             float x[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
             unsigned int rare;
-            double en = pixel_energy(x, normalize_first != 0, lo, range, sh.exp_table, rare);
-            if (rare) en = pixel_energy_plain(img + p * kMfccNum, nullptr, normalize_first != 0, lo, range);
+            double en = pixel_energy(x, normalize_first != 0, norm, sh.exp_table, rare);
+            if (rare) en = pixel_energy_plain(img + p * kMfccNum, nullptr, normalize_first != 0, norm.lo, norm.range);
             sh.map[p] = en;
             if (energy_out != nullptr) energy_out[static_cast<size_t>(frame) * kFramePixels + p] = en;
         }
