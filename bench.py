@@ -210,7 +210,10 @@ def run_gpu(args):
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # NCCL's banner / warnings go to stderr: stdout is ONE JSON line
+    # stdout carries exactly ONE JSON line: anything native libraries print meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
     torch.cuda.set_device(local)
@@ -359,6 +362,9 @@ def run_gpu(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = time_cpu(10 ** 6, 1, budget_s=args.cpu_seconds)[0]
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
