@@ -166,3 +166,26 @@ def test_soak_2048_distinct_frames_invariants_and_oracle_sample(path):
     print('soak: mfcc max abs err %.2e; boundary flips vs the all-oracle chain on %d frames: %d (all-floor frame: %d)'
           % (err, len(sample) - 2, flips, int(per_frame[1])))
     assert flips <= 10
+
+
+def test_mfcc_error_statistics_over_many_spectra(path):
+    """Error distribution of the float32 MFCC kernel against the float64 reference arithmetic over 3.3e5 spectra per input
+    family (the golden fixtures cover 1-2 frames): max, 99.99th percentile and RMS of the absolute error, all far inside
+    the 1e-4 tolerance."""
+    bank, dct, lifter, mfnorm = oracle.reference_tables()
+    rng = np.random.default_rng(123)
+    families = {
+        'chi2': synth.power_frames(64, 301, 'chi2').reshape(-1, 512),
+        'lognormal sigma=3': synth.power_frames(64, 302, 'lognormal').reshape(-1, 512),
+        'near the 0.001 floor': (rng.random((64 * 1728, 512), dtype=np.float32) * np.float32(4e-4)),
+        'one dominant bin': (rng.random((64 * 1728, 512), dtype=np.float32) * np.float32(1e-3)
+                             + (rng.random((64 * 1728, 512)) > 0.998).astype(np.float32) * np.float32(1e6)),
+        'audio-scale 1e9': synth.power_frames(64, 303, 'chi2').reshape(-1, 512) * np.float32(1e9),
+    }
+    for name, beam in families.items():
+        want = oracle.get_feats(512, beam, 12, dct, mfnorm, lifter, bank)
+        got = path.mfcc_rows(beam).astype(np.float64)
+        err = np.abs(got - np.float32(want).astype(np.float64)).ravel()
+        print('%-22s n=%d  max %.2e  p99.99 %.2e  rms %.2e  (max |mfcc| %.1f)'
+              % (name, err.size, err.max(), np.quantile(err, 0.9999), np.sqrt(np.mean(err ** 2)), np.abs(want).max()))
+        assert err.max() <= 1e-4
