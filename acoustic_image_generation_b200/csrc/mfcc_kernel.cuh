@@ -55,8 +55,12 @@ __device__ __forceinline__ void mel_tile(uint32_t ring, uint32_t bar_full, uint3
     AIG_MEL_DECL(6) AIG_MEL_DECL(7) AIG_MEL_DECL(8) AIG_MEL_DECL(9) AIG_MEL_DECL(10) AIG_MEL_DECL(11)
     AIG_MEL_DECL(12) AIG_MEL_DECL(13) AIG_MEL_DECL(14) AIG_MEL_DECL(15) AIG_MEL_DECL(16) AIG_MEL_DECL(17)
     AIG_MEL_DECL(18) AIG_MEL_DECL(19) AIG_MEL_DECL(20) AIG_MEL_DECL(21) AIG_MEL_DECL(22) AIG_MEL_DECL(23)
+    // two interleaved sets of cepstral accumulators (even / odd triangles): partial sums stay half as large, which
+    // trims the float32 rounding of the 24-term sums when |MFCC| runs into the hundreds
     float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f, c5 = 0.f;
     float c6 = 0.f, c7 = 0.f, c8 = 0.f, c9 = 0.f, c10 = 0.f, c11 = 0.f;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, d4 = 0.f, d5 = 0.f;
+    float d6 = 0.f, d7 = 0.f, d8 = 0.f, d9 = 0.f, d10 = 0.f, d11 = 0.f;
     float poison = 0.f;   // 0, or NaN once any bin of the row is NaN/Inf (reference: x * 0 = NaN)
 
 #define MEL_SLAB_BEGIN(s)                                                                        \
@@ -68,17 +72,24 @@ __device__ __forceinline__ void mel_tile(uint32_t ring, uint32_t bar_full, uint3
 #define MEL_BIN0(j, c) poison = fmaf(v##j.c, 0.f, poison);
 #define MEL_BIN1(j, c, f, p, w) m##f##_##p = fmaf(v##j.c, w, m##f##_##p);
 #define MEL_BIN2(j, c, f, p, w, g, q, u) MEL_BIN1(j, c, f, p, w) MEL_BIN1(j, c, g, q, u)
-#define MEL_DONE(f, d0, d1, d2, d3, d4, d5, d6, d7, d8, d9, d10, d11)                            \
+#define MEL_DONE(f, w0, w1, w2, w3, w4, w5, w6, w7, w8, w9, w10, w11)                            \
         {                                                                                        \
             float e = m##f##_0 + m##f##_1;                                                       \
             /* floor at 0.001 (:858); -Inf would be floored away here but is NaN in the        */\
             /* reference's other columns, so turn it into NaN                                   */\
             e = (e < 0.001f) ? ((e == -CUDART_INF_F) ? CUDART_NAN_F : 0.001f) : e;               \
             const float lg = logf(e);                                                            \
-            c0 = fmaf(lg, d0, c0); c1 = fmaf(lg, d1, c1); c2 = fmaf(lg, d2, c2);                \
-            c3 = fmaf(lg, d3, c3); c4 = fmaf(lg, d4, c4); c5 = fmaf(lg, d5, c5);                \
-            c6 = fmaf(lg, d6, c6); c7 = fmaf(lg, d7, c7); c8 = fmaf(lg, d8, c8);                \
-            c9 = fmaf(lg, d9, c9); c10 = fmaf(lg, d10, c10); c11 = fmaf(lg, d11, c11);          \
+            if ((f) % 2 == 0) {                                                                  \
+                c0 = fmaf(lg, w0, c0); c1 = fmaf(lg, w1, c1); c2 = fmaf(lg, w2, c2);            \
+                c3 = fmaf(lg, w3, c3); c4 = fmaf(lg, w4, c4); c5 = fmaf(lg, w5, c5);            \
+                c6 = fmaf(lg, w6, c6); c7 = fmaf(lg, w7, c7); c8 = fmaf(lg, w8, c8);            \
+                c9 = fmaf(lg, w9, c9); c10 = fmaf(lg, w10, c10); c11 = fmaf(lg, w11, c11);      \
+            } else {                                                                             \
+                d0 = fmaf(lg, w0, d0); d1 = fmaf(lg, w1, d1); d2 = fmaf(lg, w2, d2);            \
+                d3 = fmaf(lg, w3, d3); d4 = fmaf(lg, w4, d4); d5 = fmaf(lg, w5, d5);            \
+                d6 = fmaf(lg, w6, d6); d7 = fmaf(lg, w7, d7); d8 = fmaf(lg, w8, d8);            \
+                d9 = fmaf(lg, w9, d9); d10 = fmaf(lg, w10, d10); d11 = fmaf(lg, w11, d11);      \
+            }                                                                                    \
         }
 #define MEL_SLAB_END(s)                                                                          \
         if ((s) % SLABS_PER_STAGE == SLABS_PER_STAGE - 1) {                                      \
@@ -96,7 +107,8 @@ __device__ __forceinline__ void mel_tile(uint32_t ring, uint32_t bar_full, uint3
 #undef MEL_DONE
 #undef MEL_SLAB_END
 
-    const float raw[12] = {c0, c1, c2, c3, c4, c5, c6, c7, c8, c9, c10, c11};
+    const float raw[12] = {c0 + d0, c1 + d1, c2 + d2, c3 + d3, c4 + d4, c5 + d5,
+                           c6 + d6, c7 + d7, c8 + d8, c9 + d9, c10 + d10, c11 + d11};
 #pragma unroll
     for (int m = 0; m < 12; ++m) {
         const float v = raw[m] + poison;
