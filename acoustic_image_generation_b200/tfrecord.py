@@ -70,24 +70,31 @@ class RecordFile:
         return arr.reshape(steps.value, -1) if steps.value else arr.reshape(0, 0)
 
 
+def _scalar(records, index, key):
+    values = records.context(index, key)
+    if values.size == 0:
+        raise AigError(-1, 'context feature holds no value: ' + key)
+    return int(values[0])
+
+
 def parse_acoustic_example(records, index, flip=True):
     """_parse_sequence of the ACIVW loader (outdoor_data_mfcc.py:260-344) for the modalities present in the record:
     {'classes', 'location', 'audio_images' [T,H,W,D] float32 (flipped left-right and up-down when ``flip``, :314-315),
     'audio_samples' [T*mics, samples] int32, 'video_images' [T,H,W,3] uint8}."""
-    out = {'classes': int(records.context(index, 'classes')[0]), 'location': int(records.context(index, 'location')[0])}
+    out = {'classes': _scalar(records, index, 'classes'), 'location': _scalar(records, index, 'location')}
     try:
-        h, w, d = (int(records.context(index, 'audio_image/' + k)[0]) for k in ('height', 'width', 'depth'))
+        h, w, d = (_scalar(records, index, 'audio_image/' + k) for k in ('height', 'width', 'depth'))
         img = records.sequence(index, 'audio/image', np.float32).reshape(-1, h, w, d)
         out['audio_images'] = np.ascontiguousarray(img[:, ::-1, ::-1, :]) if flip else img
     except AigError:
         pass
     try:
-        samples = int(records.context(index, 'audio_data/samples')[0])
+        samples = _scalar(records, index, 'audio_data/samples')
         out['audio_samples'] = records.sequence(index, 'audio/data', np.int32).reshape(-1, samples)
     except AigError:
         pass
     try:
-        h, w, d = (int(records.context(index, 'video/' + k)[0]) for k in ('height', 'width', 'depth'))
+        h, w, d = (_scalar(records, index, 'video/' + k) for k in ('height', 'width', 'depth'))
         out['video_images'] = records.sequence(index, 'video/image', np.uint8).reshape(-1, h, w, d)
     except AigError:
         pass

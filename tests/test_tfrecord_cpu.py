@@ -129,3 +129,37 @@ def test_corruption_is_detected(tmp_path):
     open(empty, 'wb').close()
     with tfrecord.RecordFile(empty) as rec:
         assert len(rec) == 0
+
+
+def test_malformed_messages_never_crash_the_reader(tmp_path):
+    """Valid framing (checksums recomputed) around damaged SequenceExample bytes: every accessor either answers or
+    raises AigError - truncated varints, over-long length prefixes and wrong wire types must not read out of bounds."""
+    images = synth.sigmoid_images(2, 4)
+    good = tfrecord.encode_sequence_example(
+        {'classes': 3, 'location': 1, 'audio_image/height': 36, 'audio_image/width': 48, 'audio_image/depth': 12,
+         'xmin': [1, 2, 3]}, {'audio/image': [f.tobytes()[:64] for f in images], 'audio/data': [b'\x01\x02\x03\x04'] * 3})
+    rng = np.random.default_rng(11)
+    blobs = [good[:k] for k in range(0, len(good), 7)]                      # every kind of truncation
+    for _ in range(300):                                                     # byte flips, biased towards the tags
+        b = bytearray(good)
+        for _ in range(int(rng.integers(1, 4))):
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        blobs.append(bytes(b))
+    blobs.append(b'\xff' * 40)                                               # endless varint
+    blobs.append(b'\x0a\xff\xff\xff\xff\x0f')                                # length prefix far past the end
+    path = str(tmp_path / 'fuzz.tfrecord')
+    with open(path, 'wb') as fh:
+        fh.write(b''.join(_frame(b) for b in blobs))
+    answered = raised = 0
+    with tfrecord.RecordFile(path) as rec:
+        assert len(rec) == len(blobs)
+        for i in range(len(rec)):
+            for call in (lambda: rec.context(i, 'classes'), lambda: rec.context(i, 'xmin'),
+                         lambda: rec.sequence(i, 'audio/image', np.uint8), lambda: rec.sequence(i, 'audio/data', np.uint8),
+                         lambda: tfrecord.parse_acoustic_example(rec, i)):
+                try:
+                    call()
+                    answered += 1
+                except (AigError, ValueError, KeyError):
+                    raised += 1
+    assert answered > 0 and raised > 0
