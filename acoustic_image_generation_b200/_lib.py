@@ -97,6 +97,8 @@ SIGNATURES = {
     'aig_filtfilt': (_int, [_p, _p, _int, _i64, _int, _p, _p, _p, _int, _p]),
     'aig_normalize_mfcc': (_int, [_p, _p, _i64, _p]),
     'aig_tile_mfcc': (_int, [_p, _p, _i64, _int, _p]),
+    'aig_split_triplets': (_int, [_p, _p, _i64, _p]),
+    'aig_triplet_mse': (_int, [_p, _p, _p, _i64, _p]),
     'aig_overlay': (_int, [_p, _p, _p, _i64, _int, _int, ctypes.c_float, _p, _p]),
     'aig_records_open': (_int, [ctypes.c_char_p, ctypes.POINTER(_p)]),
     'aig_records_close': (_int, [_p]),

@@ -289,6 +289,26 @@ class AcousticPath:
         self._check(self._lib.aig_tile_mfcc(self._h, a.ptr, n, int(bool(normalize)), self._a(res, np.float32, True).ptr))
         return res
 
+    def split_triplets(self, images):
+        """The four channel triplets tf.slice(x, [0,0,0,3t], [-1,36,48,3]) of [N, 36, 48, 12] images as one contiguous
+        [4, N, 36, 48, 3] array (trainer/mfcctrainer.py:105-112)."""
+        a = self._a(images, np.float32)
+        n = self._frames(a.shape, FRAME_PIXELS * MFCC_NUM)
+        res = self._empty((4, n, FRAME_H, FRAME_W, 3), np.float32, a)
+        self._check(self._lib.aig_split_triplets(self._h, a.ptr, n, self._a(res, np.float32, True).ptr))
+        return res
+
+    def triplet_mse(self, target, generated):
+        """float64[5]: tf.losses.mean_squared_error of the whole [N, 36, 48, 12] images and of each of their four channel
+        triplets (trainer/mfcctrainer.py:103, 114-117), both images read once."""
+        a, b = self._a(target, np.float32), self._a(generated, np.float32)
+        n = self._frames(a.shape, FRAME_PIXELS * MFCC_NUM)
+        if self._frames(b.shape, FRAME_PIXELS * MFCC_NUM) != n or n == 0:
+            raise ValueError('triplet_mse needs two non-empty image batches of the same size')
+        out = np.empty(5, np.float64)
+        self._check(self._lib.aig_triplet_mse(self._h, a.ptr, b.ptr, n, out.ctypes.data))
+        return out
+
     # -- stage 2 ------------------------------------------------------------------------------
     def normalize_images(self, images):
         """Per-frame (x - min) / max(x - min) in float32 over [N, 36, 48, 12] (outdoor_data_mfcc.py:672-679)."""

@@ -1163,6 +1163,56 @@ int aig_tile_mfcc(aig_handle* h, const float* mfcc, int64_t n, int normalize, fl
     return io.finish();
 }
 
+int aig_split_triplets(aig_handle* h, const float* images, int64_t n_frames, float* triplets_out) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (n_frames < 0 || (n_frames > 0 && (!images || !triplets_out)))
+        return h->fail(AIG_ERR_ARGUMENT, "aig_split_triplets: bad buffers");
+    if (n_frames == 0) return AIG_OK;
+    Io io(h);
+    const size_t values = static_cast<size_t>(n_frames) * kFrameValues;
+    const float* d_in = io.in(images, values);
+    float* d_out = io.out(triplets_out, values);
+    if (io.failed) return io.finish();
+    const long long n_pixels = static_cast<long long>(n_frames) * kFramePixels;
+    const int grid = static_cast<int>(std::min<long long>((n_pixels + kTripletTile - 1) / kTripletTile,
+                                                          static_cast<long long>(h->sm_count) * 8));
+    LaunchScope scope(h, h->stream, kKindOther);
+    split_triplets_kernel<<<grid, kTripletThreads, 0, h->stream>>>(d_in, n_pixels, d_out);
+    rc = scope.done("split_triplets_kernel");
+    if (rc != AIG_OK) return rc;
+    return io.finish();
+}
+
+int aig_triplet_mse(aig_handle* h, const float* a, const float* b, int64_t n_frames, double* mse_out) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (n_frames <= 0 || !a || !b || !mse_out) return h->fail(AIG_ERR_ARGUMENT, "aig_triplet_mse: bad buffers");
+    Io io(h);
+    const size_t values = static_cast<size_t>(n_frames) * kFrameValues;
+    const float* d_a = io.in(a, values);
+    const float* d_b = io.in(b, values);
+    double* d_out = io.out(mse_out, 5);
+    const long long n_pixels = static_cast<long long>(n_frames) * kFramePixels;
+    const int grid = static_cast<int>(std::min<long long>((n_pixels + kTripletThreads - 1) / kTripletThreads,
+                                                          static_cast<long long>(h->sm_count) * 8));
+    double* d_partial = static_cast<double*>(scratch(h, static_cast<size_t>(grid) * 4 * sizeof(double)));
+    if (io.failed || !d_partial) { io.failed = true; return io.finish(); }
+    {
+        LaunchScope scope(h, h->stream, kKindOther);
+        triplet_mse_kernel<<<grid, kTripletThreads, 0, h->stream>>>(d_a, d_b, n_pixels, d_partial);
+        rc = scope.done("triplet_mse_kernel");
+        if (rc != AIG_OK) return rc;
+    }
+    {
+        LaunchScope scope(h, h->stream, kKindOther);
+        triplet_mse_finish_kernel<<<1, 32, 0, h->stream>>>(d_partial, grid, n_pixels, d_out);
+        rc = scope.done("triplet_mse_finish_kernel");
+        if (rc != AIG_OK) return rc;
+    }
+    return io.finish();
+}
+
 int aig_overlay(aig_handle* h, const float* heat, const uint8_t* bgr, int64_t n_frames, int out_h, int out_w, float alpha,
                 const uint8_t* jet_lut, uint8_t* rgb_out) {
     int rc = require(h);

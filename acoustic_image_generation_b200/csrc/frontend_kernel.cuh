@@ -10,6 +10,8 @@
 // N2  normalize_mfcc_kernel   _normalize_mfcc (:696-703): per-vector float32 min-max of the 12 MFCCs.
 //     tile_mfcc_kernel        mfccmap = tile(reshape(mfcc, (-1,1,12)), (1, 36*48, 1)) (trainer/mfcctrainer.py:38-40,
 //                             iouenergythreshold.py:99-101): the [B,36,48,12] conditioning image of the UNet.
+//     split_triplets_kernel, triplet_mse_kernel   the four channel-triplet slices and the five MSE terms of the
+//                             trainers (trainer/mfcctrainer.py:103-117).
 #pragma once
 
 #include <type_traits>
@@ -154,6 +156,99 @@ tile_mfcc_kernel(const float* __restrict__ mfcc, long long n, int normalize, flo
 #pragma unroll 3
         for (int i = threadIdx.x; i < kFrameValues / 4; i += kTileThreads) __stcs(dst + i, mine);
     }
+}
+
+// ---- N2: channel-triplet slices and their losses (trainer/mfcctrainer.py:103-117) -----------------------
+// The trainers cut both the target and the generated [n,36,48,12] image into the four channel triplets
+// tf.slice(x, [0,0,0,3t], [-1,36,48,3]) and take tf.losses.mean_squared_error of the whole image and of each pair of
+// triplets.  split_triplets_kernel writes the four slices as contiguous [n,36,48,3] tensors (what tf.slice returns);
+// triplet_mse_kernel reads both images once and produces all five means.
+constexpr int kTripletThreads = 256;
+constexpr int kTripletTile = 256;        // pixels per tile
+__global__ void __launch_bounds__(kTripletThreads)
+split_triplets_kernel(const float* __restrict__ images, long long n_pixels, float* __restrict__ out) {
+    // Tile of 256 pixels: coalesced float4 loads into a channel-major shared tile (row stride 257: conflict-free both
+    // ways), then each triplet's 768 floats leave as 192 coalesced float4 stores.  n_pixels is a multiple of 1728, so
+    // of 4; the last tile may be short.
+    __shared__ float s_tile[12][kTripletTile + 1];
+    const long long tiles = (n_pixels + kTripletTile - 1) / kTripletTile;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long first = tile * kTripletTile;
+        const int count = static_cast<int>(min(static_cast<long long>(kTripletTile), n_pixels - first));
+        const float4* src = reinterpret_cast<const float4*>(images + first * 12);
+        __syncthreads();
+        for (int i = threadIdx.x; i < count * 3; i += kTripletThreads) {
+            const float4 q = __ldcs(src + i);
+            const int px = i / 3, c = 4 * (i - 3 * px);
+            s_tile[c][px] = q.x; s_tile[c + 1][px] = q.y; s_tile[c + 2][px] = q.z; s_tile[c + 3][px] = q.w;
+        }
+        __syncthreads();
+        const int quads = count * 3 / 4;                     // float4 per triplet in this tile
+        for (int i = threadIdx.x; i < 4 * quads; i += kTripletThreads) {
+            const int t = i / quads, j = i - t * quads;
+            float w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int o = 4 * j + k, px = o / 3;
+                w[k] = s_tile[3 * t + (o - 3 * px)][px];
+            }
+            __stcs(reinterpret_cast<float4*>(out + (t * n_pixels + first) * 3) + j, make_float4(w[0], w[1], w[2], w[3]));
+        }
+    }
+}
+
+// partial[block][4]: float64 sums of the float32 squared differences per triplet, in a fixed order (deterministic).
+__global__ void __launch_bounds__(kTripletThreads)
+triplet_mse_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n_pixels,
+                   double* __restrict__ partial) {
+    __shared__ double s_sum[kTripletThreads / 32][4];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long px = blockIdx.x * static_cast<long long>(kTripletThreads) + threadIdx.x; px < n_pixels;
+         px += static_cast<long long>(gridDim.x) * kTripletThreads) {
+        const float4* pa = reinterpret_cast<const float4*>(a) + px * 3;
+        const float4* pb = reinterpret_cast<const float4*>(b) + px * 3;
+        float x[12], y[12];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float4 q = __ldcs(pa + i), r = __ldcs(pb + i);
+            x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
+            y[4 * i] = r.x; y[4 * i + 1] = r.y; y[4 * i + 2] = r.z; y[4 * i + 3] = r.w;
+        }
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {
+            const float d = __fsub_rn(x[c], y[c]);
+            acc[c / 3] += static_cast<double>(__fmul_rn(d, d));      // squared difference in float32, like TF
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        double v = acc[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_sum[warp][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double v = 0.0;
+        for (int w = 0; w < kTripletThreads / 32; ++w) v += s_sum[w][threadIdx.x];
+        partial[blockIdx.x * 4 + threadIdx.x] = v;
+    }
+}
+
+// mse_out[0] = whole image, mse_out[1 + t] = triplet t
+__global__ void triplet_mse_finish_kernel(const double* __restrict__ partial, int n_blocks, long long n_pixels,
+                                          double* __restrict__ mse_out) {
+    __shared__ double s_total[4];
+    if (threadIdx.x < 4) {
+        double v = 0.0;
+        for (int blk = 0; blk < n_blocks; ++blk) v += partial[blk * 4 + threadIdx.x];
+        s_total[threadIdx.x] = v;
+        mse_out[1 + threadIdx.x] = v / static_cast<double>(n_pixels * 3);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        mse_out[0] = (s_total[0] + s_total[1] + s_total[2] + s_total[3]) / static_cast<double>(n_pixels * 12);
 }
 
 // ---- N4: heat-map overlay (showvideo.py:217-233, showimages.py:144-150) ----------------------------------

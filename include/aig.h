@@ -218,6 +218,15 @@ int aig_filtfilt(aig_handle* h, const void* x, int x_is_int32, int64_t n_rows, i
 int aig_normalize_mfcc(aig_handle* h, const float* mfcc, int64_t n, float* out);
 int aig_tile_mfcc(aig_handle* h, const float* mfcc, int64_t n, int normalize, float* map_out);
 
+/* The channel-triplet slices of the trainers (trainer/mfcctrainer.py:105-112):
+ * aig_split_triplets writes tf.slice(images, [0,0,0,3t], [-1,36,48,3]) for t = 0..3 as four contiguous
+ * [n_frames, 36, 48, 3] float32 tensors, back to back in triplets_out (same total size as the input).
+ * aig_triplet_mse reads a target and a generated image once and returns the five losses of
+ * trainer/mfcctrainer.py:103,114-117: mse_out[0] = tf.losses.mean_squared_error over the whole image,
+ * mse_out[1 + t] = over triplet t; squared differences in float32, summed in float64 in a fixed order. */
+int aig_split_triplets(aig_handle* h, const float* images, int64_t n_frames, float* triplets_out);
+int aig_triplet_mse(aig_handle* h, const float* a, const float* b, int64_t n_frames, double* mse_out);
+
 /* Heat-map overlay rendering ("next" row N4; showvideo.py:217-233, showimages.py:144-150):
  *   heat     [n, out_h, out_w] float32 in [0, 1] (aig_heatmap's output)
  *   bgr      nullable [n, out_h, out_w, 3] uint8 video frames in OpenCV's BGR order

@@ -426,6 +426,21 @@ def tile_mfcc(mfcc):
     return np.reshape(np.tile(x, (1, FRAME_PIXELS, 1)), (-1, FRAME_H, FRAME_W, MFCC_NUM))
 
 
+def split_triplets(images):
+    """tf.slice(x, [0,0,0,3t], [-1,36,48,3]) for t = 0..3 (trainer/mfcctrainer.py:105-112): [4, N, 36, 48, 3]."""
+    x = np.asarray(images, dtype=np.float32).reshape(-1, FRAME_H, FRAME_W, MFCC_NUM)
+    return np.stack([np.ascontiguousarray(x[..., 3 * t:3 * t + 3]) for t in range(4)])
+
+
+def triplet_mse(target, generated):
+    """tf.losses.mean_squared_error of the whole image and of each channel-triplet pair (trainer/mfcctrainer.py:103,
+    114-117): float32 squared differences, averaged (here in float64; TF's float32 mean agrees to ~1e-7 relative)."""
+    a, b = split_triplets(target), split_triplets(generated)
+    sq = np.square(a - b)                                   # float32, like tf.squared_difference
+    per = sq.reshape(4, -1).sum(axis=1, dtype=np.float64)
+    return np.concatenate([[per.sum() / sq.size], per / (sq.size // 4)])
+
+
 # ---------------------------------------------------------------------------
 # N4  heat-map overlay                    showvideo.py:217-233, showimages.py:144-150
 # ---------------------------------------------------------------------------

@@ -545,6 +545,25 @@ def test_normalize_and_tile_mfcc_bit_exact(path, torch):
     assert np.isnan(path.normalize_mfcc(np.full((1, 12), 2.0, np.float32))).all()
 
 
+def test_triplet_slices_and_losses(path, torch):
+    """trainer/mfcctrainer.py:103-117: the four channel triplets and the five mean-squared-error terms."""
+    for n in (1, 7, 130):
+        a, b = synth.sigmoid_images(n, 3), synth.sigmoid_images(n, 4)
+        got = path.split_triplets(a)
+        assert got.shape == (4, n, 36, 48, 3) and np.array_equal(got, oracle.split_triplets(a))
+        mse = path.triplet_mse(a, b)
+        want = oracle.triplet_mse(a, b)
+        assert mse.shape == (5,) and np.abs(mse / want - 1).max() <= 1e-13
+        assert np.array_equal(mse, path.triplet_mse(a, b))                    # fixed summation order
+        assert abs(mse[0] - np.mean(mse[1:])) <= 1e-15                        # equal-sized slices
+    assert np.array_equal(path.triplet_mse(a, a), np.zeros(5))
+    dev = path.split_triplets(torch.from_numpy(a).cuda())
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), oracle.split_triplets(a))
+    assert np.array_equal(path.triplet_mse(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()), mse)
+    with pytest.raises(ValueError):
+        path.triplet_mse(a, b[:-1])
+
+
 def test_overlay_bit_exact_vs_oracle(path, golden, torch):
     lut = tables.jet_lut()
     e = golden('energy')['energy_smooth']

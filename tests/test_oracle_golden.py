@@ -238,6 +238,16 @@ def test_normalize_and_tile_mfcc():
     assert np.isnan(oracle.normalize_mfcc(np.full((1, 12), 2.0, np.float32))).all()
 
 
+def test_triplet_slices_and_losses():
+    a, b = synth.sigmoid_images(3, 1), synth.sigmoid_images(3, 2)
+    t = oracle.split_triplets(a)
+    assert t.shape == (4, 3, 36, 48, 3) and np.array_equal(t[2], a[..., 6:9]) and t[1].flags.c_contiguous
+    mse = oracle.triplet_mse(a, b)
+    d = a.astype(np.float64) - b
+    assert abs(mse[0] - np.mean(d * d)) <= 1e-8 and abs(mse[4] - np.mean(d[..., 9:] ** 2)) <= 1e-8
+    assert abs(mse[0] - mse[1:].mean()) <= 1e-15
+
+
 def test_overlay_gray_matches_cv2_and_jet_table_shape():
     import cv2
     from acoustic_image_generation_b200 import tables
