@@ -104,8 +104,21 @@ def time_cpu(steps, warmup, budget_s=None):
         if budget_s is not None and time.perf_counter() - t_all > budget_s and len(times) >= 3:
             break
     total = sum(times)
+    single = None
+    try:                                     # the same chain on one BLAS thread, a 3 s sample
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1, user_api='blas'):
+            cpu_chain(oracle, power)
+            t1, n1 = time.perf_counter(), 0
+            while time.perf_counter() - t1 < 3.0:
+                cpu_chain(oracle, power)
+                n1 += 1
+            single = CPU_SAMPLE_FRAMES * n1 / (time.perf_counter() - t1)
+    except Exception:
+        pass
     return {
         'value': CPU_SAMPLE_FRAMES * len(times) / total,
+        'single_thread_value': single,
         'unit': UNIT,
         'cores': blas_threads(),
         'kind': 'port',
