@@ -121,6 +121,7 @@ struct aig_handle {
     int64_t launch_row_limit = (int64_t(1) << 31) - 1024;   // TMA coordinates are int32: rows per launch (testable via option)
     int heatmap_exact = 0;              // 1: float64 replica of the oracle's bilinear; 0: float32 fast path
     bool heat_attr_set = false;
+    bool mask_attr_set = false;
     int l2_evict_first = 0;             // L2 evict-first hint on the spectrum loads (measured slower: off)
     int keep_mfcc_in_l2 = 1;            // fused kernel: evict-last hint on the MFCC stores the energy warps re-read
     bool fused_attr_set[4] = {false, false, false, false};
@@ -399,6 +400,20 @@ int launch_energy(aig_handle* h, cudaStream_t stream, const float* d_images, int
     energy_kernel<<<frames_grid(h, n_frames, ctas_per_sm), kEnergyThreads, 0, stream>>>(
         d_images, n_frames, normalize_first, d_scaled, d_energy, d_mask, d_mean);
     return scope.done("energy_kernel");
+}
+
+// resize_mask_kernel / ciou_sweep_kernel keep 36 blended rows of out_w uint16 in shared memory: up to 184 KiB at 2048 x 2048
+constexpr size_t kMaskSmemLimit = 200 * 1024;
+int allow_mask_smem(aig_handle* h) {
+    if (!h->mask_attr_set) {
+        AIG_CK(cudaFuncSetAttribute(resize_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaskSmemLimit)));
+        AIG_CK(cudaFuncSetAttribute(ciou_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaskSmemLimit)));
+        h->mask_attr_set = true;
+    }
+    return AIG_OK;
+}
+int mask_ctas_per_sm(size_t smem) {
+    return static_cast<int>(std::max<size_t>(1, std::min<size_t>(8, kMaskSmemLimit / (smem + 4 * 1024))));
 }
 
 int launch_heatmap(aig_handle* h, const double* d_energy, int64_t n_frames, int out_h, int out_w, float* d_heat) {
@@ -857,9 +872,11 @@ int aig_resize_mask(aig_handle* h, const uint8_t* mask, int64_t n_frames, int ou
     const uint8_t* d_mask = io.in(mask, n * kFramePixels);
     uint8_t* d_up = io.out(mask_up, n * out_h * out_w);
     if (io.failed) return io.finish();
-    const size_t smem = static_cast<size_t>(out_w + out_h) * 2 * sizeof(int);
+    const size_t smem = MaskTaps::bytes(out_h, out_w);
+    rc = allow_mask_smem(h);
+    if (rc != AIG_OK) return rc;
     LaunchScope scope(h, h->stream, kKindOther);
-    resize_mask_kernel<<<frames_grid(h, n_frames, 4), kHeatThreads, smem, h->stream>>>(d_mask, n_frames, out_h, out_w, d_up);
+    resize_mask_kernel<<<frames_grid(h, n_frames, mask_ctas_per_sm(smem)), kHeatThreads, smem, h->stream>>>(d_mask, n_frames, out_h, out_w, d_up);
     rc = scope.done("resize_mask_kernel");
     if (rc != AIG_OK) return rc;
     return io.finish();
@@ -1053,9 +1070,11 @@ int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, cons
     int64_t* d_pos = io.inout(pos_inout, static_cast<size_t>(k));
     int64_t* d_num = io.inout(num_inout, 1);
     if (io.failed) return io.finish();
-    const size_t smem = static_cast<size_t>(out_w + out_h) * 2 * sizeof(int);
+    const size_t smem = MaskTaps::bytes(out_h, out_w) + static_cast<size_t>(out_w + out_h);
+    rc = allow_mask_smem(h);
+    if (rc != AIG_OK) return rc;
     LaunchScope scope(h, h->stream, kKindOther);
-    ciou_sweep_kernel<<<frames_grid(h, n, 4), kIouThreads, smem, h->stream>>>(
+    ciou_sweep_kernel<<<frames_grid(h, n, mask_ctas_per_sm(smem)), kIouThreads, smem, h->stream>>>(
         d_mask, d_xmin, d_xmax, d_ymin, d_ymax, n, out_h, out_w, d_thr, k, reinterpret_cast<long long*>(d_inter),
         reinterpret_cast<long long*>(d_union), reinterpret_cast<unsigned long long*>(d_pos),
         reinterpret_cast<unsigned long long*>(d_num));

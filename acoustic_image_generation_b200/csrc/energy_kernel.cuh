@@ -581,43 +581,71 @@ heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int o
 }
 
 // mask [n, 36, 48] u8 -> mask_up [n, out_h, out_w] u8, value 1 iff bilinear(mask != 0) > 1/2 exactly.
-// Dynamic shared memory: (out_w + out_h) * 2 ints.
-__device__ __forceinline__ int upsampled_bit(const uint8_t* s_mask, int xi, int xn, int yi, int yn,
-                                             int xd, int yd) {
-    const int x0 = xi & 0xffff, x1 = xi >> 16, y0 = yi & 0xffff, y1 = yi >> 16;
-    const int top = s_mask[y0 * kFrameW + x0] * (xd - xn) + s_mask[y0 * kFrameW + x1] * xn;
-    const int bot = s_mask[y1 * kFrameW + x0] * (xd - xn) + s_mask[y1 * kFrameW + x1] * xn;
-    const long long val = static_cast<long long>(top) * (yd - yn) + static_cast<long long>(bot) * yn;
-    return 2 * val > static_cast<long long>(xd) * yd;
-}
+// The bilinear value is a ratio of integers: with tap numerators xn / (2 out_w) and yn / (2 out_h),
+//   val = [m00 (xd - xn) + m01 xn] (yd - yn) + [m10 (xd - xn) + m11 xn] yn   over   xd yd   (xd = 2 out_w, yd = 2 out_h)
+// so "> 0.5" is 2 val > xd yd with no rounding.  Separable: the 36 source rows are blended horizontally once per
+// frame (values 0..xd <= 4096, uint16), every output pixel then needs two shared loads and two integer multiply-adds
+// (val <= 2^24).
+struct MaskTaps {
+    int* x0;            // [out_w] x0 | x1 << 16
+    int* xn;            // [out_w]
+    int* y0;            // [out_h] y0 | y1 << 16
+    int* yn;            // [out_h]
+    uint16_t* rows;     // [36][out_w] horizontally blended source rows of the current frame
+    __device__ __forceinline__ void carve(int* base, int out_h, int out_w) {
+        x0 = base; xn = x0 + out_w; y0 = xn + out_w; yn = y0 + out_h;
+        rows = reinterpret_cast<uint16_t*>(yn + out_h);
+    }
+    static __host__ __device__ size_t bytes(int out_h, int out_w) {
+        return static_cast<size_t>(out_w + out_h) * 2 * sizeof(int) + static_cast<size_t>(kFrameH) * out_w * sizeof(uint16_t);
+    }
+    __device__ __forceinline__ void build_taps(int out_h, int out_w, int tid, int n_threads) const {
+        for (int d = tid; d < out_w; d += n_threads) {
+            int i0, i1, r; linear_tap_exact(d, kFrameW, out_w, &i0, &i1, &r);
+            x0[d] = i0 | (i1 << 16); xn[d] = r;
+        }
+        for (int d = tid; d < out_h; d += n_threads) {
+            int i0, i1, r; linear_tap_exact(d, kFrameH, out_h, &i0, &i1, &r);
+            y0[d] = i0 | (i1 << 16); yn[d] = r;
+        }
+    }
+    // warp per source row, lanes over output columns
+    __device__ __forceinline__ void blend_rows(const uint8_t* s_mask, int out_w, int warp, int lane, int n_warps) const {
+        const int xd = 2 * out_w;
+        for (int ys = warp; ys < kFrameH; ys += n_warps) {
+            const uint8_t* m = s_mask + ys * kFrameW;
+            uint16_t* dst = rows + ys * out_w;
+            for (int x = lane; x < out_w; x += 32) {
+                const int xi = x0[x], n = xn[x];
+                dst[x] = static_cast<uint16_t>(m[xi & 0xffff] * (xd - n) + m[xi >> 16] * n);
+            }
+        }
+    }
+};
 
 __global__ void __launch_bounds__(kHeatThreads)
 resize_mask_kernel(const uint8_t* __restrict__ mask, long long n_frames, int out_h, int out_w,
                    uint8_t* __restrict__ mask_up) {
     extern __shared__ int s_taps[];
     __shared__ uint8_t s_mask[kFramePixels];
-    int* s_x0 = s_taps;            // [out_w] x0 | x1 << 16
-    int* s_xn = s_x0 + out_w;      // [out_w]
-    int* s_y0 = s_xn + out_w;      // [out_h]
-    int* s_yn = s_y0 + out_h;      // [out_h]
-    const int tid = threadIdx.x;
-    for (int d = tid; d < out_w; d += kHeatThreads) {
-        int i0, i1, r; linear_tap_exact(d, kFrameW, out_w, &i0, &i1, &r);
-        s_x0[d] = i0 | (i1 << 16); s_xn[d] = r;
-    }
-    for (int d = tid; d < out_h; d += kHeatThreads) {
-        int i0, i1, r; linear_tap_exact(d, kFrameH, out_h, &i0, &i1, &r);
-        s_y0[d] = i0 | (i1 << 16); s_yn[d] = r;
-    }
-    const int xd = 2 * out_w, yd = 2 * out_h, n_out = out_h * out_w;
+    MaskTaps t;
+    t.carve(s_taps, out_h, out_w);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    t.build_taps(out_h, out_w, tid, kHeatThreads);
+    const int yd = 2 * out_h, half = 2 * out_w * out_h;       // xd * yd / 2
     for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
         __syncthreads();
         for (int p = tid; p < kFramePixels; p += kHeatThreads) s_mask[p] = mask[frame * kFramePixels + p] != 0;
         __syncthreads();
-        uint8_t* dst = mask_up + frame * n_out;
-        for (int idx = tid; idx < n_out; idx += kHeatThreads) {
-            const int y = idx / out_w, x = idx - y * out_w;
-            dst[idx] = static_cast<uint8_t>(upsampled_bit(s_mask, s_x0[x], s_xn[x], s_y0[y], s_yn[y], xd, yd));
+        t.blend_rows(s_mask, out_w, warp, lane, kHeatThreads / 32);
+        __syncthreads();
+        uint8_t* dst = mask_up + frame * static_cast<long long>(out_h) * out_w;
+        for (int y = warp; y < out_h; y += kHeatThreads / 32) {
+            const int yi = t.y0[y], n = t.yn[y];
+            const uint16_t* r0 = t.rows + (yi & 0xffff) * out_w;
+            const uint16_t* r1 = t.rows + (yi >> 16) * out_w;
+            uint8_t* o = dst + static_cast<long long>(y) * out_w;
+            for (int x = lane; x < out_w; x += 32) o[x] = static_cast<uint8_t>(r0[x] * (yd - n) + r1[x] * n > half);
         }
     }
 }

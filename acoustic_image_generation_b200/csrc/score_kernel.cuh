@@ -11,7 +11,7 @@
 #pragma once
 
 #include "aig_common.cuh"
-#include "energy_kernel.cuh"   // linear_tap_exact / upsampled_bit
+#include "energy_kernel.cuh"   // linear_tap_exact / MaskTaps
 
 namespace aig {
 
@@ -89,7 +89,7 @@ iou_sweep_clips_kernel(const uint8_t* __restrict__ mask_a, const uint8_t* __rest
     }
 }
 
-// Dynamic shared memory: (out_w + out_h) * 2 ints of bilinear taps.
+// Dynamic shared memory: MaskTaps::bytes(out_h, out_w) + out_w + out_h bytes (box membership bits per column / row).
 __global__ void __launch_bounds__(kIouThreads)
 ciou_sweep_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ xmin, const int* __restrict__ xmax,
                   const int* __restrict__ ymin, const int* __restrict__ ymax, long long n, int out_h, int out_w,
@@ -102,22 +102,15 @@ ciou_sweep_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ xmin
     __shared__ int s_box[3][4];                 // xa, xb, ya, yb (xa > xb: absent)
     __shared__ int s_sum[2][kIouThreads / 32];
     __shared__ double s_iou;
-    int* s_x0 = s_taps;
-    int* s_xn = s_x0 + out_w;
-    int* s_y0 = s_xn + out_w;
-    int* s_yn = s_y0 + out_h;
+    MaskTaps t;
+    t.carve(s_taps, out_h, out_w);
+    uint8_t* s_colbits = reinterpret_cast<uint8_t*>(t.rows + kFrameH * out_w);   // [out_w] bit c: column inside box c
+    uint8_t* s_rowbits = s_colbits + out_w;                                       // [out_h] bit c: row inside box c
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int k = tid; k < k_thr; k += kIouThreads) s_pos[k] = 0;
     if (blockIdx.x == 0 && tid == 0) atomicAdd(num, static_cast<unsigned long long>(n));   // num += 1 per frame (:321)
-    for (int d = tid; d < out_w; d += kIouThreads) {
-        int i0, i1, r; linear_tap_exact(d, kFrameW, out_w, &i0, &i1, &r);
-        s_x0[d] = i0 | (i1 << 16); s_xn[d] = r;
-    }
-    for (int d = tid; d < out_h; d += kIouThreads) {
-        int i0, i1, r; linear_tap_exact(d, kFrameH, out_h, &i0, &i1, &r);
-        s_y0[d] = i0 | (i1 << 16); s_yn[d] = r;
-    }
-    const int xd = 2 * out_w, yd = 2 * out_h, n_out = out_h * out_w;
+    t.build_taps(out_h, out_w, tid, kIouThreads);
+    const int yd = 2 * out_h, half = 2 * out_w * out_h;
     for (long long f = blockIdx.x; f < n; f += gridDim.x) {
         __syncthreads();
         for (int p = tid; p < kFramePixels; p += kIouThreads) s_mask[p] = mask[f * kFramePixels + p] != 0;
@@ -131,17 +124,31 @@ ciou_sweep_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ xmin
             s_box[tid][0] = xa; s_box[tid][1] = xb; s_box[tid][2] = ya; s_box[tid][3] = yb;
         }
         __syncthreads();
-        int inter2 = 0, union2 = 0;
-        for (int idx = tid; idx < n_out; idx += kIouThreads) {
-            const int y = idx / out_w, x = idx - y * out_w;
-            const int pred = upsampled_bit(s_mask, s_x0[x], s_xn[x], s_y0[y], s_yn[y], xd, yd);
-            int g2 = 0;                                        // ground-truth weight in half units
+        t.blend_rows(s_mask, out_w, warp, lane, kIouThreads / 32);
+        for (int x = tid; x < out_w; x += kIouThreads) {
+            int bits = 0;
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-                g2 += (x >= s_box[c][0] && x <= s_box[c][1] && y >= s_box[c][2] && y <= s_box[c][3]);
-            g2 = min(g2, 2);                                   // mtot[mtot > 1] = 1 (:296)
-            inter2 += pred ? g2 : 0;                           // (mtot and m2) * mtot (:306-308)
-            union2 += g2 > 0 ? g2 : 2 * pred;                  // (mtot or m2) + (mtot - [mtot>0]) (:310-316)
+            for (int c = 0; c < 3; ++c) bits |= (x >= s_box[c][0] && x <= s_box[c][1]) << c;
+            s_colbits[x] = static_cast<uint8_t>(bits);
+        }
+        for (int y = tid; y < out_h; y += kIouThreads) {
+            int bits = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) bits |= (y >= s_box[c][2] && y <= s_box[c][3]) << c;
+            s_rowbits[y] = static_cast<uint8_t>(bits);
+        }
+        __syncthreads();
+        int inter2 = 0, union2 = 0;
+        for (int y = warp; y < out_h; y += kIouThreads / 32) {
+            const int yi = t.y0[y], wn = t.yn[y], rowbits = s_rowbits[y];
+            const uint16_t* r0 = t.rows + (yi & 0xffff) * out_w;
+            const uint16_t* r1 = t.rows + (yi >> 16) * out_w;
+            for (int x = lane; x < out_w; x += 32) {
+                const int pred = r0[x] * (yd - wn) + r1[x] * wn > half;
+                const int g2 = min(__popc(s_colbits[x] & rowbits), 2);   // half units; mtot[mtot > 1] = 1 (:296)
+                inter2 += pred ? g2 : 0;                                  // (mtot and m2) * mtot (:306-308)
+                union2 += g2 > 0 ? g2 : 2 * pred;                         // (mtot or m2) + (mtot - [mtot>0]) (:310-316)
+            }
         }
         inter2 = warp_sum(inter2);
         union2 = warp_sum(union2);
