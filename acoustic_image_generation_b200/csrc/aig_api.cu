@@ -1248,7 +1248,12 @@ int aig_overlay(aig_handle* h, const float* heat, const uint8_t* bgr, int64_t n_
     uint8_t* d_out = io.out(rgb_out, n * px * 3);
     if (io.failed) return io.finish();
     LaunchScope scope(h, h->stream, kKindOther);
-    overlay_kernel<<<frames_grid(h, n_frames, 8), 256, 0, h->stream>>>(d_heat, d_bgr, n_frames, static_cast<int>(px), alpha, d_lut, d_out);
+    const bool vec = px % 4 == 0 && (reinterpret_cast<uintptr_t>(d_heat) & 15u) == 0 &&
+                     (reinterpret_cast<uintptr_t>(d_bgr) & 3u) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3u) == 0;
+    if (vec)
+        overlay_kernel<4><<<frames_grid(h, n_frames, 8), 256, 0, h->stream>>>(d_heat, d_bgr, n_frames, static_cast<int>(px), alpha, d_lut, d_out);
+    else
+        overlay_kernel<1><<<frames_grid(h, n_frames, 8), 256, 0, h->stream>>>(d_heat, d_bgr, n_frames, static_cast<int>(px), alpha, d_lut, d_out);
     rc = scope.done("overlay_kernel");
     if (rc != AIG_OK) return rc;
     return io.finish();

@@ -256,21 +256,51 @@ __global__ void triplet_mse_finish_kernel(const double* __restrict__ partial, in
 // normalised and quantised to 256 levels - then imshow(map, cmap=jet, alpha=0.7): the normalised heat map goes through
 // matplotlib's 256-entry jet table and is alpha-blended over the gray image.  One CTA per frame; out is RGB8.
 // jet_lut: 256 x 3 uint8.  Without a frame (bgr == nullptr) the colour-mapped heat map alone is written.
+// Per CTA: s_jet[j] = jet[j] * alpha (or jet[j] itself without a frame); per frame: s_gray[y] = quantised gray level of
+// luma y times (1 - alpha) - the blend of a pixel is then one table row plus one table value, three adds, three
+// roundings, with the reference's operation order (products rounded separately, then added).
+// VEC = 4: four pixels per thread (float4 heat, 3 x 32-bit BGR in, 3 x 32-bit RGB out); needs n_pixels % 4 == 0 and
+// 16 / 4 / 4-byte aligned heat / bgr / out.  VEC = 1: any geometry.
+__device__ __forceinline__ int luma15(unsigned b, unsigned g, unsigned r) {
+    return static_cast<int>((b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15);
+}
+
+template <int VEC>
 __global__ void __launch_bounds__(256)
 overlay_kernel(const float* __restrict__ heat, const uint8_t* __restrict__ bgr, long long n_frames, int n_pixels,
                float alpha, const uint8_t* __restrict__ jet_lut, uint8_t* __restrict__ rgb_out) {
-    __shared__ uint8_t s_lut[768];
+    __shared__ float4 s_jet[256];
+    __shared__ float s_gray[256];
     __shared__ int s_red[2][8];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < 768; i += 256) s_lut[i] = jet_lut[i];
+    {
+        const float r = jet_lut[3 * tid], g = jet_lut[3 * tid + 1], b = jet_lut[3 * tid + 2];
+        s_jet[tid] = bgr ? make_float4(__fmul_rn(r, alpha), __fmul_rn(g, alpha), __fmul_rn(b, alpha), 0.f)
+                         : make_float4(r, g, b, 0.f);
+        s_gray[tid] = 0.f;
+    }
+    const float keep = __fsub_rn(1.f, alpha);
     for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
         __syncthreads();
         const uint8_t* img = bgr ? bgr + f * n_pixels * 3 : nullptr;
-        int lo = 255, hi = 0;
         if (img != nullptr) {
-            for (int p = tid; p < n_pixels; p += 256) {
-                const int y = (img[3 * p] * 3735 + img[3 * p + 1] * 19235 + img[3 * p + 2] * 9798 + 16384) >> 15;
-                lo = min(lo, y); hi = max(hi, y);
+            int lo = 255, hi = 0;
+            if (VEC == 4) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(img);
+                for (int q = tid; q < n_pixels / 4; q += 256) {
+                    const uint32_t w0 = __ldg(w + 3 * q), w1 = __ldg(w + 3 * q + 1), w2 = __ldg(w + 3 * q + 2);
+                    const int y0 = luma15(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
+                    const int y1 = luma15(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
+                    const int y2 = luma15((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
+                    const int y3 = luma15((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+                    lo = min(min(lo, min(y0, y1)), min(y2, y3));
+                    hi = max(max(hi, max(y0, y1)), max(y2, y3));
+                }
+            } else {
+                for (int p = tid; p < n_pixels; p += 256) {
+                    const int y = luma15(img[3 * p], img[3 * p + 1], img[3 * p + 2]);
+                    lo = min(lo, y); hi = max(hi, y);
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -282,26 +312,52 @@ overlay_kernel(const float* __restrict__ heat, const uint8_t* __restrict__ bgr, 
             lo = s_red[0][0]; hi = s_red[1][0];
 #pragma unroll
             for (int w = 1; w < 8; ++w) { lo = min(lo, s_red[0][w]); hi = max(hi, s_red[1][w]); }
+            // imshow(gray, cmap=gray): level = int((y - lo) / (hi - lo) * 256) clipped to 255, for every possible luma
+            const float range = static_cast<float>(hi - lo);
+            int gi = (range > 0.f && tid >= lo) ? static_cast<int>(__fmul_rn(__fdiv_rn(static_cast<float>(tid - lo), range), 256.f)) : 0;
+            gi = min(gi, 255);
+            s_gray[tid] = __fmul_rn(static_cast<float>(gi), keep);
+            __syncthreads();
         }
-        const float range = static_cast<float>(hi - lo);
-        for (int p = tid; p < n_pixels; p += 256) {
-            const float hv = heat[f * n_pixels + p];
-            int ji = static_cast<int>(__fmul_rn(hv, 256.f));            // Colormap.__call__: int(x * N), x == 1 -> N - 1
-            ji = min(max(ji, 0), 255);
-            float r = s_lut[3 * ji], g = s_lut[3 * ji + 1], b = s_lut[3 * ji + 2];
-            if (img != nullptr) {
-                const int y = (img[3 * p] * 3735 + img[3 * p + 1] * 19235 + img[3 * p + 2] * 9798 + 16384) >> 15;
-                int gi = range > 0.f ? static_cast<int>(__fmul_rn(__fdiv_rn(static_cast<float>(y - lo), range), 256.f)) : 0;
-                gi = min(gi, 255);
-                const float gray = static_cast<float>(gi), keep = __fsub_rn(1.f, alpha);
-                r = __fadd_rn(__fmul_rn(r, alpha), __fmul_rn(gray, keep));
-                g = __fadd_rn(__fmul_rn(g, alpha), __fmul_rn(gray, keep));
-                b = __fadd_rn(__fmul_rn(b, alpha), __fmul_rn(gray, keep));
+        const float* hp = heat + f * n_pixels;
+        uint8_t* op = rgb_out + f * n_pixels * 3;
+        if (VEC == 4) {
+            const float4* h4 = reinterpret_cast<const float4*>(hp);
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(img);
+            uint32_t* o = reinterpret_cast<uint32_t*>(op);
+            for (int q = tid; q < n_pixels / 4; q += 256) {
+                const float4 hv = __ldcs(h4 + q);
+                const float hs[4] = {hv.x, hv.y, hv.z, hv.w};
+                float gk[4] = {0.f, 0.f, 0.f, 0.f};
+                if (img != nullptr) {
+                    const uint32_t w0 = __ldg(w + 3 * q), w1 = __ldg(w + 3 * q + 1), w2 = __ldg(w + 3 * q + 2);
+                    gk[0] = s_gray[luma15(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u)];
+                    gk[1] = s_gray[luma15(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u)];
+                    gk[2] = s_gray[luma15((w1 >> 16) & 255u, w1 >> 24, w2 & 255u)];
+                    gk[3] = s_gray[luma15((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24)];
+                }
+                uint32_t c[12];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ji = min(max(static_cast<int>(__fmul_rn(hs[k], 256.f)), 0), 255);   // Colormap: int(x * N)
+                    const float4 jet = s_jet[ji];
+                    c[3 * k] = static_cast<uint32_t>(__float2int_rn(__fadd_rn(jet.x, gk[k]))) & 255u;
+                    c[3 * k + 1] = static_cast<uint32_t>(__float2int_rn(__fadd_rn(jet.y, gk[k]))) & 255u;
+                    c[3 * k + 2] = static_cast<uint32_t>(__float2int_rn(__fadd_rn(jet.z, gk[k]))) & 255u;
+                }
+                __stcs(o + 3 * q, c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24));
+                __stcs(o + 3 * q + 1, c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24));
+                __stcs(o + 3 * q + 2, c[8] | (c[9] << 8) | (c[10] << 16) | (c[11] << 24));
             }
-            uint8_t* o = rgb_out + (f * n_pixels + p) * 3;
-            o[0] = static_cast<uint8_t>(__float2int_rn(r));
-            o[1] = static_cast<uint8_t>(__float2int_rn(g));
-            o[2] = static_cast<uint8_t>(__float2int_rn(b));
+        } else {
+            for (int p = tid; p < n_pixels; p += 256) {
+                const int ji = min(max(static_cast<int>(__fmul_rn(hp[p], 256.f)), 0), 255);
+                const float4 jet = s_jet[ji];
+                const float gk = img ? s_gray[luma15(img[3 * p], img[3 * p + 1], img[3 * p + 2])] : 0.f;
+                op[3 * p] = static_cast<uint8_t>(__float2int_rn(__fadd_rn(jet.x, gk)));
+                op[3 * p + 1] = static_cast<uint8_t>(__float2int_rn(__fadd_rn(jet.y, gk)));
+                op[3 * p + 2] = static_cast<uint8_t>(__float2int_rn(__fadd_rn(jet.z, gk)));
+            }
         }
     }
 }

@@ -577,6 +577,14 @@ def test_overlay_bit_exact_vs_oracle(path, golden, torch):
         assert np.array_equal(got[i], oracle.overlay(heat[i], frames[i], lut))
     bare = path.overlay(heat)
     assert np.array_equal(bare[0], oracle.overlay(heat[0], None, lut))
+    # odd geometry takes the scalar kernel: 15 x 17 = 255 pixels per frame, heat values on and past both ends
+    small = rng.random((3, 15, 17)).astype(np.float32)
+    small[0, 0, :4] = [0.0, 1.0, 1.5, -0.25]
+    small_frames = rng.integers(0, 256, (3, 15, 17, 3), dtype=np.uint8)
+    got = path.overlay(small, small_frames)
+    for i in range(3):
+        assert np.array_equal(got[i], oracle.overlay(small[i], small_frames[i], lut))
+    assert np.array_equal(path.overlay(small)[1], oracle.overlay(small[1], None, lut))
     dev = path.overlay(torch.from_numpy(heat).cuda(), torch.from_numpy(frames).cuda(), alpha=0.5)
     assert dev.is_cuda and np.array_equal(dev.cpu().numpy()[0], oracle.overlay(heat[0], frames[0], lut, 0.5))
 
