@@ -424,9 +424,14 @@ int launch_heatmap(aig_handle* h, const double* d_energy, int64_t n_frames, int 
             AIG_CK(cudaFuncSetAttribute(heatmap_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             AIG_CK(cudaFuncSetAttribute(heatmap_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             AIG_CK(cudaFuncSetAttribute(heatmap_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            // the kernels use no L1-cached global loads worth the space: give all of it to shared memory so 4 CTAs fit
+            cudaFuncSetAttribute(heatmap_fast_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(heatmap_fast_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(heatmap_fast_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
             h->heat_attr_set = true;
         }
-        const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (fast_smem + 12 * 1024))));
+        // 228 KiB per SM; each CTA also holds ~7.3 KiB of static shared memory and 1 KiB of system reserve
+        const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(6, (228 * 1024) / (fast_smem + 9 * 1024))));
         const int grid = frames_grid(h, n_frames, per_sm);
         const bool aligned = (reinterpret_cast<uintptr_t>(d_heat) & 15u) == 0;
         if (aligned && out_w % 4 == 0)

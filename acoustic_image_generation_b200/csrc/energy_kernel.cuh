@@ -513,19 +513,31 @@ heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int o
     for (int d = tid; d < out_h; d += kHeatThreads) {
         int i0, i1; double w;
         linear_tap(d, kFrameH, out_h, &i0, &i1, &w);
-        s_y0[d] = i0 | (i1 << 16); s_wy[d] = static_cast<float>(w);
+        // Bit 31 marks the first and last output row of every source-row pair.  fmaf(r1 - r0, wy, r0) is monotonic in
+        // wy, and wy grows with y inside a pair, so the image's min / max are attained on the marked rows: pass 1 visits
+        // only those (about 2 * 37 of out_h rows) and finds exactly the values a full pass would.
+        int p0, p1, n0, n1; double wn;
+        linear_tap(max(d - 1, 0), kFrameH, out_h, &p0, &p1, &wn);
+        linear_tap(min(d + 1, out_h - 1), kFrameH, out_h, &n0, &n1, &wn);
+        const bool edge = d == 0 || d == out_h - 1 || p0 != i0 || p1 != i1 || n0 != i0 || n1 != i1;
+        s_y0[d] = i0 | (i1 << 16) | (edge ? 0x80000000 : 0); s_wy[d] = static_cast<float>(w);
     }
+    constexpr int kPerThread = (kFramePixels + kHeatThreads - 1) / kHeatThreads;
+    double e[kPerThread];                                          // this thread's energies of the frame being started
+    auto fetch = [&](long long frame) {
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i) {
+            const int p = tid + i * kHeatThreads;
+            e[i] = (frame < n_frames && p < kFramePixels) ? __ldcs(energy + frame * kFramePixels + p) : CUDART_NAN;
+        }
+    };
+    fetch(blockIdx.x);
     for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
         __syncthreads();
         // frame min / max in float64, then t = (e - min) / (max - min) as float32
-        double e[(kFramePixels + kHeatThreads - 1) / kHeatThreads];
         double lo = CUDART_INF, hi = -CUDART_INF;
 #pragma unroll
-        for (int i = 0; i < (kFramePixels + kHeatThreads - 1) / kHeatThreads; ++i) {
-            const int p = tid + i * kHeatThreads;
-            e[i] = p < kFramePixels ? energy[frame * kFramePixels + p] : CUDART_NAN;
-            lo = fmin(lo, e[i]); hi = fmax(hi, e[i]);
-        }
+        for (int i = 0; i < kPerThread; ++i) { lo = fmin(lo, e[i]); hi = fmax(hi, e[i]); }
         lo = warp_min(lo); hi = warp_max(hi);
         if (lane == 0) { s_red64[0][warp] = lo; s_red64[1][warp] = hi; }
         __syncthreads();
@@ -538,6 +550,7 @@ heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int o
             const int p = tid + i * kHeatThreads;
             if (p < kFramePixels) s_t[p] = span > 0.0 ? static_cast<float>((e[i] - lo) / span) : 0.f;
         }
+        fetch(frame + gridDim.x);                                  // next frame's energies arrive during the passes below
         __syncthreads();
         // horizontal pass, once: warps own source rows, lanes walk the output columns
         for (int r = warp; r < kFrameH; r += kHeatThreads / 32) {
@@ -554,9 +567,10 @@ heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int o
         float mn = CUDART_INF_F, mx = -CUDART_INF_F;
         for (int y = warp; y < out_h; y += kHeatThreads / 32) {
             const int yi = s_y0[y];
+            if (yi >= 0) continue;                                   // interior row of its pair: cannot hold an extreme
             const float wy = s_wy[y];
             const float* r0 = s_rows + (yi & 0xffff) * out_w;
-            const float* r1 = s_rows + (yi >> 16) * out_w;
+            const float* r1 = s_rows + ((yi >> 16) & 0x7fff) * out_w;
             for (int x = lane * VEC; x < out_w; x += 32 * VEC) HeatVec<VEC>::lerp_minmax(r0, r1, x, wy, mn, mx);
         }
         mn = warp_min(mn); mx = warp_max(mx);
@@ -573,7 +587,7 @@ heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int o
             const int yi = s_y0[y];
             const float wy = s_wy[y];
             const float* r0 = s_rows + (yi & 0xffff) * out_w;
-            const float* r1 = s_rows + (yi >> 16) * out_w;
+            const float* r1 = s_rows + ((yi >> 16) & 0x7fff) * out_w;
             float* o = dst + static_cast<long long>(y) * out_w;
             for (int x = lane * VEC; x < out_w; x += 32 * VEC) HeatVec<VEC>::lerp_store(r0, r1, x, wy, mn, inv, o);
         }

@@ -276,6 +276,22 @@ def test_heatmap_matches_oracle_and_cv2_golden(path, golden, shape, exact):
         assert np.abs(got[0] - ref).max() <= HEAT_TOL
 
 
+@pytest.mark.parametrize('shape', [(224, 298), (20, 30), (500, 37), (2048, 5), (37, 49)])
+def test_heatmap_extremes_on_rough_maps(path, shape):
+    """The fast kernel looks for the image's min / max only on the first and last output row of each source-row pair
+    (bilinear interpolation is monotonic in between): on rough maps, where extremes sit anywhere, the result must still
+    span exactly [0, ~1] and match the oracle."""
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    e = rng.random((6, 36, 48)) ** 4
+    e[1, 35, :] += 3.0          # extremes on the clamped border rows
+    e[2, 0, 0] = -2.0
+    got = path.heatmap(e, *shape)
+    for i in range(6):
+        want = oracle.heatmap(e[i], *shape)
+        assert np.abs(got[i] - want).max() <= 2e-6
+        assert got[i].min() == 0.0 and abs(float(got[i].max()) - 1.0) <= 1e-6
+
+
 @pytest.mark.parametrize('shape', [(224, 298), (224, 224), (36, 48), (73, 95)])
 def test_resize_mask_bit_exact(path, golden, shape):
     e = golden('energy')
