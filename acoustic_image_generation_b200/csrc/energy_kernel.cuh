@@ -24,9 +24,12 @@ __constant__ double c_dct[kFilterNum * kMfccNum] = AIG_REF_DCT;      // [24][12]
 __constant__ double c_lifter[kMfccNum] = AIG_REF_LIFTER;
 __constant__ double c_mfnorm = AIG_REF_MFNORM;
 
-constexpr int kEnergyThreads = 192;                                  // 9 pixels per thread
-constexpr int kPixelsPerThread = kFramePixels / kEnergyThreads;
-static_assert(kFramePixels % kEnergyThreads == 0, "pixels must divide evenly over the CTA");
+// 128 threads = one warp per SM sub-partition, so four CTAs per SM may use 128 registers each (the per-pixel float64
+// chain needs ~120; with 192-thread CTAs the uneven warp split capped it at 96 and it spilled).  13.5 pixels per thread:
+// in the 14th round the upper two warps idle.
+constexpr int kEnergyThreads = 128;
+constexpr int kPixelsPerThread = (kFramePixels + kEnergyThreads - 1) / kEnergyThreads;
+static_assert(kFramePixels % 64 == 0, "whole warps drop out of the last round");
 
 // NumPy pairwise-sum leaves for n = 1728: 1728 -> 864 -> 432 -> 216 -> (104, 112); every leaf is
 // summed with 8 strided accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)).
@@ -245,7 +248,7 @@ __device__ __forceinline__ double frame_mean(const double* s_map, double (*s_par
     return *s_mean;
 }
 
-__global__ void __launch_bounds__(kEnergyThreads, 3)
+__global__ void __launch_bounds__(kEnergyThreads, 4)
 energy_kernel(const float* __restrict__ images, long long n_frames, int normalize_first,
               float* __restrict__ scaled_out, double* __restrict__ energy_out,
               uint8_t* __restrict__ mask_out, double* __restrict__ mean_out) {
@@ -287,11 +290,18 @@ energy_kernel(const float* __restrict__ images, long long n_frames, int normaliz
         }
 
         const FrameNorm norm(lo, range);
+        // software pipeline: pixel i + 1 is in flight while pixel i goes through its ~600 float64 operations
+        const float4* first = reinterpret_cast<const float4*>(img + tid * kMfccNum);
+        float4 na = __ldg(first), nb = __ldg(first + 1), nc = __ldg(first + 2);
 #pragma unroll 1
         for (int i = 0; i < kPixelsPerThread; ++i) {
             const int p = tid + i * kEnergyThreads;
-            const float4* src = reinterpret_cast<const float4*>(img + p * kMfccNum);
-            const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+            if (p >= kFramePixels) break;
+            const float4 a = na, b = nb, c = nc;
+            if (p + kEnergyThreads < kFramePixels) {
+                const float4* src = reinterpret_cast<const float4*>(img + (p + kEnergyThreads) * kMfccNum);
+                na = __ldg(src); nb = __ldg(src + 1); nc = __ldg(src + 2);
+            }
             float x[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
             unsigned int rare;
             double en = pixel_energy(x, normalize_first != 0, norm, s_exp, rare);
