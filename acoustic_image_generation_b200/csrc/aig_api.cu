@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/aig.h"
+#include "host_staging.h"
 #include "aig_common.cuh"
 #include "energy_kernel.cuh"
 #include "frontend_kernel.cuh"
@@ -132,6 +133,9 @@ struct aig_handle {
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
     double2* d_twiddle = nullptr;       // exp(-2*pi*i*k/1024), k < 512 (aig_power_spectrum)
+    // pageable host inputs are staged through a pinned ring by a few copy threads (host_staging.h)
+    aig::StagedUploader uploader;
+    int host_copy_threads = -1;         // -1: min(4, hardware threads / 2); 0: leave pageable copies to the driver
     // NCCL communicator (resolved with dlopen; see aig_comm_init)
     void* comm = nullptr;
     int comm_world = 1;
@@ -205,6 +209,28 @@ void* scratch(aig_handle* h, size_t bytes) {
     return p;
 }
 
+// Host -> device copy of `bytes` on `stream`.  Large pageable sources go through the handle's StagedUploader (4-5x the
+// driver's own pageable path); pinned sources and small copies are plain cudaMemcpyAsync.
+constexpr size_t kStagedUploadMinBytes = size_t(8) << 20;
+bool use_host_staging(aig_handle* h, size_t bytes, MemKind kind);
+cudaError_t upload_async(aig_handle* h, void* dst, const void* src, size_t bytes, MemKind kind, cudaStream_t stream) {
+    if (use_host_staging(h, bytes, kind)) return h->uploader.upload(dst, src, bytes, stream);
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+}
+
+// Device -> host copy after the work enqueued on `stream`; large pageable destinations are drained through the same
+// pinned ring (returns with the data in place), everything else is a plain asynchronous copy.
+bool use_host_staging(aig_handle* h, size_t bytes, MemKind kind) {
+    if (kind != kHostPageable || bytes < kStagedUploadMinBytes || h->host_copy_threads == 0) return false;
+    int threads = h->host_copy_threads;
+    if (threads < 0) threads = static_cast<int>(std::min(4u, std::max(1u, std::thread::hardware_concurrency() / 2)));   // 4 fill the link
+    return h->uploader.start(threads);
+}
+cudaError_t download(aig_handle* h, void* dst, const void* src, size_t bytes, MemKind kind, cudaStream_t stream) {
+    if (use_host_staging(h, bytes, kind)) return h->uploader.download(dst, src, bytes, stream);
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream);
+}
+
 // ---- host/device staging of small and medium buffers ----------------------------------------------
 struct Io {
     aig_handle* h;
@@ -217,11 +243,12 @@ struct Io {
     template <typename T>
     const T* in(const T* p, size_t count) {
         if (p == nullptr) return nullptr;
-        if (classify(p) == kDevice) return p;
+        const MemKind kind = classify(p);
+        if (kind == kDevice) return p;
         any_host = true;
         void* d = scratch(h, count * sizeof(T));
         if (!d) { failed = true; return nullptr; }
-        if (cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
+        if (upload_async(h, d, p, count * sizeof(T), kind, h->stream) != cudaSuccess) {
             h->fail_cuda(cudaGetLastError(), "cudaMemcpyAsync(H2D)");
             failed = true;
             return nullptr;
@@ -250,7 +277,7 @@ struct Io {
     int finish() {
         if (failed) return h->err.empty() ? h->fail(AIG_ERR_ALLOC, "staging failed") : AIG_ERR_ALLOC;
         for (auto& o : outs)
-            AIG_CK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, h->stream));
+            AIG_CK(download(h, o.host, o.dev, o.bytes, classify(o.host), h->stream));
         if (any_host) AIG_CK(cudaStreamSynchronize(h->stream));
         return AIG_OK;
     }
@@ -517,6 +544,7 @@ int stream_host_rows(aig_handle* h, const float* host, int64_t n_rows, int row_f
     const size_t chunk_bytes = static_cast<size_t>(rows_per_chunk) * row_floats * sizeof(float);
     float* buf[2] = {static_cast<float*>(scratch(h, chunk_bytes)), static_cast<float*>(scratch(h, chunk_bytes))};
     if (!buf[0] || !buf[1]) return AIG_ERR_ALLOC;
+    const MemKind kind = classify(host);
     // the scratch may still be in use by earlier work on h->stream
     AIG_CK(cudaEventRecord(h->ev_consumed[0], h->stream));
     AIG_CK(cudaEventRecord(h->ev_consumed[1], h->stream));
@@ -524,8 +552,8 @@ int stream_host_rows(aig_handle* h, const float* host, int64_t n_rows, int row_f
     for (int64_t row = 0; row < n_rows; row += rows_per_chunk, slot ^= 1) {
         const int64_t rows = std::min(rows_per_chunk, n_rows - row);
         AIG_CK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0));
-        AIG_CK(cudaMemcpyAsync(buf[slot], host + row * row_floats, static_cast<size_t>(rows) * row_floats * sizeof(float),
-                               cudaMemcpyHostToDevice, h->copy_stream));
+        AIG_CK(upload_async(h, buf[slot], host + row * row_floats, static_cast<size_t>(rows) * row_floats * sizeof(float),
+                            kind, h->copy_stream));
         AIG_CK(cudaEventRecord(h->ev_copied[slot], h->copy_stream));
         AIG_CK(cudaStreamWaitEvent(h->stream, h->ev_copied[slot], 0));
         int rc = consume(buf[slot], row, rows);
@@ -611,6 +639,7 @@ int aig_destroy(aig_handle* h) {
     if (h == nullptr) return AIG_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    h->uploader.shutdown();
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
     for (int i = 0; i < 4; ++i) if (h->ev_chain[i]) cudaEventDestroy(h->ev_chain[i]);
@@ -659,6 +688,10 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
     } else if (key == "fused_variant") {
         if (value < 0 || value >= kNumFusedVariants) return h->fail(AIG_ERR_ARGUMENT, "unknown fused kernel variant %lld", (long long)value);
         h->fused_variant = static_cast<int>(value);
+    } else if (key == "host_copy_threads") {
+        if (value < -1 || value > 64) return h->fail(AIG_ERR_ARGUMENT, "host_copy_threads out of range (-1 auto, 0 off, 1..64)");
+        if (static_cast<int>(value) != h->host_copy_threads) h->uploader.shutdown();
+        h->host_copy_threads = static_cast<int>(value);
     } else if (key == "chain_energy_ctas_per_sm") {
         if (value < 1 || value > 16) return h->fail(AIG_ERR_ARGUMENT, "chain_energy_ctas_per_sm out of range");
         h->chain_energy_ctas_per_sm = static_cast<int>(value);
@@ -785,7 +818,7 @@ int aig_mfcc(aig_handle* h, const float* power, int64_t n_rows, float* mfcc_out,
         if (rc != AIG_OK) return rc;
     }
     if (!out_dev)
-        AIG_CK(cudaMemcpyAsync(mfcc_out, d_out, static_cast<size_t>(n_rows) * out_floats * 4, cudaMemcpyDeviceToHost, h->stream));
+        AIG_CK(download(h, mfcc_out, d_out, static_cast<size_t>(n_rows) * out_floats * 4, classify(mfcc_out), h->stream));
     if (!out_dev || !in_dev) AIG_CK(cudaStreamSynchronize(h->stream));
     return AIG_OK;
 }
@@ -952,10 +985,14 @@ int aig_mfcc_energy(aig_handle* h, const float* power, int64_t n_frames, int fli
             const size_t per_frame[4] = {kFrameValues * sizeof(float), kFramePixels * sizeof(double), kFramePixels, sizeof(double)};
             void* const user[4] = {mfcc_out, energy_out, mask_out, mean_out};
             void* const devp[4] = {d_mfcc, d_energy, d_mask, d_mean};
+            // Pinned destinations only: a copy into pageable memory would block this thread on the chunk's kernel and
+            // stall the uploads behind it; those results go out through the staging ring at the end (io.finish()).
             for (int i = 0; i < 4; ++i)
-                if (user[i] != nullptr && devp[i] != user[i])
+                if (user[i] != nullptr && devp[i] != user[i] && classify(user[i]) == kHostPinned) {
                     host_outs.push_back({static_cast<char*>(user[i]), static_cast<char*>(devp[i]), per_frame[i]});
-            io.outs.clear();                       // handled chunk by chunk below
+                    io.outs.erase(std::remove_if(io.outs.begin(), io.outs.end(),
+                                                 [&](const Io::Pending& pd) { return pd.host == user[i]; }), io.outs.end());
+                }
             d2h_overlapped = !host_outs.empty();
         }
         const int64_t chunk_rows = host_chunk_rows(kFramePixels, kFftLen);

@@ -1,0 +1,275 @@
+// Host -> device upload of ordinary (pageable) memory at link speed.
+//
+// The reference hands this path NumPy arrays that TensorFlow's py_func allocated (dataloader/outdoor_data_mfcc.py:788):
+// pageable memory.  cudaMemcpyAsync from pageable memory is staged by the driver on one thread and reaches 8-12 GB/s on
+// the B200 boxes (tools/pageable_probe.py) against 55 GB/s for pinned memory - the whole end-to-end call is then 4-5x
+// slower than the link allows.  StagedUploader does the staging itself: a few host threads copy 1 MiB pieces of the
+// caller's array into a ring of pinned slots while the calling thread issues one asynchronous H2D copy per filled slot,
+// in order, on the given stream.  download() is the mirror image for results returned into pageable arrays: D2H copies
+// land in the pinned slots and the threads move them on into the caller's array.  CUDA is only ever called from the
+// calling thread.
+//
+// Host-side runtime code, no device code: the kernels never see the difference.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace aig {
+
+class StagedUploader {   // both directions; named after its first job
+   public:
+    static constexpr size_t kSlotBytes = size_t(1) << 20;
+    static constexpr int kSlots = 32;
+
+    StagedUploader() = default;
+    StagedUploader(const StagedUploader&) = delete;
+    StagedUploader& operator=(const StagedUploader&) = delete;
+    ~StagedUploader() { shutdown(); }
+
+    // Lazily allocates the pinned ring and starts `threads` workers.  Returns false if pinned memory is unavailable.
+    bool start(int threads) {
+        if (ready_) return true;
+        if (threads < 1) return false;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&ring_), kSlotBytes * kSlots, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            ring_ = nullptr;
+            return false;
+        }
+        for (int s = 0; s < kSlots; ++s) {
+            if (cudaEventCreateWithFlags(&slot_done_[s], cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+            slot_busy_[s] = false;
+        }
+        stop_ = false;
+        for (int t = 0; t < threads; ++t) workers_.emplace_back([this] { worker(); });
+        ready_ = true;
+        return true;
+    }
+
+    void shutdown() {
+        if (!workers_.empty()) {
+            {
+                std::lock_guard<std::mutex> lock(m_);
+                stop_ = true;
+            }
+            cv_.notify_all();
+            for (auto& w : workers_) w.join();
+            workers_.clear();
+        }
+        if (ring_ != nullptr) {
+            for (int s = 0; s < kSlots; ++s)
+                if (slot_done_[s]) { cudaEventSynchronize(slot_done_[s]); cudaEventDestroy(slot_done_[s]); slot_done_[s] = nullptr; }
+            cudaFreeHost(ring_);
+            ring_ = nullptr;
+        }
+        ready_ = false;
+    }
+
+    bool ready() const { return ready_; }
+    int threads() const { return static_cast<int>(workers_.size()); }
+
+    // Copies bytes from pageable `src` to device `dst`, ordered on `stream`.  Returns once every piece has been read
+    // from `src` and its H2D copy enqueued (the caller may then reuse `src`; the device side is stream-ordered).
+    cudaError_t upload(void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+        if (bytes == 0) return cudaSuccess;
+        const int64_t pieces = static_cast<int64_t>((bytes + kSlotBytes - 1) / kSlotBytes);
+        {
+            std::unique_lock<std::mutex> lock(m_);
+            cv_idle_.wait(lock, [this] { return active_ == 0; });     // a late waker of the previous job has left it
+            src_ = static_cast<const char*>(src);
+            user_dst_ = nullptr;
+            bytes_ = bytes;
+            pieces_ = pieces;
+            next_.store(0, std::memory_order_relaxed);
+            freed_.store(0, std::memory_order_relaxed);
+            for (int s = 0; s < kSlots; ++s) filled_[s].store(-1, std::memory_order_relaxed);
+            ++generation_;
+        }
+        cv_.notify_all();
+        // slots of an earlier upload may still be in flight on the DMA engine: their events gate the first reuse
+        cudaError_t status = cudaSuccess;
+        int64_t issued = 0, freed = 0;
+        // piece i may be written into its slot once piece i - kSlots has left it; for the first kSlots pieces that is
+        // the previous upload's copy out of the same slot
+        int64_t primed = 0;
+        const int64_t first_lap = std::min<int64_t>(pieces, kSlots);
+        unsigned spins = 0;
+        while (issued < pieces) {
+            bool progressed = false;
+            // release slots whose copies have completed, in order
+            while (primed < first_lap) {
+                const int s = static_cast<int>(primed % kSlots);
+                if (slot_busy_[s] && cudaEventQuery(slot_done_[s]) == cudaErrorNotReady) break;
+                slot_busy_[s] = false;
+                ++primed;
+                progressed = true;
+            }
+            while (freed < issued && cudaEventQuery(slot_done_[freed % kSlots]) != cudaErrorNotReady) {
+                slot_busy_[freed % kSlots] = false;
+                ++freed;
+                progressed = true;
+            }
+            // a worker may fill piece i when i < primed (first lap) and i - kSlots < freed (later laps)
+            freed_.store(primed < first_lap ? primed : freed + kSlots, std::memory_order_release);
+            const int s = static_cast<int>(issued % kSlots);
+            if (filled_[s].load(std::memory_order_acquire) == issued) {
+                const size_t off = static_cast<size_t>(issued) * kSlotBytes;
+                const size_t len = std::min(kSlotBytes, bytes - off);
+                if (status == cudaSuccess) {
+                    status = cudaMemcpyAsync(static_cast<char*>(dst) + off, ring_ + s * kSlotBytes, len, cudaMemcpyHostToDevice, stream);
+                    if (status == cudaSuccess) status = cudaEventRecord(slot_done_[s], stream);
+                    slot_busy_[s] = status == cudaSuccess;
+                }
+                ++issued;
+                progressed = true;
+            }
+            if (!progressed) {
+                if (++spins > 64) { std::this_thread::yield(); spins = 0; }
+            } else {
+                spins = 0;
+            }
+        }
+        // park the workers (they leave the job when next_ runs past pieces_) and wait until all have left it
+        std::unique_lock<std::mutex> lock(m_);
+        cv_idle_.wait(lock, [this] { return active_ == 0; });
+        pieces_ = 0;
+        if (status == cudaSuccess) cudaGetLastError();     // cudaEventQuery's cudaErrorNotReady is not an error
+        return status;
+    }
+
+    // Copies bytes from device `src` to pageable `dst` after the work already enqueued on `stream`.  Returns when the data
+    // is in `dst`.
+    cudaError_t download(void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+        if (bytes == 0) return cudaSuccess;
+        const int64_t pieces = static_cast<int64_t>((bytes + kSlotBytes - 1) / kSlotBytes);
+        {
+            std::unique_lock<std::mutex> lock(m_);
+            cv_idle_.wait(lock, [this] { return active_ == 0; });
+            src_ = nullptr;
+            user_dst_ = static_cast<char*>(dst);
+            bytes_ = bytes;
+            pieces_ = pieces;
+            next_.store(0, std::memory_order_relaxed);
+            freed_.store(0, std::memory_order_relaxed);              // download: pieces [0, freed_) have arrived in their slots
+            for (int s = 0; s < kSlots; ++s) filled_[s].store(-1, std::memory_order_relaxed);   // download: piece drained from slot
+            ++generation_;
+        }
+        cv_.notify_all();
+        cudaError_t status = cudaSuccess;
+        int64_t issued = 0, arrived = 0, drained = 0;
+        unsigned spins = 0;
+        while (drained < pieces) {
+            bool progressed = false;
+            while (arrived < issued && cudaEventQuery(slot_done_[arrived % kSlots]) != cudaErrorNotReady) {
+                slot_busy_[arrived % kSlots] = false;
+                ++arrived;
+                progressed = true;
+            }
+            freed_.store(arrived, std::memory_order_release);
+            while (drained < arrived && filled_[drained % kSlots].load(std::memory_order_acquire) == drained) {
+                ++drained;
+                progressed = true;
+            }
+            if (issued < pieces && issued < drained + kSlots) {
+                const int s = static_cast<int>(issued % kSlots);
+                // first lap: an earlier upload may still be reading this slot
+                if (!(slot_busy_[s] && cudaEventQuery(slot_done_[s]) == cudaErrorNotReady)) {
+                    const size_t off = static_cast<size_t>(issued) * kSlotBytes;
+                    const size_t len = std::min(kSlotBytes, bytes - off);
+                    if (status == cudaSuccess) {
+                        status = cudaMemcpyAsync(ring_ + s * kSlotBytes, static_cast<const char*>(src) + off, len, cudaMemcpyDeviceToHost, stream);
+                        if (status == cudaSuccess) status = cudaEventRecord(slot_done_[s], stream);
+                    }
+                    slot_busy_[s] = status == cudaSuccess;
+                    if (status != cudaSuccess) {                        // nothing will arrive: let the workers run through
+                        failed_.store(true, std::memory_order_release);
+                    }
+                    ++issued;
+                    progressed = true;
+                }
+            }
+            if (failed_.load(std::memory_order_acquire)) break;
+            if (!progressed) {
+                if (++spins > 64) { std::this_thread::yield(); spins = 0; }
+            } else {
+                spins = 0;
+            }
+        }
+        if (failed_.load(std::memory_order_acquire)) {
+            next_.store(pieces, std::memory_order_relaxed);             // no more claims
+            freed_.store(pieces, std::memory_order_release);            // release any waiter (it copies stale bytes; the call fails anyway)
+        }
+        std::unique_lock<std::mutex> lock(m_);
+        cv_idle_.wait(lock, [this] { return active_ == 0; });
+        pieces_ = 0;
+        failed_.store(false, std::memory_order_relaxed);
+        if (status == cudaSuccess) cudaGetLastError();
+        return status;
+    }
+
+   private:
+    void worker() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                cv_.wait(lock, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+                ++active_;
+            }
+            for (;;) {
+                const int64_t i = next_.fetch_add(1, std::memory_order_relaxed);
+                if (i >= pieces_) break;
+                unsigned spins = 0;
+                while (freed_.load(std::memory_order_acquire) <= i) {       // upload: slot not free yet; download: piece not here yet
+                    if (++spins > 64) { std::this_thread::yield(); spins = 0; }
+                }
+                const size_t off = static_cast<size_t>(i) * kSlotBytes;
+                const size_t len = std::min(kSlotBytes, bytes_ - off);
+                const int s = static_cast<int>(i % kSlots);
+                if (user_dst_ == nullptr) std::memcpy(ring_ + s * kSlotBytes, src_ + off, len);     // upload: fill the slot
+                else std::memcpy(user_dst_ + off, ring_ + s * kSlotBytes, len);                    // download: drain it
+                filled_[s].store(i, std::memory_order_release);
+            }
+            {
+                std::lock_guard<std::mutex> lock(m_);
+                --active_;
+            }
+            cv_idle_.notify_all();
+        }
+    }
+
+    bool ready_ = false;
+    char* ring_ = nullptr;
+    cudaEvent_t slot_done_[kSlots] = {};
+    bool slot_busy_[kSlots] = {};
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, cv_idle_;
+    bool stop_ = false;
+    uint64_t generation_ = 0;
+    int active_ = 0;
+    // current job
+    const char* src_ = nullptr;              // upload: the caller's array
+    char* user_dst_ = nullptr;               // download: the caller's array (nullptr selects upload in the workers)
+    std::atomic<bool> failed_{false};
+    size_t bytes_ = 0;
+    int64_t pieces_ = 0;
+    std::atomic<int64_t> next_{0};
+    std::atomic<int64_t> freed_{0};          // pieces [0, freed_) may be written into their slots
+    std::atomic<int64_t> filled_[kSlots];    // index of the piece a slot currently holds, -1 when stale
+};
+
+}  // namespace aig

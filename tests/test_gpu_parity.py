@@ -606,6 +606,43 @@ def test_overlay_bit_exact_vs_oracle(path, golden, torch):
 
 
 # ----------------------------------------------------------------------------------------------
+# host staging: ordinary (pageable) NumPy inputs go up through the pinned ring of host_staging.h
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('threads', [-1, 0, 1, 3])
+def test_pageable_inputs_match_device_inputs(path, torch, threads):
+    """Same bits whether the spectra arrive as device tensors, pinned arrays or pageable arrays staged by 0..n copy
+    threads; sizes below, at and above the 8 MiB staging threshold, the 4 MiB slot size and the 64 MiB device chunk."""
+    path.set_option('host_copy_threads', threads)
+    try:
+        for n in (1, 3, 19, 40):
+            power = synth.power_frames(n, 5, 'chi2')                     # pageable
+            want = [t.cpu().numpy() for t in path.mfcc_energy(torch.from_numpy(power).cuda(), flip=True)]
+            for _ in range(2):                                           # second call reuses ring slots still in flight
+                got = path.mfcc_energy(power, flip=True)
+                for a, b in zip(got, want):
+                    assert np.array_equal(a, b, equal_nan=True)
+            rows = path.mfcc_rows(power.reshape(-1, 512)[:-7])           # ragged row count through aig_mfcc
+            assert np.array_equal(rows, oracle_free_rows(path, torch, power.reshape(-1, 512)[:-7]))
+        big = synth.power_frames(110, 6, 'chi2')                         # 9.1 MB of MFCC come back through the ring too
+        want = [t.cpu().numpy() for t in path.mfcc_energy(torch.from_numpy(big).cuda(), flip=True)]
+        for a, b in zip(path.mfcc_energy(big, flip=True), want):
+            assert np.array_equal(a, b, equal_nan=True)
+        energies = np.random.default_rng(3).random((70, 36, 48))         # 18.7 MB of heat maps into a pageable array
+        assert np.array_equal(path.heatmap(energies), path.heatmap(torch.from_numpy(energies).cuda()).cpu().numpy())
+        images = synth.sigmoid_images(300, 2)                            # 24.9 MB through the generic Io staging
+        e_dev, m_dev = path.energy(torch.from_numpy(images).cuda())
+        e, m = path.energy(images)
+        assert np.array_equal(e, e_dev.cpu().numpy()) and np.array_equal(m, m_dev.cpu().numpy())
+    finally:
+        path.set_option('host_copy_threads', -1)
+
+
+def oracle_free_rows(path, torch, rows):
+    """aig_mfcc on a device copy of the same rows (no host staging involved)."""
+    return path.mfcc_rows(torch.from_numpy(np.ascontiguousarray(rows)).cuda()).cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------------
 # error behaviour of the C ABI (negative status + message, never a crash, never a CPU fallback)
 # ----------------------------------------------------------------------------------------------
 def test_argument_errors_are_reported(path):
