@@ -52,7 +52,11 @@ class StagedUploader {   // both directions; named after its first job
             slot_busy_[s] = false;
         }
         stop_ = false;
-        for (int t = 0; t < threads; ++t) workers_.emplace_back([this] { worker(); });
+        try {
+            for (int t = 0; t < threads; ++t) workers_.emplace_back([this] { worker(); });
+        } catch (...) {                       // thread creation refused: run with the workers that did start, if any
+            if (workers_.empty()) return false;
+        }
         ready_ = true;
         return true;
     }
