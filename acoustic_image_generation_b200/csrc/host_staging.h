@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
@@ -29,6 +30,14 @@ class StagedUploader {   // both directions; named after its first job
    public:
     static constexpr size_t kSlotBytes = size_t(1) << 20;
     static constexpr int kSlots = 32;
+    static constexpr int kLingerMicros = 400;
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
 
     StagedUploader() = default;
     StagedUploader(const StagedUploader&) = delete;
@@ -39,13 +48,13 @@ class StagedUploader {   // both directions; named after its first job
     bool start(int threads) {
         if (ready_) return true;
         if (threads < 1) return false;
-        if (cudaHostAlloc(reinterpret_cast<void**>(&ring_), kSlotBytes * kSlots, cudaHostAllocDefault) != cudaSuccess) {
+        if (ring_ == nullptr && cudaHostAlloc(reinterpret_cast<void**>(&ring_), kSlotBytes * kSlots, cudaHostAllocDefault) != cudaSuccess) {
             cudaGetLastError();
             ring_ = nullptr;
             return false;
         }
         for (int s = 0; s < kSlots; ++s) {
-            if (cudaEventCreateWithFlags(&slot_done_[s], cudaEventDisableTiming) != cudaSuccess) {
+            if (slot_done_[s] == nullptr && cudaEventCreateWithFlags(&slot_done_[s], cudaEventDisableTiming) != cudaSuccess) {
                 cudaGetLastError();
                 return false;
             }
@@ -66,6 +75,7 @@ class StagedUploader {   // both directions; named after its first job
             {
                 std::lock_guard<std::mutex> lock(m_);
                 stop_ = true;
+                generation_hint_.store(~uint64_t(0), std::memory_order_release);
             }
             cv_.notify_all();
             for (auto& w : workers_) w.join();
@@ -99,6 +109,7 @@ class StagedUploader {   // both directions; named after its first job
             freed_.store(0, std::memory_order_relaxed);
             for (int s = 0; s < kSlots; ++s) filled_[s].store(-1, std::memory_order_relaxed);
             ++generation_;
+            generation_hint_.store(generation_, std::memory_order_release);
         }
         cv_.notify_all();
         // slots of an earlier upload may still be in flight on the DMA engine: their events gate the first reuse
@@ -108,6 +119,7 @@ class StagedUploader {   // both directions; named after its first job
         // the previous upload's copy out of the same slot
         int64_t primed = 0;
         const int64_t first_lap = std::min<int64_t>(pieces, kSlots);
+        int64_t mine = -1;                       // piece claimed by the calling thread itself, waiting for its slot
         unsigned spins = 0;
         while (issued < pieces) {
             bool progressed = false;
@@ -136,6 +148,20 @@ class StagedUploader {   // both directions; named after its first job
                     slot_busy_[s] = status == cudaSuccess;
                 }
                 ++issued;
+                progressed = true;
+            }
+            // The calling thread copies too whenever it has nothing to issue: a sleeping worker takes 100-200 us to wake
+            // on these (virtualised) hosts, and a 16-frame call is only a millisecond of copying.
+            if (mine < 0 && !progressed && next_.load(std::memory_order_relaxed) < pieces) {
+                const int64_t i = next_.fetch_add(1, std::memory_order_relaxed);
+                if (i < pieces) mine = i;
+            }
+            if (mine >= 0 && mine < freed_.load(std::memory_order_relaxed)) {
+                const size_t off = static_cast<size_t>(mine) * kSlotBytes;
+                const int ms = static_cast<int>(mine % kSlots);
+                std::memcpy(ring_ + ms * kSlotBytes, static_cast<const char*>(src) + off, std::min(kSlotBytes, bytes - off));
+                filled_[ms].store(mine, std::memory_order_release);
+                mine = -1;
                 progressed = true;
             }
             if (!progressed) {
@@ -168,6 +194,7 @@ class StagedUploader {   // both directions; named after its first job
             freed_.store(0, std::memory_order_relaxed);              // download: pieces [0, freed_) have arrived in their slots
             for (int s = 0; s < kSlots; ++s) filled_[s].store(-1, std::memory_order_relaxed);   // download: piece drained from slot
             ++generation_;
+            generation_hint_.store(generation_, std::memory_order_release);
         }
         cv_.notify_all();
         cudaError_t status = cudaSuccess;
@@ -227,6 +254,11 @@ class StagedUploader {   // both directions; named after its first job
         uint64_t seen = 0;
         for (;;) {
             {
+                // linger for a moment before sleeping: calls usually come back to back, and waking costs more than this
+                const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(kLingerMicros);
+                while (generation_hint_.load(std::memory_order_acquire) == seen && std::chrono::steady_clock::now() < until) {
+                    for (int k = 0; k < 32; ++k) cpu_relax();
+                }
                 std::unique_lock<std::mutex> lock(m_);
                 cv_.wait(lock, [&] { return stop_ || generation_ != seen; });
                 if (stop_) return;
@@ -264,6 +296,7 @@ class StagedUploader {   // both directions; named after its first job
     std::condition_variable cv_, cv_idle_;
     bool stop_ = false;
     uint64_t generation_ = 0;
+    std::atomic<uint64_t> generation_hint_{0};   // copy of generation_ the lingering workers poll without the lock
     int active_ = 0;
     // current job
     const char* src_ = nullptr;              // upload: the caller's array

@@ -33,6 +33,17 @@ int main() {
         cudaStreamSynchronize(s);
         double dt64 = std::chrono::duration<double>(now() - t1).count();
         printf("staged, %2d threads: %.1f GB/s in one upload, %.1f GB/s as 16 uploads of 64 MiB\n", threads, bytes / dt / 1e9, bytes / dt64 / 1e9);
+        // one 16-frame call's worth (56.6 MB), synchronised each time, with a pause in between like separate API calls
+        const size_t small = size_t(16) * 3538944;
+        double total = 0;
+        for (int rep = 0; rep < 10; ++rep) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(2));
+            auto t2 = now();
+            up.upload(dst, src, small, s);
+            cudaStreamSynchronize(s);
+            total += std::chrono::duration<double>(now() - t2).count();
+        }
+        printf("            56.6 MB uploads, synchronised: %.3f ms each = %.1f GB/s\n", total / 10 * 1e3, small / (total / 10) / 1e9);
     }
     return 0;
 }
