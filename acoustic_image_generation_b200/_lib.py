@@ -94,6 +94,7 @@ SIGNATURES = {
     'aig_iou_sweep_clips': (_int, [_p, _p, _p, _i64, _i64, _p, _int, _p, _p, _p]),
     'aig_ciou_sweep': (_int, [_p, _p, _p, _p, _p, _p, _i64, _int, _int, _p, _int, _p, _p, _p, _p]),
     'aig_power_spectrum': (_int, [_p, _p, _int, _i64, _p, _p]),
+    'aig_audio_mfcc': (_int, [_p, _p, _int, _i64, _p, _p]),
     'aig_filtfilt': (_int, [_p, _p, _int, _i64, _int, _p, _p, _p, _int, _p]),
     'aig_normalize_mfcc': (_int, [_p, _p, _i64, _p]),
     'aig_tile_mfcc': (_int, [_p, _p, _i64, _int, _p]),

@@ -1125,37 +1125,71 @@ int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, cons
     return io.finish();
 }
 
-int aig_power_spectrum(aig_handle* h, const void* audio, int audio_is_int32, int64_t n_rows, const double* window,
-                       float* power_out) {
-    int rc = require(h);
-    if (rc != AIG_OK) return rc;
-    if (n_rows < 0 || (n_rows > 0 && (!audio || !power_out))) return h->fail(AIG_ERR_ARGUMENT, "aig_power_spectrum: bad buffers");
-    if (n_rows == 0) return AIG_OK;
-    if (h->d_twiddle == nullptr) {
-        std::vector<double2> tw(kAudioSamples / 2);
-        for (int k = 0; k < kAudioSamples / 2; ++k) {
-            const double ang = -2.0 * 3.14159265358979323846 * k / kAudioSamples;
-            tw[k] = make_double2(std::cos(ang), std::sin(ang));
-        }
-        if (cudaMalloc(&h->d_twiddle, tw.size() * sizeof(double2)) != cudaSuccess) {
-            cudaGetLastError();
-            return h->fail(AIG_ERR_ALLOC, "aig_power_spectrum: cudaMalloc failed");
-        }
-        AIG_CK(cudaMemcpy(h->d_twiddle, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice));
+static int ensure_twiddles(aig_handle* h) {
+    if (h->d_twiddle != nullptr) return AIG_OK;
+    std::vector<double2> tw(kAudioSamples / 2);
+    for (int k = 0; k < kAudioSamples / 2; ++k) {
+        const double ang = -2.0 * 3.14159265358979323846 * k / kAudioSamples;
+        tw[k] = make_double2(std::cos(ang), std::sin(ang));
     }
-    Io io(h);
-    const size_t n = static_cast<size_t>(n_rows);
-    const float* d_in = io.in(static_cast<const float*>(audio), n * kAudioSamples);      // 4-byte samples either way
-    const double* d_win = io.in(window, kAudioSamples);
-    float* d_out = io.out(power_out, n * (kAudioSamples / 2));
-    if (io.failed) return io.finish();
+    if (cudaMalloc(&h->d_twiddle, tw.size() * sizeof(double2)) != cudaSuccess) {
+        cudaGetLastError();
+        return h->fail(AIG_ERR_ALLOC, "aig_power_spectrum: cudaMalloc failed");
+    }
+    AIG_CK(cudaMemcpy(h->d_twiddle, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    return AIG_OK;
+}
+
+static int launch_spectrum(aig_handle* h, const float* d_in, int audio_is_int32, int64_t n_rows, const double* d_win, float* d_out) {
     const int grid = frames_grid(h, n_rows, 8);
     LaunchScope scope(h, h->stream, kKindOther);
     if (audio_is_int32)
         spectrum_kernel<int><<<grid, kSpectrumThreads, 0, h->stream>>>(reinterpret_cast<const int*>(d_in), n_rows, d_win, h->d_twiddle, d_out);
     else
         spectrum_kernel<float><<<grid, kSpectrumThreads, 0, h->stream>>>(d_in, n_rows, d_win, h->d_twiddle, d_out);
-    rc = scope.done("spectrum_kernel");
+    return scope.done("spectrum_kernel");
+}
+
+int aig_power_spectrum(aig_handle* h, const void* audio, int audio_is_int32, int64_t n_rows, const double* window,
+                       float* power_out) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (n_rows < 0 || (n_rows > 0 && (!audio || !power_out))) return h->fail(AIG_ERR_ARGUMENT, "aig_power_spectrum: bad buffers");
+    if (n_rows == 0) return AIG_OK;
+    rc = ensure_twiddles(h);
+    if (rc != AIG_OK) return rc;
+    Io io(h);
+    const size_t n = static_cast<size_t>(n_rows);
+    const float* d_in = io.in(static_cast<const float*>(audio), n * kAudioSamples);      // 4-byte samples either way
+    const double* d_win = io.in(window, kAudioSamples);
+    float* d_out = io.out(power_out, n * (kAudioSamples / 2));
+    if (io.failed) return io.finish();
+    rc = launch_spectrum(h, d_in, audio_is_int32, n_rows, d_win, d_out);
+    if (rc != AIG_OK) return rc;
+    return io.finish();
+}
+
+int aig_audio_mfcc(aig_handle* h, const void* audio, int audio_is_int32, int64_t n_rows, const double* window,
+                   float* mfcc_out) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (!h->tables_set) return h->fail(AIG_ERR_TABLES, "aig_audio_mfcc: aig_set_tables has not been called");
+    if (h->fft_len != kAudioSamples / 2)
+        return h->fail(AIG_ERR_TABLES, "aig_audio_mfcc: the tables are for %d bins, the 1024-sample spectrum has %d", h->fft_len, kAudioSamples / 2);
+    if (n_rows < 0 || (n_rows > 0 && (!audio || !mfcc_out))) return h->fail(AIG_ERR_ARGUMENT, "aig_audio_mfcc: bad buffers");
+    if (n_rows == 0) return AIG_OK;
+    rc = ensure_twiddles(h);
+    if (rc != AIG_OK) return rc;
+    Io io(h);
+    const size_t n = static_cast<size_t>(n_rows);
+    const float* d_in = io.in(static_cast<const float*>(audio), n * kAudioSamples);
+    const double* d_win = io.in(window, kAudioSamples);
+    float* d_out = io.out(mfcc_out, n * h->mfcc_num);
+    float* d_power = static_cast<float*>(scratch(h, n * (kAudioSamples / 2) * sizeof(float)));   // never leaves the device
+    if (io.failed || !d_power) { io.failed = true; return io.finish(); }
+    rc = launch_spectrum(h, d_in, audio_is_int32, n_rows, d_win, d_power);
+    if (rc != AIG_OK) return rc;
+    rc = launch_mfcc(h, d_power, n_rows, d_out, 0, 1);
     if (rc != AIG_OK) return rc;
     return io.finish();
 }

@@ -213,6 +213,11 @@ int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, cons
  * (trainer/mfcctrainer.py:38-40, iouenergythreshold.py:99-101), optionally normalising each vector first. */
 int aig_power_spectrum(aig_handle* h, const void* audio, int audio_is_int32, int64_t n_rows,
                        const double* window, float* power_out);
+/* The whole _build_spectrograms_function (outdoor_data_mfcc.py:796-824) in one call: aig_power_spectrum followed by
+ * aig_mfcc with the handle's tables, the [n_rows, 512] power spectra staying on the device.  mfcc_out: float32
+ * [n_rows, mfcc_num]. */
+int aig_audio_mfcc(aig_handle* h, const void* audio, int audio_is_int32, int64_t n_rows, const double* window,
+                   float* mfcc_out);
 int aig_filtfilt(aig_handle* h, const void* x, int x_is_int32, int64_t n_rows, int length, const double* b,
                  const double* a, const double* zi, int ntaps, float* y_out);
 int aig_normalize_mfcc(aig_handle* h, const float* mfcc, int64_t n, float* out);
