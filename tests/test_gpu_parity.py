@@ -700,12 +700,18 @@ def test_four_worker_threads_each_with_their_own_handle(golden):
     imgs = synth.sigmoid_images(4, 34)
     want_e = [oracle.find_logen(f.copy()) for f in imgs]
     results, errors, handles = [None] * 4, [], [None] * 4
+    # 14 MB per call: above the staging threshold, so four handles run their pinned rings and copy threads at once
+    batches = [synth.power_frames(4, 40 + i, 'chi2') for i in range(4)]
+    main_path = aig.default_path()
+    want_batch = [main_path.mfcc_image(b, flip=True) for b in batches]
+    staged = [None] * 4
 
     def worker(i):
         try:
             for _ in range(5):
                 feats = aig.get_feats(512, power[i], 12, dct, mfnorm, lifter, bank)
                 en = aig.find_logen(imgs[i].copy())
+                staged[i] = aig.default_path().mfcc_image(batches[i], flip=True)
             results[i] = (feats, en)
             handles[i] = id(aig.default_path())
         except Exception as exc:            # pragma: no cover
@@ -721,6 +727,7 @@ def test_four_worker_threads_each_with_their_own_handle(golden):
     for i in range(4):
         assert np.abs(results[i][0] - want[i]).max() <= MFCC_TOL
         assert np.abs(results[i][1] - want_e[i]).max() <= ENERGY_RTOL * np.abs(want_e[i]).max()
+        assert np.array_equal(staged[i], want_batch[i])
 
 
 def test_plain_c_program_against_the_abi(tmp_path):
