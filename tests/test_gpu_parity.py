@@ -637,6 +637,21 @@ def test_pageable_inputs_match_device_inputs(path, torch, threads):
         path.set_option('host_copy_threads', -1)
 
 
+def test_staging_ring_soak_over_random_sizes(path, torch):
+    """Thirty uploads of random sizes back to back (8 - 250 MB, ragged last pieces, ring slots of one call still in
+    flight when the next starts), results compared with one device-resident pass over the same rows."""
+    rng = np.random.default_rng(99)
+    rows = synth.power_frames(70, 8, 'lognormal').reshape(-1, 512)              # 248 MB pageable
+    full = path.mfcc_rows(torch.from_numpy(rows).cuda()).cpu().numpy()
+    for _ in range(30):
+        r = int(rng.integers(4096, rows.shape[0] + 1))
+        got = path.mfcc_rows(rows[:r])
+        assert np.array_equal(got, full[:r], equal_nan=True), r
+    big_out = path.tile_mfcc(full[:20000])                                      # 1.66 GB result drained through the ring
+    assert big_out.shape == (20000, 36, 48, 12) and np.array_equal(big_out[123, 5, 7], full[123])
+    assert np.array_equal(big_out[19999, 35, 47], full[19999]) and np.array_equal(big_out[:, 0, 0, :], full[:20000])
+
+
 def oracle_free_rows(path, torch, rows):
     """aig_mfcc on a device copy of the same rows (no host staging involved)."""
     return path.mfcc_rows(torch.from_numpy(np.ascontiguousarray(rows)).cuda()).cpu().numpy()
