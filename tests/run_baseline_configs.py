@@ -50,10 +50,19 @@ def main():
     t0 = time.perf_counter()
     mfcc, energy, mask = path.mfcc_energy(power, flip=True, normalize_first=True)
     dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(20):                                                     # steady state, ordinary NumPy in / out
+        path.mfcc_energy(power, flip=True, normalize_first=True)
+    steady = (time.perf_counter() - t0) / 20
+    t0 = time.perf_counter()
+    for _ in range(3):
+        oracle.energy_stage(oracle.mfcc_image(power, flip=True), normalize_first=True)
+    cpu = (time.perf_counter() - t0) / 3
     want = oracle.mfcc_image(power, flip=True)
     _, want_mask = oracle.energy_stage(want, normalize_first=True)
     print(json.dumps({'config': 'C1: 16 frames 36x48x512 -> 12-ch MFCC (+energy, mask), host in / host out',
-                      'frames_per_s_first_call': 16 / dt, 'mfcc_max_abs_err': float(np.abs(mfcc - want).max()),
+                      'frames_per_s_first_call': 16 / dt, 'frames_per_s_steady': 16 / steady, 'ms_per_call': 1e3 * steady,
+                      'numpy_oracle_frames_per_s_same_host': 16 / cpu, 'mfcc_max_abs_err': float(np.abs(mfcc - want).max()),
                       'mask_pixels_differing': int((mask != want_mask).sum())}), flush=True)
 
     # ---- resident ring for C2 / C5 ---------------------------------------------------------------------------
