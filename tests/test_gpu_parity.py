@@ -368,6 +368,23 @@ def test_flickr_ciou_sweep_bit_exact(path, golden, shape):
         assert abs(aig.auc(REF_THR, aig.success_rates(pos, num)) - float(golden('auc')['flickr11'])) <= 1e-12
 
 
+@pytest.mark.parametrize('shape', [(2048, 2048), (1, 1), (2, 2047), (1500, 3)])
+def test_mask_resize_and_ciou_at_extreme_output_sizes(path, shape):
+    """The separable integer kernels at the largest geometry the ABI accepts (184 KiB of shared rows) and at degenerate
+    ones, against the oracle's integer restatement."""
+    rng = np.random.default_rng(shape[0] + shape[1])
+    masks = (rng.random((2, 36, 48)) > 0.6).astype(np.uint8)
+    got = path.resize_mask(masks, *shape)
+    want = np.stack([oracle.resize_mask(m, *shape) for m in masks], 0)
+    assert np.array_equal(got, want)
+    h, w = shape
+    xmin = np.array([[0, w // 3, 0], [w // 2, 0, 0]], np.int32); xmax = np.array([[w // 2, w, 0], [w, 0, 0]], np.int32)
+    ymin = np.array([[0, h // 4, 0], [h // 2, 0, 0]], np.int32); ymax = np.array([[h // 2, h, 0], [h, 0, 0]], np.int32)
+    i2, u2, pos, num = path.ciou_sweep(masks, xmin, xmax, ymin, ymax, REF_THR, out_hw=shape)
+    wi, wu, wpos, wnum = oracle.flickr_sweep(masks, xmin, xmax, ymin, ymax, REF_THR, *shape)
+    assert np.array_equal(i2, wi) and np.array_equal(u2, wu) and np.array_equal(pos, wpos) and num == wnum
+
+
 def test_ciou_box_edge_cases(path):
     mask = np.zeros((4, 36, 48), np.uint8)
     mask[1] = 1
