@@ -122,6 +122,7 @@ struct aig_handle {
     int64_t launch_row_limit = (int64_t(1) << 31) - 1024;   // TMA coordinates are int32: rows per launch (testable via option)
     int heatmap_exact = 0;              // 1: float64 replica of the oracle's bilinear; 0: float32 fast path
     bool heat_attr_set = false;
+    bool heat_exact_attr_set = false;
     bool mask_attr_set = false;
     int l2_evict_first = 0;             // L2 evict-first hint on the spectrum loads (measured slower: off)
     int keep_mfcc_in_l2 = 1;            // fused kernel: evict-last hint on the MFCC stores the energy warps re-read
@@ -469,6 +470,10 @@ int launch_heatmap(aig_handle* h, const double* d_energy, int64_t n_frames, int 
             heatmap_fast_kernel<1><<<grid, kHeatThreads, fast_smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);
     } else {
         const size_t smem = static_cast<size_t>(out_w + out_h) * (sizeof(double) + sizeof(int));
+        if (!h->heat_exact_attr_set) {      // up to 48 KiB of taps at 2048 x 2048, on top of 14 KiB of static shared memory
+            AIG_CK(cudaFuncSetAttribute(heatmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            h->heat_exact_attr_set = true;
+        }
         heatmap_kernel<<<frames_grid(h, n_frames, 4), kHeatThreads, smem, h->stream>>>(d_energy, n_frames, out_h, out_w, d_heat);
     }
     return scope.done("heatmap_kernel");
