@@ -41,6 +41,7 @@ ALGO_BYTES_MFCC_KERNEL = IN_BYTES + MFCC_BYTES + FRAME_PIXELS * 4   # SURVEY 8(d
 ALGO_BYTES_PATH = IN_BYTES + MFCC_BYTES + FRAME_PIXELS * 4   # 3 628 800 B per frame, MFCC + energy
 THRESHOLDS = (0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0)
 CPU_SAMPLE_FRAMES = 16                                   # BASELINE.json configs[0]
+RING_BLOCK = 64                                          # host-generated frames per stream, cycled to fill the ring
 
 
 def workload_config(frames, n_gpus):
@@ -52,6 +53,9 @@ def workload_config(frames, n_gpus):
         'flip180': True,
         'normalize_first': True,
         'l2': 'inputs larger than L2 (no flush needed)',
+        'inputs': 'two seeded NumPy streams of %d frames each (synth.power_frames, squared normal), generated on the host, '
+                  'cycled to fill the ring: stream A = first half, stream B = second half, frame i of A scored against '
+                  'frame i of B' % RING_BLOCK,
         'parallelism': 'frames sharded by rank, dp%d, one NCCL all-reduce of int64[12] per run' % n_gpus,
     }
 
@@ -76,6 +80,7 @@ def cpu_chain(oracle, power):
     energy, mask = oracle.energy_stage(mfcc, normalize_first=True)
     half = len(mask) // 2
     scores = [oracle.iou_pair(a, b)[2] for a, b in zip(mask[:half], mask[half:])]
+    cpu_chain.last = (mfcc, mask)            # for the parity check of the GPU arm against this same sample
     return oracle.success_counts(scores, THRESHOLDS)
 
 
@@ -219,6 +224,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     import acoustic_image_generation_b200 as aig
+    from acoustic_image_generation_b200 import synth
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -245,20 +251,23 @@ def run_gpu(args):
     if world > 1:
         path.init_comm()                            # libaig's own NCCL communicator (aig_comm_init)
     frames = args.frames
-    # synthetic spectra generated on the device, chi-square like synth.power_frames (squared normal), seeded per rank
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
+    # Synthetic spectra generated ON THE HOST by the seeded NumPy generator the tests and the CPU arm use
+    # (synth.power_frames: squared standard normal), then cycled on the device: stream A (seed 2*rank) fills the first
+    # half of the ring, stream B (seed 2*rank + 1) the second, RING_BLOCK frames each (226 MB > the 126 MB L2), so frame i
+    # of A is scored against frame i of B as in SURVEY 8(d) C5 and every value is reproducible on the CPU.
     power = torch.empty((frames, 36, 48, FFT_LEN), device=dev, dtype=torch.float32)
-    for f0 in range(0, frames, 256):
-        blk = power[f0:f0 + 256]
-        blk.normal_(generator=gen)
-        blk.square_()
+    half = frames // 2
+    for seed, lo, hi in ((2 * rank, 0, half), (2 * rank + 1, half, frames)):
+        block = torch.from_numpy(synth.power_frames(min(RING_BLOCK, max(hi - lo, 1)), seed, 'chi2')).to(dev)
+        for f0 in range(lo, hi, RING_BLOCK):
+            n = min(RING_BLOCK, hi - f0)
+            power[f0:f0 + n].copy_(block[:n])
+        del block
     mfcc = torch.empty((frames, 36, 48, MFCC_NUM), device=dev, dtype=torch.float32)
     energy = torch.empty((frames, 36, 48), device=dev, dtype=torch.float64)
     mask = torch.empty((frames, 36, 48), device=dev, dtype=torch.uint8)
     thr = torch.tensor(THRESHOLDS, device=dev, dtype=torch.float64)
     counts = torch.zeros(len(THRESHOLDS) + 1, device=dev, dtype=torch.int64)   # pos[0..K-1], num
-    half = frames // 2
 
     def step():
         path.mfcc_energy(power, flip=True, normalize_first=True, out=(mfcc, energy, mask))
@@ -390,6 +399,16 @@ def run_gpu(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = time_cpu(10 ** 6, 1, budget_s=args.cpu_seconds)[0]
+        # the CPU sample is frames 0..15 of this rank's ring (same generator, same seed): the timed GPU pass must have
+        # produced the reference's results for them
+        ref_mfcc, ref_mask = cpu_chain.last
+        k = min(CPU_SAMPLE_FRAMES, frames // 2)
+        gpu_mfcc, gpu_mask = mfcc[:k].cpu().numpy(), mask[:k].cpu().numpy()
+        line['parity_check'] = {
+            'frames': k, 'against': 'NumPy oracle on the same host-generated frames (CPU baseline sample)',
+            'mfcc_max_abs_err': float(np.abs(gpu_mfcc - ref_mfcc[:k]).max()), 'mfcc_tolerance': 1e-4,
+            'mask_pixels_differing': int((gpu_mask != ref_mask[:k]).sum()), 'mask_pixels': int(gpu_mask.size)}
+        assert line['parity_check']['mfcc_max_abs_err'] <= 1e-4, line['parity_check']
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     os.close(saved_stdout)
