@@ -37,3 +37,18 @@ cases = [
 ]
 for name, gpu, cpu in cases:
     print('%-52s GPU drop-in %8.1f us   NumPy oracle %8.1f us' % (name, bench(gpu), bench(cpu, 50)))
+
+# where a small call's time goes: the bare C entry point on preallocated arrays vs the Python wrappers around it
+path = aig.default_path()
+out12 = np.empty((12, 12), np.float32)
+lib, h = path._lib, path._h
+print('%-52s %8.1f us' % ('aig_mfcc (ctypes, 12 rows, preallocated, pageable)',
+                          bench(lambda: lib.aig_mfcc(h, rows12.ctypes.data, 12, out12.ctypes.data, 0, 1))))
+print('%-52s %8.1f us' % ('AcousticPath.mfcc_rows (12 rows)', bench(lambda: path.mfcc_rows(rows12))))
+print('%-52s %8.1f us' % ('AcousticPath.set_tables (unchanged tables)', bench(lambda: path.set_tables(bank, dct, lifter, mfnorm))))
+import torch
+d_rows = torch.from_numpy(rows12).cuda(); d_out = torch.empty((12, 12), device='cuda')
+def dev_call():
+    lib.aig_mfcc(h, d_rows.data_ptr(), 12, d_out.data_ptr(), 0, 1)
+    torch.cuda.synchronize()
+print('%-52s %8.1f us' % ('aig_mfcc (device in/out) + synchronize', bench(dev_call)))
