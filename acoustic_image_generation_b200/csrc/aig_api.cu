@@ -136,7 +136,7 @@ struct aig_handle {
     double2* d_twiddle = nullptr;       // exp(-2*pi*i*k/1024), k < 512 (aig_power_spectrum)
     // pageable host inputs are staged through a pinned ring by a few copy threads (host_staging.h)
     aig::StagedUploader uploader;
-    int host_copy_threads = -1;         // -1: min(4, hardware threads / 2); 0: leave pageable copies to the driver
+    int host_copy_threads = -1;         // -1: min(6, hardware threads / 2); 0: leave pageable copies to the driver
     // NCCL communicator (resolved with dlopen; see aig_comm_init)
     void* comm = nullptr;
     int comm_world = 1;
@@ -224,7 +224,7 @@ cudaError_t upload_async(aig_handle* h, void* dst, const void* src, size_t bytes
 bool use_host_staging(aig_handle* h, size_t bytes, MemKind kind) {
     if (kind != kHostPageable || bytes < kStagedUploadMinBytes || h->host_copy_threads == 0) return false;
     int threads = h->host_copy_threads;
-    if (threads < 0) threads = static_cast<int>(std::min(4u, std::max(1u, std::thread::hardware_concurrency() / 2)));   // 4 fill the link
+    if (threads < 0) threads = static_cast<int>(std::min(6u, std::max(1u, std::thread::hardware_concurrency() / 2)));   // 4-6 fill the link
     return h->uploader.start(threads);
 }
 cudaError_t download(aig_handle* h, void* dst, const void* src, size_t bytes, MemKind kind, cudaStream_t stream) {

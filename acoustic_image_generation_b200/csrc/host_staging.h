@@ -3,7 +3,7 @@
 // The reference hands this path NumPy arrays that TensorFlow's py_func allocated (dataloader/outdoor_data_mfcc.py:788):
 // pageable memory.  cudaMemcpyAsync from pageable memory is staged by the driver on one thread and reaches 8-12 GB/s on
 // the B200 boxes (tools/pageable_probe.py) against 55 GB/s for pinned memory - the whole end-to-end call is then 4-5x
-// slower than the link allows.  StagedUploader does the staging itself: a few host threads copy 1 MiB pieces of the
+// slower than the link allows.  StagedUploader does the staging itself: a few host threads copy 4 MiB pieces of the
 // caller's array into a ring of pinned slots while the calling thread issues one asynchronous H2D copy per filled slot,
 // in order, on the given stream.  download() is the mirror image for results returned into pageable arrays: D2H copies
 // land in the pinned slots and the threads move them on into the caller's array.  CUDA is only ever called from the
@@ -28,8 +28,11 @@ namespace aig {
 
 class StagedUploader {   // both directions; named after its first job
    public:
-    static constexpr size_t kSlotBytes = size_t(1) << 20;
-    static constexpr int kSlots = 32;
+    static constexpr size_t kSlotBytes = size_t(4) << 20;
+    static constexpr int kSlots = 8;
+    // A copy engine needs 4 MiB transfers to reach the link rate (1 MiB: 45 GB/s, 4 MiB: 52.5, 16 MiB: 54.7 on this box,
+    // tools/h2d_streams_probe.py); small jobs use 1 MiB pieces so that the first transfer starts sooner.
+    static size_t piece_bytes(size_t bytes) { return bytes >= (size_t(32) << 20) ? kSlotBytes : (size_t(1) << 20); }
     static constexpr int kLingerMicros = 400;
     static void cpu_relax() {
 #if defined(__x86_64__) || defined(__i386__)
@@ -97,13 +100,16 @@ class StagedUploader {   // both directions; named after its first job
     // from `src` and its H2D copy enqueued (the caller may then reuse `src`; the device side is stream-ordered).
     cudaError_t upload(void* dst, const void* src, size_t bytes, cudaStream_t stream) {
         if (bytes == 0) return cudaSuccess;
-        const int64_t pieces = static_cast<int64_t>((bytes + kSlotBytes - 1) / kSlotBytes);
+        const size_t piece = piece_bytes(bytes);
+        const int64_t pieces = static_cast<int64_t>((bytes + piece - 1) / piece);
         {
             std::unique_lock<std::mutex> lock(m_);
             cv_idle_.wait(lock, [this] { return active_ == 0; });     // a late waker of the previous job has left it
             src_ = static_cast<const char*>(src);
             user_dst_ = nullptr;
             bytes_ = bytes;
+            piece_ = piece;
+            worker_seen_.store(false, std::memory_order_relaxed);
             pieces_ = pieces;
             next_.store(0, std::memory_order_relaxed);
             freed_.store(0, std::memory_order_relaxed);
@@ -140,8 +146,8 @@ class StagedUploader {   // both directions; named after its first job
             freed_.store(primed < first_lap ? primed : freed + kSlots, std::memory_order_release);
             const int s = static_cast<int>(issued % kSlots);
             if (filled_[s].load(std::memory_order_acquire) == issued) {
-                const size_t off = static_cast<size_t>(issued) * kSlotBytes;
-                const size_t len = std::min(kSlotBytes, bytes - off);
+                const size_t off = static_cast<size_t>(issued) * piece;
+                const size_t len = std::min(piece, bytes - off);
                 if (status == cudaSuccess) {
                     status = cudaMemcpyAsync(static_cast<char*>(dst) + off, ring_ + s * kSlotBytes, len, cudaMemcpyHostToDevice, stream);
                     if (status == cudaSuccess) status = cudaEventRecord(slot_done_[s], stream);
@@ -152,14 +158,15 @@ class StagedUploader {   // both directions; named after its first job
             }
             // The calling thread copies too whenever it has nothing to issue: a sleeping worker takes 100-200 us to wake
             // on these (virtualised) hosts, and a 16-frame call is only a millisecond of copying.
-            if (mine < 0 && !progressed && next_.load(std::memory_order_relaxed) < pieces) {
+            if (mine < 0 && !progressed && !worker_seen_.load(std::memory_order_relaxed) &&
+                next_.load(std::memory_order_relaxed) < pieces) {
                 const int64_t i = next_.fetch_add(1, std::memory_order_relaxed);
                 if (i < pieces) mine = i;
             }
             if (mine >= 0 && mine < freed_.load(std::memory_order_relaxed)) {
-                const size_t off = static_cast<size_t>(mine) * kSlotBytes;
+                const size_t off = static_cast<size_t>(mine) * piece;
                 const int ms = static_cast<int>(mine % kSlots);
-                std::memcpy(ring_ + ms * kSlotBytes, static_cast<const char*>(src) + off, std::min(kSlotBytes, bytes - off));
+                std::memcpy(ring_ + ms * kSlotBytes, static_cast<const char*>(src) + off, std::min(piece, bytes - off));
                 filled_[ms].store(mine, std::memory_order_release);
                 mine = -1;
                 progressed = true;
@@ -182,13 +189,15 @@ class StagedUploader {   // both directions; named after its first job
     // is in `dst`.
     cudaError_t download(void* dst, const void* src, size_t bytes, cudaStream_t stream) {
         if (bytes == 0) return cudaSuccess;
-        const int64_t pieces = static_cast<int64_t>((bytes + kSlotBytes - 1) / kSlotBytes);
+        const size_t piece = piece_bytes(bytes);
+        const int64_t pieces = static_cast<int64_t>((bytes + piece - 1) / piece);
         {
             std::unique_lock<std::mutex> lock(m_);
             cv_idle_.wait(lock, [this] { return active_ == 0; });
             src_ = nullptr;
             user_dst_ = static_cast<char*>(dst);
             bytes_ = bytes;
+            piece_ = piece;
             pieces_ = pieces;
             next_.store(0, std::memory_order_relaxed);
             freed_.store(0, std::memory_order_relaxed);              // download: pieces [0, freed_) have arrived in their slots
@@ -216,8 +225,8 @@ class StagedUploader {   // both directions; named after its first job
                 const int s = static_cast<int>(issued % kSlots);
                 // first lap: an earlier upload may still be reading this slot
                 if (!(slot_busy_[s] && cudaEventQuery(slot_done_[s]) == cudaErrorNotReady)) {
-                    const size_t off = static_cast<size_t>(issued) * kSlotBytes;
-                    const size_t len = std::min(kSlotBytes, bytes - off);
+                    const size_t off = static_cast<size_t>(issued) * piece;
+                    const size_t len = std::min(piece, bytes - off);
                     if (status == cudaSuccess) {
                         status = cudaMemcpyAsync(ring_ + s * kSlotBytes, static_cast<const char*>(src) + off, len, cudaMemcpyDeviceToHost, stream);
                         if (status == cudaSuccess) status = cudaEventRecord(slot_done_[s], stream);
@@ -264,6 +273,7 @@ class StagedUploader {   // both directions; named after its first job
                 if (stop_) return;
                 seen = generation_;
                 ++active_;
+                worker_seen_.store(true, std::memory_order_relaxed);
             }
             for (;;) {
                 const int64_t i = next_.fetch_add(1, std::memory_order_relaxed);
@@ -272,8 +282,8 @@ class StagedUploader {   // both directions; named after its first job
                 while (freed_.load(std::memory_order_acquire) <= i) {       // upload: slot not free yet; download: piece not here yet
                     if (++spins > 64) { std::this_thread::yield(); spins = 0; }
                 }
-                const size_t off = static_cast<size_t>(i) * kSlotBytes;
-                const size_t len = std::min(kSlotBytes, bytes_ - off);
+                const size_t off = static_cast<size_t>(i) * piece_;
+                const size_t len = std::min(piece_, bytes_ - off);
                 const int s = static_cast<int>(i % kSlots);
                 if (user_dst_ == nullptr) std::memcpy(ring_ + s * kSlotBytes, src_ + off, len);     // upload: fill the slot
                 else std::memcpy(user_dst_ + off, ring_ + s * kSlotBytes, len);                    // download: drain it
@@ -303,6 +313,8 @@ class StagedUploader {   // both directions; named after its first job
     char* user_dst_ = nullptr;               // download: the caller's array (nullptr selects upload in the workers)
     std::atomic<bool> failed_{false};
     size_t bytes_ = 0;
+    size_t piece_ = kSlotBytes;              // bytes per piece of the current job (<= kSlotBytes)
+    std::atomic<bool> worker_seen_{false};   // a worker has joined the current job: the calling thread stops copying
     int64_t pieces_ = 0;
     std::atomic<int64_t> next_{0};
     std::atomic<int64_t> freed_{0};          // pieces [0, freed_) may be written into their slots

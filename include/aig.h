@@ -314,8 +314,8 @@ int64_t aig_launch_count(const aig_handle* h);
  *                        read-back one frame later still hits L2; 0: plain stores
  *   "l2_evict_first"     1: L2 evict-first cache hint on the TMA spectrum loads; 0 (default): normal policy
  *   "host_copy_threads"  copies of 8 MiB and more from / to ordinary (pageable) host arrays are staged through a ring
- *                        of pinned 1 MiB slots by this many host threads (host_staging.h; 4-5x the driver's own
- *                        pageable path): -1 (default) min(4, hardware threads / 2); 0 leaves them to cudaMemcpyAsync
+ *                        of pinned 4 MiB slots by this many host threads (host_staging.h; 4-5x the driver's own
+ *                        pageable path): -1 (default) min(6, hardware threads / 2); 0 leaves them to cudaMemcpyAsync
  *   "profile"            1: bracket every MFCC / energy kernel launch with CUDA events on the stream it
  *                        is launched on (read back with aig_profile_read); 0 (default): off
  * Unknown names or out-of-range values return AIG_ERR_ARGUMENT. */
