@@ -101,6 +101,7 @@ SIGNATURES = {
     'aig_split_triplets': (_int, [_p, _p, _i64, _p]),
     'aig_triplet_mse': (_int, [_p, _p, _p, _i64, _p]),
     'aig_overlay': (_int, [_p, _p, _p, _i64, _int, _int, ctypes.c_float, _p, _p]),
+    'aig_crc32c': (ctypes.c_uint32, [_p, ctypes.c_size_t, _int]),
     'aig_records_open': (_int, [ctypes.c_char_p, ctypes.POINTER(_p)]),
     'aig_records_close': (_int, [_p]),
     'aig_records_count': (_i64, [_p]),

@@ -113,6 +113,37 @@ def parse_flickr_example(records, index):
     return out
 
 
+def iterate_examples(paths, parse=parse_acoustic_example, workers=4, prefetch=8, **parse_kwargs):
+    """Every example of every file in ``paths``, in order, read and parsed ``workers`` files at a time with up to
+    ``prefetch`` files ahead of the consumer - the role of ``TFRecordDataset(...).map(_parse_sequence,
+    num_parallel_calls=4).prefetch(...)`` in the reference's loaders (dataloader/outdoor_data_mfcc.py:62-82).  Inflating,
+    CRC checking and the protobuf walk run inside libaig with the GIL released, so the threads overlap."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def load(path):
+        with RecordFile(path) as rec:
+            return [parse(rec, i, **parse_kwargs) for i in range(len(rec))]
+
+    paths = list(paths)
+    if workers <= 1:
+        for path in paths:
+            yield from load(path)
+        return
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        pending = []
+        upcoming = iter(paths)
+        for path in upcoming:
+            pending.append(pool.submit(load, path))
+            if len(pending) >= max(prefetch, 1):
+                break
+        while pending:
+            examples = pending.pop(0).result()
+            nxt = next(upcoming, None)
+            if nxt is not None:
+                pending.append(pool.submit(load, nxt))
+            yield from examples
+
+
 # ---- writer (convert_data.py:247-279) -----------------------------------------------------------------
 def _varint(v):
     v &= (1 << 64) - 1

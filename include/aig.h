@@ -256,7 +256,9 @@ int aig_overlay(aig_handle* h, const float* heat, const uint8_t* bgr, int64_t n_
  *   aig_record_sequence_size   feature list of byte strings (e.g. "audio/image"): steps and total payload bytes
  *   aig_record_sequence_read   the steps' byte strings concatenated into dst (host memory) - what
  *                              tf.decode_raw + reshape([-1, H, W, D]) sees
- *   aig_records_last_error     message of the calling thread's last reader failure */
+ *   aig_records_last_error     message of the calling thread's last reader failure
+ *   aig_crc32c                 CRC-32C (Castagnoli) of a buffer, the checksum of the TFRecord framing (unmasked); uses the
+ *                              SSE4.2 instruction when the CPU has it, force_table = 1 selects the portable table loop */
 typedef struct aig_record_reader aig_record_reader;
 int aig_records_open(const char* path, aig_record_reader** out);
 int aig_records_close(aig_record_reader* r);
@@ -267,6 +269,7 @@ int aig_record_sequence_size(const aig_record_reader* r, int record, const char*
                              int64_t* bytes_out);
 int aig_record_sequence_read(const aig_record_reader* r, int record, const char* key, void* dst, int64_t dst_bytes);
 const char* aig_records_last_error(void);
+uint32_t aig_crc32c(const void* data, size_t n, int force_table);
 
 /* ---- multi-GPU: the path's only exchange ------------------------------------------------------
  * Frames shard across GPUs with no data-path collective; at the end of an evaluation the int64[K+1]

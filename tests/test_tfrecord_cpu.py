@@ -62,6 +62,24 @@ def _frame(blob):
     return header + struct.pack('<I', tfrecord._masked_crc32c(header)) + blob + struct.pack('<I', tfrecord._masked_crc32c(blob))
 
 
+def test_native_crc32c_both_paths():
+    """libaig's CRC-32C: the SSE4.2 path (when the CPU has it) and the table loop against the known answer, the
+    Python writer's implementation, and each other on unaligned ragged buffers."""
+    from acoustic_image_generation_b200 import _lib
+    lib = _lib.load()
+    crc = lambda b, table: lib.aig_crc32c(b, len(b), table)
+    assert crc(b'123456789', 0) == crc(b'123456789', 1) == 0xE3069283
+    rng = np.random.default_rng(4)
+    buf = rng.integers(0, 256, 100003, dtype=np.uint8).tobytes()
+    for start, n in ((0, 100003), (1, 9), (3, 64), (5, 4097), (7, 1), (2, 65536)):
+        piece = buf[start:start + n]
+        mv = np.frombuffer(buf, np.uint8)[start:start + n]                 # genuinely unaligned start address
+        fast = lib.aig_crc32c(mv.ctypes.data, n, 0)
+        assert fast == lib.aig_crc32c(mv.ctypes.data, n, 1) == crc(piece, 1)
+        c = fast
+        assert tfrecord._masked_crc32c(piece) == (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+
+
 def test_crc32c_known_answer():
     # CRC-32C("123456789") = 0xE3069283; the TFRecord mask is rot-right 15 plus 0xA282EAD8
     c = 0xE3069283
@@ -163,3 +181,22 @@ def test_malformed_messages_never_crash_the_reader(tmp_path):
                 except (AigError, ValueError, KeyError):
                     raised += 1
     assert answered > 0 and raised > 0
+
+
+def test_parallel_iteration_keeps_file_and_record_order(tmp_path):
+    paths = []
+    for r in range(9):
+        blobs = [tfrecord.encode_sequence_example(
+            {'classes': 10 * r + k, 'location': r, 'audio_image/height': 36, 'audio_image/width': 48, 'audio_image/depth': 12},
+            {'audio/image': [f.tobytes() for f in synth.sigmoid_images(2, 50 + 3 * r + k)]}) for k in range(1 + r % 3)]
+        paths.append(tfrecord.write_sequence_examples(str(tmp_path / ('Data_%03d.tfrecord' % r)), blobs))
+    serial = list(tfrecord.iterate_examples(paths, workers=1))
+    for workers, prefetch in ((4, 8), (2, 1), (16, 3)):
+        got = list(tfrecord.iterate_examples(paths, workers=workers, prefetch=prefetch))
+        assert [e['classes'] for e in got] == [e['classes'] for e in serial] == [10 * r + k for r in range(9) for k in range(1 + r % 3)]
+        assert all(np.array_equal(a['audio_images'], b['audio_images']) for a, b in zip(got, serial))
+    unflipped = list(tfrecord.iterate_examples(paths[:1], flip=False))
+    assert np.array_equal(unflipped[0]['audio_images'][:, ::-1, ::-1, :], serial[0]['audio_images'])
+    assert list(tfrecord.iterate_examples([])) == []
+    with pytest.raises(AigError):
+        list(tfrecord.iterate_examples(paths[:2] + [str(tmp_path / 'missing.tfrecord')]))
