@@ -39,9 +39,7 @@ def main(out_dir=None):
     path = aig.AcousticPath(0)
     ev = evaluate.AcivwEvaluation(path)
     rng = np.random.default_rng(0)
-    for p in paths:
-        with tfrecord.RecordFile(p) as rec:
-            ex = tfrecord.parse_acoustic_example(rec, 0)                     # flips as in _parse_sequence
+    for ex in tfrecord.iterate_examples(paths, workers=4):                   # parallel read + parse, flips as in _parse_sequence
         data = path.normalize_images(ex['audio_images'])                     # _map_func_acoustic_images
         mfcc = path.normalize_mfcc(path.build_spectrograms(ex['audio_samples']))   # _build_spectrograms_function + _map_func_mfcc
         assert mfcc.shape == (12, 12)
