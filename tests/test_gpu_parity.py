@@ -765,6 +765,39 @@ def test_four_worker_threads_each_with_their_own_handle(golden):
         assert np.array_equal(staged[i], want_batch[i])
 
 
+def test_record_batches_on_the_device_match_the_oracle_chain(tmp_path, torch):
+    """loader.AcousticBatches: TFRecords -> flipped, normalised acoustic images + normalised audio MFCC + mfccmap +
+    low-passed waveform as CUDA tensors, against the oracle applied to the same records (outdoor_data_mfcc.py:62-101)."""
+    from acoustic_image_generation_b200 import loader, tfrecord
+    paths, all_img, all_audio, all_cls = [], [], [], []
+    for r, frames in enumerate((12, 7, 20, 12, 3)):
+        images = synth.smooth_images(frames, 300 + r)
+        audio = synth.audio_rows(frames, 400 + r, np.int32)
+        blob = tfrecord.encode_sequence_example(
+            {'classes': r, 'location': 2, 'audio_image/height': 36, 'audio_image/width': 48, 'audio_image/depth': 12,
+             'audio_data/mics': 1, 'audio_data/samples': 1024},
+            {'audio/image': [f.tobytes() for f in images], 'audio/data': [a.tobytes() for a in audio]})
+        paths.append(tfrecord.write_sequence_examples(str(tmp_path / ('Data_%03d.tfrecord' % r)), [blob]))
+        all_img.append(images[:, ::-1, ::-1, :]); all_audio.append(audio); all_cls += [r] * frames
+    want_img = oracle.normalize_acoustic_images(np.ascontiguousarray(np.concatenate(all_img, 0)))
+    audio = np.concatenate(all_audio, 0)
+    raw_mfcc = oracle.build_spectrograms(audio)
+    want_mfcc = oracle.normalize_mfcc(raw_mfcc)
+    want_filtered = oracle.butter_lowpass_filter(audio)
+    got = list(loader.AcousticBatches(paths, batch_frames=16, low_pass=True))
+    assert [len(b['classes']) for b in got] == [16, 16, 16, 6]
+    assert np.concatenate([b['classes'] for b in got]).tolist() == all_cls
+    cat = lambda k: torch.cat([b[k] for b in got], 0).cpu().numpy()
+    assert all(b['acoustic'].is_cuda and b['mfccmap'].is_cuda for b in got)
+    assert np.array_equal(cat('acoustic'), want_img)
+    scale = 1.0 / (raw_mfcc.max(1) - raw_mfcc.min(1)).min()                   # min-max normalisation stretches the 1e-4
+    assert np.abs(cat('mfcc') - want_mfcc).max() <= 5e-4 * max(scale, 1.0) + 1e-6
+    assert np.array_equal(cat('mfccmap'), oracle.tile_mfcc(cat('mfcc')))
+    assert np.array_equal(cat('filtered'), want_filtered)
+    short = list(loader.AcousticBatches(paths, batch_frames=16, drop_last=True, tile=False))
+    assert len(short) == 3 and 'mfccmap' not in short[0]
+
+
 def test_plain_c_program_against_the_abi(tmp_path):
     """examples/c_abi_smoke.c: the ABI is usable from C with nothing but the header and the shared object."""
     import os
