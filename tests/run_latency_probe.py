@@ -9,7 +9,7 @@ import numpy as np
 
 import acoustic_image_generation_b200 as aig
 from acoustic_image_generation_b200 import synth, tables
-from oracle import acoustic_oracle as oracle      # timing comparison only (tools/, not product code)
+from oracle import acoustic_oracle as oracle      # timing comparison (tests/ may use the oracle)
 
 
 def bench(fn, reps=200):
