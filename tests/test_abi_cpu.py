@@ -119,3 +119,19 @@ def test_metric_files_round_trip(tmp_path):
         assert metrics_io.read_accuracy_file(str(tmp_path), thr) == round(pos / 10, 6)
     p = metrics_io.write_area_file(str(tmp_path), 0.4321987)
     assert open(p).read() == 'area 0.432199'
+
+
+def test_only_tests_smoke_and_bench_touch_the_oracle():
+    """oracle/ is test infrastructure: nothing in the package, tools/ or examples/ may import it; bench.py and
+    __graft_entry__.py may (CPU baseline legs and smoke())."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pattern = re.compile(r'^\s*(from\s+oracle\b|import\s+oracle\b)', re.M)
+    offenders = []
+    for sub in ('acoustic_image_generation_b200', 'tools', 'examples'):
+        for base, _, files in os.walk(os.path.join(root, sub)):
+            for name in files:
+                if name.endswith('.py') and pattern.search(open(os.path.join(base, name)).read()):
+                    offenders.append(os.path.relpath(os.path.join(base, name), root))
+    assert not offenders, offenders
