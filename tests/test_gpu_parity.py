@@ -798,6 +798,26 @@ def test_record_batches_on_the_device_match_the_oracle_chain(tmp_path, torch):
     assert len(short) == 3 and 'mfccmap' not in short[0]
 
 
+def test_integration_md_binding_sample_runs_verbatim():
+    """The ctypes stub INTEGRATION.md shows a reference maintainer (option B) is executed as printed."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, 'INTEGRATION.md')).read()
+    code = re.search(r'## B\. Bind the C ABI directly.*?```python\n(.*?)```', text, re.S).group(1)
+    scope = {}
+    cwd = os.getcwd()
+    os.chdir(root)                                    # the sample loads the library by its repo-relative path
+    try:
+        exec(compile(code, 'INTEGRATION.md', 'exec'), scope)
+        bank, dct, lifter, mfnorm = tables.reference_tables()
+        beam = synth.power_frames(1, 0, 'chi2').reshape(-1, 512)[:100]
+        got = scope['get_feats'](512, beam, 12, dct, mfnorm, lifter, bank)
+    finally:
+        os.chdir(cwd)
+    assert np.abs(got - oracle.get_feats(512, beam, 12, dct, mfnorm, lifter, bank)).max() <= MFCC_TOL
+
+
 def test_plain_c_program_against_the_abi(tmp_path):
     """examples/c_abi_smoke.c: the ABI is usable from C with nothing but the header and the shared object."""
     import os
