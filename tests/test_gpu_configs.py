@@ -189,3 +189,47 @@ def test_mfcc_error_statistics_over_many_spectra(path):
         print('%-22s n=%d  max %.2e  p99.99 %.2e  rms %.2e  (max |mfcc| %.1f)'
               % (name, err.size, err.max(), np.quantile(err, 0.9999), np.sqrt(np.mean(err ** 2)), np.abs(want).max()))
         assert err.max() <= 1e-4
+
+
+def test_full_size_properties_8192_frames(path):
+    """configs[1] at the size the bench runs (8192 resident frames, 29 GB): properties that need no oracle.
+    Determinism of the persistent fused kernel, flip equivariance, batch-split invariance, frame independence (bitwise),
+    and invariance of the MFCC to a global gain (the DCT rows m >= 1 annihilate constants; tolerance 1e-4)."""
+    import torch
+    n = 8192
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(2024)
+    power = torch.empty((n, 36, 48, 512), device='cuda', dtype=torch.float32)
+    for f0 in range(0, n, 512):
+        power[f0:f0 + 512].normal_(generator=gen).square_()
+    mfcc, energy, mask = path.mfcc_energy(power, flip=True, normalize_first=True)
+    # (a) determinism
+    mfcc2, energy2, mask2 = path.mfcc_energy(power, flip=True, normalize_first=True)
+    assert torch.equal(mfcc, mfcc2) and torch.equal(mask, mask2) and torch.equal(energy.view(torch.int64), energy2.view(torch.int64))
+    del mfcc2, energy2, mask2
+    # (b) flip equivariance: the 180-degree rotation is pure store addressing
+    plain = path.mfcc_image(power, flip=False)
+    assert torch.equal(plain.flip(1, 2), mfcc)
+    del plain
+    # (c) batch-split invariance and (d) frame independence
+    lo = path.mfcc_energy(power[:3000], flip=True, normalize_first=True)
+    hi = path.mfcc_energy(power[3000:], flip=True, normalize_first=True)
+    assert torch.equal(torch.cat([lo[0], hi[0]]), mfcc) and torch.equal(torch.cat([lo[2], hi[2]]), mask)
+    assert torch.equal(torch.cat([lo[1], hi[1]]).view(torch.int64), energy.view(torch.int64))
+    del lo, hi
+    for f in (0, 147, 148, 4095, 8191):
+        one = path.mfcc_energy(power[f:f + 1], flip=True, normalize_first=True)
+        assert torch.equal(one[0][0], mfcc[f]) and torch.equal(one[2][0], mask[f])
+        assert torch.equal(one[1][0].view(torch.int64), energy[f].view(torch.int64))
+    # (e) gain invariance: x4 is exact in float32 and every mel band stays far above the 0.001 floor
+    power.mul_(4.0)
+    gained = path.mfcc_image(power, flip=True)
+    err = float((gained - mfcc).abs().max())
+    print('full size: MFCC change under a global gain of 4: %.2e' % err)
+    assert err <= 1e-4
+    # (f) the masks are balanced and the IoU sweep is symmetric in its two streams
+    assert 0.3 < float(mask.float().mean()) < 0.7
+    half = n // 2
+    a = path.iou_sweep(mask[:half], mask[half:])
+    b = path.iou_sweep(mask[half:], mask[:half])
+    assert all(torch.equal(torch.as_tensor(x), torch.as_tensor(y)) for x, y in zip(a, b))
