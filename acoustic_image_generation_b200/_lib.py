@@ -7,9 +7,11 @@ module: if the library cannot be loaded, or no B200 is present, the calls raise.
 from __future__ import annotations
 
 import ctypes
+import hashlib
 import os
 import shutil
 import subprocess
+import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
@@ -19,10 +21,12 @@ INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 NVCC_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-pthread', '-shared', '-ldl', '-lz', '-lpthread']
 SOURCES = ['aig_api.cu', 'record_reader.cpp']
-DEPENDS = ['aig_api.cu', 'record_reader.cpp', 'aig_common.cuh', 'mfcc_kernel.cuh', 'energy_kernel.cuh', 'score_kernel.cuh', 'fused_kernel.cuh', 'frontend_kernel.cuh', 'host_staging.h',
+DEPENDS = ['aig_api.cu', 'record_reader.cpp', 'aig_common.cuh', 'mfcc_kernel.cuh', 'energy_kernel.cuh', 'heatmap_kernel.cuh', 'score_kernel.cuh', 'fused_kernel.cuh', 'frontend_kernel.cuh',
+           'host_staging.h',
            'mel_program_ref.inc', 'mel_tables_ref.inc', os.path.join(INCLUDE, 'aig.h')]
 
 AIG_OK = 0
+ABI_VERSION = 2
 ERROR_NAMES = {-1: 'AIG_ERR_ARGUMENT', -2: 'AIG_ERR_NO_DEVICE', -3: 'AIG_ERR_TABLES', -4: 'AIG_ERR_ALLOC'}
 
 
@@ -42,31 +46,59 @@ def _nvcc():
     raise RuntimeError('nvcc not found: cannot build libaig.so')
 
 
-def needs_build():
-    if not os.path.exists(LIB_PATH):
-        return True
-    built = os.path.getmtime(LIB_PATH)
+BUILD_ID_MARKER = b'AIG_BUILD_ID='
+_lock = threading.RLock()
+
+
+def source_build_id():
+    """Hash of everything the binary is made from (every file of DEPENDS, by content, plus the compiler flags).  build()
+    stamps it into the library (aig_build_id()); load() refuses a library whose stamp differs, so a shipped libaig.so
+    is always the committed source - modification times play no part."""
+    h = hashlib.sha256()
+    h.update(' '.join(NVCC_FLAGS + SOURCES).encode())
     for dep in DEPENDS:
         path = dep if os.path.isabs(dep) else os.path.join(CSRC, dep)
-        if os.path.getmtime(path) > built:
-            return True
-    return False
+        h.update(os.path.basename(path).encode() + b'\0')
+        with open(path, 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:24]
+
+
+def binary_build_id(path=None):
+    """The stamp inside a built library, read from the file (no dlopen); None when absent."""
+    path = path or LIB_PATH
+    try:
+        with open(path, 'rb') as fh:
+            blob = fh.read()
+    except OSError:
+        return None
+    at = blob.find(BUILD_ID_MARKER)
+    if at < 0:
+        return None
+    end = blob.find(b'\0', at)
+    return blob[at + len(BUILD_ID_MARKER):end].decode('ascii', 'replace')
+
+
+def needs_build():
+    return binary_build_id() != source_build_id()
 
 
 def build(force=False, verbose=False):
     """Compile csrc/*.cu into csrc/libaig.so for sm_100a (cross-compiles without a GPU)."""
-    if not force and not needs_build():
+    with _lock:
+        if not force and not needs_build():
+            return LIB_PATH
+        cmd = [_nvcc()] + NVCC_FLAGS + ['-DAIG_BUILD_ID_STRING="%s"' % source_build_id(), '-I', INCLUDE,
+                                        '-o', LIB_PATH + '.tmp'] + SOURCES
+        if verbose:
+            cmd += ['-Xptxas', '-v']
+        proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError('nvcc failed:\n%s\n%s' % (' '.join(cmd), proc.stderr[-4000:]))
+        os.replace(LIB_PATH + '.tmp', LIB_PATH)
+        if verbose:
+            print(proc.stderr)
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ['-I', INCLUDE, '-o', LIB_PATH + '.tmp'] + SOURCES
-    if verbose:
-        cmd += ['-Xptxas', '-v']
-    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError('nvcc failed:\n%s\n%s' % (' '.join(cmd), proc.stderr[-4000:]))
-    os.replace(LIB_PATH + '.tmp', LIB_PATH)
-    if verbose:
-        print(proc.stderr)
-    return LIB_PATH
 
 
 _p = ctypes.c_void_p
@@ -77,6 +109,7 @@ _dbl = ctypes.c_double
 # name -> (restype, argtypes); must list every symbol include/aig.h declares
 SIGNATURES = {
     'aig_abi_version': (_int, []),
+    'aig_build_id': (ctypes.c_char_p, []),
     'aig_create': (_int, [_int, ctypes.c_uint64, ctypes.POINTER(_p)]),
     'aig_destroy': (_int, [_p]),
     'aig_last_error': (ctypes.c_char_p, [_p]),
@@ -88,6 +121,7 @@ SIGNATURES = {
     'aig_energy': (_int, [_p, _p, _i64, _int, _p, _p, _p, _p]),
     'aig_heatmap': (_int, [_p, _p, _i64, _int, _int, _p]),
     'aig_energy_heatmap': (_int, [_p, _p, _i64, _int, _p, _p, _p, _int, _int]),
+    'aig_acivw_batch': (_int, [_p, _p, _p, _i64, _int, _p, _int, _p, _p, _p, _p, _p, _p, _p, _p]),
     'aig_resize_mask': (_int, [_p, _p, _i64, _int, _int, _p]),
     'aig_mfcc_energy': (_int, [_p, _p, _i64, _int, _int, _p, _p, _p, _p]),
     'aig_iou_sweep': (_int, [_p, _p, _p, _i64, _p, _int, _p, _p, _p, _p]),
@@ -113,6 +147,8 @@ SIGNATURES = {
     'aig_comm_init': (_int, [_p, _p, _int, _int]),
     'aig_allreduce_counts': (_int, [_p, _p, _int]),
     'aig_comm_destroy': (_int, [_p]),
+    'aig_comm_init_all': (_int, [_p, _int]),
+    'aig_group_allreduce_counts': (_int, [_p, _p, _int, _int]),
     'aig_auc': (_int, [_p, _p, _int, _p]),
     'aig_launch_count': (_i64, [_p]),
     'aig_set_option': (_int, [_p, ctypes.c_char_p, _i64]),
@@ -124,20 +160,30 @@ _lib = None
 
 
 def load(build_if_missing=True):
-    """dlopen csrc/libaig.so and attach the prototypes.  Raises if it is missing and cannot be built."""
+    """dlopen csrc/libaig.so and attach the prototypes.
+
+    The library must carry the build id of the sources next to it (source_build_id): a missing or stale binary is
+    rebuilt when ``build_if_missing`` (needs nvcc), otherwise - and if the stamp still differs afterwards - this raises.
+    Thread-safe: the loaders' worker threads may race here."""
     global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise RuntimeError('%s is missing; run __graft_entry__.build()' % LIB_PATH)
-        build()
-    lib = ctypes.CDLL(LIB_PATH)
-    for name, (restype, argtypes) in SIGNATURES.items():
-        fn = getattr(lib, name)          # AttributeError if the library does not export the symbol
-        fn.restype = restype
-        fn.argtypes = argtypes
-    if lib.aig_abi_version() != 1:
-        raise RuntimeError('libaig.so ABI version %d does not match this binding (1)' % lib.aig_abi_version())
-    _lib = lib
-    return lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        want = source_build_id()
+        if binary_build_id() != want:
+            if not build_if_missing:
+                raise RuntimeError('%s is missing or was built from other sources (build id %s, sources %s); run '
+                                   '__graft_entry__.build()' % (LIB_PATH, binary_build_id(), want))
+            build(force=True)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the library does not export the symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.aig_abi_version() != ABI_VERSION:
+            raise RuntimeError('libaig.so ABI version %d does not match this binding (%d)' % (lib.aig_abi_version(), ABI_VERSION))
+        have = (lib.aig_build_id() or b'').decode()
+        if have != want:
+            raise RuntimeError('libaig.so build id %s does not match the sources (%s)' % (have, want))
+        _lib = lib
+        return lib

@@ -136,8 +136,14 @@ class AcousticPath:
     def set_mfcc_variant(self, variant):
         self.set_option('mfcc_variant', variant)
 
+    @property
+    def has_comm(self):
+        """True once init_comm / AcousticPathGroup has joined this handle to a native (NCCL) communicator."""
+        return getattr(self, '_has_comm', False)
+
     def selftest(self, which):
-        """Device self-tests of the energy stage's exact-division and table-exp shortcuts (see aig_selftest)."""
+        """Device self-tests of the energy stage's arithmetic shortcuts: 0 lifter division, 1 table exp, 2 hoisted-
+        reciprocal min-max division (see aig_selftest)."""
         out = (ctypes.c_uint64 * 4)()
         self._check(self._lib.aig_selftest(self._h, int(which), out))
         return [int(v) for v in out]
@@ -180,6 +186,22 @@ class AcousticPath:
         dist.broadcast_object_list(box, src=0, group=group)
         ident = (ctypes.c_uint8 * 128).from_buffer_copy(box[0])
         self._check(self._lib.aig_comm_init(self._h, ident, int(rank), int(world)))
+        self._has_comm = True
+
+    def init_comm_from_id(self, ident, rank, world):
+        """Join a communicator whose 128-byte id (aig_comm_unique_id) was shipped by other means (a file, MPI ...)."""
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(bytes(ident))
+        self._check(self._lib.aig_comm_init(self._h, buf, int(rank), int(world)))
+        self._has_comm = True
+
+    @staticmethod
+    def comm_unique_id():
+        ident = (ctypes.c_uint8 * 128)()
+        lib = _lib.load()
+        code = lib.aig_comm_unique_id(ident)
+        if code != 0:
+            raise AigError(code, (lib.aig_last_error(None) or b'').decode())
+        return bytes(ident)
 
     def allreduce_counts(self, counts):
         """In-place sum of an int64 count vector over the ranks of init_comm (identity without a communicator);
@@ -380,17 +402,23 @@ class AcousticPath:
         self._check(self._lib.aig_heatmap(self._h, a.ptr, n, int(out_h), int(out_w), self._a(res, np.float32, True).ptr))
         return res
 
-    def energy_heatmap(self, images, normalize_first=False, out_h=HEAT_H, out_w=HEAT_W):
-        """find_logen -> cv2.resize -> imshow normalisation for a batch in one call (showvideo.py:226-228):
-        returns (energy f64 [N,36,48], mask u8 [N,36,48], heat f32 [N,out_h,out_w])."""
+    def energy_heatmap(self, images, normalize_first=False, out_h=HEAT_H, out_w=HEAT_W, want_energy=True, want_mask=True,
+                       out=None):
+        """find_logen -> cv2.resize -> imshow normalisation for a batch in ONE kernel launch (showvideo.py:226-228):
+        returns (energy f64 [N,36,48], mask u8 [N,36,48], heat f32 [N,out_h,out_w]); energy / mask are None when not
+        wanted (they then never leave the SM).  ``out`` supplies the heat buffer."""
         a = self._a(images, np.float32)
         n = self._frames(a.shape, FRAME_PIXELS * MFCC_NUM)
-        energy = self._empty((n, FRAME_H, FRAME_W), np.float64, a)
-        mask = self._empty((n, FRAME_H, FRAME_W), np.uint8, a)
-        heat = self._empty((n, out_h, out_w), np.float32, a)
+        energy = self._empty((n, FRAME_H, FRAME_W), np.float64, a) if want_energy else None
+        mask = self._empty((n, FRAME_H, FRAME_W), np.uint8, a) if want_mask else None
+        heat = out if out is not None else self._empty((n, out_h, out_w), np.float32, a)
+        o_heat = self._a(heat, np.float32, True)
+        if int(np.prod(o_heat.shape)) != n * out_h * out_w:
+            raise ValueError('out has shape %s, expected %d x %d x %d' % (o_heat.shape, n, out_h, out_w))
         self._check(self._lib.aig_energy_heatmap(self._h, a.ptr, n, int(bool(normalize_first)),
-                                                 self._a(energy, np.float64, True).ptr, self._a(mask, np.uint8, True).ptr,
-                                                 self._a(heat, np.float32, True).ptr, int(out_h), int(out_w)))
+                                                 self._a(energy, np.float64, True).ptr if want_energy else None,
+                                                 self._a(mask, np.uint8, True).ptr if want_mask else None,
+                                                 o_heat.ptr, int(out_h), int(out_w)))
         return energy, mask, heat
 
     def overlay(self, heat, frames_bgr=None, alpha=0.7):
@@ -512,6 +540,36 @@ class AcousticPath:
                                                   p_arg.ptr))
         return inter, union, pos
 
+    def acivw_batch(self, real, reconstructed, thresholds=REFERENCE_THRESHOLDS, pos=None, num=None, normalize_first=False,
+                    want_energy=False, want_masks=False):
+        """The reference's ACIVW evaluation step for a batch in one kernel launch (iouenergythreshold.py:213-229): the real
+        and the reconstructed [B, 36, 48, 12] image -> find_logen of each -> mean masks -> I, U -> success counts.
+
+        Returns (inter int64 [B], union int64 [B], pos int64 [K], num) and, when asked for, (energy_real, energy_recon)
+        float64 [B, 36, 48] and (mask_real, mask_recon) uint8 [B, 36, 48] appended.  Like the reference (which works on
+        an np.stack copy) the inputs are not scaled in place."""
+        a, b = self._a(real, np.float32), self._a(reconstructed, np.float32)
+        n = self._frames(a.shape, FRAME_PIXELS * MFCC_NUM)
+        if self._frames(b.shape, FRAME_PIXELS * MFCC_NUM) != n:
+            raise ValueError('image batches differ: %s vs %s' % (a.shape, b.shape))
+        thr = self._thresholds(thresholds)
+        pos, cnt, p_arg, c_arg = self._counters(thr, pos, num)
+        inter = self._empty((n,), np.int64, a)
+        union = self._empty((n,), np.int64, a)
+        energies = [self._empty((n, FRAME_H, FRAME_W), np.float64, a) for _ in range(2)] if want_energy else [None, None]
+        masks = [self._empty((n, FRAME_H, FRAME_W), np.uint8, a) for _ in range(2)] if want_masks else [None, None]
+        ptr = lambda x, dt: self._a(x, dt, True).ptr if x is not None else None
+        self._check(self._lib.aig_acivw_batch(self._h, a.ptr, b.ptr, n, int(bool(normalize_first)), thr.ptr, thr.shape[0],
+                                              ptr(inter, np.int64), ptr(union, np.int64), p_arg.ptr, c_arg.ptr,
+                                              ptr(energies[0], np.float64), ptr(energies[1], np.float64),
+                                              ptr(masks[0], np.uint8), ptr(masks[1], np.uint8)))
+        out = (inter, union, pos, self._num_result(cnt))
+        if want_energy:
+            out += (tuple(energies),)
+        if want_masks:
+            out += (tuple(masks),)
+        return out
+
     def ciou_sweep(self, mask, xmin, xmax, ymin, ymax, thresholds=REFERENCE_THRESHOLDS,
                    out_hw=(HEAT_H, HEAT_W), pos=None, num=None):
         """FlickrSoundNet consensus IoU and success counts (showimages_bb.py:288-321).
@@ -550,6 +608,13 @@ def auc(thresholds, values):
 def success_rates(pos, num):
     """``1.0 * pos / num`` (iouenergythreshold.py:236)."""
     return np.asarray(pos, dtype=np.float64) / np.float64(num)
+
+
+def rates_as_written(rates):
+    """The success rates as areaundercurve.py sees them: the evaluation scripts write each one as ``'iou {:6f}'``
+    (iouenergythreshold.py:235-236) and areaundercurve.py:28-31 parses that text back, so its AUC is computed from values
+    rounded to six decimals."""
+    return np.array([float('{:6f}'.format(float(r))) for r in np.asarray(rates, dtype=np.float64)], dtype=np.float64)
 
 
 # ---------------------------------------------------------------------------------------------

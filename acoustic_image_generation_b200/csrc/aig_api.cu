@@ -23,8 +23,13 @@
 #include "energy_kernel.cuh"
 #include "frontend_kernel.cuh"
 #include "fused_kernel.cuh"
+#include "heatmap_kernel.cuh"
 #include "mfcc_kernel.cuh"
 #include "score_kernel.cuh"
+
+#ifndef AIG_BUILD_ID_STRING
+#define AIG_BUILD_ID_STRING "unstamped"
+#endif
 
 namespace {
 
@@ -65,6 +70,14 @@ MemKind classify(const void* p) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Entry points that touch several devices, or a device other than the caller's, put the calling thread's current device
+// back (torch and other CUDA users of the thread rely on it).  Calls on a handle leave that handle's device current.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+    ~DeviceGuard() { if (prev >= 0) { cudaSetDevice(prev); cudaGetLastError(); } }
+};
+
 // ---- NCCL through dlopen --------------------------------------------------------------------------
 struct NcclId { char internal[AIG_COMM_ID_BYTES]; };
 struct NcclApi {
@@ -73,6 +86,9 @@ struct NcclApi {
     int (*comm_init_rank)(void**, int, NcclId, int) = nullptr;
     int (*all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*comm_destroy)(void*) = nullptr;
+    int (*comm_init_all)(void**, int, const int*) = nullptr;
+    int (*group_start)() = nullptr;
+    int (*group_end)() = nullptr;
     const char* (*get_error_string)(int) = nullptr;
 };
 NcclApi& nccl() {
@@ -87,6 +103,9 @@ NcclApi& nccl() {
     api.all_reduce = reinterpret_cast<decltype(api.all_reduce)>(dlsym(lib, "ncclAllReduce"));
     api.comm_destroy = reinterpret_cast<decltype(api.comm_destroy)>(dlsym(lib, "ncclCommDestroy"));
     api.get_error_string = reinterpret_cast<decltype(api.get_error_string)>(dlsym(lib, "ncclGetErrorString"));
+    api.comm_init_all = reinterpret_cast<decltype(api.comm_init_all)>(dlsym(lib, "ncclCommInitAll"));
+    api.group_start = reinterpret_cast<decltype(api.group_start)>(dlsym(lib, "ncclGroupStart"));
+    api.group_end = reinterpret_cast<decltype(api.group_end)>(dlsym(lib, "ncclGroupEnd"));
     api.ok = api.get_unique_id && api.comm_init_rank && api.all_reduce && api.comm_destroy;
     return api;
 }
@@ -123,10 +142,14 @@ struct aig_handle {
     int heatmap_exact = 0;              // 1: float64 replica of the oracle's bilinear; 0: float32 fast path
     bool heat_attr_set = false;
     bool heat_exact_attr_set = false;
+    bool heat_stream_attr_set = false;
+    int heat_bulk_store = 1;            // 0: round-1 per-thread-store kernel for every shape (comparison runs)
+    int small_batch_frames = 0;         // below this many frames a frame is split over a cluster of 8 CTAs; 0: SM count
+    unsigned int debug_jitter = 0;      // non-zero: seed of the jittered build of the fused kernel (race stress tests)
     bool mask_attr_set = false;
     int l2_evict_first = 0;             // L2 evict-first hint on the spectrum loads (measured slower: off)
     int keep_mfcc_in_l2 = 1;            // fused kernel: evict-last hint on the MFCC stores the energy warps re-read
-    bool fused_attr_set[4] = {false, false, false, false};
+    bool fused_attr_set[8] = {false, false, false, false, false, false, false, false};
     int chain_energy_ctas_per_sm = 3;   // footprint of the overlapped energy kernel (measured: profiles/r01_tune_chain.txt)
     // profiling: (start, stop) event pairs per launch, by kernel kind
     bool profile = false;
@@ -237,9 +260,16 @@ struct Io {
     aig_handle* h;
     bool any_host = false;
     bool failed = false;
+    int code = AIG_OK;               // first failure's status
     struct Pending { void* host; void* dev; size_t bytes; };
     std::vector<Pending> outs;
     explicit Io(aig_handle* handle) : h(handle) {}
+    // Error exit of an entry point: copies out of caller memory may already be in flight - they must have finished
+    // before the caller gets its buffers back.
+    int abort(int rc) {
+        if (any_host) { cudaStreamSynchronize(h->stream); cudaGetLastError(); }
+        return rc;
+    }
 
     template <typename T>
     const T* in(const T* p, size_t count) {
@@ -248,9 +278,10 @@ struct Io {
         if (kind == kDevice) return p;
         any_host = true;
         void* d = scratch(h, count * sizeof(T));
-        if (!d) { failed = true; return nullptr; }
-        if (upload_async(h, d, p, count * sizeof(T), kind, h->stream) != cudaSuccess) {
-            h->fail_cuda(cudaGetLastError(), "cudaMemcpyAsync(H2D)");
+        if (!d) { failed = true; code = AIG_ERR_ALLOC; return nullptr; }
+        const cudaError_t status = upload_async(h, d, p, count * sizeof(T), kind, h->stream);
+        if (status != cudaSuccess) {
+            code = h->fail_cuda(status, "host-to-device copy");
             failed = true;
             return nullptr;
         }
@@ -271,14 +302,16 @@ struct Io {
         if (classify(p) == kDevice) return p;
         any_host = true;
         void* d = scratch(h, count * sizeof(T));
-        if (!d) { failed = true; return nullptr; }
+        if (!d) { failed = true; code = AIG_ERR_ALLOC; return nullptr; }
         outs.push_back({p, d, count * sizeof(T)});
         return static_cast<T*>(d);
     }
     int finish() {
-        if (failed) return h->err.empty() ? h->fail(AIG_ERR_ALLOC, "staging failed") : AIG_ERR_ALLOC;
-        for (auto& o : outs)
-            AIG_CK(download(h, o.host, o.dev, o.bytes, classify(o.host), h->stream));
+        if (failed) return abort(code != AIG_OK ? code : h->fail(AIG_ERR_ALLOC, "staging failed"));
+        for (auto& o : outs) {
+            const cudaError_t status = download(h, o.host, o.dev, o.bytes, classify(o.host), h->stream);
+            if (status != cudaSuccess) return abort(h->fail_cuda(status, "device-to-host copy"));
+        }
         if (any_host) AIG_CK(cudaStreamSynchronize(h->stream));
         return AIG_OK;
     }
@@ -421,13 +454,30 @@ int launch_mfcc(aig_handle* h, const float* d_power, int64_t n_rows, float* d_ou
     return AIG_OK;
 }
 
+// Frames below which one frame is spread over a thread-block cluster of 8 CTAs (stage2_cluster_kernel): with fewer frames
+// than SMs a CTA per frame leaves SMs idle and a call costs a whole frame's 27 rounds.
+int64_t small_batch_limit(const aig_handle* h) { return h->small_batch_frames > 0 ? h->small_batch_frames : h->sm_count; }
+
+// aig_energy (GROUPS = 1) and aig_acivw_batch (GROUPS = 2) on device buffers.
+template <int GROUPS>
+int launch_stage2(aig_handle* h, cudaStream_t stream, const Stage2Args& args, int ctas_per_sm = 8) {
+    if (args.n_frames == 0) return AIG_OK;
+    LaunchScope scope(h, stream, kKindEnergy);
+    if (args.n_frames < small_batch_limit(h)) {
+        const int64_t clusters = std::min<int64_t>(args.n_frames, 4 * h->sm_count);
+        stage2_cluster_kernel<GROUPS><<<static_cast<unsigned>(clusters * kClusterSize), GROUPS * kClusterGroupThreads, 0, stream>>>(args);
+        return scope.done("stage2_cluster_kernel");
+    }
+    stage2_kernel<GROUPS><<<frames_grid(h, args.n_frames, std::min(ctas_per_sm, 8 / GROUPS)), GROUPS * kEnergyThreads, 0, stream>>>(args);
+    return scope.done("stage2_kernel");
+}
+
 int launch_energy(aig_handle* h, cudaStream_t stream, const float* d_images, int64_t n_frames, int normalize_first,
                   float* d_scaled, double* d_energy, uint8_t* d_mask, double* d_mean, int ctas_per_sm = 8) {
-    if (n_frames == 0) return AIG_OK;
-    LaunchScope scope(h, stream, kKindEnergy);
-    energy_kernel<<<frames_grid(h, n_frames, ctas_per_sm), kEnergyThreads, 0, stream>>>(
-        d_images, n_frames, normalize_first, d_scaled, d_energy, d_mask, d_mean);
-    return scope.done("energy_kernel");
+    Stage2Args args = {};
+    args.img[0] = d_images; args.scaled[0] = d_scaled; args.energy[0] = d_energy; args.mask[0] = d_mask; args.mean[0] = d_mean;
+    args.n_frames = n_frames; args.normalize_first = normalize_first;
+    return launch_stage2<1>(h, stream, args, ctas_per_sm);
 }
 
 // resize_mask_kernel / ciou_sweep_kernel keep 36 blended rows of out_w uint16 in shared memory: up to 184 KiB at 2048 x 2048
@@ -444,7 +494,42 @@ int mask_ctas_per_sm(size_t smem) {
     return static_cast<int>(std::max<size_t>(1, std::min<size_t>(8, kMaskSmemLimit / (smem + 4 * 1024))));
 }
 
+// heat_stream_kernel needs every output row pair to start on a 16-byte boundary and be a 16-byte multiple long.
+bool heat_stream_ok(const aig_handle* h, int out_h, int out_w, const float* d_heat, bool fused) {
+    return h->heat_bulk_store && !h->heatmap_exact && out_w % 2 == 0 && (static_cast<long long>(out_h) * out_w) % 4 == 0 &&
+           (reinterpret_cast<uintptr_t>(d_heat) & 15u) == 0 && heat_stream_layout(out_h, out_w, fused).total <= 100 * 1024;
+}
+
+template <bool FUSED>
+int launch_heat_stream(aig_handle* h, const HeatStreamArgs& args) {
+    if (!h->heat_stream_attr_set) {
+        AIG_CK(cudaFuncSetAttribute(heat_stream_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        AIG_CK(cudaFuncSetAttribute(heat_stream_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        AIG_CK(cudaFuncSetAttribute(heat_stream_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        AIG_CK(cudaFuncSetAttribute(heat_stream_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        cudaFuncSetAttribute(heat_stream_kernel<false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(heat_stream_kernel<false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(heat_stream_kernel<true, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(heat_stream_kernel<true, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        h->heat_stream_attr_set = true;
+    }
+    const size_t smem = heat_stream_layout(args.out_h, args.out_w, FUSED).total;
+    const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(2, (226 * 1024) / (smem + 4 * 1024))));
+    const int grid = frames_grid(h, args.n_frames, per_sm);
+    LaunchScope scope(h, h->stream, FUSED ? kKindEnergy : kKindOther);
+    if (args.out_w % 4 == 0)
+        heat_stream_kernel<FUSED, 4><<<grid, kStreamThreads, smem, h->stream>>>(args);
+    else
+        heat_stream_kernel<FUSED, 2><<<grid, kStreamThreads, smem, h->stream>>>(args);
+    return scope.done("heat_stream_kernel");
+}
+
 int launch_heatmap(aig_handle* h, const double* d_energy, int64_t n_frames, int out_h, int out_w, float* d_heat) {
+    if (heat_stream_ok(h, out_h, out_w, d_heat, false)) {
+        HeatStreamArgs args = {};
+        args.energy_in = d_energy; args.n_frames = n_frames; args.out_h = out_h; args.out_w = out_w; args.heat = d_heat;
+        return launch_heat_stream<false>(h, args);
+    }
     const size_t fast_smem = (static_cast<size_t>(kFrameH) * out_w + 2 * static_cast<size_t>(out_w + out_h)) * sizeof(float);
     LaunchScope scope(h, h->stream, kKindOther);
     if (!h->heatmap_exact && fast_smem <= 200 * 1024) {
@@ -488,20 +573,21 @@ constexpr FusedVariant kFusedVariants[kNumFusedVariants] = {
     {4, 2},    // 2: 96 KiB stages x 2
 };
 
-template <int V>
+template <int V, bool JITTER>
 int launch_fused_variant(aig_handle* h, const CUtensorMap& map, float* d_mfcc, unsigned n_frames, int flip180,
                          int normalize_first, double* d_energy, uint8_t* d_mask, double* d_mean) {
     constexpr FusedVariant v = kFusedVariants[V];
     using F = FusedPipe<v.slabs, v.stages>;
-    auto kernel = mfcc_energy_fused_kernel<v.slabs, v.stages>;
-    if (!h->fused_attr_set[V]) {
+    auto kernel = mfcc_energy_fused_kernel<v.slabs, v.stages, JITTER>;
+    if (!h->fused_attr_set[V + (JITTER ? 4 : 0)]) {
         AIG_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F::kSmemBytes));
-        h->fused_attr_set[V] = true;
+        h->fused_attr_set[V + (JITTER ? 4 : 0)] = true;
     }
     const unsigned grid = std::min<unsigned>(n_frames, static_cast<unsigned>(h->sm_count));
     LaunchScope scope(h, h->stream, kKindMfcc);
     kernel<<<grid, kFusedThreads, F::kSmemBytes, h->stream>>>(map, d_mfcc, n_frames, flip180, normalize_first, d_energy,
-                                                             d_mask, d_mean, h->l2_evict_first, h->keep_mfcc_in_l2);
+                                                             d_mask, d_mean, h->l2_evict_first, h->keep_mfcc_in_l2,
+                                                             h->debug_jitter);
     return scope.done("mfcc_energy_fused_kernel");
 }
 
@@ -521,11 +607,15 @@ int launch_fused(aig_handle* h, const float* d_power, int64_t n_frames, float* d
         uint8_t* mk = d_mask ? d_mask + done * kFramePixels : nullptr;
         double* mn = d_mean ? d_mean + done : nullptr;
         const unsigned f = static_cast<unsigned>(frames);
-        switch (h->fused_variant) {
-            case 0: rc = launch_fused_variant<0>(h, map, mf, f, flip180, normalize_first, en, mk, mn); break;
-            case 1: rc = launch_fused_variant<1>(h, map, mf, f, flip180, normalize_first, en, mk, mn); break;
-            case 2: rc = launch_fused_variant<2>(h, map, mf, f, flip180, normalize_first, en, mk, mn); break;
-            default: rc = h->fail(AIG_ERR_ARGUMENT, "unknown fused kernel variant %d", h->fused_variant);
+        if (h->debug_jitter != 0) {              // the jittered build exists for the default ring geometry only
+            rc = launch_fused_variant<2, true>(h, map, mf, f, flip180, normalize_first, en, mk, mn);
+        } else {
+            switch (h->fused_variant) {
+                case 0: rc = launch_fused_variant<0, false>(h, map, mf, f, flip180, normalize_first, en, mk, mn); break;
+                case 1: rc = launch_fused_variant<1, false>(h, map, mf, f, flip180, normalize_first, en, mk, mn); break;
+                case 2: rc = launch_fused_variant<2, false>(h, map, mf, f, flip180, normalize_first, en, mk, mn); break;
+                default: rc = h->fail(AIG_ERR_ARGUMENT, "unknown fused kernel variant %d", h->fused_variant);
+            }
         }
         if (rc != AIG_OK) return rc;
     }
@@ -568,9 +658,14 @@ int stream_host_rows(aig_handle* h, const float* host, int64_t n_rows, int row_f
     return AIG_OK;
 }
 
-int64_t host_chunk_rows(int64_t unit_rows, int row_floats) {
-    const int64_t target = int64_t(64) << 20;   // ~64 MiB per H2D copy
+// Rows per H2D chunk of a host-input call: ~64 MiB for long calls (a copy engine is at the link rate from 4 MiB up and
+// fewer chunks mean fewer launches), but at least six chunks per call down to 8 MiB each, so that a 16-frame call
+// (BASELINE configs[0], 56.6 MB) still overlaps its copies with its kernels and result copies instead of running them
+// back to back.
+int64_t host_chunk_rows(int64_t unit_rows, int row_floats, int64_t total_rows) {
     const int64_t unit_bytes = unit_rows * row_floats * 4;
+    const int64_t total_bytes = total_rows * row_floats * 4;
+    const int64_t target = std::min<int64_t>(int64_t(64) << 20, std::max<int64_t>(int64_t(8) << 20, total_bytes / 6));
     return std::max<int64_t>(1, target / unit_bytes) * unit_rows;
 }
 
@@ -580,6 +675,12 @@ int64_t host_chunk_rows(int64_t unit_rows, int row_floats) {
 extern "C" {
 
 int aig_abi_version(void) { return AIG_ABI_VERSION; }
+
+// The marker prefix lets the Python loader read the stamp from the file without dlopen (see _lib.binary_build_id).
+const char* aig_build_id(void) {
+    static const char stamp[] = "AIG_BUILD_ID=" AIG_BUILD_ID_STRING;
+    return stamp + 13;
+}
 
 const char* aig_last_error(const aig_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -709,6 +810,14 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
         h->keep_mfcc_in_l2 = value != 0;
     } else if (key == "l2_evict_first") {
         h->l2_evict_first = value != 0;
+    } else if (key == "heat_bulk_store") {
+        h->heat_bulk_store = value != 0;
+    } else if (key == "small_batch_frames") {
+        if (value < 0 || value > (1 << 20)) return h->fail(AIG_ERR_ARGUMENT, "small_batch_frames out of range");
+        h->small_batch_frames = static_cast<int>(value);
+    } else if (key == "debug_jitter") {
+        if (value < 0 || value > 0x7fffffff) return h->fail(AIG_ERR_ARGUMENT, "debug_jitter: seed out of range");
+        h->debug_jitter = static_cast<unsigned int>(value);
     } else if (key == "profile") {
         h->profile = value != 0;
     } else {
@@ -720,15 +829,17 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
 int aig_selftest(aig_handle* h, int which, uint64_t* out) {
     int rc = require(h);
     if (rc != AIG_OK) return rc;
-    if (out == nullptr || which < 0 || which > 1) return h->fail(AIG_ERR_ARGUMENT, "aig_selftest: bad arguments");
+    if (out == nullptr || which < 0 || which > 2) return h->fail(AIG_ERR_ARGUMENT, "aig_selftest: bad arguments");
     unsigned long long* d_out = static_cast<unsigned long long*>(scratch(h, 4 * sizeof(unsigned long long)));
     if (!d_out) return AIG_ERR_ALLOC;
     AIG_CK(cudaMemsetAsync(d_out, 0, 4 * sizeof(unsigned long long), h->stream));
     LaunchScope scope(h, h->stream, kKindOther);
     if (which == 0)
         selftest_division_kernel<<<h->sm_count * 16, 256, 0, h->stream>>>(d_out);
-    else
+    else if (which == 1)
         selftest_exp_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(1ull << 26, d_out);
+    else
+        selftest_norm_kernel<<<h->sm_count * 16, 256, 0, h->stream>>>(d_out);
     rc = scope.done("selftest kernel");
     if (rc != AIG_OK) return rc;
     AIG_CK(cudaMemcpyAsync(out, d_out, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
@@ -816,7 +927,7 @@ int aig_mfcc(aig_handle* h, const float* power, int64_t n_rows, float* mfcc_out,
         rc = launch_mfcc(h, power, n_rows, d_out, flip180, frame_pixels);
         if (rc != AIG_OK) return rc;
     } else {
-        const int64_t chunk = host_chunk_rows(flip180 ? frame_pixels : 128, in_floats);
+        const int64_t chunk = host_chunk_rows(flip180 ? frame_pixels : 128, in_floats, n_rows);
         rc = stream_host_rows(h, power, n_rows, in_floats, chunk, [&](const float* d_chunk, int64_t row, int64_t rows) {
             return launch_mfcc(h, d_chunk, rows, d_out + row * out_floats, flip180, frame_pixels);
         });
@@ -841,7 +952,7 @@ int aig_normalize_images(aig_handle* h, const float* images, int64_t n_frames, f
     LaunchScope scope(h, h->stream, kKindOther);
     normalize_kernel<<<frames_grid(h, n_frames, 8), 256, 0, h->stream>>>(d_in, n_frames, d_out);
     rc = scope.done("normalize_kernel");
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 
@@ -859,8 +970,10 @@ int aig_energy(aig_handle* h, const float* images, int64_t n_frames, int normali
     uint8_t* d_mask = io.out(mask_out, n * kFramePixels);
     double* d_mean = io.out(mean_out, n);
     if (io.failed) return io.finish();
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15u) || (reinterpret_cast<uintptr_t>(d_scaled) & 7u))
+        return io.abort(h->fail(AIG_ERR_ARGUMENT, "aig_energy: device image buffers must be 16-byte aligned"));
     rc = launch_energy(h, h->stream, d_in, n_frames, normalize_first, d_scaled, d_energy, d_mask, d_mean);
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 
@@ -877,7 +990,7 @@ int aig_heatmap(aig_handle* h, const double* energy, int64_t n_frames, int out_h
     float* d_heat = io.out(heat_out, n * out_h * out_w);
     if (io.failed) return io.finish();
     rc = launch_heatmap(h, d_energy, n_frames, out_h, out_w, d_heat);
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 
@@ -892,14 +1005,63 @@ int aig_energy_heatmap(aig_handle* h, const float* images, int64_t n_frames, int
     Io io(h);
     const size_t n = static_cast<size_t>(n_frames);
     const float* d_in = io.in(images, n * kFrameValues);
-    double* d_energy = energy_out ? io.out(energy_out, n * kFramePixels) : static_cast<double*>(scratch(h, n * kFramePixels * sizeof(double)));
+    double* d_energy = io.out(energy_out, n * kFramePixels);
     uint8_t* d_mask = io.out(mask_out, n * kFramePixels);
     float* d_heat = io.out(heat_out, n * out_h * out_w);
-    if (io.failed || !d_energy) return io.finish();
+    if (io.failed) return io.finish();
+    // One launch: the energy map goes from the float64 warps to the up-sampling passes through shared memory.  Small
+    // batches (fewer frames than SMs) and shapes the streaming kernel cannot take run the two kernels back to back.
+    if (heat_stream_ok(h, out_h, out_w, d_heat, true) && n_frames >= small_batch_limit(h)) {
+        HeatStreamArgs args = {};
+        args.s2.img[0] = d_in; args.s2.energy[0] = d_energy; args.s2.mask[0] = d_mask;
+        args.s2.n_frames = n_frames; args.s2.normalize_first = normalize_first;
+        args.n_frames = n_frames; args.out_h = out_h; args.out_w = out_w; args.heat = d_heat;
+        rc = launch_heat_stream<true>(h, args);
+        if (rc != AIG_OK) return io.abort(rc);
+        return io.finish();
+    }
+    if (d_energy == nullptr) d_energy = static_cast<double*>(scratch(h, n * kFramePixels * sizeof(double)));
+    if (d_energy == nullptr) return io.abort(AIG_ERR_ALLOC);
     rc = launch_energy(h, h->stream, d_in, n_frames, normalize_first, nullptr, d_energy, d_mask, nullptr);
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     rc = launch_heatmap(h, d_energy, n_frames, out_h, out_w, d_heat);
+    if (rc != AIG_OK) return io.abort(rc);
+    return io.finish();
+}
+
+int aig_acivw_batch(aig_handle* h, const float* real, const float* reconstructed, int64_t n_frames, int normalize_first,
+                    const double* thr, int k, int64_t* inter_out, int64_t* union_out, int64_t* pos_inout,
+                    int64_t* num_inout, double* energy_real_out, double* energy_recon_out, uint8_t* mask_real_out,
+                    uint8_t* mask_recon_out) {
+    int rc = require(h);
     if (rc != AIG_OK) return rc;
+    if (n_frames < 0 || k < 0 || k > kMaxThresholds)
+        return h->fail(AIG_ERR_ARGUMENT, "aig_acivw_batch: n=%lld k=%d out of range (k <= %d)", (long long)n_frames, k, kMaxThresholds);
+    if ((k > 0 && (!thr || !pos_inout)) || !num_inout) return h->fail(AIG_ERR_ARGUMENT, "aig_acivw_batch: null threshold / count buffers");
+    if (n_frames > 0 && (!real || !reconstructed)) return h->fail(AIG_ERR_ARGUMENT, "aig_acivw_batch: null images");
+    if (n_frames == 0) return AIG_OK;
+    Io io(h);
+    const size_t n = static_cast<size_t>(n_frames);
+    Stage2Args args = {};
+    args.img[0] = io.in(real, n * kFrameValues);
+    args.img[1] = io.in(reconstructed, n * kFrameValues);
+    args.energy[0] = io.out(energy_real_out, n * kFramePixels);
+    args.energy[1] = io.out(energy_recon_out, n * kFramePixels);
+    args.mask[0] = io.out(mask_real_out, n * kFramePixels);
+    args.mask[1] = io.out(mask_recon_out, n * kFramePixels);
+    args.thr = io.in(thr, static_cast<size_t>(k));
+    args.k_thr = k;
+    args.inter = reinterpret_cast<long long*>(io.out(inter_out, n));
+    args.uni = reinterpret_cast<long long*>(io.out(union_out, n));
+    args.pos = reinterpret_cast<unsigned long long*>(io.inout(pos_inout, static_cast<size_t>(k)));
+    args.num = reinterpret_cast<unsigned long long*>(io.inout(num_inout, 1));
+    args.n_frames = n_frames;
+    args.normalize_first = normalize_first;
+    if (io.failed) return io.finish();
+    if ((reinterpret_cast<uintptr_t>(args.img[0]) & 15u) || (reinterpret_cast<uintptr_t>(args.img[1]) & 15u))
+        return io.abort(h->fail(AIG_ERR_ARGUMENT, "aig_acivw_batch: image buffers must be 16-byte aligned"));
+    rc = launch_stage2<2>(h, h->stream, args);
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 
@@ -917,11 +1079,11 @@ int aig_resize_mask(aig_handle* h, const uint8_t* mask, int64_t n_frames, int ou
     if (io.failed) return io.finish();
     const size_t smem = MaskTaps::bytes(out_h, out_w);
     rc = allow_mask_smem(h);
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     LaunchScope scope(h, h->stream, kKindOther);
     resize_mask_kernel<<<frames_grid(h, n_frames, mask_ctas_per_sm(smem)), kHeatThreads, smem, h->stream>>>(d_mask, n_frames, out_h, out_w, d_up);
     rc = scope.done("resize_mask_kernel");
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 
@@ -952,8 +1114,10 @@ int aig_mfcc_energy(aig_handle* h, const float* power, int64_t n_frames, int fli
         AIG_CK(cudaStreamWaitEvent(h->aux_stream, h->ev_chain[0], 0));
     }
     int64_t chunk_index = 0;
+    // The persistent kernel gives one CTA a whole frame; with fewer frames than SMs the tiled MFCC kernel followed by the
+    // cluster-per-frame energy kernel uses the whole GPU instead (same results bit for bit).
     auto run = [&](const float* d_power, int64_t frame0, int64_t frames) -> int {
-        if (fused)
+        if (fused && (frames >= small_batch_limit(h) || h->debug_jitter != 0))
             return launch_fused(h, d_power, frames, d_mfcc + frame0 * kFrameValues, flip180, normalize_first,
                                 d_energy ? d_energy + frame0 * kFramePixels : nullptr,
                                 d_mask ? d_mask + frame0 * kFramePixels : nullptr, d_mean ? d_mean + frame0 : nullptr);
@@ -1000,7 +1164,7 @@ int aig_mfcc_energy(aig_handle* h, const float* power, int64_t n_frames, int fli
                 }
             d2h_overlapped = !host_outs.empty();
         }
-        const int64_t chunk_rows = host_chunk_rows(kFramePixels, kFftLen);
+        const int64_t chunk_rows = host_chunk_rows(kFramePixels, kFftLen, n_frames * kFramePixels);
         rc = stream_host_rows(h, power, n_frames * kFramePixels, kFftLen, chunk_rows,
                               [&](const float* d_chunk, int64_t row, int64_t rows) {
                                   const int64_t f0 = row / kFramePixels, nf = rows / kFramePixels;
@@ -1016,7 +1180,7 @@ int aig_mfcc_energy(aig_handle* h, const float* power, int64_t n_frames, int fli
                               });
     }
     if (d2h_overlapped) AIG_CK(cudaStreamSynchronize(h->aux_stream));
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     if (overlap) {
         AIG_CK(cudaEventRecord(h->ev_chain[3], h->aux_stream));          // results visible to the handle's stream
         AIG_CK(cudaStreamWaitEvent(h->stream, h->ev_chain[3], 0));
@@ -1049,7 +1213,7 @@ int aig_iou_sweep(aig_handle* h, const uint8_t* mask_a, const uint8_t* mask_b, i
     int64_t* d_num = io.inout(num_inout, 1);
     if (io.failed) return io.finish();
     if ((reinterpret_cast<uintptr_t>(d_a) & 3u) || (reinterpret_cast<uintptr_t>(d_b) & 3u))
-        return h->fail(AIG_ERR_ARGUMENT, "aig_iou_sweep: mask buffers must be 4-byte aligned");
+        return io.abort(h->fail(AIG_ERR_ARGUMENT, "aig_iou_sweep: mask buffers must be 4-byte aligned"));
     const int blocks = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 4));
     LaunchScope scope(h, h->stream, kKindOther);
     iou_sweep_kernel<<<blocks, kIouThreads, 0, h->stream>>>(d_a, d_b, n, d_thr, k, reinterpret_cast<long long*>(d_inter),
@@ -1057,7 +1221,7 @@ int aig_iou_sweep(aig_handle* h, const uint8_t* mask_a, const uint8_t* mask_b, i
                                                             reinterpret_cast<unsigned long long*>(d_pos),
                                                             reinterpret_cast<unsigned long long*>(d_num));
     rc = scope.done("iou_sweep_kernel");
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 
@@ -1081,7 +1245,7 @@ int aig_iou_sweep_clips(aig_handle* h, const uint8_t* mask_a, const uint8_t* mas
     int64_t* d_pos = io.inout(pos_inout, n_clips * k);
     if (io.failed) return io.finish();
     if ((reinterpret_cast<uintptr_t>(d_a) & 3u) || (reinterpret_cast<uintptr_t>(d_b) & 3u))
-        return h->fail(AIG_ERR_ARGUMENT, "aig_iou_sweep_clips: mask buffers must be 4-byte aligned");
+        return io.abort(h->fail(AIG_ERR_ARGUMENT, "aig_iou_sweep_clips: mask buffers must be 4-byte aligned"));
     const int blocks = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 8));
     LaunchScope scope(h, h->stream, kKindOther);
     iou_sweep_clips_kernel<<<blocks, kIouThreads, 0, h->stream>>>(d_a, d_b, n, frames_per_clip, d_thr, k,
@@ -1089,7 +1253,7 @@ int aig_iou_sweep_clips(aig_handle* h, const uint8_t* mask_a, const uint8_t* mas
                                                                   reinterpret_cast<long long*>(d_union),
                                                                   reinterpret_cast<unsigned long long*>(d_pos));
     rc = scope.done("iou_sweep_clips_kernel");
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 
@@ -1119,14 +1283,14 @@ int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, cons
     if (io.failed) return io.finish();
     const size_t smem = MaskTaps::bytes(out_h, out_w) + static_cast<size_t>(out_w + out_h);
     rc = allow_mask_smem(h);
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     LaunchScope scope(h, h->stream, kKindOther);
     ciou_sweep_kernel<<<frames_grid(h, n, mask_ctas_per_sm(smem)), kIouThreads, smem, h->stream>>>(
         d_mask, d_xmin, d_xmax, d_ymin, d_ymax, n, out_h, out_w, d_thr, k, reinterpret_cast<long long*>(d_inter),
         reinterpret_cast<long long*>(d_union), reinterpret_cast<unsigned long long*>(d_pos),
         reinterpret_cast<unsigned long long*>(d_num));
     rc = scope.done("ciou_sweep_kernel");
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 
@@ -1170,7 +1334,7 @@ int aig_power_spectrum(aig_handle* h, const void* audio, int audio_is_int32, int
     float* d_out = io.out(power_out, n * (kAudioSamples / 2));
     if (io.failed) return io.finish();
     rc = launch_spectrum(h, d_in, audio_is_int32, n_rows, d_win, d_out);
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 
@@ -1193,9 +1357,9 @@ int aig_audio_mfcc(aig_handle* h, const void* audio, int audio_is_int32, int64_t
     float* d_power = static_cast<float*>(scratch(h, n * (kAudioSamples / 2) * sizeof(float)));   // never leaves the device
     if (io.failed || !d_power) { io.failed = true; return io.finish(); }
     rc = launch_spectrum(h, d_in, audio_is_int32, n_rows, d_win, d_power);
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     rc = launch_mfcc(h, d_power, n_rows, d_out, 0, 1);
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 
@@ -1227,7 +1391,7 @@ int aig_filtfilt(aig_handle* h, const void* x, int x_is_int32, int64_t n_rows, i
     else
         filtfilt_kernel<float><<<blocks, threads, 0, h->stream>>>(d_x, n_rows, length, ntaps, pad, d_coef, d_scratch, d_y);
     rc = scope.done("filtfilt_kernel");
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 
@@ -1243,7 +1407,7 @@ int aig_normalize_mfcc(aig_handle* h, const float* mfcc, int64_t n, float* out) 
     LaunchScope scope(h, h->stream, kKindOther);
     normalize_mfcc_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, h->stream>>>(d_in, n, d_out);
     rc = scope.done("normalize_mfcc_kernel");
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 
@@ -1259,7 +1423,7 @@ int aig_tile_mfcc(aig_handle* h, const float* mfcc, int64_t n, int normalize, fl
     LaunchScope scope(h, h->stream, kKindOther);
     tile_mfcc_kernel<<<frames_grid(h, n, 8), kTileThreads, 0, h->stream>>>(d_in, n, normalize, d_out);
     rc = scope.done("tile_mfcc_kernel");
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 
@@ -1280,7 +1444,7 @@ int aig_split_triplets(aig_handle* h, const float* images, int64_t n_frames, flo
     LaunchScope scope(h, h->stream, kKindOther);
     split_triplets_kernel<<<grid, kTripletThreads, 0, h->stream>>>(d_in, n_pixels, d_out);
     rc = scope.done("split_triplets_kernel");
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 
@@ -1302,13 +1466,13 @@ int aig_triplet_mse(aig_handle* h, const float* a, const float* b, int64_t n_fra
         LaunchScope scope(h, h->stream, kKindOther);
         triplet_mse_kernel<<<grid, kTripletThreads, 0, h->stream>>>(d_a, d_b, n_pixels, d_partial);
         rc = scope.done("triplet_mse_kernel");
-        if (rc != AIG_OK) return rc;
+        if (rc != AIG_OK) return io.abort(rc);
     }
     {
         LaunchScope scope(h, h->stream, kKindOther);
         triplet_mse_finish_kernel<<<1, 32, 0, h->stream>>>(d_partial, grid, n_pixels, d_out);
         rc = scope.done("triplet_mse_finish_kernel");
-        if (rc != AIG_OK) return rc;
+        if (rc != AIG_OK) return io.abort(rc);
     }
     return io.finish();
 }
@@ -1336,7 +1500,7 @@ int aig_overlay(aig_handle* h, const float* heat, const uint8_t* bgr, int64_t n_
     else
         overlay_kernel<1><<<frames_grid(h, n_frames, 8), 256, 0, h->stream>>>(d_heat, d_bgr, n_frames, static_cast<int>(px), alpha, d_lut, d_out);
     rc = scope.done("overlay_kernel");
-    if (rc != AIG_OK) return rc;
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 
@@ -1385,13 +1549,58 @@ int aig_allreduce_counts(aig_handle* h, int64_t* counts, int n) {
     int rc = require(h);
     if (rc != AIG_OK) return rc;
     if (counts == nullptr || n < 0) return h->fail(AIG_ERR_ARGUMENT, "aig_allreduce_counts: bad buffer");
-    if (h->comm == nullptr || h->comm_world == 1 || n == 0) return AIG_OK;    // single rank: identity
+    if (h->comm == nullptr || n == 0) return AIG_OK;    // no communicator: identity (a one-rank communicator still runs NCCL)
     Io io(h);
     int64_t* d = io.inout(counts, static_cast<size_t>(n));
     if (io.failed) return io.finish();
     const int r = nccl().all_reduce(d, d, static_cast<size_t>(n), kNcclInt64, kNcclSum, h->comm, h->stream);
     if (r != 0) return h->fail(AIG_ERR_CUDA_BASE, "ncclAllReduce failed: %s", nccl().get_error_string ? nccl().get_error_string(r) : "?");
     return io.finish();
+}
+
+int aig_comm_init_all(aig_handle** handles, int n) {
+    if (handles == nullptr || n < 1) return AIG_ERR_ARGUMENT;
+    for (int i = 0; i < n; ++i) if (handles[i] == nullptr) return AIG_ERR_ARGUMENT;
+    aig_handle* h0 = handles[0];
+    DeviceGuard guard;
+    NcclApi& api = nccl();
+    if (!api.ok || !api.comm_init_all) return h0->fail(AIG_ERR_NO_DEVICE, "aig_comm_init_all: libnccl.so.2 could not be loaded");
+    std::vector<int> devices(n);
+    std::vector<void*> comms(n, nullptr);
+    for (int i = 0; i < n; ++i) {
+        aig_comm_destroy(handles[i]);
+        devices[i] = handles[i]->device;
+        for (int j = 0; j < i; ++j)
+            if (devices[j] == devices[i]) return h0->fail(AIG_ERR_ARGUMENT, "aig_comm_init_all: device %d listed twice", devices[i]);
+    }
+    const int r = api.comm_init_all(comms.data(), n, devices.data());
+    if (r != 0) return h0->fail(AIG_ERR_CUDA_BASE, "ncclCommInitAll failed: %s", api.get_error_string ? api.get_error_string(r) : "?");
+    for (int i = 0; i < n; ++i) { handles[i]->comm = comms[i]; handles[i]->comm_world = n; }
+    return AIG_OK;
+}
+
+int aig_group_allreduce_counts(aig_handle** handles, int64_t* const* counts, int n_handles, int n) {
+    if (handles == nullptr || counts == nullptr || n_handles < 1 || n < 0) return AIG_ERR_ARGUMENT;
+    aig_handle* h0 = handles[0];
+    if (h0 == nullptr) return AIG_ERR_ARGUMENT;
+    NcclApi& api = nccl();
+    if (!api.ok || !api.group_start || !api.group_end) return h0->fail(AIG_ERR_NO_DEVICE, "aig_group_allreduce_counts: NCCL is not available");
+    for (int i = 0; i < n_handles; ++i) {
+        if (handles[i] == nullptr || counts[i] == nullptr || handles[i]->comm == nullptr || handles[i]->comm_world != n_handles)
+            return h0->fail(AIG_ERR_ARGUMENT, "aig_group_allreduce_counts: handle %d is not part of a %d-rank aig_comm_init_all communicator", i, n_handles);
+        if (classify(counts[i]) != kDevice) return h0->fail(AIG_ERR_ARGUMENT, "aig_group_allreduce_counts: counts[%d] must be device memory", i);
+    }
+    if (n == 0) return AIG_OK;
+    DeviceGuard guard;
+    int r = api.group_start();
+    for (int i = 0; i < n_handles && r == 0; ++i) {
+        cudaSetDevice(handles[i]->device);
+        r = api.all_reduce(counts[i], counts[i], static_cast<size_t>(n), kNcclInt64, kNcclSum, handles[i]->comm, handles[i]->stream);
+    }
+    const int r_end = api.group_end();
+    if (r == 0) r = r_end;
+    if (r != 0) return h0->fail(AIG_ERR_CUDA_BASE, "grouped ncclAllReduce failed: %s", api.get_error_string ? api.get_error_string(r) : "?");
+    return AIG_OK;
 }
 
 int aig_auc(const double* thr, const double* value, int k, double* auc_out) {

@@ -94,6 +94,43 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+// ---- bulk asynchronous stores shared -> global (TMA unit, SASS UBLKCP) ---------------------------
+// Generic-proxy writes to shared memory (st.shared) must be fenced before the async proxy reads them.
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// dst (global) and src (shared) 16-byte aligned, bytes a multiple of 16.  Completion is tracked by the issuing
+// thread's bulk-copy groups.
+__device__ __forceinline__ void bulk_store_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// Wait until at most N of this thread's groups are still reading their shared-memory source ...
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// ... or are incomplete altogether (writes performed).
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---- debug jitter ("debug_jitter" option) -------------------------------------------------------
+// compute-sanitizer's racecheck is not available on the pool this library is tested on.  The hand-rolled mbarrier
+// protocols are instead exercised by perturbing the relative timing of their roles: every call spins for a
+// pseudo-random 0 .. 2^14 cycles derived from (seed, salt, CTA, warp, call count).  A protocol that is only correct by
+// timing luck then produces results that differ from the sequential two-kernel path (tests/test_gpu_stress.py).
+__device__ __forceinline__ void jitter_spin(unsigned int seed, unsigned int salt, unsigned int& counter) {
+    unsigned int x = seed * 2654435761u ^ (salt + 0x9e3779b9u) * 40503u ^ (blockIdx.x * 977u + (threadIdx.x >> 5)) * 2246822519u ^
+                     (++counter) * 3266489917u;
+    x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+    if ((x & 3u) != 0u) return;                            // three calls out of four pass straight through
+    const long long until = clock64() + ((x >> 8) & 0x3fffu);
+    while (clock64() < until) {
+    }
+}
+
 // ---- shared-memory vector load ----------------------------------------------------------------
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;

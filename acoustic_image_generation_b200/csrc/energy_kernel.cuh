@@ -1,11 +1,12 @@
-// Stage 2 kernels: 12-channel acoustic image -> energy map, mean mask, up-sampled heat map.
+// Stage 2 kernels: 12-channel acoustic image -> energy map and mean mask (the heat map is heatmap_kernel.cuh).
 //
-// energy_kernel      F4 + F5 + F7  per-frame min-max (outdoor_data_mfcc.py:672-679), find_logen
-//                    (iouenergythreshold.py:294-323) and the mean-threshold mask (:217-219).
-// heatmap_kernel     F6            cv2.resize bilinear + implicit Normalize (showimages.py:147-148).
-// resize_mask_kernel F9 (part)     cv2.resize(mask) > 0.5 in exact integers (showimages_bb.py:303-304).
+// energy_kernel          F4 + F5 + F7  per-frame min-max (outdoor_data_mfcc.py:672-679), find_logen
+//                        (iouenergythreshold.py:294-323) and the mean-threshold mask (:217-219).
+// energy_cluster_kernel  the same for small batches: one frame per thread-block cluster of 8 CTAs.
+// acivw_kernel           the reference's whole evaluation step (iouenergythreshold.py:213-229) in one launch: real and
+// acivw_cluster_kernel   reconstructed image -> two energy maps -> two masks -> (I, U) -> success counts.
 //
-// One CTA per frame: the per-frame reductions (min, max, mean) are CTA-local.  The energy is
+// One CTA (or cluster) per frame: the per-frame reductions (min, max, mean) are CTA-local.  The energy is
 // computed in float64 like the reference (float32-stored in-place scaling, then a float64
 // 12x24 projection, exp, band sum in NumPy's pairwise order, reciprocal) so that the
 // `map > mean(map)` decision is reproduced bit for bit up to the last-ulp differences of exp()
@@ -13,6 +14,8 @@
 // for 1728 elements exactly.  FP64 work per frame is ~2 MFLOP, far below the HBM time of the
 // stage-1 stream it follows, and runs on the otherwise idle FP64 pipe.
 #pragma once
+
+#include <cooperative_groups.h>
 
 #include "aig_common.cuh"
 #include "mel_tables_ref.inc"
@@ -24,12 +27,7 @@ __constant__ double c_dct[kFilterNum * kMfccNum] = AIG_REF_DCT;      // [24][12]
 __constant__ double c_lifter[kMfccNum] = AIG_REF_LIFTER;
 __constant__ double c_mfnorm = AIG_REF_MFNORM;
 
-// 128 threads = one warp per SM sub-partition, so four CTAs per SM may use 128 registers each (the per-pixel float64
-// chain needs ~120; with 192-thread CTAs the uneven warp split capped it at 96 and it spilled).  13.5 pixels per thread:
-// in the 14th round the upper two warps idle.
-constexpr int kEnergyThreads = 128;
-constexpr int kPixelsPerThread = (kFramePixels + kEnergyThreads - 1) / kEnergyThreads;
-static_assert(kFramePixels % 64 == 0, "whole warps drop out of the last round");
+static_assert(kFramePixels % 64 == 0, "whole warp pairs drop out of the last round");
 
 // NumPy pairwise-sum leaves for n = 1728: 1728 -> 864 -> 432 -> 216 -> (104, 112); every leaf is
 // summed with 8 strided accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)).
@@ -90,12 +88,14 @@ __device__ __forceinline__ double exp_table64(double x, const double* __restrict
 
 // The plain form of one pixel (IEEE divisions, exp(), straight 12-term dot products), kept out of line: it serves the
 // pixels the fast path cannot (non-finite inputs, |mel| > 700) and is what the fast path is checked against.
-// `src` / `scaled_dst` are global-memory pointers (scaled_dst may be null).
-__device__ __noinline__ double pixel_energy_plain(const float* __restrict__ src, float* __restrict__ scaled_dst, bool normalize,
+// `raw` holds the pixel's 12 input values, already in registers: the image may alias `scaled_dst` (find_logen scales its
+// argument in place) or have been written by other warps of the same kernel (fused kernel), so it is never re-read
+// here through a read-only path.  scaled_dst may be null.
+__device__ __noinline__ double pixel_energy_plain(const float (&raw)[kMfccNum], float* scaled_dst, bool normalize,
                                                   float lo, float range) {
     double z[kMfccNum];
     for (int m = 0; m < kMfccNum; ++m) {
-        float v = src[m];
+        float v = raw[m];
         if (normalize) v = __fdiv_rn(__fsub_rn(v, lo), range);
         v = __double2float_rn(__ddiv_rn(static_cast<double>(v), c_lifter[m]));
         v = __double2float_rn(__dmul_rn(static_cast<double>(v), c_mfnorm));
@@ -248,110 +248,558 @@ __device__ __forceinline__ double frame_mean(const double* s_map, double (*s_par
     return *s_mean;
 }
 
-__global__ void __launch_bounds__(kEnergyThreads, 4)
-energy_kernel(const float* __restrict__ images, long long n_frames, int normalize_first,
-              float* __restrict__ scaled_out, double* __restrict__ energy_out,
-              uint8_t* __restrict__ mask_out, double* __restrict__ mean_out) {
-    __shared__ double s_map[kFramePixels];
-    __shared__ double s_part[16][8];
-    __shared__ double s_leaf[16];
-    __shared__ float s_red[2][kEnergyThreads / 32];
-    __shared__ double s_mean;
-    __shared__ double s_exp[64];
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    if (tid < 64) s_exp[tid] = c_exp2_table[tid];
-    __syncthreads();
 
-    for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
-        const float* img = images + frame * kFrameValues;
-        float lo = 0.f, range = 1.f;
-        if (normalize_first) {
-            // min and max of the frame; max(x - min) == fl(max - min) because rounding is monotonic
-            float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-            const float4* img4 = reinterpret_cast<const float4*>(img);
-            for (int i = tid; i < kFrameValues / 4; i += kEnergyThreads) {
-                const float4 v = __ldg(img4 + i);
-                mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
-                mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
-            }
-            mn = warp_min(mn);
-            mx = warp_max(mx);
-            if (lane == 0) { s_red[0][warp] = mn; s_red[1][warp] = mx; }
-            __syncthreads();
-            mn = s_red[0][0]; mx = s_red[1][0];
+// =====================================================================================================================
+// Two threads per pixel (energy_kernel, stage2_kernel, stage2_cluster_kernel)
+// =====================================================================================================================
+// One thread per pixel needs ~120 registers for the float64 chain of find_logen (12 scaled values, 24 exponentials in
+// flight, the NumPy-ordered band sums): 16 warps per SM, a dependent DFMA chain in each, and the FP64 pipe sat at 43 %
+// (profiles/r01_ncu_secondary_kernels.csv) with 116 bytes of spills.  Here a pixel is shared by the same lane of two
+// adjacent warps ("halves" of a warp pair).  The 24 mel bands fall into four groups of three (j, 23 - j) basis pairs,
+//     group g = pairs {g, 7 - g, 8 + g}  ->  bands {g, 23-g, 7-g, 16+g, 8+g, 15-g}  =  all terms of r[g] and r[7-g]
+// (r[k] = (e[k] + e[k+8]) + e[k+16] is NumPy's strided partial sum for n = 24), so half 0 (groups 0, 1) produces
+// r0, r1, r6, r7 and half 1 (groups 2, 3) r2..r5 without exchanging a single exponential; only the 6 + 6 scaled float32
+// channel values, two float64 partial sums (r2 + r3, r4 + r5) and a flag cross the pair, through shared memory around two
+// 64-thread named barriers.  Every operation keeps the order of pixel_energy(), so the result is bit-identical to the
+// one-thread form the fused kernel's energy warps run.  Which half a warp is decides its constants at compile time
+// (template parameter, warp-uniform branch): every DCT coefficient stays a constant-bank operand.
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// The per-frame min-max normalisation with the reciprocal hoisted out of the per-value division.  With r = RN(1 / range),
+// q0 = RN(d * r), rem = d - q0 * range (exact in one FMA), q = RN(q0 + rem * r) is the correctly rounded quotient
+// (Markstein) as long as nothing over- or underflows: taken when range and d are within 2^+-60, IEEE division otherwise
+// (zero, denormal, huge, non-finite).  aig_selftest(2) compares it with __fdiv_rn on 2^32 (d, range) pairs.
+struct FrameNormFast {
+    float lo, range, r;
+    bool fast;
+    __device__ __forceinline__ FrameNormFast(float lo_, float range_) : lo(lo_), range(range_) {
+        const unsigned int e = (__float_as_uint(range_) >> 23) & 0xffu;
+        fast = (e - 67u) <= 120u && range_ > 0.f;
+        r = fast ? __frcp_rn(range_) : 0.f;
+    }
+    __device__ __forceinline__ float apply(float x) const {
+        const float d = __fsub_rn(x, lo);
+        const unsigned int e = (__float_as_uint(d) >> 23) & 0xffu;
+        if (fast && (e - 67u) <= 120u) {
+            const float q0 = __fmul_rn(d, r);
+            const float rem = __fmaf_rn(-q0, range, d);
+            return __fmaf_rn(rem, r, q0);
+        }
+        return __fdiv_rn(d, range);
+    }
+};
+
+// out[0]: (d, range) pairs where FrameNormFast::apply differs from __fdiv_rn(d, range) (as bit patterns, NaN == NaN);
+// out[1]: pairs compared; out[2]: pairs that took the fast path.  Ranges: 2^12 values spread over float32's exponent
+// range (dense around 2^-4 .. 2^8, where MFCC frames live); d: 2^20 values per range, half of them in [0, range].
+__global__ void selftest_norm_kernel(unsigned long long* out) {
+    unsigned long long bad = 0, count = 0, fast_taken = 0;
+    const unsigned long long total = 1ull << 32;
+    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+        const unsigned int ri = static_cast<unsigned int>(i >> 20), di = static_cast<unsigned int>(i & 0xfffffu);
+        unsigned int h = ri * 2654435761u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        // exponent: three quarters of the ranges in [2^-4, 2^8), the rest anywhere (including denormal and huge)
+        const unsigned int ex = (ri & 3u) ? (123u + (h >> 8) % 12u) : ((h >> 8) % 255u);
+        const float range = __uint_as_float((ex << 23) | (h & 0x7fffffu));
+        unsigned int g = (di + 1u) * 2246822519u + ri * 3266489917u;
+        g ^= g >> 16; g *= 2654435761u; g ^= g >> 13;
+        float d;
+        if (di & 1u) d = range * (static_cast<float>(g >> 8) * (1.0f / 16777216.0f));     // in [0, range)
+        else d = __uint_as_float(g);                                                       // any bit pattern
+        const FrameNormFast norm(0.f, range);
+        const float a = norm.apply(d), b = __fdiv_rn(__fsub_rn(d, 0.f), range);
+        const unsigned int e = (__float_as_uint(d) >> 23) & 0xffu;
+        fast_taken += norm.fast && (e - 67u) <= 120u;
+        bad += !((__float_as_uint(a) == __float_as_uint(b)) || (a != a && b != b));
+        ++count;
+    }
+    if (bad) atomicAdd(out, bad);
+    atomicAdd(out + 1, count);
+    atomicAdd(out + 2, fast_taken);
+}
+
+// The constants of the pair kernels live in SHARED memory, not in the constant bank: ptxas hoists loop-invariant
+// constant-bank loads out of the pixel loop, and ~100 float64 coefficients overflow the 63 uniform registers into
+// spilled vector registers (500 bytes of local-memory traffic per pixel in the first build of these kernels).  Shared
+// loads cannot move across the pair barriers inside the loop; all lanes read the same address (one wavefront), two
+// coefficients per LDS.128.
+struct __align__(16) EnergyTables {
+    double dct[12 * kMfccNum];         // rows 0..11 of dct_base^T (the other twelve follow from the symmetry)
+    double lifter[kMfccNum];
+    double inv_lifter[kMfccNum];
+    double exp2[64];                   // 2^(j/64)
+    double mfnorm;
+};
+__device__ __forceinline__ void load_energy_tables(EnergyTables& t, int tid, int threads) {
+    for (int i = tid; i < 12 * kMfccNum; i += threads) t.dct[i] = c_dct[i];
+    for (int i = tid; i < 64; i += threads) t.exp2[i] = c_exp2_table[i];
+    if (tid < kMfccNum) { t.lifter[tid] = c_lifter[tid]; t.inv_lifter[tid] = c_inv_lifter[tid]; }
+    if (tid == 0) t.mfnorm = c_mfnorm;
+}
+
+// One (j, 23 - j) basis pair: the two exponentials exp(A + B), exp(A - B) of pixel_energy(), same operation order.
+template <int J>
+__device__ __forceinline__ void band_pair(const double (&z)[kMfccNum], const EnergyTables& tab, unsigned int& rare,
+                                          double& e_lo, double& e_hi) {
+    double a = 0.0, b = 0.0;
 #pragma unroll
-            for (int w = 1; w < kEnergyThreads / 32; ++w) {
-                mn = fminf(mn, s_red[0][w]);
-                mx = fmaxf(mx, s_red[1][w]);
-            }
-            lo = mn;
-            range = __fsub_rn(mx, mn);
-        }
+    for (int m = 0; m < kMfccNum; m += 2) {
+        b = fma(z[m], tab.dct[J * kMfccNum + m], b);
+        a = fma(z[m + 1], tab.dct[J * kMfccNum + m + 1], a);
+    }
+    e_lo = exp_table64(__dadd_rn(a, b), tab.exp2, rare);       // band J
+    e_hi = exp_table64(__dadd_rn(a, -b), tab.exp2, rare);      // band 23 - J
+}
 
-        const FrameNorm norm(lo, range);
-        // software pipeline: pixel i + 1 is in flight while pixel i goes through its ~600 float64 operations
-        const float4* first = reinterpret_cast<const float4*>(img + tid * kMfccNum);
-        float4 na = __ldg(first), nb = __ldg(first + 1), nc = __ldg(first + 2);
+// Group G: r[G] = (e[G] + e[G+8]) + e[G+16] and r[7-G] = (e[7-G] + e[15-G]) + e[23-G].
+template <int G>
+__device__ __forceinline__ void band_group(const double (&z)[kMfccNum], const EnergyTables& tab, unsigned int& rare,
+                                           double& r_g, double& r_7g) {
+    double lo1, hi1, lo2, hi2, lo3, hi3;
+    band_pair<G>(z, tab, rare, lo1, hi1);          // bands G,     23 - G
+    band_pair<8 + G>(z, tab, rare, lo3, hi3);      // bands 8 + G, 15 - G
+    r_g = __dadd_rn(lo1, lo3);
+    band_pair<7 - G>(z, tab, rare, lo2, hi2);      // bands 7 - G, 16 + G
+    r_g = __dadd_rn(r_g, hi2);
+    r_7g = __dadd_rn(__dadd_rn(lo2, hi3), hi1);
+}
+
+struct PairExchange {                  // one per warp pair, in shared memory
+    float x[2][6][32];                 // each half's six scaled channel values
+    double sum[2][32];                 // half 1's r2 + r3 and r4 + r5
+    unsigned int flag[2][32];          // each half's "needs the plain path"
+};
+
+// This half's share of one pixel.  raw: channels 6 * HALF .. 6 * HALF + 5.  Returns the energy in half 0 (0 in half 1);
+// `scaled` receives this half's float32-stored scaled values (find_logen's side effect), `rare` the pair's combined flag.
+template <int HALF>
+__device__ __forceinline__ double half_pixel(const float (&raw)[6], bool normalize, const FrameNormFast& norm,
+                                             const EnergyTables& tab, PairExchange& ex, int lane, int bar_id,
+                                             float (&scaled)[6], unsigned int& rare_out) {
+    unsigned int rare = 0;
+    double z[kMfccNum];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int m = 6 * HALF + i;
+        float v = raw[i];
+        if (normalize) v = norm.apply(v);                                     // float32, as TF
+        rare |= (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u;            // NaN / Inf: plain path
+        {                                                                     // div_by_lifter with the shared-memory constants
+            const double d = static_cast<double>(v), r = tab.inv_lifter[m];
+            const double q0 = __dmul_rn(d, r);
+            v = __double2float_rn(__fma_rn(__fma_rn(-q0, tab.lifter[m], d), r, q0));
+        }
+        v = __double2float_rn(__dmul_rn(static_cast<double>(v), tab.mfnorm));
+        scaled[i] = v;
+        ex.x[HALF][i][lane] = v;
+        z[m] = static_cast<double>(v);
+    }
+    named_bar_sync(bar_id, 64);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) z[6 * (1 - HALF) + i] = static_cast<double>(ex.x[1 - HALF][i][lane]);
+    double ra, rb, rc, rd;
+    band_group<2 * HALF>(z, tab, rare, ra, rb);          // half 0: r0, r7     half 1: r2, r5
+    band_group<2 * HALF + 1>(z, tab, rare, rc, rd);      // half 0: r1, r6     half 1: r3, r4
+    const double s_lo = __dadd_rn(ra, rc);                     // half 0: r0 + r1    half 1: r2 + r3
+    const double s_hi = __dadd_rn(rd, rb);                     // half 0: r6 + r7    half 1: r4 + r5
+    ex.flag[HALF][lane] = rare;
+    if (HALF == 1) { ex.sum[0][lane] = s_lo; ex.sum[1][lane] = s_hi; }
+    named_bar_sync(bar_id, 64);
+    rare_out = rare | ex.flag[1 - HALF][lane];
+    if (HALF == 1) return 0.0;
+    const double total = __dadd_rn(__dadd_rn(s_lo, ex.sum[0][lane]), __dadd_rn(ex.sum[1][lane], s_hi));
+    return __ddiv_rn(1.0, total);
+}
+
+// Pixels [p_begin, p_end) of one frame by a group of PAIRS warp pairs (thread index gt within the group; named barriers
+// bar_base .. bar_base + PAIRS - 1 belong to the pairs).  img / scaled / energy point at the frame; img may alias scaled
+// (find_logen's in-place scaling), so neither is read through a read-only path and a pixel's raw values are loaded before
+// anything of that pixel is stored.  Leaves map[p - p_begin] = energy.  Pixels the fast path cannot serve (non-finite
+// input, |mel| > 700) only get their bit set in rare_bits (zero on entry); the caller runs frame_energy_fixup after a
+// group barrier - the out-of-line plain path stays out of this loop and so do the register spills around its call.
+template <int PAIRS>
+__device__ __forceinline__ void frame_energy_range(const float* img, int p_begin, int p_end, bool normalize,
+                                                   const FrameNormFast& norm, float* scaled, double* energy, double* map,
+                                                   PairExchange* ex, unsigned int* rare_bits, const EnergyTables& tab, int gt,
+                                                   int bar_base) {
+    const int warp = gt >> 5, lane = gt & 31, pair = warp >> 1, half = warp & 1;
+    constexpr int kStep = 32 * PAIRS;
+    const int bar_id = bar_base + pair;
+    auto load6 = [&](int p, float (&r)[6]) {
+        const float2* s = reinterpret_cast<const float2*>(img + p * kMfccNum + 6 * half);
+        const float2 a = s[0], b = s[1], c = s[2];
+        r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y; r[4] = c.x; r[5] = c.y;
+    };
 #pragma unroll 1
-        for (int i = 0; i < kPixelsPerThread; ++i) {
-            const int p = tid + i * kEnergyThreads;
-            if (p >= kFramePixels) break;
-            const float4 a = na, b = nb, c = nc;
-            if (p + kEnergyThreads < kFramePixels) {
-                const float4* src = reinterpret_cast<const float4*>(img + (p + kEnergyThreads) * kMfccNum);
-                na = __ldg(src); nb = __ldg(src + 1); nc = __ldg(src + 2);
-            }
-            float x[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-            unsigned int rare;
-            double en = pixel_energy(x, normalize_first != 0, norm, s_exp, rare);
-            float* scaled_dst = scaled_out != nullptr ? scaled_out + frame * kFrameValues + p * kMfccNum : nullptr;
-            if (rare) {
-                en = pixel_energy_plain(img + p * kMfccNum, scaled_dst, normalize_first != 0, lo, range);
-            } else if (scaled_dst != nullptr) {
-                float4* dst = reinterpret_cast<float4*>(scaled_dst);
-                dst[0] = make_float4(x[0], x[1], x[2], x[3]);
-                dst[1] = make_float4(x[4], x[5], x[6], x[7]);
-                dst[2] = make_float4(x[8], x[9], x[10], x[11]);
-            }
-            s_map[p] = en;
-            if (energy_out != nullptr) energy_out[frame * kFramePixels + p] = en;
+    for (int base = p_begin + pair * 32; base < p_end; base += kStep) {          // pair-uniform trip count
+        const int p = base + lane;
+        const bool active = p < p_end;
+        float raw[6];
+        load6(min(p, p_end - 1), raw);
+        // next round's line on its way while this one computes (a prefetch, not a register prefetch: the float64 chain
+        // needs every register the 8-CTAs-per-SM budget has)
+        if (base + kStep < p_end)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(img + min(p + kStep, p_end - 1) * kMfccNum + 6 * half));
+        float sc[6];
+        unsigned int rare;
+        double en;
+        if (half == 0) en = half_pixel<0>(raw, normalize, norm, tab, ex[pair], lane, bar_id, sc, rare);
+        else en = half_pixel<1>(raw, normalize, norm, tab, ex[pair], lane, bar_id, sc, rare);
+        if (rare) {
+            // neither half stores anything of this pixel: frame_energy_fixup redoes it from its raw values
+            if (half == 0 && active) atomicOr(&rare_bits[(p - p_begin) >> 5], 1u << ((p - p_begin) & 31));
+        } else if (scaled != nullptr && active) {
+            float2* dst = reinterpret_cast<float2*>(scaled + p * kMfccNum + 6 * half);
+            dst[0] = make_float2(sc[0], sc[1]);
+            dst[1] = make_float2(sc[2], sc[3]);
+            dst[2] = make_float2(sc[4], sc[5]);
         }
-        __syncthreads();
-
-        if (mask_out != nullptr || mean_out != nullptr) {
-            const double mean = frame_mean(s_map, s_part, s_leaf, &s_mean, tid, [] { __syncthreads(); });
-            if (tid == 0 && mean_out != nullptr) mean_out[frame] = mean;
-            if (mask_out != nullptr) {
-                for (int p = tid; p < kFramePixels; p += kEnergyThreads)
-                    mask_out[frame * kFramePixels + p] = s_map[p] > mean ? 1 : 0;
-            }
+        if (half == 0 && active) {
+            map[p - p_begin] = en;
+            if (energy != nullptr) energy[p] = en;
         }
-        __syncthreads();   // s_map / s_red are reused by the next frame
     }
 }
 
-// F4 alone: _normalize_acoustic_images_rescaled over frames (float32).
+// Second pass for the flagged pixels: the plain path (IEEE divisions, exp()) from the raw values, which are still intact
+// because neither half stored the pixel.  Called by the whole group after a barrier.  Returns (group-uniformly) whether
+// any bit was set; the caller then synchronises and clears the words before the next frame.
+__device__ __forceinline__ bool frame_energy_fixup(const float* img, int p_begin, int p_end, bool normalize,
+                                                   const FrameNormFast& norm, float* scaled, double* energy, double* map,
+                                                   unsigned int* rare_bits, int gt, int threads) {
+    const int words = (p_end - p_begin + 31) >> 5;
+    bool any = false;
+    for (int w = 0; w < words; ++w) any |= rare_bits[w] != 0u;
+    if (!any) return false;                                        // group-uniform: every thread reads the same words
+    for (int i = gt; i < p_end - p_begin; i += threads) {
+        if (!((rare_bits[i >> 5] >> (i & 31)) & 1u)) continue;
+        const int p = p_begin + i;
+        float all[kMfccNum];
+#pragma unroll
+        for (int m = 0; m < kMfccNum; ++m) all[m] = img[p * kMfccNum + m];
+        const double en = pixel_energy_plain(all, scaled != nullptr ? scaled + p * kMfccNum : nullptr, normalize, norm.lo, norm.range);
+        map[i] = en;
+        if (energy != nullptr) energy[p] = en;
+    }
+    return true;
+}
+
+// min / max of n4 float4 values by a group of `threads` threads, NaN-propagating like tf.reduce_min / reduce_max
+// (outdoor_data_mfcc.py:674,677): any NaN in the frame makes both NaN, hence the whole normalised frame.
+// red: float [3][threads / 32] scratch.  Result in every thread of the group.
+template <typename Sync>
+__device__ __forceinline__ void group_minmax(const float* values, int n4, int gt, int threads, float* red, Sync sync,
+                                             float& lo, float& hi) {
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    bool nan = false;
+    const float4* v4 = reinterpret_cast<const float4*>(values);
+    for (int i = gt; i < n4; i += threads) {
+        const float4 v = v4[i];
+        mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
+        mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+        nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    nan = __any_sync(0xffffffffu, nan);
+    const int warps = threads >> 5;
+    if ((gt & 31) == 0) { red[gt >> 5] = mn; red[warps + (gt >> 5)] = mx; red[2 * warps + (gt >> 5)] = nan ? 1.f : 0.f; }
+    sync();
+    mn = red[0]; mx = red[warps];
+    float bad = red[2 * warps];
+    for (int w = 1; w < warps; ++w) { mn = fminf(mn, red[w]); mx = fmaxf(mx, red[warps + w]); bad += red[2 * warps + w]; }
+    sync();                                                     // red may be reused right away
+    lo = bad != 0.f ? CUDART_NAN_F : mn;
+    hi = bad != 0.f ? CUDART_NAN_F : mx;
+}
+
+constexpr int kEnergyPairs = 2;                        // warp pairs per frame in the batch kernels: 64 pixels per round, 27 rounds
+constexpr int kEnergyThreads = kEnergyPairs * 64;
+constexpr int kScoreThresholdsMax = 1024;              // == kMaxThresholds of score_kernel.cuh
+
+template <int PAIRS>
+struct EnergyGroupShared {
+    double map[kFramePixels];
+    double part[16][8];
+    double leaf[16];
+    double mean;
+    PairExchange ex[PAIRS];
+    float red[3 * PAIRS * 2];
+    unsigned int rare_bits[kFramePixels / 32];
+};
+
+// Arguments of the stage-2 kernels.  Slot 0 is the image of aig_energy, or the real image of aig_acivw_batch; slot 1 the
+// reconstructed image (GROUPS == 2 only).  Every output pointer is nullable.
+struct Stage2Args {
+    const float* img[2];
+    float* scaled[2];
+    double* energy[2];
+    uint8_t* mask[2];
+    double* mean[2];
+    long long n_frames;
+    int normalize_first;
+    // scoring, GROUPS == 2 (iouenergythreshold.py:224-229)
+    const double* thr;
+    int k_thr;
+    long long* inter;
+    long long* uni;
+    unsigned long long* pos;
+    unsigned long long* num;
+};
+
+// GROUPS == 1: energy_kernel (aig_energy).  GROUPS == 2: the ACIVW evaluation step (aig_acivw_batch): threads 0-127 take
+// the real image, 128-255 the reconstructed one, both energy maps stay in shared memory, and the masks, their
+// intersection / union counts, the IoU and the per-threshold success counts follow in the same CTA - no mask ever
+// travels through HBM unless the caller asks for it.
+template <int GROUPS>
+__global__ void __launch_bounds__(GROUPS * kEnergyThreads, 8 / GROUPS)
+stage2_kernel(const __grid_constant__ Stage2Args a) {
+    __shared__ EnergyGroupShared<kEnergyPairs> sh[GROUPS];
+    __shared__ EnergyTables s_tab;
+    __shared__ unsigned int s_pos[GROUPS == 2 ? kScoreThresholdsMax : 1];
+    __shared__ int s_iu[2];
+    __shared__ double s_iou;
+    const int tid = threadIdx.x;
+    const int group = tid / kEnergyThreads, gt = tid % kEnergyThreads;
+    const int bar_base = 1 + group * (kEnergyPairs + 1), bar_group = bar_base + kEnergyPairs;
+    auto group_sync = [&] { if (GROUPS == 1) __syncthreads(); else named_bar_sync(bar_group, kEnergyThreads); };
+    load_energy_tables(s_tab, tid, GROUPS * kEnergyThreads);
+    if (gt < kFramePixels / 32) sh[group].rare_bits[gt] = 0u;
+    if (GROUPS == 2) {
+        for (int k = tid; k < a.k_thr; k += GROUPS * kEnergyThreads) s_pos[k] = 0;
+        if (blockIdx.x == 0 && tid == 0) atomicAdd(a.num, static_cast<unsigned long long>(a.n_frames));   // num += 1 per frame (:229)
+    }
+    __syncthreads();
+    EnergyGroupShared<kEnergyPairs>& g = sh[group];
+
+    for (long long frame = blockIdx.x; frame < a.n_frames; frame += gridDim.x) {
+        const float* img = a.img[group] + frame * kFrameValues;
+        float lo = 0.f, hi = 1.f;
+        if (a.normalize_first) group_minmax(img, kFrameValues / 4, gt, kEnergyThreads, g.red, group_sync, lo, hi);
+        const FrameNormFast norm(lo, __fsub_rn(hi, lo));        // max(x - min) == fl(max - min): rounding is monotonic
+        float* scaled = a.scaled[group] ? a.scaled[group] + frame * kFrameValues : nullptr;
+        double* energy = a.energy[group] ? a.energy[group] + frame * kFramePixels : nullptr;
+        frame_energy_range<kEnergyPairs>(img, 0, kFramePixels, a.normalize_first != 0, norm, scaled, energy, g.map, g.ex,
+                                         g.rare_bits, s_tab, gt, bar_base);
+        group_sync();
+        if (frame_energy_fixup(img, 0, kFramePixels, a.normalize_first != 0, norm, scaled, energy, g.map, g.rare_bits, gt,
+                               kEnergyThreads)) {
+            group_sync();
+            if (gt < kFramePixels / 32) g.rare_bits[gt] = 0u;
+            group_sync();
+        }
+        if (GROUPS == 2 || a.mask[group] != nullptr || a.mean[group] != nullptr) {
+            const double mean = frame_mean(g.map, g.part, g.leaf, &g.mean, gt, group_sync);
+            if (gt == 0 && a.mean[group] != nullptr) a.mean[group][frame] = mean;
+            if (a.mask[group] != nullptr) {
+                for (int p = gt; p < kFramePixels; p += kEnergyThreads)
+                    a.mask[group][frame * kFramePixels + p] = g.map[p] > mean ? 1 : 0;
+            }
+        }
+        if (GROUPS == 2) {
+            if (tid < 2) s_iu[tid] = 0;
+            __syncthreads();
+            const double mean_a = sh[0].mean, mean_b = sh[GROUPS - 1].mean;
+            int inter = 0, uni = 0;
+            for (int p = tid; p < kFramePixels; p += GROUPS * kEnergyThreads) {       // 1728 = 6.75 * 256: whole warps only
+                const bool ma = sh[0].map[p] > mean_a, mb = sh[GROUPS - 1].map[p] > mean_b;
+                inter += __popc(__ballot_sync(0xffffffffu, ma && mb));
+                uni += __popc(__ballot_sync(0xffffffffu, ma || mb));
+            }
+            if ((tid & 31) == 0) { atomicAdd(&s_iu[0], inter); atomicAdd(&s_iu[1], uni); }
+            __syncthreads();
+            if (tid == 0) {
+                if (a.inter != nullptr) a.inter[frame] = s_iu[0];
+                if (a.uni != nullptr) a.uni[frame] = s_iu[1];
+                s_iou = __ddiv_rn(static_cast<double>(s_iu[0]), static_cast<double>(s_iu[1]));   // 0 / 0 = NaN: never counts
+            }
+            __syncthreads();
+            const double iou = s_iou;
+            for (int k = tid; k < a.k_thr; k += GROUPS * kEnergyThreads)
+                if (iou > a.thr[k]) s_pos[k] += 1u;                                   // thread k owns s_pos[k]
+        }
+        __syncthreads();     // maps, s_iu and s_iou are reused by the next frame
+    }
+    if (GROUPS == 2) {
+        for (int k = tid; k < a.k_thr; k += GROUPS * kEnergyThreads)
+            if (s_pos[k] != 0) atomicAdd(a.pos + k, static_cast<unsigned long long>(s_pos[k]));
+    }
+}
+
+// ---- small batches: one frame (pair) per thread-block cluster -----------------------------------------------------
+// Below ~150 frames one CTA per frame leaves most of the 148 SMs idle and a call costs a whole frame's 27 rounds
+// (45 us for the reference's batches of 2-16).  Here a cluster of 8 CTAs shares a frame: CTA r takes pixels
+// [216 r, 216 r + 216), which are exactly leaves 2r (104 values) and 2r + 1 (112 values) of NumPy's pairwise-sum tree for
+// n = 1728, so each CTA reduces its own two leaves and only eight float64 partial sums (plus, when normalising, eight
+// min / max pairs, and for the ACIVW step eight (I, U) pairs) cross the cluster through distributed shared memory.
+// Every CTA then walks the top of the tree itself, in NumPy's order: the mean - and with it the mask - is bit-identical
+// to the one-CTA kernels.
+constexpr int kClusterSize = 8;
+constexpr int kSlicePixels = kFramePixels / kClusterSize;          // 216
+constexpr int kClusterPairs = 4;                                   // 128 pixels per round: two rounds per slice
+constexpr int kClusterGroupThreads = kClusterPairs * 64;           // 256
+static_assert(kSlicePixels == 104 + 112, "a slice is two leaves of the pairwise tree");
+
+struct ClusterGroupShared {
+    double map[kSlicePixels];
+    double r8[2][8];
+    double leaf[2];
+    double mean;
+    float lo, hi;
+    PairExchange ex[kClusterPairs];
+    float red[3 * kClusterPairs * 2];
+    unsigned int rare_bits[(kSlicePixels + 31) / 32];
+};
+struct ClusterMail {               // what the other CTAs of the cluster read
+    float mn[2], mx[2];
+    double s8[2];
+    int inter, uni;
+};
+
+template <int GROUPS>
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(GROUPS * kClusterGroupThreads, 1)
+stage2_cluster_kernel(const __grid_constant__ Stage2Args a) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ ClusterGroupShared sh[GROUPS];
+    __shared__ ClusterMail mail;
+    __shared__ EnergyTables s_tab;
+    __shared__ int s_iu[2];
+    const int tid = threadIdx.x;
+    const int group = tid / kClusterGroupThreads, gt = tid % kClusterGroupThreads;
+    const int lane = tid & 31;
+    const int bar_base = 1 + group * (kClusterPairs + 1), bar_group = bar_base + kClusterPairs;
+    auto group_sync = [&] { if (GROUPS == 1) __syncthreads(); else named_bar_sync(bar_group, kClusterGroupThreads); };
+    const unsigned int rank = cluster.block_rank();
+    const long long n_clusters = gridDim.x / kClusterSize;
+    load_energy_tables(s_tab, tid, GROUPS * kClusterGroupThreads);
+    if (gt < (kSlicePixels + 31) / 32) sh[group].rare_bits[gt] = 0u;
+    if (GROUPS == 2 && blockIdx.x == 0 && tid == 0) atomicAdd(a.num, static_cast<unsigned long long>(a.n_frames));
+    __syncthreads();
+    ClusterGroupShared& g = sh[group];
+    const int p0 = static_cast<int>(rank) * kSlicePixels;
+
+    for (long long frame = blockIdx.x / kClusterSize; frame < a.n_frames; frame += n_clusters) {
+        const float* img = a.img[group] + frame * kFrameValues;
+        float lo = 0.f, hi = 1.f;
+        if (a.normalize_first) {
+            group_minmax(img + p0 * kMfccNum, kSlicePixels * kMfccNum / 4, gt, kClusterGroupThreads, g.red, group_sync, lo, hi);
+            if (gt == 0) { mail.mn[group] = lo; mail.mx[group] = hi; }
+            cluster.sync();
+            if (gt < 32) {                                     // lanes 0-7 fetch the eight slices' extremes, NaN-propagating
+                float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+                bool nan = false;
+                if (lane < kClusterSize) {
+                    const ClusterMail* remote = cluster.map_shared_rank(&mail, lane);
+                    mn = remote->mn[group]; mx = remote->mx[group];
+                    nan = (mn != mn) || (mx != mx);
+                }
+                nan = __any_sync(0xffffffffu, nan);
+                mn = warp_min(mn); mx = warp_max(mx);
+                if (lane == 0) { g.lo = nan ? CUDART_NAN_F : mn; g.hi = nan ? CUDART_NAN_F : mx; }
+            }
+            group_sync();
+            lo = g.lo; hi = g.hi;
+        }
+        const FrameNormFast norm(lo, __fsub_rn(hi, lo));
+        float* scaled = a.scaled[group] ? a.scaled[group] + frame * kFrameValues : nullptr;
+        double* energy = a.energy[group] ? a.energy[group] + frame * kFramePixels : nullptr;
+        frame_energy_range<kClusterPairs>(img, p0, p0 + kSlicePixels, a.normalize_first != 0, norm, scaled, energy, g.map,
+                                          g.ex, g.rare_bits, s_tab, gt, bar_base);
+        group_sync();
+        if (frame_energy_fixup(img, p0, p0 + kSlicePixels, a.normalize_first != 0, norm, scaled, energy, g.map, g.rare_bits,
+                               gt, kClusterGroupThreads)) {
+            group_sync();
+            if (gt < (kSlicePixels + 31) / 32) g.rare_bits[gt] = 0u;
+            group_sync();
+        }
+        // this slice's two leaves of the pairwise tree, then their sum (one of the eight s8 terms of frame_mean)
+        if (gt < 16) {
+            const int leaf = gt >> 3, k = gt & 7;
+            const double* v = g.map + (leaf ? 104 : 0);
+            const int len = leaf ? 112 : 104;
+            double r = v[k];
+            for (int i = 8; i < len; i += 8) r = __dadd_rn(r, v[i + k]);
+            g.r8[leaf][k] = r;
+        }
+        group_sync();
+        if (gt < 2) {
+            const double* r = g.r8[gt];
+            g.leaf[gt] = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                                   __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        }
+        group_sync();
+        if (gt == 0) mail.s8[group] = __dadd_rn(g.leaf[0], g.leaf[1]);
+        cluster.sync();
+        if (gt < 32) {
+            double v = 0.0;
+            if (lane < kClusterSize) v = cluster.map_shared_rank(&mail, lane)->s8[group];
+            double s8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s8[i] = __shfl_sync(0xffffffffu, v, i);
+            if (lane == 0) {
+                double s4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s4[i] = __dadd_rn(s8[2 * i], s8[2 * i + 1]);
+                const double sum = __dadd_rn(__dadd_rn(s4[0], s4[1]), __dadd_rn(s4[2], s4[3]));
+                g.mean = __ddiv_rn(sum, static_cast<double>(kFramePixels));
+            }
+        }
+        group_sync();
+        const double mean = g.mean;
+        if (rank == 0 && gt == 0 && a.mean[group] != nullptr) a.mean[group][frame] = mean;
+        if (a.mask[group] != nullptr) {
+            for (int p = gt; p < kSlicePixels; p += kClusterGroupThreads)
+                a.mask[group][frame * kFramePixels + p0 + p] = g.map[p] > mean ? 1 : 0;
+        }
+        if (GROUPS == 2) {
+            if (tid < 2) s_iu[tid] = 0;
+            __syncthreads();
+            const double mean_a = sh[0].mean, mean_b = sh[GROUPS - 1].mean;
+            if (tid < 224) {                                   // 216 pixels: seven whole warps
+                const bool in = tid < kSlicePixels;
+                const bool ma = in && sh[0].map[in ? tid : 0] > mean_a, mb = in && sh[GROUPS - 1].map[in ? tid : 0] > mean_b;
+                const int inter = __popc(__ballot_sync(0xffffffffu, ma && mb)), uni = __popc(__ballot_sync(0xffffffffu, ma || mb));
+                if (lane == 0) { atomicAdd(&s_iu[0], inter); atomicAdd(&s_iu[1], uni); }
+            }
+            __syncthreads();
+            if (tid == 0) { mail.inter = s_iu[0]; mail.uni = s_iu[1]; }
+            cluster.sync();
+            if (rank == 0 && tid < 32) {
+                int inter = 0, uni = 0;
+                if (lane < kClusterSize) {
+                    const ClusterMail* remote = cluster.map_shared_rank(&mail, lane);
+                    inter = remote->inter; uni = remote->uni;
+                }
+                inter = warp_sum(inter); uni = warp_sum(uni);
+                if (lane == 0) {
+                    if (a.inter != nullptr) a.inter[frame] = inter;
+                    if (a.uni != nullptr) a.uni[frame] = uni;
+                }
+                const double iou = __ddiv_rn(static_cast<double>(inter), static_cast<double>(uni));
+                for (int k = lane; k < a.k_thr; k += 32)
+                    if (iou > a.thr[k]) atomicAdd(a.pos + k, 1ull);
+            }
+        }
+        cluster.sync();      // nobody leaves (or overwrites its mail) while a neighbour may still be reading it
+    }
+}
+
+// F4 alone: _normalize_acoustic_images_rescaled over frames (float32); `images` may alias `out`.
 __global__ void __launch_bounds__(256)
-normalize_kernel(const float* __restrict__ images, long long n_frames, float* __restrict__ out) {
-    __shared__ float s_red[2][8];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+normalize_kernel(const float* images, long long n_frames, float* out) {
+    __shared__ float s_red[3 * 8];
+    const int tid = threadIdx.x;
     for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
         const float4* img4 = reinterpret_cast<const float4*>(images + frame * kFrameValues);
         float4* out4 = reinterpret_cast<float4*>(out + frame * kFrameValues);
-        float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-        for (int i = tid; i < kFrameValues / 4; i += 256) {
-            const float4 v = img4[i];
-            mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
-            mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
-        }
-        mn = warp_min(mn);
-        mx = warp_max(mx);
-        if (lane == 0) { s_red[0][warp] = mn; s_red[1][warp] = mx; }
-        __syncthreads();
-        mn = s_red[0][0]; mx = s_red[1][0];
-#pragma unroll
-        for (int w = 1; w < 8; ++w) { mn = fminf(mn, s_red[0][w]); mx = fmaxf(mx, s_red[1][w]); }
+        float mn, mx;
+        group_minmax(images + frame * kFrameValues, kFrameValues / 4, tid, 256, s_red, [] { __syncthreads(); }, mn, mx);
         const float range = __fsub_rn(mx, mn);
         for (int i = tid; i < kFrameValues / 4; i += 256) {
             float4 v = img4[i];
@@ -360,316 +808,6 @@ normalize_kernel(const float* __restrict__ images, long long n_frames, float* __
             v.z = __fdiv_rn(__fsub_rn(v.z, mn), range);
             v.w = __fdiv_rn(__fsub_rn(v.w, mn), range);
             out4[i] = v;
-        }
-        __syncthreads();
-    }
-}
-
-// ---- bilinear taps (cv2.resize INTER_LINEAR: half-pixel centres, border clamp) -------------------
-// float64 taps exactly as the oracle forms them: pos = (d + 0.5) * (n_src / n_dst) - 0.5.
-__device__ __forceinline__ void linear_tap(int d, int n_src, int n_dst, int* i0, int* i1, double* w1) {
-    const double scale = __ddiv_rn(static_cast<double>(n_src), static_cast<double>(n_dst));
-    const double pos = __dadd_rn(__dmul_rn(static_cast<double>(d) + 0.5, scale), -0.5);
-    int lo = static_cast<int>(floor(pos));
-    double w = __dadd_rn(pos, -static_cast<double>(lo));
-    if (lo < 0) { lo = 0; w = 0.0; }
-    if (lo >= n_src - 1) { lo = n_src - 1; w = 0.0; }
-    *i0 = lo;
-    *i1 = min(lo + 1, n_src - 1);
-    *w1 = w;
-}
-// Integer taps: pos = ((2d+1) * n_src - n_dst) / (2 * n_dst); weight numerator over den = 2 * n_dst.
-__device__ __forceinline__ void linear_tap_exact(int d, int n_src, int n_dst, int* i0, int* i1, int* num) {
-    const int den = 2 * n_dst;
-    const int t = (2 * d + 1) * n_src - n_dst;
-    int lo = (t >= 0) ? t / den : -((-t + den - 1) / den);
-    int r = t - lo * den;
-    if (lo < 0) { lo = 0; r = 0; }
-    if (lo >= n_src - 1) { lo = n_src - 1; r = 0; }
-    *i0 = lo;
-    *i1 = min(lo + 1, n_src - 1);
-    *num = r;
-}
-
-constexpr int kHeatThreads = 256;
-constexpr int kMaxOut = 2048;   // out_h, out_w <= 2048
-
-// energy [n, 36, 48] f64 -> heat [n, out_h, out_w] f32 = (up - min(up)) / (max(up) - min(up)).
-// Dynamic shared memory: out_w * (2 int + 1 double) + out_h * (2 int + 1 double).
-__global__ void __launch_bounds__(kHeatThreads)
-heatmap_kernel(const double* __restrict__ energy, long long n_frames, int out_h, int out_w,
-               float* __restrict__ heat) {
-    extern __shared__ double s_dyn[];
-    __shared__ double s_map[kFramePixels];
-    __shared__ double s_red[2][kHeatThreads / 32];
-    double* s_wx = s_dyn;                      // [out_w]
-    double* s_wy = s_wx + out_w;               // [out_h]
-    int* s_x0 = reinterpret_cast<int*>(s_wy + out_h);   // [out_w] x0 | x1 << 16
-    int* s_y0 = s_x0 + out_w;                  // [out_h]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int d = tid; d < out_w; d += kHeatThreads) {
-        int i0, i1; double w;
-        linear_tap(d, kFrameW, out_w, &i0, &i1, &w);
-        s_x0[d] = i0 | (i1 << 16); s_wx[d] = w;
-    }
-    for (int d = tid; d < out_h; d += kHeatThreads) {
-        int i0, i1; double w;
-        linear_tap(d, kFrameH, out_h, &i0, &i1, &w);
-        s_y0[d] = i0 | (i1 << 16); s_wy[d] = w;
-    }
-    const int n_out = out_h * out_w;
-    for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
-        __syncthreads();
-        for (int p = tid; p < kFramePixels; p += kHeatThreads) s_map[p] = energy[frame * kFramePixels + p];
-        __syncthreads();
-        auto sample = [&](int idx) -> double {
-            const int y = idx / out_w, x = idx - y * out_w;
-            const int xi = s_x0[x], yi = s_y0[y];
-            const int x0 = xi & 0xffff, x1 = xi >> 16, y0 = yi & 0xffff, y1 = yi >> 16;
-            const double wx = s_wx[x], wy = s_wy[y];
-            const double ux = __dadd_rn(1.0, -wx), uy = __dadd_rn(1.0, -wy);
-            // horizontal pass on the two source rows, then the vertical pass (no FMA contraction)
-            const double top = __dadd_rn(__dmul_rn(s_map[y0 * kFrameW + x0], ux), __dmul_rn(s_map[y0 * kFrameW + x1], wx));
-            const double bot = __dadd_rn(__dmul_rn(s_map[y1 * kFrameW + x0], ux), __dmul_rn(s_map[y1 * kFrameW + x1], wx));
-            return __dadd_rn(__dmul_rn(top, uy), __dmul_rn(bot, wy));
-        };
-        double mn = CUDART_INF, mx = -CUDART_INF;
-        for (int idx = tid; idx < n_out; idx += kHeatThreads) {
-            const double v = sample(idx);
-            mn = fmin(mn, v); mx = fmax(mx, v);
-        }
-        mn = warp_min(mn); mx = warp_max(mx);
-        if (lane == 0) { s_red[0][warp] = mn; s_red[1][warp] = mx; }
-        __syncthreads();
-        mn = s_red[0][0]; mx = s_red[1][0];
-#pragma unroll
-        for (int w = 1; w < kHeatThreads / 32; ++w) { mn = fmin(mn, s_red[0][w]); mx = fmax(mx, s_red[1][w]); }
-        const double range = __dadd_rn(mx, -mn);
-        float* dst = heat + frame * n_out;
-        for (int idx = tid; idx < n_out; idx += kHeatThreads)
-            dst[idx] = __double2float_rn(__ddiv_rn(__dadd_rn(sample(idx), -mn), range));
-    }
-}
-
-// Fast path (default): the same map in float32.  Bilinear interpolation commutes with the affine map
-// t = (e - min e) / (max e - min e), so the frame is first normalised to [0, 1] in float64 (1728 values) and everything
-// per output pixel - separable bilinear, min/max of the up-sampled image, final normalisation - runs in float32 on
-// values of order one: error ~1e-7 of the output range however flat the raw energies are.  The horizontal pass is done
-// once into shared memory (36 x out_w), so an output pixel costs two shared loads and three FMAs per pass and the
-// kernel approaches the HBM write rate (out_h * out_w * 4 B per frame).
-// Dynamic shared memory: 36 * out_w floats (rows) + out_w * (int + float) + out_h * (int + float).
-// VEC = pixels per thread per step (4 when out_w % 4 == 0, 2 when even, else 1): the kernel is issue-bound, so the
-// vertical passes use 8/16-byte shared loads and global stores.
-template <int VEC>
-struct HeatVec;
-template <>
-struct HeatVec<1> {
-    using T = float;
-    static __device__ __forceinline__ void lerp_minmax(const float* r0, const float* r1, int x, float wy, float& mn, float& mx) {
-        const float v = fmaf(r1[x] - r0[x], wy, r0[x]);
-        mn = fminf(mn, v); mx = fmaxf(mx, v);
-    }
-    static __device__ __forceinline__ void lerp_store(const float* r0, const float* r1, int x, float wy, float mn, float inv, float* o) {
-        __stcs(o + x, (fmaf(r1[x] - r0[x], wy, r0[x]) - mn) * inv);
-    }
-};
-template <>
-struct HeatVec<2> {
-    static __device__ __forceinline__ void lerp_minmax(const float* r0, const float* r1, int x, float wy, float& mn, float& mx) {
-        const float2 a = *reinterpret_cast<const float2*>(r0 + x), b = *reinterpret_cast<const float2*>(r1 + x);
-        const float v0 = fmaf(b.x - a.x, wy, a.x), v1 = fmaf(b.y - a.y, wy, a.y);
-        mn = fminf(mn, fminf(v0, v1)); mx = fmaxf(mx, fmaxf(v0, v1));
-    }
-    static __device__ __forceinline__ void lerp_store(const float* r0, const float* r1, int x, float wy, float mn, float inv, float* o) {
-        const float2 a = *reinterpret_cast<const float2*>(r0 + x), b = *reinterpret_cast<const float2*>(r1 + x);
-        __stcs(reinterpret_cast<float2*>(o + x), make_float2((fmaf(b.x - a.x, wy, a.x) - mn) * inv, (fmaf(b.y - a.y, wy, a.y) - mn) * inv));
-    }
-};
-template <>
-struct HeatVec<4> {
-    static __device__ __forceinline__ void lerp_minmax(const float* r0, const float* r1, int x, float wy, float& mn, float& mx) {
-        const float4 a = *reinterpret_cast<const float4*>(r0 + x), b = *reinterpret_cast<const float4*>(r1 + x);
-        const float v0 = fmaf(b.x - a.x, wy, a.x), v1 = fmaf(b.y - a.y, wy, a.y);
-        const float v2 = fmaf(b.z - a.z, wy, a.z), v3 = fmaf(b.w - a.w, wy, a.w);
-        mn = fminf(fminf(mn, fminf(v0, v1)), fminf(v2, v3)); mx = fmaxf(fmaxf(mx, fmaxf(v0, v1)), fmaxf(v2, v3));
-    }
-    static __device__ __forceinline__ void lerp_store(const float* r0, const float* r1, int x, float wy, float mn, float inv, float* o) {
-        const float4 a = *reinterpret_cast<const float4*>(r0 + x), b = *reinterpret_cast<const float4*>(r1 + x);
-        __stcs(reinterpret_cast<float4*>(o + x),
-               make_float4((fmaf(b.x - a.x, wy, a.x) - mn) * inv, (fmaf(b.y - a.y, wy, a.y) - mn) * inv,
-                           (fmaf(b.z - a.z, wy, a.z) - mn) * inv, (fmaf(b.w - a.w, wy, a.w) - mn) * inv));
-    }
-};
-
-template <int VEC>
-__global__ void __launch_bounds__(kHeatThreads)
-heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int out_h, int out_w,
-                    float* __restrict__ heat) {
-    extern __shared__ __align__(16) float s_fast[];
-    __shared__ float s_t[kFramePixels];
-    __shared__ double s_red64[2][kHeatThreads / 32];
-    __shared__ float s_red32[2][kHeatThreads / 32];
-    float* s_rows = s_fast;                                         // [36][out_w]
-    float* s_wx = s_rows + kFrameH * out_w;                         // [out_w]
-    float* s_wy = s_wx + out_w;                                     // [out_h]
-    int* s_x0 = reinterpret_cast<int*>(s_wy + out_h);               // [out_w] x0 | x1 << 16
-    int* s_y0 = s_x0 + out_w;                                       // [out_h]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int d = tid; d < out_w; d += kHeatThreads) {
-        int i0, i1; double w;
-        linear_tap(d, kFrameW, out_w, &i0, &i1, &w);
-        s_x0[d] = i0 | (i1 << 16); s_wx[d] = static_cast<float>(w);
-    }
-    for (int d = tid; d < out_h; d += kHeatThreads) {
-        int i0, i1; double w;
-        linear_tap(d, kFrameH, out_h, &i0, &i1, &w);
-        // Bit 31 marks the first and last output row of every source-row pair.  fmaf(r1 - r0, wy, r0) is monotonic in
-        // wy, and wy grows with y inside a pair, so the image's min / max are attained on the marked rows: pass 1 visits
-        // only those (about 2 * 37 of out_h rows) and finds exactly the values a full pass would.
-        int p0, p1, n0, n1; double wn;
-        linear_tap(max(d - 1, 0), kFrameH, out_h, &p0, &p1, &wn);
-        linear_tap(min(d + 1, out_h - 1), kFrameH, out_h, &n0, &n1, &wn);
-        const bool edge = d == 0 || d == out_h - 1 || p0 != i0 || p1 != i1 || n0 != i0 || n1 != i1;
-        s_y0[d] = i0 | (i1 << 16) | (edge ? 0x80000000 : 0); s_wy[d] = static_cast<float>(w);
-    }
-    constexpr int kPerThread = (kFramePixels + kHeatThreads - 1) / kHeatThreads;
-    double e[kPerThread];                                          // this thread's energies of the frame being started
-    auto fetch = [&](long long frame) {
-#pragma unroll
-        for (int i = 0; i < kPerThread; ++i) {
-            const int p = tid + i * kHeatThreads;
-            e[i] = (frame < n_frames && p < kFramePixels) ? __ldcs(energy + frame * kFramePixels + p) : CUDART_NAN;
-        }
-    };
-    fetch(blockIdx.x);
-    for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
-        __syncthreads();
-        // frame min / max in float64, then t = (e - min) / (max - min) as float32
-        double lo = CUDART_INF, hi = -CUDART_INF;
-#pragma unroll
-        for (int i = 0; i < kPerThread; ++i) { lo = fmin(lo, e[i]); hi = fmax(hi, e[i]); }
-        lo = warp_min(lo); hi = warp_max(hi);
-        if (lane == 0) { s_red64[0][warp] = lo; s_red64[1][warp] = hi; }
-        __syncthreads();
-        lo = s_red64[0][0]; hi = s_red64[1][0];
-#pragma unroll
-        for (int w = 1; w < kHeatThreads / 32; ++w) { lo = fmin(lo, s_red64[0][w]); hi = fmax(hi, s_red64[1][w]); }
-        const double span = hi - lo;
-#pragma unroll
-        for (int i = 0; i < (kFramePixels + kHeatThreads - 1) / kHeatThreads; ++i) {
-            const int p = tid + i * kHeatThreads;
-            if (p < kFramePixels) s_t[p] = span > 0.0 ? static_cast<float>((e[i] - lo) / span) : 0.f;
-        }
-        fetch(frame + gridDim.x);                                  // next frame's energies arrive during the passes below
-        __syncthreads();
-        // horizontal pass, once: warps own source rows, lanes walk the output columns
-        for (int r = warp; r < kFrameH; r += kHeatThreads / 32) {
-            const float* t = s_t + r * kFrameW;
-            float* row = s_rows + r * out_w;
-            for (int x = lane; x < out_w; x += 32) {
-                const int xi = s_x0[x];
-                const float a = t[xi & 0xffff], b = t[xi >> 16];
-                row[x] = fmaf(b - a, s_wx[x], a);
-            }
-        }
-        __syncthreads();
-        // pass 1: min / max of the up-sampled image
-        float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-        for (int y = warp; y < out_h; y += kHeatThreads / 32) {
-            const int yi = s_y0[y];
-            if (yi >= 0) continue;                                   // interior row of its pair: cannot hold an extreme
-            const float wy = s_wy[y];
-            const float* r0 = s_rows + (yi & 0xffff) * out_w;
-            const float* r1 = s_rows + ((yi >> 16) & 0x7fff) * out_w;
-            for (int x = lane * VEC; x < out_w; x += 32 * VEC) HeatVec<VEC>::lerp_minmax(r0, r1, x, wy, mn, mx);
-        }
-        mn = warp_min(mn); mx = warp_max(mx);
-        if (lane == 0) { s_red32[0][warp] = mn; s_red32[1][warp] = mx; }
-        __syncthreads();
-        mn = s_red32[0][0]; mx = s_red32[1][0];
-#pragma unroll
-        for (int w = 1; w < kHeatThreads / 32; ++w) { mn = fminf(mn, s_red32[0][w]); mx = fmaxf(mx, s_red32[1][w]); }
-        // a constant frame gives 0/0 = NaN, like the reference's (x - min) / (max - min)
-        const float inv = (span > 0.0 && mx > mn) ? 1.f / (mx - mn) : CUDART_NAN_F;
-        float* dst = heat + frame * static_cast<long long>(out_h) * out_w;
-        // pass 2: normalise and stream out
-        for (int y = warp; y < out_h; y += kHeatThreads / 32) {
-            const int yi = s_y0[y];
-            const float wy = s_wy[y];
-            const float* r0 = s_rows + (yi & 0xffff) * out_w;
-            const float* r1 = s_rows + ((yi >> 16) & 0x7fff) * out_w;
-            float* o = dst + static_cast<long long>(y) * out_w;
-            for (int x = lane * VEC; x < out_w; x += 32 * VEC) HeatVec<VEC>::lerp_store(r0, r1, x, wy, mn, inv, o);
-        }
-    }
-}
-
-// mask [n, 36, 48] u8 -> mask_up [n, out_h, out_w] u8, value 1 iff bilinear(mask != 0) > 1/2 exactly.
-// The bilinear value is a ratio of integers: with tap numerators xn / (2 out_w) and yn / (2 out_h),
-//   val = [m00 (xd - xn) + m01 xn] (yd - yn) + [m10 (xd - xn) + m11 xn] yn   over   xd yd   (xd = 2 out_w, yd = 2 out_h)
-// so "> 0.5" is 2 val > xd yd with no rounding.  Separable: the 36 source rows are blended horizontally once per
-// frame (values 0..xd <= 4096, uint16), every output pixel then needs two shared loads and two integer multiply-adds
-// (val <= 2^24).
-struct MaskTaps {
-    int* x0;            // [out_w] x0 | x1 << 16
-    int* xn;            // [out_w]
-    int* y0;            // [out_h] y0 | y1 << 16
-    int* yn;            // [out_h]
-    uint16_t* rows;     // [36][out_w] horizontally blended source rows of the current frame
-    __device__ __forceinline__ void carve(int* base, int out_h, int out_w) {
-        x0 = base; xn = x0 + out_w; y0 = xn + out_w; yn = y0 + out_h;
-        rows = reinterpret_cast<uint16_t*>(yn + out_h);
-    }
-    static __host__ __device__ size_t bytes(int out_h, int out_w) {
-        return static_cast<size_t>(out_w + out_h) * 2 * sizeof(int) + static_cast<size_t>(kFrameH) * out_w * sizeof(uint16_t);
-    }
-    __device__ __forceinline__ void build_taps(int out_h, int out_w, int tid, int n_threads) const {
-        for (int d = tid; d < out_w; d += n_threads) {
-            int i0, i1, r; linear_tap_exact(d, kFrameW, out_w, &i0, &i1, &r);
-            x0[d] = i0 | (i1 << 16); xn[d] = r;
-        }
-        for (int d = tid; d < out_h; d += n_threads) {
-            int i0, i1, r; linear_tap_exact(d, kFrameH, out_h, &i0, &i1, &r);
-            y0[d] = i0 | (i1 << 16); yn[d] = r;
-        }
-    }
-    // warp per source row, lanes over output columns
-    __device__ __forceinline__ void blend_rows(const uint8_t* s_mask, int out_w, int warp, int lane, int n_warps) const {
-        const int xd = 2 * out_w;
-        for (int ys = warp; ys < kFrameH; ys += n_warps) {
-            const uint8_t* m = s_mask + ys * kFrameW;
-            uint16_t* dst = rows + ys * out_w;
-            for (int x = lane; x < out_w; x += 32) {
-                const int xi = x0[x], n = xn[x];
-                dst[x] = static_cast<uint16_t>(m[xi & 0xffff] * (xd - n) + m[xi >> 16] * n);
-            }
-        }
-    }
-};
-
-__global__ void __launch_bounds__(kHeatThreads)
-resize_mask_kernel(const uint8_t* __restrict__ mask, long long n_frames, int out_h, int out_w,
-                   uint8_t* __restrict__ mask_up) {
-    extern __shared__ int s_taps[];
-    __shared__ uint8_t s_mask[kFramePixels];
-    MaskTaps t;
-    t.carve(s_taps, out_h, out_w);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    t.build_taps(out_h, out_w, tid, kHeatThreads);
-    const int yd = 2 * out_h, half = 2 * out_w * out_h;       // xd * yd / 2
-    for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
-        __syncthreads();
-        for (int p = tid; p < kFramePixels; p += kHeatThreads) s_mask[p] = mask[frame * kFramePixels + p] != 0;
-        __syncthreads();
-        t.blend_rows(s_mask, out_w, warp, lane, kHeatThreads / 32);
-        __syncthreads();
-        uint8_t* dst = mask_up + frame * static_cast<long long>(out_h) * out_w;
-        for (int y = warp; y < out_h; y += kHeatThreads / 32) {
-            const int yi = t.y0[y], n = t.yn[y];
-            const uint16_t* r0 = t.rows + (yi & 0xffff) * out_w;
-            const uint16_t* r1 = t.rows + (yi >> 16) * out_w;
-            uint8_t* o = dst + static_cast<long long>(y) * out_w;
-            for (int x = lane; x < out_w; x += 32) o[x] = static_cast<uint8_t>(r0[x] * (yd - n) + r1[x] * n > half);
         }
     }
 }

@@ -119,10 +119,13 @@ __global__ void filtfilt_kernel(const In* __restrict__ x, long long n_rows, int 
 }
 
 // ---- N2: per-vector min-max and the tiled conditioning image ------------------------------------------
+// tf.reduce_min / reduce_max propagate NaN (outdoor_data_mfcc.py:699,701): one NaN makes the whole vector NaN.
 __device__ __forceinline__ void minmax_normalize12(float (&v)[12]) {
     float mn = v[0], mx = v[0];
+    bool nan = v[0] != v[0];
 #pragma unroll
-    for (int m = 1; m < 12; ++m) { mn = fminf(mn, v[m]); mx = fmaxf(mx, v[m]); }
+    for (int m = 1; m < 12; ++m) { mn = fminf(mn, v[m]); mx = fmaxf(mx, v[m]); nan |= v[m] != v[m]; }
+    if (nan) mn = CUDART_NAN_F;
     const float range = __fsub_rn(mx, mn);          // max(x - min) == fl(max - min)
 #pragma unroll
     for (int m = 0; m < 12; ++m) v[m] = __fdiv_rn(__fsub_rn(v[m], mn), range);

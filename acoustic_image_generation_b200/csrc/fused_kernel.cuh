@@ -51,12 +51,18 @@ __device__ __forceinline__ void energy_group_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(kFusedEnergyThreads) : "memory");
 }
 
-template <int SLABS_PER_STAGE, int STAGES>
+// JITTER = true is the "debug_jitter" build of the same kernel: every role spins for pseudo-random times before its
+// barrier waits and arrives (aig_common.cuh: jitter_spin), which moves the three roles through every relative order the
+// protocol allows; the production instantiation (JITTER = false) contains none of it.
+// mfcc_out is written by the consumer warps and read back by the energy warps of the same CTA: no __restrict__, no
+// read-only loads on it.
+template <int SLABS_PER_STAGE, int STAGES, bool JITTER>
 __global__ void __launch_bounds__(kFusedThreads, 1)
-mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ mfcc_out,
+mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* mfcc_out,
                          unsigned int n_frames, int flip180, int normalize_first,
                          double* __restrict__ energy_out, uint8_t* __restrict__ mask_out,
-                         double* __restrict__ mean_out, int l2_evict_first, int keep_mfcc_in_l2) {
+                         double* __restrict__ mean_out, int l2_evict_first, int keep_mfcc_in_l2,
+                         unsigned int jitter_seed) {
     using P = MfccPipe<kFusedRows, SLABS_PER_STAGE, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -86,6 +92,7 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* __rest
 
     int stage = 0;
     uint32_t phase = 0;
+    unsigned int jitter_counter = 0;
 
     if (warp == kFusedConsumerWarps) {
         // ------------------------------------ TMA producer -----------------------------------------
@@ -97,7 +104,8 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* __rest
                 for (int t = 0; t < kFusedTilesPerFrame; ++t)
                     load_tile<kFusedRows, SLABS_PER_STAGE, STAGES>(
                         &tmap, ring, bar_full, bar_empty,
-                        static_cast<int32_t>(frame * kFramePixels + t * kFusedRows), policy, stage, phase);
+                        static_cast<int32_t>(frame * kFramePixels + t * kFusedRows), policy, stage, phase,
+                        JITTER ? jitter_seed : 0u, &jitter_counter);
         }
         return;
     }
@@ -115,7 +123,8 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* __rest
 #pragma unroll 1
             for (int t = 0; t < kFusedTilesPerFrame; ++t) {
                 float c[12];
-                mel_tile<kFusedRows, SLABS_PER_STAGE, STAGES>(ring, bar_full, bar_empty, row_off, sw, lane, stage, phase, c);
+                mel_tile<kFusedRows, SLABS_PER_STAGE, STAGES, JITTER>(ring, bar_full, bar_empty, row_off, sw, lane, stage, phase,
+                                                                      c, jitter_seed, &jitter_counter);
                 const unsigned int p = t * kFusedRows + threadIdx.x;                 // pixel within the frame
                 const unsigned int dst = flip180 ? (kFramePixels - 1u - p) : p;
                 const size_t dst_row = static_cast<size_t>(frame) * kFramePixels + dst;
@@ -133,9 +142,11 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* __rest
             mn = warp_min(mn);
             mx = warp_max(mx);
             const int slot = it & 1;
+            if (JITTER) jitter_spin(jitter_seed, 4u, jitter_counter);
             mbar_wait(frame_empty + 8 * slot, ((it >> 1) & 1u) ^ 1u);    // slot consumed by the energy warps
             if (lane == 0) { sh.minmax[slot][warp][0] = mn; sh.minmax[slot][warp][1] = mx; }
             __syncwarp();
+            if (JITTER) jitter_spin(jitter_seed, 5u, jitter_counter);
             mbar_arrive(frame_full + 8 * slot);                           // release: MFCC rows + min/max visible
         }
         return;
@@ -146,6 +157,7 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* __rest
     unsigned int it = 0;
     for (unsigned int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++it) {
         const int slot = it & 1;
+        if (JITTER) jitter_spin(jitter_seed, 6u, jitter_counter);
         mbar_wait(frame_full + 8 * slot, (it >> 1) & 1u);
         float lo = sh.minmax[slot][0][0], hi = sh.minmax[slot][0][1];
 #pragma unroll
@@ -153,6 +165,7 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* __rest
             lo = fminf(lo, sh.minmax[slot][w][0]);
             hi = fmaxf(hi, sh.minmax[slot][w][1]);
         }
+        if (JITTER) jitter_spin(jitter_seed, 7u, jitter_counter);
         mbar_arrive(frame_empty + 8 * slot);
         const FrameNorm norm(lo, __fsub_rn(hi, lo));
         const float* img = mfcc_out + static_cast<size_t>(frame) * kFrameValues;
@@ -163,7 +176,11 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* __rest
             float x[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
             unsigned int rare;
             double en = pixel_energy(x, normalize_first != 0, norm, sh.exp_table, rare);
-            if (rare) en = pixel_energy_plain(img + p * kMfccNum, nullptr, normalize_first != 0, norm.lo, norm.range);
+            if (rare) {                                            // the values already loaded, not a second (read-only) load
+                const float raw[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+                en = pixel_energy_plain(raw, nullptr, normalize_first != 0, norm.lo, norm.range);
+            }
+            if (JITTER && (p & 255) == (et & 255)) jitter_spin(jitter_seed, 8u, jitter_counter);
             sh.map[p] = en;
             if (energy_out != nullptr) energy_out[static_cast<size_t>(frame) * kFramePixels + p] = en;
         }

@@ -47,9 +47,11 @@ struct MfccPipe {
 // One consumer thread's work on one tile: wait for the tile's ring stages, run the straight-line mel
 // program on the thread's spectrum, release the stages, and return the 12 cepstra with the reference's
 // NaN/Inf -> 0 fix-up applied.  `stage` / `phase` are the thread's view of the ring position.
-template <int ROWS, int SLABS_PER_STAGE, int STAGES>
+// JITTER (debug builds of the fused kernel only): pseudo-random delays before every barrier wait / arrive.
+template <int ROWS, int SLABS_PER_STAGE, int STAGES, bool JITTER = false>
 __device__ __forceinline__ void mel_tile(uint32_t ring, uint32_t bar_full, uint32_t bar_empty, uint32_t row_off,
-                                         uint32_t sw, int lane, int& stage, uint32_t& phase, float (&c)[12]) {
+                                         uint32_t sw, int lane, int& stage, uint32_t& phase, float (&c)[12],
+                                         unsigned int jitter_seed = 0, unsigned int* jitter_counter = nullptr) {
     using P = MfccPipe<ROWS, SLABS_PER_STAGE, STAGES>;
     AIG_MEL_DECL(0) AIG_MEL_DECL(1) AIG_MEL_DECL(2) AIG_MEL_DECL(3) AIG_MEL_DECL(4) AIG_MEL_DECL(5)
     AIG_MEL_DECL(6) AIG_MEL_DECL(7) AIG_MEL_DECL(8) AIG_MEL_DECL(9) AIG_MEL_DECL(10) AIG_MEL_DECL(11)
@@ -65,6 +67,7 @@ __device__ __forceinline__ void mel_tile(uint32_t ring, uint32_t bar_full, uint3
 
 #define MEL_SLAB_BEGIN(s)                                                                        \
     {                                                                                            \
+        if (JITTER && (s) % SLABS_PER_STAGE == 0) jitter_spin(jitter_seed, 1u, *jitter_counter); \
         if ((s) % SLABS_PER_STAGE == 0) mbar_wait(bar_full + 8 * stage, phase);                  \
         const uint32_t slab = ring + stage * P::kStageBytes +                                    \
                               ((s) % SLABS_PER_STAGE) * P::kSlabBytes + row_off;
@@ -93,6 +96,7 @@ __device__ __forceinline__ void mel_tile(uint32_t ring, uint32_t bar_full, uint3
         }
 #define MEL_SLAB_END(s)                                                                          \
         if ((s) % SLABS_PER_STAGE == SLABS_PER_STAGE - 1) {                                      \
+            if (JITTER) jitter_spin(jitter_seed, 2u, *jitter_counter);                           \
             __syncwarp();                                                                        \
             if (lane == 0) mbar_arrive(bar_empty + 8 * stage);                                   \
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }                                   \
@@ -120,10 +124,12 @@ __device__ __forceinline__ void mel_tile(uint32_t ring, uint32_t bar_full, uint3
 template <int ROWS, int SLABS_PER_STAGE, int STAGES>
 __device__ __forceinline__ void load_tile(const CUtensorMap* tmap, uint32_t ring, uint32_t bar_full,
                                           uint32_t bar_empty, int32_t row0, uint64_t policy, int& stage,
-                                          uint32_t& phase) {
+                                          uint32_t& phase, unsigned int jitter_seed = 0,
+                                          unsigned int* jitter_counter = nullptr) {
     using P = MfccPipe<ROWS, SLABS_PER_STAGE, STAGES>;
 #pragma unroll 1
     for (int kb = 0; kb < P::kStagesPerTile; ++kb) {
+        if (jitter_seed != 0u) jitter_spin(jitter_seed, 3u, *jitter_counter);
         mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
         mbar_arrive_expect_tx(bar_full + 8 * stage, P::kStageBytes);
 #pragma unroll

@@ -11,7 +11,7 @@
 #pragma once
 
 #include "aig_common.cuh"
-#include "energy_kernel.cuh"   // linear_tap_exact / MaskTaps
+#include "heatmap_kernel.cuh"   // linear_tap_exact / MaskTaps
 
 namespace aig {
 

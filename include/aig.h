@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define AIG_ABI_VERSION 1
+#define AIG_ABI_VERSION 2
 
 #define AIG_OK 0
 #define AIG_ERR_ARGUMENT (-1)    /* null / out-of-range / inconsistent argument        */
@@ -71,6 +71,11 @@ const char* aig_last_error(const aig_handle* h);
 
 /* ABI version of the loaded library (== AIG_ABI_VERSION of the header it was built from). */
 int aig_abi_version(void);
+
+/* Hash of the sources and compiler flags the library was built from, stamped in by the build
+ * (acoustic_image_generation_b200/_lib.py: source_build_id).  The Python loader refuses a library whose stamp differs
+ * from the sources next to it, so a shipped binary is always the committed source. */
+const char* aig_build_id(void);
 
 /* Block until everything enqueued on the handle's stream(s) has finished. */
 int aig_synchronize(aig_handle* h);
@@ -124,7 +129,13 @@ int aig_normalize_images(aig_handle* h, const float* images, int64_t n_frames, f
  *   energy_out      nullable [n_frames, 36, 48] float64: 1 / sum_j exp(sum_m x_m dct[j][m])
  *   mask_out        nullable [n_frames, 36, 48] uint8: energy > mean(energy), mean in
  *                   float64 with NumPy's pairwise summation order
- *   mean_out        nullable [n_frames] float64 */
+ *   mean_out        nullable [n_frames] float64
+ * Aliasing contract: scaled_out may be the very same buffer as images (find_logen scales its argument in place); no
+ * other pair of buffers may overlap.  The kernels read images through ordinary (coherent) loads and load a pixel's
+ * values before storing anything of that pixel.  Device image buffers must be 16-byte aligned.
+ * Fewer frames than the device has SMs run one frame per thread-block cluster of 8 CTAs (see "small_batch_frames");
+ * the results are bit-identical either way.  NaN in a frame propagates through the min / max of normalize_first like
+ * tf.reduce_min / reduce_max: the whole frame's energies are NaN and its mask is empty. */
 int aig_energy(aig_handle* h, const float* images, int64_t n_frames, int normalize_first,
                float* scaled_out, double* energy_out, uint8_t* mask_out, double* mean_out);
 
@@ -138,8 +149,11 @@ int aig_energy(aig_handle* h, const float* images, int64_t n_frames, int normali
 int aig_heatmap(aig_handle* h, const double* energy, int64_t n_frames, int out_h, int out_w,
                 float* heat_out);
 
-/* aig_energy followed by aig_heatmap on the device, without a host round trip for the energy map: the per-frame body of
- * showvideo.py:226-228 / showimages.py:146-148 (find_logen -> cv2.resize -> imshow normalisation) for a batch.
+/* The per-frame body of showvideo.py:226-228 / showimages.py:146-148 (find_logen -> cv2.resize -> imshow
+ * normalisation) for a batch, in ONE kernel launch: the float64 energy map goes from the find_logen warps to the
+ * up-sampling and normalisation passes through shared memory and the heat map leaves the SM as bulk asynchronous
+ * copies.  (Shapes with odd out_w or out_h * out_w not a multiple of 4, "heatmap_exact" mode and batches smaller than
+ * the SM count run aig_energy's and aig_heatmap's kernels back to back instead - same arithmetic.)
  * energy_out / mask_out are nullable; heat_out [n_frames, out_h, out_w] float32 is required. */
 int aig_energy_heatmap(aig_handle* h, const float* images, int64_t n_frames, int normalize_first, double* energy_out,
                        uint8_t* mask_out, float* heat_out, int out_h, int out_w);
@@ -159,6 +173,20 @@ int aig_mfcc_energy(aig_handle* h, const float* power, int64_t n_frames, int fli
                     double* mean_out);
 
 /* ---- stage 3: scoring ------------------------------------------------------------------ */
+
+/* The reference's whole ACIVW / AVIA evaluation step (iouenergythreshold.py:213-229) for a batch in one kernel launch:
+ * real and reconstructed 12-channel image -> find_logen of each (on the np.stack copy, :216: the caller's arrays are not
+ * scaled) -> mean masks -> I = sum(m & m2), U = sum(m | m2) -> iou -> pos[j] += iou > thr[j], num += 1 per frame.
+ * Both energy maps and both masks stay in shared memory; they are written out only where a pointer is given.
+ *   real, reconstructed  [n, 36, 48, 12] float32 (device buffers 16-byte aligned)
+ *   normalize_first      as in aig_energy (0 for the reference's call)
+ *   thr [k], inter_out / union_out nullable [n], pos_inout [k], num_inout [1]: as in aig_iou_sweep (accumulating)
+ *   energy_*_out nullable [n, 36, 48] float64, mask_*_out nullable [n, 36, 48] uint8
+ * Batches smaller than the SM count (the reference's are 2-16 frames) split every frame pair over a cluster of 8 CTAs. */
+int aig_acivw_batch(aig_handle* h, const float* real, const float* reconstructed, int64_t n_frames, int normalize_first,
+                    const double* thr, int k, int64_t* inter_out, int64_t* union_out, int64_t* pos_inout,
+                    int64_t* num_inout, double* energy_real_out, double* energy_recon_out, uint8_t* mask_real_out,
+                    uint8_t* mask_recon_out);
 
 /* ACIVW / AVIA IoU and success counts (iouenergythreshold.py:224-229), all thresholds in one pass
  * (the reference re-runs the evaluation once per threshold, scripts/iou.bash:47-53).
@@ -283,12 +311,22 @@ uint32_t aig_crc32c(const void* data, size_t n, int force_table);
  *   aig_allreduce_counts in-place sum of n int64 values over all ranks, enqueued on the handle's stream
  *                        (device buffer: asynchronous, ordered after the sweeps that filled it; host buffer:
  *                        staged and synchronous).  With no communicator (single rank) it is the identity.
- *   aig_comm_destroy     leave the communicator (also done by aig_destroy) */
+ *                        A one-rank communicator (world == 1) is legal and still goes through ncclAllReduce.
+ *   aig_comm_destroy     leave the communicator (also done by aig_destroy)
+ * One process driving several GPUs - the shape of the reference's callers, which are single processes
+ * (iouenergythreshold.py:140-236, scripts/iou.bash:47-53):
+ *   aig_comm_init_all           one communicator over n handles of this process, one per distinct device
+ *                               (ncclCommInitAll); handle i becomes rank i
+ *   aig_group_allreduce_counts  the all-reduce for all n handles in one grouped NCCL call (ncclGroupStart / End) from one
+ *                               host thread; counts[i] is handle i's DEVICE buffer of n int64, summed in place on
+ *                               handle i's stream */
 #define AIG_COMM_ID_BYTES 128
 int aig_comm_unique_id(uint8_t* id_out);
 int aig_comm_init(aig_handle* h, const uint8_t* id, int rank, int world);
 int aig_allreduce_counts(aig_handle* h, int64_t* counts, int n);
 int aig_comm_destroy(aig_handle* h);
+int aig_comm_init_all(aig_handle** handles, int n);
+int aig_group_allreduce_counts(aig_handle** handles, int64_t* const* counts, int n_handles, int n);
 
 /* areaundercurve.py:32-37: sklearn.metrics.auc on the reversed (descending) threshold / success-rate
  * arrays == direction * trapezoid.  Host-side, float64.  thr / value are host arrays of length k. */
@@ -319,6 +357,14 @@ int64_t aig_launch_count(const aig_handle* h);
  *   "host_copy_threads"  copies of 8 MiB and more from / to ordinary (pageable) host arrays are staged through a ring
  *                        of pinned 4 MiB slots by this many host threads (host_staging.h; 4-5x the driver's own
  *                        pageable path): -1 (default) min(6, hardware threads / 2); 0 leaves them to cudaMemcpyAsync
+ *   "heat_bulk_store"    1 (default): heat maps are staged in shared memory and written with bulk asynchronous copies
+ *                        (heat_stream_kernel); 0: the round-1 kernel with per-thread stores, for comparison runs
+ *   "small_batch_frames" batches with fewer frames than this spread each frame over a cluster of 8 CTAs (aig_energy,
+ *                        aig_acivw_batch) and run aig_mfcc_energy as tiled MFCC kernel + cluster energy kernel instead of
+ *                        the one-CTA-per-frame persistent kernel; 0 (default) = the device's SM count
+ *   "debug_jitter"       non-zero seed: aig_mfcc_energy runs the jittered build of the persistent kernel, in which the TMA
+ *                        producer, the MFCC consumers and the energy warps spin for pseudo-random times before every
+ *                        barrier wait / arrive (race stress test standing in for compute-sanitizer); 0 (default): off
  *   "profile"            1: bracket every MFCC / energy kernel launch with CUDA events on the stream it
  *                        is launched on (read back with aig_profile_read); 0 (default): off
  * Unknown names or out-of-range values return AIG_ERR_ARGUMENT. */
@@ -329,6 +375,9 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value);
  *              out[0] = mismatching (input, lifter) pairs, out[1] = mismatches surviving the float32 store
  *   which = 1  the table-driven exp against CUDA's exp() on 2 * 2^26 points of [-700, 700] and [-12, 12]:
  *              out[0] = points differing, out[1] = largest difference in ulps, out[2] = points compared
+ *   which = 2  the hoisted-reciprocal float32 division of the per-frame min-max normalisation against __fdiv_rn on
+ *              2^32 (value, range) pairs: out[0] = pairs differing, out[1] = pairs compared, out[2] = pairs that took
+ *              the reciprocal path (the rest fall back to IEEE division)
  * `out` is a host array of 4 uint64. */
 int aig_selftest(aig_handle* h, int which, uint64_t* out);
 

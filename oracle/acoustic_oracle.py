@@ -345,6 +345,12 @@ def success_rates(pos, num):
     return np.asarray(pos, dtype=np.float64) / np.float64(num)
 
 
+def rates_as_written(rates):
+    """The success rates as areaundercurve.py:28-31 reads them: each was written as 'iou {:6f}'
+    (iouenergythreshold.py:235-236) and is parsed back from that text, i.e. rounded to six decimals."""
+    return np.array([float('iou {:6f}'.format(float(r)).split(' ')[1]) for r in np.asarray(rates, dtype=np.float64)])
+
+
 def auc(thresholds, values):
     """sklearn.metrics.auc on the *reversed* arrays, as areaundercurve.py:32-37 does:
     x decreasing => direction -1 times the trapezoid sum of diff(x)*(y[1:]+y[:-1])/2."""

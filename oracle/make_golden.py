@@ -111,6 +111,81 @@ def replay_flickr_frame(ref, cv2, recon_frame, xmin, xmax, ymin, ymax, out_w=298
     return float(np.sum(intersection)), float(np.sum(unionbig)), float(iou_score), mtot, m2
 
 
+def replay_flickr_mask(cv2, mask_small, xmin, xmax, ymin, ymax, out_w=298, out_h=224):
+    """showimages_bb.py:288-296 and :303-318 for one frame whose mean-threshold mask `1 * (map2 > mean2)` is given
+    (int64 [36, 48]) - the same statements and dtypes as replay_flickr_frame from `m2 = cv2.resize(...)` on."""
+    m = np.zeros((3, out_h, out_w), dtype=np.float32)
+    for contour in range(3):
+        if xmax[contour] != 0:
+            cv2.rectangle(m[contour], (int(xmin[contour]), int(ymin[contour])),
+                          (int(xmax[contour]), int(ymax[contour])), (255, 255, 255), -1)
+            m[contour] = m[contour] / 255.
+            m[contour] = m[contour] / 2.
+    mtot = np.sum(m, axis=0)
+    mtot[mtot > 1.0] = 1.0
+    m2 = np.asarray(mask_small, np.int64)
+    m2 = cv2.resize(m2 * 1.0, (out_w, out_h))
+    m2 = 1.0 * (m2 > 0.5)
+    intersection = np.logical_and(mtot, m2) * mtot
+    union = np.logical_or(mtot, m2)
+    box = 1 * (mtot > 0)
+    unionbig = union + (mtot - box)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        iou_score = np.sum(intersection) / np.sum(unionbig)
+    return np.sum(intersection), np.sum(unionbig), iou_score
+
+
+def round2_goldens(cv2, metrics, acivw_pos11, n_pairs, flickr_pos11, n_fl):
+    """Round-2 additions: (a) the AUC the way the reference's PIPELINE computes it - the evaluation scripts
+    write each success rate as 'iou {:6f}' (iouenergythreshold.py:235-236), areaundercurve.py:28-37 parses the text back
+    and integrates those six-decimal values; (b) consensus-IoU frames whose I / U is exactly 1/10 and 3/10: the dtype of
+    the reference's ratio (float32 sum / float64 sum -> float64) decides whether `iou_score > 0.1` counts them."""
+    import tempfile
+    out = {}
+    cases = (('acivw11', acivw_pos11, n_pairs), ('flickr11', flickr_pos11, n_fl),
+             ('sevenths', np.array([7, 6, 5, 4, 3, 3, 2, 1, 1, 0, 0], np.int64), 7),
+             ('thirds', np.array([3, 3, 2, 2, 2, 1, 1, 1, 0, 0, 0], np.int64), 3))
+    for name, pos, num in cases:
+        with tempfile.TemporaryDirectory() as data_dir:
+            for threshold, p in zip(REFERENCE_THRESHOLDS, pos):                       # the writers, :235-236
+                with open('{}'.format(data_dir) + "/intersection_{}_accuracy.txt".format(threshold * 1.0), "w") as outfile:
+                    outfile.write('iou {:6f}'.format(1.0 * int(p) / num))
+            value = np.zeros(11)                                                        # areaundercurve.py:26-37
+            threshold = list(REFERENCE_THRESHOLDS)
+            for i in range(len(threshold)):
+                with open('{}'.format(data_dir) + "/intersection_{}_accuracy.txt".format(threshold[i]), "r") as outfile:
+                    t = outfile.read()
+                    value[i] = t.split(' ')[1]
+            value = value[::-1]
+            threshold = threshold[::-1]
+            area = metrics.auc(threshold, value)
+        out[name + '_pos'] = np.asarray(pos, np.int64)
+        out[name + '_num'] = np.int64(num)
+        out[name + '_auc_from_files'] = np.float64(area)
+        out[name + '_area_text'] = np.array('area {:6f}'.format(area))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, 'auc_files.npz'), **out)
+
+    # (b) identity-size "up-sampling" (out 48 x 36), one annotator (weight 0.5) inside the predicted region:
+    # I = 0.5 B, U = P - 0.5 B for a box of B pixels inside P predicted pixels
+    masks = np.zeros((3, 36, 48), np.uint8)
+    boxes = np.zeros((4, 3, 3), np.int32)                  # xmin, xmax, ymin, ymax  x  frame  x  annotator
+    masks[0, 5, 10:21] = 1                                 # P = 11, box B = 2  ->  I / U = 1 / 10
+    boxes[:, 0, 0] = (12, 13, 5, 5)
+    masks[1, 8, 3:16] = 1                                  # P = 13, box B = 6  ->  3 / 10
+    boxes[:, 1, 0] = (4, 9, 8, 8)
+    masks[2, 20:24, 20:30] = 1                             # P = 40, two overlapping annotators -> generic control case
+    boxes[:, 2, 0] = (18, 25, 19, 22)
+    boxes[:, 2, 1] = (22, 33, 21, 26)
+    rows = [replay_flickr_mask(cv2, masks[f], boxes[0, f], boxes[1, f], boxes[2, f], boxes[3, f], 48, 36) for f in range(3)]
+    score = np.array([np.float64(r[2]) for r in rows])
+    ratio = dict(masks=masks, xmin=boxes[0], xmax=boxes[1], ymin=boxes[2], ymax=boxes[3],
+                 inter=np.array([np.float64(r[0]) for r in rows]), union=np.array([np.float64(r[1]) for r in rows]),
+                 iou=score, ratio_dtype=np.array(str(np.asarray(rows[0][2]).dtype)),
+                 counted=np.array([[bool(r[2] > t) for t in REFERENCE_THRESHOLDS] for r in rows]),
+                 pos11=np.array([int(sum(bool(r[2] > t) for r in rows)) for t in REFERENCE_THRESHOLDS], np.int64))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, 'ciou_ratio.npz'), **ratio)
+
+
 def main(reference_root='/root/reference'):
     import cv2
     from sklearn import metrics
@@ -214,6 +289,7 @@ def main(reference_root='/root/reference'):
         value = np.array([1.0 * p / num for p in pos])
         aucs[name] = np.float64(metrics.auc(list(thr)[::-1], value[::-1]))
     np.savez_compressed(os.path.join(GOLDEN_DIR, 'auc.npz'), **aucs)
+    round2_goldens(cv2, metrics, acivw['pos11'], n_pairs, flickr['pos11'], n_fl)
 
     # ---- G8: audio front half (N1): the reference's module-level _build_spectrograms_function and the loader's
     # butter_lowpass_filter, unmodified; `signal.tukey` moved to scipy.signal.windows in current scipy, so the

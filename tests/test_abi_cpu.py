@@ -35,7 +35,28 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version(lib):
-    assert lib.aig_abi_version() == 1
+    assert lib.aig_abi_version() == _lib.ABI_VERSION == 2
+    header = open(os.path.join(ROOT, 'include', 'aig.h')).read()
+    assert '#define AIG_ABI_VERSION %d' % _lib.ABI_VERSION in header
+
+
+def test_binary_carries_the_build_id_of_the_sources(lib, tmp_path, monkeypatch):
+    """The shipped libaig.so is tied to the sources next to it by content hash, not by modification time: the stamp in
+    the file, the stamp the loaded library reports and the hash of DEPENDS + compiler flags must all agree, and a
+    library with another stamp is refused."""
+    want = _lib.source_build_id()
+    assert _lib.binary_build_id() == want and not _lib.needs_build()
+    assert lib.aig_build_id().decode() == want
+    # any change to a source file changes the id ...
+    blob = open(_lib.LIB_PATH, 'rb').read()
+    fake = tmp_path / 'libaig.so'
+    fake.write_bytes(blob.replace(_lib.BUILD_ID_MARKER + want.encode(), _lib.BUILD_ID_MARKER + b'0' * len(want)))
+    assert _lib.binary_build_id(str(fake)) == '0' * len(want)
+    # ... and load() refuses a stale binary when it may not rebuild it
+    monkeypatch.setattr(_lib, 'LIB_PATH', str(fake))
+    monkeypatch.setattr(_lib, '_lib', None)
+    with pytest.raises(RuntimeError, match='built from other sources'):
+        _lib.load(build_if_missing=False)
 
 
 def test_shared_object_is_in_tree_and_sm100a():

@@ -1,0 +1,334 @@
+"""Round-2 kernels through the C ABI, against the oracle, the golden vectors and each other.  Needs a B200.
+
+* stage2_kernel / stage2_cluster_kernel (two threads per pixel; one CTA or one cluster of 8 CTAs per frame): the two
+  forms must agree bit for bit with each other - energies, means, masks, in-place scaling - and with the oracle within
+  the float64 tolerance; NaN propagation of the min / max; in-place aliasing on device tensors.
+* aig_acivw_batch: the reference's evaluation step in one launch == energy + energy + iou_sweep, == the golden replay.
+* heat_stream_kernel (bulk shared -> global copies): == the round-1 per-thread-store kernel bit for bit, fused
+  aig_energy_heatmap == the two-kernel chain bit for bit.
+* debug_jitter: 200 random (frames, seed) cases of the jittered persistent kernel == the sequential two-kernel path.
+* one-rank NCCL communicator: aig_comm_init / aig_allreduce_counts run NCCL on a single-GPU box.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import acoustic_image_generation_b200 as aig
+from acoustic_image_generation_b200 import evaluate, synth
+from oracle import acoustic_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+ENERGY_RTOL = 1e-13
+REF_THR = list(oracle.REFERENCE_THRESHOLDS)
+
+
+@pytest.fixture(scope='module')
+def path():
+    p = aig.AcousticPath(0)
+    yield p
+    p.close()
+
+
+@pytest.fixture(scope='module')
+def path_cta():
+    """A handle that never takes the cluster-per-frame form: one CTA per frame whatever the batch size."""
+    p = aig.AcousticPath(0)
+    p.set_option('small_batch_frames', 1)
+    yield p
+    p.close()
+
+
+@pytest.fixture(scope='module')
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _images_with_hard_cases(n, seed):
+    """Smooth / sigmoid images plus the pixels the fast float64 path hands to the plain path: huge values (|mel| > 700),
+    an Inf, a NaN, a constant frame."""
+    imgs = np.concatenate([synth.smooth_images(n // 2, seed), synth.sigmoid_images(n - n // 2, seed + 1)], 0)
+    imgs[1, 3, 5, :] = 400.0                 # exp overflow on the fast path -> plain path
+    imgs[2, 10, 7, 4] = np.inf
+    imgs[3, 0, 0, 0] = -250.0
+    imgs[4] = 0.25                           # constant frame
+    return imgs
+
+
+# ----------------------------------------------------------------------------------------------
+# energy: the two kernel forms, the oracle, aliasing, NaN
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('normalize_first', [False, True])
+def test_energy_cluster_and_cta_forms_are_bit_identical(path, path_cta, normalize_first):
+    imgs = _images_with_hard_cases(23, 40)
+    a = path.energy(imgs, normalize_first=normalize_first, want_scaled=True, want_mean=True)
+    b = path_cta.energy(imgs, normalize_first=normalize_first, want_scaled=True, want_mean=True)
+    for name, x, y in zip(('energy', 'mask', 'scaled', 'mean'), a, b):
+        assert np.array_equal(x, y, equal_nan=True), name
+    want_e, want_m = oracle.energy_stage(imgs, normalize_first=normalize_first)
+    ok = np.isfinite(want_e)
+    assert np.array_equal(np.isfinite(a[0]), ok)
+    assert np.abs(a[0][ok] - want_e[ok]).max() <= ENERGY_RTOL * np.abs(want_e[ok]).max()
+    diff = int((a[1] != want_m).sum())
+    print('masks differing from the oracle on the hard-case batch: %d' % diff)
+    assert diff == 0
+
+
+def test_energy_large_batch_equals_small_batch_form(path, path_cta):
+    """Above the SM count the default handle runs one CTA per frame; below, a cluster per frame: same bits."""
+    imgs = synth.smooth_images(200, 41)
+    big = path.energy(imgs, normalize_first=True, want_mean=True)
+    small = [path.energy(imgs[i:i + 50], normalize_first=True, want_mean=True) for i in range(0, 200, 50)]
+    for k in range(3):
+        assert np.array_equal(big[k], np.concatenate([s[k] for s in small], 0))
+
+
+def test_find_logen_in_place_on_device_tensors_both_forms(path, path_cta, golden, torch):
+    """scaled_out == images (find_logen scales its argument in place): ADVICE r1 flagged read-only loads on memory the
+    kernel writes.  Both forms, one frame and a batch, against the reference-run golden."""
+    g = golden('energy')
+    for p in (path, path_cta):
+        dev = torch.from_numpy(synth.sigmoid_images(2, 3)[0].copy()).cuda()
+        en = p.find_logen(dev)
+        assert np.array_equal(dev.cpu().numpy(), g['sigmoid0_after_call'])
+        assert np.abs(en.cpu().numpy() - g['energy_sigmoid'][0]).max() <= ENERGY_RTOL * float(en.max())
+        # a batch, in place through the raw ABI (images == scaled_out), hard cases included
+        imgs = _images_with_hard_cases(12, 44)
+        want = p.energy(imgs, want_scaled=True)
+        t = torch.from_numpy(imgs.copy()).cuda()
+        e = torch.empty((12, 36, 48), dtype=torch.float64, device='cuda')
+        assert p._lib.aig_energy(p._h, t.data_ptr(), 12, 0, t.data_ptr(), e.data_ptr(), None, None) == 0
+        assert np.array_equal(t.cpu().numpy(), want[2], equal_nan=True)
+        assert np.array_equal(e.cpu().numpy(), want[0], equal_nan=True)
+
+
+def test_nan_propagates_through_min_max_like_tf(path, path_cta):
+    """tf.reduce_min / reduce_max propagate NaN (outdoor_data_mfcc.py:674,677): a frame holding one NaN normalises to
+    all-NaN; its energies are NaN and its mask empty.  (fminf / fmaxf would have dropped the NaN.)"""
+    imgs = synth.sigmoid_images(3, 45)
+    imgs[1, 7, 9, 2] = np.nan
+    for p in (path, path_cta):
+        normed = p.normalize_images(imgs)
+        assert np.isnan(normed[1]).all() and np.isfinite(normed[0]).all() and np.isfinite(normed[2]).all()
+        assert np.array_equal(normed, oracle.normalize_acoustic_images(imgs), equal_nan=True)
+        energy, mask = p.energy(imgs, normalize_first=True)
+        assert np.isnan(energy[1]).all() and mask[1].sum() == 0
+        assert np.isfinite(energy[0]).all() and np.isfinite(energy[2]).all()
+    vec = synth.sigmoid_images(1, 46)[0, 0, :5, :].copy()           # five 12-vectors
+    vec[2, 3] = np.nan
+    got = path.normalize_mfcc(vec)
+    assert np.isnan(got[2]).all() and np.isfinite(got[[0, 1, 3, 4]]).all()
+
+
+def test_selftest_hoisted_reciprocal_division(path):
+    """FrameNormFast::apply against __fdiv_rn on 2^32 (value, range) pairs: no difference anywhere."""
+    bad, count, fast, _ = path.selftest(2)
+    print('min-max division selftest: %d pairs, %d on the reciprocal path, %d mismatches' % (count, fast, bad))
+    assert count == 1 << 32 and bad == 0 and fast > count // 3
+
+
+# ----------------------------------------------------------------------------------------------
+# aig_acivw_batch
+# ----------------------------------------------------------------------------------------------
+def test_acivw_batch_matches_reference_replay(path, path_cta, golden):
+    g = golden('acivw_iou')
+    n = int(g['num'])
+    a, b = synth.smooth_images(n, 10), synth.smooth_images(n, 11)
+    b[: n // 2] = a[: n // 2] * np.float32(0.9) + b[: n // 2] * np.float32(0.1)
+    assert synth.digest(a) == str(g['digest_a']) and synth.digest(b) == str(g['digest_b'])
+    keep_a, keep_b = a.copy(), b.copy()
+    for p in (path, path_cta):
+        inter, union, pos, num = p.acivw_batch(a, b)
+        assert np.array_equal(inter, g['inter']) and np.array_equal(union, g['union'])
+        assert np.array_equal(pos, g['pos11']) and num == n
+        inter, union, pos, num = p.acivw_batch(a, b, np.linspace(0, 1, 101))
+        assert np.array_equal(pos, g['pos101'])
+    assert np.array_equal(a, keep_a) and np.array_equal(b, keep_b)      # the reference works on an np.stack copy
+
+
+@pytest.mark.parametrize('n', [1, 7, 16, 150, 333])
+@pytest.mark.parametrize('normalize_first', [False, True])
+def test_acivw_batch_equals_separate_kernels(path, path_cta, torch, n, normalize_first):
+    a = _images_with_hard_cases(max(n, 6), 50 + n)[:n] if n >= 6 else synth.smooth_images(n, 50)
+    b = synth.smooth_images(n, 51 + n)
+    if n > 3:
+        b[3] = a[3]                                        # identical pair: IoU exactly 1
+    e_a, m_a = path.energy(a, normalize_first=normalize_first)
+    e_b, m_b = path.energy(b, normalize_first=normalize_first)
+    want_i, want_u, want_pos, want_num = path.iou_sweep(m_a, m_b, REF_THR)
+    for p in (path, path_cta):
+        inter, union, pos, num, energies, masks = p.acivw_batch(a, b, REF_THR, normalize_first=normalize_first,
+                                                                want_energy=True, want_masks=True)
+        assert np.array_equal(inter, want_i) and np.array_equal(union, want_u)
+        assert np.array_equal(pos, want_pos) and num == want_num == n
+        assert np.array_equal(energies[0], e_a, equal_nan=True) and np.array_equal(energies[1], e_b, equal_nan=True)
+        assert np.array_equal(masks[0], m_a) and np.array_equal(masks[1], m_b)
+    # device tensors, accumulating device counters (two calls)
+    thr = torch.tensor(REF_THR, dtype=torch.float64, device='cuda')
+    counts = torch.zeros(12, dtype=torch.int64, device='cuda')
+    for _ in range(2):
+        path.acivw_batch(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), thr, pos=counts[:-1], num=counts[-1:],
+                         normalize_first=normalize_first)
+    assert np.array_equal(counts.cpu().numpy(), np.concatenate([2 * want_pos, [2 * n]]))
+
+
+def test_acivw_evaluation_driver_uses_one_launch_per_batch(path, golden):
+    g = golden('acivw_iou')
+    n = int(g['num'])
+    a, b = synth.smooth_images(n, 10), synth.smooth_images(n, 11)
+    b[: n // 2] = a[: n // 2] * np.float32(0.9) + b[: n // 2] * np.float32(0.1)
+    ev = evaluate.AcivwEvaluation(path)
+    before = path.launch_count
+    for lo in range(0, n, 16):                            # the reference's batch size
+        ev.add_batch(a[lo:lo + 16], b[lo:lo + 16])
+    assert path.launch_count - before == 3                # one kernel per add_batch
+    res = ev.finish()
+    assert np.array_equal(res['pos'], g['pos11']) and res['num'] == n
+    assert abs(res['auc_exact'] - float(golden('auc')['acivw11'])) <= 1e-12
+    assert abs(res['auc'] - float(golden('auc_files')['acivw11_auc_from_files'])) <= 1e-12
+
+
+def test_consensus_iou_exact_tenth_is_not_counted(path, golden):
+    """I / U exactly 1/10 and 3/10: the reference's ratio is float64 (golden made from its statements), so thresholds 0.1
+    and 0.3 do not count those frames; the kernel's float64 ratio agrees."""
+    g = golden('ciou_ratio')
+    i2, u2, pos, num = path.ciou_sweep(g['masks'], g['xmin'], g['xmax'], g['ymin'], g['ymax'], REF_THR, out_hw=(36, 48))
+    assert np.array_equal(i2, (2 * g['inter']).astype(np.int64)) and np.array_equal(u2, (2 * g['union']).astype(np.int64))
+    assert np.array_equal(pos, g['pos11']) and num == 3
+
+
+# ----------------------------------------------------------------------------------------------
+# heat maps: bulk-copy kernel, fused energy + heat map
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape', [(224, 298), (224, 224), (36, 48), (100, 78), (448, 596), (7, 12), (2, 2)])
+def test_heat_stream_kernel_equals_per_thread_store_kernel(path, shape):
+    """Same arithmetic (float32 lerp, min / max on the edge rows, (v - min) * inv), different way out of the SM: staged rows
+    + cp.async.bulk instead of st.global.  Bit-identical, and within tolerance of the oracle."""
+    rng = np.random.default_rng(shape[0] * 31 + shape[1])
+    e = rng.random((301, 36, 48)) ** 3
+    e[5] = 0.75                                           # constant map -> NaN
+    got = path.heatmap(e, *shape)
+    path.set_option('heat_bulk_store', 0)
+    try:
+        old = path.heatmap(e, *shape)
+    finally:
+        path.set_option('heat_bulk_store', 1)
+    assert np.array_equal(got, old, equal_nan=True)
+    assert np.isnan(got[5]).all()
+    for i in (0, 150, 300):
+        assert np.abs(got[i] - oracle.heatmap(e[i], *shape)).max() <= 2e-6
+        assert got[i].min() == 0.0 and abs(float(got[i].max()) - 1.0) <= 1e-6
+
+
+@pytest.mark.parametrize('shape', [(224, 298), (224, 224)])
+@pytest.mark.parametrize('normalize_first', [False, True])
+def test_fused_energy_heatmap_equals_the_two_kernel_chain(path, torch, shape, normalize_first):
+    """n >= SM count takes the single-launch kernel (energy map handed over in shared memory); the chain of aig_energy
+    and aig_heatmap is the reference for it: energies, masks and heat maps bit for bit."""
+    imgs = _images_with_hard_cases(400, 60)
+    before = path.launch_count
+    energy, mask, heat = path.energy_heatmap(imgs, normalize_first, *shape)
+    assert path.launch_count - before == 1
+    e2, m2 = path.energy(imgs, normalize_first=normalize_first)
+    h2 = path.heatmap(e2, *shape)
+    assert np.array_equal(energy, e2, equal_nan=True) and np.array_equal(mask, m2)
+    assert np.array_equal(heat, h2, equal_nan=True)
+    _, _, only_heat = path.energy_heatmap(torch.from_numpy(imgs).cuda(), normalize_first, *shape, want_energy=False, want_mask=False)
+    assert np.array_equal(only_heat.cpu().numpy(), heat, equal_nan=True)
+    i = 7
+    base = imgs[i:i + 1]
+    want = oracle.heatmap(oracle.energy_stage(base, normalize_first=normalize_first)[0][0], *shape)
+    assert np.abs(heat[i] - want).max() <= 1e-4
+
+
+def test_heatmap_exact_mode_still_bit_exact_through_the_combined_call(path):
+    imgs = synth.smooth_images(160, 61)
+    path.set_option('heatmap_exact', 1)
+    try:
+        energy, _, heat = path.energy_heatmap(imgs)
+    finally:
+        path.set_option('heatmap_exact', 0)
+    for i in (0, 80, 159):
+        assert np.array_equal(heat[i], oracle.heatmap(energy[i]).astype(np.float32))
+
+
+# ----------------------------------------------------------------------------------------------
+# small batches of the chained call, race stress
+# ----------------------------------------------------------------------------------------------
+def test_small_batch_mfcc_energy_equals_persistent_kernel(path, path_cta):
+    """Below the SM count aig_mfcc_energy runs the tiled MFCC kernel + the cluster energy kernel; path_cta
+    (small_batch_frames = 1) keeps the one-CTA-per-frame persistent kernel.  Same bits."""
+    power = synth.power_frames(9, 70, 'chi2')
+    a = path.mfcc_energy(power, flip=True, normalize_first=True, want_mean=True)
+    b = path_cta.mfcc_energy(power, flip=True, normalize_first=True, want_mean=True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_race_stress_jittered_persistent_kernel(torch):
+    """compute-sanitizer's racecheck is closed on this pool.  Instead the persistent kernel is built a second time with
+    pseudo-random clock64() spins before every mbarrier wait / arrive of its three roles (TMA producer, MFCC consumers,
+    energy warps; option debug_jitter = seed): 200 random (frame count, seed, flip, normalise) cases must reproduce the
+    sequential two-kernel path (chain_mode 0) bit for bit.  A hand-off that only works by timing luck would not."""
+    rng = np.random.default_rng(2024)
+    pool = torch.from_numpy(synth.power_frames(24, 71, 'chi2')).cuda()
+    extra = torch.from_numpy(synth.power_frames(8, 72, 'lognormal')).cuda()
+    pool = torch.cat([pool, extra], 0)
+    ref_path = aig.AcousticPath(0)
+    ref_path.set_option('chain_mode', 0)
+    ref_path.set_option('small_batch_frames', 1)
+    jit_path = aig.AcousticPath(0)
+    failures = []
+    try:
+        for case in range(200):
+            n = int(rng.integers(1, 420))
+            seed = int(rng.integers(1, 2 ** 31 - 1))
+            flip, norm = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+            idx = torch.from_numpy(rng.integers(0, len(pool), n)).cuda()
+            power = pool[idx].contiguous()
+            want = ref_path.mfcc_energy(power, flip=flip, normalize_first=norm, want_mean=True)
+            jit_path.set_option('debug_jitter', seed)
+            got = jit_path.mfcc_energy(power, flip=flip, normalize_first=norm, want_mean=True)
+            for name, x, y in zip(('mfcc', 'energy', 'mask', 'mean'), got, want):
+                if not torch.equal(x, y):
+                    failures.append((case, n, seed, name))
+    finally:
+        ref_path.close()
+        jit_path.close()
+    assert not failures, failures[:10]
+
+
+# ----------------------------------------------------------------------------------------------
+# NCCL on one GPU
+# ----------------------------------------------------------------------------------------------
+def test_one_rank_nccl_communicator_runs_the_native_allreduce(path, torch):
+    """aig_comm_unique_id -> aig_comm_init(rank 0 of 1) -> aig_allreduce_counts: a legal one-rank NCCL communicator, so the
+    library's own collective path (dlopen'd NCCL, the handle's stream, device and host buffers) is exercised on a
+    single-GPU box; with several ranks only the sum changes (tests/test_gpu_multirank.py)."""
+    p = aig.AcousticPath(0)
+    try:
+        ident = aig.AcousticPath.comm_unique_id()
+        assert len(ident) == 128 and any(ident)
+        p.init_comm_from_id(ident, 0, 1)
+        assert p.has_comm
+        dev = torch.arange(12, dtype=torch.int64, device='cuda') * 3
+        before = dev.clone()
+        p.allreduce_counts(dev)
+        p.synchronize()
+        assert torch.equal(dev, before)
+        host = np.arange(12, dtype=np.int64) + 5
+        p.allreduce_counts(host)
+        assert np.array_equal(host, np.arange(12) + 5)
+        # an evaluation that finishes through the handle's communicator
+        ev = evaluate.AcivwEvaluation(p)
+        ev.add_batch(synth.smooth_images(4, 80), synth.smooth_images(4, 81))
+        res = ev.finish()
+        assert res['num'] == 4
+        assert p._lib.aig_comm_destroy(p._h) == 0
+        bad = (ctypes.c_uint8 * 128)()
+        assert p._lib.aig_comm_init(p._h, bad, 1, 1) == -1              # rank out of range
+    finally:
+        p.close()

@@ -202,6 +202,45 @@ def test_auc_matches_sklearn(golden):
     assert abs(oracle.auc(t, v) - np.sum((t[1:] - t[:-1]) * (v[1:] + v[:-1]) / 2)) < 1e-15
 
 
+def test_auc_the_way_the_reference_pipeline_computes_it(golden):
+    """areaundercurve.py integrates the rates it parses back from the 'iou {:6f}' files (six decimals), not pos / num:
+    golden = those files written and parsed with the reference's own statements, then sklearn's auc.  The host-side
+    product function (aig.auc, plain C) and the oracle must both reproduce it; the unrounded AUC differs where the
+    rates are not six-decimal numbers (sevenths, thirds)."""
+    import acoustic_image_generation_b200 as aig
+    g = golden('auc_files')
+    for name in ('acivw11', 'flickr11', 'sevenths', 'thirds'):
+        pos, num = g[name + '_pos'], int(g[name + '_num'])
+        want = float(g[name + '_auc_from_files'])
+        rates = oracle.success_rates(pos, num)
+        assert abs(oracle.auc(oracle.REFERENCE_THRESHOLDS, oracle.rates_as_written(rates)) - want) <= 1e-12
+        assert np.array_equal(aig.rates_as_written(rates), oracle.rates_as_written(rates))
+        got = aig.auc(oracle.REFERENCE_THRESHOLDS, aig.rates_as_written(aig.success_rates(pos, num)))
+        assert abs(got - want) <= 1e-12
+        assert 'area {:6f}'.format(got) == str(g[name + '_area_text'])
+    exact = oracle.auc(oracle.REFERENCE_THRESHOLDS, oracle.success_rates(g['sevenths_pos'], 7))
+    assert abs(exact - float(g['sevenths_auc_from_files'])) > 1e-8          # the rounding is visible
+
+
+def test_consensus_iou_ratio_is_float64(golden):
+    """ADVICE (round 1) suspected the reference divides two float32 sums.  It does not: unionbig = union + (mtot - box)
+    is float64 because box is int64 (showimages_bb.py:312-316), so iou_score = float32 / float64 -> float64, and a frame
+    with I / U exactly 1/10 is NOT counted at threshold 0.1 (0.1 > 0.1 is false; in float32 it would be).  Golden =
+    the reference's statements replayed on crafted masks (oracle/make_golden.py: replay_flickr_mask)."""
+    g = golden('ciou_ratio')
+    assert str(g['ratio_dtype']) == 'float64'
+    assert g['iou'][0] == 0.1 and g['iou'][1] == 0.3
+    assert not g['counted'][0][1] and not g['counted'][1][3]
+    scores = []
+    for f in range(3):
+        gt = oracle.boxes_to_consensus(g['xmin'][f], g['xmax'][f], g['ymin'][f], g['ymax'][f], 36, 48)
+        i2, u2, score = oracle.consensus_iou(gt, oracle.resize_mask(g['masks'][f], 36, 48))
+        assert i2 == 2 * g['inter'][f] and u2 == 2 * g['union'][f] and score == g['iou'][f]
+        scores.append(score)
+    pos, num = oracle.success_counts(scores, oracle.REFERENCE_THRESHOLDS)
+    assert np.array_equal(pos, g['pos11']) and num == 3
+
+
 def test_success_counts_nan_and_strictness():
     pos, num = oracle.success_counts([np.nan, 0.5, 1.0, 0.0], [0.0, 0.5, 1.0])
     assert pos.tolist() == [2, 1, 0] and num == 4
