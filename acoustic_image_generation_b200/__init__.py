@@ -9,7 +9,7 @@ fails loudly if the library or a B200 is missing (there is no CPU fallback).
 """
 from . import synth, tables  # noqa: F401
 from .api import (AcousticPath, AigError, REFERENCE_THRESHOLDS, _build_spectrograms_function,  # noqa: F401
-                  _map_func_acoustic_images, _map_func_mfcc, _normalize_acoustic_images_rescaled, _normalize_mfcc,
+                  _map_func_acoustic_images, _map_func_audio_samples_build_spectrogram, _map_func_mfcc, _normalize_acoustic_images_rescaled, _normalize_mfcc,
                   auc, butter_lowpass_filter, createfilters, default_path, find_logen,
                   get_feats, rates_as_written, success_rates)
 from .metrics_io import read_accuracy_file, write_accuracy_file, write_area_file  # noqa: F401

@@ -162,9 +162,11 @@ class AcousticPath:
             raise ValueError('tensor is on %s but this AcousticPath runs on cuda:%d' % (arg.torch_device, self.device))
         return arg
 
-    def _empty(self, shape, dtype, like):
-        """Output buffer on the side the input lives on."""
-        if like.torch_device is not None or like.on_device:
+    def _empty(self, shape, dtype, like, device_out=False):
+        """Output buffer on the side the input lives on; ``device_out`` forces a CUDA tensor for a host input (the library
+        then uploads the input itself - through its pinned staging ring when the array is pageable - and the result
+        never returns to the host)."""
+        if device_out or like.torch_device is not None or like.on_device:
             torch = _torch()
             dev = like.torch_device if like.torch_device is not None else torch.device('cuda', self.device)
             return torch.empty(shape, dtype=_TORCH_DTYPES[np.dtype(dtype)], device=dev)
@@ -277,17 +279,17 @@ class AcousticPath:
                                                  self._a(res, np.float32, True).ptr))
         return res
 
-    def build_spectrograms(self, audio):
+    def build_spectrograms(self, audio, device_out=False):
         """_build_spectrograms_function (outdoor_data_mfcc.py:796-824): [n, 1024] audio -> float32 [n, 12] MFCC,
         spectrum and MFCC kernels chained on the device."""
         a, is_int = self._audio_arg(audio)
         n = self._frames(a.shape, 1024)
         win = tables.tukey_window()
-        res = self._empty((n, self.mfcc_num), np.float32, a)
+        res = self._empty((n, self.mfcc_num), np.float32, a, device_out)
         self._check(self._lib.aig_audio_mfcc(self._h, a.ptr, is_int, n, win.ctypes.data, self._a(res, np.float32, True).ptr))
         return res
 
-    def butter_lowpass_filter(self, data, cutoff=125, order=10, sample_rate=12288):
+    def butter_lowpass_filter(self, data, cutoff=125, order=10, sample_rate=12288, device_out=False):
         """butter_lowpass_filter (outdoor_data_mfcc.py:571-575): zero-phase order-10 Butterworth low-pass along rows,
         float32 out."""
         a, is_int = self._audio_arg(data)
@@ -296,7 +298,7 @@ class AcousticPath:
         length = a.shape[-1]
         n = int(np.prod(a.shape)) // length
         b, acoef, zi = tables.butter_lowpass(sample_rate, cutoff, order)
-        res = self._empty(a.shape, np.float32, a)
+        res = self._empty(a.shape, np.float32, a, device_out)
         self._check(self._lib.aig_filtfilt(self._h, a.ptr, is_int, n, int(length), b.ctypes.data, acoef.ctypes.data,
                                            zi.ctypes.data, len(b), self._a(res, np.float32, True).ptr))
         return res
@@ -338,11 +340,11 @@ class AcousticPath:
         return out
 
     # -- stage 2 ------------------------------------------------------------------------------
-    def normalize_images(self, images):
+    def normalize_images(self, images, device_out=False):
         """Per-frame (x - min) / max(x - min) in float32 over [N, 36, 48, 12] (outdoor_data_mfcc.py:672-679)."""
         a = self._a(images, np.float32)
         n = self._frames(a.shape, FRAME_PIXELS * MFCC_NUM)
-        res = self._empty(a.shape, np.float32, a)
+        res = self._empty(a.shape, np.float32, a, device_out)
         self._check(self._lib.aig_normalize_images(self._h, a.ptr, n, self._a(res, np.float32, True).ptr))
         return res
 
@@ -668,6 +670,14 @@ def _build_spectrograms_function(audio_data):
 def butter_lowpass_filter(data, cutoff=125, order=10, sample_rate=12288):
     """Drop-in for ActionsDataLoader.butter_lowpass_filter (outdoor_data_mfcc.py:571-575)."""
     return default_path().butter_lowpass_filter(data, cutoff, order, sample_rate)
+
+
+def _map_func_audio_samples_build_spectrogram(audio_images, audio_wav, processed_images, action, location, filtered_audio_wav):
+    """Drop-in for ActionsDataLoader._map_func_audio_samples_build_spectrogram (outdoor_data_mfcc.py:783-794): elements
+    1 and 5 (the raw and the low-passed waveform, [T, 1024]) become their [T, 12] MFCCs."""
+    path = default_path()
+    return (audio_images, path.build_spectrograms(audio_wav), processed_images, action, location,
+            path.build_spectrograms(filtered_audio_wav))
 
 
 def _normalize_mfcc(mfcc):

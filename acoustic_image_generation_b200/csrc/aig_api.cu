@@ -142,7 +142,8 @@ struct aig_handle {
     int heatmap_exact = 0;              // 1: float64 replica of the oracle's bilinear; 0: float32 fast path
     bool heat_attr_set = false;
     bool heat_exact_attr_set = false;
-    bool heat_stream_attr_set = false;
+    bool heat_stream_attr_set[8] = {false, false, false, false, false, false, false, false};
+    bool stage2_attr_set[2] = {false, false};
     int heat_bulk_store = 1;            // 0: round-1 per-thread-store kernel for every shape (comparison runs)
     int small_batch_frames = 0;         // below this many frames a frame is split over a cluster of 8 CTAs; 0: SM count
     unsigned int debug_jitter = 0;      // non-zero: seed of the jittered build of the fused kernel (race stress tests)
@@ -462,6 +463,12 @@ int64_t small_batch_limit(const aig_handle* h) { return h->small_batch_frames > 
 template <int GROUPS>
 int launch_stage2(aig_handle* h, cudaStream_t stream, const Stage2Args& args, int ctas_per_sm = 8) {
     if (args.n_frames == 0) return AIG_OK;
+    if (!h->stage2_attr_set[GROUPS - 1]) {
+        // 8 CTAs of 20 KiB (4 of 45 KiB) per SM only fit with the shared-memory carveout at its maximum
+        cudaFuncSetAttribute(stage2_kernel<GROUPS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaGetLastError();
+        h->stage2_attr_set[GROUPS - 1] = true;
+    }
     LaunchScope scope(h, stream, kKindEnergy);
     if (args.n_frames < small_batch_limit(h)) {
         const int64_t clusters = std::min<int64_t>(args.n_frames, 4 * h->sm_count);
@@ -500,28 +507,30 @@ bool heat_stream_ok(const aig_handle* h, int out_h, int out_w, const float* d_he
            (reinterpret_cast<uintptr_t>(d_heat) & 15u) == 0 && heat_stream_layout(out_h, out_w, fused).total <= 100 * 1024;
 }
 
-template <bool FUSED>
-int launch_heat_stream(aig_handle* h, const HeatStreamArgs& args) {
-    if (!h->heat_stream_attr_set) {
-        AIG_CK(cudaFuncSetAttribute(heat_stream_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        AIG_CK(cudaFuncSetAttribute(heat_stream_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        AIG_CK(cudaFuncSetAttribute(heat_stream_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        AIG_CK(cudaFuncSetAttribute(heat_stream_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        cudaFuncSetAttribute(heat_stream_kernel<false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(heat_stream_kernel<false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(heat_stream_kernel<true, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(heat_stream_kernel<true, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        h->heat_stream_attr_set = true;
+template <bool FUSED, int VEC, int W, int H>
+int launch_heat_stream_variant(aig_handle* h, const HeatStreamArgs& args, int slot) {
+    auto kernel = heat_stream_kernel<FUSED, VEC, W, H>;
+    if (!h->heat_stream_attr_set[slot]) {
+        AIG_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        h->heat_stream_attr_set[slot] = true;
     }
     const size_t smem = heat_stream_layout(args.out_h, args.out_w, FUSED).total;
     const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(2, (226 * 1024) / (smem + 4 * 1024))));
     const int grid = frames_grid(h, args.n_frames, per_sm);
     LaunchScope scope(h, h->stream, FUSED ? kKindEnergy : kKindOther);
-    if (args.out_w % 4 == 0)
-        heat_stream_kernel<FUSED, 4><<<grid, kStreamThreads, smem, h->stream>>>(args);
-    else
-        heat_stream_kernel<FUSED, 2><<<grid, kStreamThreads, smem, h->stream>>>(args);
+    kernel<<<grid, kStreamThreads, smem, h->stream>>>(args);
     return scope.done("heat_stream_kernel");
+}
+
+// The reference's two output sizes run builds with the size as a compile-time constant; anything else the generic one.
+template <bool FUSED>
+int launch_heat_stream(aig_handle* h, const HeatStreamArgs& args) {
+    const int base = FUSED ? 4 : 0;
+    if (args.out_h == 224 && args.out_w == 298) return launch_heat_stream_variant<FUSED, 2, 298, 224>(h, args, base + 0);
+    if (args.out_h == 224 && args.out_w == 224) return launch_heat_stream_variant<FUSED, 4, 224, 224>(h, args, base + 1);
+    if (args.out_w % 4 == 0) return launch_heat_stream_variant<FUSED, 4, 0, 0>(h, args, base + 2);
+    return launch_heat_stream_variant<FUSED, 2, 0, 0>(h, args, base + 3);
 }
 
 int launch_heatmap(aig_handle* h, const double* d_energy, int64_t n_frames, int out_h, int out_w, float* d_heat) {

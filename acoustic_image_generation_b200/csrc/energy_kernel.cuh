@@ -86,6 +86,24 @@ __device__ __forceinline__ double exp_table64(double x, const double* __restrict
     return __hiloint2double(__double2hiint(y) + ((k >> 6) << 20), __double2loint(y));   // * 2^(k >> 6)
 }
 
+// The same without the range bookkeeping: the pair kernels bound every exponent once per pixel instead
+// (|mel_j| <= sum_m |z_m| because |cos| <= 1; half_pixel sends the pixel to the plain path when that sum exceeds 700).
+__device__ __forceinline__ double exp_table64_inrange(double x, const double* __restrict__ table) {
+    const double t = __fma_rn(x, c_exp_k[0], c_exp_k[1]);
+    const int k = __double2loint(t);
+    const double kd = __dadd_rn(t, -c_exp_k[1]);
+    double r = __fma_rn(kd, c_exp_k[2], x);
+    r = __fma_rn(kd, c_exp_k[3], r);
+    double p = __fma_rn(r, c_exp_k[4], c_exp_k[5]);
+    p = __fma_rn(p, r, c_exp_k[6]);
+    p = __fma_rn(p, r, c_exp_k[7]);
+    p = __fma_rn(p, r, c_exp_k[8]);
+    p = __fma_rn(__dmul_rn(r, r), p, r);
+    const double tj = table[k & 63];
+    const double y = __fma_rn(tj, p, tj);
+    return __hiloint2double(__double2hiint(y) + ((k >> 6) << 20), __double2loint(y));
+}
+
 // The plain form of one pixel (IEEE divisions, exp(), straight 12-term dot products), kept out of line: it serves the
 // pixels the fast path cannot (non-finite inputs, |mel| > 700) and is what the fast path is checked against.
 // `raw` holds the pixel's 12 input values, already in registers: the image may alias `scaled_dst` (find_logen scales its
@@ -127,17 +145,22 @@ __device__ __noinline__ double pixel_energy_plain(const float (&raw)[kMfccNum], 
 __device__ __forceinline__ double pixel_energy(float (&x)[kMfccNum], bool normalize, const FrameNorm& norm,
                                                const double* __restrict__ exp_table, unsigned int& rare) {
     double z[kMfccNum];
-    rare = 0;
+    float sum_abs = 0.f;                // NaN / Inf in, NaN / Inf out
 #pragma unroll
     for (int m = 0; m < kMfccNum; ++m) {
         float v = x[m];
         if (normalize) v = norm.apply(v);                                     // float32, as TF
-        rare |= (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u;            // NaN / Inf: plain path
         v = __double2float_rn(div_by_lifter(static_cast<double>(v), m));
         v = __double2float_rn(__dmul_rn(static_cast<double>(v), c_mfnorm));
         x[m] = v;
+        sum_abs += fabsf(v);
         z[m] = static_cast<double>(v);
     }
+    // Every |mel_j| <= sum_m |z_m| (|cos| <= 1): at most 700 keeps all 24 table exponentials in range; anything else -
+    // huge values, Inf, NaN (the comparison is false for NaN) - takes the plain path.  One float32 test per pixel
+    // instead of range bookkeeping in each of the 24 exponentials; the pair kernels below use the same criterion, so
+    // every kernel sends exactly the same pixels down the plain path.
+    rare = !(sum_abs <= 700.f);
     double r[8], third[8];
 #pragma unroll
     for (int j = 0; j < 12; ++j) {
@@ -147,8 +170,8 @@ __device__ __forceinline__ double pixel_energy(float (&x)[kMfccNum], bool normal
             b = fma(z[m], c_dct[j * kMfccNum + m], b);                        // m + 1 odd: antisymmetric in j <-> 23 - j
             a = fma(z[m + 1], c_dct[j * kMfccNum + m + 1], a);                // m + 1 even: symmetric
         }
-        const double e_lo = exp_table64(__dadd_rn(a, b), exp_table, rare);   // band j
-        const double e_hi = exp_table64(__dadd_rn(a, -b), exp_table, rare);  // band 23 - j
+        const double e_lo = exp_table64_inrange(__dadd_rn(a, b), exp_table);   // band j
+        const double e_hi = exp_table64_inrange(__dadd_rn(a, -b), exp_table);  // band 23 - j
         if (j < 8) {
             r[j] = e_lo;                      // first term of r[j]
             third[7 - j] = e_hi;              // band 23 - j = 16 + (7 - j): third term of r[7 - j]
@@ -259,14 +282,28 @@ __device__ __forceinline__ double frame_mean(const double* s_map, double (*s_par
 //     group g = pairs {g, 7 - g, 8 + g}  ->  bands {g, 23-g, 7-g, 16+g, 8+g, 15-g}  =  all terms of r[g] and r[7-g]
 // (r[k] = (e[k] + e[k+8]) + e[k+16] is NumPy's strided partial sum for n = 24), so half 0 (groups 0, 1) produces
 // r0, r1, r6, r7 and half 1 (groups 2, 3) r2..r5 without exchanging a single exponential; only the 6 + 6 scaled float32
-// channel values, two float64 partial sums (r2 + r3, r4 + r5) and a flag cross the pair, through shared memory around two
+// channel values and two float64 partial sums (r2 + r3, r4 + r5) cross the pair, through shared memory around two
 // 64-thread named barriers.  Every operation keeps the order of pixel_energy(), so the result is bit-identical to the
 // one-thread form the fused kernel's energy warps run.  Which half a warp is decides its constants at compile time
 // (template parameter, warp-uniform branch): every DCT coefficient stays a constant-bank operand.
 
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
+// Named barriers with IMMEDIATE ids.  With the id in a register ptxas must assume all 16 hardware barriers are in use
+// ("used 16 barriers"), and an SM only has 64: four CTAs per SM however few registers and shared memory they need - the
+// first build of these kernels ran at half its intended occupancy for exactly that reason.  NamedBar<1, MAX_ID, T>::sync(id)
+// is an if-chain over the ids 1 .. MAX_ID a kernel really uses, each branch a `bar.sync <imm>, <imm>`.
+template <int ID, int MAX_ID, int THREADS>
+struct NamedBar {
+    static __device__ __forceinline__ void sync(int id) {
+        if (id == ID) asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(THREADS) : "memory");
+        else NamedBar<ID + 1, MAX_ID, THREADS>::sync(id);
+    }
+};
+template <int MAX_ID, int THREADS>
+struct NamedBar<MAX_ID, MAX_ID, THREADS> {
+    static __device__ __forceinline__ void sync(int) {
+        asm volatile("bar.sync %0, %1;" ::"n"(MAX_ID), "n"(THREADS) : "memory");
+    }
+};
 
 // The per-frame min-max normalisation with the reciprocal hoisted out of the per-value division.  With r = RN(1 / range),
 // q0 = RN(d * r), rem = d - q0 * range (exact in one FMA), q = RN(q0 + rem * r) is the correctly rounded quotient
@@ -282,9 +319,10 @@ struct FrameNormFast {
     }
     __device__ __forceinline__ float apply(float x) const {
         const float d = __fsub_rn(x, lo);
-        const unsigned int e = (__float_as_uint(d) >> 23) & 0xffu;
-        if (fast && (e - 67u) <= 120u) {
-            const float q0 = __fmul_rn(d, r);
+        const float q0 = __fmul_rn(d, r);
+        // fast: range (hence r) within 2^+-60, so q0 in [2^-40, 2^40] means d within 2^+-100: nothing under- or overflows.
+        // Zero, tiny, huge and non-finite differences (comparison false for NaN) take IEEE division.
+        if (fast && q0 >= 9.094947e-13f && q0 <= 1.0995116e12f) {
             const float rem = __fmaf_rn(-q0, range, d);
             return __fmaf_rn(rem, r, q0);
         }
@@ -313,8 +351,8 @@ __global__ void selftest_norm_kernel(unsigned long long* out) {
         else d = __uint_as_float(g);                                                       // any bit pattern
         const FrameNormFast norm(0.f, range);
         const float a = norm.apply(d), b = __fdiv_rn(__fsub_rn(d, 0.f), range);
-        const unsigned int e = (__float_as_uint(d) >> 23) & 0xffu;
-        fast_taken += norm.fast && (e - 67u) <= 120u;
+        const float q0 = __fmul_rn(d, norm.r);
+        fast_taken += norm.fast && q0 >= 9.094947e-13f && q0 <= 1.0995116e12f;
         bad += !((__float_as_uint(a) == __float_as_uint(b)) || (a != a && b != b));
         ++count;
     }
@@ -344,27 +382,25 @@ __device__ __forceinline__ void load_energy_tables(EnergyTables& t, int tid, int
 
 // One (j, 23 - j) basis pair: the two exponentials exp(A + B), exp(A - B) of pixel_energy(), same operation order.
 template <int J>
-__device__ __forceinline__ void band_pair(const double (&z)[kMfccNum], const EnergyTables& tab, unsigned int& rare,
-                                          double& e_lo, double& e_hi) {
+__device__ __forceinline__ void band_pair(const double (&z)[kMfccNum], const EnergyTables& tab, double& e_lo, double& e_hi) {
     double a = 0.0, b = 0.0;
 #pragma unroll
     for (int m = 0; m < kMfccNum; m += 2) {
         b = fma(z[m], tab.dct[J * kMfccNum + m], b);
         a = fma(z[m + 1], tab.dct[J * kMfccNum + m + 1], a);
     }
-    e_lo = exp_table64(__dadd_rn(a, b), tab.exp2, rare);       // band J
-    e_hi = exp_table64(__dadd_rn(a, -b), tab.exp2, rare);      // band 23 - J
+    e_lo = exp_table64_inrange(__dadd_rn(a, b), tab.exp2);       // band J
+    e_hi = exp_table64_inrange(__dadd_rn(a, -b), tab.exp2);      // band 23 - J
 }
 
 // Group G: r[G] = (e[G] + e[G+8]) + e[G+16] and r[7-G] = (e[7-G] + e[15-G]) + e[23-G].
 template <int G>
-__device__ __forceinline__ void band_group(const double (&z)[kMfccNum], const EnergyTables& tab, unsigned int& rare,
-                                           double& r_g, double& r_7g) {
+__device__ __forceinline__ void band_group(const double (&z)[kMfccNum], const EnergyTables& tab, double& r_g, double& r_7g) {
     double lo1, hi1, lo2, hi2, lo3, hi3;
-    band_pair<G>(z, tab, rare, lo1, hi1);          // bands G,     23 - G
-    band_pair<8 + G>(z, tab, rare, lo3, hi3);      // bands 8 + G, 15 - G
+    band_pair<G>(z, tab, lo1, hi1);          // bands G,     23 - G
+    band_pair<8 + G>(z, tab, lo3, hi3);      // bands 8 + G, 15 - G
     r_g = __dadd_rn(lo1, lo3);
-    band_pair<7 - G>(z, tab, rare, lo2, hi2);      // bands 7 - G, 16 + G
+    band_pair<7 - G>(z, tab, lo2, hi2);      // bands 7 - G, 16 + G
     r_g = __dadd_rn(r_g, hi2);
     r_7g = __dadd_rn(__dadd_rn(lo2, hi3), hi1);
 }
@@ -372,23 +408,21 @@ __device__ __forceinline__ void band_group(const double (&z)[kMfccNum], const En
 struct PairExchange {                  // one per warp pair, in shared memory
     float x[2][6][32];                 // each half's six scaled channel values
     double sum[2][32];                 // half 1's r2 + r3 and r4 + r5
-    unsigned int flag[2][32];          // each half's "needs the plain path"
 };
 
 // This half's share of one pixel.  raw: channels 6 * HALF .. 6 * HALF + 5.  Returns the energy in half 0 (0 in half 1);
 // `scaled` receives this half's float32-stored scaled values (find_logen's side effect), `rare` the pair's combined flag.
-template <int HALF>
+template <int HALF, int MAX_BAR>
 __device__ __forceinline__ double half_pixel(const float (&raw)[6], bool normalize, const FrameNormFast& norm,
                                              const EnergyTables& tab, PairExchange& ex, int lane, int bar_id,
                                              float (&scaled)[6], unsigned int& rare_out) {
-    unsigned int rare = 0;
     double z[kMfccNum];
+    float own_abs = 0.f;                // sum of |scaled value|: NaN / Inf in, NaN / Inf out
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         const int m = 6 * HALF + i;
         float v = raw[i];
         if (normalize) v = norm.apply(v);                                     // float32, as TF
-        rare |= (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u;            // NaN / Inf: plain path
         {                                                                     // div_by_lifter with the shared-memory constants
             const double d = static_cast<double>(v), r = tab.inv_lifter[m];
             const double q0 = __dmul_rn(d, r);
@@ -397,32 +431,41 @@ __device__ __forceinline__ double half_pixel(const float (&raw)[6], bool normali
         v = __double2float_rn(__dmul_rn(static_cast<double>(v), tab.mfnorm));
         scaled[i] = v;
         ex.x[HALF][i][lane] = v;
+        own_abs += fabsf(v);
         z[m] = static_cast<double>(v);
     }
-    named_bar_sync(bar_id, 64);
+    NamedBar<1, MAX_BAR, 64>::sync(bar_id);
+    float all_abs = own_abs;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) z[6 * (1 - HALF) + i] = static_cast<double>(ex.x[1 - HALF][i][lane]);
+    for (int i = 0; i < 6; ++i) {
+        const float v = ex.x[1 - HALF][i][lane];
+        all_abs += fabsf(v);
+        z[6 * (1 - HALF) + i] = static_cast<double>(v);
+    }
+    // Every |mel_j| <= sum_m |z_m| (|cos| <= 1): at most 700 keeps all 24 table exponentials in range; anything else -
+    // huge values, Inf, NaN (the comparison is false for NaN) - goes to the plain path.  Both halves see the same 12
+    // values, so the flag needs no exchange.
+    const unsigned int rare = !(all_abs <= 700.f);
     double ra, rb, rc, rd;
-    band_group<2 * HALF>(z, tab, rare, ra, rb);          // half 0: r0, r7     half 1: r2, r5
-    band_group<2 * HALF + 1>(z, tab, rare, rc, rd);      // half 0: r1, r6     half 1: r3, r4
+    band_group<2 * HALF>(z, tab, ra, rb);          // half 0: r0, r7     half 1: r2, r5
+    band_group<2 * HALF + 1>(z, tab, rc, rd);      // half 0: r1, r6     half 1: r3, r4
     const double s_lo = __dadd_rn(ra, rc);                     // half 0: r0 + r1    half 1: r2 + r3
     const double s_hi = __dadd_rn(rd, rb);                     // half 0: r6 + r7    half 1: r4 + r5
-    ex.flag[HALF][lane] = rare;
     if (HALF == 1) { ex.sum[0][lane] = s_lo; ex.sum[1][lane] = s_hi; }
-    named_bar_sync(bar_id, 64);
-    rare_out = rare | ex.flag[1 - HALF][lane];
+    NamedBar<1, MAX_BAR, 64>::sync(bar_id);
+    rare_out = rare;
     if (HALF == 1) return 0.0;
     const double total = __dadd_rn(__dadd_rn(s_lo, ex.sum[0][lane]), __dadd_rn(ex.sum[1][lane], s_hi));
     return __ddiv_rn(1.0, total);
 }
 
 // Pixels [p_begin, p_end) of one frame by a group of PAIRS warp pairs (thread index gt within the group; named barriers
-// bar_base .. bar_base + PAIRS - 1 belong to the pairs).  img / scaled / energy point at the frame; img may alias scaled
+// bar_base .. bar_base + PAIRS - 1 <= MAX_BAR belong to the pairs).  img / scaled / energy point at the frame; img may alias scaled
 // (find_logen's in-place scaling), so neither is read through a read-only path and a pixel's raw values are loaded before
 // anything of that pixel is stored.  Leaves map[p - p_begin] = energy.  Pixels the fast path cannot serve (non-finite
 // input, |mel| > 700) only get their bit set in rare_bits (zero on entry); the caller runs frame_energy_fixup after a
 // group barrier - the out-of-line plain path stays out of this loop and so do the register spills around its call.
-template <int PAIRS>
+template <int PAIRS, int MAX_BAR>
 __device__ __forceinline__ void frame_energy_range(const float* img, int p_begin, int p_end, bool normalize,
                                                    const FrameNormFast& norm, float* scaled, double* energy, double* map,
                                                    PairExchange* ex, unsigned int* rare_bits, const EnergyTables& tab, int gt,
@@ -448,8 +491,8 @@ __device__ __forceinline__ void frame_energy_range(const float* img, int p_begin
         float sc[6];
         unsigned int rare;
         double en;
-        if (half == 0) en = half_pixel<0>(raw, normalize, norm, tab, ex[pair], lane, bar_id, sc, rare);
-        else en = half_pixel<1>(raw, normalize, norm, tab, ex[pair], lane, bar_id, sc, rare);
+        if (half == 0) en = half_pixel<0, MAX_BAR>(raw, normalize, norm, tab, ex[pair], lane, bar_id, sc, rare);
+        else en = half_pixel<1, MAX_BAR>(raw, normalize, norm, tab, ex[pair], lane, bar_id, sc, rare);
         if (rare) {
             // neither half stores anything of this pixel: frame_energy_fixup redoes it from its raw values
             if (half == 0 && active) atomicOr(&rare_bits[(p - p_begin) >> 5], 1u << ((p - p_begin) & 31));
@@ -566,8 +609,10 @@ stage2_kernel(const __grid_constant__ Stage2Args a) {
     __shared__ double s_iou;
     const int tid = threadIdx.x;
     const int group = tid / kEnergyThreads, gt = tid % kEnergyThreads;
+    // barriers: GROUPS == 1: 1, 2 = the pairs, 0 = the group; GROUPS == 2: 1, 2 | 3 and 4, 5 | 6 = pairs | group of each image
+    constexpr int kMaxBar = GROUPS == 1 ? kEnergyPairs : GROUPS * (kEnergyPairs + 1);
     const int bar_base = 1 + group * (kEnergyPairs + 1), bar_group = bar_base + kEnergyPairs;
-    auto group_sync = [&] { if (GROUPS == 1) __syncthreads(); else named_bar_sync(bar_group, kEnergyThreads); };
+    auto group_sync = [&] { if (GROUPS == 1) __syncthreads(); else NamedBar<1, kMaxBar, kEnergyThreads>::sync(bar_group); };
     load_energy_tables(s_tab, tid, GROUPS * kEnergyThreads);
     if (gt < kFramePixels / 32) sh[group].rare_bits[gt] = 0u;
     if (GROUPS == 2) {
@@ -584,7 +629,7 @@ stage2_kernel(const __grid_constant__ Stage2Args a) {
         const FrameNormFast norm(lo, __fsub_rn(hi, lo));        // max(x - min) == fl(max - min): rounding is monotonic
         float* scaled = a.scaled[group] ? a.scaled[group] + frame * kFrameValues : nullptr;
         double* energy = a.energy[group] ? a.energy[group] + frame * kFramePixels : nullptr;
-        frame_energy_range<kEnergyPairs>(img, 0, kFramePixels, a.normalize_first != 0, norm, scaled, energy, g.map, g.ex,
+        frame_energy_range<kEnergyPairs, kMaxBar>(img, 0, kFramePixels, a.normalize_first != 0, norm, scaled, energy, g.map, g.ex,
                                          g.rare_bits, s_tab, gt, bar_base);
         group_sync();
         if (frame_energy_fixup(img, 0, kFramePixels, a.normalize_first != 0, norm, scaled, energy, g.map, g.rare_bits, gt,
@@ -673,8 +718,9 @@ stage2_cluster_kernel(const __grid_constant__ Stage2Args a) {
     const int tid = threadIdx.x;
     const int group = tid / kClusterGroupThreads, gt = tid % kClusterGroupThreads;
     const int lane = tid & 31;
+    constexpr int kMaxBar = GROUPS == 1 ? kClusterPairs : GROUPS * (kClusterPairs + 1);
     const int bar_base = 1 + group * (kClusterPairs + 1), bar_group = bar_base + kClusterPairs;
-    auto group_sync = [&] { if (GROUPS == 1) __syncthreads(); else named_bar_sync(bar_group, kClusterGroupThreads); };
+    auto group_sync = [&] { if (GROUPS == 1) __syncthreads(); else NamedBar<1, kMaxBar, kClusterGroupThreads>::sync(bar_group); };
     const unsigned int rank = cluster.block_rank();
     const long long n_clusters = gridDim.x / kClusterSize;
     load_energy_tables(s_tab, tid, GROUPS * kClusterGroupThreads);
@@ -709,7 +755,7 @@ stage2_cluster_kernel(const __grid_constant__ Stage2Args a) {
         const FrameNormFast norm(lo, __fsub_rn(hi, lo));
         float* scaled = a.scaled[group] ? a.scaled[group] + frame * kFrameValues : nullptr;
         double* energy = a.energy[group] ? a.energy[group] + frame * kFramePixels : nullptr;
-        frame_energy_range<kClusterPairs>(img, p0, p0 + kSlicePixels, a.normalize_first != 0, norm, scaled, energy, g.map,
+        frame_energy_range<kClusterPairs, kMaxBar>(img, p0, p0 + kSlicePixels, a.normalize_first != 0, norm, scaled, energy, g.map,
                                           g.ex, g.rare_bits, s_tab, gt, bar_base);
         group_sync();
         if (frame_energy_fixup(img, p0, p0 + kSlicePixels, a.normalize_first != 0, norm, scaled, energy, g.map, g.rare_bits,

@@ -14,6 +14,8 @@
 // resize_mask_kernel   cv2.resize(mask) > 0.5 in exact integers (showimages_bb.py:303-304).
 #pragma once
 
+#include <type_traits>
+
 #include "aig_common.cuh"
 #include "energy_kernel.cuh"
 
@@ -348,14 +350,34 @@ struct HeatStreamArgs {
     float* heat;
 };
 
-template <bool FUSED, int VEC>
+// (d = b - a) once per column pair, then per output row v = d * wy + a, (v - mn) * inv: the roundings of lerp_norm2.
+__device__ __forceinline__ unsigned long long diff2(unsigned long long pa, unsigned long long pb) {
+    unsigned long long d;
+    const unsigned long long neg1 = pack2(make_float2(-1.f, -1.f));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pa), "l"(neg1), "l"(pb));
+    return d;
+}
+__device__ __forceinline__ unsigned long long norm2(unsigned long long pa, unsigned long long d, unsigned long long w2,
+                                                    unsigned long long nmn, unsigned long long i2) {
+    unsigned long long v, t, o;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(v) : "l"(d), "l"(w2), "l"(pa));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(v), "l"(nmn));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(o) : "l"(t), "l"(i2));
+    return o;
+}
+
+// W, H: the output size as template constants (0 = run-time size from the arguments).  The reference's two sizes,
+// 298 x 224 (showimages.py:147) and 224 x 224 (BASELINE configs[2]), are instantiated with constants: every column loop
+// then unrolls completely with immediate offsets - the run-time-size build spent half of its instructions on loop
+// bounds and address arithmetic (profiles/r02_ncu_stage2_kernels_a.csv).
+template <bool FUSED, int VEC, int W, int H>
 __global__ void __launch_bounds__(kStreamThreads, 2)
 heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ double s_red64[2][kStreamWarps];
     __shared__ float s_red32[2][kStreamWarps];
     __shared__ EnergyTables s_tab;
-    const int out_h = a.out_h, out_w = a.out_w;
+    const int out_h = H ? H : a.out_h, out_w = W ? W : a.out_w;
     const HeatStreamLayout lay = heat_stream_layout(out_h, out_w, FUSED);
     float* s_t = reinterpret_cast<float*>(s_raw);
     float* s_rows = reinterpret_cast<float*>(s_raw + lay.off_rows);
@@ -382,6 +404,20 @@ heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
         const bool edge = d == 0 || d == out_h - 1 || p0 != i0 || p1 != i1 || n0 != i0 || n1 != i1;
         s_y0[d] = i0 | (i1 << 16) | (edge ? 0x80000000 : 0); s_wy[d] = static_cast<float>(w);
     }
+    // column loops: x = (lane + 32 k) * V for k = 0 .. ; fully unrolled when the width is a template constant
+    auto columns = [&](auto vec_tag, auto body) {
+        constexpr int V = decltype(vec_tag)::value;
+        if constexpr (W != 0) {
+            constexpr int kIters = (W / V + 31) / 32;
+#pragma unroll
+            for (int k = 0; k < kIters; ++k) {
+                const int x = (lane + 32 * k) * V;
+                if (k + 1 < kIters || x < W) body(x);
+            }
+        } else {
+            for (int x = lane * V; x < out_w; x += 32 * V) body(x);
+        }
+    };
     constexpr int kPerThread = (kFramePixels + kStreamThreads - 1) / kStreamThreads;     // 7 (6.75)
     double e[kPerThread];
     auto fetch = [&](long long frame) {
@@ -411,7 +447,7 @@ heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
             double* energy = s.energy[0] ? s.energy[0] + frame * kFramePixels : nullptr;
             if (tid < kFramePixels / 32) eph.rare_bits[tid] = 0u;       // the staging area held heat-map rows a moment ago
             __syncthreads();
-            frame_energy_range<kStreamPairs>(img, 0, kFramePixels, s.normalize_first != 0, norm, nullptr, energy, eph.map,
+            frame_energy_range<kStreamPairs, kStreamPairs>(img, 0, kFramePixels, s.normalize_first != 0, norm, nullptr, energy, eph.map,
                                              eph.ex, eph.rare_bits, s_tab, tid, 1);
             __syncthreads();
             if (frame_energy_fixup(img, 0, kFramePixels, s.normalize_first != 0, norm, nullptr, energy, eph.map, eph.rare_bits,
@@ -449,16 +485,17 @@ heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
         }
         if (!FUSED) fetch(frame + gridDim.x);                     // next frame's energies arrive during the passes below
         __syncthreads();
-        // 3. horizontal pass: warps own source rows, lanes walk the output columns
-        for (int r = warp; r < kFrameH; r += kStreamWarps) {
-            const float* t = s_t + r * kFrameW;
-            float* row = s_rows + r * wp;
-            for (int x = lane; x < out_w; x += 32) {
-                const int xi = s_x0[x];
-                const float u = t[xi & 0xffff], v = t[xi >> 16];
-                row[x] = fmaf(v - u, s_wx[x], u);
+        // 3. horizontal pass: a column's taps are loaded once and applied to this warp's source rows (warp, warp + 8, ...)
+        columns(std::integral_constant<int, 1>{}, [&](int x) {
+            const int xi = s_x0[x];
+            const float wx = s_wx[x];
+            const int c0 = xi & 0xffff, c1 = xi >> 16;
+#pragma unroll
+            for (int r = warp; r < kFrameH; r += kStreamWarps) {
+                const float u = s_t[r * kFrameW + c0], v = s_t[r * kFrameW + c1];
+                s_rows[r * wp + x] = fmaf(v - u, wx, u);
             }
-        }
+        });
         __syncthreads();
         // 4. min / max of the up-sampled image
         float mn = CUDART_INF_F, mx = -CUDART_INF_F;
@@ -468,7 +505,7 @@ heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
             const float wy = s_wy[y];
             const float* r0 = s_rows + (yi & 0xffff) * wp;
             const float* r1 = s_rows + ((yi >> 16) & 0x7fff) * wp;
-            for (int x = lane * VEC; x < out_w; x += 32 * VEC) HeatVec<VEC>::lerp_minmax(r0, r1, x, wy, mn, mx);
+            columns(std::integral_constant<int, VEC>{}, [&](int x) { HeatVec<VEC>::lerp_minmax(r0, r1, x, wy, mn, mx); });
         }
         mn = warp_min(mn); mx = warp_max(mx);
         if (lane == 0) { s_red32[0][warp] = mn; s_red32[1][warp] = mx; }
@@ -478,6 +515,7 @@ heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
         for (int w = 1; w < kStreamWarps; ++w) { mn = fminf(mn, s_red32[0][w]); mx = fmaxf(mx, s_red32[1][w]); }
         // a constant frame gives 0/0 = NaN, like the reference's (x - min) / (max - min)
         const float inv = (span > 0.0 && mx > mn) ? 1.f / (mx - mn) : CUDART_NAN_F;
+        const unsigned long long nmn2 = pack2(make_float2(-mn, -mn)), inv2 = pack2(make_float2(inv, inv));
         float* dst = a.heat + frame * frame_values;
         // 5. output: row pairs through this warp's staging slot, one bulk copy each
         for (int q = warp; q < n_pairs; q += kStreamWarps, ++chunk_it) {
@@ -487,21 +525,48 @@ heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
                 __syncwarp();
             }
             float* stage = my_stage + buf * 2 * out_w;
-            const int rows = min(2, out_h - 2 * q);
-            for (int r = 0; r < rows; ++r) {
-                const int y = 2 * q + r;
-                const int yi = s_y0[y];
-                const float wy = s_wy[y];
-                const float* r0 = s_rows + (yi & 0xffff) * wp;
-                const float* r1 = s_rows + ((yi >> 16) & 0x7fff) * wp;
-                float* o = stage + r * out_w;
-                for (int x = lane * VEC; x < out_w; x += 32 * VEC) HeatVec<VEC>::norm_store(r0, r1, x, wy, mn, inv, o);
+            const int y0 = 2 * q;
+            const bool two = (H != 0 && H % 2 == 0) || y0 + 1 < out_h;
+            const int ya = s_y0[y0], yb = s_y0[two ? y0 + 1 : y0];
+            const float wa = s_wy[y0], wb = s_wy[two ? y0 + 1 : y0];
+            const unsigned long long wa2 = pack2(make_float2(wa, wa)), wb2 = pack2(make_float2(wb, wb));
+            const float* a0 = s_rows + (ya & 0xffff) * wp;
+            const float* a1 = s_rows + ((ya >> 16) & 0x7fff) * wp;
+            if (two && ((ya ^ yb) & 0x7fffffff) == 0) {
+                // both output rows interpolate between the same two source rows (five times out of six at 36 -> 224):
+                // one pair of loads and one difference serve both
+                columns(std::integral_constant<int, VEC>{}, [&](int x) {
+#pragma unroll
+                    for (int h = 0; h < VEC; h += 2) {
+                        const unsigned long long pa = *reinterpret_cast<const unsigned long long*>(a0 + x + h);
+                        const unsigned long long pb = *reinterpret_cast<const unsigned long long*>(a1 + x + h);
+                        const unsigned long long d = diff2(pa, pb);
+                        *reinterpret_cast<unsigned long long*>(stage + x + h) = norm2(pa, d, wa2, nmn2, inv2);
+                        *reinterpret_cast<unsigned long long*>(stage + out_w + x + h) = norm2(pa, d, wb2, nmn2, inv2);
+                    }
+                });
+            } else {
+                const float* b0 = s_rows + (yb & 0xffff) * wp;
+                const float* b1 = s_rows + ((yb >> 16) & 0x7fff) * wp;
+                columns(std::integral_constant<int, VEC>{}, [&](int x) {
+#pragma unroll
+                    for (int h = 0; h < VEC; h += 2) {
+                        const unsigned long long pa = *reinterpret_cast<const unsigned long long*>(a0 + x + h);
+                        const unsigned long long pb = *reinterpret_cast<const unsigned long long*>(a1 + x + h);
+                        *reinterpret_cast<unsigned long long*>(stage + x + h) = norm2(pa, diff2(pa, pb), wa2, nmn2, inv2);
+                        if (two) {
+                            const unsigned long long qa = *reinterpret_cast<const unsigned long long*>(b0 + x + h);
+                            const unsigned long long qb = *reinterpret_cast<const unsigned long long*>(b1 + x + h);
+                            *reinterpret_cast<unsigned long long*>(stage + out_w + x + h) = norm2(qa, diff2(qa, qb), wb2, nmn2, inv2);
+                        }
+                    }
+                });
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                bulk_store_s2g(dst + static_cast<long long>(2 * q) * out_w, my_stage_addr + buf * 2 * out_w * 4,
-                               static_cast<uint32_t>(rows * out_w * 4));
+                bulk_store_s2g(dst + static_cast<long long>(y0) * out_w, my_stage_addr + buf * 2 * out_w * 4,
+                               static_cast<uint32_t>((two ? 2 : 1) * out_w * 4));
                 bulk_commit();
             }
         }

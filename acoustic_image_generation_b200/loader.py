@@ -24,7 +24,10 @@ class AcousticBatches:
                                            per frame (_map_func_acoustic_images)
       'mfcc'      float32 [B, 12]          audio MFCC per frame's 1024 samples, min-max normalised per vector (_map_func_mfcc)
       'mfccmap'   float32 [B, 36, 48, 12]  the MFCC vector tiled over the image (only with ``tile=True``)
-      'filtered'  float32 [B, 1024]        low-passed waveform (only with ``low_pass=True``; butter_lowpass_filter)
+      'filtered'  float32 [B, 1024]        low-passed waveform (only with ``low_pass=True``; butter_lowpass_filter, :558-575)
+      'filtered_mfcc' float32 [B, 12]      MFCC of the low-passed waveform, normalised per vector (with ``low_pass=True``):
+                                           _map_func_audio_samples_build_spectrogram returns both MFCCs (:788-794) and
+                                           _map_func_mfcc normalises both (:692-693)
     plus NumPy int64 arrays 'classes' and 'location' [B].  The last batch may be short unless ``drop_last``.
     Records without audio samples yield no 'mfcc' / 'mfccmap' / 'filtered'.
     """
@@ -81,17 +84,20 @@ class AcousticBatches:
         return np.concatenate(out, 0) if len(out) > 1 else np.ascontiguousarray(out[0])
 
     def _emit(self, images, audio, classes, location, n):
-        torch = _torch()
-        dev = torch.device('cuda', self.path.device)
+        """Host arrays go to the device through libaig itself (``device_out=True``): ordinary (pageable) NumPy memory is
+        staged through the handle's pinned ring by its copy threads (host_staging.h, 4-5x the driver's pageable path) and
+        the kernel's result stays on the device - no torch ``.to(device)`` copy in between."""
+        path = self.path
         batch = {'classes': self._take(classes, n), 'location': self._take(location, n)}
-        img = torch.from_numpy(self._take(images, n)).to(dev, non_blocking=False)
-        batch['acoustic'] = self.path.normalize_images(img).reshape(n, FRAME_H, FRAME_W, MFCC_NUM)
+        batch['acoustic'] = path.normalize_images(self._take(images, n), device_out=True).reshape(n, FRAME_H, FRAME_W, MFCC_NUM)
         if audio:
-            wav = torch.from_numpy(self._take(audio, n)).to(dev)
-            mfcc = self.path.normalize_mfcc(self.path.build_spectrograms(wav))
+            wav = self._take(audio, n)
+            if self.low_pass:
+                filtered = path.butter_lowpass_filter(wav, device_out=True)           # float32 [n, 1024] on the device
+                batch['filtered'] = filtered
+                batch['filtered_mfcc'] = path.normalize_mfcc(path.build_spectrograms(filtered))
+            mfcc = path.normalize_mfcc(path.build_spectrograms(wav, device_out=True))
             batch['mfcc'] = mfcc
             if self.tile:
-                batch['mfccmap'] = self.path.tile_mfcc(mfcc)
-            if self.low_pass:
-                batch['filtered'] = self.path.butter_lowpass_filter(wav)
+                batch['mfccmap'] = path.tile_mfcc(mfcc)
         return batch

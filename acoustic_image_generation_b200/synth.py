@@ -19,7 +19,7 @@ import hashlib
 import numpy as np
 
 FRAME_H, FRAME_W, FFT_LEN, MFCC_NUM = 36, 48, 512, 12
-POWER_KINDS = ('chi2', 'lognormal', 'floor')
+POWER_KINDS = ('chi2', 'lognormal', 'floor')        # structured_power_frames() adds spatial structure to 'chi2'
 
 
 def power_frames(n, seed=0, kind='chi2'):
@@ -39,6 +39,38 @@ def power_frames(n, seed=0, kind='chi2'):
     if kind == 'floor':
         return np.float32(1e-6) * rng.random(shape, dtype=np.float32)
     raise ValueError('unknown kind %r (expected one of %s)' % (kind, POWER_KINDS))
+
+
+def structured_power_frames(n, seed=0, layout_seed=1000, shift=0.0, gain=1000.0):
+    """n multispectral frames with spatial structure: squared-normal noise (as ``power_frames('chi2')``) whose spectrum is
+    tilted, pixel by pixel, by a field of one to three Gaussian "sources" per frame - the sources boost a band of bins,
+    so the 12-channel MFCC image, and with it the energy map and its mean mask, show connected blobs like a real
+    acoustic image instead of salt and pepper.  (find_logen's map of a min-max-normalised MFCC image is flat to first
+    order - the cepstral basis annihilates constants - so the sources need a strong gain, default 1000 in their band,
+    to stand out of the noise; the background stays salt and pepper.)
+
+    The source layout of frame i comes from ``layout_seed`` alone; ``seed`` drives the noise and, scaled by ``shift``
+    (pixels, standard deviation), a per-frame displacement of the whole layout.  Two streams with the same
+    ``layout_seed`` therefore show the same sources, displaced: their mask IoU spreads over (0, 1) instead of being all
+    or nothing, which is what a "real vs reconstructed" comparison (iouenergythreshold.py:213-229) looks like."""
+    rng = np.random.default_rng(seed)
+    lay = np.random.default_rng(layout_seed)
+    x = rng.standard_normal((n, FRAME_H, FRAME_W, FFT_LEN), dtype=np.float32)
+    power = x * x
+    yy, xx = np.mgrid[0:FRAME_H, 0:FRAME_W].astype(np.float32)
+    bins = np.arange(FFT_LEN, dtype=np.float32)
+    for i in range(n):
+        count = int(lay.integers(1, 4))
+        cy, cx = lay.uniform(4, FRAME_H - 4, count), lay.uniform(4, FRAME_W - 4, count)
+        sig = lay.uniform(2.5, 7.0, count)
+        tone, width = lay.uniform(60.0, 420.0), lay.uniform(30.0, 90.0)
+        dy, dx = (rng.normal(0.0, 1.0, 2) * shift).astype(np.float32)
+        field = np.zeros((FRAME_H, FRAME_W), np.float32)
+        for k in range(count):
+            field += np.exp(-((yy - cy[k] - dy) ** 2 + (xx - cx[k] - dx) ** 2) / np.float32(2 * sig[k] * sig[k])).astype(np.float32)
+        band = np.exp(-((bins - np.float32(tone)) / np.float32(width)) ** 2).astype(np.float32)
+        power[i] *= np.float32(1.0) + np.float32(gain) * field[:, :, None] * band[None, None, :]
+    return power
 
 
 def sigmoid_images(n, seed=0):

@@ -842,8 +842,11 @@ def test_batches_beyond_the_per_launch_limit_are_split(path):
     before = path.launch_count
     path.set_option('launch_row_limit', 3000)
     try:
-        rows = path.mfcc_rows(power.reshape(-1, 512)[:7000])
-        assert path.launch_count - before == 3                      # 7000 rows in launches of 2816 (11 x 256)
+        import torch
+        dev_rows = path.mfcc_rows(torch.from_numpy(power.reshape(-1, 512)[:7000]).cuda())
+        assert path.launch_count - before == 3                      # 7000 resident rows in launches of 2816 (11 x 256)
+        assert np.array_equal(dev_rows.cpu().numpy(), ref_rows)
+        rows = path.mfcc_rows(power.reshape(-1, 512)[:7000])        # host rows: also cut into H2D chunks
         img = path.mfcc_image(power, flip=True)
         path.set_option('launch_row_limit', 2 * 1728)
         chain = path.mfcc_energy(power, flip=True, normalize_first=True)

@@ -65,12 +65,33 @@ def main():
     del power
     ms = timed(lambda: path.energy(mfcc, normalize_first=True))
     report('energy+mask alone (aig_energy)', n, 'frames', ms, n * (82944 + 13824 + 1728), 'FP64-bound')
+    other = torch.rand((n, 36, 48, 12), device=dev, dtype=torch.float32)
+    thr11 = torch.tensor(aig.REFERENCE_THRESHOLDS, device=dev, dtype=torch.float64)
+    cnt = torch.zeros(12, device=dev, dtype=torch.int64)
+    ms = timed(lambda: path.acivw_batch(mfcc, other, thr11, pos=cnt[:-1], num=cnt[-1:]))
+    report('ACIVW step, one launch (aig_acivw_batch)', n, 'pairs', ms, n * 2 * 82944, 'FP64-bound: two energy maps per pair')
+    for small in (1, 2, 16, 64):
+        ms = timed(lambda: path.energy(mfcc[:small]))
+        report('energy, cluster form, %d frames' % small, small, 'frames', ms, small * (82944 + 13824 + 1728), 'latency')
+        ms = timed(lambda: path.acivw_batch(mfcc[:small], other[:small], thr11, pos=cnt[:-1], num=cnt[-1:]))
+        report('ACIVW step, cluster form, %d pairs' % small, small, 'pairs', ms, small * 2 * 82944, 'latency')
+    del other
     ms = timed(lambda: path.normalize_images(mfcc))
     report('min-max normalise (aig_normalize)', n, 'frames', ms, n * 2 * 82944)
     m = min(n, 2048)
     for shape in ((224, 298), (224, 224)):
-        ms = timed(lambda: path.heatmap(energy[:m], *shape))
-        report('heat map %dx%d (aig_heatmap)' % shape, m, 'frames', ms, m * (13824 + shape[0] * shape[1] * 4), 'float32 fast path, write-bound')
+        out = torch.empty((n,) + shape, device=dev, dtype=torch.float32)
+        for count in sorted({m, n}):
+            ms = timed(lambda: path._lib.aig_heatmap(path._h, energy.data_ptr(), count, shape[0], shape[1], out.data_ptr()))
+            report('heat map %dx%d (aig_heatmap, bulk copies)' % shape, count, 'frames', ms, count * (13824 + shape[0] * shape[1] * 4),
+                   'write roof 6.3 TB/s: %.2f' % (count * shape[0] * shape[1] * 4 / ms / 1e6 / 6300.0))
+        path.set_option('heat_bulk_store', 0)
+        ms = timed(lambda: path._lib.aig_heatmap(path._h, energy.data_ptr(), n, shape[0], shape[1], out.data_ptr()))
+        path.set_option('heat_bulk_store', 1)
+        report('heat map %dx%d (round-1 st.global kernel)' % shape, n, 'frames', ms, n * (13824 + shape[0] * shape[1] * 4))
+        ms = timed(lambda: path.energy_heatmap(mfcc, True, shape[0], shape[1], want_energy=False, want_mask=False, out=out))
+        report('energy + heat map %dx%d, one launch' % shape, n, 'frames', ms, n * (82944 + shape[0] * shape[1] * 4), 'aig_energy_heatmap')
+        del out
         ms = timed(lambda: path.resize_mask(mask[:m], *shape))
         report('mask resize %dx%d' % shape, m, 'frames', ms, m * (1728 + shape[0] * shape[1]))
     heat = path.heatmap(energy[:m])
