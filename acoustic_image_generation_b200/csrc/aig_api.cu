@@ -131,6 +131,11 @@ struct aig_handle {
     char* arena = nullptr;
     size_t arena_cap = 0, arena_off = 0;
     std::vector<std::pair<void*, size_t>> overflow;
+    // small host buffers (a frame, a few vectors) skip cudaMemcpy altogether: they are copied into this pinned, device-
+    // mapped arena and the kernels read / write it directly over PCIe (zero-copy); see Io
+    char* pinned = nullptr;
+    size_t pinned_cap = 0, pinned_off = 0;
+    int small_host_bytes = 128 * 1024;  // per-buffer limit of the zero-copy path; 0 switches it off
     // chained MFCC -> energy pipeline
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_chain[4] = {nullptr, nullptr, nullptr, nullptr};   // start, mfcc[2], energy-done
@@ -214,7 +219,29 @@ int scratch_reset(aig_handle* h) {
         h->arena_cap = total;
     }
     h->arena_off = 0;
+    h->pinned_off = 0;
     return AIG_OK;
+}
+
+// A slot of the pinned zero-copy arena, or null when the buffer is too large / the arena is full or unavailable.
+constexpr size_t kPinnedArenaBytes = size_t(1) << 20;
+void* pinned_slot(aig_handle* h, size_t bytes) {
+    if (h->small_host_bytes <= 0 || bytes > static_cast<size_t>(h->small_host_bytes)) return nullptr;
+    if (h->pinned == nullptr) {
+        if (h->pinned_cap == size_t(-1)) return nullptr;                   // allocation failed before: do not retry
+        if (cudaHostAlloc(reinterpret_cast<void**>(&h->pinned), kPinnedArenaBytes, cudaHostAllocMapped) != cudaSuccess) {
+            cudaGetLastError();
+            h->pinned = nullptr;
+            h->pinned_cap = size_t(-1);
+            return nullptr;
+        }
+        h->pinned_cap = kPinnedArenaBytes;
+    }
+    const size_t need = align_up(std::max<size_t>(bytes, 1), 256);
+    if (h->pinned_off + need > h->pinned_cap) return nullptr;
+    void* p = h->pinned + h->pinned_off;
+    h->pinned_off += need;
+    return p;
 }
 
 void* scratch(aig_handle* h, size_t bytes) {
@@ -261,8 +288,10 @@ struct Io {
     aig_handle* h;
     bool any_host = false;
     bool failed = false;
+    bool zero_copy_ok = false;       // set by latency-bound entry points (one-frame find_logen): small host buffers are then
+                                     // read / written by the kernel in pinned mapped memory instead of being copied
     int code = AIG_OK;               // first failure's status
-    struct Pending { void* host; void* dev; size_t bytes; };
+    struct Pending { void* host; void* dev; size_t bytes; bool zero_copy; };
     std::vector<Pending> outs;
     explicit Io(aig_handle* handle) : h(handle) {}
     // Error exit of an entry point: copies out of caller memory may already be in flight - they must have finished
@@ -278,6 +307,10 @@ struct Io {
         const MemKind kind = classify(p);
         if (kind == kDevice) return p;
         any_host = true;
+        if (void* z = zero_copy_ok ? pinned_slot(h, count * sizeof(T)) : nullptr) {   // the kernel reads the pinned copy itself
+            std::memcpy(z, p, count * sizeof(T));
+            return static_cast<const T*>(z);
+        }
         void* d = scratch(h, count * sizeof(T));
         if (!d) { failed = true; code = AIG_ERR_ALLOC; return nullptr; }
         const cudaError_t status = upload_async(h, d, p, count * sizeof(T), kind, h->stream);
@@ -293,8 +326,11 @@ struct Io {
     T* inout(T* p, size_t count) {
         if (p == nullptr) return nullptr;
         if (classify(p) == kDevice) return p;
+        const bool keep = zero_copy_ok;
+        zero_copy_ok = false;                    // accumulators take device atomics: always a device copy
         T* d = const_cast<T*>(in(const_cast<const T*>(p), count));
-        if (d) outs.push_back({p, d, count * sizeof(T)});
+        zero_copy_ok = keep;
+        if (d) outs.push_back({p, d, count * sizeof(T), false});
         return d;
     }
     template <typename T>
@@ -302,18 +338,25 @@ struct Io {
         if (p == nullptr) return nullptr;
         if (classify(p) == kDevice) return p;
         any_host = true;
+        if (void* z = zero_copy_ok ? pinned_slot(h, count * sizeof(T)) : nullptr) {   // the kernel writes the pinned slot itself
+            outs.push_back({p, z, count * sizeof(T), true});
+            return static_cast<T*>(z);
+        }
         void* d = scratch(h, count * sizeof(T));
         if (!d) { failed = true; code = AIG_ERR_ALLOC; return nullptr; }
-        outs.push_back({p, d, count * sizeof(T)});
+        outs.push_back({p, d, count * sizeof(T), false});
         return static_cast<T*>(d);
     }
     int finish() {
         if (failed) return abort(code != AIG_OK ? code : h->fail(AIG_ERR_ALLOC, "staging failed"));
         for (auto& o : outs) {
+            if (o.zero_copy) continue;
             const cudaError_t status = download(h, o.host, o.dev, o.bytes, classify(o.host), h->stream);
             if (status != cudaSuccess) return abort(h->fail_cuda(status, "device-to-host copy"));
         }
         if (any_host) AIG_CK(cudaStreamSynchronize(h->stream));
+        for (auto& o : outs)
+            if (o.zero_copy) std::memcpy(o.host, o.dev, o.bytes);           // the kernel wrote the pinned slot; hand it over
         return AIG_OK;
     }
 };
@@ -668,13 +711,15 @@ int stream_host_rows(aig_handle* h, const float* host, int64_t n_rows, int row_f
 }
 
 // Rows per H2D chunk of a host-input call: ~64 MiB for long calls (a copy engine is at the link rate from 4 MiB up and
-// fewer chunks mean fewer launches), but at least six chunks per call down to 8 MiB each, so that a 16-frame call
-// (BASELINE configs[0], 56.6 MB) still overlaps its copies with its kernels and result copies instead of running them
-// back to back.
-int64_t host_chunk_rows(int64_t unit_rows, int row_floats, int64_t total_rows) {
+// fewer chunks mean fewer launches); a pinned call is cut into at least six chunks down to 8 MiB each, so that a
+// 16-frame call (BASELINE configs[0], 56.6 MB) still overlaps its copies with its kernels and result copies.
+int64_t host_chunk_rows(int64_t unit_rows, int row_floats, int64_t total_rows, MemKind kind) {
     const int64_t unit_bytes = unit_rows * row_floats * 4;
     const int64_t total_bytes = total_rows * row_floats * 4;
-    const int64_t target = std::min<int64_t>(int64_t(64) << 20, std::max<int64_t>(int64_t(8) << 20, total_bytes / 6));
+    int64_t target = int64_t(64) << 20;
+    // pageable sources already stream through the staging ring in 1-4 MiB pieces: cutting the call further only adds
+    // start-up cost per chunk (measured: 16 pageable frames 4.0 ms in six chunks, 1.8 ms in one)
+    if (kind == kHostPinned) target = std::min(target, std::max<int64_t>(int64_t(8) << 20, total_bytes / 6));
     return std::max<int64_t>(1, target / unit_bytes) * unit_rows;
 }
 
@@ -769,6 +814,7 @@ int aig_destroy(aig_handle* h) {
     if (h->arena) cudaFree(h->arena);
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_twiddle) cudaFree(h->d_twiddle);
+    if (h->pinned) cudaFreeHost(h->pinned);
     cudaGetLastError();
     delete h;
     return AIG_OK;
@@ -819,6 +865,9 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
         h->keep_mfcc_in_l2 = value != 0;
     } else if (key == "l2_evict_first") {
         h->l2_evict_first = value != 0;
+    } else if (key == "small_host_bytes") {
+        if (value < 0 || value > static_cast<int64_t>(kPinnedArenaBytes)) return h->fail(AIG_ERR_ARGUMENT, "small_host_bytes out of range");
+        h->small_host_bytes = static_cast<int>(value);
     } else if (key == "heat_bulk_store") {
         h->heat_bulk_store = value != 0;
     } else if (key == "small_batch_frames") {
@@ -936,7 +985,7 @@ int aig_mfcc(aig_handle* h, const float* power, int64_t n_rows, float* mfcc_out,
         rc = launch_mfcc(h, power, n_rows, d_out, flip180, frame_pixels);
         if (rc != AIG_OK) return rc;
     } else {
-        const int64_t chunk = host_chunk_rows(flip180 ? frame_pixels : 128, in_floats, n_rows);
+        const int64_t chunk = host_chunk_rows(flip180 ? frame_pixels : 128, in_floats, n_rows, classify(power));
         rc = stream_host_rows(h, power, n_rows, in_floats, chunk, [&](const float* d_chunk, int64_t row, int64_t rows) {
             return launch_mfcc(h, d_chunk, rows, d_out + row * out_floats, flip180, frame_pixels);
         });
@@ -972,6 +1021,7 @@ int aig_energy(aig_handle* h, const float* images, int64_t n_frames, int normali
     if (n_frames < 0 || (n_frames > 0 && !images)) return h->fail(AIG_ERR_ARGUMENT, "aig_energy: bad buffers");
     if (n_frames == 0) return AIG_OK;
     Io io(h);
+    io.zero_copy_ok = n_frames <= 1;             // the find_logen drop-in: a frame in, a frame and a map out, latency-bound
     const size_t n = static_cast<size_t>(n_frames);
     const float* d_in = io.in(images, n * kFrameValues);
     float* d_scaled = io.out(scaled_out, n * kFrameValues);
@@ -1173,7 +1223,7 @@ int aig_mfcc_energy(aig_handle* h, const float* power, int64_t n_frames, int fli
                 }
             d2h_overlapped = !host_outs.empty();
         }
-        const int64_t chunk_rows = host_chunk_rows(kFramePixels, kFftLen, n_frames * kFramePixels);
+        const int64_t chunk_rows = host_chunk_rows(kFramePixels, kFftLen, n_frames * kFramePixels, classify(power));
         rc = stream_host_rows(h, power, n_frames * kFramePixels, kFftLen, chunk_rows,
                               [&](const float* d_chunk, int64_t row, int64_t rows) {
                                   const int64_t f0 = row / kFramePixels, nf = rows / kFramePixels;

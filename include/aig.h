@@ -357,6 +357,10 @@ int64_t aig_launch_count(const aig_handle* h);
  *   "host_copy_threads"  copies of 8 MiB and more from / to ordinary (pageable) host arrays are staged through a ring
  *                        of pinned 4 MiB slots by this many host threads (host_staging.h; 4-5x the driver's own
  *                        pageable path): -1 (default) min(6, hardware threads / 2); 0 leaves them to cudaMemcpyAsync
+ *   "small_host_bytes"   host buffers up to this size (default 131072) are not copied with cudaMemcpy at all: they pass
+ *                        through a pinned, device-mapped 1 MiB arena of the handle that the kernels read and write
+ *                        directly over PCIe (zero-copy), which halves the latency of one-frame calls such as the
+ *                        find_logen drop-in; 0 switches the path off
  *   "heat_bulk_store"    1 (default): heat maps are staged in shared memory and written with bulk asynchronous copies
  *                        (heat_stream_kernel); 0: the round-1 kernel with per-thread stores, for comparison runs
  *   "small_batch_frames" batches with fewer frames than this spread each frame over a cluster of 8 CTAs (aig_energy,
