@@ -124,6 +124,7 @@ SIGNATURES = {
     'aig_acivw_batch': (_int, [_p, _p, _p, _i64, _int, _p, _int, _p, _p, _p, _p, _p, _p, _p, _p]),
     'aig_resize_mask': (_int, [_p, _p, _i64, _int, _int, _p]),
     'aig_mfcc_energy': (_int, [_p, _p, _i64, _int, _int, _p, _p, _p, _p]),
+    'aig_mfcc_energy_heatmap': (_int, [_p, _p, _i64, _int, _int, _p, _p, _p, _p, _p, _int, _int]),
     'aig_iou_sweep': (_int, [_p, _p, _p, _i64, _p, _int, _p, _p, _p, _p]),
     'aig_iou_sweep_clips': (_int, [_p, _p, _p, _i64, _i64, _p, _int, _p, _p, _p]),
     'aig_ciou_sweep': (_int, [_p, _p, _p, _p, _p, _p, _i64, _int, _int, _p, _int, _p, _p, _p, _p]),

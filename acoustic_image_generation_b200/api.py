@@ -472,6 +472,29 @@ class AcousticPath:
             self._a(mean, np.float64, True).ptr if want_mean else None))
         return (mfcc, energy, mask) + ((mean,) if want_mean else ())
 
+    def mfcc_energy_heatmap(self, power, flip=False, normalize_first=True, out_h=HEAT_H, out_w=HEAT_W, out=None):
+        """Stages 1 + 2 including the up-sampled, normalised heat map in the one persistent kernel (opt-in,
+        aig_mfcc_energy_heatmap): [N,36,48,512] f32 -> (mfcc f32 [N,36,48,12], energy f64, mask u8, heat f32 [N,out_h,out_w]).
+        ``out=(mfcc, energy, mask, heat)`` supplies the result buffers."""
+        a = self._a(power, np.float32)
+        n = self._frames(a.shape, FRAME_PIXELS * FFT_LEN)
+        if out is not None:
+            mfcc, energy, mask, heat = out
+        else:
+            mfcc = self._empty((n, FRAME_H, FRAME_W, MFCC_NUM), np.float32, a)
+            energy = self._empty((n, FRAME_H, FRAME_W), np.float64, a)
+            mask = self._empty((n, FRAME_H, FRAME_W), np.uint8, a)
+            heat = self._empty((n, out_h, out_w), np.float32, a)
+        args = [self._a(mfcc, np.float32, True), self._a(energy, np.float64, True), self._a(mask, np.uint8, True),
+                self._a(heat, np.float32, True)]
+        sizes = (n * FRAME_PIXELS * MFCC_NUM, n * FRAME_PIXELS, n * FRAME_PIXELS, n * out_h * out_w)
+        if tuple(int(np.prod(x.shape)) for x in args) != sizes:
+            raise ValueError('out buffers do not match %d frames of %d x %d heat maps' % (n, out_h, out_w))
+        self._check(self._lib.aig_mfcc_energy_heatmap(self._h, a.ptr, n, int(bool(flip)), int(bool(normalize_first)),
+                                                      args[0].ptr, args[1].ptr, args[2].ptr, None, args[3].ptr,
+                                                      int(out_h), int(out_w)))
+        return mfcc, energy, mask, heat
+
     # -- stage 3 ------------------------------------------------------------------------------
     @staticmethod
     def _thresholds(thresholds):

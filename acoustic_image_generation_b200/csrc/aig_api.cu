@@ -156,6 +156,7 @@ struct aig_handle {
     int l2_evict_first = 0;             // L2 evict-first hint on the spectrum loads (measured slower: off)
     int keep_mfcc_in_l2 = 1;            // fused kernel: evict-last hint on the MFCC stores the energy warps re-read
     bool fused_attr_set[8] = {false, false, false, false, false, false, false, false};
+    bool fused_heat_attr_set[3] = {false, false, false};
     int chain_energy_ctas_per_sm = 3;   // footprint of the overlapped energy kernel (measured: profiles/r01_tune_chain.txt)
     // profiling: (start, stop) event pairs per launch, by kernel kind
     bool profile = false;
@@ -639,8 +640,57 @@ int launch_fused_variant(aig_handle* h, const CUtensorMap& map, float* d_mfcc, u
     LaunchScope scope(h, h->stream, kKindMfcc);
     kernel<<<grid, kFusedThreads, F::kSmemBytes, h->stream>>>(map, d_mfcc, n_frames, flip180, normalize_first, d_energy,
                                                              d_mask, d_mean, h->l2_evict_first, h->keep_mfcc_in_l2,
-                                                             h->debug_jitter);
+                                                             h->debug_jitter, FusedHeatOut{nullptr, 0, 0});
     return scope.done("mfcc_energy_fused_kernel");
+}
+
+// The opt-in persistent kernel with the heat-map phase: ring of 4 x 24 KiB stages (the heat phase needs 92 KiB at 224 x 298).
+constexpr int kHeatFusedSlabs = 1, kHeatFusedStages = 4;
+bool fused_heat_ok(const aig_handle* h, int out_h, int out_w, const float* d_heat) {
+    using F = FusedPipe<kHeatFusedSlabs, kHeatFusedStages>;
+    return !h->heatmap_exact && out_w % 2 == 0 && (static_cast<long long>(out_h) * out_w) % 4 == 0 &&
+           (reinterpret_cast<uintptr_t>(d_heat) & 15u) == 0 && F::smem_with_heat(out_h, out_w) <= 227 * 1024;
+}
+template <int VEC, int W, int H>
+int launch_fused_heat_variant(aig_handle* h, const CUtensorMap& map, float* d_mfcc, unsigned n_frames, int flip180,
+                              int normalize_first, double* d_energy, uint8_t* d_mask, double* d_mean, const FusedHeatOut& heat,
+                              int slot) {
+    using F = FusedPipe<kHeatFusedSlabs, kHeatFusedStages>;
+    auto kernel = mfcc_energy_fused_kernel<kHeatFusedSlabs, kHeatFusedStages, false, VEC, W, H>;
+    if (!h->fused_heat_attr_set[slot]) {
+        AIG_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        h->fused_heat_attr_set[slot] = true;
+    }
+    const size_t smem = F::smem_with_heat(heat.out_h, heat.out_w);
+    const unsigned grid = std::min<unsigned>(n_frames, static_cast<unsigned>(h->sm_count));
+    LaunchScope scope(h, h->stream, kKindMfcc);
+    kernel<<<grid, kFusedThreads, smem, h->stream>>>(map, d_mfcc, n_frames, flip180, normalize_first, d_energy, d_mask, d_mean,
+                                                    h->l2_evict_first, h->keep_mfcc_in_l2, 0u, heat);
+    return scope.done("mfcc_energy_fused_kernel<heat>");
+}
+int launch_fused_heat(aig_handle* h, const float* d_power, int64_t n_frames, float* d_mfcc, int flip180, int normalize_first,
+                      double* d_energy, uint8_t* d_mask, double* d_mean, float* d_heat, int out_h, int out_w) {
+    if ((reinterpret_cast<uintptr_t>(d_power) & 15u) || (reinterpret_cast<uintptr_t>(d_mfcc) & 15u))
+        return h->fail(AIG_ERR_ARGUMENT, "aig_mfcc_energy_heatmap: device buffers must be 16-byte aligned");
+    const int64_t max_frames = std::max<int64_t>(1, h->launch_row_limit / kFramePixels);
+    for (int64_t done = 0; done < n_frames; done += max_frames) {
+        const int64_t frames = std::min(max_frames, n_frames - done);
+        CUtensorMap map;
+        int rc = encode_spectrum_map(h, d_power + done * kFramePixels * kFftLen, static_cast<uint64_t>(frames) * kFramePixels,
+                                     kFusedRows, &map);
+        if (rc != AIG_OK) return rc;
+        float* mf = d_mfcc + done * kFrameValues;
+        double* en = d_energy ? d_energy + done * kFramePixels : nullptr;
+        uint8_t* mk = d_mask ? d_mask + done * kFramePixels : nullptr;
+        double* mn = d_mean ? d_mean + done : nullptr;
+        const FusedHeatOut heat = {d_heat + done * out_h * out_w, out_h, out_w};
+        const unsigned f = static_cast<unsigned>(frames);
+        if (out_h == 224 && out_w == 298) rc = launch_fused_heat_variant<2, 298, 224>(h, map, mf, f, flip180, normalize_first, en, mk, mn, heat, 0);
+        else if (out_h == 224 && out_w == 224) rc = launch_fused_heat_variant<4, 224, 224>(h, map, mf, f, flip180, normalize_first, en, mk, mn, heat, 1);
+        else rc = launch_fused_heat_variant<2, 0, 0>(h, map, mf, f, flip180, normalize_first, en, mk, mn, heat, 2);
+        if (rc != AIG_OK) return rc;
+    }
+    return AIG_OK;
 }
 
 int launch_fused(aig_handle* h, const float* d_power, int64_t n_frames, float* d_mfcc, int flip180, int normalize_first,
@@ -1244,6 +1294,47 @@ int aig_mfcc_energy(aig_handle* h, const float* power, int64_t n_frames, int fli
         AIG_CK(cudaEventRecord(h->ev_chain[3], h->aux_stream));          // results visible to the handle's stream
         AIG_CK(cudaStreamWaitEvent(h->stream, h->ev_chain[3], 0));
     }
+    return io.finish();
+}
+
+int aig_mfcc_energy_heatmap(aig_handle* h, const float* power, int64_t n_frames, int flip180, int normalize_first,
+                            float* mfcc_out, double* energy_out, uint8_t* mask_out, double* mean_out, float* heat_out,
+                            int out_h, int out_w) {
+    int rc = require(h);
+    if (rc != AIG_OK) return rc;
+    if (!h->tables_set || !h->tables_ref)
+        return h->fail(AIG_ERR_TABLES, "aig_mfcc_energy_heatmap: needs the reference tables (aig_set_tables)");
+    if (n_frames < 0 || (n_frames > 0 && (!power || !mfcc_out || !heat_out)))
+        return h->fail(AIG_ERR_ARGUMENT, "aig_mfcc_energy_heatmap: bad buffers");
+    if (out_h < 1 || out_w < 1 || out_h > kMaxOut || out_w > kMaxOut)
+        return h->fail(AIG_ERR_ARGUMENT, "aig_mfcc_energy_heatmap: output size %dx%d outside 1..%d", out_h, out_w, kMaxOut);
+    if (n_frames == 0) return AIG_OK;
+    const size_t n = static_cast<size_t>(n_frames);
+    Io io(h);
+    const float* d_power = io.in(power, n * kFramePixels * kFftLen);
+    float* d_mfcc = io.out(mfcc_out, n * kFrameValues);
+    double* d_energy = io.out(energy_out, n * kFramePixels);
+    uint8_t* d_mask = io.out(mask_out, n * kFramePixels);
+    double* d_mean = io.out(mean_out, n);
+    float* d_heat = io.out(heat_out, n * out_h * out_w);
+    if (io.failed) return io.finish();
+    if (fused_heat_ok(h, out_h, out_w, d_heat) && n_frames >= small_batch_limit(h) && h->chain_mode == 2) {
+        rc = launch_fused_heat(h, d_power, n_frames, d_mfcc, flip180, normalize_first, d_energy, d_mask, d_mean, d_heat, out_h, out_w);
+        if (rc != AIG_OK) return io.abort(rc);
+        return io.finish();
+    }
+    // small batches, odd shapes, exact mode: the same arithmetic as separate launches
+    if (d_energy == nullptr) d_energy = static_cast<double*>(scratch(h, n * kFramePixels * sizeof(double)));
+    if (d_energy == nullptr) return io.abort(AIG_ERR_ALLOC);
+    if (n_frames >= small_batch_limit(h) && h->chain_mode == 2) {
+        rc = launch_fused(h, d_power, n_frames, d_mfcc, flip180, normalize_first, d_energy, d_mask, d_mean);
+    } else {
+        rc = launch_mfcc(h, d_power, n_frames * kFramePixels, d_mfcc, flip180, kFramePixels);
+        if (rc == AIG_OK) rc = launch_energy(h, h->stream, d_mfcc, n_frames, normalize_first, nullptr, d_energy, d_mask, d_mean);
+    }
+    if (rc != AIG_OK) return io.abort(rc);
+    rc = launch_heatmap(h, d_energy, n_frames, out_h, out_w, d_heat);
+    if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
 }
 

@@ -18,6 +18,7 @@
 
 #include "aig_common.cuh"
 #include "energy_kernel.cuh"
+#include "heatmap_kernel.cuh"
 #include "mfcc_kernel.cuh"
 
 namespace aig {
@@ -38,6 +39,15 @@ struct FusedShared {           // lives after the ring in dynamic shared memory
     double exp_table[64];
     float minmax[2][kFusedConsumerWarps][2];
     unsigned long long bar[4];         // frame_full[2], frame_empty[2]
+    double red64[2][kStreamWarps];     // heat-map phase (HEAT builds): min / max reductions of the energy warps
+    float red32[2][kStreamWarps];
+};
+static_assert(kFusedEnergyThreads == kStreamThreads, "the energy warps run heat_phase(), which is written for kStreamThreads threads");
+
+// Output of the opt-in heat-map phase (aig_mfcc_energy_heatmap).
+struct FusedHeatOut {
+    float* heat;               // [n_frames, out_h, out_w]
+    int out_h, out_w;
 };
 
 template <int SLABS_PER_STAGE, int STAGES>
@@ -45,6 +55,10 @@ struct FusedPipe {
     using P = MfccPipe<kFusedRows, SLABS_PER_STAGE, STAGES>;
     static constexpr int kRingBytes = STAGES * P::kStageBytes;
     static constexpr int kSmemBytes = kRingBytes + 2 * STAGES * 8 + static_cast<int>(sizeof(FusedShared)) + 1024 + 64;
+    // HEAT builds append the heat-map phase's rows, staging slots and taps (heat_stream_layout) behind FusedShared
+    static __host__ __device__ size_t smem_with_heat(int out_h, int out_w) {
+        return static_cast<size_t>(kSmemBytes) + 16 + heat_stream_layout(out_h, out_w, false).total;
+    }
 };
 
 __device__ __forceinline__ void energy_group_sync() {
@@ -56,13 +70,17 @@ __device__ __forceinline__ void energy_group_sync() {
 // protocol allows; the production instantiation (JITTER = false) contains none of it.
 // mfcc_out is written by the consumer warps and read back by the energy warps of the same CTA: no __restrict__, no
 // read-only loads on it.
-template <int SLABS_PER_STAGE, int STAGES, bool JITTER>
+// HEAT_VEC != 0 (opt-in, aig_mfcc_energy_heatmap): the energy warps go on from the energy map to the normalised,
+// up-sampled heat map of showvideo.py:226-228 (heat_phase() of heatmap_kernel.cuh: 2 or 4 pixels per lane, output size
+// HW x HH as template constants or 0 = run-time), staging its rows in shared memory behind FusedShared and shipping them
+// with bulk copies - 267 KB more per frame (+7 % of the bytes) for which the ring gives up half of its 192 KiB.
+template <int SLABS_PER_STAGE, int STAGES, bool JITTER, int HEAT_VEC = 0, int HW = 0, int HH = 0>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* mfcc_out,
                          unsigned int n_frames, int flip180, int normalize_first,
                          double* __restrict__ energy_out, uint8_t* __restrict__ mask_out,
                          double* __restrict__ mean_out, int l2_evict_first, int keep_mfcc_in_l2,
-                         unsigned int jitter_seed) {
+                         unsigned int jitter_seed, const FusedHeatOut heat_out) {
     using P = MfccPipe<kFusedRows, SLABS_PER_STAGE, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -155,6 +173,15 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* mfcc_o
     // ---------------------------------------- energy warps -----------------------------------------
     const int et = threadIdx.x - (kFusedRows + 32);                     // 0..255
     unsigned int it = 0;
+    HeatSmem hs = {};
+    unsigned int chunk_it = 0;
+    const int heat_h = HH ? HH : heat_out.out_h, heat_w = HW ? HW : heat_out.out_w;
+    if (HEAT_VEC != 0) {
+        unsigned char* heat_base = reinterpret_cast<unsigned char*>(&sh) + ((sizeof(FusedShared) + 15) & ~size_t(15));
+        hs = heat_smem_carve(heat_base, heat_stream_layout(heat_h, heat_w, false), heat_h, heat_w);
+        heat_taps_init(hs, heat_h, heat_w, et);
+        energy_group_sync();
+    }
     for (unsigned int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++it) {
         const int slot = it & 1;
         if (JITTER) jitter_spin(jitter_seed, 6u, jitter_counter);
@@ -194,7 +221,20 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* mfcc_o
             }
         }
         energy_group_sync();      // sh.map is rewritten for the next frame
+        if (HEAT_VEC != 0) {
+            double e[kHeatPerThread];
+#pragma unroll
+            for (int i = 0; i < kHeatPerThread; ++i) {
+                const int p = et + i * kStreamThreads;
+                e[i] = p < kFramePixels ? sh.map[p] : CUDART_NAN;
+            }
+            // (heat_phase's first barrier comes after these reads, so no thread starts the next frame's map before them)
+            heat_phase<HEAT_VEC == 0 ? 2 : HEAT_VEC, HW, HH>(
+                e, hs, sh.red64, sh.red32, heat_h, heat_w,
+                heat_out.heat + static_cast<size_t>(frame) * heat_h * heat_w, et, chunk_it, [] { energy_group_sync(); }, [] {});
+        }
     }
+    if (HEAT_VEC != 0 && lane == 0) bulk_wait_all<0>();        // shared memory must outlive the copies that read it
 }
 
 }  // namespace aig

@@ -366,34 +366,33 @@ __device__ __forceinline__ unsigned long long norm2(unsigned long long pa, unsig
     return o;
 }
 
-// W, H: the output size as template constants (0 = run-time size from the arguments).  The reference's two sizes,
-// 298 x 224 (showimages.py:147) and 224 x 224 (BASELINE configs[2]), are instantiated with constants: every column loop
-// then unrolls completely with immediate offsets - the run-time-size build spent half of its instructions on loop
-// bounds and address arithmetic (profiles/r02_ncu_stage2_kernels_a.csv).
-template <bool FUSED, int VEC, int W, int H>
-__global__ void __launch_bounds__(kStreamThreads, 2)
-heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ double s_red64[2][kStreamWarps];
-    __shared__ float s_red32[2][kStreamWarps];
-    __shared__ EnergyTables s_tab;
-    const int out_h = H ? H : a.out_h, out_w = W ? W : a.out_w;
-    const HeatStreamLayout lay = heat_stream_layout(out_h, out_w, FUSED);
-    float* s_t = reinterpret_cast<float*>(s_raw);
-    float* s_rows = reinterpret_cast<float*>(s_raw + lay.off_rows);
-    float* s_stage = reinterpret_cast<float*>(s_raw + lay.off_stage);
-    EnergyPhaseShared& eph = *reinterpret_cast<EnergyPhaseShared*>(s_raw + lay.off_stage);
-    float* s_wx = reinterpret_cast<float*>(s_raw + lay.off_taps);
-    float* s_wy = s_wx + out_w;
-    int* s_x0 = reinterpret_cast<int*>(s_wy + out_h);
-    int* s_y0 = s_x0 + out_w;
-    const int wp = lay.wp;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (FUSED) load_energy_tables(s_tab, tid, kStreamThreads);
+// ---- the heat-map phase of one frame, shared by heat_stream_kernel and the persistent MFCC + energy + heat-map kernel ----
+struct HeatSmem {              // carved out of dynamic shared memory (heat_stream_layout)
+    float* t;                  // [1728] frame-normalised energies
+    float* rows;               // [36][wp] horizontally blended rows
+    float* stage;              // [8 warps][2 buffers][2 rows][out_w] staging slots of the bulk copies
+    float* wx; float* wy;      // [out_w], [out_h] tap weights
+    int* x0; int* y0;          // [out_w], [out_h] tap indices (lo | hi << 16; y0 bit 31 = edge row of its source-row pair)
+    int wp;
+};
+__device__ __forceinline__ HeatSmem heat_smem_carve(unsigned char* base, const HeatStreamLayout& lay, int out_h, int out_w) {
+    HeatSmem s;
+    s.t = reinterpret_cast<float*>(base);
+    s.rows = reinterpret_cast<float*>(base + lay.off_rows);
+    s.stage = reinterpret_cast<float*>(base + lay.off_stage);
+    s.wx = reinterpret_cast<float*>(base + lay.off_taps);
+    s.wy = s.wx + out_w;
+    s.x0 = reinterpret_cast<int*>(s.wy + out_h);
+    s.y0 = s.x0 + out_w;
+    s.wp = lay.wp;
+    return s;
+}
+// Called once per CTA by the kStreamThreads threads that run the heat phase (index tid); synchronise before first use.
+__device__ __forceinline__ void heat_taps_init(const HeatSmem& s, int out_h, int out_w, int tid) {
     for (int d = tid; d < out_w; d += kStreamThreads) {
         int i0, i1; double w;
         linear_tap(d, kFrameW, out_w, &i0, &i1, &w);
-        s_x0[d] = i0 | (i1 << 16); s_wx[d] = static_cast<float>(w);
+        s.x0[d] = i0 | (i1 << 16); s.wx[d] = static_cast<float>(w);
     }
     for (int d = tid; d < out_h; d += kStreamThreads) {
         int i0, i1; double w;
@@ -402,8 +401,26 @@ heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
         linear_tap(max(d - 1, 0), kFrameH, out_h, &p0, &p1, &wn);
         linear_tap(min(d + 1, out_h - 1), kFrameH, out_h, &n0, &n1, &wn);
         const bool edge = d == 0 || d == out_h - 1 || p0 != i0 || p1 != i1 || n0 != i0 || n1 != i1;
-        s_y0[d] = i0 | (i1 << 16) | (edge ? 0x80000000 : 0); s_wy[d] = static_cast<float>(w);
+        s.y0[d] = i0 | (i1 << 16) | (edge ? 0x80000000 : 0); s.wy[d] = static_cast<float>(w);
     }
+}
+
+constexpr int kHeatPerThread = (kFramePixels + kStreamThreads - 1) / kStreamThreads;     // 7 (6.75)
+
+// Steps 2-5 of the list above for one frame whose 1728 energies the kStreamThreads threads hold in e[] (thread tid owns
+// pixels tid + 256 i).  W, H: the output size as template constants (0 = run-time size): the reference's two sizes,
+// 298 x 224 (showimages.py:147) and 224 x 224 (BASELINE configs[2]), are instantiated with constants, every column loop
+// then unrolls completely with immediate offsets - the run-time-size build spent half of its instructions on loop
+// bounds and address arithmetic (profiles/r02_ncu_stage2_kernels.csv).  `sync` is the barrier of the participating
+// threads, `after_t` runs once the energies have been consumed (the stand-alone kernel prefetches the next frame's there).
+// chunk_it is the calling warp's running chunk counter (selects its staging buffer; survives across frames).
+template <int VEC, int W, int H, typename Sync, typename AfterT>
+__device__ __forceinline__ void heat_phase(const double (&e)[kHeatPerThread], const HeatSmem& s, double (*red64)[kStreamWarps],
+                                           float (*red32)[kStreamWarps], int out_h_rt, int out_w_rt, float* dst, int tid,
+                                           unsigned int& chunk_it, Sync sync, AfterT after_t) {
+    const int out_h = H ? H : out_h_rt, out_w = W ? W : out_w_rt;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wp = s.wp;
     // column loops: x = (lane + 32 k) * V for k = 0 .. ; fully unrolled when the width is a template constant
     auto columns = [&](auto vec_tag, auto body) {
         constexpr int V = decltype(vec_tag)::value;
@@ -418,21 +435,140 @@ heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
             for (int x = lane * V; x < out_w; x += 32 * V) body(x);
         }
     };
-    constexpr int kPerThread = (kFramePixels + kStreamThreads - 1) / kStreamThreads;     // 7 (6.75)
-    double e[kPerThread];
+    // 2. frame min / max in float64, t = (e - min) / (max - min) as float32
+    double lo = CUDART_INF, hi = -CUDART_INF;
+#pragma unroll
+    for (int i = 0; i < kHeatPerThread; ++i) { lo = fmin(lo, e[i]); hi = fmax(hi, e[i]); }
+    lo = warp_min(lo); hi = warp_max(hi);
+    sync();                               // the previous frame's readers of red64 / t / rows are done
+    if (lane == 0) { red64[0][warp] = lo; red64[1][warp] = hi; }
+    sync();
+    lo = red64[0][0]; hi = red64[1][0];
+#pragma unroll
+    for (int w = 1; w < kStreamWarps; ++w) { lo = fmin(lo, red64[0][w]); hi = fmax(hi, red64[1][w]); }
+    const double span = hi - lo;
+#pragma unroll
+    for (int i = 0; i < kHeatPerThread; ++i) {
+        const int p = tid + i * kStreamThreads;
+        if (p < kFramePixels) s.t[p] = span > 0.0 ? static_cast<float>((e[i] - lo) / span) : 0.f;
+    }
+    after_t();
+    sync();
+    // 3. horizontal pass: a column's taps are loaded once and applied to this warp's source rows (warp, warp + 8, ...)
+    columns(std::integral_constant<int, 1>{}, [&](int x) {
+        const int xi = s.x0[x];
+        const float wx = s.wx[x];
+        const int c0 = xi & 0xffff, c1 = xi >> 16;
+#pragma unroll
+        for (int r = warp; r < kFrameH; r += kStreamWarps) {
+            const float u = s.t[r * kFrameW + c0], v = s.t[r * kFrameW + c1];
+            s.rows[r * wp + x] = fmaf(v - u, wx, u);
+        }
+    });
+    sync();
+    // 4. min / max of the up-sampled image
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    for (int y = warp; y < out_h; y += kStreamWarps) {
+        const int yi = s.y0[y];
+        if (yi >= 0) continue;                                // interior row of its pair: cannot hold an extreme
+        const float wy = s.wy[y];
+        const float* r0 = s.rows + (yi & 0xffff) * wp;
+        const float* r1 = s.rows + ((yi >> 16) & 0x7fff) * wp;
+        columns(std::integral_constant<int, VEC>{}, [&](int x) { HeatVec<VEC>::lerp_minmax(r0, r1, x, wy, mn, mx); });
+    }
+    mn = warp_min(mn); mx = warp_max(mx);
+    if (lane == 0) { red32[0][warp] = mn; red32[1][warp] = mx; }
+    sync();
+    mn = red32[0][0]; mx = red32[1][0];
+#pragma unroll
+    for (int w = 1; w < kStreamWarps; ++w) { mn = fminf(mn, red32[0][w]); mx = fmaxf(mx, red32[1][w]); }
+    // a constant frame gives 0/0 = NaN, like the reference's (x - min) / (max - min)
+    const float inv = (span > 0.0 && mx > mn) ? 1.f / (mx - mn) : CUDART_NAN_F;
+    const unsigned long long nmn2 = pack2(make_float2(-mn, -mn)), inv2 = pack2(make_float2(inv, inv));
+    // 5. output: row pairs through this warp's staging slot, one bulk copy each
+    float* my_stage = s.stage + warp * 4 * out_w;                 // [2 buffers][2 rows][out_w]
+    const uint32_t my_stage_addr = smem_u32(my_stage);
+    const int n_pairs = (out_h + 1) / 2;
+    for (int q = warp; q < n_pairs; q += kStreamWarps, ++chunk_it) {
+        const unsigned int buf = chunk_it & 1u;
+        if (chunk_it >= 2u) {                                 // the copy issued two chunks ago has finished reading this buffer
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+        }
+        float* stage = my_stage + buf * 2 * out_w;
+        const int y0 = 2 * q;
+        const bool two = (H != 0 && H % 2 == 0) || y0 + 1 < out_h;
+        const int ya = s.y0[y0], yb = s.y0[two ? y0 + 1 : y0];
+        const float wa = s.wy[y0], wb = s.wy[two ? y0 + 1 : y0];
+        const unsigned long long wa2 = pack2(make_float2(wa, wa)), wb2 = pack2(make_float2(wb, wb));
+        const float* a0 = s.rows + (ya & 0xffff) * wp;
+        const float* a1 = s.rows + ((ya >> 16) & 0x7fff) * wp;
+        if (two && ((ya ^ yb) & 0x7fffffff) == 0) {
+            // both output rows interpolate between the same two source rows (five times out of six at 36 -> 224):
+            // one pair of loads and one difference serve both
+            columns(std::integral_constant<int, VEC>{}, [&](int x) {
+#pragma unroll
+                for (int h = 0; h < VEC; h += 2) {
+                    const unsigned long long pa = *reinterpret_cast<const unsigned long long*>(a0 + x + h);
+                    const unsigned long long pb = *reinterpret_cast<const unsigned long long*>(a1 + x + h);
+                    const unsigned long long d = diff2(pa, pb);
+                    *reinterpret_cast<unsigned long long*>(stage + x + h) = norm2(pa, d, wa2, nmn2, inv2);
+                    *reinterpret_cast<unsigned long long*>(stage + out_w + x + h) = norm2(pa, d, wb2, nmn2, inv2);
+                }
+            });
+        } else {
+            const float* b0 = s.rows + (yb & 0xffff) * wp;
+            const float* b1 = s.rows + ((yb >> 16) & 0x7fff) * wp;
+            columns(std::integral_constant<int, VEC>{}, [&](int x) {
+#pragma unroll
+                for (int h = 0; h < VEC; h += 2) {
+                    const unsigned long long pa = *reinterpret_cast<const unsigned long long*>(a0 + x + h);
+                    const unsigned long long pb = *reinterpret_cast<const unsigned long long*>(a1 + x + h);
+                    *reinterpret_cast<unsigned long long*>(stage + x + h) = norm2(pa, diff2(pa, pb), wa2, nmn2, inv2);
+                    if (two) {
+                        const unsigned long long qa = *reinterpret_cast<const unsigned long long*>(b0 + x + h);
+                        const unsigned long long qb = *reinterpret_cast<const unsigned long long*>(b1 + x + h);
+                        *reinterpret_cast<unsigned long long*>(stage + out_w + x + h) = norm2(qa, diff2(qa, qb), wb2, nmn2, inv2);
+                    }
+                }
+            });
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_store_s2g(dst + static_cast<long long>(y0) * out_w, my_stage_addr + buf * 2 * out_w * 4,
+                           static_cast<uint32_t>((two ? 2 : 1) * out_w * 4));
+            bulk_commit();
+        }
+    }
+}
+
+template <bool FUSED, int VEC, int W, int H>
+__global__ void __launch_bounds__(kStreamThreads, 2)
+heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ double s_red64[2][kStreamWarps];
+    __shared__ float s_red32[2][kStreamWarps];
+    __shared__ EnergyTables s_tab;
+    const int out_h = H ? H : a.out_h, out_w = W ? W : a.out_w;
+    const HeatStreamLayout lay = heat_stream_layout(out_h, out_w, FUSED);
+    const HeatSmem hs = heat_smem_carve(s_raw, lay, out_h, out_w);
+    EnergyPhaseShared& eph = *reinterpret_cast<EnergyPhaseShared*>(s_raw + lay.off_stage);
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (FUSED) load_energy_tables(s_tab, tid, kStreamThreads);
+    heat_taps_init(hs, out_h, out_w, tid);
+    double e[kHeatPerThread];
     auto fetch = [&](long long frame) {
 #pragma unroll
-        for (int i = 0; i < kPerThread; ++i) {
+        for (int i = 0; i < kHeatPerThread; ++i) {
             const int p = tid + i * kStreamThreads;
             e[i] = (frame < a.n_frames && p < kFramePixels) ? __ldcs(a.energy_in + frame * kFramePixels + p) : CUDART_NAN;
         }
     };
     if (!FUSED) fetch(blockIdx.x);
-    float* my_stage = s_stage + warp * 4 * out_w;                 // [2 buffers][2 rows][out_w]
-    const uint32_t my_stage_addr = smem_u32(my_stage);
-    const int n_pairs = (out_h + 1) / 2;
     unsigned int chunk_it = 0;                                    // this warp's chunk counter: selects the staging buffer
     const long long frame_values = static_cast<long long>(out_h) * out_w;
+    __syncthreads();
 
     for (long long frame = blockIdx.x; frame < a.n_frames; frame += gridDim.x) {
         if (FUSED) {
@@ -461,115 +597,15 @@ heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
                         s.mask[0][frame * kFramePixels + p] = eph.map[p] > mean ? 1 : 0;
             }
 #pragma unroll
-            for (int i = 0; i < kPerThread; ++i) {
+            for (int i = 0; i < kHeatPerThread; ++i) {
                 const int p = tid + i * kStreamThreads;
                 e[i] = p < kFramePixels ? eph.map[p] : CUDART_NAN;
             }
         }
-        // 2. frame min / max in float64, t = (e - min) / (max - min) as float32
-        double lo = CUDART_INF, hi = -CUDART_INF;
-#pragma unroll
-        for (int i = 0; i < kPerThread; ++i) { lo = fmin(lo, e[i]); hi = fmax(hi, e[i]); }
-        lo = warp_min(lo); hi = warp_max(hi);
-        __syncthreads();                      // previous frame's readers of s_red64 / s_t / s_rows are done; FUSED: eph.map was read
-        if (lane == 0) { s_red64[0][warp] = lo; s_red64[1][warp] = hi; }
-        __syncthreads();
-        lo = s_red64[0][0]; hi = s_red64[1][0];
-#pragma unroll
-        for (int w = 1; w < kStreamWarps; ++w) { lo = fmin(lo, s_red64[0][w]); hi = fmax(hi, s_red64[1][w]); }
-        const double span = hi - lo;
-#pragma unroll
-        for (int i = 0; i < kPerThread; ++i) {
-            const int p = tid + i * kStreamThreads;
-            if (p < kFramePixels) s_t[p] = span > 0.0 ? static_cast<float>((e[i] - lo) / span) : 0.f;
-        }
-        if (!FUSED) fetch(frame + gridDim.x);                     // next frame's energies arrive during the passes below
-        __syncthreads();
-        // 3. horizontal pass: a column's taps are loaded once and applied to this warp's source rows (warp, warp + 8, ...)
-        columns(std::integral_constant<int, 1>{}, [&](int x) {
-            const int xi = s_x0[x];
-            const float wx = s_wx[x];
-            const int c0 = xi & 0xffff, c1 = xi >> 16;
-#pragma unroll
-            for (int r = warp; r < kFrameH; r += kStreamWarps) {
-                const float u = s_t[r * kFrameW + c0], v = s_t[r * kFrameW + c1];
-                s_rows[r * wp + x] = fmaf(v - u, wx, u);
-            }
-        });
-        __syncthreads();
-        // 4. min / max of the up-sampled image
-        float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-        for (int y = warp; y < out_h; y += kStreamWarps) {
-            const int yi = s_y0[y];
-            if (yi >= 0) continue;                                // interior row of its pair: cannot hold an extreme
-            const float wy = s_wy[y];
-            const float* r0 = s_rows + (yi & 0xffff) * wp;
-            const float* r1 = s_rows + ((yi >> 16) & 0x7fff) * wp;
-            columns(std::integral_constant<int, VEC>{}, [&](int x) { HeatVec<VEC>::lerp_minmax(r0, r1, x, wy, mn, mx); });
-        }
-        mn = warp_min(mn); mx = warp_max(mx);
-        if (lane == 0) { s_red32[0][warp] = mn; s_red32[1][warp] = mx; }
-        __syncthreads();
-        mn = s_red32[0][0]; mx = s_red32[1][0];
-#pragma unroll
-        for (int w = 1; w < kStreamWarps; ++w) { mn = fminf(mn, s_red32[0][w]); mx = fmaxf(mx, s_red32[1][w]); }
-        // a constant frame gives 0/0 = NaN, like the reference's (x - min) / (max - min)
-        const float inv = (span > 0.0 && mx > mn) ? 1.f / (mx - mn) : CUDART_NAN_F;
-        const unsigned long long nmn2 = pack2(make_float2(-mn, -mn)), inv2 = pack2(make_float2(inv, inv));
-        float* dst = a.heat + frame * frame_values;
-        // 5. output: row pairs through this warp's staging slot, one bulk copy each
-        for (int q = warp; q < n_pairs; q += kStreamWarps, ++chunk_it) {
-            const unsigned int buf = chunk_it & 1u;
-            if (chunk_it >= 2u) {                                 // the copy issued two chunks ago has finished reading this buffer
-                if (lane == 0) bulk_wait_read<1>();
-                __syncwarp();
-            }
-            float* stage = my_stage + buf * 2 * out_w;
-            const int y0 = 2 * q;
-            const bool two = (H != 0 && H % 2 == 0) || y0 + 1 < out_h;
-            const int ya = s_y0[y0], yb = s_y0[two ? y0 + 1 : y0];
-            const float wa = s_wy[y0], wb = s_wy[two ? y0 + 1 : y0];
-            const unsigned long long wa2 = pack2(make_float2(wa, wa)), wb2 = pack2(make_float2(wb, wb));
-            const float* a0 = s_rows + (ya & 0xffff) * wp;
-            const float* a1 = s_rows + ((ya >> 16) & 0x7fff) * wp;
-            if (two && ((ya ^ yb) & 0x7fffffff) == 0) {
-                // both output rows interpolate between the same two source rows (five times out of six at 36 -> 224):
-                // one pair of loads and one difference serve both
-                columns(std::integral_constant<int, VEC>{}, [&](int x) {
-#pragma unroll
-                    for (int h = 0; h < VEC; h += 2) {
-                        const unsigned long long pa = *reinterpret_cast<const unsigned long long*>(a0 + x + h);
-                        const unsigned long long pb = *reinterpret_cast<const unsigned long long*>(a1 + x + h);
-                        const unsigned long long d = diff2(pa, pb);
-                        *reinterpret_cast<unsigned long long*>(stage + x + h) = norm2(pa, d, wa2, nmn2, inv2);
-                        *reinterpret_cast<unsigned long long*>(stage + out_w + x + h) = norm2(pa, d, wb2, nmn2, inv2);
-                    }
-                });
-            } else {
-                const float* b0 = s_rows + (yb & 0xffff) * wp;
-                const float* b1 = s_rows + ((yb >> 16) & 0x7fff) * wp;
-                columns(std::integral_constant<int, VEC>{}, [&](int x) {
-#pragma unroll
-                    for (int h = 0; h < VEC; h += 2) {
-                        const unsigned long long pa = *reinterpret_cast<const unsigned long long*>(a0 + x + h);
-                        const unsigned long long pb = *reinterpret_cast<const unsigned long long*>(a1 + x + h);
-                        *reinterpret_cast<unsigned long long*>(stage + x + h) = norm2(pa, diff2(pa, pb), wa2, nmn2, inv2);
-                        if (two) {
-                            const unsigned long long qa = *reinterpret_cast<const unsigned long long*>(b0 + x + h);
-                            const unsigned long long qb = *reinterpret_cast<const unsigned long long*>(b1 + x + h);
-                            *reinterpret_cast<unsigned long long*>(stage + out_w + x + h) = norm2(qa, diff2(qa, qb), wb2, nmn2, inv2);
-                        }
-                    }
-                });
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                bulk_store_s2g(dst + static_cast<long long>(y0) * out_w, my_stage_addr + buf * 2 * out_w * 4,
-                               static_cast<uint32_t>((two ? 2 : 1) * out_w * 4));
-                bulk_commit();
-            }
-        }
+        // (FUSED: heat_phase's first barrier also orders the reads of eph.map above before the staging area is written)
+        heat_phase<VEC, W, H>(e, hs, s_red64, s_red32, out_h, out_w, a.heat + frame * frame_values, tid, chunk_it,
+                              [] { __syncthreads(); },
+                              [&] { if (!FUSED) fetch(frame + gridDim.x); });   // next frame's energies arrive during the passes
     }
     if (lane == 0) bulk_wait_all<0>();        // shared memory must outlive the copies that read it
 }

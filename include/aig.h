@@ -172,6 +172,17 @@ int aig_mfcc_energy(aig_handle* h, const float* power, int64_t n_frames, int fli
                     int normalize_first, float* mfcc_out, double* energy_out, uint8_t* mask_out,
                     double* mean_out);
 
+/* Stages 1 + 2 INCLUDING the heat map in the one persistent kernel (opt-in; the north star's "fused energy, upsample and
+ * normalise" applied to the streaming pass): as aig_mfcc_energy, and the energy warps of every SM go on to up-sample and
+ * normalise their frame's energy map (the arithmetic of aig_heatmap's default mode) and ship the rows with bulk
+ * asynchronous copies while the next frame's spectra stream in.  heat_out [n_frames, out_h, out_w] float32, required.
+ * Shapes the streaming heat-map code cannot take (odd out_w, out_h * out_w not a multiple of 4, > ~100 KiB of rows),
+ * "heatmap_exact" mode and batches smaller than the SM count run the separate kernels instead - same arithmetic.
+ * Host buffers are accepted but copied whole (no chunked overlap): the call is meant for device-resident streams. */
+int aig_mfcc_energy_heatmap(aig_handle* h, const float* power, int64_t n_frames, int flip180, int normalize_first,
+                            float* mfcc_out, double* energy_out, uint8_t* mask_out, double* mean_out, float* heat_out,
+                            int out_h, int out_w);
+
 /* ---- stage 3: scoring ------------------------------------------------------------------ */
 
 /* The reference's whole ACIVW / AVIA evaluation step (iouenergythreshold.py:213-229) for a batch in one kernel launch:

@@ -244,6 +244,28 @@ def test_fused_energy_heatmap_equals_the_two_kernel_chain(path, torch, shape, no
     assert np.abs(heat[i] - want).max() <= 1e-4
 
 
+@pytest.mark.parametrize('shape', [(224, 298), (224, 224), (100, 78), (37, 49)])
+def test_persistent_kernel_with_heat_map_phase(path, torch, shape):
+    """aig_mfcc_energy_heatmap (opt-in): the energy warps of the persistent kernel also up-sample and normalise.  MFCC,
+    energy and mask must equal aig_mfcc_energy's and the heat map aig_heatmap's, bit for bit; (37, 49) cannot stream
+    (odd width) and takes the separate kernels, 3 frames the small-batch path."""
+    pool = torch.from_numpy(synth.power_frames(12, 73, 'chi2')).cuda()
+    for n in (3, 310):
+        power = pool[torch.arange(n, device='cuda') % 12].contiguous()
+        mfcc, energy, mask = path.mfcc_energy(power, flip=True, normalize_first=True)
+        want_heat = path.heatmap(energy, *shape)
+        before = path.launch_count
+        got = path.mfcc_energy_heatmap(power, flip=True, normalize_first=True, out_h=shape[0], out_w=shape[1])
+        launches = path.launch_count - before
+        assert torch.equal(got[0], mfcc) and torch.equal(got[1], energy) and torch.equal(got[2], mask)
+        assert torch.equal(got[3], want_heat)
+        if n == 310 and shape[1] % 2 == 0:
+            assert launches == 1
+    host = path.mfcc_energy_heatmap(pool[:2].cpu().numpy(), flip=True, normalize_first=True, out_h=shape[0], out_w=shape[1])
+    dev = path.mfcc_energy_heatmap(pool[:2].contiguous(), flip=True, normalize_first=True, out_h=shape[0], out_w=shape[1])
+    assert np.array_equal(host[3], dev[3].cpu().numpy()) and np.array_equal(host[0], dev[0].cpu().numpy())
+
+
 def test_heatmap_exact_mode_still_bit_exact_through_the_combined_call(path):
     imgs = synth.smooth_images(160, 61)
     path.set_option('heatmap_exact', 1)

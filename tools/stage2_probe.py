@@ -58,6 +58,18 @@ for shape in ((224, 298), (224, 224), (112, 150)):
     ms = timed(lambda: lib.aig_energy_heatmap(h, img.data_ptr(), n, 1, None, None, heat.data_ptr(), shape[0], shape[1]))
     line('aig_energy_heatmap %dx%d one launch (%d frames)' % (shape + (n,)), ms, n, shape[0] * shape[1] * 4)
     del heat
+power = torch.rand(4096, 36, 48, 512, device='cuda')
+mfcc = torch.empty(4096, 36, 48, 12, device='cuda')
+heat = torch.empty(4096, 224, 298, device='cuda')
+ms = timed(lambda: lib.aig_mfcc_energy(h, power.data_ptr(), 4096, 1, 1, mfcc.data_ptr(), energy.data_ptr(), mask.data_ptr(), None))
+line('aig_mfcc_energy (4096 frames)', ms, 4096, 3628800)
+ms = timed(lambda: lib.aig_mfcc_energy_heatmap(h, power.data_ptr(), 4096, 1, 1, mfcc.data_ptr(), energy.data_ptr(), mask.data_ptr(), None,
+                                               heat.data_ptr(), 224, 298))
+line('aig_mfcc_energy_heatmap 224x298, one persistent kernel', ms, 4096, 3628800 + 224 * 298 * 4)
+ms0 = timed(lambda: (lib.aig_mfcc_energy(h, power.data_ptr(), 4096, 1, 1, mfcc.data_ptr(), energy.data_ptr(), mask.data_ptr(), None),
+                     lib.aig_heatmap(h, energy.data_ptr(), 4096, 224, 298, heat.data_ptr())))
+line('aig_mfcc_energy + aig_heatmap 224x298, two launches', ms0, 4096, 3628800 + 224 * 298 * 4)
+del power, mfcc, heat
 for small in (1, 2, 16, 64, 128):
     ms = timed(lambda: lib.aig_energy(h, img.data_ptr(), small, 0, None, energy.data_ptr(), mask.data_ptr(), None), 21)
     line('aig_energy cluster form, %d frames (incl. launch)' % small, ms, small)
