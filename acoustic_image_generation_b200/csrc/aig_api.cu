@@ -548,19 +548,19 @@ int mask_ctas_per_sm(size_t smem) {
 // heat_stream_kernel needs every output row pair to start on a 16-byte boundary and be a 16-byte multiple long.
 bool heat_stream_ok(const aig_handle* h, int out_h, int out_w, const float* d_heat, bool fused) {
     return h->heat_bulk_store && !h->heatmap_exact && out_w % 2 == 0 && (static_cast<long long>(out_h) * out_w) % 4 == 0 &&
-           (reinterpret_cast<uintptr_t>(d_heat) & 15u) == 0 && heat_stream_layout(out_h, out_w, fused).total <= 100 * 1024;
+           (reinterpret_cast<uintptr_t>(d_heat) & 15u) == 0 && heat_stream_layout(out_h, out_w, fused).total <= 120 * 1024;
 }
 
 template <bool FUSED, int VEC, int W, int H>
 int launch_heat_stream_variant(aig_handle* h, const HeatStreamArgs& args, int slot) {
     auto kernel = heat_stream_kernel<FUSED, VEC, W, H>;
     if (!h->heat_stream_attr_set[slot]) {
-        AIG_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        AIG_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
         cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         h->heat_stream_attr_set[slot] = true;
     }
     const size_t smem = heat_stream_layout(args.out_h, args.out_w, FUSED).total;
-    const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(2, (226 * 1024) / (smem + 4 * 1024))));
+    const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024 + 512))));
     const int grid = frames_grid(h, args.n_frames, per_sm);
     LaunchScope scope(h, h->stream, FUSED ? kKindEnergy : kKindOther);
     kernel<<<grid, kStreamThreads, smem, h->stream>>>(args);

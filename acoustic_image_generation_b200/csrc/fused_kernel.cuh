@@ -39,10 +39,9 @@ struct FusedShared {           // lives after the ring in dynamic shared memory
     double exp_table[64];
     float minmax[2][kFusedConsumerWarps][2];
     unsigned long long bar[4];         // frame_full[2], frame_empty[2]
-    double red64[2][kStreamWarps];     // heat-map phase (HEAT builds): min / max reductions of the energy warps
-    float red32[2][kStreamWarps];
+    double red64[2][kHeatMaxWarps];    // heat-map phase (HEAT builds): min / max reductions of the energy warps
+    float red32[2][kHeatMaxWarps];
 };
-static_assert(kFusedEnergyThreads == kStreamThreads, "the energy warps run heat_phase(), which is written for kStreamThreads threads");
 
 // Output of the opt-in heat-map phase (aig_mfcc_energy_heatmap).
 struct FusedHeatOut {
@@ -57,7 +56,7 @@ struct FusedPipe {
     static constexpr int kSmemBytes = kRingBytes + 2 * STAGES * 8 + static_cast<int>(sizeof(FusedShared)) + 1024 + 64;
     // HEAT builds append the heat-map phase's rows, staging slots and taps (heat_stream_layout) behind FusedShared
     static __host__ __device__ size_t smem_with_heat(int out_h, int out_w) {
-        return static_cast<size_t>(kSmemBytes) + 16 + heat_stream_layout(out_h, out_w, false).total;
+        return static_cast<size_t>(kSmemBytes) + 16 + heat_stream_layout(out_h, out_w, false, kFusedEnergyWarps).total;
     }
 };
 
@@ -178,8 +177,8 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* mfcc_o
     const int heat_h = HH ? HH : heat_out.out_h, heat_w = HW ? HW : heat_out.out_w;
     if (HEAT_VEC != 0) {
         unsigned char* heat_base = reinterpret_cast<unsigned char*>(&sh) + ((sizeof(FusedShared) + 15) & ~size_t(15));
-        hs = heat_smem_carve(heat_base, heat_stream_layout(heat_h, heat_w, false), heat_h, heat_w);
-        heat_taps_init(hs, heat_h, heat_w, et);
+        hs = heat_smem_carve(heat_base, heat_stream_layout(heat_h, heat_w, false, kFusedEnergyWarps), heat_h, heat_w);
+        heat_taps_init<kFusedEnergyThreads>(hs, heat_h, heat_w, et);
         energy_group_sync();
     }
     for (unsigned int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++it) {
@@ -222,14 +221,15 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* mfcc_o
         }
         energy_group_sync();      // sh.map is rewritten for the next frame
         if (HEAT_VEC != 0) {
-            double e[kHeatPerThread];
+            constexpr int kPerThread = HeatPerThread<kFusedEnergyThreads>::value;
+            double e[kPerThread];
 #pragma unroll
-            for (int i = 0; i < kHeatPerThread; ++i) {
-                const int p = et + i * kStreamThreads;
+            for (int i = 0; i < kPerThread; ++i) {
+                const int p = et + i * kFusedEnergyThreads;
                 e[i] = p < kFramePixels ? sh.map[p] : CUDART_NAN;
             }
             // (heat_phase's first barrier comes after these reads, so no thread starts the next frame's map before them)
-            heat_phase<HEAT_VEC == 0 ? 2 : HEAT_VEC, HW, HH>(
+            heat_phase<kFusedEnergyThreads, HEAT_VEC == 0 ? 2 : HEAT_VEC, HW, HH>(
                 e, hs, sh.red64, sh.red32, heat_h, heat_w,
                 heat_out.heat + static_cast<size_t>(frame) * heat_h * heat_w, et, chunk_it, [] { energy_group_sync(); }, [] {});
         }

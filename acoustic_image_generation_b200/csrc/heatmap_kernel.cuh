@@ -300,8 +300,8 @@ heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int o
 
 
 // ---- heat_stream_kernel ---------------------------------------------------------------------------------------------
-// 256 threads = 8 warps (= 4 warp pairs in the energy phase), two CTAs per SM so that one CTA's float64 phase overlaps the
-// other's store phase.  Per frame:
+// 384 threads = 12 warps (= 6 warp pairs in the energy phase), two CTAs per SM so that one CTA's float64 phase overlaps the
+// other's store phase (24 warps per SM: with 16 the passes were latency-bound, profiles/r02_ncu_heat_stream.csv).  Per frame:
 //   1. energies: loaded (and prefetched a frame ahead) or computed in place (FUSED)
 //   2. float64 min / max of the 1728 energies, t = (e - min) / (max - min) as float32            (as heatmap_fast_kernel)
 //   3. horizontal pass once into 36 rows of out_w floats
@@ -312,9 +312,10 @@ heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int o
 //      needs no CTA-wide barrier at all.
 // Requirements (checked by the host): out_w even, out_h * out_w a multiple of 4, heat 16-byte aligned - then every
 // row pair starts on a 16-byte boundary and is a 16-byte multiple long.  Other shapes run heatmap_fast_kernel.
-constexpr int kStreamThreads = 256;
+constexpr int kStreamThreads = 384;                  // 12 warps: 1728 pixels = 9 rounds of 6 warp pairs, 36 source rows = 3 per warp
 constexpr int kStreamWarps = kStreamThreads / 32;
 constexpr int kStreamPairs = kStreamWarps / 2;
+constexpr int kHeatMaxWarps = 12;                    // size of the reduction scratch of heat_phase
 
 struct EnergyPhaseShared {             // FUSED: lives in the staging area, which is idle while a frame's energies are computed
     double map[kFramePixels];
@@ -330,12 +331,12 @@ struct HeatStreamLayout {
     int wp;                 // row stride of the 36 blended rows (out_w rounded up to 4)
     unsigned int off_rows, off_stage, off_taps, total;
 };
-__host__ __device__ inline HeatStreamLayout heat_stream_layout(int out_h, int out_w, bool fused) {
+__host__ __device__ inline HeatStreamLayout heat_stream_layout(int out_h, int out_w, bool fused, int warps = kStreamWarps) {
     HeatStreamLayout l;
     l.wp = (out_w + 3) & ~3;
     l.off_rows = kFramePixels * 4;                                          // after t[1728]
     l.off_stage = l.off_rows + kFrameH * l.wp * 4;
-    unsigned int stage = kStreamWarps * 2 * 2 * out_w * 4;                  // per warp: 2 buffers of 2 rows
+    unsigned int stage = warps * 2 * 2 * out_w * 4;                         // per warp: 2 buffers of 2 rows
     if (fused && stage < sizeof(EnergyPhaseShared)) stage = sizeof(EnergyPhaseShared);
     l.off_taps = l.off_stage + ((stage + 15u) & ~15u);
     l.total = l.off_taps + (out_w + out_h) * 8;
@@ -370,7 +371,7 @@ __device__ __forceinline__ unsigned long long norm2(unsigned long long pa, unsig
 struct HeatSmem {              // carved out of dynamic shared memory (heat_stream_layout)
     float* t;                  // [1728] frame-normalised energies
     float* rows;               // [36][wp] horizontally blended rows
-    float* stage;              // [8 warps][2 buffers][2 rows][out_w] staging slots of the bulk copies
+    float* stage;              // [warps][2 buffers][2 rows][out_w] staging slots of the bulk copies
     float* wx; float* wy;      // [out_w], [out_h] tap weights
     int* x0; int* y0;          // [out_w], [out_h] tap indices (lo | hi << 16; y0 bit 31 = edge row of its source-row pair)
     int wp;
@@ -387,14 +388,15 @@ __device__ __forceinline__ HeatSmem heat_smem_carve(unsigned char* base, const H
     s.wp = lay.wp;
     return s;
 }
-// Called once per CTA by the kStreamThreads threads that run the heat phase (index tid); synchronise before first use.
+// Called once per CTA by the THREADS threads that run the heat phase (index tid); synchronise before first use.
+template <int THREADS>
 __device__ __forceinline__ void heat_taps_init(const HeatSmem& s, int out_h, int out_w, int tid) {
-    for (int d = tid; d < out_w; d += kStreamThreads) {
+    for (int d = tid; d < out_w; d += THREADS) {
         int i0, i1; double w;
         linear_tap(d, kFrameW, out_w, &i0, &i1, &w);
         s.x0[d] = i0 | (i1 << 16); s.wx[d] = static_cast<float>(w);
     }
-    for (int d = tid; d < out_h; d += kStreamThreads) {
+    for (int d = tid; d < out_h; d += THREADS) {
         int i0, i1; double w;
         linear_tap(d, kFrameH, out_h, &i0, &i1, &w);
         int p0, p1, n0, n1; double wn;                  // bit 31: first / last output row of its source-row pair (see heatmap_fast_kernel)
@@ -405,19 +407,23 @@ __device__ __forceinline__ void heat_taps_init(const HeatSmem& s, int out_h, int
     }
 }
 
-constexpr int kHeatPerThread = (kFramePixels + kStreamThreads - 1) / kStreamThreads;     // 7 (6.75)
+// pixels of the frame held by each of THREADS threads (thread tid owns pixels tid + THREADS * i)
+template <int THREADS>
+struct HeatPerThread { static constexpr int value = (kFramePixels + THREADS - 1) / THREADS; };
 
-// Steps 2-5 of the list above for one frame whose 1728 energies the kStreamThreads threads hold in e[] (thread tid owns
-// pixels tid + 256 i).  W, H: the output size as template constants (0 = run-time size): the reference's two sizes,
+// Steps 2-5 of the list above for one frame whose 1728 energies the THREADS threads hold in e[] (thread tid owns
+// pixels tid + THREADS i).  W, H: the output size as template constants (0 = run-time size): the reference's two sizes,
 // 298 x 224 (showimages.py:147) and 224 x 224 (BASELINE configs[2]), are instantiated with constants, every column loop
 // then unrolls completely with immediate offsets - the run-time-size build spent half of its instructions on loop
 // bounds and address arithmetic (profiles/r02_ncu_stage2_kernels.csv).  `sync` is the barrier of the participating
 // threads, `after_t` runs once the energies have been consumed (the stand-alone kernel prefetches the next frame's there).
 // chunk_it is the calling warp's running chunk counter (selects its staging buffer; survives across frames).
-template <int VEC, int W, int H, typename Sync, typename AfterT>
-__device__ __forceinline__ void heat_phase(const double (&e)[kHeatPerThread], const HeatSmem& s, double (*red64)[kStreamWarps],
-                                           float (*red32)[kStreamWarps], int out_h_rt, int out_w_rt, float* dst, int tid,
-                                           unsigned int& chunk_it, Sync sync, AfterT after_t) {
+template <int THREADS, int VEC, int W, int H, typename Sync, typename AfterT>
+__device__ __forceinline__ void heat_phase(const double (&e)[HeatPerThread<THREADS>::value], const HeatSmem& s,
+                                           double (*red64)[kHeatMaxWarps], float (*red32)[kHeatMaxWarps], int out_h_rt,
+                                           int out_w_rt, float* dst, int tid, unsigned int& chunk_it, Sync sync, AfterT after_t) {
+    constexpr int kWarps = THREADS / 32, kPerThread = HeatPerThread<THREADS>::value;
+    static_assert(kWarps <= kHeatMaxWarps, "reduction scratch too small");
     const int out_h = H ? H : out_h_rt, out_w = W ? W : out_w_rt;
     const int warp = tid >> 5, lane = tid & 31;
     const int wp = s.wp;
@@ -438,18 +444,18 @@ __device__ __forceinline__ void heat_phase(const double (&e)[kHeatPerThread], co
     // 2. frame min / max in float64, t = (e - min) / (max - min) as float32
     double lo = CUDART_INF, hi = -CUDART_INF;
 #pragma unroll
-    for (int i = 0; i < kHeatPerThread; ++i) { lo = fmin(lo, e[i]); hi = fmax(hi, e[i]); }
+    for (int i = 0; i < kPerThread; ++i) { lo = fmin(lo, e[i]); hi = fmax(hi, e[i]); }
     lo = warp_min(lo); hi = warp_max(hi);
     sync();                               // the previous frame's readers of red64 / t / rows are done
     if (lane == 0) { red64[0][warp] = lo; red64[1][warp] = hi; }
     sync();
     lo = red64[0][0]; hi = red64[1][0];
 #pragma unroll
-    for (int w = 1; w < kStreamWarps; ++w) { lo = fmin(lo, red64[0][w]); hi = fmax(hi, red64[1][w]); }
+    for (int w = 1; w < kWarps; ++w) { lo = fmin(lo, red64[0][w]); hi = fmax(hi, red64[1][w]); }
     const double span = hi - lo;
 #pragma unroll
-    for (int i = 0; i < kHeatPerThread; ++i) {
-        const int p = tid + i * kStreamThreads;
+    for (int i = 0; i < kPerThread; ++i) {
+        const int p = tid + i * THREADS;
         if (p < kFramePixels) s.t[p] = span > 0.0 ? static_cast<float>((e[i] - lo) / span) : 0.f;
     }
     after_t();
@@ -460,7 +466,7 @@ __device__ __forceinline__ void heat_phase(const double (&e)[kHeatPerThread], co
         const float wx = s.wx[x];
         const int c0 = xi & 0xffff, c1 = xi >> 16;
 #pragma unroll
-        for (int r = warp; r < kFrameH; r += kStreamWarps) {
+        for (int r = warp; r < kFrameH; r += kWarps) {
             const float u = s.t[r * kFrameW + c0], v = s.t[r * kFrameW + c1];
             s.rows[r * wp + x] = fmaf(v - u, wx, u);
         }
@@ -468,7 +474,7 @@ __device__ __forceinline__ void heat_phase(const double (&e)[kHeatPerThread], co
     sync();
     // 4. min / max of the up-sampled image
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-    for (int y = warp; y < out_h; y += kStreamWarps) {
+    for (int y = warp; y < out_h; y += kWarps) {
         const int yi = s.y0[y];
         if (yi >= 0) continue;                                // interior row of its pair: cannot hold an extreme
         const float wy = s.wy[y];
@@ -481,7 +487,7 @@ __device__ __forceinline__ void heat_phase(const double (&e)[kHeatPerThread], co
     sync();
     mn = red32[0][0]; mx = red32[1][0];
 #pragma unroll
-    for (int w = 1; w < kStreamWarps; ++w) { mn = fminf(mn, red32[0][w]); mx = fmaxf(mx, red32[1][w]); }
+    for (int w = 1; w < kWarps; ++w) { mn = fminf(mn, red32[0][w]); mx = fmaxf(mx, red32[1][w]); }
     // a constant frame gives 0/0 = NaN, like the reference's (x - min) / (max - min)
     const float inv = (span > 0.0 && mx > mn) ? 1.f / (mx - mn) : CUDART_NAN_F;
     const unsigned long long nmn2 = pack2(make_float2(-mn, -mn)), inv2 = pack2(make_float2(inv, inv));
@@ -489,7 +495,7 @@ __device__ __forceinline__ void heat_phase(const double (&e)[kHeatPerThread], co
     float* my_stage = s.stage + warp * 4 * out_w;                 // [2 buffers][2 rows][out_w]
     const uint32_t my_stage_addr = smem_u32(my_stage);
     const int n_pairs = (out_h + 1) / 2;
-    for (int q = warp; q < n_pairs; q += kStreamWarps, ++chunk_it) {
+    for (int q = warp; q < n_pairs; q += kWarps, ++chunk_it) {
         const unsigned int buf = chunk_it & 1u;
         if (chunk_it >= 2u) {                                 // the copy issued two chunks ago has finished reading this buffer
             if (lane == 0) bulk_wait_read<1>();
@@ -547,8 +553,8 @@ template <bool FUSED, int VEC, int W, int H>
 __global__ void __launch_bounds__(kStreamThreads, 2)
 heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ double s_red64[2][kStreamWarps];
-    __shared__ float s_red32[2][kStreamWarps];
+    __shared__ double s_red64[2][kHeatMaxWarps];
+    __shared__ float s_red32[2][kHeatMaxWarps];
     __shared__ EnergyTables s_tab;
     const int out_h = H ? H : a.out_h, out_w = W ? W : a.out_w;
     const HeatStreamLayout lay = heat_stream_layout(out_h, out_w, FUSED);
@@ -556,11 +562,12 @@ heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
     EnergyPhaseShared& eph = *reinterpret_cast<EnergyPhaseShared*>(s_raw + lay.off_stage);
     const int tid = threadIdx.x, lane = tid & 31;
     if (FUSED) load_energy_tables(s_tab, tid, kStreamThreads);
-    heat_taps_init(hs, out_h, out_w, tid);
-    double e[kHeatPerThread];
+    heat_taps_init<kStreamThreads>(hs, out_h, out_w, tid);
+    constexpr int kPerThread = HeatPerThread<kStreamThreads>::value;
+    double e[kPerThread];
     auto fetch = [&](long long frame) {
 #pragma unroll
-        for (int i = 0; i < kHeatPerThread; ++i) {
+        for (int i = 0; i < kPerThread; ++i) {
             const int p = tid + i * kStreamThreads;
             e[i] = (frame < a.n_frames && p < kFramePixels) ? __ldcs(a.energy_in + frame * kFramePixels + p) : CUDART_NAN;
         }
@@ -597,13 +604,13 @@ heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
                         s.mask[0][frame * kFramePixels + p] = eph.map[p] > mean ? 1 : 0;
             }
 #pragma unroll
-            for (int i = 0; i < kHeatPerThread; ++i) {
+            for (int i = 0; i < kPerThread; ++i) {
                 const int p = tid + i * kStreamThreads;
                 e[i] = p < kFramePixels ? eph.map[p] : CUDART_NAN;
             }
         }
         // (FUSED: heat_phase's first barrier also orders the reads of eph.map above before the staging area is written)
-        heat_phase<VEC, W, H>(e, hs, s_red64, s_red32, out_h, out_w, a.heat + frame * frame_values, tid, chunk_it,
+        heat_phase<kStreamThreads, VEC, W, H>(e, hs, s_red64, s_red32, out_h, out_w, a.heat + frame * frame_values, tid, chunk_it,
                               [] { __syncthreads(); },
                               [&] { if (!FUSED) fetch(frame + gridDim.x); });   // next frame's energies arrive during the passes
     }
