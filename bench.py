@@ -436,7 +436,8 @@ def config_c3(torch, aig, path, dev):
 def config_c4(torch, dist, aig, path, dev, power, half, rank, world, mask_blocks):
     """configs[3]: a stream of 10 s clips at 30 fps (300 frames), MFCC + energy + per-clip and global AUC, sharded by clip."""
     from acoustic_image_generation_b200 import sharding
-    frames_per_clip, clips_per_rank = 300, 8
+    frames_per_clip = 300
+    clips_per_rank = min(8, half // frames_per_clip)     # the clips are cut from the two halves of the resident ring
     n_clips = clips_per_rank * world
     c0, c1, _, _ = sharding.shard_clips(n_clips, frames_per_clip, rank, world)
     n = (c1 - c0) * frames_per_clip                      # frame pairs of this rank: ring frames [0, n) vs [half, half + n)
@@ -709,7 +710,8 @@ def run_gpu(args):
     del h_power, h_out
 
     configs = {}
-    configs['C4_clip_stream'] = config_c4(torch, dist, aig, path, dev, power, half, rank, world, mask_blocks)
+    if not args.no_configs and half >= 300:          # collective at N > 1: every rank takes the same branch
+        configs['C4_clip_stream'] = config_c4(torch, dist, aig, path, dev, power, half, rank, world, mask_blocks)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -918,7 +920,7 @@ def main():
     ap.add_argument('--sustain-seconds', type=float, default=3.2, help='length of the sustained loop (0 = skip)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='CPU baseline time budget')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-configs', action='store_true', help='skip the C1 / C3 / loader sub-records')
+    ap.add_argument('--no-configs', action='store_true', help='skip the C1 / C3 / C4 / loader sub-records')
     ap.add_argument('--single-process', action='store_true', help='one process drives all --gpus devices (AcousticPathGroup)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     args = ap.parse_args()
