@@ -14,6 +14,7 @@ or on the host when NCCL is absent.  Frames are independent, so every result equ
 from __future__ import annotations
 
 import ctypes
+import threading
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -77,10 +78,31 @@ class AcousticPathGroup:
                 out.append((i, lo, hi))
         return out
 
-    def _run(self, n, fn):
-        """fn(device index, path, lo, hi) for every shard, one host thread per device; re-raises the first failure."""
-        futures = [self._pool.submit(fn, i, self.paths[i], lo, hi) for i, lo, hi in self.shards(n)]
-        return [f.result() for f in futures]
+    def _run(self, n, fn, chunk=None):
+        """fn(device index, path, lo, hi) over [0, n), one host thread per device; re-raises the first failure.
+
+        ``chunk=None``: one contiguous shard per device (``shards``).  ``chunk=c``: the frames are cut into pieces of c
+        and every device thread takes the next piece when it has finished its last one.  On boxes whose GPUs do not see
+        the same host bandwidth (profiles/r02_h2d_scale.txt: 23 GB/s for four of the eight links, 36 GB/s for the other
+        four when all run at once) equal shards finish with the slowest link while dynamic pieces keep every link busy
+        to the end; results do not depend on which device computed which piece."""
+        if chunk is None or len(self.paths) == 1 or n <= chunk:
+            futures = [self._pool.submit(fn, i, self.paths[i], lo, hi) for i, lo, hi in self.shards(n)]
+            return [f.result() for f in futures]
+        pieces = [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
+        lock, state = threading.Lock(), {'next': 0}
+
+        def worker(i):
+            out = []
+            while True:
+                with lock:
+                    k = state['next']
+                    state['next'] = k + 1
+                if k >= len(pieces):
+                    return out
+                out.append(fn(i, self.paths[i], *pieces[k]))
+        futures = [self._pool.submit(worker, i) for i in range(len(self.paths))]
+        return [r for f in futures for r in f.result()]
 
     def synchronize(self):
         for p in self.paths:
@@ -99,9 +121,10 @@ class AcousticPathGroup:
         return arr.reshape((arr.size // per,) + tuple(shape_tail))
 
     # -- stages 1 + 2 -------------------------------------------------------------------------
-    def mfcc_energy(self, power, flip=False, normalize_first=True, out=None):
+    def mfcc_energy(self, power, flip=False, normalize_first=True, out=None, chunk_frames=64):
         """[N, 36, 48, 512] float32 spectra (NumPy) -> (mfcc f32 [N,36,48,12], energy f64 [N,36,48], mask u8 [N,36,48]),
-        frames sharded over the devices; ``out`` supplies the result arrays (e.g. pinned)."""
+        frames spread over the devices in pieces of ``chunk_frames`` taken dynamically (None: one equal shard per
+        device); ``out`` supplies the result arrays (e.g. pinned)."""
         power = self._host(power, np.float32, (FRAME_H, FRAME_W, FFT_LEN))
         n = len(power)
         if out is None:
@@ -109,7 +132,7 @@ class AcousticPathGroup:
                    np.empty((n, FRAME_H, FRAME_W), np.uint8))
         mfcc, energy, mask = out
         self._run(n, lambda i, p, lo, hi: p.mfcc_energy(power[lo:hi], flip=flip, normalize_first=normalize_first,
-                                                       out=(mfcc[lo:hi], energy[lo:hi], mask[lo:hi])))
+                                                       out=(mfcc[lo:hi], energy[lo:hi], mask[lo:hi])), chunk=chunk_frames)
         return mfcc, energy, mask
 
     def energy_heatmap(self, images, normalize_first=False, out_h=HEAT_H, out_w=HEAT_W):

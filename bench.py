@@ -883,6 +883,10 @@ def run_single_process(args):
     for _ in range(args.e2e_steps):
         group.mfcc_energy(np_power, flip=True, normalize_first=True, out=np_out)
     e2e_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        group.mfcc_energy(np_power, flip=True, normalize_first=True, out=np_out, chunk_frames=None)
+    e2e_equal_s = time.perf_counter() - t0
     single = group.paths[0].mfcc_energy(np_power[:RING_BLOCK], flip=True, normalize_first=True)
     same = all(np.array_equal(x, y[:RING_BLOCK]) for x, y in zip(single, np_out))
     rates = aig.success_rates(totals[:-1], max(int(totals[-1]), 1))
@@ -894,7 +898,9 @@ def run_single_process(args):
         'counts_merged_by': 'aig_group_allreduce_counts (ncclCommInitAll)' if group.nccl else 'host sum',
         'e2e': {'value': e2e_frames * args.e2e_steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': e2e_frames * IN_BYTES,
                 'd2h_bytes_per_step': e2e_frames * OUT_BYTES, 'frames_per_step': e2e_frames, 'steps': args.e2e_steps,
-                'api': 'AcousticPathGroup.mfcc_energy(pinned numpy): one host call, frames sharded over %d devices' % n_dev,
+                'api': 'AcousticPathGroup.mfcc_energy(pinned numpy): one host call, frames spread over %d devices in 64-frame pieces '
+                       'taken dynamically' % n_dev,
+                'value_with_equal_shards': e2e_frames * args.e2e_steps / e2e_equal_s,
                 'sharded_result_equals_one_gpu_result': bool(same)},
         'gpu_launches': int(launches), 'clocks': clocks,
         'result': {'auc': aig.auc(THRESHOLDS, rates), 'num': int(totals[-1]), 'pos': [int(v) for v in totals[:-1]],

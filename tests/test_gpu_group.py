@@ -45,6 +45,9 @@ def test_group_results_equal_one_gpu_bitwise(n_devices):
         got = group.mfcc_energy(power, flip=True, normalize_first=True)
         for a, b in zip(got, chain):
             assert np.array_equal(a, b)
+        dyn = group.mfcc_energy(power, flip=True, normalize_first=True, chunk_frames=2)     # pieces taken dynamically
+        for a, b in zip(dyn, chain):
+            assert np.array_equal(a, b)
         inter, union = group.add_acivw_batch(real, recon)
         assert np.array_equal(inter, acivw[0]) and np.array_equal(union, acivw[1])
         res = group.finish()
