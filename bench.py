@@ -100,9 +100,9 @@ def base_streams(n):
             synth.structured_power_frames(n, 1, LAYOUT_SEED, STREAM_SHIFT))
 
 
-def cpu_chain(oracle, stream_a, stream_b):
-    """The reference path on the host for one sample: get_feats -> flip -> min-max -> find_logen -> mask -> IoU -> counts."""
-    power = np.concatenate([stream_a, stream_b], 0)
+def cpu_chain(oracle, power):
+    """The reference path on the host for one sample (first half = stream A, second half = stream B):
+    get_feats -> flip -> min-max -> find_logen -> mask -> IoU -> counts."""
     mfcc = oracle.mfcc_image(power, flip=True)
     energy, mask = oracle.energy_stage(mfcc, normalize_first=True)
     half = len(mask) // 2
@@ -125,14 +125,14 @@ def time_cpu(steps, warmup, budget_s=None, streams=None):
     use_all_host_threads()
     half = CPU_SAMPLE_FRAMES // 2
     a, b = streams if streams is not None else base_streams(half)
-    a, b = a[:half], b[:half]                 # frames 0..7 of each stream: 16 frames = BASELINE configs[0]
+    power = np.concatenate([a[:half], b[:half]], 0)    # frames 0..7 of each stream: 16 frames = BASELINE configs[0]
     for _ in range(warmup):
-        cpu_chain(oracle, a, b)
+        cpu_chain(oracle, power)
     times = []
     t_all = time.perf_counter()
     for _ in range(steps):
         t0 = time.perf_counter()
-        cpu_chain(oracle, a, b)
+        cpu_chain(oracle, power)
         times.append(time.perf_counter() - t0)
         if budget_s is not None and time.perf_counter() - t_all > budget_s and len(times) >= 3:
             break
@@ -141,10 +141,10 @@ def time_cpu(steps, warmup, budget_s=None, streams=None):
     try:                                     # the same chain on one BLAS thread, a 3 s sample
         from threadpoolctl import threadpool_limits
         with threadpool_limits(limits=1, user_api='blas'):
-            cpu_chain(oracle, a, b)
+            cpu_chain(oracle, power)
             t1, n1 = time.perf_counter(), 0
             while time.perf_counter() - t1 < 3.0:
-                cpu_chain(oracle, a, b)
+                cpu_chain(oracle, power)
                 n1 += 1
             single = CPU_SAMPLE_FRAMES * n1 / (time.perf_counter() - t1)
     except Exception:

@@ -116,7 +116,10 @@ def test_config3_clip_stream_sharded_by_clip(path, frames_per_clip, n_clips):
     host_idx = idx.cpu().numpy()
     flips = 0
     for h in range(0, n, max(1, n // 40)):
-        flips += int((mask_a[h].cpu().numpy() != want_masks[host_idx[h]]).sum())
+        differing = np.argwhere(mask_a[h].cpu().numpy() != want_masks[host_idx[h]])
+        flips += len(differing)
+        for y, x in differing:                  # north star: every boundary-pixel disagreement is reported
+            print('  boundary pixel: stream frame %d (base frame %d) pixel (%d, %d)' % (h, host_idx[h], y, x))
     print('clip stream: boundary-pixel disagreements on sampled frames: %d' % flips)
     assert flips <= 8
 
@@ -157,8 +160,13 @@ def test_soak_2048_distinct_frames_invariants_and_oracle_sample(path):
     assert np.array_equal(mask_h[sample][fin], m_replay[fin])
     # and end to end against the oracle's own MFCC: count boundary flips
     with np.errstate(invalid='ignore'):
-        _, m_oracle = oracle.energy_stage(want_mfcc, normalize_first=True)
+        e_oracle, m_oracle = oracle.energy_stage(want_mfcc, normalize_first=True)
     per_frame = (mask_h[sample] != m_oracle).reshape(len(sample), -1).sum(axis=1)
+    # north star: every boundary-pixel disagreement is reported - frame, pixel, both energies and both frame means
+    for k, y, x in np.argwhere(mask_h[sample][2:] != m_oracle[2:]):
+        f = sample[2 + k]
+        print('  boundary pixel: frame %d (%d, %d)  gpu energy %.17g mean %.17g | oracle energy %.17g mean %.17g'
+              % (f, y, x, energy_h[f, y, x], mean_h[f], e_oracle[2 + k, y, x], e_oracle[2 + k].mean()))
     # sample[1] is the all-floor frame: its MFCC is mathematically 0, i.e. pure rounding noise (1e-15 in the reference's
     # float64, 1e-6 here, both far inside the 1e-4 tolerance) that the min-max normalisation then stretches to [0, 1] -
     # the reference's own mask for such a frame is noise, so it is excluded from the boundary-pixel count
