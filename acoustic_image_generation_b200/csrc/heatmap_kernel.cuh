@@ -249,10 +249,11 @@ heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int o
 #pragma unroll
         for (int w = 1; w < kHeatThreads / 32; ++w) { lo = fmin(lo, s_red64[0][w]); hi = fmax(hi, s_red64[1][w]); }
         const double span = hi - lo;
+        const double inv_span = 1.0 / span;        // one division per frame: t = (e - min) * (1 / span), rounded to float32
 #pragma unroll
         for (int i = 0; i < (kFramePixels + kHeatThreads - 1) / kHeatThreads; ++i) {
             const int p = tid + i * kHeatThreads;
-            if (p < kFramePixels) s_t[p] = span > 0.0 ? static_cast<float>((e[i] - lo) / span) : 0.f;
+            if (p < kFramePixels) s_t[p] = span > 0.0 ? static_cast<float>((e[i] - lo) * inv_span) : 0.f;
         }
         fetch(frame + gridDim.x);                                  // next frame's energies arrive during the passes below
         __syncthreads();
@@ -453,10 +454,11 @@ __device__ __forceinline__ void heat_phase(const double (&e)[HeatPerThread<THREA
 #pragma unroll
     for (int w = 1; w < kWarps; ++w) { lo = fmin(lo, red64[0][w]); hi = fmax(hi, red64[1][w]); }
     const double span = hi - lo;
+    const double inv_span = 1.0 / span;            // one division per frame, not one per energy
 #pragma unroll
     for (int i = 0; i < kPerThread; ++i) {
         const int p = tid + i * THREADS;
-        if (p < kFramePixels) s.t[p] = span > 0.0 ? static_cast<float>((e[i] - lo) / span) : 0.f;
+        if (p < kFramePixels) s.t[p] = span > 0.0 ? static_cast<float>((e[i] - lo) * inv_span) : 0.f;
     }
     after_t();
     sync();
