@@ -1,18 +1,34 @@
 // Stage 2 kernels: 12-channel acoustic image -> energy map and mean mask (the heat map is heatmap_kernel.cuh).
 //
-// energy_kernel          F4 + F5 + F7  per-frame min-max (outdoor_data_mfcc.py:672-679), find_logen
-//                        (iouenergythreshold.py:294-323) and the mean-threshold mask (:217-219).
-// energy_cluster_kernel  the same for small batches: one frame per thread-block cluster of 8 CTAs.
-// acivw_kernel           the reference's whole evaluation step (iouenergythreshold.py:213-229) in one launch: real and
-// acivw_cluster_kernel   reconstructed image -> two energy maps -> two masks -> (I, U) -> success counts.
+// stage2_kernel<1>          F4 + F5 + F7  per-frame min-max (outdoor_data_mfcc.py:672-679), find_logen
+//                           (iouenergythreshold.py:294-323) and the mean-threshold mask (:217-219).
+// stage2_cluster_kernel<1>  the same for small batches: one frame per thread-block cluster of 8 CTAs.
+// stage2_kernel<2>          the reference's whole evaluation step (iouenergythreshold.py:213-229) in one launch: real and
+// stage2_cluster_kernel<2>  reconstructed image -> two energy maps -> two masks -> (I, U) -> success counts.
 //
 // One CTA (or cluster) per frame: the per-frame reductions (min, max, mean) are CTA-local.  The energy is
 // computed in float64 like the reference (float32-stored in-place scaling, then a float64
 // 12x24 projection, exp, band sum in NumPy's pairwise order, reciprocal) so that the
 // `map > mean(map)` decision is reproduced bit for bit up to the last-ulp differences of exp()
 // and of the BLAS summation order; the float64 mean follows NumPy's pairwise summation tree
-// for 1728 elements exactly.  FP64 work per frame is ~2 MFLOP, far below the HBM time of the
-// stage-1 stream it follows, and runs on the otherwise idle FP64 pipe.
+// for 1728 elements exactly.
+//
+// Round 2, second pass: ONE THREAD PER PIXEL again, with leaner arithmetic.  tools/energy_lab.cu / energy_lab2.cu
+// measured the candidates on a B200 (gpurun_out/lab*.txt): two threads per pixel exchanging through shared memory and
+// named barriers (round 2, first pass) 10.7 M frames/s with this arithmetic, the two halves in one warp exchanging by
+// shuffles 11.5 M, one thread per pixel 13.7 M, and 14.2 M with the input staged by cp.async - against 9.6 M for the
+// pair kernel with the old arithmetic.  The FP64 pipe is the bound (tools/fp64_peak.cu: 56 DFMA/clk/SM at best, 0.87 of
+// nominal; it needs >= 12 independent operations in flight per scheduler), so what pays is fewer FP64 instructions:
+//   * the projection uses both symmetries of the basis: cos((m+1) pi (j+1/2) / 24) is (anti)symmetric under j -> 23 - j
+//     by the parity of m + 1 and, for even m + 1, again under j -> 11 - j: 24 band sums from six "couples" (j, 11 - j),
+//     j < 6, at 24 operations per couple = 144 (288 for the plain product, 168 in the first pass);
+//   * the coefficients carry the factor 2^10 / ln2, so a band sum x is already in units of the exp table's step: its
+//     integer part k (by the 1.5 * 2^52 trick) is table index and binary exponent, the remainder r = x - k is exact,
+//     and 2^(r / 1024) - 1 needs four Taylor terms with a 1024-entry table of 2^(i / 1024): 8 FP64 operations per
+//     exponential (11 in the first pass, ~17 + branches for exp()).  Same error class as before: table entry and the
+//     final FMA are rounded once each (tests/test_energy_tables_cpu.py bounds the whole thing in exact arithmetic,
+//     aig_selftest(1) compares it with CUDA's exp on the device).
+// Per pixel: 412 FP64 instructions (500 before) out of 770 (1310 before).
 #pragma once
 
 #include <cooperative_groups.h>
@@ -23,22 +39,18 @@
 namespace aig {
 
 // find_logen's constants (iouenergythreshold.py:304-308), identical to the MFCC constants.
-__constant__ double c_dct[kFilterNum * kMfccNum] = AIG_REF_DCT;      // [24][12]
+__constant__ double c_dct[kFilterNum * kMfccNum] = AIG_REF_DCT;      // [24][12], the plain path
 __constant__ double c_lifter[kMfccNum] = AIG_REF_LIFTER;
 __constant__ double c_mfnorm = AIG_REF_MFNORM;
-
-static_assert(kFramePixels % 64 == 0, "whole warp pairs drop out of the last round");
+__constant__ double c_inv_lifter[kMfccNum] = AIG_REF_INV_LIFTER;     // RN(1 / lifter[m])
 
 // NumPy pairwise-sum leaves for n = 1728: 1728 -> 864 -> 432 -> 216 -> (104, 112); every leaf is
 // summed with 8 strided accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)).
 __device__ __forceinline__ int leaf_start(int leaf) { return 216 * (leaf >> 1) + ((leaf & 1) ? 104 : 0); }
 __device__ __forceinline__ int leaf_len(int leaf) { return (leaf & 1) ? 112 : 104; }
 
-__constant__ double c_inv_lifter[kMfccNum] = AIG_REF_INV_LIFTER;     // RN(1 / lifter[m])
-__constant__ double c_exp2_table[64] = AIG_EXP2_TABLE;               // RN(2^(j/64)); kernels copy it to shared memory
-
 // v / L for a constant L with r = RN(1 / L): q0 = RN(v * r), e = v - q0 * L (exact in one FMA), q = RN(q0 + e * r).
-// By Markstein's theorem q is the correctly rounded quotient for finite v; tests/test_gpu_parity.py checks it against
+// By Markstein's theorem q is the correctly rounded quotient for finite v; aig_selftest(0) checks it against
 // __ddiv_rn for every finite float32 v and all twelve lifter constants.  Non-finite inputs never reach it: pixel_energy
 // sends such pixels down the plain path.
 __device__ __forceinline__ double div_by_lifter(double v, int m) {
@@ -48,64 +60,67 @@ __device__ __forceinline__ double div_by_lifter(double v, int m) {
     return __fma_rn(e, r, q0);
 }
 
-// The per-frame min-max normalisation (x - lo) / range in float32 (:672-679): one IEEE division per value, like the
-// reference.  (A shared-reciprocal form with one or two residual corrections was tried and rejected: against __fdiv_rn on
-// 2^34 pseudo-random triples it left 7e-5 of the quotients one ulp off - a 24-bit reciprocal is not enough - so unlike
-// the float64 division by the lifter constants it cannot replace the division exactly.)
-struct FrameNorm {
-    float lo, range;
-    __device__ __forceinline__ FrameNorm(float lo_, float range_) : lo(lo_), range(range_) {}
-    __device__ __forceinline__ float apply(float x) const { return __fdiv_rn(__fsub_rn(x, lo), range); }
+// ---- the tables of the pixel arithmetic --------------------------------------------------------------------------
+constexpr int kExpLog2 = AIG_EXP_TABLE_LOG2;                          // 1024 entries
+constexpr int kExpEntries = 1 << kExpLog2;
+constexpr double kExpMagic = 6755399441055744.0;                     // 1.5 * 2^52: rint by addition
+static_assert(kExpLog2 == 10, "the Taylor degree below is chosen for a 1024-entry table");
+
+// Couple j < 6 (bands j, 23 - j, 11 - j, 12 + j): AA over channels m = 3, 7, 11, AB over m = 1, 5, 9, B_j and B_(11-j) over
+// m = 0, 2 .. 10; all times 2^10 / ln2 (tools/gen_mel_tables.py, rounded once from the reference's float64 cosines).
+struct CoupleCoef { double aa[3], ab[3], b0[6], b1[6]; };
+__device__ const double g_couple_coef[6 * 18] = AIG_COUPLE_COEF;
+__device__ const double g_exp_poly[4] = AIG_EXP_POLY;                 // (ln2 / 1024)^n / n!, n = 1 .. 4
+__device__ const double g_exp2_table[kExpEntries] = AIG_EXP2_TABLE;   // RN(2^(i / 1024))
+
+// The tables live in SHARED memory in every kernel: the exp table is indexed by data, and shared loads of the projection
+// coefficients cannot be hoisted out of the pixel loop (loop-invariant constant-bank loads were, in the first build of
+// the pair kernels: ~100 float64 coefficients overflow the uniform registers into spilled vector registers).  All lanes
+// read the same coefficient address (one wavefront), two coefficients per LDS.128.
+struct __align__(16) EnergyTables {
+    CoupleCoef couple[6];
+    double lift[kMfccNum][2];          // {1 / lifter[m], lifter[m]}
+    double poly[4];
+    double mfnorm, pad;
+    double exp2[kExpEntries];
 };
-
-// exp(x) by table: k = rint(x * 64 / ln2), r = x - k * ln2 / 64 (two-part constant), exp(x) =
-// 2^(k >> 6) * T[k & 63] * (1 + p(r)) with a degree-6 polynomial on |r| <= ln2 / 128 (truncation 3e-20).  Worst-case
-// error just under 1 ulp (table entry + final rounding), the same class as CUDA's and NumPy's exp; 11 FP64 operations
-// instead of ~17 plus the special-case branches.  Valid for |x| <= 700 (|k| < 2^16); `out_of_range` collects the
-// violation so that the caller can redo the pixel with exp() - NaN propagates by itself.
-// The constants live in __constant__ memory so that each FMA takes its coefficient as a constant-bank operand (as
-// immediates every 64-bit coefficient costs two extra UMOVs per use).
-__constant__ double c_exp_k[9] = {AIG_EXP_64_OVER_LN2, 6755399441055744.0 /* 1.5 * 2^52: rint by addition */,
-                                  -(AIG_EXP_LN2_64_HEAD), -(AIG_EXP_LN2_64_TAIL),
-                                  1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
-
-__device__ __forceinline__ double exp_table64(double x, const double* __restrict__ table, unsigned int& out_of_range) {
-    const double t = __fma_rn(x, c_exp_k[0], c_exp_k[1]);
-    const int k = __double2loint(t);
-    out_of_range |= static_cast<unsigned int>(k + 65536) >> 17;       // non-zero iff |k| >= 2^16 (|x| > ~709)
-    const double kd = __dadd_rn(t, -c_exp_k[1]);
-    double r = __fma_rn(kd, c_exp_k[2], x);
-    r = __fma_rn(kd, c_exp_k[3], r);
-    double p = __fma_rn(r, c_exp_k[4], c_exp_k[5]);
-    p = __fma_rn(p, r, c_exp_k[6]);
-    p = __fma_rn(p, r, c_exp_k[7]);
-    p = __fma_rn(p, r, c_exp_k[8]);
-    p = __fma_rn(__dmul_rn(r, r), p, r);                              // e^r - 1
-    const double tj = table[k & 63];
-    const double y = __fma_rn(tj, p, tj);
-    return __hiloint2double(__double2hiint(y) + ((k >> 6) << 20), __double2loint(y));   // * 2^(k >> 6)
+static_assert(sizeof(CoupleCoef) == 18 * sizeof(double), "g_couple_coef is copied as is");
+__device__ __forceinline__ void load_energy_tables(EnergyTables& t, int tid, int threads) {
+    double* couple = reinterpret_cast<double*>(t.couple);
+    for (int i = tid; i < 6 * 18; i += threads) couple[i] = g_couple_coef[i];
+    for (int i = tid; i < kExpEntries; i += threads) t.exp2[i] = g_exp2_table[i];
+    if (tid < kMfccNum) { t.lift[tid][0] = c_inv_lifter[tid]; t.lift[tid][1] = c_lifter[tid]; }
+    if (tid < 4) t.poly[tid] = g_exp_poly[tid];
+    if (tid == 0) { t.mfnorm = c_mfnorm; t.pad = 0.0; }
 }
 
-// The same without the range bookkeeping: the pair kernels bound every exponent once per pixel instead
-// (|mel_j| <= sum_m |z_m| because |cos| <= 1; half_pixel sends the pixel to the plain path when that sum exceeds 700).
-__device__ __forceinline__ double exp_table64_inrange(double x, const double* __restrict__ table) {
-    const double t = __fma_rn(x, c_exp_k[0], c_exp_k[1]);
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));     // the table is read-only after the kernel's first barrier
+    return v;
+}
+
+// exp(x * ln2 / 1024) for x in table-step units, |x| < 2^20 (|x ln2 / 1024| <= 700 and more; pixel_energy guarantees it):
+// k = rint(x), r = x - k exact, result = 2^(k >> 10) * T[k & 1023] * (1 + p(r)) with p the degree-4 Taylor polynomial of
+// 2^(r / 1024) - 1 (truncation 3.7e-20).  `table` is the shared-memory byte address of EnergyTables::exp2.
+__device__ __forceinline__ double exp_units(double x, uint32_t table, const double (&poly)[4]) {
+    const double t = __dadd_rn(x, kExpMagic);
     const int k = __double2loint(t);
-    const double kd = __dadd_rn(t, -c_exp_k[1]);
-    double r = __fma_rn(kd, c_exp_k[2], x);
-    r = __fma_rn(kd, c_exp_k[3], r);
-    double p = __fma_rn(r, c_exp_k[4], c_exp_k[5]);
-    p = __fma_rn(p, r, c_exp_k[6]);
-    p = __fma_rn(p, r, c_exp_k[7]);
-    p = __fma_rn(p, r, c_exp_k[8]);
-    p = __fma_rn(__dmul_rn(r, r), p, r);
-    const double tj = table[k & 63];
-    const double y = __fma_rn(tj, p, tj);
-    return __hiloint2double(__double2hiint(y) + ((k >> 6) << 20), __double2loint(y));
+    const double r = __dadd_rn(x, -__dadd_rn(t, -kExpMagic));
+    double p = __fma_rn(poly[3], r, poly[2]);
+    p = __fma_rn(p, r, poly[1]);
+    p = __fma_rn(p, r, poly[0]);
+    const double q = __dmul_rn(p, r);                                  // 2^(r / 1024) - 1
+    const int idx = k & (kExpEntries - 1);
+    const double tj = lds_f64(table + static_cast<uint32_t>(idx) * 8u);
+    const double y = __fma_rn(tj, q, tj);
+    int hi;                                                            // * 2^(k >> 10): (k - idx) << 10 added to the high word
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(hi) : "r"(k - idx), "n"(1 << (20 - kExpLog2)), "r"(__double2hiint(y)));
+    return __hiloint2double(hi, __double2loint(y));
 }
 
 // The plain form of one pixel (IEEE divisions, exp(), straight 12-term dot products), kept out of line: it serves the
-// pixels the fast path cannot (non-finite inputs, |mel| > 700) and is what the fast path is checked against.
+// pixels the fast path cannot (non-finite inputs, huge values) and is what the fast path is checked against.
 // `raw` holds the pixel's 12 input values, already in registers: the image may alias `scaled_dst` (find_logen scales its
 // argument in place) or have been written by other warps of the same kernel (fused kernel), so it is never re-read
 // here through a read-only path.  scaled_dst may be null.
@@ -132,58 +147,127 @@ __device__ __noinline__ double pixel_energy_plain(const float (&raw)[kMfccNum], 
     return __ddiv_rn(1.0, total);
 }
 
+// The per-frame min-max normalisation with the reciprocal hoisted out of the per-value division.  With r = RN(1 / range),
+// q0 = RN(d * r), rem = d - q0 * range (exact in one FMA), q = RN(q0 + rem * r) is the correctly rounded quotient
+// (Markstein) as long as nothing over- or underflows: proven for range within 2^+-60 and q0 in [2^-40, 2^40] or d = 0
+// (aig_selftest(2) compares it with __fdiv_rn on 2^32 (d, range) pairs), IEEE division otherwise.
+//   mode 2  every value of the frame is inside that domain, no per-value test: d = x - lo lies in {0} u [2^-25 |lo|, range]
+//           (a non-zero difference of two floats is at least half an ulp of the smaller one, and lo is the frame's
+//           minimum), so |lo| >= 2^-14 range gives q0 >= 2^-40, and range >= 2^-30 keeps rem a normal number;
+//   mode 1  sane range but lo too close to zero for that guarantee (an already normalised frame): per-value test;
+//   mode 0  zero, denormal, huge or non-finite range: IEEE division (fast == false in apply()).
+struct FrameNormFast {
+    float lo, range, r;
+    int mode;
+    bool fast;
+    __device__ __forceinline__ FrameNormFast(float lo_, float range_) : lo(lo_), range(range_) {
+        const unsigned int e = (__float_as_uint(range_) >> 23) & 0xffu;
+        fast = (e - 67u) <= 120u && range_ > 0.f;
+        r = fast ? __frcp_rn(range_) : 0.f;
+        mode = !fast ? 0 : ((e >= 97u && fabsf(lo_) >= __fmul_rn(range_, 6.103515625e-05f)) ? 2 : 1);
+    }
+    __device__ __forceinline__ float apply(float x) const {
+        const float d = __fsub_rn(x, lo);
+        const float q0 = __fmul_rn(d, r);
+        // fast: range (hence r) within 2^+-60, so q0 in [2^-40, 2^40] means d within 2^+-100: nothing under- or overflows.
+        // Zero, tiny, huge and non-finite differences (comparison false for NaN) take IEEE division.
+        if (fast && q0 >= 9.094947e-13f && q0 <= 1.0995116e12f) {
+            const float rem = __fmaf_rn(-q0, range, d);
+            return __fmaf_rn(rem, r, q0);
+        }
+        return __fdiv_rn(d, range);
+    }
+    __device__ __forceinline__ float apply_mode2(float x) const {
+        const float d = __fsub_rn(x, lo);
+        const float q0 = __fmul_rn(d, r);
+        return __fmaf_rn(__fmaf_rn(-q0, range, d), r, q0);
+    }
+};
+
+__device__ __forceinline__ float max_nan_abs(float m, float a) {     // max(m, |a|), NaN if either is
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(m), "f"(fabsf(a)));
+    return r;
+}
+
+// The four exponentials of couple j: bands j, 23 - j (p) and 11 - j, 12 + j (q), "lo" the first of each pair.
+struct CoupleExp { double lo_p, hi_p, lo_q, hi_q; };
+__device__ __forceinline__ CoupleExp couple_exp(const double (&z)[kMfccNum], const CoupleCoef& c, uint32_t exp_table,
+                                                const double (&poly)[4]) {
+    double aa = __dmul_rn(z[3], c.aa[0]);                 // m + 1 = 4, 8, 12: symmetric under j -> 23 - j and j -> 11 - j
+    aa = __fma_rn(z[7], c.aa[1], aa);
+    aa = __fma_rn(z[11], c.aa[2], aa);
+    double ab = __dmul_rn(z[1], c.ab[0]);                 // m + 1 = 2, 6, 10: symmetric under j -> 23 - j, antisymmetric under j -> 11 - j
+    ab = __fma_rn(z[5], c.ab[1], ab);
+    ab = __fma_rn(z[9], c.ab[2], ab);
+    double b0 = __dmul_rn(z[0], c.b0[0]), b1 = __dmul_rn(z[0], c.b1[0]);   // odd m + 1: antisymmetric under j -> 23 - j
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+        b0 = __fma_rn(z[2 * i], c.b0[i], b0);
+        b1 = __fma_rn(z[2 * i], c.b1[i], b1);
+    }
+    const double a0 = __dadd_rn(aa, ab), a1 = __dadd_rn(aa, -ab);
+    CoupleExp e;
+    e.lo_p = exp_units(__dadd_rn(a0, b0), exp_table, poly);           // band j
+    e.hi_p = exp_units(__dadd_rn(a0, -b0), exp_table, poly);          // band 23 - j
+    e.lo_q = exp_units(__dadd_rn(a1, b1), exp_table, poly);           // band 11 - j
+    e.hi_q = exp_units(__dadd_rn(a1, -b1), exp_table, poly);          // band 12 + j
+    return e;
+}
+
 // One pixel of find_logen: optional float32 min-max normalisation (:672-679), the float64-compute /
 // float32-store scaling `mfcc /= lifter; mfcc *= mfnorm` (:310-311), the float64 projection on dct_base^T,
-// exp, the band sum in NumPy's order for n = 24 (r[k] = e[k] + e[k+8] + e[k+16], then the balanced tree
+// exp, the band sum in NumPy's order for n = 24 (r[k] = (e[k] + e[k+8]) + e[k+16], then the balanced tree
 // over r[0..7]) and the reciprocal (:313-321).  x[] is left holding the scaled float32 values.
-//
-// FP64 work is what this stage costs (and, on a board that sits at its power cap, what it costs the HBM stream next to
-// it), so the projection uses the symmetry of the basis: cos((m+1) pi (23-j+0.5) / 24) = (-1)^(m+1) cos((m+1) pi (j+0.5) / 24),
-// i.e. mel[j] = A_j + B_j and mel[23-j] = A_j - B_j with A over odd m and B over even m - 144 FMAs instead of 288.
-// The result differs from a straight 12-term dot product only in the last ulp, like one BLAS differs from another.
-// `rare` comes back non-zero when the pixel needs the plain path instead (the caller redoes it with pixel_energy_plain).
-__device__ __forceinline__ double pixel_energy(float (&x)[kMfccNum], bool normalize, const FrameNorm& norm,
-                                               const double* __restrict__ exp_table, unsigned int& rare) {
+// `rare` comes back non-zero when the pixel needs the plain path instead (the caller redoes it with pixel_energy_plain):
+// every |band sum| <= sum_m |z_m| <= 12 max_m |z_m| (|cos| <= 1), so max |z_m| <= 58 keeps all 24 table exponentials in
+// range; anything else - huge values, Inf, NaN (max.NaN propagates it, the comparison is then false) - is rare.  Every
+// kernel uses this one function, so all of them send exactly the same pixels down the plain path and agree bit for bit.
+__device__ __forceinline__ double pixel_energy(float (&x)[kMfccNum], bool normalize, const FrameNormFast& norm,
+                                               const EnergyTables& tab, uint32_t exp_table, unsigned int& rare) {
+    if (normalize) {                                      // float32, as TF; a frame-uniform choice of the division's form
+        if (norm.mode == 2) {
+#pragma unroll
+            for (int m = 0; m < kMfccNum; ++m) x[m] = norm.apply_mode2(x[m]);
+        } else {
+#pragma unroll
+            for (int m = 0; m < kMfccNum; ++m) x[m] = norm.apply(x[m]);
+        }
+    }
     double z[kMfccNum];
-    float sum_abs = 0.f;                // NaN / Inf in, NaN / Inf out
+    float big = 0.f;
+    const double mfnorm = tab.mfnorm;
 #pragma unroll
     for (int m = 0; m < kMfccNum; ++m) {
-        float v = x[m];
-        if (normalize) v = norm.apply(v);                                     // float32, as TF
-        v = __double2float_rn(div_by_lifter(static_cast<double>(v), m));
-        v = __double2float_rn(__dmul_rn(static_cast<double>(v), c_mfnorm));
+        const double d = static_cast<double>(x[m]), r = tab.lift[m][0];
+        const double q0 = __dmul_rn(d, r);                                                  // div_by_lifter
+        float v = __double2float_rn(__fma_rn(__fma_rn(-q0, tab.lift[m][1], d), r, q0));
+        v = __double2float_rn(__dmul_rn(static_cast<double>(v), mfnorm));
         x[m] = v;
-        sum_abs += fabsf(v);
+        big = max_nan_abs(big, v);
         z[m] = static_cast<double>(v);
     }
-    // Every |mel_j| <= sum_m |z_m| (|cos| <= 1): at most 700 keeps all 24 table exponentials in range; anything else -
-    // huge values, Inf, NaN (the comparison is false for NaN) - takes the plain path.  One float32 test per pixel
-    // instead of range bookkeeping in each of the 24 exponentials; the pair kernels below use the same criterion, so
-    // every kernel sends exactly the same pixels down the plain path.
-    rare = !(sum_abs <= 700.f);
-    double r[8], third[8];
+    rare = !(big <= 58.f);
+    double poly[4];
 #pragma unroll
-    for (int j = 0; j < 12; ++j) {
-        double a = 0.0, b = 0.0;
-#pragma unroll
-        for (int m = 0; m < kMfccNum; m += 2) {
-            b = fma(z[m], c_dct[j * kMfccNum + m], b);                        // m + 1 odd: antisymmetric in j <-> 23 - j
-            a = fma(z[m + 1], c_dct[j * kMfccNum + m + 1], a);                // m + 1 even: symmetric
-        }
-        const double e_lo = exp_table64_inrange(__dadd_rn(a, b), exp_table);   // band j
-        const double e_hi = exp_table64_inrange(__dadd_rn(a, -b), exp_table);  // band 23 - j
-        if (j < 8) {
-            r[j] = e_lo;                      // first term of r[j]
-            third[7 - j] = e_hi;              // band 23 - j = 16 + (7 - j): third term of r[7 - j]
-        } else {
-            r[j - 8] = __dadd_rn(r[j - 8], e_lo);          // band j = 8 + (j - 8): second term of r[j - 8]
-            r[15 - j] = __dadd_rn(r[15 - j], e_hi);        // band 23 - j = 8 + (15 - j): second term of r[15 - j]
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], third[k]);
-    const double total = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                                   __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (int i = 0; i < 4; ++i) poly[i] = tab.poly[i];
+    // couple j holds e[j], e[23-j], e[11-j], e[12+j];  r[k] = (e[k] + e[k+8]) + e[k+16]
+    const CoupleExp c0 = couple_exp(z, tab.couple[0], exp_table, poly);   // e0  e23 e11 e12
+    const CoupleExp c3 = couple_exp(z, tab.couple[3], exp_table, poly);   // e3  e20 e8  e15
+    const CoupleExp c4 = couple_exp(z, tab.couple[4], exp_table, poly);   // e4  e19 e7  e16
+    const double r0 = __dadd_rn(__dadd_rn(c0.lo_p, c3.lo_q), c4.hi_q);    // (e0 + e8)  + e16
+    const double r7 = __dadd_rn(__dadd_rn(c4.lo_q, c3.hi_q), c0.hi_p);    // (e7 + e15) + e23
+    const double r3 = __dadd_rn(__dadd_rn(c3.lo_p, c0.lo_q), c4.hi_p);    // (e3 + e11) + e19
+    const double r4 = __dadd_rn(__dadd_rn(c4.lo_p, c0.hi_q), c3.hi_p);    // (e4 + e12) + e20
+    const CoupleExp c1 = couple_exp(z, tab.couple[1], exp_table, poly);   // e1  e22 e10 e13
+    const CoupleExp c2 = couple_exp(z, tab.couple[2], exp_table, poly);   // e2  e21 e9  e14
+    const CoupleExp c5 = couple_exp(z, tab.couple[5], exp_table, poly);   // e5  e18 e6  e17
+    const double r1 = __dadd_rn(__dadd_rn(c1.lo_p, c2.lo_q), c5.hi_q);    // (e1 + e9)  + e17
+    const double r6 = __dadd_rn(__dadd_rn(c5.lo_q, c2.hi_q), c1.hi_p);    // (e6 + e14) + e22
+    const double r2 = __dadd_rn(__dadd_rn(c2.lo_p, c1.lo_q), c5.hi_p);    // (e2 + e10) + e18
+    const double r5 = __dadd_rn(__dadd_rn(c5.lo_p, c1.hi_q), c2.hi_p);    // (e5 + e13) + e21
+    const double total = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
+                                   __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
     return __ddiv_rn(1.0, total);
 }
 
@@ -212,21 +296,27 @@ __global__ void selftest_division_kernel(unsigned long long* out) {
     if (bad_after_store) atomicAdd(out + 1, bad_after_store);
 }
 
-// exp_table64 against CUDA's exp() (itself <= 1 ulp) on n points spread over [-700, 700] plus a dense sweep of
-// [-12, 12], the range find_logen's inputs produce: out[0] = points differing, out[1] = max difference in ulps,
-// out[2] = points compared.
+// exp_units against CUDA's exp() (itself <= 1 ulp) on n points spread over [-700, 700] plus a dense sweep of
+// [-12, 12], the range find_logen's inputs produce.  The argument is given in table-step units x; its natural value
+// u = x ln2 / 1024 is not a double, so the reference is exp(u_hi) (1 + u_lo) with u = u_hi + u_lo from the double-double
+// form of ln2 / 1024.  out[0] = points differing, out[1] = max difference in ulps, out[2] = points compared.
 __global__ void selftest_exp_kernel(unsigned long long n, unsigned long long* out) {
-    __shared__ double s_exp[64];
-    if (threadIdx.x < 64) s_exp[threadIdx.x] = c_exp2_table[threadIdx.x];
+    __shared__ double s_exp[kExpEntries];
+    for (int i = threadIdx.x; i < kExpEntries; i += blockDim.x) s_exp[i] = g_exp2_table[i];
     __syncthreads();
+    const uint32_t table = smem_u32(s_exp);
+    const double poly[4] = {g_exp_poly[0], g_exp_poly[1], g_exp_poly[2], g_exp_poly[3]};
+    const double step_hi = AIG_EXP_STEP_HI, step_lo = AIG_EXP_STEP_LO;
     unsigned long long differ = 0, max_ulps = 0, count = 0;
     for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < 2 * n;
          i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
-        const double u = static_cast<double>(i % n) / static_cast<double>(n);           // [0, 1)
-        const double x = (i < n) ? (u * 1400.0 - 700.0) : (u * 24.0 - 12.0);
-        unsigned int oob = 0;
-        const long long a = __double_as_longlong(exp_table64(x, s_exp, oob)), b = __double_as_longlong(exp(x));
-        if (oob) { differ += 1ull << 40; }                      // must never trigger on [-700, 700]
+        const double f = static_cast<double>(i % n) / static_cast<double>(n);           // [0, 1)
+        const double nat = (i < n) ? (f * 1400.0 - 700.0) : (f * 24.0 - 12.0);
+        const double x = nat / step_hi;                                                  // some double in table-step units
+        const double u_hi = __dmul_rn(x, step_hi);
+        const double u_lo = __fma_rn(x, step_lo, __fma_rn(x, step_hi, -u_hi));
+        const double e = exp(u_hi);
+        const long long a = __double_as_longlong(exp_units(x, table, poly)), b = __double_as_longlong(__fma_rn(e, u_lo, e));
         const unsigned long long d = static_cast<unsigned long long>(a > b ? a - b : b - a);
         differ += d != 0;
         max_ulps = d > max_ulps ? d : max_ulps;
@@ -238,13 +328,13 @@ __global__ void selftest_exp_kernel(unsigned long long n, unsigned long long* ou
 }
 
 // np.mean over the 1728 doubles of s_map, bit-compatible with NumPy's pairwise summation.  Called by a
-// thread group of at least 128 threads (index t within the group); `sync` is the group's barrier.
+// thread group of `threads` threads (index t within the group); `sync` is the group's barrier.
 // Returns the mean in every thread of the group.
 template <typename Sync>
 __device__ __forceinline__ double frame_mean(const double* s_map, double (*s_part)[8], double* s_leaf,
-                                             double* s_mean, int t, Sync sync) {
-    if (t < 128) {
-        const int leaf = t >> 3, k = t & 7;
+                                             double* s_mean, int t, int threads, Sync sync) {
+    for (int u = t; u < 128; u += threads) {
+        const int leaf = u >> 3, k = u & 7;
         const double* a = s_map + leaf_start(leaf);
         const int len = leaf_len(leaf);
         double r = a[k];
@@ -273,19 +363,8 @@ __device__ __forceinline__ double frame_mean(const double* s_map, double (*s_par
 
 
 // =====================================================================================================================
-// Two threads per pixel (energy_kernel, stage2_kernel, stage2_cluster_kernel)
+// The pixel loops and kernels
 // =====================================================================================================================
-// One thread per pixel needs ~120 registers for the float64 chain of find_logen (12 scaled values, 24 exponentials in
-// flight, the NumPy-ordered band sums): 16 warps per SM, a dependent DFMA chain in each, and the FP64 pipe sat at 43 %
-// (profiles/r01_ncu_secondary_kernels.csv) with 116 bytes of spills.  Here a pixel is shared by the same lane of two
-// adjacent warps ("halves" of a warp pair).  The 24 mel bands fall into four groups of three (j, 23 - j) basis pairs,
-//     group g = pairs {g, 7 - g, 8 + g}  ->  bands {g, 23-g, 7-g, 16+g, 8+g, 15-g}  =  all terms of r[g] and r[7-g]
-// (r[k] = (e[k] + e[k+8]) + e[k+16] is NumPy's strided partial sum for n = 24), so half 0 (groups 0, 1) produces
-// r0, r1, r6, r7 and half 1 (groups 2, 3) r2..r5 without exchanging a single exponential; only the 6 + 6 scaled float32
-// channel values and two float64 partial sums (r2 + r3, r4 + r5) cross the pair, through shared memory around two
-// 64-thread named barriers.  Every operation keeps the order of pixel_energy(), so the result is bit-identical to the
-// one-thread form the fused kernel's energy warps run.  Which half a warp is decides its constants at compile time
-// (template parameter, warp-uniform branch): every DCT coefficient stays a constant-bank operand.
 
 // Named barriers with IMMEDIATE ids.  With the id in a register ptxas must assume all 16 hardware barriers are in use
 // ("used 16 barriers"), and an SM only has 64: four CTAs per SM however few registers and shared memory they need - the
@@ -302,31 +381,6 @@ template <int MAX_ID, int THREADS>
 struct NamedBar<MAX_ID, MAX_ID, THREADS> {
     static __device__ __forceinline__ void sync(int) {
         asm volatile("bar.sync %0, %1;" ::"n"(MAX_ID), "n"(THREADS) : "memory");
-    }
-};
-
-// The per-frame min-max normalisation with the reciprocal hoisted out of the per-value division.  With r = RN(1 / range),
-// q0 = RN(d * r), rem = d - q0 * range (exact in one FMA), q = RN(q0 + rem * r) is the correctly rounded quotient
-// (Markstein) as long as nothing over- or underflows: taken when range and d are within 2^+-60, IEEE division otherwise
-// (zero, denormal, huge, non-finite).  aig_selftest(2) compares it with __fdiv_rn on 2^32 (d, range) pairs.
-struct FrameNormFast {
-    float lo, range, r;
-    bool fast;
-    __device__ __forceinline__ FrameNormFast(float lo_, float range_) : lo(lo_), range(range_) {
-        const unsigned int e = (__float_as_uint(range_) >> 23) & 0xffu;
-        fast = (e - 67u) <= 120u && range_ > 0.f;
-        r = fast ? __frcp_rn(range_) : 0.f;
-    }
-    __device__ __forceinline__ float apply(float x) const {
-        const float d = __fsub_rn(x, lo);
-        const float q0 = __fmul_rn(d, r);
-        // fast: range (hence r) within 2^+-60, so q0 in [2^-40, 2^40] means d within 2^+-100: nothing under- or overflows.
-        // Zero, tiny, huge and non-finite differences (comparison false for NaN) take IEEE division.
-        if (fast && q0 >= 9.094947e-13f && q0 <= 1.0995116e12f) {
-            const float rem = __fmaf_rn(-q0, range, d);
-            return __fmaf_rn(rem, r, q0);
-        }
-        return __fdiv_rn(d, range);
     }
 };
 
@@ -361,156 +415,64 @@ __global__ void selftest_norm_kernel(unsigned long long* out) {
     atomicAdd(out + 2, fast_taken);
 }
 
-// The constants of the pair kernels live in SHARED memory, not in the constant bank: ptxas hoists loop-invariant
-// constant-bank loads out of the pixel loop, and ~100 float64 coefficients overflow the 63 uniform registers into
-// spilled vector registers (500 bytes of local-memory traffic per pixel in the first build of these kernels).  Shared
-// loads cannot move across the pair barriers inside the loop; all lanes read the same address (one wavefront), two
-// coefficients per LDS.128.
-struct __align__(16) EnergyTables {
-    double dct[12 * kMfccNum];         // rows 0..11 of dct_base^T (the other twelve follow from the symmetry)
-    double lifter[kMfccNum];
-    double inv_lifter[kMfccNum];
-    double exp2[64];                   // 2^(j/64)
-    double mfnorm;
-};
-__device__ __forceinline__ void load_energy_tables(EnergyTables& t, int tid, int threads) {
-    for (int i = tid; i < 12 * kMfccNum; i += threads) t.dct[i] = c_dct[i];
-    for (int i = tid; i < 64; i += threads) t.exp2[i] = c_exp2_table[i];
-    if (tid < kMfccNum) { t.lifter[tid] = c_lifter[tid]; t.inv_lifter[tid] = c_inv_lifter[tid]; }
-    if (tid == 0) t.mfnorm = c_mfnorm;
-}
-
-// One (j, 23 - j) basis pair: the two exponentials exp(A + B), exp(A - B) of pixel_energy(), same operation order.
-template <int J>
-__device__ __forceinline__ void band_pair(const double (&z)[kMfccNum], const EnergyTables& tab, double& e_lo, double& e_hi) {
-    double a = 0.0, b = 0.0;
+// Pixels p_begin + gt, + THREADS, ... < p_end of one frame, one thread per pixel (gt = thread index within the group of
+// THREADS).  img / scaled / energy point at the frame; img may alias scaled (find_logen's in-place scaling), so neither
+// is read through a read-only path and a pixel's raw values are loaded before anything of that pixel is stored.  Leaves
+// map[p - p_begin] = energy.  Pixels the fast path cannot serve (non-finite input, huge values) only get their bit set in
+// rare_bits (zero on entry); the caller runs frame_energy_fixup after a group barrier - the out-of-line plain path stays
+// out of this loop and so do the register spills around its call.
+// STAGED: the next pixel's 48 bytes travel into this thread's own shared-memory slots (cp.async) while the current pixel
+// is computed - a plain load at the top of the round leaves 13 % of the warps' time waiting for L2 (ncu, energy_lab2),
+// registers for a software prefetch do not exist (122 are in use), and a prefetch hint only helps half way.
+template <int THREADS, bool STAGED>
+__device__ __forceinline__ void frame_energy_pixels(const float* img, int p_begin, int p_end, bool normalize,
+                                                    const FrameNormFast& norm, float* scaled, double* energy, double* map,
+                                                    unsigned int* rare_bits, const EnergyTables& tab, float4 (*stage)[THREADS],
+                                                    int gt) {
+    const uint32_t exp_table = smem_u32(tab.exp2);
+    auto stage_in = [&](int p) {
+        const float* src = img + p * kMfccNum;
 #pragma unroll
-    for (int m = 0; m < kMfccNum; m += 2) {
-        b = fma(z[m], tab.dct[J * kMfccNum + m], b);
-        a = fma(z[m + 1], tab.dct[J * kMfccNum + m + 1], a);
-    }
-    e_lo = exp_table64_inrange(__dadd_rn(a, b), tab.exp2);       // band J
-    e_hi = exp_table64_inrange(__dadd_rn(a, -b), tab.exp2);      // band 23 - J
-}
-
-// Group G: r[G] = (e[G] + e[G+8]) + e[G+16] and r[7-G] = (e[7-G] + e[15-G]) + e[23-G].
-template <int G>
-__device__ __forceinline__ void band_group(const double (&z)[kMfccNum], const EnergyTables& tab, double& r_g, double& r_7g) {
-    double lo1, hi1, lo2, hi2, lo3, hi3;
-    band_pair<G>(z, tab, lo1, hi1);          // bands G,     23 - G
-    band_pair<8 + G>(z, tab, lo3, hi3);      // bands 8 + G, 15 - G
-    r_g = __dadd_rn(lo1, lo3);
-    band_pair<7 - G>(z, tab, lo2, hi2);      // bands 7 - G, 16 + G
-    r_g = __dadd_rn(r_g, hi2);
-    r_7g = __dadd_rn(__dadd_rn(lo2, hi3), hi1);
-}
-
-struct PairExchange {                  // one per warp pair, in shared memory
-    float x[2][6][32];                 // each half's six scaled channel values
-    double sum[2][32];                 // half 1's r2 + r3 and r4 + r5
-};
-
-// This half's share of one pixel.  raw: channels 6 * HALF .. 6 * HALF + 5.  Returns the energy in half 0 (0 in half 1);
-// `scaled` receives this half's float32-stored scaled values (find_logen's side effect), `rare` the pair's combined flag.
-template <int HALF, int MAX_BAR>
-__device__ __forceinline__ double half_pixel(const float (&raw)[6], bool normalize, const FrameNormFast& norm,
-                                             const EnergyTables& tab, PairExchange& ex, int lane, int bar_id,
-                                             float (&scaled)[6], unsigned int& rare_out) {
-    double z[kMfccNum];
-    float own_abs = 0.f;                // sum of |scaled value|: NaN / Inf in, NaN / Inf out
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const int m = 6 * HALF + i;
-        float v = raw[i];
-        if (normalize) v = norm.apply(v);                                     // float32, as TF
-        {                                                                     // div_by_lifter with the shared-memory constants
-            const double d = static_cast<double>(v), r = tab.inv_lifter[m];
-            const double q0 = __dmul_rn(d, r);
-            v = __double2float_rn(__fma_rn(__fma_rn(-q0, tab.lifter[m], d), r, q0));
-        }
-        v = __double2float_rn(__dmul_rn(static_cast<double>(v), tab.mfnorm));
-        scaled[i] = v;
-        ex.x[HALF][i][lane] = v;
-        own_abs += fabsf(v);
-        z[m] = static_cast<double>(v);
-    }
-    NamedBar<1, MAX_BAR, 64>::sync(bar_id);
-    float all_abs = own_abs;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const float v = ex.x[1 - HALF][i][lane];
-        all_abs += fabsf(v);
-        z[6 * (1 - HALF) + i] = static_cast<double>(v);
-    }
-    // Every |mel_j| <= sum_m |z_m| (|cos| <= 1): at most 700 keeps all 24 table exponentials in range; anything else -
-    // huge values, Inf, NaN (the comparison is false for NaN) - goes to the plain path.  Both halves see the same 12
-    // values, so the flag needs no exchange.
-    const unsigned int rare = !(all_abs <= 700.f);
-    double ra, rb, rc, rd;
-    band_group<2 * HALF>(z, tab, ra, rb);          // half 0: r0, r7     half 1: r2, r5
-    band_group<2 * HALF + 1>(z, tab, rc, rd);      // half 0: r1, r6     half 1: r3, r4
-    const double s_lo = __dadd_rn(ra, rc);                     // half 0: r0 + r1    half 1: r2 + r3
-    const double s_hi = __dadd_rn(rd, rb);                     // half 0: r6 + r7    half 1: r4 + r5
-    if (HALF == 1) { ex.sum[0][lane] = s_lo; ex.sum[1][lane] = s_hi; }
-    NamedBar<1, MAX_BAR, 64>::sync(bar_id);
-    rare_out = rare;
-    if (HALF == 1) return 0.0;
-    const double total = __dadd_rn(__dadd_rn(s_lo, ex.sum[0][lane]), __dadd_rn(ex.sum[1][lane], s_hi));
-    return __ddiv_rn(1.0, total);
-}
-
-// Pixels [p_begin, p_end) of one frame by a group of PAIRS warp pairs (thread index gt within the group; named barriers
-// bar_base .. bar_base + PAIRS - 1 <= MAX_BAR belong to the pairs).  img / scaled / energy point at the frame; img may alias scaled
-// (find_logen's in-place scaling), so neither is read through a read-only path and a pixel's raw values are loaded before
-// anything of that pixel is stored.  Leaves map[p - p_begin] = energy.  Pixels the fast path cannot serve (non-finite
-// input, |mel| > 700) only get their bit set in rare_bits (zero on entry); the caller runs frame_energy_fixup after a
-// group barrier - the out-of-line plain path stays out of this loop and so do the register spills around its call.
-template <int PAIRS, int MAX_BAR>
-__device__ __forceinline__ void frame_energy_range(const float* img, int p_begin, int p_end, bool normalize,
-                                                   const FrameNormFast& norm, float* scaled, double* energy, double* map,
-                                                   PairExchange* ex, unsigned int* rare_bits, const EnergyTables& tab, int gt,
-                                                   int bar_base) {
-    const int warp = gt >> 5, lane = gt & 31, pair = warp >> 1, half = warp & 1;
-    constexpr int kStep = 32 * PAIRS;
-    const int bar_id = bar_base + pair;
-    auto load6 = [&](int p, float (&r)[6]) {
-        const float2* s = reinterpret_cast<const float2*>(img + p * kMfccNum + 6 * half);
-        const float2 a = s[0], b = s[1], c = s[2];
-        r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y; r[4] = c.x; r[5] = c.y;
+        for (int c = 0; c < 3; ++c)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&stage[c][gt])), "l"(src + 4 * c) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    if (STAGED && p_begin + gt < p_end) stage_in(p_begin + gt);
 #pragma unroll 1
-    for (int base = p_begin + pair * 32; base < p_end; base += kStep) {          // pair-uniform trip count
-        const int p = base + lane;
-        const bool active = p < p_end;
-        float raw[6];
-        load6(min(p, p_end - 1), raw);
-        // next round's line on its way while this one computes (a prefetch, not a register prefetch: the float64 chain
-        // needs every register the 8-CTAs-per-SM budget has)
-        if (base + kStep < p_end)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(img + min(p + kStep, p_end - 1) * kMfccNum + 6 * half));
-        float sc[6];
+    for (int p = p_begin + gt; p < p_end; p += THREADS) {
+        float4 a, b, c;
+        if (STAGED) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            a = stage[0][gt]; b = stage[1][gt]; c = stage[2][gt];
+            if (p + THREADS < p_end) stage_in(p + THREADS);
+        } else {
+            const float4* src = reinterpret_cast<const float4*>(img + p * kMfccNum);
+            a = src[0]; b = src[1]; c = src[2];
+            // (also a compiler barrier: without one the coefficient loads are hoisted out of the loop into 700 bytes of spills)
+            if (p + THREADS < p_end) asm volatile("prefetch.global.L1 [%0];" ::"l"(img + (p + THREADS) * kMfccNum) : "memory");
+            else asm volatile("" ::: "memory");
+        }
+        float x[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
         unsigned int rare;
-        double en;
-        if (half == 0) en = half_pixel<0, MAX_BAR>(raw, normalize, norm, tab, ex[pair], lane, bar_id, sc, rare);
-        else en = half_pixel<1, MAX_BAR>(raw, normalize, norm, tab, ex[pair], lane, bar_id, sc, rare);
+        const double en = pixel_energy(x, normalize, norm, tab, exp_table, rare);
         if (rare) {
-            // neither half stores anything of this pixel: frame_energy_fixup redoes it from its raw values
-            if (half == 0 && active) atomicOr(&rare_bits[(p - p_begin) >> 5], 1u << ((p - p_begin) & 31));
-        } else if (scaled != nullptr && active) {
-            float2* dst = reinterpret_cast<float2*>(scaled + p * kMfccNum + 6 * half);
-            dst[0] = make_float2(sc[0], sc[1]);
-            dst[1] = make_float2(sc[2], sc[3]);
-            dst[2] = make_float2(sc[4], sc[5]);
+            // nothing of this pixel is stored: frame_energy_fixup redoes it from its raw values
+            atomicOr(&rare_bits[(p - p_begin) >> 5], 1u << ((p - p_begin) & 31));
+            continue;
         }
-        if (half == 0 && active) {
-            map[p - p_begin] = en;
-            if (energy != nullptr) energy[p] = en;
+        if (scaled != nullptr) {
+            float4* dst = reinterpret_cast<float4*>(scaled + p * kMfccNum);
+            dst[0] = make_float4(x[0], x[1], x[2], x[3]);
+            dst[1] = make_float4(x[4], x[5], x[6], x[7]);
+            dst[2] = make_float4(x[8], x[9], x[10], x[11]);
         }
+        map[p - p_begin] = en;
+        if (energy != nullptr) energy[p] = en;
     }
 }
 
 // Second pass for the flagged pixels: the plain path (IEEE divisions, exp()) from the raw values, which are still intact
-// because neither half stored the pixel.  Called by the whole group after a barrier.  Returns (group-uniformly) whether
+// because nothing of the pixel was stored.  Called by the whole group after a barrier.  Returns (group-uniformly) whether
 // any bit was set; the caller then synchronises and clears the words before the next frame.
 __device__ __forceinline__ bool frame_energy_fixup(const float* img, int p_begin, int p_end, bool normalize,
                                                    const FrameNormFast& norm, float* scaled, double* energy, double* map,
@@ -541,12 +503,17 @@ __device__ __forceinline__ void group_minmax(const float* values, int n4, int gt
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
     bool nan = false;
     const float4* v4 = reinterpret_cast<const float4*>(values);
-    for (int i = gt; i < n4; i += threads) {
-        const float4 v = v4[i];
+    auto take = [&](const float4& v) {
         mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
         mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
         nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+    };
+    int i = gt;
+    for (; i + 3 * threads < n4; i += 4 * threads) {       // four loads in flight: a 64-thread group would otherwise wait 81 times
+        const float4 a = v4[i], b = v4[i + threads], c = v4[i + 2 * threads], d = v4[i + 3 * threads];
+        take(a); take(b); take(c); take(d);
     }
+    for (; i < n4; i += threads) take(v4[i]);
     mn = warp_min(mn);
     mx = warp_max(mx);
     nan = __any_sync(0xffffffffu, nan);
@@ -561,18 +528,18 @@ __device__ __forceinline__ void group_minmax(const float* values, int n4, int gt
     hi = bad != 0.f ? CUDART_NAN_F : mx;
 }
 
-constexpr int kEnergyPairs = 2;                        // warp pairs per frame in the batch kernels: 64 pixels per round, 27 rounds
-constexpr int kEnergyThreads = kEnergyPairs * 64;
+constexpr int kEnergyThreads = 64;                     // threads per frame in the batch kernels: 27 rounds of 64 pixels
 constexpr int kScoreThresholdsMax = 1024;              // == kMaxThresholds of score_kernel.cuh
+static_assert(kFramePixels % kEnergyThreads == 0, "whole rounds only");
 
-template <int PAIRS>
 struct EnergyGroupShared {
     double map[kFramePixels];
-    double part[16][8];
-    double leaf[16];
+    union {                            // the staging slots are idle while the mean is formed
+        float4 stage[3][kEnergyThreads];
+        struct { double part[16][8]; double leaf[16]; } sum;
+    };
     double mean;
-    PairExchange ex[PAIRS];
-    float red[3 * PAIRS * 2];
+    float red[3 * (kEnergyThreads / 32)];
     unsigned int rare_bits[kFramePixels / 32];
 };
 
@@ -595,24 +562,22 @@ struct Stage2Args {
     unsigned long long* num;
 };
 
-// GROUPS == 1: energy_kernel (aig_energy).  GROUPS == 2: the ACIVW evaluation step (aig_acivw_batch): threads 0-127 take
-// the real image, 128-255 the reconstructed one, both energy maps stay in shared memory, and the masks, their
-// intersection / union counts, the IoU and the per-threshold success counts follow in the same CTA - no mask ever
-// travels through HBM unless the caller asks for it.
+// GROUPS == 1: aig_energy, 64 threads per CTA, 8 CTAs per SM (26 KB of shared memory and 122 registers each).
+// GROUPS == 2: the ACIVW evaluation step (aig_acivw_batch): threads 0-63 take the real image, 64-127 the reconstructed
+// one, both energy maps stay in shared memory, and the masks, their intersection / union counts, the IoU and the
+// per-threshold success counts follow in the same CTA - no mask ever travels through HBM unless the caller asks for it.
 template <int GROUPS>
 __global__ void __launch_bounds__(GROUPS * kEnergyThreads, 8 / GROUPS)
 stage2_kernel(const __grid_constant__ Stage2Args a) {
-    __shared__ EnergyGroupShared<kEnergyPairs> sh[GROUPS];
+    __shared__ EnergyGroupShared sh[GROUPS];
     __shared__ EnergyTables s_tab;
     __shared__ unsigned int s_pos[GROUPS == 2 ? kScoreThresholdsMax : 1];
     __shared__ int s_iu[2];
     __shared__ double s_iou;
     const int tid = threadIdx.x;
     const int group = tid / kEnergyThreads, gt = tid % kEnergyThreads;
-    // barriers: GROUPS == 1: 1, 2 = the pairs, 0 = the group; GROUPS == 2: 1, 2 | 3 and 4, 5 | 6 = pairs | group of each image
-    constexpr int kMaxBar = GROUPS == 1 ? kEnergyPairs : GROUPS * (kEnergyPairs + 1);
-    const int bar_base = 1 + group * (kEnergyPairs + 1), bar_group = bar_base + kEnergyPairs;
-    auto group_sync = [&] { if (GROUPS == 1) __syncthreads(); else NamedBar<1, kMaxBar, kEnergyThreads>::sync(bar_group); };
+    // barriers: 0 = the CTA; GROUPS == 2: 1, 2 = the two images' groups
+    auto group_sync = [&] { if (GROUPS == 1) __syncthreads(); else NamedBar<1, GROUPS, kEnergyThreads>::sync(1 + group); };
     load_energy_tables(s_tab, tid, GROUPS * kEnergyThreads);
     if (gt < kFramePixels / 32) sh[group].rare_bits[gt] = 0u;
     if (GROUPS == 2) {
@@ -620,7 +585,7 @@ stage2_kernel(const __grid_constant__ Stage2Args a) {
         if (blockIdx.x == 0 && tid == 0) atomicAdd(a.num, static_cast<unsigned long long>(a.n_frames));   // num += 1 per frame (:229)
     }
     __syncthreads();
-    EnergyGroupShared<kEnergyPairs>& g = sh[group];
+    EnergyGroupShared& g = sh[group];
 
     for (long long frame = blockIdx.x; frame < a.n_frames; frame += gridDim.x) {
         const float* img = a.img[group] + frame * kFrameValues;
@@ -629,8 +594,8 @@ stage2_kernel(const __grid_constant__ Stage2Args a) {
         const FrameNormFast norm(lo, __fsub_rn(hi, lo));        // max(x - min) == fl(max - min): rounding is monotonic
         float* scaled = a.scaled[group] ? a.scaled[group] + frame * kFrameValues : nullptr;
         double* energy = a.energy[group] ? a.energy[group] + frame * kFramePixels : nullptr;
-        frame_energy_range<kEnergyPairs, kMaxBar>(img, 0, kFramePixels, a.normalize_first != 0, norm, scaled, energy, g.map, g.ex,
-                                         g.rare_bits, s_tab, gt, bar_base);
+        frame_energy_pixels<kEnergyThreads, true>(img, 0, kFramePixels, a.normalize_first != 0, norm, scaled, energy, g.map,
+                                                  g.rare_bits, s_tab, g.stage, gt);
         group_sync();
         if (frame_energy_fixup(img, 0, kFramePixels, a.normalize_first != 0, norm, scaled, energy, g.map, g.rare_bits, gt,
                                kEnergyThreads)) {
@@ -639,11 +604,20 @@ stage2_kernel(const __grid_constant__ Stage2Args a) {
             group_sync();
         }
         if (GROUPS == 2 || a.mask[group] != nullptr || a.mean[group] != nullptr) {
-            const double mean = frame_mean(g.map, g.part, g.leaf, &g.mean, gt, group_sync);
+            const double mean = frame_mean(g.map, g.sum.part, g.sum.leaf, &g.mean, gt, kEnergyThreads, group_sync);
             if (gt == 0 && a.mean[group] != nullptr) a.mean[group][frame] = mean;
             if (a.mask[group] != nullptr) {
-                for (int p = gt; p < kFramePixels; p += kEnergyThreads)
-                    a.mask[group][frame * kFramePixels + p] = g.map[p] > mean ? 1 : 0;
+                uint8_t* mask = a.mask[group] + frame * kFramePixels;
+                if ((reinterpret_cast<uintptr_t>(mask) & 3u) == 0) {                  // four pixels per store
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(mask);
+                    for (int q = gt; q < kFramePixels / 4; q += kEnergyThreads) {
+                        const double* e = g.map + 4 * q;
+                        dst[q] = (e[0] > mean ? 1u : 0u) | (e[1] > mean ? 0x100u : 0u) | (e[2] > mean ? 0x10000u : 0u) |
+                                 (e[3] > mean ? 0x1000000u : 0u);
+                    }
+                } else {
+                    for (int p = gt; p < kFramePixels; p += kEnergyThreads) mask[p] = g.map[p] > mean ? 1 : 0;
+                }
             }
         }
         if (GROUPS == 2) {
@@ -651,7 +625,7 @@ stage2_kernel(const __grid_constant__ Stage2Args a) {
             __syncthreads();
             const double mean_a = sh[0].mean, mean_b = sh[GROUPS - 1].mean;
             int inter = 0, uni = 0;
-            for (int p = tid; p < kFramePixels; p += GROUPS * kEnergyThreads) {       // 1728 = 6.75 * 256: whole warps only
+            for (int p = tid; p < kFramePixels; p += GROUPS * kEnergyThreads) {       // 1728 = 13.5 * 128: whole warps only
                 const bool ma = sh[0].map[p] > mean_a, mb = sh[GROUPS - 1].map[p] > mean_b;
                 inter += __popc(__ballot_sync(0xffffffffu, ma && mb));
                 uni += __popc(__ballot_sync(0xffffffffu, ma || mb));
@@ -666,7 +640,7 @@ stage2_kernel(const __grid_constant__ Stage2Args a) {
             __syncthreads();
             const double iou = s_iou;
             for (int k = tid; k < a.k_thr; k += GROUPS * kEnergyThreads)
-                if (iou > a.thr[k]) s_pos[k] += 1u;                                   // thread k owns s_pos[k]
+                if (iou > a.thr[k]) s_pos[k] += 1u;                                   // thread k % 128 owns s_pos[k]
         }
         __syncthreads();     // maps, s_iu and s_iou are reused by the next frame
     }
@@ -677,18 +651,18 @@ stage2_kernel(const __grid_constant__ Stage2Args a) {
 }
 
 // ---- small batches: one frame (pair) per thread-block cluster -----------------------------------------------------
-// Below ~150 frames one CTA per frame leaves most of the 148 SMs idle and a call costs a whole frame's 27 rounds
-// (45 us for the reference's batches of 2-16).  Here a cluster of 8 CTAs shares a frame: CTA r takes pixels
-// [216 r, 216 r + 216), which are exactly leaves 2r (104 values) and 2r + 1 (112 values) of NumPy's pairwise-sum tree for
+// Below ~150 frames one CTA per frame leaves most of the 148 SMs idle and a call costs a whole frame's 27 rounds.
+// Here a cluster of 8 CTAs shares a frame: CTA r takes pixels [216 r, 216 r + 216), one pixel per thread in a single
+// round; these are exactly leaves 2r (104 values) and 2r + 1 (112 values) of NumPy's pairwise-sum tree for
 // n = 1728, so each CTA reduces its own two leaves and only eight float64 partial sums (plus, when normalising, eight
 // min / max pairs, and for the ACIVW step eight (I, U) pairs) cross the cluster through distributed shared memory.
 // Every CTA then walks the top of the tree itself, in NumPy's order: the mean - and with it the mask - is bit-identical
 // to the one-CTA kernels.
 constexpr int kClusterSize = 8;
 constexpr int kSlicePixels = kFramePixels / kClusterSize;          // 216
-constexpr int kClusterPairs = 4;                                   // 128 pixels per round: two rounds per slice
-constexpr int kClusterGroupThreads = kClusterPairs * 64;           // 256
+constexpr int kClusterGroupThreads = 224;                          // seven warps: one pixel per thread, 8 lanes idle
 static_assert(kSlicePixels == 104 + 112, "a slice is two leaves of the pairwise tree");
+static_assert(kClusterGroupThreads >= kSlicePixels && kClusterGroupThreads % 32 == 0, "one round");
 
 struct ClusterGroupShared {
     double map[kSlicePixels];
@@ -696,8 +670,7 @@ struct ClusterGroupShared {
     double leaf[2];
     double mean;
     float lo, hi;
-    PairExchange ex[kClusterPairs];
-    float red[3 * kClusterPairs * 2];
+    float red[3 * (kClusterGroupThreads / 32)];
     unsigned int rare_bits[(kSlicePixels + 31) / 32];
 };
 struct ClusterMail {               // what the other CTAs of the cluster read
@@ -718,9 +691,7 @@ stage2_cluster_kernel(const __grid_constant__ Stage2Args a) {
     const int tid = threadIdx.x;
     const int group = tid / kClusterGroupThreads, gt = tid % kClusterGroupThreads;
     const int lane = tid & 31;
-    constexpr int kMaxBar = GROUPS == 1 ? kClusterPairs : GROUPS * (kClusterPairs + 1);
-    const int bar_base = 1 + group * (kClusterPairs + 1), bar_group = bar_base + kClusterPairs;
-    auto group_sync = [&] { if (GROUPS == 1) __syncthreads(); else NamedBar<1, kMaxBar, kClusterGroupThreads>::sync(bar_group); };
+    auto group_sync = [&] { if (GROUPS == 1) __syncthreads(); else NamedBar<1, GROUPS, kClusterGroupThreads>::sync(1 + group); };
     const unsigned int rank = cluster.block_rank();
     const long long n_clusters = gridDim.x / kClusterSize;
     load_energy_tables(s_tab, tid, GROUPS * kClusterGroupThreads);
@@ -755,8 +726,8 @@ stage2_cluster_kernel(const __grid_constant__ Stage2Args a) {
         const FrameNormFast norm(lo, __fsub_rn(hi, lo));
         float* scaled = a.scaled[group] ? a.scaled[group] + frame * kFrameValues : nullptr;
         double* energy = a.energy[group] ? a.energy[group] + frame * kFramePixels : nullptr;
-        frame_energy_range<kClusterPairs, kMaxBar>(img, p0, p0 + kSlicePixels, a.normalize_first != 0, norm, scaled, energy, g.map,
-                                          g.ex, g.rare_bits, s_tab, gt, bar_base);
+        frame_energy_pixels<kClusterGroupThreads, false>(img, p0, p0 + kSlicePixels, a.normalize_first != 0, norm, scaled, energy,
+                                                         g.map, g.rare_bits, s_tab, nullptr, gt);
         group_sync();
         if (frame_energy_fixup(img, p0, p0 + kSlicePixels, a.normalize_first != 0, norm, scaled, energy, g.map, g.rare_bits,
                                gt, kClusterGroupThreads)) {

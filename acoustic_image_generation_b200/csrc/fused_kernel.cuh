@@ -36,7 +36,7 @@ struct FusedShared {           // lives after the ring in dynamic shared memory
     double part[16][8];
     double leaf[16];
     double mean;
-    double exp_table[64];
+    EnergyTables tab;
     float minmax[2][kFusedConsumerWarps][2];
     unsigned long long bar[4];         // frame_full[2], frame_empty[2]
     double red64[2][kHeatMaxWarps];    // heat-map phase (HEAT builds): min / max reductions of the energy warps
@@ -104,7 +104,7 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* mfcc_o
         }
         mbar_fence_init();
     }
-    if (threadIdx.x < 64) sh.exp_table[threadIdx.x] = c_exp2_table[threadIdx.x];
+    load_energy_tables(sh.tab, threadIdx.x, kFusedThreads);
     __syncthreads();
 
     int stage = 0;
@@ -171,6 +171,7 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* mfcc_o
 
     // ---------------------------------------- energy warps -----------------------------------------
     const int et = threadIdx.x - (kFusedRows + 32);                     // 0..255
+    const uint32_t exp_table = smem_u32(sh.tab.exp2);
     unsigned int it = 0;
     HeatSmem hs = {};
     unsigned int chunk_it = 0;
@@ -193,7 +194,7 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* mfcc_o
         }
         if (JITTER) jitter_spin(jitter_seed, 7u, jitter_counter);
         mbar_arrive(frame_empty + 8 * slot);
-        const FrameNorm norm(lo, __fsub_rn(hi, lo));
+        const FrameNormFast norm(lo, __fsub_rn(hi, lo));
         const float* img = mfcc_out + static_cast<size_t>(frame) * kFrameValues;
 #pragma unroll 1
         for (int p = et; p < kFramePixels; p += kFusedEnergyThreads) {
@@ -201,7 +202,7 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* mfcc_o
             const float4 a = __ldcg(src), b = __ldcg(src + 1), c = __ldcg(src + 2);   // L2: written by this SM just now
             float x[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
             unsigned int rare;
-            double en = pixel_energy(x, normalize_first != 0, norm, sh.exp_table, rare);
+            double en = pixel_energy(x, normalize_first != 0, norm, sh.tab, exp_table, rare);
             if (rare) {                                            // the values already loaded, not a second (read-only) load
                 const float raw[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
                 en = pixel_energy_plain(raw, nullptr, normalize_first != 0, norm.lo, norm.range);
@@ -212,7 +213,7 @@ mfcc_energy_fused_kernel(const __grid_constant__ CUtensorMap tmap, float* mfcc_o
         }
         energy_group_sync();
         if (mask_out != nullptr || mean_out != nullptr) {
-            const double mean = frame_mean(sh.map, sh.part, sh.leaf, &sh.mean, et, [] { energy_group_sync(); });
+            const double mean = frame_mean(sh.map, sh.part, sh.leaf, &sh.mean, et, kFusedEnergyThreads, [] { energy_group_sync(); });
             if (et == 0 && mean_out != nullptr) mean_out[frame] = mean;
             if (mask_out != nullptr) {
                 for (int p = et; p < kFramePixels; p += kFusedEnergyThreads)

@@ -315,7 +315,6 @@ heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int o
 // row pair starts on a 16-byte boundary and is a 16-byte multiple long.  Other shapes run heatmap_fast_kernel.
 constexpr int kStreamThreads = 384;                  // 12 warps: 1728 pixels = 9 rounds of 6 warp pairs, 36 source rows = 3 per warp
 constexpr int kStreamWarps = kStreamThreads / 32;
-constexpr int kStreamPairs = kStreamWarps / 2;
 constexpr int kHeatMaxWarps = 12;                    // size of the reduction scratch of heat_phase
 
 struct EnergyPhaseShared {             // FUSED: lives in the staging area, which is idle while a frame's energies are computed
@@ -323,9 +322,9 @@ struct EnergyPhaseShared {             // FUSED: lives in the staging area, whic
     double part[16][8];
     double leaf[16];
     double mean;
-    PairExchange ex[kStreamPairs];
     float red[3 * kStreamWarps];
     unsigned int rare_bits[kFramePixels / 32];
+    EnergyTables tab;                  // reloaded every frame (9 KB from L2): the heat-map rows overwrite it
 };
 
 struct HeatStreamLayout {
@@ -557,13 +556,11 @@ heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ double s_red64[2][kHeatMaxWarps];
     __shared__ float s_red32[2][kHeatMaxWarps];
-    __shared__ EnergyTables s_tab;
     const int out_h = H ? H : a.out_h, out_w = W ? W : a.out_w;
     const HeatStreamLayout lay = heat_stream_layout(out_h, out_w, FUSED);
     const HeatSmem hs = heat_smem_carve(s_raw, lay, out_h, out_w);
     EnergyPhaseShared& eph = *reinterpret_cast<EnergyPhaseShared*>(s_raw + lay.off_stage);
     const int tid = threadIdx.x, lane = tid & 31;
-    if (FUSED) load_energy_tables(s_tab, tid, kStreamThreads);
     heat_taps_init<kStreamThreads>(hs, out_h, out_w, tid);
     constexpr int kPerThread = HeatPerThread<kStreamThreads>::value;
     double e[kPerThread];
@@ -591,15 +588,16 @@ heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
             const FrameNormFast norm(lo, __fsub_rn(hi, lo));
             double* energy = s.energy[0] ? s.energy[0] + frame * kFramePixels : nullptr;
             if (tid < kFramePixels / 32) eph.rare_bits[tid] = 0u;       // the staging area held heat-map rows a moment ago
+            load_energy_tables(eph.tab, tid, kStreamThreads);
             __syncthreads();
-            frame_energy_range<kStreamPairs, kStreamPairs>(img, 0, kFramePixels, s.normalize_first != 0, norm, nullptr, energy, eph.map,
-                                             eph.ex, eph.rare_bits, s_tab, tid, 1);
+            frame_energy_pixels<kStreamThreads, false>(img, 0, kFramePixels, s.normalize_first != 0, norm, nullptr, energy, eph.map,
+                                                       eph.rare_bits, eph.tab, nullptr, tid);
             __syncthreads();
             if (frame_energy_fixup(img, 0, kFramePixels, s.normalize_first != 0, norm, nullptr, energy, eph.map, eph.rare_bits,
                                    tid, kStreamThreads))
                 __syncthreads();
             if (s.mask[0] != nullptr || s.mean[0] != nullptr) {
-                const double mean = frame_mean(eph.map, eph.part, eph.leaf, &eph.mean, tid, [] { __syncthreads(); });
+                const double mean = frame_mean(eph.map, eph.part, eph.leaf, &eph.mean, tid, kStreamThreads, [] { __syncthreads(); });
                 if (tid == 0 && s.mean[0] != nullptr) s.mean[0][frame] = mean;
                 if (s.mask[0] != nullptr)
                     for (int p = tid; p < kFramePixels; p += kStreamThreads)

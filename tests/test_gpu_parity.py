@@ -947,11 +947,13 @@ def test_tfrecord_to_metric_files_example(tmp_path):
 
 def test_energy_stage_arithmetic_shortcuts_selftest(path):
     """The energy stage divides by the lifter with a reciprocal + one exact FMA correction (Markstein) and evaluates exp
-    with a 64-entry table; both are checked on the device: the division against IEEE division for every float32 input
-    and all twelve lifters, the exp against CUDA's exp() on 1.3e8 points."""
+    with a 1024-entry table on arguments in table-step units; both are checked on the device: the division against IEEE
+    division for every float32 input and all twelve lifters, the exp against CUDA's exp() on 1.3e8 points.  The exp
+    reference is exp(u_hi) * (1 + u_lo) with CUDA's exp (documented <= 1 ulp), so 2 ulp between the two is the bound a
+    <= 1 ulp table exp can show; tests/test_energy_tables_cpu.py measures the table exp itself in exact arithmetic."""
     bad, bad_after_store, _, _ = path.selftest(0)
     print('division: %d of %d (input, lifter) pairs differ from IEEE division; %d after the float32 store' % (bad, 12 << 32, bad_after_store))
     assert bad == 0 and bad_after_store == 0
     differ, max_ulps, count, _ = path.selftest(1)
     print('exp: %d of %d points differ from CUDA exp(), max %d ulp' % (differ, count, max_ulps))
-    assert count == 2 << 26 and max_ulps <= 1
+    assert count == 2 << 26 and max_ulps <= 2
