@@ -1645,10 +1645,13 @@ int aig_overlay(aig_handle* h, const float* heat, const uint8_t* bgr, int64_t n_
     LaunchScope scope(h, h->stream, kKindOther);
     const bool vec = px % 4 == 0 && (reinterpret_cast<uintptr_t>(d_heat) & 15u) == 0 &&
                      (reinterpret_cast<uintptr_t>(d_bgr) & 3u) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3u) == 0;
+    // one CTA per frame, handed out by the hardware as CTAs retire: a persistent grid of SM-count multiples ends on a
+    // partial wave worth up to a whole frame time (2048 frames on 1184 CTAs: 2 rounds for 1.73 frames per CTA)
+    const unsigned overlay_grid = static_cast<unsigned>(std::min<int64_t>(n_frames, 1 << 20));
     if (vec)
-        overlay_kernel<4><<<frames_grid(h, n_frames, 8), 256, 0, h->stream>>>(d_heat, d_bgr, n_frames, static_cast<int>(px), alpha, d_lut, d_out);
+        overlay_kernel<4><<<overlay_grid, kOverlayThreads, 0, h->stream>>>(d_heat, d_bgr, n_frames, static_cast<int>(px), alpha, d_lut, d_out);
     else
-        overlay_kernel<1><<<frames_grid(h, n_frames, 8), 256, 0, h->stream>>>(d_heat, d_bgr, n_frames, static_cast<int>(px), alpha, d_lut, d_out);
+        overlay_kernel<1><<<overlay_grid, kOverlayThreads, 0, h->stream>>>(d_heat, d_bgr, n_frames, static_cast<int>(px), alpha, d_lut, d_out);
     rc = scope.done("overlay_kernel");
     if (rc != AIG_OK) return io.abort(rc);
     return io.finish();

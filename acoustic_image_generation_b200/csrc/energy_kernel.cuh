@@ -70,7 +70,7 @@ static_assert(kExpLog2 == 10, "the Taylor degree below is chosen for a 1024-entr
 // m = 0, 2 .. 10; all times 2^10 / ln2 (tools/gen_mel_tables.py, rounded once from the reference's float64 cosines).
 struct CoupleCoef { double aa[3], ab[3], b0[6], b1[6]; };
 __device__ const double g_couple_coef[6 * 18] = AIG_COUPLE_COEF;
-__device__ const double g_exp_poly[4] = AIG_EXP_POLY;                 // (ln2 / 1024)^n / n!, n = 1 .. 4
+__constant__ double c_exp_poly[4] = AIG_EXP_POLY;                     // (ln2 / 1024)^n / n!, n = 1 .. 4 (uniform-register operands)
 __device__ const double g_exp2_table[kExpEntries] = AIG_EXP2_TABLE;   // RN(2^(i / 1024))
 
 // The tables live in SHARED memory in every kernel: the exp table is indexed by data, and shared loads of the projection
@@ -80,7 +80,6 @@ __device__ const double g_exp2_table[kExpEntries] = AIG_EXP2_TABLE;   // RN(2^(i
 struct __align__(16) EnergyTables {
     CoupleCoef couple[6];
     double lift[kMfccNum][2];          // {1 / lifter[m], lifter[m]}
-    double poly[4];
     double mfnorm, pad;
     double exp2[kExpEntries];
 };
@@ -90,7 +89,6 @@ __device__ __forceinline__ void load_energy_tables(EnergyTables& t, int tid, int
     for (int i = tid; i < 6 * 18; i += threads) couple[i] = g_couple_coef[i];
     for (int i = tid; i < kExpEntries; i += threads) t.exp2[i] = g_exp2_table[i];
     if (tid < kMfccNum) { t.lift[tid][0] = c_inv_lifter[tid]; t.lift[tid][1] = c_lifter[tid]; }
-    if (tid < 4) t.poly[tid] = g_exp_poly[tid];
     if (tid == 0) { t.mfnorm = c_mfnorm; t.pad = 0.0; }
 }
 
@@ -103,13 +101,13 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 // exp(x * ln2 / 1024) for x in table-step units, |x| < 2^20 (|x ln2 / 1024| <= 700 and more; pixel_energy guarantees it):
 // k = rint(x), r = x - k exact, result = 2^(k >> 10) * T[k & 1023] * (1 + p(r)) with p the degree-4 Taylor polynomial of
 // 2^(r / 1024) - 1 (truncation 3.7e-20).  `table` is the shared-memory byte address of EnergyTables::exp2.
-__device__ __forceinline__ double exp_units(double x, uint32_t table, const double (&poly)[4]) {
+__device__ __forceinline__ double exp_units(double x, uint32_t table) {
     const double t = __dadd_rn(x, kExpMagic);
     const int k = __double2loint(t);
     const double r = __dadd_rn(x, -__dadd_rn(t, -kExpMagic));
-    double p = __fma_rn(poly[3], r, poly[2]);
-    p = __fma_rn(p, r, poly[1]);
-    p = __fma_rn(p, r, poly[0]);
+    double p = __fma_rn(c_exp_poly[3], r, c_exp_poly[2]);
+    p = __fma_rn(p, r, c_exp_poly[1]);
+    p = __fma_rn(p, r, c_exp_poly[0]);
     const double q = __dmul_rn(p, r);                                  // 2^(r / 1024) - 1
     const int idx = k & (kExpEntries - 1);
     const double tj = lds_f64(table + static_cast<uint32_t>(idx) * 8u);
@@ -192,8 +190,7 @@ __device__ __forceinline__ float max_nan_abs(float m, float a) {     // max(m, |
 
 // The four exponentials of couple j: bands j, 23 - j (p) and 11 - j, 12 + j (q), "lo" the first of each pair.
 struct CoupleExp { double lo_p, hi_p, lo_q, hi_q; };
-__device__ __forceinline__ CoupleExp couple_exp(const double (&z)[kMfccNum], const CoupleCoef& c, uint32_t exp_table,
-                                                const double (&poly)[4]) {
+__device__ __forceinline__ CoupleExp couple_exp(const double (&z)[kMfccNum], const CoupleCoef& c, uint32_t exp_table) {
     double aa = __dmul_rn(z[3], c.aa[0]);                 // m + 1 = 4, 8, 12: symmetric under j -> 23 - j and j -> 11 - j
     aa = __fma_rn(z[7], c.aa[1], aa);
     aa = __fma_rn(z[11], c.aa[2], aa);
@@ -208,10 +205,10 @@ __device__ __forceinline__ CoupleExp couple_exp(const double (&z)[kMfccNum], con
     }
     const double a0 = __dadd_rn(aa, ab), a1 = __dadd_rn(aa, -ab);
     CoupleExp e;
-    e.lo_p = exp_units(__dadd_rn(a0, b0), exp_table, poly);           // band j
-    e.hi_p = exp_units(__dadd_rn(a0, -b0), exp_table, poly);          // band 23 - j
-    e.lo_q = exp_units(__dadd_rn(a1, b1), exp_table, poly);           // band 11 - j
-    e.hi_q = exp_units(__dadd_rn(a1, -b1), exp_table, poly);          // band 12 + j
+    e.lo_p = exp_units(__dadd_rn(a0, b0), exp_table);           // band j
+    e.hi_p = exp_units(__dadd_rn(a0, -b0), exp_table);          // band 23 - j
+    e.lo_q = exp_units(__dadd_rn(a1, b1), exp_table);           // band 11 - j
+    e.hi_q = exp_units(__dadd_rn(a1, -b1), exp_table);          // band 12 + j
     return e;
 }
 
@@ -248,20 +245,17 @@ __device__ __forceinline__ double pixel_energy(float (&x)[kMfccNum], bool normal
         z[m] = static_cast<double>(v);
     }
     rare = !(big <= 58.f);
-    double poly[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) poly[i] = tab.poly[i];
     // couple j holds e[j], e[23-j], e[11-j], e[12+j];  r[k] = (e[k] + e[k+8]) + e[k+16]
-    const CoupleExp c0 = couple_exp(z, tab.couple[0], exp_table, poly);   // e0  e23 e11 e12
-    const CoupleExp c3 = couple_exp(z, tab.couple[3], exp_table, poly);   // e3  e20 e8  e15
-    const CoupleExp c4 = couple_exp(z, tab.couple[4], exp_table, poly);   // e4  e19 e7  e16
+    const CoupleExp c0 = couple_exp(z, tab.couple[0], exp_table);   // e0  e23 e11 e12
+    const CoupleExp c3 = couple_exp(z, tab.couple[3], exp_table);   // e3  e20 e8  e15
+    const CoupleExp c4 = couple_exp(z, tab.couple[4], exp_table);   // e4  e19 e7  e16
     const double r0 = __dadd_rn(__dadd_rn(c0.lo_p, c3.lo_q), c4.hi_q);    // (e0 + e8)  + e16
     const double r7 = __dadd_rn(__dadd_rn(c4.lo_q, c3.hi_q), c0.hi_p);    // (e7 + e15) + e23
     const double r3 = __dadd_rn(__dadd_rn(c3.lo_p, c0.lo_q), c4.hi_p);    // (e3 + e11) + e19
     const double r4 = __dadd_rn(__dadd_rn(c4.lo_p, c0.hi_q), c3.hi_p);    // (e4 + e12) + e20
-    const CoupleExp c1 = couple_exp(z, tab.couple[1], exp_table, poly);   // e1  e22 e10 e13
-    const CoupleExp c2 = couple_exp(z, tab.couple[2], exp_table, poly);   // e2  e21 e9  e14
-    const CoupleExp c5 = couple_exp(z, tab.couple[5], exp_table, poly);   // e5  e18 e6  e17
+    const CoupleExp c1 = couple_exp(z, tab.couple[1], exp_table);   // e1  e22 e10 e13
+    const CoupleExp c2 = couple_exp(z, tab.couple[2], exp_table);   // e2  e21 e9  e14
+    const CoupleExp c5 = couple_exp(z, tab.couple[5], exp_table);   // e5  e18 e6  e17
     const double r1 = __dadd_rn(__dadd_rn(c1.lo_p, c2.lo_q), c5.hi_q);    // (e1 + e9)  + e17
     const double r6 = __dadd_rn(__dadd_rn(c5.lo_q, c2.hi_q), c1.hi_p);    // (e6 + e14) + e22
     const double r2 = __dadd_rn(__dadd_rn(c2.lo_p, c1.lo_q), c5.hi_p);    // (e2 + e10) + e18
@@ -305,7 +299,6 @@ __global__ void selftest_exp_kernel(unsigned long long n, unsigned long long* ou
     for (int i = threadIdx.x; i < kExpEntries; i += blockDim.x) s_exp[i] = g_exp2_table[i];
     __syncthreads();
     const uint32_t table = smem_u32(s_exp);
-    const double poly[4] = {g_exp_poly[0], g_exp_poly[1], g_exp_poly[2], g_exp_poly[3]};
     const double step_hi = AIG_EXP_STEP_HI, step_lo = AIG_EXP_STEP_LO;
     unsigned long long differ = 0, max_ulps = 0, count = 0;
     for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < 2 * n;
@@ -316,7 +309,7 @@ __global__ void selftest_exp_kernel(unsigned long long n, unsigned long long* ou
         const double u_hi = __dmul_rn(x, step_hi);
         const double u_lo = __fma_rn(x, step_lo, __fma_rn(x, step_hi, -u_hi));
         const double e = exp(u_hi);
-        const long long a = __double_as_longlong(exp_units(x, table, poly)), b = __double_as_longlong(__fma_rn(e, u_lo, e));
+        const long long a = __double_as_longlong(exp_units(x, table)), b = __double_as_longlong(__fma_rn(e, u_lo, e));
         const unsigned long long d = static_cast<unsigned long long>(a > b ? a - b : b - a);
         differ += d != 0;
         max_ulps = d > max_ulps ? d : max_ulps;
@@ -495,37 +488,42 @@ __device__ __forceinline__ bool frame_energy_fixup(const float* img, int p_begin
 }
 
 // min / max of n4 float4 values by a group of `threads` threads, NaN-propagating like tf.reduce_min / reduce_max
-// (outdoor_data_mfcc.py:674,677): any NaN in the frame makes both NaN, hence the whole normalised frame.
-// red: float [3][threads / 32] scratch.  Result in every thread of the group.
+// (outdoor_data_mfcc.py:674,677): any NaN in the frame makes both NaN, hence the whole normalised frame.  min.NaN /
+// max.NaN carry the NaN through the reduction themselves (no separate flag: half the instructions of the pass).
+// red: float [2][threads / 32] scratch.  Result in every thread of the group.
+__device__ __forceinline__ float min_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float max_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 template <typename Sync>
 __device__ __forceinline__ void group_minmax(const float* values, int n4, int gt, int threads, float* red, Sync sync,
                                              float& lo, float& hi) {
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-    bool nan = false;
     const float4* v4 = reinterpret_cast<const float4*>(values);
     auto take = [&](const float4& v) {
-        mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
-        mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
-        nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+        mn = min_nan(min_nan(mn, v.x), min_nan(v.y, min_nan(v.z, v.w)));
+        mx = max_nan(max_nan(mx, v.x), max_nan(v.y, max_nan(v.z, v.w)));
     };
     int i = gt;
-    for (; i + 3 * threads < n4; i += 4 * threads) {       // four loads in flight: a 64-thread group would otherwise wait 81 times
-        const float4 a = v4[i], b = v4[i + threads], c = v4[i + 2 * threads], d = v4[i + 3 * threads];
-        take(a); take(b); take(c); take(d);
+    for (; i + 7 * threads < n4; i += 8 * threads) {       // eight loads in flight: a 64-thread group would otherwise wait 81 times
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = v4[i + u * threads];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) take(v[u]);
     }
     for (; i < n4; i += threads) take(v4[i]);
-    mn = warp_min(mn);
-    mx = warp_max(mx);
-    nan = __any_sync(0xffffffffu, nan);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
     const int warps = threads >> 5;
-    if ((gt & 31) == 0) { red[gt >> 5] = mn; red[warps + (gt >> 5)] = mx; red[2 * warps + (gt >> 5)] = nan ? 1.f : 0.f; }
+    if ((gt & 31) == 0) { red[gt >> 5] = mn; red[warps + (gt >> 5)] = mx; }
     sync();
     mn = red[0]; mx = red[warps];
-    float bad = red[2 * warps];
-    for (int w = 1; w < warps; ++w) { mn = fminf(mn, red[w]); mx = fmaxf(mx, red[warps + w]); bad += red[2 * warps + w]; }
+    for (int w = 1; w < warps; ++w) { mn = min_nan(mn, red[w]); mx = max_nan(mx, red[warps + w]); }
     sync();                                                     // red may be reused right away
-    lo = bad != 0.f ? CUDART_NAN_F : mn;
-    hi = bad != 0.f ? CUDART_NAN_F : mx;
+    lo = mn;
+    hi = mx;
 }
 
 constexpr int kEnergyThreads = 64;                     // threads per frame in the batch kernels: 27 rounds of 64 pixels

@@ -12,8 +12,8 @@ import acoustic_image_generation_b200 as aig
 
 p = aig.AcousticPath(0)
 n = int(os.environ.get('AIG_FRAMES', '4096'))
-img = torch.rand(n, 36, 48, 12, device='cuda')
-other = torch.rand(n, 36, 48, 12, device='cuda')
+img = torch.randn(n, 36, 48, 12, device='cuda') * 12 - 8            # MFCC-like magnitudes
+other = torch.randn(n, 36, 48, 12, device='cuda') * 12 - 8
 thr = torch.tensor(aig.REFERENCE_THRESHOLDS, device='cuda', dtype=torch.float64)
 cnt = torch.zeros(12, device='cuda', dtype=torch.int64)
 heat = torch.empty(2048, 224, 298, device='cuda')

@@ -11,8 +11,9 @@ import acoustic_image_generation_b200 as aig
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 p = aig.AcousticPath(0)
-img = torch.rand(n, 36, 48, 12, device='cuda')
-other = torch.rand(n, 36, 48, 12, device='cuda')
+img = torch.randn(n, 36, 48, 12, device='cuda') * 12 - 8            # MFCC-like magnitudes (per-frame minimum far from 0)
+other = torch.randn(n, 36, 48, 12, device='cuda') * 12 - 8
+unit = torch.rand(n, 36, 48, 12, device='cuda')                    # an already normalised frame: minimum ~ 0
 thr = torch.tensor(aig.REFERENCE_THRESHOLDS, device='cuda', dtype=torch.float64)
 cnt = torch.zeros(12, device='cuda', dtype=torch.int64)
 energy = torch.empty(n, 36, 48, device='cuda', dtype=torch.float64)
@@ -43,6 +44,11 @@ def line(name, ms, frames, bytes_per_frame=None):
 for norm in (0, 1):
     ms = timed(lambda: lib.aig_energy(h, img.data_ptr(), n, norm, None, energy.data_ptr(), mask.data_ptr(), None))
     line('aig_energy normalize_first=%d (%d frames)' % (norm, n), ms, n)
+ms = timed(lambda: lib.aig_energy(h, unit.data_ptr(), n, 1, None, energy.data_ptr(), mask.data_ptr(), None))
+line('aig_energy normalize_first=1, frame minimum ~ 0 (%d frames)' % n, ms, n)
+ms = timed(lambda: lib.aig_energy(h, unit.data_ptr(), n, 0, None, energy.data_ptr(), mask.data_ptr(), None))
+line('aig_energy normalize_first=0, values in [0, 1) (%d frames)' % n, ms, n)
+del unit
 ms = timed(lambda: lib.aig_acivw_batch(h, img.data_ptr(), other.data_ptr(), n, 0, thr.data_ptr(), 11, None, None,
                                        cnt.data_ptr(), cnt[11:].data_ptr(), None, None, None, None))
 line('aig_acivw_batch (%d pairs = %d energy maps)' % (n, 2 * n), ms, 2 * n)
