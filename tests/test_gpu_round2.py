@@ -1,6 +1,6 @@
 """Round-2 kernels through the C ABI, against the oracle, the golden vectors and each other.  Needs a B200.
 
-* stage2_kernel / stage2_cluster_kernel (two threads per pixel; one CTA or one cluster of 8 CTAs per frame): the two
+* stage2_kernel / stage2_cluster_kernel (one thread per pixel; one CTA or one cluster of 8 CTAs per frame): the two
   forms must agree bit for bit with each other - energies, means, masks, in-place scaling - and with the oracle within
   the float64 tolerance; NaN propagation of the min / max; in-place aliasing on device tensors.
 * aig_acivw_batch: the reference's evaluation step in one launch == energy + energy + iou_sweep, == the golden replay.
@@ -121,6 +121,58 @@ def test_nan_propagates_through_min_max_like_tf(path, path_cta):
     vec[2, 3] = np.nan
     got = path.normalize_mfcc(vec)
     assert np.isnan(got[2]).all() and np.isfinite(got[[0, 1, 3, 4]]).all()
+
+
+def _normalisation_frames():
+    """Frames built around the three forms of the per-frame division (FrameNormFast in csrc/energy_kernel.cuh): mode 2
+    (no per-value test: |min| >= 2^-14 range), mode 1 (per-value test: minimum at or near zero) and mode 0 (IEEE division:
+    tiny / huge range), each salted with values one or a few ulps above the minimum, exact zeros, the maximum itself and
+    values straddling the 2^-14 bound."""
+    rng = np.random.default_rng(77)
+    frames = []
+
+    def frame(lo, hi):
+        f = rng.uniform(lo, hi, (36, 48, 12)).astype(np.float32)
+        flat = f.reshape(-1)
+        lo32, hi32 = np.float32(lo), np.float32(hi)
+        flat[0], flat[1] = lo32, hi32
+        v = lo32
+        for i in range(2, 40):                      # the smallest non-zero differences the frame can hold
+            v = np.nextafter(v, np.float32(np.inf), dtype=np.float32)
+            flat[i] = v
+        flat[40:60] = lo32 + (hi32 - lo32) * np.float32(2.0) ** -np.arange(20, 40).astype(np.float32)   # d / range down to 2^-39
+        return f
+
+    frames.append(frame(-37.5, 22.25))                                   # MFCC-like: mode 2
+    frames.append(frame(3.0, 9.0))                                       # positive minimum: mode 2
+    frames.append(frame(-2.0 ** -14, 1.0 - 2.0 ** -14))                  # |lo| == 2^-14 range: the bound itself
+    frames.append(frame(-2.0 ** -14 * 0.999, 1.0))                       # just under it: mode 1
+    frames.append(frame(0.0, 1.0))                                       # an already normalised frame: mode 1
+    frames.append(frame(1e-30, 1.0))                                     # minimum a denormal-sized step from zero
+    frames.append(frame(-1e-12, 3e-12))                                  # range below 2^-30: mode 1 / tiny quotients
+    frames.append(frame(-3e-25, 1e-25))                                  # range below 2^-60: IEEE division
+    frames.append(frame(-1e25, 2e25))                                    # range above 2^60: IEEE division
+    frames.append(frame(5.0, 5.0 + 2.0 ** -20))                          # a handful of distinct values
+    return np.stack(frames, 0)
+
+
+def test_min_max_division_forms_are_the_ieee_quotient(path, path_cta, torch):
+    """(x - min) / (max - min) of every value, bit for bit the float32 division the reference does (:672-679), through
+    the kernels' reciprocal forms: frames for each FrameNormFast mode, read back as the scaled image - which is
+    the quotient divided by the lifter and multiplied by mfnorm, so it is compared with the oracle's chain - and through
+    the stand-alone normalise kernel (IEEE division per value)."""
+    imgs = _normalisation_frames()
+    want_norm = np.stack([oracle.normalize_acoustic_image(f) for f in imgs], 0)
+    got_norm = path.normalize_images(imgs)
+    assert np.array_equal(got_norm.view(np.uint32), want_norm.view(np.uint32))
+    want_scaled = want_norm.copy()
+    want_energy = np.stack([oracle.find_logen(f) for f in want_scaled], 0)          # scales want_scaled in place
+    for p in (path, path_cta):
+        energy, _, scaled = p.energy(torch.from_numpy(imgs.copy()).cuda(), normalize_first=True, want_scaled=True)
+        got = scaled.cpu().numpy()
+        differ = np.argwhere(got.view(np.uint32) != want_scaled.view(np.uint32))
+        assert differ.size == 0, 'first differing values (frame, y, x, c): %s' % differ[:5].tolist()
+        np.testing.assert_allclose(energy.cpu().numpy(), want_energy, rtol=ENERGY_RTOL, atol=0)
 
 
 def test_selftest_hoisted_reciprocal_division(path):
