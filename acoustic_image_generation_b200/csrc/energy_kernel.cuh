@@ -14,7 +14,7 @@
 // for 1728 elements exactly.
 //
 // Round 2, second pass: ONE THREAD PER PIXEL again, with leaner arithmetic.  tools/energy_lab.cu / energy_lab2.cu
-// measured the candidates on a B200 (gpurun_out/lab*.txt): two threads per pixel exchanging through shared memory and
+// measured the candidates on a B200 (profiles/r02_energy_lab.txt): two threads per pixel exchanging through shared memory and
 // named barriers (round 2, first pass) 10.7 M frames/s with this arithmetic, the two halves in one warp exchanging by
 // shuffles 11.5 M, one thread per pixel 13.7 M, and 14.2 M with the input staged by cp.async - against 9.6 M for the
 // pair kernel with the old arithmetic.  The FP64 pipe is the bound (tools/fp64_peak.cu: 56 DFMA/clk/SM at best, 0.87 of
