@@ -150,6 +150,7 @@ struct aig_handle {
     bool heat_stream_attr_set[8] = {false, false, false, false, false, false, false, false};
     bool stage2_attr_set[2] = {false, false};
     int heat_bulk_store = 1;            // 0: round-1 per-thread-store kernel for every shape (comparison runs)
+    bool norm_bulk_attr_set = false;
     int small_batch_frames = 0;         // below this many frames a frame is split over a cluster of 8 CTAs; 0: SM count
     unsigned int debug_jitter = 0;      // non-zero: seed of the jittered build of the fused kernel (race stress tests)
     bool mask_attr_set = false;
@@ -920,6 +921,7 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
         h->small_host_bytes = static_cast<int>(value);
     } else if (key == "heat_bulk_store") {
         h->heat_bulk_store = value != 0;
+
     } else if (key == "small_batch_frames") {
         if (value < 0 || value > (1 << 20)) return h->fail(AIG_ERR_ARGUMENT, "small_batch_frames out of range");
         h->small_batch_frames = static_cast<int>(value);
@@ -1057,8 +1059,16 @@ int aig_normalize_images(aig_handle* h, const float* images, int64_t n_frames, f
     const float* d_in = io.in(images, count);
     float* d_out = io.out(out, count);
     if (io.failed) return io.finish();
+    const bool bulk = ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15u) == 0;
+    if (bulk && !h->norm_bulk_attr_set) {
+        AIG_CK(cudaFuncSetAttribute(normalize_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kNormBulkSmem)));
+        h->norm_bulk_attr_set = true;
+    }
     LaunchScope scope(h, h->stream, kKindOther);
-    normalize_kernel<<<frames_grid(h, n_frames, 8), 256, 0, h->stream>>>(d_in, n_frames, d_out);
+    if (bulk)
+        normalize_bulk_kernel<<<frames_grid(h, n_frames, 1), kNormBulkThreads, kNormBulkSmem, h->stream>>>(d_in, n_frames, d_out);
+    else
+        normalize_kernel<<<frames_grid(h, n_frames, 8), 256, 0, h->stream>>>(d_in, n_frames, d_out);
     rc = scope.done("normalize_kernel");
     if (rc != AIG_OK) return io.abort(rc);
     return io.finish();
@@ -1570,6 +1580,8 @@ int aig_tile_mfcc(aig_handle* h, const float* mfcc, int64_t n, int normalize, fl
     const float* d_in = io.in(mfcc, static_cast<size_t>(n) * kMfccNum);
     float* d_out = io.out(map_out, static_cast<size_t>(n) * kFrameValues);
     if (io.failed) return io.finish();
+    if (((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15u) != 0)
+        return io.abort(h->fail(AIG_ERR_ARGUMENT, "aig_tile_mfcc: device buffers must be 16-byte aligned"));
     LaunchScope scope(h, h->stream, kKindOther);
     tile_mfcc_kernel<<<frames_grid(h, n, 8), kTileThreads, 0, h->stream>>>(d_in, n, normalize, d_out);
     rc = scope.done("tile_mfcc_kernel");

@@ -94,6 +94,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+// ---- bulk asynchronous loads global -> shared (TMA unit, no tensor map) -------------------------------
+// src (global) and dst (shared) 16-byte aligned, bytes a multiple of 16; completion arrives on the mbarrier as
+// transaction bytes (arm it with mbar_arrive_expect_tx first).
+__device__ __forceinline__ void bulk_load_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // ---- bulk asynchronous stores shared -> global (TMA unit, SASS UBLKCP) ---------------------------
 // Generic-proxy writes to shared memory (st.shared) must be fenced before the async proxy reads them.
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -827,4 +827,69 @@ normalize_kernel(const float* images, long long n_frames, float* out) {
     }
 }
 
+// The same with the frame resident in shared memory: one bulk asynchronous copy brings a frame's 82 944 bytes in, the CTA
+// finds min / max and normalises it in place, one bulk copy takes it out - HBM sees each byte once in each direction
+// (normalize_kernel's second pass over the frame re-reads it through L2, and its per-thread loads keep too few bytes in
+// flight: 0.58 of the copy roof).  Two frame buffers per CTA, one CTA per SM: the next frame's load and the previous
+// frame's store run while the current one is computed.  Needs 16-byte aligned buffers; `images` may alias `out`.
+constexpr int kNormBulkThreads = 1024;
+constexpr uint32_t kFrameBytes = kFrameValues * sizeof(float);
+constexpr size_t kNormBulkSmem = 2 * static_cast<size_t>(kFrameBytes) + 128;
+static_assert(kFrameBytes % 16 == 0, "bulk copies move 16-byte units");
+
+__global__ void __launch_bounds__(kNormBulkThreads, 1)
+normalize_bulk_kernel(const float* images, long long n_frames, float* out) {
+    extern __shared__ __align__(128) unsigned char s_frames[];
+    __shared__ unsigned long long s_bar[2];
+    __shared__ float s_red[3 * (kNormBulkThreads / 32)];
+    const int tid = threadIdx.x;
+    float* buf[2] = {reinterpret_cast<float*>(s_frames), reinterpret_cast<float*>(s_frames + kFrameBytes)};
+    const uint32_t bar[2] = {smem_u32(&s_bar[0]), smem_u32(&s_bar[1])};
+    if (tid == 0) {
+        mbar_init(bar[0], 1);
+        mbar_init(bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    long long frame = blockIdx.x;
+    if (tid == 0 && frame < n_frames) {
+        mbar_arrive_expect_tx(bar[0], kFrameBytes);
+        bulk_load_g2s(smem_u32(buf[0]), images + frame * kFrameValues, kFrameBytes, bar[0]);
+    }
+    for (unsigned int it = 0; frame < n_frames; frame += gridDim.x, ++it) {
+        const unsigned int s = it & 1u;
+        const long long next = frame + gridDim.x;
+        if (tid == 0 && next < n_frames) {
+            bulk_wait_read<0>();                               // the store of the previous frame has finished reading buf[s ^ 1]
+            mbar_arrive_expect_tx(bar[s ^ 1u], kFrameBytes);
+            bulk_load_g2s(smem_u32(buf[s ^ 1u]), images + next * kFrameValues, kFrameBytes, bar[s ^ 1u]);
+        }
+        mbar_wait(bar[s], (it >> 1) & 1u);
+        float mn, mx;
+        group_minmax(buf[s], kFrameValues / 4, tid, kNormBulkThreads, s_red, [] { __syncthreads(); }, mn, mx);
+        const FrameNormFast norm(mn, __fsub_rn(mx, mn));
+        float4* v4 = reinterpret_cast<float4*>(buf[s]);
+        if (norm.mode == 2) {
+            for (int i = tid; i < kFrameValues / 4; i += kNormBulkThreads) {
+                float4 v = v4[i];
+                v.x = norm.apply_mode2(v.x); v.y = norm.apply_mode2(v.y); v.z = norm.apply_mode2(v.z); v.w = norm.apply_mode2(v.w);
+                v4[i] = v;
+            }
+        } else {
+            for (int i = tid; i < kFrameValues / 4; i += kNormBulkThreads) {
+                float4 v = v4[i];
+                v.x = norm.apply(v.x); v.y = norm.apply(v.y); v.z = norm.apply(v.z); v.w = norm.apply(v.w);
+                v4[i] = v;
+            }
+        }
+        fence_proxy_async_smem();                              // the bulk copy reads what the threads just wrote
+        __syncthreads();
+        if (tid == 0) {
+            bulk_store_s2g(out + frame * kFrameValues, smem_u32(buf[s]), kFrameBytes);
+            bulk_commit();
+        }
+    }
+    if (tid == 0) bulk_wait_all<0>();                          // shared memory must outlive the copies that read it
+}
+
 }  // namespace aig

@@ -74,6 +74,7 @@ struct LabTables {
     double exp2[1024];
 };
 __device__ LabTables g_tables[3];         // LOGN = 6, 8, 10
+__constant__ CoupleCoef c_couple10[6];    // LOGN = 10 coefficients in the constant bank (COEF variants)
 
 static void fill_tables(int logn, LabTables& out) {
     const long double ln2 = 0.693147180559945309417232121458176568L;
@@ -138,6 +139,7 @@ struct Couple { double lo_p, hi_p, lo_q, hi_q; };     // exp of bands j, 23 - j,
 
 template <int LOGN, bool HAND>
 __device__ __forceinline__ Couple couple(const double (&z)[12], const CoupleCoef& c, uint32_t tab_lane, const double (&poly)[6]) {
+    // (c may point into shared memory or into the constant bank)
     double aa = __dmul_rn(z[3], c.aa[0]);
     aa = __fma_rn(z[7], c.aa[1], aa);
     aa = __fma_rn(z[11], c.aa[2], aa);
@@ -177,7 +179,7 @@ struct LabArgs {
 
 // PREFETCH: 0 = prefetch.global.L1 hint, 1 = next pixel's values in registers, 2 = nothing,
 //           3 = the next pixel's 48 bytes on their way into a per-thread shared-memory slot (cp.async) during this pixel's arithmetic
-template <int LOGN, bool HAND, int PREFETCH, int THREADS, int MINB>
+template <int LOGN, bool HAND, int PREFETCH, int THREADS, int MINB, int COEF = 0>
 __global__ void __launch_bounds__(THREADS, MINB) lab_single_kernel(const LabArgs a) {
     __shared__ __align__(16) LabTables tab;
     __shared__ double s_map[kPixels];
@@ -256,18 +258,20 @@ __global__ void __launch_bounds__(THREADS, MINB) lab_single_kernel(const LabArgs
                 z[m] = static_cast<double>(v[m]);
             }
             const bool rare = !(big <= 58.f);
+            int zero = 0;
+            if (COEF == 2) asm volatile("mov.u32 %0, 0;" : "=r"(zero));
             // r[k] = (e[k] + e[k+8]) + e[k+16];  lo(j) = e[j], hi(j) = e[23-j] for j < 12
             //   couple j holds lo(j) = e[j], hi(j) = e[23-j], lo(11-j) = e[11-j], hi(11-j) = e[12+j]
-            Couple c0 = couple<LOGN, HAND>(z, tab.couple[0], tab_lane, poly);   // e0 e23 e11 e12
-            Couple c3 = couple<LOGN, HAND>(z, tab.couple[3], tab_lane, poly);   // e3 e20 e8  e15
-            Couple c4 = couple<LOGN, HAND>(z, tab.couple[4], tab_lane, poly);   // e4 e19 e7  e16
+            Couple c0 = couple<LOGN, HAND>(z, COEF == 0 ? tab.couple[0] : (COEF == 1 ? c_couple10[0] : c_couple10[0 + zero]), tab_lane, poly);   // e0 e23 e11 e12
+            Couple c3 = couple<LOGN, HAND>(z, COEF == 0 ? tab.couple[3] : (COEF == 1 ? c_couple10[3] : c_couple10[3 + zero]), tab_lane, poly);   // e3 e20 e8  e15
+            Couple c4 = couple<LOGN, HAND>(z, COEF == 0 ? tab.couple[4] : (COEF == 1 ? c_couple10[4] : c_couple10[4 + zero]), tab_lane, poly);   // e4 e19 e7  e16
             const double r0 = __dadd_rn(__dadd_rn(c0.lo_p, c3.lo_q), c4.hi_q);   // e0 + e8 + e16
             const double r7 = __dadd_rn(__dadd_rn(c4.lo_q, c3.hi_q), c0.hi_p);   // e7 + e15 + e23
             const double r3 = __dadd_rn(__dadd_rn(c3.lo_p, c0.lo_q), c4.hi_p);   // e3 + e11 + e19
             const double r4 = __dadd_rn(__dadd_rn(c4.lo_p, c0.hi_q), c3.hi_p);   // e4 + e12 + e20
-            Couple c1 = couple<LOGN, HAND>(z, tab.couple[1], tab_lane, poly);   // e1 e22 e10 e13
-            Couple c2 = couple<LOGN, HAND>(z, tab.couple[2], tab_lane, poly);   // e2 e21 e9  e14
-            Couple c5 = couple<LOGN, HAND>(z, tab.couple[5], tab_lane, poly);   // e5 e18 e6  e17
+            Couple c1 = couple<LOGN, HAND>(z, COEF == 0 ? tab.couple[1] : (COEF == 1 ? c_couple10[1] : c_couple10[1 + zero]), tab_lane, poly);   // e1 e22 e10 e13
+            Couple c2 = couple<LOGN, HAND>(z, COEF == 0 ? tab.couple[2] : (COEF == 1 ? c_couple10[2] : c_couple10[2 + zero]), tab_lane, poly);   // e2 e21 e9  e14
+            Couple c5 = couple<LOGN, HAND>(z, COEF == 0 ? tab.couple[5] : (COEF == 1 ? c_couple10[5] : c_couple10[5 + zero]), tab_lane, poly);   // e5 e18 e6  e17
             const double r1 = __dadd_rn(__dadd_rn(c1.lo_p, c2.lo_q), c5.hi_q);   // e1 + e9 + e17
             const double r6 = __dadd_rn(__dadd_rn(c5.lo_q, c2.hi_q), c1.hi_p);   // e6 + e14 + e22
             const double r2 = __dadd_rn(__dadd_rn(c2.lo_p, c1.lo_q), c5.hi_p);   // e2 + e10 + e18
@@ -306,6 +310,7 @@ static float time_ms(F launch, int reps = 9) {
 
 struct Variant { const char* name; void (*launch)(const LabArgs&, int sms); };
 #define V(name, LOGN, HAND, PF, THREADS, MINB) {name, [](const LabArgs& a, int sms) { lab_single_kernel<LOGN, HAND, PF, THREADS, MINB><<<sms * MINB, THREADS>>>(a); }}
+#define VC(name, LOGN, HAND, PF, THREADS, MINB, COEF) {name, [](const LabArgs& a, int sms) { lab_single_kernel<LOGN, HAND, PF, THREADS, MINB, COEF><<<sms * MINB, THREADS>>>(a); }}
 
 int main(int argc, char** argv) {
     const long long n = argc > 1 ? atoll(argv[1]) : 8192;
@@ -314,6 +319,7 @@ int main(int argc, char** argv) {
     LabTables* lt = new LabTables[3];
     fill_tables(6, lt[0]); fill_tables(8, lt[1]); fill_tables(10, lt[2]);
     CK(cudaMemcpyToSymbol(g_tables, lt, 3 * sizeof(LabTables)));
+    CK(cudaMemcpyToSymbol(c_couple10, lt[2].couple, sizeof(CoupleCoef) * 6));
     double dct[24][12], lifter[12], mfnorm = std::sqrt(2.0 / 24);
     for (int j = 0; j < 24; ++j) for (int m = 0; m < 12; ++m) dct[j][m] = std::cos((m + 1) * M_PI / 24 * (j + 0.5));
     for (int m = 0; m < 12; ++m) lifter[m] = 1 + 11.0 * std::sin(M_PI * (m + 1) / 22);
@@ -338,6 +344,8 @@ int main(int argc, char** argv) {
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
 
     const Variant variants[] = {
+        VC("1024x1 deg4, cp.async, coefficients: constant bank", 10, true, 3, 64, 8, 1),
+        VC("1024x1 deg4, cp.async, constant bank, opaque index", 10, true, 3, 64, 8, 2),
         V("1024x1 deg4, hand, cp.async staging,      8x64", 10, true, 3, 64, 8),
         V("1024x1 deg4, hand, cp.async staging,      9x64", 10, true, 3, 64, 9),
         V("1024x1 deg4, hand, cp.async staging,      4x128", 10, true, 3, 128, 4),
