@@ -151,6 +151,7 @@ struct aig_handle {
     bool stage2_attr_set[2] = {false, false};
     int heat_bulk_store = 1;            // 0: round-1 per-thread-store kernel for every shape (comparison runs)
     bool norm_bulk_attr_set = false;
+    int norm_bulk_copy = 1;             // aig_normalize_images with the frame resident in shared memory (0: two-pass per-thread kernel)
     int small_batch_frames = 0;         // below this many frames a frame is split over a cluster of 8 CTAs; 0: SM count
     unsigned int debug_jitter = 0;      // non-zero: seed of the jittered build of the fused kernel (race stress tests)
     bool mask_attr_set = false;
@@ -921,6 +922,8 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
         h->small_host_bytes = static_cast<int>(value);
     } else if (key == "heat_bulk_store") {
         h->heat_bulk_store = value != 0;
+    } else if (key == "norm_bulk_copy") {
+        h->norm_bulk_copy = value != 0;
 
     } else if (key == "small_batch_frames") {
         if (value < 0 || value > (1 << 20)) return h->fail(AIG_ERR_ARGUMENT, "small_batch_frames out of range");
@@ -1059,7 +1062,9 @@ int aig_normalize_images(aig_handle* h, const float* images, int64_t n_frames, f
     const float* d_in = io.in(images, count);
     float* d_out = io.out(out, count);
     if (io.failed) return io.finish();
-    const bool bulk = ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15u) == 0;
+    if (((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15u) != 0)
+        return io.abort(h->fail(AIG_ERR_ARGUMENT, "aig_normalize_images: device buffers must be 16-byte aligned"));
+    const bool bulk = h->norm_bulk_copy != 0;
     if (bulk && !h->norm_bulk_attr_set) {
         AIG_CK(cudaFuncSetAttribute(normalize_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kNormBulkSmem)));
         h->norm_bulk_attr_set = true;

@@ -374,6 +374,8 @@ int64_t aig_launch_count(const aig_handle* h);
  *                        find_logen drop-in; 0 switches the path off
  *   "heat_bulk_store"    1 (default): heat maps are staged in shared memory and written with bulk asynchronous copies
  *                        (heat_stream_kernel); 0: the round-1 kernel with per-thread stores, for comparison runs
+ *   "norm_bulk_copy"     1 (default): aig_normalize_images keeps each frame in shared memory between one bulk asynchronous
+ *                        load and one bulk store (normalize_bulk_kernel); 0: the two-pass per-thread kernel, for comparison
  *   "small_batch_frames" batches with fewer frames than this spread each frame over a cluster of 8 CTAs (aig_energy,
  *                        aig_acivw_batch) and run aig_mfcc_energy as tiled MFCC kernel + cluster energy kernel instead of
  *                        the one-CTA-per-frame persistent kernel; 0 (default) = the device's SM count

@@ -175,6 +175,47 @@ def test_min_max_division_forms_are_the_ieee_quotient(path, path_cta, torch):
         np.testing.assert_allclose(energy.cpu().numpy(), want_energy, rtol=ENERGY_RTOL, atol=0)
 
 
+def test_normalise_bulk_copy_kernel(path, torch):
+    """aig_normalize_images with the frame resident in shared memory between a bulk load and a bulk store
+    (normalize_bulk_kernel: two buffers per CTA, several frames per CTA) == the per-thread kernel == the oracle, bit for
+    bit: 700 frames (4-5 per CTA on 148 SMs) including the adversarial ones, a NaN frame and a constant frame; in place;
+    device buffers off the 16-byte grid are refused, here and by aig_tile_mfcc."""
+    rng = np.random.default_rng(12)
+    imgs = np.concatenate([_normalisation_frames(), (rng.normal(-8, 12, (690, 36, 48, 12))).astype(np.float32)], 0)
+    imgs[13, 5, 5, 5] = np.nan
+    imgs[14] = 2.5
+    want = oracle.normalize_acoustic_images(imgs)
+    d = torch.from_numpy(imgs).cuda()
+    got = path.normalize_images(d)
+
+    def same(a, b):                                  # bit for bit, any NaN equal to any NaN (payloads are not specified)
+        a, b = np.asarray(a), np.asarray(b)
+        nan = np.isnan(a)
+        return np.array_equal(nan, np.isnan(b)) and np.array_equal(a[~nan].view(np.uint32), b[~nan].view(np.uint32))
+
+    got_host = got.cpu().numpy()
+    assert np.isnan(got_host[13]).all() and np.isnan(got_host[14]).all()
+    assert same(got_host, want)
+    path.set_option('norm_bulk_copy', 0)
+    try:
+        old = path.normalize_images(d)
+    finally:
+        path.set_option('norm_bulk_copy', 1)
+    assert same(old.cpu().numpy(), got_host)
+    lib, h = path._lib, path._h
+    assert lib.aig_normalize_images(h, d.data_ptr(), d.shape[0], d.data_ptr()) == 0          # in place
+    torch.cuda.synchronize()
+    assert same(d.cpu().numpy(), got_host)
+    flat = torch.zeros(2 * 20736 + 8, device='cuda')
+    out = torch.empty(2 * 20736 + 8, device='cuda')
+    assert lib.aig_normalize_images(h, flat.data_ptr() + 4, 2, out.data_ptr()) == -1         # AIG_ERR_ARGUMENT, no fault
+    assert b'aligned' in lib.aig_last_error(h)
+    assert lib.aig_tile_mfcc(h, flat.data_ptr() + 4, 2, 0, out.data_ptr()) == -1
+    assert b'aligned' in lib.aig_last_error(h)
+    assert lib.aig_normalize_images(h, flat.data_ptr(), 2, out.data_ptr()) == 0              # the handle still works
+    torch.cuda.synchronize()
+
+
 def test_selftest_hoisted_reciprocal_division(path):
     """FrameNormFast::apply against __fdiv_rn on 2^32 (value, range) pairs: no difference anywhere."""
     bad, count, fast, _ = path.selftest(2)
