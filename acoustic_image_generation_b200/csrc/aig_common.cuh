@@ -53,6 +53,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// For waits that usually last microseconds: the polling loop of mbar_wait costs two issue slots every ~30 cycles per
+// waiting warp (ncu, energy_heat_ws_kernel: a fifth of all instructions issued were polls), which the warps being
+// waited for could use.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned int ns) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 
 // ---- TMA --------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {

@@ -315,7 +315,7 @@ heatmap_fast_kernel(const double* __restrict__ energy, long long n_frames, int o
 // row pair starts on a 16-byte boundary and is a 16-byte multiple long.  Other shapes run heatmap_fast_kernel.
 constexpr int kStreamThreads = 384;                  // 12 warps: 1728 pixels = 9 rounds of 6 warp pairs, 36 source rows = 3 per warp
 constexpr int kStreamWarps = kStreamThreads / 32;
-constexpr int kHeatMaxWarps = 12;                    // size of the reduction scratch of heat_phase
+constexpr int kHeatMaxWarps = 16;                    // size of the reduction scratch of heat_phase
 
 struct EnergyPhaseShared {             // FUSED: lives in the staging area, which is idle while a frame's energies are computed
     double map[kFramePixels];
@@ -331,10 +331,11 @@ struct HeatStreamLayout {
     int wp;                 // row stride of the 36 blended rows (out_w rounded up to 4)
     unsigned int off_rows, off_stage, off_taps, total;
 };
-__host__ __device__ inline HeatStreamLayout heat_stream_layout(int out_h, int out_w, bool fused, int warps = kStreamWarps) {
+__host__ __device__ inline HeatStreamLayout heat_stream_layout(int out_h, int out_w, bool fused, int warps = kStreamWarps,
+                                                              bool t_elsewhere = false) {
     HeatStreamLayout l;
     l.wp = (out_w + 3) & ~3;
-    l.off_rows = kFramePixels * 4;                                          // after t[1728]
+    l.off_rows = t_elsewhere ? 0 : kFramePixels * 4;                        // after t[1728] unless the caller places t itself
     l.off_stage = l.off_rows + kFrameH * l.wp * 4;
     unsigned int stage = warps * 2 * 2 * out_w * 4;                         // per warp: 2 buffers of 2 rows
     if (fused && stage < sizeof(EnergyPhaseShared)) stage = sizeof(EnergyPhaseShared);
@@ -418,10 +419,12 @@ struct HeatPerThread { static constexpr int value = (kFramePixels + THREADS - 1)
 // bounds and address arithmetic (profiles/r02_ncu_stage2_kernels.csv).  `sync` is the barrier of the participating
 // threads, `after_t` runs once the energies have been consumed (the stand-alone kernel prefetches the next frame's there).
 // chunk_it is the calling warp's running chunk counter (selects its staging buffer; survives across frames).
-template <int THREADS, int VEC, int W, int H, typename Sync, typename AfterT>
+struct HeatNoHook { __device__ __forceinline__ void operator()() const {} };
+template <int THREADS, int VEC, int W, int H, typename Sync, typename AfterT, typename AfterRows = HeatNoHook>
 __device__ __forceinline__ void heat_phase(const double (&e)[HeatPerThread<THREADS>::value], const HeatSmem& s,
                                            double (*red64)[kHeatMaxWarps], float (*red32)[kHeatMaxWarps], int out_h_rt,
-                                           int out_w_rt, float* dst, int tid, unsigned int& chunk_it, Sync sync, AfterT after_t) {
+                                           int out_w_rt, float* dst, int tid, unsigned int& chunk_it, Sync sync, AfterT after_t,
+                                           AfterRows after_rows = AfterRows{}) {
     constexpr int kWarps = THREADS / 32, kPerThread = HeatPerThread<THREADS>::value;
     static_assert(kWarps <= kHeatMaxWarps, "reduction scratch too small");
     const int out_h = H ? H : out_h_rt, out_w = W ? W : out_w_rt;
@@ -473,6 +476,7 @@ __device__ __forceinline__ void heat_phase(const double (&e)[HeatPerThread<THREA
         }
     });
     sync();
+    after_rows();                         // every participating thread is done with s.t
     // 4. min / max of the up-sampled image
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
     for (int y = warp; y < out_h; y += kWarps) {
@@ -615,6 +619,137 @@ heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
                               [&] { if (!FUSED) fetch(frame + gridDim.x); });   // next frame's energies arrive during the passes
     }
     if (lane == 0) bulk_wait_all<0>();        // shared memory must outlive the copies that read it
+}
+
+// ---- energy + heat map, warp-specialised (aig_energy_heatmap) --------------------------------------------------------
+// heat_stream_kernel<true> runs find_logen and the heat-map phase one after the other in the same warps: ncu (round 2)
+// shows the two phases simply add up - 55 % of the samples in the float64 pixel loop, 25 % in the up-sampling passes, the
+// FP64 pipe busy 29 % of the time against 50-58 % in the stand-alone energy kernel - because two CTAs per SM drift into
+// the same phase and a lone CTA's 12 warps cannot fill the pipe.  Here the two stages are different warps of a CTA and
+// overlap by construction:
+//   ET threads          find_logen of frame i + 1 (+ optional min-max, mean, mask, energy output) into map[slot]
+//   HW warps            heat_phase() of frame i: normalise, up-sample, stage rows, bulk copies
+// The map is handed over through a full / empty mbarrier pair per slot, as the persistent MFCC + energy kernel hands its
+// frames to the energy warps.  The shape in use (WsTwin): two CTAs of 256 + 256 threads per SM - two independent
+// pipelines whose min-max / pixel-loop / mean phases interleave, 6.75 pixel rounds per frame (the last one 3/4 full) -
+// with ONE map slot whose first half doubles as the heat-map phase's float32 t[] (the energies are in the heat-map
+// threads' registers by then; the slot goes back to the float64 warps after the horizontal pass), which is what lets two
+// CTAs fit in 227 KB.  One CTA of 512 + 512 threads with two map slots (WsConfig<512, 16, 1, 2>) measured 6.85 M frames/s
+// at 224 x 298 against 7.69 M for the twin form and 7.02 M for heat_stream_kernel<true>.  ncu on the twin form
+// (profiles/r02_ncu_energy_heat_ws.csv): FP64 pipe 31 %, shared-memory wavefronts 66 % of peak - the exp-table look-ups
+// of the float64 warps and the row passes of the heat-map warps share one shared-memory pipe, which is why the overlap
+// pays 10 % and not the 20 % two perfectly chained kernels would give (8.4 M).
+template <int ET_, int HW_, int CTAS_, int SLOTS_>
+struct WsConfig {
+    static constexpr int ET = ET_, HW = HW_, CTAS = CTAS_, SLOTS = SLOTS_;
+    static constexpr int HT = HW * 32, THREADS = ET + HT;
+    static_assert(HW <= kHeatMaxWarps, "reduction scratch of heat_phase");
+    static_assert(SLOTS == 1 || SLOTS == 2, "map slots");
+};
+using WsTwin = WsConfig<256, 8, 2, 1>;
+
+template <typename C>
+struct WsShared {                      // behind the heat-map phase's rows / staging slots / taps in dynamic shared memory
+    EnergyTables tab;
+    double map[C::SLOTS][kFramePixels];
+    double part[16][8];
+    double leaf[16];
+    double mean;
+    double red64[2][kHeatMaxWarps];
+    float red32[2][kHeatMaxWarps];
+    float red[3 * (C::ET / 32)];
+    unsigned int rare_bits[kFramePixels / 32];
+    unsigned long long bar[4];         // full[2], empty[2]
+};
+template <typename C>
+__host__ __device__ inline size_t energy_heat_ws_smem(int out_h, int out_w) {
+    return ((heat_stream_layout(out_h, out_w, false, C::HW, C::SLOTS == 1).total + 15u) & ~15u) + sizeof(WsShared<C>) + 16;
+}
+
+template <typename C, int VEC, int W, int H>
+__global__ void __launch_bounds__(C::THREADS, C::CTAS)
+energy_heat_ws_kernel(const __grid_constant__ HeatStreamArgs a) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    constexpr bool kOneSlot = C::SLOTS == 1;
+    const int out_h = H ? H : a.out_h, out_w = W ? W : a.out_w;
+    const HeatStreamLayout lay = heat_stream_layout(out_h, out_w, false, C::HW, kOneSlot);
+    HeatSmem hs = heat_smem_carve(s_raw, lay, out_h, out_w);
+    WsShared<C>& ws = *reinterpret_cast<WsShared<C>*>(s_raw + ((lay.total + 15u) & ~15u));
+    if (kOneSlot) hs.t = reinterpret_cast<float*>(ws.map[0]);
+    const uint32_t full = smem_u32(&ws.bar[0]), empty = smem_u32(&ws.bar[2]);        // + 8 * slot
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < C::SLOTS; ++s) {
+            mbar_init(full + 8 * s, C::ET);                  // every energy thread arrives (release of its map values)
+            mbar_init(empty + 8 * s, C::HT);                 // every heat-map thread arrives when it no longer needs the slot
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (tid < C::ET) {
+        // ---------------------------------------- float64 warps ----------------------------------------
+        const int et = tid;
+        auto group_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(C::ET) : "memory"); };
+        load_energy_tables(ws.tab, et, C::ET);
+        if (et < kFramePixels / 32) ws.rare_bits[et] = 0u;
+        group_sync();
+        const Stage2Args& s = a.s2;
+        unsigned int it = 0;
+        for (long long frame = blockIdx.x; frame < a.n_frames; frame += gridDim.x, ++it) {
+            const unsigned int slot = kOneSlot ? 0u : it & 1u, use = kOneSlot ? it : it >> 1;
+            const float* img = s.img[0] + frame * kFrameValues;
+            float lo = 0.f, hi = 1.f;
+            if (s.normalize_first) group_minmax(img, kFrameValues / 4, et, C::ET, ws.red, group_sync, lo, hi);
+            const FrameNormFast norm(lo, __fsub_rn(hi, lo));
+            double* energy = s.energy[0] ? s.energy[0] + frame * kFramePixels : nullptr;
+            double* map = ws.map[slot];
+            mbar_wait(empty + 8 * slot, (use & 1u) ^ 1u);                      // the heat-map warps are done with this slot's last frame
+            frame_energy_pixels<C::ET, false>(img, 0, kFramePixels, s.normalize_first != 0, norm, nullptr, energy, map,
+                                              ws.rare_bits, ws.tab, nullptr, et);
+            group_sync();
+            if (frame_energy_fixup(img, 0, kFramePixels, s.normalize_first != 0, norm, nullptr, energy, map, ws.rare_bits, et,
+                                   C::ET)) {
+                group_sync();
+                if (et < kFramePixels / 32) ws.rare_bits[et] = 0u;
+                group_sync();
+            }
+            if (s.mask[0] != nullptr || s.mean[0] != nullptr) {
+                const double mean = frame_mean(map, ws.part, ws.leaf, &ws.mean, et, C::ET, group_sync);
+                if (et == 0 && s.mean[0] != nullptr) s.mean[0][frame] = mean;
+                if (s.mask[0] != nullptr)
+                    for (int p = et; p < kFramePixels; p += C::ET)
+                        s.mask[0][frame * kFramePixels + p] = map[p] > mean ? 1 : 0;
+            }
+            mbar_arrive(full + 8 * slot);                                      // release: this thread's map values are visible
+        }
+        return;
+    }
+
+    // -------------------------------------------- heat-map warps --------------------------------------------
+    const int ht = tid - C::ET;
+    auto heat_sync = [] { asm volatile("bar.sync 2, %0;" ::"n"(C::HT) : "memory"); };
+    heat_taps_init<C::HT>(hs, out_h, out_w, ht);
+    heat_sync();
+    constexpr int kPerThread = HeatPerThread<C::HT>::value;
+    unsigned int chunk_it = 0, it = 0;
+    const long long frame_values = static_cast<long long>(out_h) * out_w;
+    for (long long frame = blockIdx.x; frame < a.n_frames; frame += gridDim.x, ++it) {
+        const unsigned int slot = kOneSlot ? 0u : it & 1u, use = kOneSlot ? it : it >> 1;
+        mbar_wait_relaxed(full + 8 * slot, use & 1u, 256);                     // usually microseconds: the float64 warps are the slower side
+        double e[kPerThread];
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i) {
+            const int p = ht + i * C::HT;
+            e[i] = p < kFramePixels ? ws.map[slot][p] : CUDART_NAN;
+        }
+        // two slots: the energies are in registers, the slot is free.  One slot: t[] lives in it until the horizontal pass
+        // is over (heat_phase's first barrier orders every thread's reads of the map above before anyone writes t).
+        if (!kOneSlot) mbar_arrive(empty + 8 * slot);
+        heat_phase<C::HT, VEC, W, H>(e, hs, ws.red64, ws.red32, out_h, out_w, a.heat + frame * frame_values, ht, chunk_it,
+                                     heat_sync, [] {}, [&] { if (kOneSlot) mbar_arrive(empty); });
+    }
+    if ((ht & 31) == 0) bulk_wait_all<0>();       // shared memory must outlive the copies that read it
 }
 
 // mask [n, 36, 48] u8 -> mask_up [n, out_h, out_w] u8, value 1 iff bilinear(mask != 0) > 1/2 exactly.

@@ -374,6 +374,8 @@ int64_t aig_launch_count(const aig_handle* h);
  *                        find_logen drop-in; 0 switches the path off
  *   "heat_bulk_store"    1 (default): heat maps are staged in shared memory and written with bulk asynchronous copies
  *                        (heat_stream_kernel); 0: the round-1 kernel with per-thread stores, for comparison runs
+ *   "energy_heat_ws"     1 (default): aig_energy_heatmap runs the warp-specialised kernel (float64 warps and heat-map warps
+ *                        of a CTA working on consecutive frames, two CTAs per SM); 0: the same warps do both phases in sequence
  *   "norm_bulk_copy"     1 (default): aig_normalize_images keeps each frame in shared memory between one bulk asynchronous
  *                        load and one bulk store (normalize_bulk_kernel); 0: the two-pass per-thread kernel, for comparison
  *   "small_batch_frames" batches with fewer frames than this spread each frame over a cluster of 8 CTAs (aig_energy,
@@ -390,7 +392,9 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value);
 /* Device self-tests of the energy stage's two arithmetic shortcuts (energy_kernel.cuh):
  *   which = 0  the Markstein division by the lifter constants against IEEE division for ALL 2^32 float32 inputs:
  *              out[0] = mismatching (input, lifter) pairs, out[1] = mismatches surviving the float32 store
- *   which = 1  the table-driven exp against CUDA's exp() on 2 * 2^26 points of [-700, 700] and [-12, 12]:
+ *   which = 1  the table-driven exp (1024-entry table, arguments in units of ln2 / 1024) against CUDA's exp() on
+ *              2 * 2^26 points of [-700, 700] and [-12, 12]; the reference value is exp(u_hi) * (1 + u_lo) for the
+ *              double-double natural argument, so two <= 1 ulp functions are compared (<= 2 ulp expected):
  *              out[0] = points differing, out[1] = largest difference in ulps, out[2] = points compared
  *   which = 2  the hoisted-reciprocal float32 division of the per-frame min-max normalisation against __fdiv_rn on
  *              2^32 (value, range) pairs: out[0] = pairs differing, out[1] = pairs compared, out[2] = pairs that took

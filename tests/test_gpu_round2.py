@@ -337,6 +337,27 @@ def test_fused_energy_heatmap_equals_the_two_kernel_chain(path, torch, shape, no
     assert np.abs(heat[i] - want).max() <= 1e-4
 
 
+@pytest.mark.parametrize('shape', [(224, 298), (224, 224), (100, 78), (64, 60), (448, 596)])
+@pytest.mark.parametrize('n_frames', [149, 297, 1000])
+def test_warp_specialised_energy_heatmap_equals_the_sequential_kernel(path, shape, n_frames):
+    """energy_heat_ws_kernel (float64 warps and heat-map warps of one CTA hand the map over through mbarriers; default) against
+    heat_stream_kernel<true> (option energy_heat_ws = 0): energies, masks and heat maps bit for bit, for frame counts that
+    leave CTAs with 0, 1 and several frames and an odd one out, a generic-size build and a size too large for two CTAs
+    per SM (falls back).  The hand-over is also a race test: any frame read too early or overwritten too late shows."""
+    imgs = _images_with_hard_cases(n_frames, 40)
+    for normalize_first in (False, True):
+        before = path.launch_count
+        got = path.energy_heatmap(imgs, normalize_first, *shape)
+        assert path.launch_count - before == (1 if shape[0] <= 224 else 2)     # 448 x 596 rows do not fit: two kernels
+        path.set_option('energy_heat_ws', 0)
+        try:
+            want = path.energy_heatmap(imgs, normalize_first, *shape)
+        finally:
+            path.set_option('energy_heat_ws', 1)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w, equal_nan=True)
+
+
 @pytest.mark.parametrize('shape', [(224, 298), (224, 224), (100, 78), (37, 49)])
 def test_persistent_kernel_with_heat_map_phase(path, torch, shape):
     """aig_mfcc_energy_heatmap (opt-in): the energy warps of the persistent kernel also up-sample and normalise.  MFCC,

@@ -47,7 +47,14 @@ line('aig_energy normalize_first=0, values in [0, 1)', timed(lambda: lib.aig_ene
 line('aig_energy, energy only (no mask)', timed(lambda: lib.aig_energy(h, unit.data_ptr(), n, 0, None, energy.data_ptr(), None, None)), n)
 line('aig_acivw_batch (energy maps)', timed(lambda: lib.aig_acivw_batch(h, unit.data_ptr(), other.data_ptr(), n, 0, thr.data_ptr(), 11, None, None,
                                                                        cnt.data_ptr(), cnt[11:].data_ptr(), None, None, None, None)), 2 * n)
-line('aig_energy_heatmap 224x298 one launch', timed(lambda: lib.aig_energy_heatmap(h, img.data_ptr(), n, 1, None, None, heat.data_ptr(), 224, 298)), n)
+for ws in (1, 0):
+    p.set_option('energy_heat_ws', ws)
+    line('aig_energy_heatmap 224x298 one launch, energy_heat_ws=%d' % ws, timed(lambda: lib.aig_energy_heatmap(h, img.data_ptr(), n, 1, None, None, heat.data_ptr(), 224, 298)), n)
+    line('aig_energy_heatmap 224x298 + energy + mask, energy_heat_ws=%d' % ws,
+         timed(lambda: lib.aig_energy_heatmap(h, img.data_ptr(), n, 1, energy.data_ptr(), mask.data_ptr(), heat.data_ptr(), 224, 298)), n)
+    line('aig_energy_heatmap 224x224 one launch, energy_heat_ws=%d' % ws,
+         timed(lambda: lib.aig_energy_heatmap(h, img.data_ptr(), n, 1, None, None, heat.data_ptr(), 224, 224)), n)
+p.set_option("energy_heat_ws", 1)
 for small in (1, 16):
     line('aig_energy cluster form, %d frames (incl. launch)' % small,
          timed(lambda: lib.aig_energy(h, img.data_ptr(), small, 0, None, energy.data_ptr(), mask.data_ptr(), None), 21), small)
