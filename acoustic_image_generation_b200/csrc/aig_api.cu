@@ -26,6 +26,7 @@
 #include "heatmap_kernel.cuh"
 #include "mfcc_kernel.cuh"
 #include "score_kernel.cuh"
+#include "mask_packed_kernel.cuh"
 
 #ifndef AIG_BUILD_ID_STRING
 #define AIG_BUILD_ID_STRING "unstamped"
@@ -151,6 +152,8 @@ struct aig_handle {
     bool stage2_attr_set[2] = {false, false};
     int heat_bulk_store = 1;            // 0: round-1 per-thread-store kernel for every shape (comparison runs)
     bool norm_bulk_attr_set = false;
+    bool packed_attr_set[4] = {};
+    int mask_packed = 1;                // aig_resize_mask / aig_ciou_sweep at 224 x 298 and 224 x 224 as the packed kernels (0: the generic kernels)
     bool energy_heat_ws_attr_set[4] = {};
     int energy_heat_ws = 1;             // aig_energy_heatmap as the warp-specialised kernel (0: heat_stream_kernel<true>, phases in sequence)
     int norm_bulk_copy = 1;             // aig_normalize_images with the frame resident in shared memory (0: two-pass per-thread kernel)
@@ -547,6 +550,22 @@ int allow_mask_smem(aig_handle* h) {
 }
 int mask_ctas_per_sm(size_t smem) {
     return static_cast<int>(std::max<size_t>(1, std::min<size_t>(8, kMaskSmemLimit / (smem + 4 * 1024))));
+}
+
+// The reference's two output sizes run the packed mask kernels (mask_packed_kernel.cuh).
+bool packed_size(const aig_handle* h, int out_h, int out_w) { return h->mask_packed && out_h == 224 && (out_w == 298 || out_w == 224); }
+template <int W, int H>
+int launch_resize_packed(aig_handle* h, const uint8_t* d_mask, int64_t n_frames, uint8_t* d_up, int slot) {
+    auto kernel = resize_mask_packed_kernel<W, H>;
+    const size_t smem = sizeof(ResizePackedSmem<W, H>);
+    if (!h->packed_attr_set[slot]) {
+        AIG_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        h->packed_attr_set[slot] = true;
+    }
+    LaunchScope scope(h, h->stream, kKindOther);
+    const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (smem + 1024))));
+    kernel<<<frames_grid(h, n_frames, per_sm), kPackedThreads, smem, h->stream>>>(d_mask, n_frames, d_up);
+    return scope.done("resize_mask_packed_kernel");
 }
 
 // heat_stream_kernel needs every output row pair to start on a 16-byte boundary and be a 16-byte multiple long.
@@ -957,6 +976,8 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
         h->heat_bulk_store = value != 0;
     } else if (key == "energy_heat_ws") {
         h->energy_heat_ws = value != 0;
+    } else if (key == "mask_packed") {
+        h->mask_packed = value != 0;
     } else if (key == "norm_bulk_copy") {
         h->norm_bulk_copy = value != 0;
 
@@ -1236,6 +1257,11 @@ int aig_resize_mask(aig_handle* h, const uint8_t* mask, int64_t n_frames, int ou
     const uint8_t* d_mask = io.in(mask, n * kFramePixels);
     uint8_t* d_up = io.out(mask_up, n * out_h * out_w);
     if (io.failed) return io.finish();
+    if (packed_size(h, out_h, out_w) && (reinterpret_cast<uintptr_t>(d_up) & 15u) == 0) {
+        rc = out_w == 298 ? launch_resize_packed<298, 224>(h, d_mask, n_frames, d_up, 0) : launch_resize_packed<224, 224>(h, d_mask, n_frames, d_up, 1);
+        if (rc != AIG_OK) return io.abort(rc);
+        return io.finish();
+    }
     const size_t smem = MaskTaps::bytes(out_h, out_w);
     rc = allow_mask_smem(h);
     if (rc != AIG_OK) return io.abort(rc);
@@ -1481,6 +1507,25 @@ int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, cons
     int64_t* d_pos = io.inout(pos_inout, static_cast<size_t>(k));
     int64_t* d_num = io.inout(num_inout, 1);
     if (io.failed) return io.finish();
+    if (packed_size(h, out_h, out_w)) {
+        auto go = [&](auto kernel, size_t smem, int slot) {
+            if (!h->packed_attr_set[slot]) {
+                AIG_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                h->packed_attr_set[slot] = true;
+            }
+            LaunchScope scope(h, h->stream, kKindOther);
+            const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (smem + 1024))));
+            kernel<<<frames_grid(h, n, per_sm), kPackedThreads, smem, h->stream>>>(
+                d_mask, d_xmin, d_xmax, d_ymin, d_ymax, n, d_thr, k, reinterpret_cast<long long*>(d_inter),
+                reinterpret_cast<long long*>(d_union), reinterpret_cast<unsigned long long*>(d_pos),
+                reinterpret_cast<unsigned long long*>(d_num));
+            return scope.done("ciou_packed_kernel");
+        };
+        rc = out_w == 298 ? go(ciou_packed_kernel<298, 224>, sizeof(CiouPackedSmem<298, 224>), 2)
+                          : go(ciou_packed_kernel<224, 224>, sizeof(CiouPackedSmem<224, 224>), 3);
+        if (rc != AIG_OK) return io.abort(rc);
+        return io.finish();
+    }
     const size_t smem = MaskTaps::bytes(out_h, out_w) + static_cast<size_t>(out_w + out_h);
     rc = allow_mask_smem(h);
     if (rc != AIG_OK) return io.abort(rc);

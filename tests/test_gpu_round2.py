@@ -468,3 +468,82 @@ def test_one_rank_nccl_communicator_runs_the_native_allreduce(path, torch):
         assert p._lib.aig_comm_init(p._h, bad, 1, 1) == -1              # rank out of range
     finally:
         p.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# packed mask kernels (mask_packed_kernel.cuh): the reference's two output sizes
+# ----------------------------------------------------------------------------------------------
+def _random_masks(n, seed):
+    """Blobs (mean-threshold masks of smooth maps), salt-and-pepper, stripes, empty and full frames."""
+    rng = np.random.default_rng(seed)
+    imgs = synth.smooth_images(n, seed)
+    e = imgs.sum(-1)
+    m = (e > e.mean(axis=(1, 2), keepdims=True)).astype(np.uint8)
+    m[n // 4:n // 2] = rng.random((n // 2 - n // 4, 36, 48)) > 0.5
+    m[0] = 0
+    m[1] = 1
+    m[2, ::2] = 1
+    m[2, 1::2] = 0
+    m[3, :, ::2] = 1
+    m[3, :, 1::2] = 0
+    m[4] = 7                                               # any non-zero byte counts as set
+    return m
+
+
+def _adversarial_boxes(n, seed, h, w):
+    xmin, xmax, ymin, ymax = [a.copy() for a in synth.flickr_boxes(n, seed, h, w)]
+    rng = np.random.default_rng(seed + 1)
+    k = n // 8
+    # identical triples, nested, disjoint, swapped corners, out of range, 8-row-chunk boundaries, one-pixel boxes
+    xmin[:k] = xmin[:k, :1]; xmax[:k] = xmax[:k, :1]; ymin[:k] = ymin[:k, :1]; ymax[:k] = ymax[:k, :1]
+    for i in range(k, 2 * k):
+        xmin[i] = [10, 20, 30]; xmax[i] = [w - 10, w - 20, w - 30]; ymin[i] = [8, 16, 23]; ymax[i] = [h - 9, h - 16, h - 24]
+    for i in range(2 * k, 3 * k):
+        a = rng.integers(-20, w + 20, (3, 2)); b = rng.integers(-20, h + 20, (3, 2))
+        xmin[i], xmax[i], ymin[i], ymax[i] = a[:, 0], a[:, 1], b[:, 0], b[:, 1]          # any order, any range, xmax may be 0
+    for i in range(3 * k, 4 * k):
+        x, y = rng.integers(0, w, 3), rng.integers(0, h, 3)
+        xmin[i], xmax[i], ymin[i], ymax[i] = x, np.maximum(x, 1), y, y                  # single pixels / columns
+    return xmin, xmax, ymin, ymax
+
+
+@pytest.mark.parametrize('shape', [(224, 298), (224, 224)])
+def test_packed_resize_mask_equals_generic_kernel_and_oracle(path, torch, shape):
+    masks = _random_masks(333, 11)
+    before = path.launch_count
+    got = path.resize_mask(masks, *shape)
+    assert path.launch_count - before == 1
+    path.set_option('mask_packed', 0)
+    try:
+        want = path.resize_mask(masks, *shape)
+    finally:
+        path.set_option('mask_packed', 1)
+    assert got.dtype == np.uint8 and np.array_equal(got, want)
+    for i in (0, 1, 2, 3, 4, 100, 332):
+        assert np.array_equal(got[i], oracle.resize_mask(masks[i], *shape))
+    # a device buffer that is not 16-byte aligned takes the generic kernel: same bytes
+    dev = torch.from_numpy(masks).cuda()
+    out = torch.zeros(333 * shape[0] * shape[1] + 4, dtype=torch.uint8, device='cuda')
+    view = out[4:].view(333, *shape)
+    path._check(path._lib.aig_resize_mask(path._h, dev.data_ptr(), 333, shape[0], shape[1], view.data_ptr()))
+    assert np.array_equal(view.cpu().numpy(), got)
+
+
+@pytest.mark.parametrize('shape', [(224, 298), (224, 224)])
+def test_packed_ciou_equals_generic_kernel_and_oracle(path, shape):
+    n = 640
+    masks = _random_masks(n, 12)
+    boxes = _adversarial_boxes(n, 13, *shape)
+    thr = np.linspace(0, 1, 101)
+    got = path.ciou_sweep(masks, *boxes, thr, out_hw=shape)
+    path.set_option('mask_packed', 0)
+    try:
+        want = path.ciou_sweep(masks, *boxes, thr, out_hw=shape)
+    finally:
+        path.set_option('mask_packed', 1)
+    for g, w in zip(got[:3], want[:3]):
+        assert np.array_equal(g, w)
+    assert got[3] == want[3] == n
+    sel = np.r_[0:8, n // 8 - 2:n // 8 + 2, n // 4:n // 4 + 4, 3 * n // 8 - 2:3 * n // 8 + 2, n - 4:n]
+    wi, wu, _, _ = oracle.flickr_sweep(masks[sel], *[b[sel] for b in boxes], thr, *shape)
+    assert np.array_equal(got[0][sel], wi) and np.array_equal(got[1][sel], wu)
