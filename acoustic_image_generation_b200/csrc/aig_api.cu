@@ -153,6 +153,7 @@ struct aig_handle {
     int heat_bulk_store = 1;            // 0: round-1 per-thread-store kernel for every shape (comparison runs)
     bool norm_bulk_attr_set = false;
     bool packed_attr_set[4] = {};
+    int packed_ctas[4] = {};
     int mask_packed = 1;                // aig_resize_mask / aig_ciou_sweep at 224 x 298 and 224 x 224 as the packed kernels (0: the generic kernels)
     bool energy_heat_ws_attr_set[4] = {};
     int energy_heat_ws = 1;             // aig_energy_heatmap as the warp-specialised kernel (0: heat_stream_kernel<true>, phases in sequence)
@@ -554,6 +555,17 @@ int mask_ctas_per_sm(size_t smem) {
 
 // The reference's two output sizes run the packed mask kernels (mask_packed_kernel.cuh).
 bool packed_size(const aig_handle* h, int out_h, int out_w) { return h->mask_packed && out_h == 224 && (out_w == 298 || out_w == 224); }
+// CTAs of a packed kernel that are resident per SM (asked of the runtime once): the grid is exactly one wave, a partial
+// second wave cost 25 % (ncu: 1.5 waves with a grid sized by shared memory alone).
+template <typename Kernel>
+int packed_ctas_per_sm(aig_handle* h, Kernel kernel, size_t smem, int slot) {
+    if (h->packed_ctas[slot] == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kPackedThreads, smem) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
+        h->packed_ctas[slot] = n;
+    }
+    return h->packed_ctas[slot];
+}
 template <int W, int H>
 int launch_resize_packed(aig_handle* h, const uint8_t* d_mask, int64_t n_frames, uint8_t* d_up, int slot) {
     auto kernel = resize_mask_packed_kernel<W, H>;
@@ -563,8 +575,7 @@ int launch_resize_packed(aig_handle* h, const uint8_t* d_mask, int64_t n_frames,
         h->packed_attr_set[slot] = true;
     }
     LaunchScope scope(h, h->stream, kKindOther);
-    const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (smem + 1024))));
-    kernel<<<frames_grid(h, n_frames, per_sm), kPackedThreads, smem, h->stream>>>(d_mask, n_frames, d_up);
+    kernel<<<frames_grid(h, n_frames, packed_ctas_per_sm(h, kernel, smem, slot)), kPackedThreads, smem, h->stream>>>(d_mask, n_frames, d_up);
     return scope.done("resize_mask_packed_kernel");
 }
 
@@ -1514,8 +1525,7 @@ int aig_ciou_sweep(aig_handle* h, const uint8_t* mask, const int32_t* xmin, cons
                 h->packed_attr_set[slot] = true;
             }
             LaunchScope scope(h, h->stream, kKindOther);
-            const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (smem + 1024))));
-            kernel<<<frames_grid(h, n, per_sm), kPackedThreads, smem, h->stream>>>(
+            kernel<<<frames_grid(h, n, packed_ctas_per_sm(h, kernel, smem, slot)), kPackedThreads, smem, h->stream>>>(
                 d_mask, d_xmin, d_xmax, d_ymin, d_ymax, n, d_thr, k, reinterpret_cast<long long*>(d_inter),
                 reinterpret_cast<long long*>(d_union), reinterpret_cast<unsigned long long*>(d_pos),
                 reinterpret_cast<unsigned long long*>(d_num));

@@ -13,6 +13,11 @@
 //     adding K = 32767 - T first puts "value > T" (T = half of full scale, exact) into bit 15 of each half;
 //   * a lane owns four adjacent columns: one 64-bit shared load per source row, reused by the output rows that
 //     interpolate between the same two source rows (five of six);
+//   * the vertical taps repeat every 56 output rows = 9 source rows (224 / 36 = 56 / 9), i.e. every 7 chunks of 8 rows:
+//     warp w of 7 takes chunks w, w + 7, w + 14, w + 21, whose source rows and weights are compile-time constants of w
+//     (a 7-way switch on the warp index): weights are immediates, shared-memory offsets are immediates, and which rows
+//     reuse the previous row's loads is decided by the compiler.  The clamped taps of the first and last rows fit the
+//     same pattern because the blended rows carry a copy of the first row above them and of the last row below;
 //   * resize: the four flags become four bytes with one PRMT, one shift and one AND, rows are staged in shared memory in
 //     chunks of 8 rows (a multiple of 16 bytes at both sizes) and leave the SM as bulk asynchronous copies;
 //   * consensus IoU: nothing is stored.  With at most three boxes, min(count, 2) = count - [count == 3], so
@@ -24,12 +29,18 @@
 // Both are bit-exact replacements (tests compare them with the generic kernels and the oracle).
 #pragma once
 
+#include <type_traits>
+
 #include "aig_common.cuh"
 #include "heatmap_kernel.cuh"   // linear_tap_exact
 
 namespace aig {
 
-constexpr int packed_gcd(int a, int b) { return b == 0 ? (a < 0 ? -a : a) : packed_gcd(b, a % b); }
+__host__ __device__ constexpr int packed_gcd(int a, int b) { return b == 0 ? (a < 0 ? -a : a) : packed_gcd(b, a % b); }
+__host__ __device__ constexpr int packed_floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+constexpr int kPackedWarps = 7;                    // H = 224: 28 chunks of 8 rows, four per warp
+constexpr int kPackedThreads = kPackedWarps * 32;
 
 template <int W, int H>
 struct PackedGeom {
@@ -42,18 +53,24 @@ struct PackedGeom {
     static constexpr int WP = (W + 3) & ~3;                        // row stride of the blended rows (uint16)
     static constexpr int STEPS = (W / 4 + (W % 4 ? 1 : 0) + 31) / 32;   // column steps of 32 lanes x 4 columns
     static constexpr int CHUNKS = H / 8;
+    static constexpr int PERIOD_OUT = H / packed_gcd(H, kFrameH);  // the vertical taps repeat every PERIOD_OUT output rows ...
+    static constexpr int PERIOD_SRC = kFrameH / packed_gcd(H, kFrameH);   // ... = PERIOD_SRC source rows
+    static constexpr int PERIODS = H / PERIOD_OUT;
+    // output row y (unclamped): between source rows lo and lo + 1 with weight n / YD on the latter.  Rows above the first
+    // source row (lo = -1) and below the last fit in because the blended rows are stored with one copy of the edge row
+    // on either side (index lo + 1 into PackedTaps::rows).
+    static __host__ __device__ constexpr int tap_lo(int y) { return packed_floor_div((2 * y + 1) * kFrameH - H, 2 * H); }
+    static __host__ __device__ constexpr int tap_n(int y) { return ((2 * y + 1) * kFrameH - H - tap_lo(y) * 2 * H) / FY; }
     static_assert((XD * YD) % 2 == 0 && XD * YD <= 65535, "two pixels per 32-bit multiply-add need 16-bit values");
     static_assert(W % 2 == 0 && (8 * W) % 16 == 0 && H % 8 == 0, "8-row chunks must be 16-byte multiples");
+    static_assert(PERIOD_OUT == 8 * kPackedWarps, "one chunk of every period per warp");
+    static_assert(tap_lo(0) == -1 && tap_lo(H - 1) == kFrameH - 1, "one padding row on either side is enough");
 };
-
-constexpr int kPackedWarps = 7;                    // H = 224: 28 chunks of 8 rows, four per warp
-constexpr int kPackedThreads = kPackedWarps * 32;
 
 template <int W, int H>
 struct PackedTaps {
     using G = PackedGeom<W, H>;
-    alignas(16) uint16_t rows[kFrameH][G::WP];     // horizontally blended source rows, values 0 .. XD
-    alignas(16) int ytap[H];                       // i0 | i1 << 8 | n << 16 (n = reduced weight of row i1)
+    alignas(16) uint16_t rows[kFrameH + 2][G::WP]; // horizontally blended source rows (values 0 .. XD); [0] = [1], [37] = [36]
     int x01[W];                                    // i0 | i1 << 16
     int xn[W];                                     // reduced weight of column i1
     uint8_t mask[kFramePixels];
@@ -63,13 +80,9 @@ struct PackedTaps {
             int i0, i1, r; linear_tap_exact(d, kFrameW, W, &i0, &i1, &r);
             x01[d] = i0 | (i1 << 16); xn[d] = r / G::FX;
         }
-        for (int d = tid; d < H; d += kPackedThreads) {
-            int i0, i1, r; linear_tap_exact(d, kFrameH, H, &i0, &i1, &r);
-            ytap[d] = i0 | (i1 << 8) | ((r / G::FY) << 16);
-        }
-        if constexpr (G::WP > W) {                   // padding columns: read by the last lane's 64-bit loads, never selected
+        if constexpr (G::WP > W) {                   // padding columns: read by the last lane's 64-bit loads, never used
             constexpr int kPad = G::WP - W;
-            for (int i = tid; i < kFrameH * kPad; i += kPackedThreads) rows[i / kPad][W + i % kPad] = 0;
+            for (int i = tid; i < (kFrameH + 2) * kPad; i += kPackedThreads) rows[i / kPad][W + i % kPad] = 0;
         }
     }
     __device__ __forceinline__ void load_mask(const uint8_t* src, int tid) {
@@ -86,37 +99,73 @@ struct PackedTaps {
 #pragma unroll
             for (int r = 0; r < kRowsPer; ++r) {
                 const uint8_t* m = mask + (r0 + r) * kFrameW;
-                rows[r0 + r][x] = static_cast<uint16_t>(m[c0] * (G::XD - n) + m[c1] * n);
+                const uint16_t v = static_cast<uint16_t>(m[c0] * (G::XD - n) + m[c1] * n);
+                rows[r0 + r + 1][x] = v;
+                if (r0 + r == 0) rows[0][x] = v;
+                if (r0 + r == kFrameH - 1) rows[kFrameH + 1][x] = v;
             }
         }
     }
     // flags of the four pixels (x .. x + 3) of one output row: bit 7 of byte j set iff pixel x + j is above one half.
-    // a, b: the lane's four blended values of the row's two source rows.
+    // a, b: the lane's four blended values of the row's two source rows, n the weight of b.
     static __device__ __forceinline__ unsigned int flags4(const uint2& a, const uint2& b, unsigned int n) {
         const unsigned int w0 = G::YD - n;
         unsigned int lo = a.x * w0 + G::KK; lo = b.x * n + lo;
         unsigned int hi = a.y * w0 + G::KK; hi = b.y * n + hi;
         return __byte_perm(lo, hi, 0x7531);
     }
+    // The 8 rows of chunk PHASE + 7 * period for columns x .. x + 3: emit(r, flags) for r = 0 .. 7.  Everything that depends
+    // on the row - its two source rows, its weight, whether the previous row's loads still serve - is a constant.
+    template <int PHASE, typename Emit>
+    __device__ __forceinline__ void chunk(int period, int x, Emit emit) const {
+        const uint16_t* base = &rows[period * G::PERIOD_SRC][x];
+        uint2 a = make_uint2(0u, 0u), b = a;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            constexpr int y0 = 8 * PHASE;
+            const int p = G::tap_lo(y0 + r) + 1, prev = r ? G::tap_lo(y0 + r - 1) + 1 : -5;
+            if (p == prev + 1) {
+                a = b;
+                b = *reinterpret_cast<const uint2*>(base + (p + 1) * G::WP);
+            } else if (p != prev) {
+                a = *reinterpret_cast<const uint2*>(base + p * G::WP);
+                b = *reinterpret_cast<const uint2*>(base + (p + 1) * G::WP);
+            }
+            emit(r, flags4(a, b, static_cast<unsigned int>(G::tap_n(y0 + r))));
+        }
+    }
 };
+
+// f(std::integral_constant<int, warp>) for the calling warp: every warp runs code specialised for its chunks
+template <typename F>
+__device__ __forceinline__ void packed_dispatch(int warp, F f) {
+    switch (warp) {
+        case 0: f(std::integral_constant<int, 0>{}); break;
+        case 1: f(std::integral_constant<int, 1>{}); break;
+        case 2: f(std::integral_constant<int, 2>{}); break;
+        case 3: f(std::integral_constant<int, 3>{}); break;
+        case 4: f(std::integral_constant<int, 4>{}); break;
+        case 5: f(std::integral_constant<int, 5>{}); break;
+        default: f(std::integral_constant<int, 6>{}); break;
+    }
+}
+static_assert(kPackedWarps == 7, "packed_dispatch lists the warps");
 
 // mask [n, 36, 48] u8 -> mask_up [n, H, W] u8 (1 iff bilinear(mask != 0) > 1/2).  mask_up must be 16-byte aligned.
 template <int W, int H>
 struct ResizePackedSmem {
     PackedTaps<W, H> t;
-    alignas(16) uint8_t stage[kPackedWarps][2][8 * W];
+    alignas(16) uint8_t stage[kPackedWarps][8 * W];   // one slot per warp: 44 KB in all at 224 x 298, five CTAs per SM
 };
 
 template <int W, int H>
 __global__ void __launch_bounds__(kPackedThreads)
 resize_mask_packed_kernel(const uint8_t* __restrict__ mask, long long n_frames, uint8_t* __restrict__ mask_up) {
     using G = PackedGeom<W, H>;
-    using T = PackedTaps<W, H>;
     extern __shared__ __align__(16) unsigned char s_packed_raw[];
     ResizePackedSmem<W, H>& s = *reinterpret_cast<ResizePackedSmem<W, H>*>(s_packed_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     s.t.build(tid);
-    unsigned int chunk_it = 0;
     for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
         __syncthreads();                                   // the previous frame's rows have been read
         s.t.load_mask(mask + frame * kFramePixels, tid);
@@ -124,48 +173,34 @@ resize_mask_packed_kernel(const uint8_t* __restrict__ mask, long long n_frames, 
         s.t.blend(warp, lane);
         __syncthreads();
         uint8_t* dst = mask_up + frame * static_cast<long long>(H) * W;
-        for (int c = warp; c < G::CHUNKS; c += kPackedWarps, ++chunk_it) {
-            const unsigned int buf = chunk_it & 1u;
-            if (chunk_it >= 2u) {                          // the copy issued two chunks ago has finished reading this buffer
-                if (lane == 0) bulk_wait_read<1>();
+        packed_dispatch(warp, [&](auto phase) {
+            constexpr int PHASE = decltype(phase)::value;
+            for (int period = 0; period < G::PERIODS; ++period) {
+                if (lane == 0) bulk_wait_read<0>();        // the previous chunk's copy has finished reading the slot
                 __syncwarp();
-            }
-            uint8_t* st = s.stage[warp][buf];
-            int yt[8];
-            {
-                const int4 t0 = *reinterpret_cast<const int4*>(&s.t.ytap[8 * c]), t1 = *reinterpret_cast<const int4*>(&s.t.ytap[8 * c + 4]);
-                yt[0] = t0.x; yt[1] = t0.y; yt[2] = t0.z; yt[3] = t0.w; yt[4] = t1.x; yt[5] = t1.y; yt[6] = t1.z; yt[7] = t1.w;
-            }
-#pragma unroll
-            for (int k = 0; k < G::STEPS; ++k) {
-                const int x = 4 * (lane + 32 * k);
-                if (x >= W) break;
-                uint2 a = make_uint2(0u, 0u), b = a;
-                int cur = -1;
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int pair = yt[r] & 0xffff;
-                    if (pair != cur) {                     // warp-uniform: five rows of six keep their source rows
-                        cur = pair;
-                        a = *reinterpret_cast<const uint2*>(&s.t.rows[pair & 0xff][x]);
-                        b = *reinterpret_cast<const uint2*>(&s.t.rows[pair >> 8][x]);
-                    }
-                    const unsigned int bytes = (T::flags4(a, b, static_cast<unsigned int>(yt[r]) >> 16) >> 7) & 0x01010101u;
-                    if (W % 4 == 0) {
-                        *reinterpret_cast<unsigned int*>(st + r * W + x) = bytes;
-                    } else {                               // rows start on 2-byte boundaries only
-                        *reinterpret_cast<unsigned short*>(st + r * W + x) = static_cast<unsigned short>(bytes);
-                        if (x + 2 < W) *reinterpret_cast<unsigned short*>(st + r * W + x + 2) = static_cast<unsigned short>(bytes >> 16);
-                    }
+                uint8_t* st = s.stage[PHASE];
+#pragma unroll 1                                           // (seven warps run seven different bodies: unrolled further, instruction fetch stalls them)
+                for (int k = 0; k < G::STEPS; ++k) {
+                    const int x = 4 * (lane + 32 * k);
+                    if (x >= W) break;
+                    s.t.template chunk<PHASE>(period, x, [&](int r, unsigned int flags) {
+                        const unsigned int bytes = (flags >> 7) & 0x01010101u;
+                        if (W % 4 == 0) {
+                            *reinterpret_cast<unsigned int*>(st + r * W + x) = bytes;
+                        } else {                           // rows start on 2-byte boundaries only
+                            *reinterpret_cast<unsigned short*>(st + r * W + x) = static_cast<unsigned short>(bytes);
+                            if (x + 2 < W) *reinterpret_cast<unsigned short*>(st + r * W + x + 2) = static_cast<unsigned short>(bytes >> 16);
+                        }
+                    });
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_store_s2g(dst + static_cast<long long>(PHASE + kPackedWarps * period) * 8 * W, smem_u32(st), 8 * W);
+                    bulk_commit();
                 }
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                bulk_store_s2g(dst + static_cast<long long>(c) * 8 * W, smem_u32(st), 8 * W);
-                bulk_commit();
-            }
-        }
+        });
     }
     if (lane == 0) bulk_wait_all<0>();                     // shared memory must outlive the copies that read it
 }
@@ -179,7 +214,7 @@ template <int W, int H>
 struct CiouPackedSmem {
     PackedTaps<W, H> t;
     int rect[kPackedRects][4];                     // xa, xb, ya, yb (inclusive; xa > xb: empty)
-    unsigned int rowmask[PackedGeom<W, H>::CHUNKS][kPackedRects];   // 0x01010101 * (bit r: row 8 c + r inside the rectangle)
+    unsigned int rowmask[kPackedRects][PackedGeom<W, H>::CHUNKS];   // 0x01010101 * (bit r: row 8 c + r inside the rectangle)
     unsigned int active;                           // bit R: rectangle R is not empty
     int count[kPackedWarps][kPackedRects];
     unsigned int pos[kPackedMaxThresholds];
@@ -187,13 +222,12 @@ struct CiouPackedSmem {
 };
 
 template <int W, int H>
-__global__ void __launch_bounds__(kPackedThreads)
+__global__ void __launch_bounds__(kPackedThreads, 5)
 ciou_packed_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ xmin, const int* __restrict__ xmax,
                    const int* __restrict__ ymin, const int* __restrict__ ymax, long long n, const double* __restrict__ thr,
                    int k_thr, long long* __restrict__ inter2_out, long long* __restrict__ union2_out,
                    unsigned long long* __restrict__ pos, unsigned long long* __restrict__ num) {
     using G = PackedGeom<W, H>;
-    using T = PackedTaps<W, H>;
     extern __shared__ __align__(16) unsigned char s_packed_raw[];
     CiouPackedSmem<W, H>& s = *reinterpret_cast<CiouPackedSmem<W, H>*>(s_packed_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -233,64 +267,55 @@ ciou_packed_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ xmi
         }
         __syncthreads();
         for (int i = tid; i < G::CHUNKS * kPackedRects; i += kPackedThreads) {
-            const int c = i / kPackedRects, r = i % kPackedRects;
+            const int r = i / G::CHUNKS, c = i % G::CHUNKS;
             const int ya = s.rect[r][2] - 8 * c, yb = s.rect[r][3] - 8 * c;       // rows of this chunk inside: [max(ya, 0), min(yb, 7)]
             unsigned int bits = 0;
             if (s.rect[r][0] <= s.rect[r][1] && yb >= 0 && ya <= 7)
                 bits = (0xffu >> (7 - min(yb, 7))) & (0xffu << max(ya, 0));
-            s.rowmask[c][r] = bits * 0x01010101u;
+            s.rowmask[r][c] = bits * 0x01010101u;
         }
         s.t.blend(warp, lane);
         __syncthreads();
+        // Per column step k and chunk: bit r of byte j of `flags` says pixel (8 chunk + r, 4 (lane + 32 k) + j) is predicted; a
+        // rectangle's count grows by the bits inside its columns (colsel) and rows (rowmask).  Both loops stay rolled: seven
+        // warps run seven different bodies, and unrolled further (4096 instructions) instruction fetch stalled them
+        // (ncu: 7.5 warps waiting for instructions per instruction issued).
         const unsigned int active = s.active;
         int cnt[kPackedRects];
 #pragma unroll
         for (int r = 0; r < kPackedRects; ++r) cnt[r] = 0;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < G::STEPS; ++k) {
-            const int x = 4 * (lane + 32 * k);
+            const unsigned int x = 4 * (lane + 32 * k);
             if (x >= W) break;
-            unsigned int colsel[kPackedRects];             // 0xff in byte j iff column x + j lies inside the rectangle
+            unsigned int colsel[kPackedRects];              // 0xff in byte j iff column x + j lies inside the rectangle
 #pragma unroll
             for (int r = 0; r < kPackedRects; ++r) {
-                const int xa = s.rect[r][0], xb = s.rect[r][1];
-                unsigned int sel = 0;
+                colsel[r] = 0;
+                if (active & (1u << r)) {                   // warp-uniform
+                    const unsigned int xa = s.rect[r][0], span = s.rect[r][1] - s.rect[r][0];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) sel |= (x + j >= xa && x + j <= xb) ? (0xffu << (8 * j)) : 0u;
-                colsel[r] = sel;
-            }
-            for (int c = warp; c < G::CHUNKS; c += kPackedWarps) {
-                int yt[8];
-                {
-                    const int4 t0 = *reinterpret_cast<const int4*>(&s.t.ytap[8 * c]), t1 = *reinterpret_cast<const int4*>(&s.t.ytap[8 * c + 4]);
-                    yt[0] = t0.x; yt[1] = t0.y; yt[2] = t0.z; yt[3] = t0.w; yt[4] = t1.x; yt[5] = t1.y; yt[6] = t1.z; yt[7] = t1.w;
+                    for (int j = 0; j < 4; ++j) colsel[r] |= (x + j - xa <= span) ? (0xffu << (8 * j)) : 0u;
                 }
-                uint2 a = make_uint2(0u, 0u), b = a;
-                int cur = -1;
-                unsigned int flags = 0;                     // bit r of byte j: pixel (8 c + r, x + j) is predicted
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int pair = yt[r] & 0xffff;
-                    if (pair != cur) {
-                        cur = pair;
-                        a = *reinterpret_cast<const uint2*>(&s.t.rows[pair & 0xff][x]);
-                        b = *reinterpret_cast<const uint2*>(&s.t.rows[pair >> 8][x]);
-                    }
-                    flags = (flags >> 1) | (T::flags4(a, b, static_cast<unsigned int>(yt[r]) >> 16) & 0x80808080u);
-                }
-#pragma unroll
-                for (int r = 0; r < kPackedRects; ++r)
-                    if (active & (1u << r)) cnt[r] += __popc(flags & colsel[r] & s.rowmask[c][r]);
             }
+            packed_dispatch(warp, [&](auto phase) {
+                constexpr int PHASE = decltype(phase)::value;
+#pragma unroll 1
+                for (int period = 0; period < G::PERIODS; ++period) {
+                    unsigned int flags = 0;
+                    s.t.template chunk<PHASE>(period, x, [&](int, unsigned int fl) { flags = (flags >> 1) | (fl & 0x80808080u); });
+                    const unsigned int* rowmask = &s.rowmask[0][PHASE + kPackedWarps * period];
+#pragma unroll
+                    for (int r = 0; r < kPackedRects; ++r)
+                        if (active & (1u << r)) cnt[r] += __popc(flags & colsel[r] & rowmask[r * G::CHUNKS]);
+                }
+            });
         }
 #pragma unroll
         for (int r = 0; r < kPackedRects; ++r) {
-            if (active & (1u << r)) {                       // warp-uniform
-                const int v = warp_sum(cnt[r]);
-                if (lane == 0) s.count[warp][r] = v;
-            } else if (lane == 0) {
-                s.count[warp][r] = 0;
-            }
+            int v = 0;
+            if (active & (1u << r)) v = warp_sum(cnt[r]);
+            if (lane == 0) s.count[warp][r] = v;
         }
         __syncthreads();
         if (tid == 0) {
