@@ -96,14 +96,17 @@ struct PackedTaps {
             if (x >= W) continue;
             const int xi = x01[x], n = xn[x];
             const int c0 = xi & 0xffff, c1 = xi >> 16;
+            uint16_t first = 0, last = 0;
 #pragma unroll
             for (int r = 0; r < kRowsPer; ++r) {
                 const uint8_t* m = mask + (r0 + r) * kFrameW;
                 const uint16_t v = static_cast<uint16_t>(m[c0] * (G::XD - n) + m[c1] * n);
                 rows[r0 + r + 1][x] = v;
-                if (r0 + r == 0) rows[0][x] = v;
-                if (r0 + r == kFrameH - 1) rows[kFrameH + 1][x] = v;
+                if (r == 0) first = v;
+                if (r == kRowsPer - 1) last = v;
             }
+            if (r0 == 0) rows[0][x] = first;                                   // the copies above the first and below the last row
+            if (r0 + kRowsPer == kFrameH) rows[kFrameH + 1][x] = last;
         }
     }
     // flags of the four pixels (x .. x + 3) of one output row: bit 7 of byte j set iff pixel x + j is above one half.
