@@ -155,7 +155,7 @@ struct aig_handle {
     bool packed_attr_set[4] = {};
     int packed_ctas[4] = {};
     int mask_packed = 1;                // aig_resize_mask / aig_ciou_sweep at 224 x 298 and 224 x 224 as the packed kernels (0: the generic kernels)
-    bool energy_heat_ws_attr_set[4] = {};
+    bool energy_heat_ws_attr_set[5] = {};
     int energy_heat_ws = 1;             // aig_energy_heatmap as the warp-specialised kernel (0: heat_stream_kernel<true>, phases in sequence)
     int norm_bulk_copy = 1;             // aig_normalize_images with the frame resident in shared memory (0: two-pass per-thread kernel)
     int small_batch_frames = 0;         // below this many frames a frame is split over a cluster of 8 CTAs; 0: SM count
@@ -636,6 +636,18 @@ int launch_energy_heat_ws_variant(aig_handle* h, const HeatStreamArgs& args, int
 }
 template <typename C>
 int launch_energy_heat_ws(aig_handle* h, const HeatStreamArgs& args, int base) {
+    if (h->debug_jitter != 0) {                  // the jittered build exists for the generic-size kernel only (race stress tests)
+        HeatStreamArgs jittered = args;
+        jittered.jitter_seed = h->debug_jitter;
+        auto kernel = energy_heat_ws_kernel<C, 2, 0, 0, true>;
+        if (!h->energy_heat_ws_attr_set[base + 4]) {
+            AIG_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ws_smem_limit<C>())));
+            h->energy_heat_ws_attr_set[base + 4] = true;
+        }
+        LaunchScope scope(h, h->stream, kKindEnergy);
+        kernel<<<frames_grid(h, args.n_frames, C::CTAS), C::THREADS, energy_heat_ws_smem<C>(args.out_h, args.out_w), h->stream>>>(jittered);
+        return scope.done("energy_heat_ws_kernel<jitter>");
+    }
     if (args.out_h == 224 && args.out_w == 298) return launch_energy_heat_ws_variant<C, 2, 298, 224>(h, args, base + 0);
     if (args.out_h == 224 && args.out_w == 224) return launch_energy_heat_ws_variant<C, 4, 224, 224>(h, args, base + 1);
     if (args.out_w % 4 == 0) return launch_energy_heat_ws_variant<C, 4, 0, 0>(h, args, base + 2);

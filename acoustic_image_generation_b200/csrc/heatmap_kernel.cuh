@@ -350,6 +350,7 @@ struct HeatStreamArgs {
     long long n_frames;
     int out_h, out_w;
     float* heat;
+    unsigned int jitter_seed;   // energy_heat_ws_kernel<..., JITTER = true> only ("debug_jitter")
 };
 
 // (d = b - a) once per column pair, then per output row v = d * wy + a, (v - mn) * inv: the roundings of lerp_norm2.
@@ -666,7 +667,10 @@ __host__ __device__ inline size_t energy_heat_ws_smem(int out_h, int out_w) {
     return ((heat_stream_layout(out_h, out_w, false, C::HW, C::SLOTS == 1).total + 15u) & ~15u) + sizeof(WsShared<C>) + 16;
 }
 
-template <typename C, int VEC, int W, int H>
+// JITTER = true is the "debug_jitter" build: both roles spin for pseudo-random times around their barrier operations
+// (aig_common.cuh: jitter_spin), which walks the hand-over through every relative order of the two sides; its results
+// must still equal the sequential kernel's (tests: test_race_stress_jittered_energy_heat_ws_kernel).
+template <typename C, int VEC, int W, int H, bool JITTER = false>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS)
 energy_heat_ws_kernel(const __grid_constant__ HeatStreamArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -678,6 +682,7 @@ energy_heat_ws_kernel(const __grid_constant__ HeatStreamArgs a) {
     if (kOneSlot) hs.t = reinterpret_cast<float*>(ws.map[0]);
     const uint32_t full = smem_u32(&ws.bar[0]), empty = smem_u32(&ws.bar[2]);        // + 8 * slot
     const int tid = threadIdx.x;
+    unsigned int jitter_counter = 0;
     if (tid == 0) {
         for (int s = 0; s < C::SLOTS; ++s) {
             mbar_init(full + 8 * s, C::ET);                  // every energy thread arrives (release of its map values)
@@ -704,7 +709,9 @@ energy_heat_ws_kernel(const __grid_constant__ HeatStreamArgs a) {
             const FrameNormFast norm(lo, __fsub_rn(hi, lo));
             double* energy = s.energy[0] ? s.energy[0] + frame * kFramePixels : nullptr;
             double* map = ws.map[slot];
+            if (JITTER) jitter_spin(a.jitter_seed, 11u, jitter_counter);
             mbar_wait(empty + 8 * slot, (use & 1u) ^ 1u);                      // the heat-map warps are done with this slot's last frame
+            if (JITTER) jitter_spin(a.jitter_seed, 12u, jitter_counter);
             frame_energy_pixels<C::ET, false>(img, 0, kFramePixels, s.normalize_first != 0, norm, nullptr, energy, map,
                                               ws.rare_bits, ws.tab, nullptr, et);
             group_sync();
@@ -721,6 +728,7 @@ energy_heat_ws_kernel(const __grid_constant__ HeatStreamArgs a) {
                     for (int p = et; p < kFramePixels; p += C::ET)
                         s.mask[0][frame * kFramePixels + p] = map[p] > mean ? 1 : 0;
             }
+            if (JITTER) jitter_spin(a.jitter_seed, 13u, jitter_counter);
             mbar_arrive(full + 8 * slot);                                      // release: this thread's map values are visible
         }
         return;
@@ -736,6 +744,7 @@ energy_heat_ws_kernel(const __grid_constant__ HeatStreamArgs a) {
     const long long frame_values = static_cast<long long>(out_h) * out_w;
     for (long long frame = blockIdx.x; frame < a.n_frames; frame += gridDim.x, ++it) {
         const unsigned int slot = kOneSlot ? 0u : it & 1u, use = kOneSlot ? it : it >> 1;
+        if (JITTER) jitter_spin(a.jitter_seed, 14u, jitter_counter);
         mbar_wait_relaxed(full + 8 * slot, use & 1u, 256);                     // usually microseconds: the float64 warps are the slower side
         double e[kPerThread];
 #pragma unroll
@@ -745,9 +754,13 @@ energy_heat_ws_kernel(const __grid_constant__ HeatStreamArgs a) {
         }
         // two slots: the energies are in registers, the slot is free.  One slot: t[] lives in it until the horizontal pass
         // is over (heat_phase's first barrier orders every thread's reads of the map above before anyone writes t).
+        if (JITTER) jitter_spin(a.jitter_seed, 15u, jitter_counter);
         if (!kOneSlot) mbar_arrive(empty + 8 * slot);
         heat_phase<C::HT, VEC, W, H>(e, hs, ws.red64, ws.red32, out_h, out_w, a.heat + frame * frame_values, ht, chunk_it,
-                                     heat_sync, [] {}, [&] { if (kOneSlot) mbar_arrive(empty); });
+                                     heat_sync, [] {}, [&] {
+                                         if (JITTER) jitter_spin(a.jitter_seed, 16u, jitter_counter);
+                                         if (kOneSlot) mbar_arrive(empty);
+                                     });
     }
     if ((ht & 31) == 0) bulk_wait_all<0>();       // shared memory must outlive the copies that read it
 }

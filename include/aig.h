@@ -376,6 +376,9 @@ int64_t aig_launch_count(const aig_handle* h);
  *                        (heat_stream_kernel); 0: the round-1 kernel with per-thread stores, for comparison runs
  *   "energy_heat_ws"     1 (default): aig_energy_heatmap runs the warp-specialised kernel (float64 warps and heat-map warps
  *                        of a CTA working on consecutive frames, two CTAs per SM); 0: the same warps do both phases in sequence
+ *   "mask_packed"        1 (default): aig_resize_mask and aig_ciou_sweep at the reference's output sizes (224 x 298, 224 x 224)
+ *                        run the packed kernels (two pixels per 32-bit multiply-add, compile-time taps, bulk-copy stores /
+ *                        rectangle counts); 0: the generic kernels that serve every other size, for comparison runs
  *   "norm_bulk_copy"     1 (default): aig_normalize_images keeps each frame in shared memory between one bulk asynchronous
  *                        load and one bulk store (normalize_bulk_kernel); 0: the two-pass per-thread kernel, for comparison
  *   "small_batch_frames" batches with fewer frames than this spread each frame over a cluster of 8 CTAs (aig_energy,
@@ -383,7 +386,8 @@ int64_t aig_launch_count(const aig_handle* h);
  *                        the one-CTA-per-frame persistent kernel; 0 (default) = the device's SM count
  *   "debug_jitter"       non-zero seed: aig_mfcc_energy runs the jittered build of the persistent kernel, in which the TMA
  *                        producer, the MFCC consumers and the energy warps spin for pseudo-random times before every
- *                        barrier wait / arrive (race stress test standing in for compute-sanitizer); 0 (default): off
+ *                        barrier wait / arrive (race stress test standing in for compute-sanitizer), and aig_energy_heatmap
+ *                        the jittered build of the warp-specialised kernel (float64 warps / heat-map warps); 0 (default): off
  *   "profile"            1: bracket every MFCC / energy kernel launch with CUDA events on the stream it
  *                        is launched on (read back with aig_profile_read); 0 (default): off
  * Unknown names or out-of-range values return AIG_ERR_ARGUMENT. */

@@ -437,6 +437,40 @@ def test_race_stress_jittered_persistent_kernel(torch):
     assert not failures, failures[:10]
 
 
+def test_race_stress_jittered_energy_heat_ws_kernel(torch):
+    """The warp-specialised aig_energy_heatmap kernel hands each energy map from its float64 warps to its heat-map warps
+    through one shared-memory slot and a full / empty mbarrier pair (and the slot doubles as the heat-map warps' t[]).  Its
+    jittered build spins both sides for pseudo-random times around every wait / arrive; 120 random (frame count, seed, size,
+    normalise) cases must reproduce the sequential kernel (energy_heat_ws = 0) bit for bit: energies, masks, heat maps."""
+    rng = np.random.default_rng(77)
+    pool = torch.from_numpy(_images_with_hard_cases(64, 90)).cuda()
+    ref_path = aig.AcousticPath(0)
+    ref_path.set_option('energy_heat_ws', 0)
+    jit_path = aig.AcousticPath(0)
+    failures = []
+    try:
+        for case in range(120):
+            n = int(rng.integers(148, 700))
+            seed = int(rng.integers(1, 2 ** 31 - 1))
+            shape = [(224, 298), (224, 224), (96, 130), (50, 64)][int(rng.integers(0, 4))]
+            norm = bool(rng.integers(0, 2))
+            imgs = pool[torch.from_numpy(rng.integers(0, len(pool), n)).cuda()].contiguous()
+            want = ref_path.energy_heatmap(imgs, norm, *shape)
+            jit_path.set_option('debug_jitter', seed)
+            before = jit_path.launch_count
+            got = jit_path.energy_heatmap(imgs, norm, *shape)
+            assert jit_path.launch_count - before == 1
+            for name, x, y in zip(('energy', 'mask', 'heat'), got, want):
+                same = torch.equal(x.view(torch.int64) if x.dtype == torch.float64 else x.view(torch.int32) if x.dtype == torch.float32 else x,
+                                   y.view(torch.int64) if y.dtype == torch.float64 else y.view(torch.int32) if y.dtype == torch.float32 else y)
+                if not same:
+                    failures.append((case, n, seed, shape, name))
+    finally:
+        ref_path.close()
+        jit_path.close()
+    assert not failures, failures[:10]
+
+
 # ----------------------------------------------------------------------------------------------
 # NCCL on one GPU
 # ----------------------------------------------------------------------------------------------
