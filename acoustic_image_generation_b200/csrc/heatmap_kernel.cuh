@@ -631,15 +631,16 @@ heat_stream_kernel(const __grid_constant__ HeatStreamArgs a) {
 //   ET threads          find_logen of frame i + 1 (+ optional min-max, mean, mask, energy output) into map[slot]
 //   HW warps            heat_phase() of frame i: normalise, up-sample, stage rows, bulk copies
 // The map is handed over through a full / empty mbarrier pair per slot, as the persistent MFCC + energy kernel hands its
-// frames to the energy warps.  The shape in use (WsTwin): two CTAs of 256 + 256 threads per SM - two independent
-// pipelines whose min-max / pixel-loop / mean phases interleave, 6.75 pixel rounds per frame (the last one 3/4 full) -
-// with ONE map slot whose first half doubles as the heat-map phase's float32 t[] (the energies are in the heat-map
-// threads' registers by then; the slot goes back to the float64 warps after the horizontal pass), which is what lets two
-// CTAs fit in 227 KB.  One CTA of 512 + 512 threads with two map slots (WsConfig<512, 16, 1, 2>) measured 6.85 M frames/s
-// at 224 x 298 against 7.69 M for the twin form and 7.02 M for heat_stream_kernel<true>.  ncu on the twin form
-// (profiles/r02_ncu_energy_heat_ws.csv): FP64 pipe 31 %, shared-memory wavefronts 66 % of peak - the exp-table look-ups
-// of the float64 warps and the row passes of the heat-map warps share one shared-memory pipe, which is why the overlap
-// pays 10 % and not the 20 % two perfectly chained kernels would give (8.4 M).
+// frames to the energy warps.  The shape in use (WsTwin): two CTAs of 352 + 160 threads per SM - two independent
+// pipelines whose min-max / pixel-loop / mean phases interleave, 4.9 pixel rounds per frame - with ONE map slot whose
+// first half doubles as the heat-map phase's float32 t[] (the energies are in the heat-map threads' registers by then;
+// the slot goes back to the float64 warps after the horizontal pass), which is what lets two CTAs fit in 227 KB.
+// How the 512 threads (64 registers each: the whole register file with two CTAs) are split was measured at 224 x 298
+// (M frames/s, 8192 frames; heat_stream_kernel<true>: 7.03): float64 + heat-map threads 256 + 256: 7.70, 288 + 224: 7.95,
+// 320 + 192: 7.83, 352 + 160: 8.48, 352 + 128: 8.24, 384 + 128: 8.37 (8.14 with two map slots), 416 + 96: 7.56,
+// 448 + 64: 5.88; one CTA of 512 + 512 per SM with two map slots: 6.85.  The float64 side is the critical path and is
+// latency-bound at this occupancy (ncu, 256 + 256: FP64 pipe 31 %, issue slots 52 %, 5.5 warps per issue waiting on the
+// long scoreboard), so it gets the warps; five heat-map warps per CTA still keep up (20 M frames/s with 24 per SM alone).
 template <int ET_, int HW_, int CTAS_, int SLOTS_>
 struct WsConfig {
     static constexpr int ET = ET_, HW = HW_, CTAS = CTAS_, SLOTS = SLOTS_;
@@ -647,7 +648,7 @@ struct WsConfig {
     static_assert(HW <= kHeatMaxWarps, "reduction scratch of heat_phase");
     static_assert(SLOTS == 1 || SLOTS == 2, "map slots");
 };
-using WsTwin = WsConfig<256, 8, 2, 1>;
+using WsTwin = WsConfig<352, 5, 2, 1>;
 
 template <typename C>
 struct WsShared {                      // behind the heat-map phase's rows / staging slots / taps in dynamic shared memory
@@ -712,6 +713,7 @@ energy_heat_ws_kernel(const __grid_constant__ HeatStreamArgs a) {
             if (JITTER) jitter_spin(a.jitter_seed, 11u, jitter_counter);
             mbar_wait(empty + 8 * slot, (use & 1u) ^ 1u);                      // the heat-map warps are done with this slot's last frame
             if (JITTER) jitter_spin(a.jitter_seed, 12u, jitter_counter);
+            // (the cp.async input staging of stage2_kernel was measured here too: 8.18 M frames/s against 8.48 M without)
             frame_energy_pixels<C::ET, false>(img, 0, kFramePixels, s.normalize_first != 0, norm, nullptr, energy, map,
                                               ws.rare_bits, ws.tab, nullptr, et);
             group_sync();
