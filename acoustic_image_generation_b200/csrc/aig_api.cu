@@ -612,10 +612,9 @@ int launch_heat_stream(aig_handle* h, const HeatStreamArgs& args) {
 }
 
 // aig_energy_heatmap as one warp-specialised launch (energy_heat_ws_kernel): float64 warps and heat-map warps of a CTA
-// overlap, two CTAs of 256 + 256 threads per SM (WsTwin).  Taken when its rows and staging slots fit in half an SM's
-// shared memory (both of the reference's sizes do); otherwise, or with option energy_heat_ws = 0, heat_stream_kernel<true>.
-// (One CTA of 512 + 512 threads with two map slots, WsConfig<512, 16, 1, 2>, was measured too: 6.85 M frames/s against
-// 7.69 M for the twin form and 7.02 M for the sequential kernel - a lone float64 group cannot overlap its own phases.)
+// overlap, two CTAs of 352 + 160 threads per SM (WsTwin; the other splits measured are listed in heatmap_kernel.cuh).
+// Taken when its rows and staging slots fit in half an SM's shared memory (both of the reference's sizes do); otherwise,
+// or with option energy_heat_ws = 0, heat_stream_kernel<true>.
 template <typename C>
 size_t ws_smem_limit() { return std::min<size_t>((228 * 1024 - C::CTAS * 1024) / C::CTAS / 16 * 16, 227 * 1024); }
 template <typename C>
