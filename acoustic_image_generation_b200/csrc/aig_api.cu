@@ -156,6 +156,8 @@ struct aig_handle {
     int packed_ctas[4] = {};
     int mask_packed = 1;                // aig_resize_mask / aig_ciou_sweep at 224 x 298 and 224 x 224 as the packed kernels (0: the generic kernels)
     bool energy_heat_ws_attr_set[5] = {};
+    int overlay_luma = 1;               // aig_overlay keeps the luma plane of a frame in shared memory between its passes (0: BGR read twice)
+    bool overlay_luma_attr_set = false;
     int energy_heat_ws = 1;             // aig_energy_heatmap as the warp-specialised kernel (0: heat_stream_kernel<true>, phases in sequence)
     int norm_bulk_copy = 1;             // aig_normalize_images with the frame resident in shared memory (0: two-pass per-thread kernel)
     int small_batch_frames = 0;         // below this many frames a frame is split over a cluster of 8 CTAs; 0: SM count
@@ -996,6 +998,8 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
         h->small_host_bytes = static_cast<int>(value);
     } else if (key == "heat_bulk_store") {
         h->heat_bulk_store = value != 0;
+    } else if (key == "overlay_luma") {
+        h->overlay_luma = value != 0;
     } else if (key == "energy_heat_ws") {
         h->energy_heat_ws = value != 0;
     } else if (key == "mask_packed") {
@@ -1766,7 +1770,16 @@ int aig_overlay(aig_handle* h, const float* heat, const uint8_t* bgr, int64_t n_
     // one CTA per frame, handed out by the hardware as CTAs retire: a persistent grid of SM-count multiples ends on a
     // partial wave worth up to a whole frame time (2048 frames on 1184 CTAs: 2 rounds for 1.73 frames per CTA)
     const unsigned overlay_grid = static_cast<unsigned>(std::min<int64_t>(n_frames, 1 << 20));
-    if (vec)
+    // with a frame of up to 80 k pixels the luma plane stays in shared memory between the two passes (two CTAs per SM)
+    const size_t luma_bytes = px;
+    if (vec && d_bgr != nullptr && h->overlay_luma && luma_bytes <= kOverlayLumaMaxBytes) {
+        auto kernel = overlay_kernel<4, true>;
+        if (!h->overlay_luma_attr_set) {
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kOverlayLumaMaxBytes));
+            h->overlay_luma_attr_set = true;
+        }
+        kernel<<<overlay_grid, kOverlayThreads, luma_bytes, h->stream>>>(d_heat, d_bgr, n_frames, static_cast<int>(px), alpha, d_lut, d_out);
+    } else if (vec)
         overlay_kernel<4><<<overlay_grid, kOverlayThreads, 0, h->stream>>>(d_heat, d_bgr, n_frames, static_cast<int>(px), alpha, d_lut, d_out);
     else
         overlay_kernel<1><<<overlay_grid, kOverlayThreads, 0, h->stream>>>(d_heat, d_bgr, n_frames, static_cast<int>(px), alpha, d_lut, d_out);

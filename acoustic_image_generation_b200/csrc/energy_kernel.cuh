@@ -587,6 +587,9 @@ stage2_kernel(const __grid_constant__ Stage2Args a) {
 
     for (long long frame = blockIdx.x; frame < a.n_frames; frame += gridDim.x) {
         const float* img = a.img[group] + frame * kFrameValues;
+        // (asking this CTA's next image into L2 here - prefetch.global.L2, 10 lines per thread - was measured: 14.05 M frames/s
+        // against 14.5 M, and 8.15 M against 8.48 M in the warp-specialised energy + heat-map kernel: these kernels do not wait
+        // on DRAM, the float64 pipe is their bound)
         float lo = 0.f, hi = 1.f;
         if (a.normalize_first) group_minmax(img, kFrameValues / 4, gt, kEnergyThreads, g.red, group_sync, lo, hi);
         const FrameNormFast norm(lo, __fsub_rn(hi, lo));        // max(x - min) == fl(max - min): rounding is monotonic

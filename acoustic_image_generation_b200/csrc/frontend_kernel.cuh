@@ -263,41 +263,81 @@ __global__ void triplet_mse_finish_kernel(const double* __restrict__ partial, in
 // normalised and quantised to 256 levels - then imshow(map, cmap=jet, alpha=0.7): the normalised heat map goes through
 // matplotlib's 256-entry jet table and is alpha-blended over the gray image.  One CTA per frame; out is RGB8.
 // jet_lut: 256 x 3 uint8.  Without a frame (bgr == nullptr) the colour-mapped heat map alone is written.
-// Per CTA: s_jet[j] = jet[j] * alpha (or jet[j] itself without a frame); per frame: s_gray[y] = quantised gray level of
-// luma y times (1 - alpha) - the blend of a pixel is then one table row plus one table value, three adds, three
-// roundings, with the reference's operation order (products rounded separately, then added).
+// Per CTA: s_jet[j] = jet[j] * alpha (or jet[j] itself without a frame), eight conflict-free copies; per frame: the gray
+// level of a luma is one multiply-high by the frame's reciprocal (GrayLevels) - the blend of a pixel is then one table row
+// plus one product, three adds, three roundings, with the reference's operation order (products rounded separately, then added).
 // VEC = 4: four pixels per thread (float4 heat, 3 x 32-bit BGR in, 3 x 32-bit RGB out); needs n_pixels % 4 == 0 and
 // 16 / 4 / 4-byte aligned heat / bgr / out.  VEC = 1: any geometry.
 __device__ __forceinline__ int luma15(unsigned b, unsigned g, unsigned r) {
     return static_cast<int>((b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15);
 }
 
-constexpr int kOverlayThreads = 512;     // 2 CTAs per SM: ~300 frames in flight, whose BGR images (200 KB each) stay in L2 between the two passes
+// imshow(gray, cmap=gray): level = min(int(fl(fl((y - lo) / (hi - lo)) * 256)), 255).  With a = y - lo <= b = hi - lo <= 255 the
+// float32 quotient can only land on the other side of a multiple of 1/256 if 256 a / b is within 2^-24 of an integer without
+// being one, and its distance to the next integer is at least 1 / 255: the level IS the integer quotient 256 a / b, which
+// one multiply-high by a per-frame reciprocal returns exactly (n = 256 a <= 65 280, M = floor(2^32 / b) + 1 overshoots
+// 2^32 / b by e / b with e <= b, and n e < 2^32).  b = 1: M = 2^32 - 1 gives 0 and 255.  b = 0 (constant frame): level 0.
+struct GrayLevels {
+    unsigned lo8, m;          // lo << 8, reciprocal
+    float keep;               // 1 - alpha
+    __device__ __forceinline__ GrayLevels(int lo, int hi, float keep_) : lo8(static_cast<unsigned>(lo) << 8), keep(keep_) {
+        const unsigned b = static_cast<unsigned>(hi - lo);
+        m = b == 0u ? 0u : b == 1u ? 0xffffffffu : 0xffffffffu / b + 1u;      // a power of two gets 2^32 / b itself (e = 0), every other b floor(2^32 / b) + 1
+    }
+    // y8 = luma << 8; returns fl(level * (1 - alpha))
+    __device__ __forceinline__ float operator()(unsigned y8) const {
+        return __fmul_rn(static_cast<float>(min(__umulhi(y8 - lo8, m), 255u)), keep);
+    }
+};
 
-template <int VEC>
+// Pixel quads ahead (per thread, in strides of the CTA) whose lines are asked into L2 (prefetch.global.L2) while the current
+// ones are worked on; the first kOverlayPrefetch quads of the heat map are asked for at the end of the luma pass.  The kernel
+// was short of bytes in flight, not of bandwidth or issue slots (ncu: DRAM 55 %, issue slots 54 %, L1 49 %, the same time
+// with and without the second BGR read): 7.3 -> 9.3 M frames/s at 224 x 298 (8 192 frames; 4 / 8 / 16 ahead: 9.20 / 9.26 / 8.95).
+constexpr int kOverlayPrefetch = 8;
+
+// the low bytes of four words as one word (three byte permutes)
+__device__ __forceinline__ uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+constexpr size_t kOverlayLumaMaxBytes = 80 * 1024;    // luma plane + 32 KB of colour-table copies + 1 KB reserved, twice, in 228 KB
+constexpr int kOverlayThreads = 512;     // 2 CTAs per SM
+
+// LUMA (VEC = 4 with a frame only): the first pass leaves the four lumas of every pixel quad as one 32-bit word in dynamic
+// shared memory (n_pixels bytes: 65 KB at 224 x 298, two CTAs per SM; up to 80 KB), so the second pass neither reads the BGR frame
+// again (ncu, round 2: 867 KB of DRAM traffic per frame against 667 KB algorithmic - the re-read missed L2) nor repeats
+// the luma arithmetic.
+template <int VEC, bool LUMA = false>
 __global__ void __launch_bounds__(kOverlayThreads, 2)
 overlay_kernel(const float* __restrict__ heat, const uint8_t* __restrict__ bgr, long long n_frames, int n_pixels,
                float alpha, const uint8_t* __restrict__ jet_lut, uint8_t* __restrict__ rgb_out) {
-    __shared__ float4 s_jet[256];
-    __shared__ float s_gray[256];
+    static_assert(!LUMA || VEC == 4, "the luma plane is stored per pixel quad");
+    extern __shared__ __align__(16) uint32_t s_luma[];       // LUMA: [n_pixels / 4]
+    // eight copies of the colour table, one per lane of a quarter warp: the 128-bit look-ups of a warp are free of bank
+    // conflicts whatever the heat values (ncu, round 2, one copy + a 256-entry gray table: the L1 data pipe 87 % busy, 29 k
+    // shared-memory wavefronts per frame where 8 k are the minimum - that pipe, not DRAM, was the bound)
+    __shared__ float4 s_jet[256][8];
     __shared__ int s_red[2][kOverlayThreads / 32];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid < 256) {
-        const float r = jet_lut[3 * tid], g = jet_lut[3 * tid + 1], b = jet_lut[3 * tid + 2];
-        s_jet[tid] = bgr ? make_float4(__fmul_rn(r, alpha), __fmul_rn(g, alpha), __fmul_rn(b, alpha), 0.f)
-                         : make_float4(r, g, b, 0.f);
-        s_gray[tid] = 0.f;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, copy = tid & 7;
+    for (int i = tid; i < 256 * 8; i += kOverlayThreads) {
+        const int j = i >> 3;
+        const float r = jet_lut[3 * j], g = jet_lut[3 * j + 1], b = jet_lut[3 * j + 2];
+        s_jet[j][i & 7] = bgr ? make_float4(__fmul_rn(r, alpha), __fmul_rn(g, alpha), __fmul_rn(b, alpha), 0.f)
+                              : make_float4(r, g, b, 0.f);
     }
     const float keep = __fsub_rn(1.f, alpha);
     for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
         __syncthreads();
         const uint8_t* img = bgr ? bgr + f * n_pixels * 3 : nullptr;
+        int lo = 255, hi = 255;
         if (img != nullptr) {
-            int lo = 255, hi = 0;
+            hi = 0;
             if (VEC == 4) {
                 const uint32_t* w = reinterpret_cast<const uint32_t*>(img);
 #pragma unroll 4
                 for (int q = tid; q < n_pixels / 4; q += kOverlayThreads) {
+                    if (kOverlayPrefetch && q + kOverlayPrefetch * kOverlayThreads < n_pixels / 4) prefetch_l2(w + 3 * (q + kOverlayPrefetch * kOverlayThreads));
                     const uint32_t w0 = __ldg(w + 3 * q), w1 = __ldg(w + 3 * q + 1), w2 = __ldg(w + 3 * q + 2);
                     const int y0 = luma15(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
                     const int y1 = luma15(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
@@ -305,12 +345,19 @@ overlay_kernel(const float* __restrict__ heat, const uint8_t* __restrict__ bgr, 
                     const int y3 = luma15((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
                     lo = min(min(lo, min(y0, y1)), min(y2, y3));
                     hi = max(max(hi, max(y0, y1)), max(y2, y3));
+                    if (LUMA) s_luma[q] = static_cast<uint32_t>(y0 | (y1 << 8) | (y2 << 16) | (y3 << 24));
                 }
             } else {
                 for (int p = tid; p < n_pixels; p += kOverlayThreads) {
                     const int y = luma15(img[3 * p], img[3 * p + 1], img[3 * p + 2]);
                     lo = min(lo, y); hi = max(hi, y);
                 }
+            }
+            if (kOverlayPrefetch && VEC == 4) {
+                const float4* h4 = reinterpret_cast<const float4*>(heat + f * n_pixels);
+#pragma unroll
+                for (int u = 0; u < kOverlayPrefetch; ++u)
+                    if (tid + u * kOverlayThreads < n_pixels / 4) prefetch_l2(h4 + tid + u * kOverlayThreads);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -322,15 +369,8 @@ overlay_kernel(const float* __restrict__ heat, const uint8_t* __restrict__ bgr, 
             lo = s_red[0][0]; hi = s_red[1][0];
 #pragma unroll
             for (int w = 1; w < kOverlayThreads / 32; ++w) { lo = min(lo, s_red[0][w]); hi = max(hi, s_red[1][w]); }
-            // imshow(gray, cmap=gray): level = int((y - lo) / (hi - lo) * 256) clipped to 255, for every possible luma
-            const float range = static_cast<float>(hi - lo);
-            if (tid < 256) {
-                int gi = (range > 0.f && tid >= lo) ? static_cast<int>(__fmul_rn(__fdiv_rn(static_cast<float>(tid - lo), range), 256.f)) : 0;
-                gi = min(gi, 255);
-                s_gray[tid] = __fmul_rn(static_cast<float>(gi), keep);
-            }
-            __syncthreads();
         }
+        const GrayLevels gray(lo, hi, keep);
         const float* hp = heat + f * n_pixels;
         uint8_t* op = rgb_out + f * n_pixels * 3;
         if (VEC == 4) {
@@ -341,49 +381,56 @@ overlay_kernel(const float* __restrict__ heat, const uint8_t* __restrict__ bgr, 
             // Four pixel quads per thread and round, all their loads issued before the first is used: with one quad per round
             // the kernel sat on global-memory latency (ncu, round 2: 20 of 26 warp-cycles per issue on the long scoreboard,
             // 0.55 of the DRAM roof with 55 resident warps per SM).
-            for (int q0 = tid; q0 < nq; q0 += 4 * kOverlayThreads) {
-                float4 hv[4];
-                uint32_t wv[4][3];
+            constexpr int U = 4;                  // (six quads for the luma form, whose quads need one word instead of three: 6.61 M frames/s against 6.89 M)
+            for (int q0 = tid; q0 < nq; q0 += U * kOverlayThreads) {
+                float4 hv[U];
+                uint32_t wv[U][3];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int q = q0 + u * kOverlayThreads;
+                    if (kOverlayPrefetch && q + kOverlayPrefetch * kOverlayThreads < nq) prefetch_l2(h4 + q + kOverlayPrefetch * kOverlayThreads);
                     if (q < nq) {
                         hv[u] = __ldcs(h4 + q);
-                        if (img != nullptr) { wv[u][0] = __ldg(w + 3 * q); wv[u][1] = __ldg(w + 3 * q + 1); wv[u][2] = __ldg(w + 3 * q + 2); }
+                        if (LUMA) wv[u][0] = s_luma[q];
+                        else if (img != nullptr) { wv[u][0] = __ldg(w + 3 * q); wv[u][1] = __ldg(w + 3 * q + 1); wv[u][2] = __ldg(w + 3 * q + 2); }
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int q = q0 + u * kOverlayThreads;
                     if (q >= nq) break;
                     const float hs[4] = {hv[u].x, hv[u].y, hv[u].z, hv[u].w};
                     float gk[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (img != nullptr) {
+                    if (LUMA) {
+                        const uint32_t y = wv[u][0];
+                        gk[0] = gray((y << 8) & 0xff00u); gk[1] = gray(y & 0xff00u); gk[2] = gray((y >> 8) & 0xff00u); gk[3] = gray((y >> 16) & 0xff00u);
+                    } else if (img != nullptr) {
                         const uint32_t w0 = wv[u][0], w1 = wv[u][1], w2 = wv[u][2];
-                        gk[0] = s_gray[luma15(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u)];
-                        gk[1] = s_gray[luma15(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u)];
-                        gk[2] = s_gray[luma15((w1 >> 16) & 255u, w1 >> 24, w2 & 255u)];
-                        gk[3] = s_gray[luma15((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24)];
+                        gk[0] = gray(static_cast<unsigned>(luma15(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u)) << 8);
+                        gk[1] = gray(static_cast<unsigned>(luma15(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u)) << 8);
+                        gk[2] = gray(static_cast<unsigned>(luma15((w1 >> 16) & 255u, w1 >> 24, w2 & 255u)) << 8);
+                        gk[3] = gray(static_cast<unsigned>(luma15((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24)) << 8);
                     }
                     uint32_t c[12];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int ji = min(max(static_cast<int>(__fmul_rn(hs[k], 256.f)), 0), 255);   // Colormap: int(x * N)
-                        const float4 jet = s_jet[ji];
-                        c[3 * k] = static_cast<uint32_t>(__float2int_rn(__fadd_rn(jet.x, gk[k]))) & 255u;
-                        c[3 * k + 1] = static_cast<uint32_t>(__float2int_rn(__fadd_rn(jet.y, gk[k]))) & 255u;
-                        c[3 * k + 2] = static_cast<uint32_t>(__float2int_rn(__fadd_rn(jet.z, gk[k]))) & 255u;
+                        const float4 jet = s_jet[ji][copy];
+                        // rint of a sum in [0, 255] without the conversion unit: + 2^23 leaves it, rounded to nearest even, in the low mantissa byte
+                        c[3 * k] = __float_as_uint(__fadd_rn(__fadd_rn(jet.x, gk[k]), 8388608.f));
+                        c[3 * k + 1] = __float_as_uint(__fadd_rn(__fadd_rn(jet.y, gk[k]), 8388608.f));
+                        c[3 * k + 2] = __float_as_uint(__fadd_rn(__fadd_rn(jet.z, gk[k]), 8388608.f));
                     }
-                    __stcs(o + 3 * q, c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24));
-                    __stcs(o + 3 * q + 1, c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24));
-                    __stcs(o + 3 * q + 2, c[8] | (c[9] << 8) | (c[10] << 16) | (c[11] << 24));
+                    __stcs(o + 3 * q, pack_low_bytes(c[0], c[1], c[2], c[3]));
+                    __stcs(o + 3 * q + 1, pack_low_bytes(c[4], c[5], c[6], c[7]));
+                    __stcs(o + 3 * q + 2, pack_low_bytes(c[8], c[9], c[10], c[11]));
                 }
             }
         } else {
             for (int p = tid; p < n_pixels; p += kOverlayThreads) {
                 const int ji = min(max(static_cast<int>(__fmul_rn(hp[p], 256.f)), 0), 255);
-                const float4 jet = s_jet[ji];
-                const float gk = img ? s_gray[luma15(img[3 * p], img[3 * p + 1], img[3 * p + 2])] : 0.f;
+                const float4 jet = s_jet[ji][copy];
+                const float gk = img ? gray(static_cast<unsigned>(luma15(img[3 * p], img[3 * p + 1], img[3 * p + 2])) << 8) : 0.f;
                 op[3 * p] = static_cast<uint8_t>(__float2int_rn(__fadd_rn(jet.x, gk)));
                 op[3 * p + 1] = static_cast<uint8_t>(__float2int_rn(__fadd_rn(jet.y, gk)));
                 op[3 * p + 2] = static_cast<uint8_t>(__float2int_rn(__fadd_rn(jet.z, gk)));

@@ -374,6 +374,9 @@ int64_t aig_launch_count(const aig_handle* h);
  *                        find_logen drop-in; 0 switches the path off
  *   "heat_bulk_store"    1 (default): heat maps are staged in shared memory and written with bulk asynchronous copies
  *                        (heat_stream_kernel); 0: the round-1 kernel with per-thread stores, for comparison runs
+ *   "overlay_luma"       1 (default): aig_overlay with a frame of up to 81 920 pixels (a multiple of four, aligned buffers) keeps
+ *                        the frame's luma plane in shared memory between its min/max pass and its blend pass, so the BGR
+ *                        frame is read once; 0: the BGR frame is read (and its luma computed) in both passes, as for larger frames
  *   "energy_heat_ws"     1 (default): aig_energy_heatmap runs the warp-specialised kernel (float64 warps and heat-map warps
  *                        of a CTA working on consecutive frames, two CTAs per SM); 0: the same warps do both phases in sequence
  *   "mask_packed"        1 (default): aig_resize_mask and aig_ciou_sweep at the reference's output sizes (224 x 298, 224 x 224)

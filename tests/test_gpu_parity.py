@@ -625,6 +625,32 @@ def test_overlay_bit_exact_vs_oracle(path, golden, torch):
     assert dev.is_cuda and np.array_equal(dev.cpu().numpy()[0], oracle.overlay(heat[0], frames[0], lut, 0.5))
 
 
+def test_overlay_luma_plane_form_equals_two_read_form(path, torch):
+    """aig_overlay keeps a frame's luma plane in shared memory between its passes (option overlay_luma, default on); the
+    form that reads the BGR frame in both passes serves larger frames.  Both against the oracle and against each other,
+    on more frames than CTAs in flight (a CTA's plane is overwritten by its next frame), with constant and two-level
+    frames, at a size just inside the shared-memory limit and one past it."""
+    lut = tables.jet_lut()
+    rng = np.random.default_rng(11)
+    for (n, h, w) in ((700, 24, 36), (3, 224, 298), (5, 30, 34), (2, 256, 320), (2, 256, 324)):     # 81 920 px = the limit; 82 944 px falls back
+        heat = torch.rand(n, h, w, device='cuda')
+        frames = torch.from_numpy(rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)).cuda()
+        frames[0] = 200
+        frames[1, : h // 2] = 3
+        frames[1, h // 2:] = 250
+        try:
+            path.set_option('overlay_luma', 1)
+            a = path.overlay(heat, frames)
+            path.set_option('overlay_luma', 0)
+            b = path.overlay(heat, frames)
+        finally:
+            path.set_option('overlay_luma', 1)
+        assert torch.equal(a, b)
+        hn, fn, an = heat.cpu().numpy(), frames.cpu().numpy(), a.cpu().numpy()
+        for i in sorted({0, 1, n - 1, n // 2}):
+            assert np.array_equal(an[i], oracle.overlay(hn[i], fn[i], lut))
+
+
 # ----------------------------------------------------------------------------------------------
 # host staging: ordinary (pageable) NumPy inputs go up through the pinned ring of host_staging.h
 # ----------------------------------------------------------------------------------------------

@@ -301,3 +301,18 @@ def test_overlay_gray_matches_cv2_and_jet_table_shape():
     assert lut[128].tolist() == [124, 255, 121]                                   # green plateau in the middle
     out = oracle.overlay(np.zeros((4, 4), np.float32), None, lut)
     assert out.shape == (4, 4, 3) and np.array_equal(out[0, 0], lut[0])
+
+
+def test_overlay_gray_level_is_an_integer_quotient():
+    """The overlay kernels take the gray level of a luma as min(mulhi(256 (y - lo), M), 255) with one reciprocal M per
+    frame (frontend_kernel.cuh: GrayLevels) instead of the oracle's float32 expression
+    min(int(fl(fl((y - lo) / (hi - lo)) * 256)), 255): equal for every lo <= y <= hi in 0..255."""
+    lo, hi, y = np.meshgrid(np.arange(256), np.arange(256), np.arange(256), indexing='ij', sparse=True)
+    ok = (lo <= y) & (y <= hi) & (lo < hi)
+    a = np.broadcast_to((y - lo), ok.shape)[ok].astype(np.int64)
+    b = np.broadcast_to((hi - lo), ok.shape)[ok].astype(np.int64)
+    want = np.minimum(((a.astype(np.float32) / b.astype(np.float32)) * np.float32(256.0)).astype(np.int64), 255)
+    m = np.where(b == 1, 0xffffffff, 0xffffffff // b + 1).astype(np.uint64)
+    got = np.minimum(((a.astype(np.uint64) << np.uint64(8)) * m) >> np.uint64(32), np.uint64(255)).astype(np.int64)
+    assert a.size > 2_000_000 and np.array_equal(got, want)
+

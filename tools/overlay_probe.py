@@ -18,6 +18,12 @@ for n in (2048, 4096, 8192):
     lut = aig.tables.jet_lut()
     ms = timed(lambda: p._check(p._lib.aig_overlay(p._h, heat.data_ptr(), bgr.data_ptr(), n, 224, 298, 0.7, lut.ctypes.data, out.data_ptr())))
     print('overlay %5d frames  %.3f ms  %.2f M frames/s  %.2f TB/s (heat + BGR in, RGB out)' % (n, ms, n/ms/1e3, n*224*298*10/ms/1e9))
+    p.set_option('overlay_luma', 0)
+    out2 = torch.empty_like(out)
+    ms0 = timed(lambda: p._check(p._lib.aig_overlay(p._h, heat.data_ptr(), bgr.data_ptr(), n, 224, 298, 0.7, lut.ctypes.data, out2.data_ptr())))
+    p.set_option('overlay_luma', 1)
+    print('   BGR read in both passes (overlay_luma = 0)  %.3f ms  %.2f M frames/s; outputs equal: %s' % (ms0, n/ms0/1e3, bool(torch.equal(out, out2))))
+    del out2
     smooth = torch.nn.functional.interpolate(torch.rand(n, 1, 9, 12, device='cuda'), size=(224, 298), mode='bilinear').squeeze(1).contiguous()
     ms = timed(lambda: p._check(p._lib.aig_overlay(p._h, smooth.data_ptr(), bgr.data_ptr(), n, 224, 298, 0.7, lut.ctypes.data, out.data_ptr())))
     print('   smooth heat maps    %.3f ms  %.2f M frames/s' % (ms, n/ms/1e3))
