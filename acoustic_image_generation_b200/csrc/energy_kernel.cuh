@@ -101,6 +101,9 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 // exp(x * ln2 / 1024) for x in table-step units, |x| < 2^20 (|x ln2 / 1024| <= 700 and more; pixel_energy guarantees it):
 // k = rint(x), r = x - k exact, result = 2^(k >> 10) * T[k & 1023] * (1 + p(r)) with p the degree-4 Taylor polynomial of
 // 2^(r / 1024) - 1 (truncation 3.7e-20).  `table` is the shared-memory byte address of EnergyTables::exp2.
+// EXP_STRIDE: bytes between consecutive table entries (8: EnergyTables::exp2; 64: one of the eight interleaved copies of
+// stage2_wide_kernel, `table` then pointing at this lane's copy of entry 0).
+template <int EXP_STRIDE = 8>
 __device__ __forceinline__ double exp_units(double x, uint32_t table) {
     const double t = __dadd_rn(x, kExpMagic);
     const int k = __double2loint(t);
@@ -110,7 +113,7 @@ __device__ __forceinline__ double exp_units(double x, uint32_t table) {
     p = __fma_rn(p, r, c_exp_poly[0]);
     const double q = __dmul_rn(p, r);                                  // 2^(r / 1024) - 1
     const int idx = k & (kExpEntries - 1);
-    const double tj = lds_f64(table + static_cast<uint32_t>(idx) * 8u);
+    const double tj = lds_f64(table + static_cast<uint32_t>(idx) * static_cast<uint32_t>(EXP_STRIDE));
     const double y = __fma_rn(tj, q, tj);
     int hi;                                                            // * 2^(k >> 10): (k - idx) << 10 added to the high word
     asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(hi) : "r"(k - idx), "n"(1 << (20 - kExpLog2)), "r"(__double2hiint(y)));
@@ -190,6 +193,7 @@ __device__ __forceinline__ float max_nan_abs(float m, float a) {     // max(m, |
 
 // The four exponentials of couple j: bands j, 23 - j (p) and 11 - j, 12 + j (q), "lo" the first of each pair.
 struct CoupleExp { double lo_p, hi_p, lo_q, hi_q; };
+template <int EXP_STRIDE = 8>
 __device__ __forceinline__ CoupleExp couple_exp(const double (&z)[kMfccNum], const CoupleCoef& c, uint32_t exp_table) {
     double aa = __dmul_rn(z[3], c.aa[0]);                 // m + 1 = 4, 8, 12: symmetric under j -> 23 - j and j -> 11 - j
     aa = __fma_rn(z[7], c.aa[1], aa);
@@ -205,10 +209,10 @@ __device__ __forceinline__ CoupleExp couple_exp(const double (&z)[kMfccNum], con
     }
     const double a0 = __dadd_rn(aa, ab), a1 = __dadd_rn(aa, -ab);
     CoupleExp e;
-    e.lo_p = exp_units(__dadd_rn(a0, b0), exp_table);           // band j
-    e.hi_p = exp_units(__dadd_rn(a0, -b0), exp_table);          // band 23 - j
-    e.lo_q = exp_units(__dadd_rn(a1, b1), exp_table);           // band 11 - j
-    e.hi_q = exp_units(__dadd_rn(a1, -b1), exp_table);          // band 12 + j
+    e.lo_p = exp_units<EXP_STRIDE>(__dadd_rn(a0, b0), exp_table);           // band j
+    e.hi_p = exp_units<EXP_STRIDE>(__dadd_rn(a0, -b0), exp_table);          // band 23 - j
+    e.lo_q = exp_units<EXP_STRIDE>(__dadd_rn(a1, b1), exp_table);           // band 11 - j
+    e.hi_q = exp_units<EXP_STRIDE>(__dadd_rn(a1, -b1), exp_table);          // band 12 + j
     return e;
 }
 
@@ -220,6 +224,7 @@ __device__ __forceinline__ CoupleExp couple_exp(const double (&z)[kMfccNum], con
 // every |band sum| <= sum_m |z_m| <= 12 max_m |z_m| (|cos| <= 1), so max |z_m| <= 58 keeps all 24 table exponentials in
 // range; anything else - huge values, Inf, NaN (max.NaN propagates it, the comparison is then false) - is rare.  Every
 // kernel uses this one function, so all of them send exactly the same pixels down the plain path and agree bit for bit.
+template <int EXP_STRIDE = 8>
 __device__ __forceinline__ double pixel_energy(float (&x)[kMfccNum], bool normalize, const FrameNormFast& norm,
                                                const EnergyTables& tab, uint32_t exp_table, unsigned int& rare) {
     if (normalize) {                                      // float32, as TF; a frame-uniform choice of the division's form
@@ -246,16 +251,16 @@ __device__ __forceinline__ double pixel_energy(float (&x)[kMfccNum], bool normal
     }
     rare = !(big <= 58.f);
     // couple j holds e[j], e[23-j], e[11-j], e[12+j];  r[k] = (e[k] + e[k+8]) + e[k+16]
-    const CoupleExp c0 = couple_exp(z, tab.couple[0], exp_table);   // e0  e23 e11 e12
-    const CoupleExp c3 = couple_exp(z, tab.couple[3], exp_table);   // e3  e20 e8  e15
-    const CoupleExp c4 = couple_exp(z, tab.couple[4], exp_table);   // e4  e19 e7  e16
+    const CoupleExp c0 = couple_exp<EXP_STRIDE>(z, tab.couple[0], exp_table);   // e0  e23 e11 e12
+    const CoupleExp c3 = couple_exp<EXP_STRIDE>(z, tab.couple[3], exp_table);   // e3  e20 e8  e15
+    const CoupleExp c4 = couple_exp<EXP_STRIDE>(z, tab.couple[4], exp_table);   // e4  e19 e7  e16
     const double r0 = __dadd_rn(__dadd_rn(c0.lo_p, c3.lo_q), c4.hi_q);    // (e0 + e8)  + e16
     const double r7 = __dadd_rn(__dadd_rn(c4.lo_q, c3.hi_q), c0.hi_p);    // (e7 + e15) + e23
     const double r3 = __dadd_rn(__dadd_rn(c3.lo_p, c0.lo_q), c4.hi_p);    // (e3 + e11) + e19
     const double r4 = __dadd_rn(__dadd_rn(c4.lo_p, c0.hi_q), c3.hi_p);    // (e4 + e12) + e20
-    const CoupleExp c1 = couple_exp(z, tab.couple[1], exp_table);   // e1  e22 e10 e13
-    const CoupleExp c2 = couple_exp(z, tab.couple[2], exp_table);   // e2  e21 e9  e14
-    const CoupleExp c5 = couple_exp(z, tab.couple[5], exp_table);   // e5  e18 e6  e17
+    const CoupleExp c1 = couple_exp<EXP_STRIDE>(z, tab.couple[1], exp_table);   // e1  e22 e10 e13
+    const CoupleExp c2 = couple_exp<EXP_STRIDE>(z, tab.couple[2], exp_table);   // e2  e21 e9  e14
+    const CoupleExp c5 = couple_exp<EXP_STRIDE>(z, tab.couple[5], exp_table);   // e5  e18 e6  e17
     const double r1 = __dadd_rn(__dadd_rn(c1.lo_p, c2.lo_q), c5.hi_q);    // (e1 + e9)  + e17
     const double r6 = __dadd_rn(__dadd_rn(c5.lo_q, c2.hi_q), c1.hi_p);    // (e6 + e14) + e22
     const double r2 = __dadd_rn(__dadd_rn(c2.lo_p, c1.lo_q), c5.hi_p);    // (e2 + e10) + e18
@@ -417,12 +422,13 @@ __global__ void selftest_norm_kernel(unsigned long long* out) {
 // STAGED: the next pixel's 48 bytes travel into this thread's own shared-memory slots (cp.async) while the current pixel
 // is computed - a plain load at the top of the round leaves 13 % of the warps' time waiting for L2 (ncu, energy_lab2),
 // registers for a software prefetch do not exist (122 are in use), and a prefetch hint only helps half way.
-template <int THREADS, bool STAGED>
+// EXP_STRIDE / exp_table: see exp_units (0 = the table of `tab`).
+template <int THREADS, bool STAGED, int EXP_STRIDE = 8>
 __device__ __forceinline__ void frame_energy_pixels(const float* img, int p_begin, int p_end, bool normalize,
                                                     const FrameNormFast& norm, float* scaled, double* energy, double* map,
                                                     unsigned int* rare_bits, const EnergyTables& tab, float4 (*stage)[THREADS],
-                                                    int gt) {
-    const uint32_t exp_table = smem_u32(tab.exp2);
+                                                    int gt, uint32_t exp_table = 0) {
+    if (exp_table == 0) exp_table = smem_u32(tab.exp2);
     auto stage_in = [&](int p) {
         const float* src = img + p * kMfccNum;
 #pragma unroll
@@ -447,7 +453,7 @@ __device__ __forceinline__ void frame_energy_pixels(const float* img, int p_begi
         }
         float x[kMfccNum] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
         unsigned int rare;
-        const double en = pixel_energy(x, normalize, norm, tab, exp_table, rare);
+        const double en = pixel_energy<EXP_STRIDE>(x, normalize, norm, tab, exp_table, rare);
         if (rare) {
             // nothing of this pixel is stored: frame_energy_fixup redoes it from its raw values
             atomicOr(&rare_bits[(p - p_begin) >> 5], 1u << ((p - p_begin) & 31));
@@ -648,6 +654,75 @@ stage2_kernel(const __grid_constant__ Stage2Args a) {
     if (GROUPS == 2) {
         for (int k = tid; k < a.k_thr; k += GROUPS * kEnergyThreads)
             if (s_pos[k] != 0) atomicAdd(a.pos + k, static_cast<unsigned long long>(s_pos[k]));
+    }
+}
+
+// ---- aig_energy, large batches: eight frames per CTA around one conflict-free exponential table ----------------------
+// ncu on stage2_kernel<1> (round 2): FP64 pipe 50 %, but the shared-memory pipe 66 % of its peak over the whole launch -
+// 287 wavefronts per warp and pixel against 206 cycles of float64 pipe: 132 for the 66 broadcast coefficient loads, 48
+// for the 24 exponential-table look-ups and 79 more for their bank conflicts (16 lanes of a half warp picking 16 random
+// doubles collide ~3-fold).  The shared-memory pipe, not the float64 pipe, is what the kernel runs into.  Eight
+// interleaved copies of the table (entry i of copy c at (8 i + c) doubles; a lane reads copy lane % 8, so the 16 lanes
+// of a half warp meet at most in pairs) take the conflicts away, but cost 64 KB: affordable once per SM, not once per
+// 64-thread CTA.  Hence one CTA of 512 threads per SM: eight groups of 64 threads, each with its own frame, energy map,
+// staging slots and named barrier - the same 16 warps at 128 registers as eight CTAs of stage2_kernel<1> - and one table.
+constexpr int kWideGroups = 8;
+constexpr int kExpCopies = 8;
+struct WideShared {
+    EnergyTables tab;                                  // coefficients; its one-copy exponential table serves the plain path only
+    double exp2x[kExpEntries][kExpCopies];
+    EnergyGroupShared group[kWideGroups];
+};
+__global__ void __launch_bounds__(kWideGroups * kEnergyThreads, 1)
+stage2_wide_kernel(const __grid_constant__ Stage2Args a) {
+    extern __shared__ __align__(16) unsigned char s_wide_raw[];
+    WideShared& ws = *reinterpret_cast<WideShared*>(s_wide_raw);
+    const int tid = threadIdx.x;
+    const int group = tid / kEnergyThreads, gt = tid % kEnergyThreads;
+    auto group_sync = [&] { asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kEnergyThreads) : "memory"); };
+    load_energy_tables(ws.tab, tid, kWideGroups * kEnergyThreads);
+    for (int i = tid; i < kExpEntries * kExpCopies; i += kWideGroups * kEnergyThreads)
+        ws.exp2x[i / kExpCopies][i % kExpCopies] = g_exp2_table[i / kExpCopies];
+    EnergyGroupShared& g = ws.group[group];
+    if (gt < kFramePixels / 32) g.rare_bits[gt] = 0u;
+    __syncthreads();
+    const uint32_t exp_table = smem_u32(&ws.exp2x[0][tid % kExpCopies]);
+
+    for (long long frame = static_cast<long long>(blockIdx.x) * kWideGroups + group; frame < a.n_frames;
+         frame += static_cast<long long>(gridDim.x) * kWideGroups) {
+        const float* img = a.img[0] + frame * kFrameValues;
+        float lo = 0.f, hi = 1.f;
+        if (a.normalize_first) group_minmax(img, kFrameValues / 4, gt, kEnergyThreads, g.red, group_sync, lo, hi);
+        const FrameNormFast norm(lo, __fsub_rn(hi, lo));
+        float* scaled = a.scaled[0] ? a.scaled[0] + frame * kFrameValues : nullptr;
+        double* energy = a.energy[0] ? a.energy[0] + frame * kFramePixels : nullptr;
+        frame_energy_pixels<kEnergyThreads, true, 8 * kExpCopies>(img, 0, kFramePixels, a.normalize_first != 0, norm, scaled, energy,
+                                                                 g.map, g.rare_bits, ws.tab, g.stage, gt, exp_table);
+        group_sync();
+        if (frame_energy_fixup(img, 0, kFramePixels, a.normalize_first != 0, norm, scaled, energy, g.map, g.rare_bits, gt,
+                               kEnergyThreads)) {
+            group_sync();
+            if (gt < kFramePixels / 32) g.rare_bits[gt] = 0u;
+            group_sync();
+        }
+        if (a.mask[0] != nullptr || a.mean[0] != nullptr) {
+            const double mean = frame_mean(g.map, g.sum.part, g.sum.leaf, &g.mean, gt, kEnergyThreads, group_sync);
+            if (gt == 0 && a.mean[0] != nullptr) a.mean[0][frame] = mean;
+            if (a.mask[0] != nullptr) {
+                uint8_t* mask = a.mask[0] + frame * kFramePixels;
+                if ((reinterpret_cast<uintptr_t>(mask) & 3u) == 0) {                  // four pixels per store
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(mask);
+                    for (int q = gt; q < kFramePixels / 4; q += kEnergyThreads) {
+                        const double* e = g.map + 4 * q;
+                        dst[q] = (e[0] > mean ? 1u : 0u) | (e[1] > mean ? 0x100u : 0u) | (e[2] > mean ? 0x10000u : 0u) |
+                                 (e[3] > mean ? 0x1000000u : 0u);
+                    }
+                } else {
+                    for (int p = gt; p < kFramePixels; p += kEnergyThreads) mask[p] = g.map[p] > mean ? 1 : 0;
+                }
+            }
+        }
+        group_sync();     // the map and the staging slots are reused by the group's next frame
     }
 }
 

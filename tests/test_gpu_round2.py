@@ -77,6 +77,28 @@ def test_energy_cluster_and_cta_forms_are_bit_identical(path, path_cta, normaliz
     assert diff == 0
 
 
+@pytest.mark.parametrize('normalize_first', [False, True])
+def test_energy_wide_kernel_equals_one_cta_per_frame_kernel(path_cta, normalize_first):
+    """aig_energy on large batches runs stage2_wide_kernel (eight frames per 512-thread CTA, eight interleaved copies of
+    the exponential table); option energy_wide = 0 keeps stage2_kernel<1> (one 64-thread CTA per frame, one copy).  Same
+    bits - energies, masks, in-place scaled values, means - for batch sizes around the group count and the grid size,
+    hard cases (plain-path pixels, Inf, NaN, a constant frame) included; and the oracle's masks."""
+    for n in (1, 7, 8, 9, 23, 300, 8 * 148 + 5):
+        imgs = _images_with_hard_cases(max(n, 6), 50 + n)[:n] if n >= 6 else synth.smooth_images(n, 50 + n)
+        try:
+            path_cta.set_option('energy_wide', 1)
+            a = path_cta.energy(imgs, normalize_first=normalize_first, want_scaled=True, want_mean=True)
+            path_cta.set_option('energy_wide', 0)
+            b = path_cta.energy(imgs, normalize_first=normalize_first, want_scaled=True, want_mean=True)
+        finally:
+            path_cta.set_option('energy_wide', 1)
+        for name, x, y in zip(('energy', 'mask', 'scaled', 'mean'), a, b):
+            assert np.array_equal(x, y, equal_nan=True), (n, name)
+        if n <= 23:
+            want_e, want_m = oracle.energy_stage(imgs, normalize_first=normalize_first)
+            assert np.array_equal(a[1], want_m), n
+
+
 def test_energy_large_batch_equals_small_batch_form(path, path_cta):
     """Above the SM count the default handle runs one CTA per frame; below, a cluster per frame: same bits."""
     imgs = synth.smooth_images(200, 41)

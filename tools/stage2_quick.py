@@ -45,6 +45,10 @@ line('aig_energy normalize_first=1, MFCC-like', timed(lambda: lib.aig_energy(h, 
 line('aig_energy normalize_first=1, minimum ~ 0', timed(lambda: lib.aig_energy(h, unit.data_ptr(), n, 1, None, energy.data_ptr(), mask.data_ptr(), None)), n)
 line('aig_energy normalize_first=0, values in [0, 1)', timed(lambda: lib.aig_energy(h, unit.data_ptr(), n, 0, None, energy.data_ptr(), mask.data_ptr(), None)), n)
 line('aig_energy, energy only (no mask)', timed(lambda: lib.aig_energy(h, unit.data_ptr(), n, 0, None, energy.data_ptr(), None, None)), n)
+p.set_option('energy_wide', 0)
+line('aig_energy normalize_first=0, MFCC-like, energy_wide=0', timed(lambda: lib.aig_energy(h, img.data_ptr(), n, 0, None, energy.data_ptr(), mask.data_ptr(), None)), n)
+line('aig_energy normalize_first=1, MFCC-like, energy_wide=0', timed(lambda: lib.aig_energy(h, img.data_ptr(), n, 1, None, energy.data_ptr(), mask.data_ptr(), None)), n)
+p.set_option('energy_wide', 1)
 line('aig_acivw_batch (energy maps)', timed(lambda: lib.aig_acivw_batch(h, unit.data_ptr(), other.data_ptr(), n, 0, thr.data_ptr(), 11, None, None,
                                                                        cnt.data_ptr(), cnt[11:].data_ptr(), None, None, None, None)), 2 * n)
 for ws in (1, 0):
