@@ -156,8 +156,8 @@ struct aig_handle {
     int packed_ctas[4] = {};
     int mask_packed = 1;                // aig_resize_mask / aig_ciou_sweep at 224 x 298 and 224 x 224 as the packed kernels (0: the generic kernels)
     bool energy_heat_ws_attr_set[5] = {};
-    int energy_wide = 1;                // aig_energy on large batches: eight frames per 512-thread CTA around one conflict-free exp table (0: stage2_kernel<1>, eight CTAs of 64 threads per SM)
-    bool stage2_wide_attr_set = false;
+    int energy_wide = 1;                // aig_energy / aig_acivw_batch on large batches: eight frames (four pairs) per 512-thread CTA around one conflict-free exp table (0: stage2_kernel, eight CTAs of 64 (four of 128) threads per SM)
+    bool stage2_wide_attr_set[2] = {};
     int overlay_luma = 1;               // aig_overlay keeps the luma plane of a frame in shared memory between its passes (0: BGR read twice)
     bool overlay_luma_attr_set = false;
     int energy_heat_ws = 1;             // aig_energy_heatmap as the warp-specialised kernel (0: heat_stream_kernel<true>, phases in sequence)
@@ -531,14 +531,16 @@ int launch_stage2(aig_handle* h, cudaStream_t stream, const Stage2Args& args, in
         stage2_cluster_kernel<GROUPS><<<static_cast<unsigned>(clusters * kClusterSize), GROUPS * kClusterGroupThreads, 0, stream>>>(args);
         return scope.done("stage2_cluster_kernel");
     }
-    if (GROUPS == 1 && ctas_per_sm >= 8 && h->energy_wide) {
-        // eight frames per CTA of 512 threads, one CTA per SM, around one conflict-free exponential table (stage2_wide_kernel)
-        if (!h->stage2_wide_attr_set) {
-            AIG_CK(cudaFuncSetAttribute(stage2_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(WideShared))));
-            h->stage2_wide_attr_set = true;
+    if (ctas_per_sm >= 8 && h->energy_wide) {
+        // eight frames (four pairs) per CTA of 512 threads, one CTA per SM, around one conflict-free exponential table
+        if (!h->stage2_wide_attr_set[GROUPS - 1]) {
+            AIG_CK(cudaFuncSetAttribute(stage2_wide_kernel<GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(sizeof(WideShared<GROUPS>))));
+            h->stage2_wide_attr_set[GROUPS - 1] = true;
         }
-        const int64_t ctas = std::min<int64_t>((args.n_frames + kWideGroups - 1) / kWideGroups, h->sm_count);
-        stage2_wide_kernel<<<static_cast<unsigned>(ctas), kWideGroups * kEnergyThreads, sizeof(WideShared), stream>>>(args);
+        constexpr int kUnits = kWideGroups / GROUPS;
+        const int64_t ctas = std::min<int64_t>((args.n_frames + kUnits - 1) / kUnits, h->sm_count);
+        stage2_wide_kernel<GROUPS><<<static_cast<unsigned>(ctas), kWideGroups * kEnergyThreads, sizeof(WideShared<GROUPS>), stream>>>(args);
         return scope.done("stage2_wide_kernel");
     }
     stage2_kernel<GROUPS><<<frames_grid(h, args.n_frames, std::min(ctas_per_sm, 8 / GROUPS)), GROUPS * kEnergyThreads, 0, stream>>>(args);

@@ -668,34 +668,53 @@ stage2_kernel(const __grid_constant__ Stage2Args a) {
 // staging slots and named barrier - the same 16 warps at 128 registers as eight CTAs of stage2_kernel<1> - and one table.
 constexpr int kWideGroups = 8;
 constexpr int kExpCopies = 8;
+template <int GROUPS>
 struct WideShared {
     EnergyTables tab;                                  // coefficients; its one-copy exponential table serves the plain path only
     double exp2x[kExpEntries][kExpCopies];
     EnergyGroupShared group[kWideGroups];
+    unsigned int pos[GROUPS == 2 ? kScoreThresholdsMax : 1];
+    int iu[kWideGroups / GROUPS][2];
+    double iou[kWideGroups / GROUPS];
 };
+// GROUPS == 1: aig_energy, a unit is a frame (eight per CTA).  GROUPS == 2: aig_acivw_batch, a unit is a pair of images -
+// real and reconstructed, 128 threads, four pairs per CTA - scored in the same CTA as in stage2_kernel<2>; the
+// per-threshold success counts of the four pairs meet in one shared vector (shared-memory atomics).
+template <int GROUPS>
 __global__ void __launch_bounds__(kWideGroups * kEnergyThreads, 1)
 stage2_wide_kernel(const __grid_constant__ Stage2Args a) {
     extern __shared__ __align__(16) unsigned char s_wide_raw[];
-    WideShared& ws = *reinterpret_cast<WideShared*>(s_wide_raw);
+    WideShared<GROUPS>& ws = *reinterpret_cast<WideShared<GROUPS>*>(s_wide_raw);
+    constexpr int kUnits = kWideGroups / GROUPS, kUnitThreads = GROUPS * kEnergyThreads;
     const int tid = threadIdx.x;
-    const int group = tid / kEnergyThreads, gt = tid % kEnergyThreads;
-    auto group_sync = [&] { asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kEnergyThreads) : "memory"); };
+    const int slot = tid / kEnergyThreads, gt = tid % kEnergyThreads;     // slot: which of the CTA's eight 64-thread groups
+    const int unit = slot / GROUPS, group = slot % GROUPS, ut = tid % kUnitThreads;
+    // barriers: 0 = the CTA, 1 .. 8 = the groups, 9 .. 12 = the pairs (GROUPS == 2)
+    auto group_sync = [&] { asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "n"(kEnergyThreads) : "memory"); };
+    auto unit_sync = [&] {
+        if (GROUPS == 1) group_sync();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + kWideGroups + unit), "n"(kUnitThreads) : "memory");
+    };
     load_energy_tables(ws.tab, tid, kWideGroups * kEnergyThreads);
     for (int i = tid; i < kExpEntries * kExpCopies; i += kWideGroups * kEnergyThreads)
         ws.exp2x[i / kExpCopies][i % kExpCopies] = g_exp2_table[i / kExpCopies];
-    EnergyGroupShared& g = ws.group[group];
+    EnergyGroupShared& g = ws.group[slot];
     if (gt < kFramePixels / 32) g.rare_bits[gt] = 0u;
+    if (GROUPS == 2) {
+        for (int k = tid; k < a.k_thr; k += kWideGroups * kEnergyThreads) ws.pos[k] = 0;
+        if (blockIdx.x == 0 && tid == 0) atomicAdd(a.num, static_cast<unsigned long long>(a.n_frames));   // num += 1 per frame (:229)
+    }
     __syncthreads();
     const uint32_t exp_table = smem_u32(&ws.exp2x[0][tid % kExpCopies]);
 
-    for (long long frame = static_cast<long long>(blockIdx.x) * kWideGroups + group; frame < a.n_frames;
-         frame += static_cast<long long>(gridDim.x) * kWideGroups) {
-        const float* img = a.img[0] + frame * kFrameValues;
+    for (long long frame = static_cast<long long>(blockIdx.x) * kUnits + unit; frame < a.n_frames;
+         frame += static_cast<long long>(gridDim.x) * kUnits) {
+        const float* img = a.img[group] + frame * kFrameValues;
         float lo = 0.f, hi = 1.f;
         if (a.normalize_first) group_minmax(img, kFrameValues / 4, gt, kEnergyThreads, g.red, group_sync, lo, hi);
         const FrameNormFast norm(lo, __fsub_rn(hi, lo));
-        float* scaled = a.scaled[0] ? a.scaled[0] + frame * kFrameValues : nullptr;
-        double* energy = a.energy[0] ? a.energy[0] + frame * kFramePixels : nullptr;
+        float* scaled = a.scaled[group] ? a.scaled[group] + frame * kFrameValues : nullptr;
+        double* energy = a.energy[group] ? a.energy[group] + frame * kFramePixels : nullptr;
         frame_energy_pixels<kEnergyThreads, true, 8 * kExpCopies>(img, 0, kFramePixels, a.normalize_first != 0, norm, scaled, energy,
                                                                  g.map, g.rare_bits, ws.tab, g.stage, gt, exp_table);
         group_sync();
@@ -705,11 +724,11 @@ stage2_wide_kernel(const __grid_constant__ Stage2Args a) {
             if (gt < kFramePixels / 32) g.rare_bits[gt] = 0u;
             group_sync();
         }
-        if (a.mask[0] != nullptr || a.mean[0] != nullptr) {
+        if (GROUPS == 2 || a.mask[group] != nullptr || a.mean[group] != nullptr) {
             const double mean = frame_mean(g.map, g.sum.part, g.sum.leaf, &g.mean, gt, kEnergyThreads, group_sync);
-            if (gt == 0 && a.mean[0] != nullptr) a.mean[0][frame] = mean;
-            if (a.mask[0] != nullptr) {
-                uint8_t* mask = a.mask[0] + frame * kFramePixels;
+            if (gt == 0 && a.mean[group] != nullptr) a.mean[group][frame] = mean;
+            if (a.mask[group] != nullptr) {
+                uint8_t* mask = a.mask[group] + frame * kFramePixels;
                 if ((reinterpret_cast<uintptr_t>(mask) & 3u) == 0) {                  // four pixels per store
                     uint32_t* dst = reinterpret_cast<uint32_t*>(mask);
                     for (int q = gt; q < kFramePixels / 4; q += kEnergyThreads) {
@@ -722,7 +741,35 @@ stage2_wide_kernel(const __grid_constant__ Stage2Args a) {
                 }
             }
         }
-        group_sync();     // the map and the staging slots are reused by the group's next frame
+        if (GROUPS == 2) {
+            const EnergyGroupShared& ga = ws.group[unit * GROUPS], & gb = ws.group[unit * GROUPS + GROUPS - 1];
+            if (ut < 2) ws.iu[unit][ut] = 0;
+            unit_sync();                                                              // both maps and means are complete
+            const double mean_a = ga.mean, mean_b = gb.mean;
+            int inter = 0, uni = 0;
+            for (int p = ut; p < kFramePixels; p += kUnitThreads) {                   // 1728 = 13.5 * 128: whole warps only
+                const bool ma = ga.map[p] > mean_a, mb = gb.map[p] > mean_b;
+                inter += __popc(__ballot_sync(0xffffffffu, ma && mb));
+                uni += __popc(__ballot_sync(0xffffffffu, ma || mb));
+            }
+            if ((ut & 31) == 0) { atomicAdd(&ws.iu[unit][0], inter); atomicAdd(&ws.iu[unit][1], uni); }
+            unit_sync();
+            if (ut == 0) {
+                if (a.inter != nullptr) a.inter[frame] = ws.iu[unit][0];
+                if (a.uni != nullptr) a.uni[frame] = ws.iu[unit][1];
+                ws.iou[unit] = __ddiv_rn(static_cast<double>(ws.iu[unit][0]), static_cast<double>(ws.iu[unit][1]));   // 0 / 0 = NaN: never counts
+            }
+            unit_sync();
+            const double iou = ws.iou[unit];
+            for (int k = ut; k < a.k_thr; k += kUnitThreads)
+                if (iou > a.thr[k]) atomicAdd(&ws.pos[k], 1u);
+        }
+        unit_sync();     // the maps, the staging slots, iu and iou are reused by the unit's next frame
+    }
+    if (GROUPS == 2) {
+        __syncthreads();
+        for (int k = tid; k < a.k_thr; k += kWideGroups * kEnergyThreads)
+            if (ws.pos[k] != 0) atomicAdd(a.pos + k, static_cast<unsigned long long>(ws.pos[k]));
     }
 }
 

@@ -374,10 +374,10 @@ int64_t aig_launch_count(const aig_handle* h);
  *                        find_logen drop-in; 0 switches the path off
  *   "heat_bulk_store"    1 (default): heat maps are staged in shared memory and written with bulk asynchronous copies
  *                        (heat_stream_kernel); 0: the round-1 kernel with per-thread stores, for comparison runs
- *   "energy_wide"        1 (default): aig_energy on batches of at least small_batch_frames frames runs eight frames per CTA of
- *                        512 threads around one conflict-free (eight-copy) exponential table, one CTA per SM; 0: one CTA of
- *                        64 threads per frame, eight per SM, each with a one-copy table (the kernel the chained modes overlap
- *                        with the MFCC kernel)
+ *   "energy_wide"        1 (default): aig_energy and aig_acivw_batch on batches of at least small_batch_frames frames run eight
+ *                        frames (four pairs) per CTA of 512 threads around one conflict-free (eight-copy) exponential table,
+ *                        one CTA per SM; 0: one CTA of 64 (128) threads per frame (pair), eight (four) per SM, each with a
+ *                        one-copy table (the kernel the chained modes overlap with the MFCC kernel)
  *   "overlay_luma"       1 (default): aig_overlay with a frame of up to 81 920 pixels (a multiple of four, aligned buffers) keeps
  *                        the frame's luma plane in shared memory between its min/max pass and its blend pass, so the BGR
  *                        frame is read once; 0: the BGR frame is read (and its luma computed) in both passes, as for larger frames

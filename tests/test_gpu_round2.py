@@ -97,6 +97,23 @@ def test_energy_wide_kernel_equals_one_cta_per_frame_kernel(path_cta, normalize_
         if n <= 23:
             want_e, want_m = oracle.energy_stage(imgs, normalize_first=normalize_first)
             assert np.array_equal(a[1], want_m), n
+    # the pair form (aig_acivw_batch: four pairs per CTA) against stage2_kernel<2>, 101 thresholds
+    for n in (1, 3, 4, 5, 4 * 148 + 3):
+        real = _images_with_hard_cases(max(n, 6), 70 + n)[:n]
+        recon = synth.smooth_images(n, 71 + n)
+        recon[0] = real[0]                                 # identical pair: IoU exactly 1 (or 0 / 0 for a NaN frame)
+        out = []
+        try:
+            for wide in (1, 0):
+                path_cta.set_option('energy_wide', wide)
+                out.append(path_cta.acivw_batch(real, recon, np.linspace(0, 1, 101), normalize_first=normalize_first,
+                                                want_energy=True, want_masks=True))
+        finally:
+            path_cta.set_option('energy_wide', 1)
+        (i1, u1, pos1, num1, e1, m1), (i0, u0, pos0, num0, e0, m0) = out
+        assert np.array_equal(i1, i0) and np.array_equal(u1, u0) and np.array_equal(pos1, pos0) and num1 == num0 == n
+        for x, y in zip(e1 + m1, e0 + m0):
+            assert np.array_equal(x, y, equal_nan=True)
 
 
 def test_energy_large_batch_equals_small_batch_form(path, path_cta):
