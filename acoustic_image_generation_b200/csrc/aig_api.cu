@@ -158,6 +158,7 @@ struct aig_handle {
     bool energy_heat_ws_attr_set[5] = {};
     int energy_wide = 1;                // aig_energy / aig_acivw_batch on large batches: eight frames (four pairs) per 512-thread CTA around one conflict-free exp table (0: stage2_kernel, eight CTAs of 64 (four of 128) threads per SM)
     bool stage2_wide_attr_set[2] = {};
+    int64_t acivw_wide_pairs = 8192;    // aig_acivw_batch takes the wide form from this many pairs up
     int overlay_luma = 1;               // aig_overlay keeps the luma plane of a frame in shared memory between its passes (0: BGR read twice)
     bool overlay_luma_attr_set = false;
     int energy_heat_ws = 1;             // aig_energy_heatmap as the warp-specialised kernel (0: heat_stream_kernel<true>, phases in sequence)
@@ -531,15 +532,15 @@ int launch_stage2(aig_handle* h, cudaStream_t stream, const Stage2Args& args, in
         stage2_cluster_kernel<GROUPS><<<static_cast<unsigned>(clusters * kClusterSize), GROUPS * kClusterGroupThreads, 0, stream>>>(args);
         return scope.done("stage2_cluster_kernel");
     }
-    if (ctas_per_sm >= 8 && h->energy_wide) {
+    // (the pair form only pays from 8192 pairs up: 6.65 against 6.53 M pairs/s there, 5.74 against 6.06 M at 2048 - tools/energy_sizes_probe.py)
+    if (ctas_per_sm >= 8 && h->energy_wide && (GROUPS == 1 || args.n_frames >= h->acivw_wide_pairs)) {
         // eight frames (four pairs) per CTA of 512 threads, one CTA per SM, around one conflict-free exponential table
         if (!h->stage2_wide_attr_set[GROUPS - 1]) {
             AIG_CK(cudaFuncSetAttribute(stage2_wide_kernel<GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(sizeof(WideShared<GROUPS>))));
             h->stage2_wide_attr_set[GROUPS - 1] = true;
         }
-        constexpr int kUnits = kWideGroups / GROUPS;
-        const int64_t ctas = std::min<int64_t>((args.n_frames + kUnits - 1) / kUnits, h->sm_count);
+        const int64_t ctas = std::min<int64_t>(args.n_frames, h->sm_count);
         stage2_wide_kernel<GROUPS><<<static_cast<unsigned>(ctas), kWideGroups * kEnergyThreads, sizeof(WideShared<GROUPS>), stream>>>(args);
         return scope.done("stage2_wide_kernel");
     }
@@ -1014,6 +1015,9 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
         h->heat_bulk_store = value != 0;
     } else if (key == "energy_wide") {
         h->energy_wide = value != 0;
+    } else if (key == "acivw_wide_pairs") {
+        if (value < 0) return h->fail(AIG_ERR_ARGUMENT, "acivw_wide_pairs out of range");
+        h->acivw_wide_pairs = value;
     } else if (key == "overlay_luma") {
         h->overlay_luma = value != 0;
     } else if (key == "energy_heat_ws") {

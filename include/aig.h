@@ -378,6 +378,8 @@ int64_t aig_launch_count(const aig_handle* h);
  *                        frames (four pairs) per CTA of 512 threads around one conflict-free (eight-copy) exponential table,
  *                        one CTA per SM; 0: one CTA of 64 (128) threads per frame (pair), eight (four) per SM, each with a
  *                        one-copy table (the kernel the chained modes overlap with the MFCC kernel)
+ *   "acivw_wide_pairs"   aig_acivw_batch takes that form from this many pairs up (default 8192; below, four 128-thread CTAs per
+ *                        SM balance a partial last round better)
  *   "overlay_luma"       1 (default): aig_overlay with a frame of up to 81 920 pixels (a multiple of four, aligned buffers) keeps
  *                        the frame's luma plane in shared memory between its min/max pass and its blend pass, so the BGR
  *                        frame is read once; 0: the BGR frame is read (and its luma computed) in both passes, as for larger frames

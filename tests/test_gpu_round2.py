@@ -104,12 +104,14 @@ def test_energy_wide_kernel_equals_one_cta_per_frame_kernel(path_cta, normalize_
         recon[0] = real[0]                                 # identical pair: IoU exactly 1 (or 0 / 0 for a NaN frame)
         out = []
         try:
+            path_cta.set_option('acivw_wide_pairs', 0)     # the default takes the pair form from 8192 pairs up only
             for wide in (1, 0):
                 path_cta.set_option('energy_wide', wide)
                 out.append(path_cta.acivw_batch(real, recon, np.linspace(0, 1, 101), normalize_first=normalize_first,
                                                 want_energy=True, want_masks=True))
         finally:
             path_cta.set_option('energy_wide', 1)
+            path_cta.set_option('acivw_wide_pairs', 8192)
         (i1, u1, pos1, num1, e1, m1), (i0, u0, pos0, num0, e0, m0) = out
         assert np.array_equal(i1, i0) and np.array_equal(u1, u0) and np.array_equal(pos1, pos0) and num1 == num0 == n
         for x, y in zip(e1 + m1, e0 + m0):
