@@ -675,23 +675,26 @@ def run_gpu(args):
     np_power, np_out = h_power.numpy(), tuple(t.numpy() for t in h_out)
     for _ in range(2):
         path.mfcc_energy(np_power, flip=True, normalize_first=True, out=np_out)
-    best_e2e, best_bare = None, None
-    for _ in range(args.e2e_rounds):                 # library call and bare copies alternate, all ranks in step; best of each
+    e2e_times, bare_times = [], []
+    for _ in range(args.e2e_rounds):                 # library call and bare copies alternate, all ranks in step; every round counts
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             path.mfcc_energy(np_power, flip=True, normalize_first=True, out=np_out)   # returns after the D2H copies
         torch.cuda.synchronize()
         e2e_s = all_max(torch, dist, world, dev, time.perf_counter() - t0)
-        best_e2e = e2e_s if best_e2e is None else min(best_e2e, e2e_s)
+        e2e_times.append(e2e_s)
         bare_s, up_bytes, down_bytes = bare_link_probe(torch, dev, h_power, power[:e2e_frames], h_out,
                                                        (mfcc[:e2e_frames], energy[:e2e_frames], mask[:e2e_frames]),
                                                        args.e2e_steps, barrier)
         bare_s = all_max(torch, dist, world, dev, bare_s)
-        best_bare = bare_s if best_bare is None else min(best_bare, bare_s)
-    e2e_value = world * e2e_frames * args.e2e_steps / best_e2e
-    link_gbs = world * args.e2e_steps * (up_bytes + down_bytes) / best_e2e / 1e9
-    bare_gbs = world * args.e2e_steps * (up_bytes + down_bytes) / best_bare / 1e9
+        bare_times.append(bare_s)
+    # the reported figure is the aggregate over ALL rounds (total frames / total time), not the best round
+    e2e_calls = args.e2e_steps * len(e2e_times)
+    e2e_value = world * e2e_frames * e2e_calls / sum(e2e_times)
+    link_gbs = world * e2e_calls * (up_bytes + down_bytes) / sum(e2e_times) / 1e9
+    bare_gbs = world * e2e_calls * (up_bytes + down_bytes) / sum(bare_times) / 1e9
+    e2e_round_values = [world * e2e_frames * args.e2e_steps / t for t in e2e_times]
     # the end-to-end result must be the resident result (same frames)
     assert np.array_equal(np_out[2], mask[:e2e_frames].cpu().numpy()), 'e2e mask differs from the resident run'
     # the same call the way the reference makes it: ordinary (pageable) NumPy arrays in, freshly allocated arrays out
@@ -766,7 +769,9 @@ def run_gpu(args):
         'sustained': sustained,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': e2e_frames * IN_BYTES,
                 'd2h_bytes_per_step': e2e_frames * OUT_BYTES,
-                'frames_per_step': e2e_frames, 'steps': args.e2e_steps, 'rounds_best_of': args.e2e_rounds,
+                'frames_per_step': e2e_frames, 'steps': e2e_calls, 'rounds': len(e2e_times),
+                'statistic': 'all rounds: frames of every timed call / their summed time (max over ranks per round)',
+                'round_values': e2e_round_values,
                 'api': 'AcousticPath.mfcc_energy(pinned numpy) -> aig_mfcc_energy, synchronous',
                 'link_gbs': link_gbs, 'bare_link_gbs': bare_gbs, 'frac_of_bare_link': link_gbs / bare_gbs,
                 'bare_link_probe': 'the same bytes as bare pinned cudaMemcpyAsync (64 MiB H2D pieces, result-sized D2H on a second '
@@ -922,7 +927,7 @@ def main():
                     help='resident frames per step per GPU')
     ap.add_argument('--e2e-frames', type=int, default=256, help='frames per end-to-end step (pinned host batch)')
     ap.add_argument('--e2e-steps', type=int, default=5)
-    ap.add_argument('--e2e-rounds', type=int, default=3, help='library call / bare-copy probe alternations (best of each)')
+    ap.add_argument('--e2e-rounds', type=int, default=3, help='library call / bare-copy probe alternations (all of them counted)')
     ap.add_argument('--sustain-seconds', type=float, default=3.2, help='length of the sustained loop (0 = skip)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='CPU baseline time budget')
     ap.add_argument('--no-cpu-baseline', action='store_true')
