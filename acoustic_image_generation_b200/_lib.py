@@ -20,8 +20,8 @@ INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
 NVCC_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-pthread', '-shared', '-ldl', '-lz', '-lpthread']
-SOURCES = ['aig_api.cu', 'record_reader.cpp']
-DEPENDS = ['aig_api.cu', 'record_reader.cpp', 'aig_common.cuh', 'mfcc_kernel.cuh', 'energy_kernel.cuh', 'heatmap_kernel.cuh', 'score_kernel.cuh', 'mask_packed_kernel.cuh', 'fused_kernel.cuh', 'frontend_kernel.cuh',
+SOURCES = ['aig_api.cu', 'record_reader.cpp', 'host_copy.cpp']
+DEPENDS = ['aig_api.cu', 'record_reader.cpp', 'host_copy.cpp', 'aig_common.cuh', 'mfcc_kernel.cuh', 'energy_kernel.cuh', 'heatmap_kernel.cuh', 'score_kernel.cuh', 'mask_packed_kernel.cuh', 'fused_kernel.cuh', 'frontend_kernel.cuh',
            'host_staging.h',
            'mel_program_ref.inc', 'mel_tables_ref.inc', os.path.join(INCLUDE, 'aig.h')]
 

@@ -996,6 +996,9 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
         if (value < -1 || value > 64) return h->fail(AIG_ERR_ARGUMENT, "host_copy_threads out of range (-1 auto, 0 off, 1..64)");
         if (static_cast<int>(value) != h->host_copy_threads) h->uploader.shutdown();
         h->host_copy_threads = static_cast<int>(value);
+    } else if (key == "host_copy_streaming") {
+        if (value < -1 || value > 1) return h->fail(AIG_ERR_ARGUMENT, "host_copy_streaming must be -1 (by job size), 0 or 1");
+        h->uploader.set_streaming_fill(static_cast<int>(value));   // staging-slot fills with non-temporal stores (host_copy.cpp)
     } else if (key == "chain_energy_ctas_per_sm") {
         if (value < 1 || value > 16) return h->fail(AIG_ERR_ARGUMENT, "chain_energy_ctas_per_sm out of range");
         h->chain_energy_ctas_per_sm = static_cast<int>(value);

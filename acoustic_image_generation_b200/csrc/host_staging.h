@@ -24,6 +24,10 @@
 #include <thread>
 #include <vector>
 
+// host_copy.cpp: slot fills with non-temporal stores (no read-for-ownership of the pinned slot)
+extern "C" void aig_host_copy_streaming(void* dst, const void* src, size_t bytes);
+extern "C" int aig_host_copy_streaming_supported();
+
 namespace aig {
 
 class StagedUploader {   // both directions; named after its first job
@@ -94,6 +98,15 @@ class StagedUploader {   // both directions; named after its first job
     }
 
     bool ready() const { return ready_; }
+    // Upload fills: streaming stores or std::memcpy.  Set between jobs only.  mode 0: memcpy; 1: streaming stores
+    // (where the CPU has AVX2); -1 (default): streaming stores for jobs up to kStreamingAutoBytes.  Measured on a B200
+    // box (tools/c1_breakdown_probe.py, profiles/r02_c1_breakdown_streaming.txt, six threads): a 57 MB job whose source
+    // is still in the host's caches 1.56 ms against 1.94 ms with memcpy (the slots stop evicting the source), the same
+    // job from a cold source 1.95 against 2.17 ms, but a 906 MB job 22.6 against 21.1 ms - there the 32 MB ring stays
+    // cache-resident under ordinary stores and the copy engine reads it from the cache, which streaming stores undo.
+    static constexpr size_t kStreamingAutoBytes = size_t(128) << 20;
+    void set_streaming_fill(int mode) { streaming_mode_ = aig_host_copy_streaming_supported() != 0 ? mode : 0; }
+    int streaming_fill() const { return streaming_mode_; }
     int threads() const { return static_cast<int>(workers_.size()); }
 
     // Copies bytes from pageable `src` to device `dst`, ordered on `stream`.  Returns once every piece has been read
@@ -109,6 +122,7 @@ class StagedUploader {   // both directions; named after its first job
             user_dst_ = nullptr;
             bytes_ = bytes;
             piece_ = piece;
+            streaming_job_ = streaming_mode_ > 0 || (streaming_mode_ < 0 && bytes <= kStreamingAutoBytes);
             worker_seen_.store(false, std::memory_order_relaxed);
             pieces_ = pieces;
             next_.store(0, std::memory_order_relaxed);
@@ -166,7 +180,7 @@ class StagedUploader {   // both directions; named after its first job
             if (mine >= 0 && mine < freed_.load(std::memory_order_relaxed)) {
                 const size_t off = static_cast<size_t>(mine) * piece;
                 const int ms = static_cast<int>(mine % kSlots);
-                std::memcpy(ring_ + ms * kSlotBytes, static_cast<const char*>(src) + off, std::min(piece, bytes - off));
+                fill_slot(ring_ + ms * kSlotBytes, static_cast<const char*>(src) + off, std::min(piece, bytes - off));
                 filled_[ms].store(mine, std::memory_order_release);
                 mine = -1;
                 progressed = true;
@@ -259,6 +273,11 @@ class StagedUploader {   // both directions; named after its first job
     }
 
    private:
+    void fill_slot(char* slot, const char* src, size_t len) const {
+        if (streaming_job_) aig_host_copy_streaming(slot, src, len);
+        else std::memcpy(slot, src, len);
+    }
+
     void worker() {
         uint64_t seen = 0;
         for (;;) {
@@ -285,7 +304,7 @@ class StagedUploader {   // both directions; named after its first job
                 const size_t off = static_cast<size_t>(i) * piece_;
                 const size_t len = std::min(piece_, bytes_ - off);
                 const int s = static_cast<int>(i % kSlots);
-                if (user_dst_ == nullptr) std::memcpy(ring_ + s * kSlotBytes, src_ + off, len);     // upload: fill the slot
+                if (user_dst_ == nullptr) fill_slot(ring_ + s * kSlotBytes, src_ + off, len);       // upload: fill the slot
                 else std::memcpy(user_dst_ + off, ring_ + s * kSlotBytes, len);                    // download: drain it
                 filled_[s].store(i, std::memory_order_release);
             }
@@ -298,6 +317,8 @@ class StagedUploader {   // both directions; named after its first job
     }
 
     bool ready_ = false;
+    int streaming_mode_ = aig_host_copy_streaming_supported() != 0 ? -1 : 0;
+    bool streaming_job_ = false;             // the current upload job's choice (written before the workers are woken)
     char* ring_ = nullptr;
     cudaEvent_t slot_done_[kSlots] = {};
     bool slot_busy_[kSlots] = {};

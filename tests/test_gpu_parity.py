@@ -683,6 +683,27 @@ def test_pageable_inputs_match_device_inputs(path, torch, threads):
         path.set_option('host_copy_threads', -1)
 
 
+@pytest.mark.parametrize('streaming', [0, 1])
+def test_staging_fill_forms_agree(path, torch, streaming):
+    """The pinned slots filled by memcpy or by non-temporal stores (host_copy.cpp): same bits as a device-resident pass,
+    for sources at every 4-byte alignment within a 32-byte vector and ragged sizes; bad option values are refused."""
+    rows = synth.power_frames(12, 21, 'chi2').reshape(-1, 512)                  # 42 MB
+    full = path.mfcc_rows(torch.from_numpy(rows).cuda()).cpu().numpy()
+    raw = np.empty(rows.nbytes + 64, np.uint8)
+    path.set_option('host_copy_streaming', streaming)
+    try:
+        for shift in (0, 4, 12, 28):
+            base = (-raw.ctypes.data) % 32 + shift                              # source address = shift (mod 32)
+            view = raw[base:base + rows.nbytes].view(np.float32).reshape(rows.shape)
+            view[...] = rows
+            for r in (rows.shape[0], rows.shape[0] - 1, 4099):
+                assert np.array_equal(path.mfcc_rows(view[:r]), full[:r], equal_nan=True), (shift, r)
+        with pytest.raises(Exception):
+            path.set_option('host_copy_streaming', 2)
+    finally:
+        path.set_option('host_copy_streaming', -1)
+
+
 def test_staging_ring_soak_over_random_sizes(path, torch):
     """Thirty uploads of random sizes back to back (8 - 250 MB, ragged last pieces, ring slots of one call still in
     flight when the next starts), results compared with one device-resident pass over the same rows."""
