@@ -115,6 +115,7 @@ constexpr int kNcclSum = 0;     // ncclSum
 
 }  // namespace
 
+constexpr size_t kStagedUploadMinBytes = size_t(1) << 20;      // default of option staged_min_bytes (8 MiB until the last session)
 struct aig_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -179,6 +180,7 @@ struct aig_handle {
     double2* d_twiddle = nullptr;       // exp(-2*pi*i*k/1024), k < 512 (aig_power_spectrum)
     // pageable host inputs are staged through a pinned ring by a few copy threads (host_staging.h)
     aig::StagedUploader uploader;
+    size_t staged_min_bytes = kStagedUploadMinBytes;   // pageable copies from this size on go through the staging ring
     int host_copy_threads = -1;         // -1: min(6, hardware threads / 2); 0: leave pageable copies to the driver
     // NCCL communicator (resolved with dlopen; see aig_comm_init)
     void* comm = nullptr;
@@ -277,7 +279,6 @@ void* scratch(aig_handle* h, size_t bytes) {
 
 // Host -> device copy of `bytes` on `stream`.  Large pageable sources go through the handle's StagedUploader (4-5x the
 // driver's own pageable path); pinned sources and small copies are plain cudaMemcpyAsync.
-constexpr size_t kStagedUploadMinBytes = size_t(8) << 20;
 bool use_host_staging(aig_handle* h, size_t bytes, MemKind kind);
 cudaError_t upload_async(aig_handle* h, void* dst, const void* src, size_t bytes, MemKind kind, cudaStream_t stream) {
     if (use_host_staging(h, bytes, kind)) return h->uploader.upload(dst, src, bytes, stream);
@@ -287,7 +288,7 @@ cudaError_t upload_async(aig_handle* h, void* dst, const void* src, size_t bytes
 // Device -> host copy after the work enqueued on `stream`; large pageable destinations are drained through the same
 // pinned ring (returns with the data in place), everything else is a plain asynchronous copy.
 bool use_host_staging(aig_handle* h, size_t bytes, MemKind kind) {
-    if (kind != kHostPageable || bytes < kStagedUploadMinBytes || h->host_copy_threads == 0) return false;
+    if (kind != kHostPageable || bytes < h->staged_min_bytes || h->host_copy_threads == 0) return false;
     int threads = h->host_copy_threads;
     if (threads < 0) threads = static_cast<int>(std::min(6u, std::max(1u, std::thread::hardware_concurrency() / 2)));   // 4-6 fill the link
     return h->uploader.start(threads);
@@ -996,6 +997,12 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
         if (value < -1 || value > 64) return h->fail(AIG_ERR_ARGUMENT, "host_copy_threads out of range (-1 auto, 0 off, 1..64)");
         if (static_cast<int>(value) != h->host_copy_threads) h->uploader.shutdown();
         h->host_copy_threads = static_cast<int>(value);
+    } else if (key == "staged_min_bytes") {
+        if (value < (64 << 10) || value > (int64_t(1) << 40)) return h->fail(AIG_ERR_ARGUMENT, "staged_min_bytes out of range (from 65536)");
+        h->staged_min_bytes = static_cast<size_t>(value);
+    } else if (key == "staged_small_piece_bytes") {
+        if (value < (64 << 10) || value > (4 << 20)) return h->fail(AIG_ERR_ARGUMENT, "staged_small_piece_bytes out of range (64 KiB .. 4 MiB)");
+        h->uploader.set_small_piece(static_cast<size_t>(value));
     } else if (key == "host_copy_streaming") {
         if (value < -1 || value > 1) return h->fail(AIG_ERR_ARGUMENT, "host_copy_streaming must be -1 (by job size), 0 or 1");
         h->uploader.set_streaming_fill(static_cast<int>(value));   // staging-slot fills with non-temporal stores (host_copy.cpp)

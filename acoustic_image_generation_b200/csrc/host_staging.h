@@ -36,7 +36,12 @@ class StagedUploader {   // both directions; named after its first job
     static constexpr int kSlots = 8;
     // A copy engine needs 4 MiB transfers to reach the link rate (1 MiB: 45 GB/s, 4 MiB: 52.5, 16 MiB: 54.7 on this box,
     // tools/h2d_streams_probe.py); small jobs use 1 MiB pieces so that the first transfer starts sooner.
-    static size_t piece_bytes(size_t bytes) { return bytes >= (size_t(32) << 20) ? kSlotBytes : (size_t(1) << 20); }
+    // Jobs under 4 MiB (a batch of 16 acoustic images is 1.3 MB) are cut finer still (small_piece_, default 512 KiB;
+    // tools/small_upload_probe.py, profiles/r02_small_upload_probe.txt: 128 KiB pieces cost 20 % on such a batch).
+    size_t piece_bytes(size_t bytes) const {
+        return bytes >= (size_t(32) << 20) ? kSlotBytes : bytes >= (size_t(4) << 20) ? (size_t(1) << 20) : small_piece_;
+    }
+    void set_small_piece(size_t bytes) { small_piece_ = std::min(kSlotBytes, std::max<size_t>(bytes, 64 << 10)); }
     static constexpr int kLingerMicros = 400;
     static void cpu_relax() {
 #if defined(__x86_64__) || defined(__i386__)
@@ -317,6 +322,7 @@ class StagedUploader {   // both directions; named after its first job
     }
 
     bool ready_ = false;
+    size_t small_piece_ = size_t(512) << 10;
     int streaming_mode_ = aig_host_copy_streaming_supported() != 0 ? -1 : 0;
     bool streaming_job_ = false;             // the current upload job's choice (written before the workers are woken)
     char* ring_ = nullptr;

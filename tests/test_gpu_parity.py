@@ -657,7 +657,7 @@ def test_overlay_luma_plane_form_equals_two_read_form(path, torch):
 @pytest.mark.parametrize('threads', [-1, 0, 1, 3])
 def test_pageable_inputs_match_device_inputs(path, torch, threads):
     """Same bits whether the spectra arrive as device tensors, pinned arrays or pageable arrays staged by 0..n copy
-    threads; sizes below, at and above the 8 MiB staging threshold, the 4 MiB slot size and the 64 MiB device chunk."""
+    threads; sizes below, at and above the staging thresholds (8 MiB until the last session, 1 MiB now), the 4 MiB slot size and the 64 MiB device chunk."""
     path.set_option('host_copy_threads', threads)
     try:
         for n in (1, 3, 19, 40):
@@ -702,6 +702,32 @@ def test_staging_fill_forms_agree(path, torch, streaming):
             path.set_option('host_copy_streaming', 2)
     finally:
         path.set_option('host_copy_streaming', -1)
+
+
+@pytest.mark.parametrize('piece', [64 << 10, 512 << 10, 4 << 20])
+def test_small_staged_uploads(path, torch, piece):
+    """Mid-size pageable arrays (the reference's evaluation batches: 16 images = 1.3 MB) through the staging ring in
+    small pieces, around the staged_min_bytes threshold and with ragged last pieces: same bits as device inputs."""
+    path.set_option('staged_small_piece_bytes', piece)
+    try:
+        for min_bytes in (65536, 1 << 20, 8 << 20):
+            path.set_option('staged_min_bytes', min_bytes)
+            for n in (1, 3, 13, 16, 49):
+                real, recon = synth.sigmoid_images(n, 40 + n), synth.sigmoid_images(n, 80 + n)
+                want = path.acivw_batch(torch.from_numpy(real).cuda(), torch.from_numpy(recon).cuda())
+                as_np = lambda x: x.cpu().numpy() if hasattr(x, 'cpu') else np.asarray(x)
+                for _ in range(2):
+                    got = path.acivw_batch(real, recon)
+                    for g, w in zip(got, want):
+                        assert np.array_equal(as_np(g), as_np(w))
+                e_dev, m_dev = path.energy(torch.from_numpy(real).cuda())
+                e, m = path.energy(real)
+                assert np.array_equal(e, e_dev.cpu().numpy()) and np.array_equal(m, m_dev.cpu().numpy())
+        with pytest.raises(Exception):
+            path.set_option('staged_min_bytes', 1000)
+    finally:
+        path.set_option('staged_min_bytes', 1 << 20)
+        path.set_option('staged_small_piece_bytes', 512 << 10)
 
 
 def test_staging_ring_soak_over_random_sizes(path, torch):
