@@ -115,7 +115,8 @@ constexpr int kNcclSum = 0;     // ncclSum
 
 }  // namespace
 
-constexpr size_t kStagedUploadMinBytes = size_t(1) << 20;      // default of option staged_min_bytes (8 MiB until the last session)
+constexpr size_t kStagedUploadMinBytes = size_t(8) << 20;      // default of option staged_min_bytes
+constexpr size_t kStagedDownloadMinBytes = size_t(8) << 20;
 struct aig_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -279,22 +280,23 @@ void* scratch(aig_handle* h, size_t bytes) {
 
 // Host -> device copy of `bytes` on `stream`.  Large pageable sources go through the handle's StagedUploader (4-5x the
 // driver's own pageable path); pinned sources and small copies are plain cudaMemcpyAsync.
-bool use_host_staging(aig_handle* h, size_t bytes, MemKind kind);
+bool use_host_staging(aig_handle* h, size_t bytes, size_t min_bytes, MemKind kind);
 cudaError_t upload_async(aig_handle* h, void* dst, const void* src, size_t bytes, MemKind kind, cudaStream_t stream) {
-    if (use_host_staging(h, bytes, kind)) return h->uploader.upload(dst, src, bytes, stream);
+    if (use_host_staging(h, bytes, h->staged_min_bytes, kind)) return h->uploader.upload(dst, src, bytes, stream);
     return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
 }
 
 // Device -> host copy after the work enqueued on `stream`; large pageable destinations are drained through the same
 // pinned ring (returns with the data in place), everything else is a plain asynchronous copy.
-bool use_host_staging(aig_handle* h, size_t bytes, MemKind kind) {
-    if (kind != kHostPageable || bytes < h->staged_min_bytes || h->host_copy_threads == 0) return false;
+bool use_host_staging(aig_handle* h, size_t bytes, size_t min_bytes, MemKind kind) {
+    if (kind != kHostPageable || bytes < min_bytes || h->host_copy_threads == 0) return false;
     int threads = h->host_copy_threads;
     if (threads < 0) threads = static_cast<int>(std::min(6u, std::max(1u, std::thread::hardware_concurrency() / 2)));   // 4-6 fill the link
     return h->uploader.start(threads);
 }
 cudaError_t download(aig_handle* h, void* dst, const void* src, size_t bytes, MemKind kind, cudaStream_t stream) {
-    if (use_host_staging(h, bytes, kind)) return h->uploader.download(dst, src, bytes, stream);
+    // (results under 8 MiB stay with the driver: draining needs the worker threads, whose wake-up a small result cannot repay)
+    if (use_host_staging(h, bytes, kStagedDownloadMinBytes, kind)) return h->uploader.download(dst, src, bytes, stream);
     return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream);
 }
 
@@ -1000,6 +1002,9 @@ int aig_set_option(aig_handle* h, const char* name, int64_t value) {
     } else if (key == "staged_min_bytes") {
         if (value < (64 << 10) || value > (int64_t(1) << 40)) return h->fail(AIG_ERR_ARGUMENT, "staged_min_bytes out of range (from 65536)");
         h->staged_min_bytes = static_cast<size_t>(value);
+    } else if (key == "staged_solo_bytes") {
+        if (value < 0 || value > (int64_t(1) << 40)) return h->fail(AIG_ERR_ARGUMENT, "staged_solo_bytes out of range");
+        h->uploader.set_solo_bytes(static_cast<size_t>(value));
     } else if (key == "staged_small_piece_bytes") {
         if (value < (64 << 10) || value > (4 << 20)) return h->fail(AIG_ERR_ARGUMENT, "staged_small_piece_bytes out of range (64 KiB .. 4 MiB)");
         h->uploader.set_small_piece(static_cast<size_t>(value));

@@ -36,11 +36,12 @@ class StagedUploader {   // both directions; named after its first job
     static constexpr int kSlots = 8;
     // A copy engine needs 4 MiB transfers to reach the link rate (1 MiB: 45 GB/s, 4 MiB: 52.5, 16 MiB: 54.7 on this box,
     // tools/h2d_streams_probe.py); small jobs use 1 MiB pieces so that the first transfer starts sooner.
-    // Jobs under 4 MiB (a batch of 16 acoustic images is 1.3 MB) are cut finer still (small_piece_, default 512 KiB;
-    // tools/small_upload_probe.py, profiles/r02_small_upload_probe.txt: 128 KiB pieces cost 20 % on such a batch).
+    // Jobs under 4 MiB (reached only when option staged_min_bytes is lowered: a batch of 16 acoustic images is 1.3 MB)
+    // are cut finer still (small_piece_, default 512 KiB; tools/small_upload_probe.py: 128 KiB pieces cost 20 %).
     size_t piece_bytes(size_t bytes) const {
         return bytes >= (size_t(32) << 20) ? kSlotBytes : bytes >= (size_t(4) << 20) ? (size_t(1) << 20) : small_piece_;
     }
+    void set_solo_bytes(size_t bytes) { solo_bytes_ = bytes; }
     void set_small_piece(size_t bytes) { small_piece_ = std::min(kSlotBytes, std::max<size_t>(bytes, 64 << 10)); }
     static constexpr int kLingerMicros = 400;
     static void cpu_relax() {
@@ -120,6 +121,7 @@ class StagedUploader {   // both directions; named after its first job
         if (bytes == 0) return cudaSuccess;
         const size_t piece = piece_bytes(bytes);
         const int64_t pieces = static_cast<int64_t>((bytes + piece - 1) / piece);
+        bool solo = false;
         {
             std::unique_lock<std::mutex> lock(m_);
             cv_idle_.wait(lock, [this] { return active_ == 0; });     // a late waker of the previous job has left it
@@ -133,10 +135,15 @@ class StagedUploader {   // both directions; named after its first job
             next_.store(0, std::memory_order_relaxed);
             freed_.store(0, std::memory_order_relaxed);
             for (int s = 0; s < kSlots; ++s) filled_[s].store(-1, std::memory_order_relaxed);
-            ++generation_;
-            generation_hint_.store(generation_, std::memory_order_release);
+            // Jobs under solo_bytes_ (option staged_solo_bytes, default 0 = none) are copied by the calling thread alone, piece
+            // by piece, each piece's H2D copy overlapping the next fill, without waking the workers.
+            solo = bytes < solo_bytes_;
+            if (!solo) {
+                ++generation_;
+                generation_hint_.store(generation_, std::memory_order_release);
+            }
         }
-        cv_.notify_all();
+        if (!solo) cv_.notify_all();
         // slots of an earlier upload may still be in flight on the DMA engine: their events gate the first reuse
         cudaError_t status = cudaSuccess;
         int64_t issued = 0, freed = 0;
@@ -323,6 +330,7 @@ class StagedUploader {   // both directions; named after its first job
 
     bool ready_ = false;
     size_t small_piece_ = size_t(512) << 10;
+    size_t solo_bytes_ = 0;                  // uploads under this size do not wake the workers
     int streaming_mode_ = aig_host_copy_streaming_supported() != 0 ? -1 : 0;
     bool streaming_job_ = false;             // the current upload job's choice (written before the workers are woken)
     char* ring_ = nullptr;

@@ -365,12 +365,16 @@ int64_t aig_launch_count(const aig_handle* h);
  *   "keep_mfcc_in_l2"    fused kernel: 1 (default) L2 evict-last hint on the MFCC stores, so the energy warps'
  *                        read-back one frame later still hits L2; 0: plain stores
  *   "l2_evict_first"     1: L2 evict-first cache hint on the TMA spectrum loads; 0 (default): normal policy
- *   "host_copy_threads"  copies of staged_min_bytes and more from / to ordinary (pageable) host arrays are staged through
+ *   "host_copy_threads"  copies of 8 MiB (uploads: staged_min_bytes) and more from / to ordinary (pageable) host arrays are staged through
  *                        a ring of pinned 4 MiB slots by this many host threads (host_staging.h; 4-5x the driver's own
  *                        pageable path): -1 (default) min(6, hardware threads / 2); 0 leaves them to cudaMemcpyAsync
- *   "staged_min_bytes"   the size from which pageable copies take that ring (default 1 MiB: the reference's evaluation
- *                        step from NumPy arrays, two arrays of 1.3 MB for a batch of 16, 274 -> 188 us; from 65536)
- *   "staged_small_piece_bytes"  piece size of staged copies under 4 MiB (default 512 KiB; 64 KiB .. 4 MiB)
+ *   "staged_min_bytes"   the size from which pageable uploads take that ring (default 8 MiB, from 65536).  Lowering it
+ *                        to 1 MiB makes the reference's evaluation step from NumPy arrays (two arrays of 1.3 MB for a
+ *                        batch of 16) 188 us instead of 274 us in the median, but bursts of 5-8 ms calls were measured
+ *                        when the copy threads had been asleep (tools/add_batch_outlier_probe.py), so it is not the default
+ *   "staged_small_piece_bytes"  piece size of staged uploads under 4 MiB (default 512 KiB; 64 KiB .. 4 MiB)
+ *   "staged_solo_bytes"  uploads under this size are staged by the calling thread alone, the copy threads stay asleep
+ *                        (default 0: none; measured equal to the driver's own pageable path, 266 vs 259 us)
  *   "host_copy_streaming" how the staging threads fill the pinned slots: 1 non-temporal stores (host_copy.cpp; needs AVX2:
  *                        a slot only the copy engine will read no longer evicts the caller's array from the host caches),
  *                        0 memcpy, -1 (default) non-temporal stores for uploads up to 128 MiB (measured: 20 % faster

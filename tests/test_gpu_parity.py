@@ -657,7 +657,7 @@ def test_overlay_luma_plane_form_equals_two_read_form(path, torch):
 @pytest.mark.parametrize('threads', [-1, 0, 1, 3])
 def test_pageable_inputs_match_device_inputs(path, torch, threads):
     """Same bits whether the spectra arrive as device tensors, pinned arrays or pageable arrays staged by 0..n copy
-    threads; sizes below, at and above the staging thresholds (8 MiB until the last session, 1 MiB now), the 4 MiB slot size and the 64 MiB device chunk."""
+    threads; sizes below, at and above the 8 MiB staging threshold, the 4 MiB slot size and the 64 MiB device chunk."""
     path.set_option('host_copy_threads', threads)
     try:
         for n in (1, 3, 19, 40):
@@ -707,11 +707,13 @@ def test_staging_fill_forms_agree(path, torch, streaming):
 @pytest.mark.parametrize('piece', [64 << 10, 512 << 10, 4 << 20])
 def test_small_staged_uploads(path, torch, piece):
     """Mid-size pageable arrays (the reference's evaluation batches: 16 images = 1.3 MB) through the staging ring in
-    small pieces, around the staged_min_bytes threshold and with ragged last pieces: same bits as device inputs."""
+    small pieces (options staged_min_bytes / staged_solo_bytes: by the copy threads or by the calling thread alone), around
+    the threshold and with ragged last pieces: same bits as device inputs."""
     path.set_option('staged_small_piece_bytes', piece)
     try:
-        for min_bytes in (65536, 1 << 20, 8 << 20):
+        for min_bytes, solo in ((65536, 0), (1 << 20, 0), (1 << 20, 4 << 20), (8 << 20, 0)):
             path.set_option('staged_min_bytes', min_bytes)
+            path.set_option('staged_solo_bytes', solo)
             for n in (1, 3, 13, 16, 49):
                 real, recon = synth.sigmoid_images(n, 40 + n), synth.sigmoid_images(n, 80 + n)
                 want = path.acivw_batch(torch.from_numpy(real).cuda(), torch.from_numpy(recon).cuda())
@@ -726,7 +728,8 @@ def test_small_staged_uploads(path, torch, piece):
         with pytest.raises(Exception):
             path.set_option('staged_min_bytes', 1000)
     finally:
-        path.set_option('staged_min_bytes', 1 << 20)
+        path.set_option('staged_min_bytes', 8 << 20)
+        path.set_option('staged_solo_bytes', 0)
         path.set_option('staged_small_piece_bytes', 512 << 10)
 
 

@@ -37,3 +37,23 @@ for min_bytes, piece in ((8 << 20, 256 << 10), (256 << 10, 128 << 10), (256 << 1
             out.append('B=%d: %.0f us (min %.0f)' % ((b,) + lat(lambda: ev.add_batch(real, recon))))
         e = lat(lambda: p.energy(cases[64][0]), 100)
         print('staged_min_bytes %8d piece %7d streaming %2d | add_batch %s | energy(64 frames, 5.3 MB) %.0f us' % (min_bytes, piece, streaming, ' | '.join(out), e[0]))
+
+# ---- the same step while the host's cores are busy: NumPy's BLAS threads keep spinning for a while after a product (what
+# bench.py's config_c1 does just before timing add_batch), and a reference process has TensorFlow's threads besides
+print('--- busy host: a 16-thread BLAS product right before every timing loop ---')
+p.set_option('staged_min_bytes', 1 << 20)
+p.set_option('staged_small_piece_bytes', 512 << 10)
+p.set_option('host_copy_streaming', -1)
+m = np.random.default_rng(0).random((3000, 3000))
+for solo_bytes, min_bytes in ((0, 1 << 20), (4 << 20, 1 << 20), (4 << 20, 8 << 20)):
+    p.set_option('staged_solo_bytes', solo_bytes)
+    p.set_option('staged_min_bytes', min_bytes)
+    out = []
+    for b, (real, recon) in cases.items():
+        quiet = lat(lambda: ev.add_batch(real, recon))
+        m @ m
+        busy = lat(lambda: ev.add_batch(real, recon), 50)
+        out.append('B=%d: quiet %.0f us, after BLAS %.0f us' % (b, quiet[0], busy[0]))
+    m @ m
+    e = lat(lambda: p.energy(cases[64][0]), 50)
+    print('staged_solo_bytes %8d staged_min_bytes %8d | add_batch %s | energy(64 frames) after BLAS %.0f us' % (solo_bytes, min_bytes, ' | '.join(out), e[0]))
