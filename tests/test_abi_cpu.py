@@ -156,3 +156,21 @@ def test_only_tests_smoke_and_bench_touch_the_oracle():
                 if name.endswith('.py') and pattern.search(open(os.path.join(base, name)).read()):
                     offenders.append(os.path.relpath(os.path.join(base, name), root))
     assert not offenders, offenders
+
+
+def test_streaming_slot_fill_copies_exactly(lib):
+    """host_copy.cpp (the non-temporal fill of the pinned staging slots) is plain host code: every source / destination
+    alignment, sizes from 0 to 2 MiB, nothing written outside the destination range."""
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    raw.aig_host_copy_streaming.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    raw.aig_host_copy_streaming.restype = None
+    assert raw.aig_host_copy_streaming_supported() in (0, 1)
+    rng = np.random.default_rng(7)
+    src = rng.integers(0, 256, size=(2 << 20) + 256, dtype=np.uint8)
+    sizes = [0, 1, 31, 32, 4095, 4096, 4097, 4096 + 127, 4096 + 128, 65536 + 33] + [int(v) for v in rng.integers(0, 2 << 20, 40)]
+    for k, n in enumerate(sizes):
+        so, do = (k * 7) % 64, (k * 13) % 64
+        dst = np.full(n + do + 96, 0xA5, np.uint8)
+        raw.aig_host_copy_streaming(dst.ctypes.data + do, src.ctypes.data + so, n)
+        assert np.array_equal(dst[do:do + n], src[so:so + n]), (n, so, do)
+        assert (dst[:do] == 0xA5).all() and (dst[do + n:] == 0xA5).all(), (n, so, do)
